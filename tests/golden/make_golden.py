@@ -1,0 +1,466 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference modules.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or golden vectors, so parity is pinned on outputs
+of its own code: mcts.MCTS / mcts.Node / mcts.MinMaxStats, config.Config (select_action and the
+transforms), game.Game.store_search_statistics, replay_buffer.PrioritizedReplay
+(save_history / sample_batch / insert_target / update, with a 3-line stub for the `ray` decorator)
+and networks.FCNetwork.  The only things replaced are the random sources (np.random.dirichlet,
+np.random.choice, random.uniform, np.random.randint), which are fed from recorded buffers so that
+the oracle and the CUDA engine can consume identical numbers, and the network, which is the
+batch-invariant HashNetwork for the search fixtures.
+"""
+import math
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("MZ_REFERENCE", "/root/reference")
+sys.path.insert(0, REPO)
+sys.path.insert(0, REF)
+
+ray_stub = types.ModuleType("ray")
+ray_stub.remote = lambda cls: cls
+sys.modules.setdefault("ray", ray_stub)
+
+import mcts as ref_mcts  # noqa: E402  (reference)
+import config as ref_config  # noqa: E402
+import game as ref_game  # noqa: E402
+import replay_buffer as ref_replay  # noqa: E402
+import networks as ref_networks  # noqa: E402
+
+from model_based_rl_b200.testing import HashNetwork  # noqa: E402
+
+BASE_CFG = dict(
+    value_support=[-15, 15], reward_support=[-15, 15], no_support=False, no_target_transform=False,
+    num_simulations=30, discount=0.997, pb_c_base=19652, pb_c_init=1.25, init_value_score=0.0,
+    action_space=4, two_players=False, known_bounds=[None, None], root_dirichlet_alpha=0.25,
+    root_exploration_fraction=0.25, episode_life=False, clip_rewards=False, sticky_actions=1,
+    batch_size=32, beta_increment_per_sampling=0.001, epsilon=0.01, alpha=1.0, beta=1.0,
+    stored_before_train=0, num_unroll_steps=5, td_steps=10, obs_space=(8,), window_size=4096,
+    window_step=None, seed=None)
+
+
+def make_config(**kw):
+  d = dict(BASE_CFG)
+  d.update(kw)
+  return ref_config.Config(d)
+
+
+# --------------------------------------------------------------------------------------------
+# search
+# --------------------------------------------------------------------------------------------
+def run_reference_search(cfg, net, root_state, legal, noise, to_play):
+  """Restates the move body of Actor.play_game (actors.py:131-147) around the reference classes."""
+  G = len(root_state)
+  S, A = cfg.num_simulations, cfg.action_space
+  engine = ref_mcts.MCTS(cfg)
+  out = dict(
+      visits=np.zeros((G, A), np.int32), root_value=np.zeros(G), root_vsum=np.zeros(G),
+      minmax=np.zeros((G, 2)), trace_parent=np.zeros((G, S), np.int32),
+      trace_action=np.zeros((G, S), np.int32), trace_depth=np.zeros((G, S), np.int32),
+      edge_prior=np.zeros((G, S + 1, A)), edge_vsum=np.zeros((G, S + 1, A)),
+      edge_visit=np.zeros((G, S + 1, A), np.int32), edge_reward=np.zeros((G, S + 1, A)),
+      edge_child=np.full((G, S + 1, A), -2, np.int32), root_logits=np.zeros((G, A), np.float32),
+      root_net_value=np.zeros(G, np.float32))
+  real_dirichlet = np.random.dirichlet
+  for g in range(G):
+    root = ref_mcts.Node(0)
+    state = torch.tensor([[int(root_state[g])]], dtype=torch.int64)
+    init = net.initial_inference(state)
+    out["root_logits"][g] = init.policy_logits[0].numpy()
+    out["root_net_value"][g] = init.value.item()
+    legal_actions = [a for a in range(A) if (int(legal[g]) >> a) & 1]
+    root.expand(init, int(to_play[g]), legal_actions)
+    if noise is not None:
+      np.random.dirichlet = lambda alpha, g=g: noise[g, :len(alpha)].copy()
+      root.add_exploration_noise(cfg.root_dirichlet_alpha, cfg.root_exploration_fraction)
+      np.random.dirichlet = real_dirichlet
+    paths = engine.run(root, net)
+
+    ids = {id(root): 0}
+    nodes = [root]
+    for s, path in enumerate(paths):
+      leaf = path[-1]
+      assert id(leaf) not in ids
+      ids[id(leaf)] = s + 1
+      nodes.append(leaf)
+      parent = path[-2]
+      act = [a for a, c in parent.children.items() if c is leaf][0]
+      out["trace_parent"][g, s] = ids[id(parent)]
+      out["trace_action"][g, s] = act
+      out["trace_depth"][g, s] = len(path) - 1
+    for n, node in enumerate(nodes):
+      for a, child in node.children.items():
+        out["edge_prior"][g, n, a] = child.prior
+        out["edge_vsum"][g, n, a] = child.value_sum
+        out["edge_visit"][g, n, a] = child.visit_count
+        out["edge_reward"][g, n, a] = child.reward
+        out["edge_child"][g, n, a] = ids.get(id(child), -1)
+    for a, child in root.children.items():
+      out["visits"][g, a] = child.visit_count
+    out["root_value"][g] = root.value()
+    out["root_vsum"][g] = root.value_sum
+    out["minmax"][g] = (engine.min_max_stats.minimum, engine.min_max_stats.maximum)
+  return out
+
+
+SEARCH_CASES = {
+    # name: (config overrides, G, hashnet kwargs, use_noise, legal subsets, random to_play)
+    "ttt": (dict(action_space=9, num_simulations=30, two_players=True, discount=1.0,
+                 known_bounds=[-1.0, 1.0], td_steps=10),
+            12, dict(value_scale=1.0, reward_scale=1.0, logit_scale=2.0, reward_density=2), True,
+            True, True),
+    "lunar": (dict(action_space=4, num_simulations=30, discount=0.997, td_steps=1000),
+              12, dict(value_scale=4.0, reward_scale=2.0, logit_scale=1.5, reward_density=6), True,
+              False, False),
+    "breakout": (dict(action_space=4, num_simulations=50, discount=0.997),
+                 8, dict(value_scale=2.0, reward_scale=1.0, logit_scale=3.0, reward_density=1), True,
+                 False, False),
+    "atari18": (dict(action_space=18, num_simulations=50, discount=0.997),
+                8, dict(value_scale=1.0, reward_scale=0.5, logit_scale=2.0, reward_density=3), True,
+                False, False),
+    "atari18_nonoise_bounds": (dict(action_space=18, num_simulations=50, discount=0.95,
+                                    known_bounds=[-2.0, 2.0], init_value_score=0.5),
+                               4, dict(value_scale=1.0, reward_scale=0.5, logit_scale=0.25,
+                                       reward_density=8), False, False, False),
+    "flat_ties": (dict(action_space=6, num_simulations=20, discount=1.0),
+                  4, dict(value_scale=0.0, reward_scale=0.0, logit_scale=0.0, reward_density=0),
+                  False, False, False),
+}
+
+
+def gen_search(rng):
+  for name, (over, G, hk, use_noise, subsets, rand_tp) in SEARCH_CASES.items():
+    cfg = make_config(**over)
+    A = cfg.action_space
+    net = HashNetwork(A, **hk)
+    root_state = rng.integers(0, 2**63 - 1, size=G, dtype=np.int64)
+    if subsets:
+      legal = rng.integers(1, 2**A, size=G, dtype=np.int64).astype(np.uint32)
+      legal[0] = (1 << A) - 1
+      legal[1] = 1 << (A - 1)  # a single legal move
+    else:
+      legal = np.full(G, (1 << A) - 1, np.uint32)
+    noise = None
+    if use_noise:
+      noise = np.zeros((G, A))
+      for g in range(G):
+        n = bin(int(legal[g])).count("1")
+        noise[g, :n] = rng.dirichlet([cfg.root_dirichlet_alpha] * n)
+    to_play = rng.choice([-1, 1], size=G).astype(np.int8) if rand_tp else np.ones(G, np.int8)
+    out = run_reference_search(cfg, net, root_state, legal, noise, to_play)
+    np.savez_compressed(
+        os.path.join(HERE, "search_%s.npz" % name), root_state=root_state, legal=legal,
+        noise=noise if noise is not None else np.zeros((0, A)), use_noise=np.int32(use_noise),
+        to_play=to_play, num_simulations=np.int32(cfg.num_simulations), action_space=np.int32(A),
+        two_players=np.int32(cfg.two_players), discount=np.float64(cfg.discount),
+        pb_c_base=np.float64(cfg.pb_c_base), pb_c_init=np.float64(cfg.pb_c_init),
+        init_value_score=np.float64(cfg.init_value_score),
+        known_bounds=np.array([np.nan if b is None else b for b in cfg.known_bounds]),
+        noise_frac=np.float64(cfg.root_exploration_fraction),
+        hashnet=np.array([hk["value_scale"], hk["reward_scale"], hk["logit_scale"],
+                          hk["reward_density"]], np.float64),
+        py_sum_mode=np.int32(1 if sys.version_info >= (3, 12) else 0), **out)
+    print("search", name, "mean depth %.2f" % out["trace_depth"].mean(),
+          "max depth", out["trace_depth"].max())
+
+
+# --------------------------------------------------------------------------------------------
+# select_action / store_search_statistics
+# --------------------------------------------------------------------------------------------
+class _U(object):
+  """np.random.choice stand-in driven by one host-supplied uniform (legacy RandomState.choice
+  draws exactly one random_sample() and searchsorts the normalised cdf, side='right')."""
+
+  def __init__(self):
+    self.u = None
+
+  def __call__(self, a, p=None):
+    if p is not None:
+      cdf = np.asarray(p, dtype=np.float64).cumsum()
+      cdf /= cdf[-1]
+      return int(cdf.searchsorted(self.u, side='right'))
+    arr = np.arange(a) if np.isscalar(a) else np.asarray(a)
+    return arr[int(math.floor(self.u * len(arr)))]
+
+
+def gen_select_action(rng):
+  # first: the stand-in reproduces numpy's own draw for the same underlying uniform
+  for seed in range(200):
+    n = int(rng.integers(1, 19))
+    p = rng.random(n) + 1e-3
+    p /= p.sum()
+    np.random.seed(seed)
+    u = np.random.random_sample()
+    np.random.seed(seed)
+    want = np.random.choice(n, p=p)
+    fake = _U()
+    fake.u = u
+    assert fake(n, p=p) == want, (seed, n)
+  cfg = make_config()
+  fake = _U()
+  real_choice = np.random.choice
+  rows = []
+  np.random.choice = fake
+  try:
+    for i in range(400):
+      A = int(rng.choice([4, 9, 18]))
+      n_children = A if i % 3 else int(rng.integers(1, A + 1))
+      actions = sorted(rng.choice(A, size=n_children, replace=False).tolist())
+      S = int(rng.choice([30, 50]))
+      visits = rng.multinomial(S, rng.dirichlet([0.3] * n_children))
+      if i % 7 == 0:
+        visits[:] = S // n_children  # many ties
+      T = float(rng.choice([0.0, 0.1, 0.25, 0.5, 0.7, 1.0]))
+      u = float(rng.random())
+      root = ref_mcts.Node(0)
+      for a, v in zip(actions, visits):
+        root.children[a] = ref_mcts.Node(0.1)
+        root.children[a].visit_count = int(v)
+      root.visit_count = int(visits.sum())
+      root.value_sum = float(rng.normal()) * root.visit_count
+      fake.u = u
+      action = cfg.select_action(root, T)
+      # store_search_statistics only touches game.history / running stats
+      g = types.SimpleNamespace(history=types.SimpleNamespace(child_visits=[], root_values=[]),
+                                action_space=range(A), sum_values=0, max_value=-np.inf)
+      ref_game.Game.store_search_statistics(g, root)
+      v_full = np.zeros(18, np.int32)
+      mask = 0
+      for a, v in zip(actions, visits):
+        v_full[a] = v
+        mask |= 1 << a
+      cv = np.zeros(18)
+      cv[:A] = g.history.child_visits[0]
+      rows.append((A, mask, T, u, int(action), v_full, cv, g.history.root_values[0],
+                   root.value_sum, root.visit_count))
+  finally:
+    np.random.choice = real_choice
+  np.savez_compressed(
+      os.path.join(HERE, "select_action.npz"),
+      A=np.array([r[0] for r in rows], np.int32), legal=np.array([r[1] for r in rows], np.uint32),
+      temperature=np.array([r[2] for r in rows]), u=np.array([r[3] for r in rows]),
+      action=np.array([r[4] for r in rows], np.int32), visits=np.stack([r[5] for r in rows]),
+      child_visits=np.stack([r[6] for r in rows]), root_value=np.array([r[7] for r in rows]),
+      root_vsum=np.array([r[8] for r in rows]), root_visit=np.array([r[9] for r in rows], np.int32))
+  print("select_action rows", len(rows))
+
+
+# --------------------------------------------------------------------------------------------
+# replay / targets
+# --------------------------------------------------------------------------------------------
+def synth_history(rng, n, A, obs_dim, two_players, obs_uint8, running):
+  """A HistorySlice shaped like what Actor.play_game sends (actors.py:160-169)."""
+  n_obs = n + (1 if running else 0)
+  if obs_uint8:
+    obs = [rng.integers(0, 256, size=obs_dim, dtype=np.uint8) for _ in range(n_obs)]
+  else:
+    obs = [rng.normal(size=obs_dim).astype(np.float32) for _ in range(n_obs)]
+  cv = []
+  for _ in range(n):
+    c = rng.multinomial(30, rng.dirichlet([0.5] * A))
+    cv.append([int(x) / 30 for x in c])
+  root_values = [float(x) for x in rng.normal(0, 2, size=n)]
+  actions = [int(x) for x in rng.integers(0, A, size=n)]
+  kind = rng.integers(0, 3)
+  if kind == 0:
+    rewards = [float(np.sign(x)) if abs(x) > 1.3 else 0.0 for x in rng.normal(size=n)]
+  elif kind == 1:
+    rewards = [float(x) for x in rng.normal(0, 1, size=n)]
+  else:
+    rewards = [int(x) for x in rng.integers(-1, 2, size=n)]  # python ints, as gym may return
+  errors = [float(x) for x in rng.normal(0, 1, size=n)]
+  dones = [False] * n
+  steps = list(range(n))
+  to_play = [1 if (not two_players or i % 2 == 0) else -1 for i in range(n)]
+  return ref_game.HistorySlice(obs, cv, root_values, actions, rewards, errors, dones, steps,
+                               [None] * n, to_play)
+
+
+REPLAY_CASES = {
+    "breakout": dict(cfg=dict(action_space=4, td_steps=10, num_unroll_steps=5, discount=0.997,
+                              batch_size=64, obs_space=(128,), window_size=2048, beta=0.4),
+                     lens=[60, 37, 5, 120, 3, 90, 200], obs_uint8=True, two_players=False),
+    "lunar_td1000": dict(cfg=dict(action_space=4, td_steps=1000, num_unroll_steps=5,
+                                  discount=0.997, batch_size=32, obs_space=(8,), window_size=4096,
+                                  alpha=0.6, beta=1.0),
+                         lens=[1300, 40, 700, 1005, 1006, 12], obs_uint8=False, two_players=False),
+    "ttt": dict(cfg=dict(action_space=9, td_steps=10, num_unroll_steps=5, discount=1.0,
+                         batch_size=48, obs_space=(9,), window_size=256, window_step=64,
+                         two_players=True),
+                lens=[9, 5, 7, 9, 6, 8, 9, 9, 5, 7, 9, 8, 6, 9, 9, 7, 5, 9, 9, 9, 8, 7, 9, 9, 6, 9,
+                      9, 9, 9, 9, 9, 9, 9, 9, 9, 9, 9, 9, 9, 9], obs_uint8=False,
+                two_players=True),
+}
+
+
+def gen_replay(rng):
+  for name, case in REPLAY_CASES.items():
+    cfg = make_config(**case["cfg"])
+    A, K, B = cfg.action_space, cfg.num_unroll_steps, cfg.batch_size
+    obs_dim = cfg.obs_space[0]
+    rb = ref_replay.PrioritizedReplay(cfg)
+    hists, ignores = [], []
+    overlap = cfg.num_unroll_steps + cfg.td_steps
+    for i, n in enumerate(case["lens"]):
+      running = (i % 3 == 1) and n > overlap
+      h = synth_history(rng, n, A, obs_dim, case["two_players"], case["obs_uint8"], running)
+      ignore = overlap if running else None
+      rb.save_history(h, ignore=ignore, terminal=not running)
+      hists.append(h)
+      ignores.append(-1 if ignore is None else ignore)
+    hist_index = {id(h): i for i, h in enumerate(hists)}
+
+    batches = []
+    real_uniform, real_randint = ref_replay.random.uniform, np.random.randint
+    try:
+      for it in range(3):
+        frac = rng.random(B)
+        pads = rng.integers(0, A, size=(B, K))
+        state = {"b": 0, "k": [0] * B}
+
+        def fake_uniform(s1, s2):
+          b = state["b"]
+          state["b"] += 1
+          return s1 + (s2 - s1) * frac[b]
+
+        def fake_randint(n):
+          b = state["b"] - 1
+          k = state["k"][b]
+          state["k"][b] += 1
+          return int(pads[b, k])
+
+        ref_replay.random.uniform = fake_uniform
+        np.random.randint = fake_randint
+        # which (history, step) each row lands on: replay the same descent through get_leaf
+        total = rb.tree.total_priority
+        seg = total / B
+        picks = []
+        for b in range(B):
+          v = seg * b + (seg * (b + 1) - seg * b) * frac[b]
+          idx, pr, step, h = rb.tree.get_leaf(v)
+          picks.append((idx, pr, step, hist_index[id(h)]))
+        beta_before = rb.beta
+        (obs, actions, (t_r, t_v, t_p)), idxs, is_w = rb.sample_batch()
+        # sample_batch mutates history.actions when padding (replay_buffer.py:149-151 appends to a
+        # slice copy, so the stored list is untouched) -- nothing to undo.
+        assert [p[0] for p in picks] == list(idxs)
+        batches.append(dict(
+            frac=frac, pads=pads, idxs=np.array(idxs, np.int64),
+            priorities=np.array([p[1] for p in picks]), steps=np.array([p[2] for p in picks], np.int32),
+            hist=np.array([p[3] for p in picks], np.int32), obs=obs,
+            actions=np.array(actions, np.int32), t_rewards=t_r, t_values=t_v, t_policies=t_p,
+            is_weights=is_w, beta_before=beta_before, beta_after=rb.beta, total_priority=total,
+            num_memories=rb.tree.num_memories))
+        # priority update with fresh errors (learners.py:182-184)
+        errs = rng.normal(0, 1, size=B).astype(np.float32)
+        rb.update(idxs, errs)
+        batches[-1]["update_errors"] = errs
+        batches[-1]["tree_after_update"] = rb.tree.tree.copy()
+    finally:
+      ref_replay.random.uniform = real_uniform
+      np.random.randint = real_randint
+
+    save = dict(action_space=np.int32(A), num_unroll_steps=np.int32(K), td_steps=np.int32(cfg.td_steps),
+                discount=np.float64(cfg.discount), batch_size=np.int32(B), obs_dim=np.int32(obs_dim),
+                window_size=np.int32(cfg.window_size),
+                window_step=np.int32(cfg.window_size if cfg.window_step is None else cfg.window_step),
+                alpha=np.float64(cfg.alpha), beta=np.float64(case["cfg"].get("beta", 1.0)),
+                beta_increment=np.float64(cfg.beta_increment_per_sampling),
+                epsilon=np.float64(cfg.epsilon), obs_uint8=np.int32(case["obs_uint8"]),
+                n_hist=np.int32(len(hists)), ignores=np.array(ignores, np.int32),
+                n_batches=np.int32(len(batches)))
+    for i, h in enumerate(hists):
+      save["h%d_obs" % i] = np.stack(h.observations)
+      save["h%d_child_visits" % i] = np.array(h.child_visits, np.float64).reshape(-1, A)
+      save["h%d_root_values" % i] = np.array(h.root_values, np.float64)
+      save["h%d_actions" % i] = np.array(h.actions, np.int32)
+      save["h%d_rewards" % i] = np.array(h.rewards, np.float64)
+      save["h%d_errors" % i] = np.array(h.errors, np.float64)
+      save["h%d_to_play" % i] = np.array(h.to_play, np.int8)
+    for i, b in enumerate(batches):
+      for k, v in b.items():
+        save["b%d_%s" % (i, k)] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, "replay_%s.npz" % name), **save)
+    print("replay", name, "memories", rb.tree.num_memories)
+
+
+# --------------------------------------------------------------------------------------------
+# transforms and FCNetwork
+# --------------------------------------------------------------------------------------------
+def gen_transforms(rng):
+  cfg = make_config()
+  x = np.concatenate([
+      rng.normal(0, 3, size=400), rng.normal(0, 40, size=200), np.arange(-17, 18, dtype=np.float64),
+      np.array([0.0, -0.0, 1e-8, -1e-8, 14.999, 15.0, 15.001, -15.0, 0.5, -0.5, 300.0, -300.0])
+  ]).astype(np.float32)
+  xt = torch.from_numpy(x.copy())
+  h = ref_config.Config.scalar_transform(xt).numpy()
+  x2 = np.concatenate([h, rng.uniform(-16, 16, size=300).astype(np.float32)]).reshape(-1, 1)
+  sup_in = torch.from_numpy(x2.copy())
+  support = cfg.value_phi(sup_in).numpy()  # clamps sup_in in place
+  logits = (rng.normal(0, 2, size=(512, 31)) * rng.choice([0.1, 1.0, 4.0], size=(512, 1))).astype(
+      np.float32)
+  inv = cfg.inverse_value_transform(torch.from_numpy(logits.copy())).numpy()
+  cfg_nt = make_config(no_target_transform=True)
+  inv_nt = cfg_nt.inverse_value_transform(torch.from_numpy(logits.copy())).numpy()
+  # h^-1 alone on exact float32 inputs (the expectation), to pin the float32 op order bit for bit
+  v = np.concatenate([rng.uniform(-15, 15, size=2000), [0.0, -0.0, 1.0, -1.0, 15.0, -15.0]]).astype(
+      np.float32).reshape(-1, 1)
+  onehot_logits = None
+  vt = torch.from_numpy(v.copy())
+  hinv = (torch.sign(vt) * (((torch.sqrt(1 + 4 * 0.001 * (torch.abs(vt) + 1 + 0.001)) - 1) /
+                             (2 * 0.001)) ** 2 - 1)).numpy()  # the expression at config.py:32
+  np.savez_compressed(os.path.join(HERE, "transforms.npz"), x=x, h=h, support_in=x2,
+                      support=support, logits=logits, inverse=inv, inverse_no_transform=inv_nt,
+                      hinv_in=v, hinv_out=hinv)
+  print("transforms ok")
+
+
+def gen_fcnet(rng):
+  torch.manual_seed(1234)
+  for name, (obs_dim, A, B) in {"atari18": (128, 18, 64), "ttt": (9, 9, 16)}.items():
+    cfg = make_config(action_space=A)
+    net = ref_networks.FCNetwork(obs_dim, A, torch.device("cpu"), cfg)
+    with torch.no_grad():  # make LayerNorm non-trivial
+      net.LN.weight.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, size=50).astype(np.float32)))
+      net.LN.bias.copy_(torch.from_numpy(rng.normal(0, 0.1, size=50).astype(np.float32)))
+    net.eval()
+    obs = torch.from_numpy(rng.normal(size=(B, obs_dim)).astype(np.float32))
+    actions = [int(a) for a in rng.integers(0, A, size=B)]
+    with torch.inference_mode():
+      init = net.initial_inference(obs)
+      rec = net.recurrent_inference(init.hidden_state, actions)
+      net.train()
+      rec_train = net.recurrent_inference(init.hidden_state, actions)
+      net.eval()
+    save = {"w_" + k: v.numpy() for k, v in net.state_dict().items()}
+    np.savez_compressed(
+        os.path.join(HERE, "fcnet_%s.npz" % name), obs=obs.numpy(), actions=np.array(actions, np.int32),
+        init_value=init.value.numpy(), init_logits=init.policy_logits.numpy(),
+        init_hidden=init.hidden_state.numpy(), rec_value=rec.value.numpy(),
+        rec_reward=rec.reward.numpy(), rec_logits=rec.policy_logits.numpy(),
+        rec_hidden=rec.hidden_state.numpy(), rec_value_logits=rec_train.value.numpy(),
+        rec_reward_logits=rec_train.reward.numpy(), **save)
+    print("fcnet", name, "params", sum(p.numel() for p in net.parameters()))
+
+
+if __name__ == "__main__":
+  torch.set_num_threads(1)
+  rng = np.random.default_rng(20261017)
+  gen_search(rng)
+  gen_select_action(rng)
+  gen_replay(rng)
+  gen_transforms(rng)
+  gen_fcnet(rng)
+  print("python", sys.version.split()[0], "numpy", np.__version__, "torch", torch.__version__)

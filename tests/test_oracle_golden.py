@@ -1,0 +1,99 @@
+"""Pins the CPU oracle (oracle/mz_oracle.c) to outputs of the unmodified reference (tests/golden).
+
+Everything the search produces is compared BIT FOR BIT, including float64 priors, value sums and
+MinMaxStats: on this platform the oracle's libm exp/log are the ones math.exp/math.log call.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import (REPLAY_CASES, SEARCH_CASES, SEARCH_EXACT_KEYS, load,
+                     oracle_search_from_golden)
+
+
+@pytest.mark.parametrize("case", SEARCH_CASES)
+def test_search_bit_exact(case):
+  g = load("search_" + case)
+  out = oracle_search_from_golden(g)
+  for k in SEARCH_EXACT_KEYS:
+    want, got = g[k], out[k]
+    if k == "edge_child":
+      pass
+    assert want.shape == got.shape, k
+    assert np.array_equal(want, got), "%s differs (max abs %g)" % (
+        k, np.max(np.abs(want.astype(np.float64) - got.astype(np.float64))))
+
+
+def test_py_sum_matches_builtin():
+  rng = np.random.default_rng(1)
+  for _ in range(3000):
+    n = int(rng.integers(1, 19))
+    xs = np.exp(rng.normal(0, 2, size=n).astype(np.float32).astype(np.float64))
+    assert oracle.py_sum(xs) == sum(float(x) for x in xs)
+    s = 0.0
+    for x in xs:
+      s += float(x)
+    assert oracle.py_sum(xs, mode=0) == s
+
+
+def test_select_action_and_child_visits():
+  g = load("select_action")
+  for i in range(len(g["A"])):
+    A, mask = int(g["A"][i]), int(g["legal"][i])
+    actions = [a for a in range(A) if (mask >> a) & 1]
+    dense = g["visits"][i][actions]
+    idx = oracle.select_action(dense, g["temperature"][i], g["u"][i])
+    assert actions[idx] == int(g["action"][i]), i
+    child = np.array([-1 if (mask >> a) & 1 else -2 for a in range(A)], np.int32)
+    cv = oracle.child_visits(g["visits"][i][:A], child)
+    assert np.array_equal(cv, g["child_visits"][i][:A]), i
+    assert g["root_vsum"][i] / g["root_visit"][i] == g["root_value"][i]
+
+
+@pytest.mark.parametrize("case", REPLAY_CASES)
+def test_insert_target(case):
+  g = load("replay_" + case)
+  K, T, disc = int(g["num_unroll_steps"]), int(g["td_steps"]), float(g["discount"])
+  worst = 0.0
+  for b in range(int(g["n_batches"])):
+    steps, hist = g["b%d_steps" % b], g["b%d_hist" % b]
+    for row in range(len(steps)):
+      h = int(hist[row])
+      tr, tv, tp = oracle.insert_target(g["h%d_rewards" % h], g["h%d_to_play" % h],
+                                        g["h%d_root_values" % h], g["h%d_child_visits" % h], K, T,
+                                        disc, int(steps[row]))
+      assert np.array_equal(tr, g["b%d_t_rewards" % b][row])
+      assert np.array_equal(tp, g["b%d_t_policies" % b][row])
+      want = g["b%d_t_values" % b][row]
+      # tolerance (north_star): 1e-5 relative in fp32; np.dot's float32 summation order is BLAS's
+      scale = np.maximum(np.abs(want), 1.0)
+      err = np.max(np.abs(tv - want) / scale)
+      worst = max(worst, err)
+      assert err <= 1e-5, (b, row, tv, want)
+      obs = g["h%d_obs" % h][int(steps[row])].astype(np.float32)
+      assert np.array_equal(obs, g["b%d_obs" % b][row])
+  print("worst value-target rel err", worst)
+
+
+def test_transforms():
+  g = load("transforms")
+  # float32 op order of config.py:53 restated with correctly rounded sqrtf; torch's vectorised CPU
+  # sqrt is NOT correctly rounded (~0.7% of inputs are 1 ulp off), so this is a few-ulp tolerance
+  h = oracle.scalar_transform(g["x"])
+  assert np.mean(h == g["h"]) > 0.98
+  assert np.max(np.abs(h - g["h"]) / np.maximum(np.abs(g["h"]), 1e-3)) < 1e-6
+  sup = oracle.scalar_to_support(g["support_in"][:, 0], -15, 15)
+  assert np.array_equal(sup, g["support"][:, 0, :])
+  # h^-1 (config.py:32) cancels catastrophically in float32: a 1-ulp sqrt difference moves the
+  # result by ~6e-5 relative.  Same op order => bit-identical except where torch's sqrt is 1 ulp off.
+  hi = oracle.inverse_scalar_transform(g["hinv_in"])
+  assert np.mean(hi == g["hinv_out"]) > 0.98
+  assert np.max(np.abs(hi - g["hinv_out"]) / np.maximum(np.abs(g["hinv_out"]), 1.0)) < 5e-4
+  inv_nt = oracle.inverse_transform(g["logits"], -15, 15, True)
+  assert np.allclose(inv_nt, g["inverse_no_transform"], rtol=1e-5, atol=1e-6)
+  inv = oracle.inverse_transform(g["logits"], -15, 15, False)
+  # h^-1 in float32 quantises its output in steps of ~1e-4 (SURVEY.md section 7 hard part 4): a 1-ulp
+  # difference in the softmax expectation can move the result by one such step.
+  rel = np.abs(inv - g["inverse"]) / np.maximum(np.abs(g["inverse"]), 1.0)
+  assert np.mean(rel <= 1e-5) > 0.97
+  assert rel.max() < 5e-4
