@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""Benchmark of the search-and-target hot path (BASELINE.json metric: MCTS node expansions/sec).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU path (port)
+
+A "step" is one move for every game: initial_inference + root expansion + Dirichlet noise +
+num_simulations x (descent -> batched recurrent_inference -> expand + backup) + root statistics +
+action selection (the body of Actor.play_game, actors.py:131-153).  Workload (configs[3] of
+BASELINE.json, "C4"): 18 actions, 4096 games x 50 simulations per GPU, FCNetwork(128 -> 50),
+synthetic observations, random-init weights.
+
+Prints ONE JSON line on rank 0.  See DESIGN.md section "Measurement" for how every field is defined.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+  sys.path.insert(0, REPO)
+
+METRIC = "mcts_node_expansions_per_sec"
+UNIT = "expansions/s"
+
+
+def FC_FLOPS_PER_EXPANSION(A):
+  """2 * MACs of FCNetwork.recurrent_inference: 0.375 MFLOP for A=18."""
+  return 2 * (2 * (50 + A) * 512 + 512 * 31 + 512 * 50 + 2 * 50 * 512 + 512 * 31 + 512 * A)
+
+
+def parse():
+  p = argparse.ArgumentParser()
+  p.add_argument("--gpus", type=int, default=1)
+  p.add_argument("--steps", type=int, default=20)
+  p.add_argument("--warmup", type=int, default=3)
+  p.add_argument("--impl", choices=["b200", "reference"], default="b200")
+  p.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
+  p.add_argument("--sims", type=int, default=50)
+  p.add_argument("--actions", type=int, default=18)
+  p.add_argument("--obs-dim", type=int, default=128)
+  p.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+  p.add_argument("--no-cpu-baseline", action="store_true")
+  p.add_argument("--no-graph", action="store_true")
+  p.add_argument("--ref-moves-per-step", type=int, default=2,
+                 help="reference arm: moves each worker plays per step")
+  return p.parse_args()
+
+
+def search_config(args):
+  import types
+  return types.SimpleNamespace(
+      num_simulations=args.sims, action_space=args.actions, two_players=False, discount=0.997,
+      pb_c_base=19652, pb_c_init=1.25, init_value_score=0.0, known_bounds=[None, None],
+      root_dirichlet_alpha=0.25, root_exploration_fraction=0.25, value_support=[-15, 15],
+      reward_support=[-15, 15], no_support=False, no_target_transform=False)
+
+
+def synthetic_inputs(args, rank, games):
+  rng = np.random.default_rng(1234 + rank)
+  obs = (rng.integers(0, 256, size=(games, args.obs_dim)).astype(np.float32) / 255.0)
+  noise = rng.dirichlet([0.25] * args.actions, size=games)
+  uniforms = rng.random(games)
+  temperature = np.ones(games)
+  return obs, noise, uniforms, temperature
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the pure-Python port of the reference path (oracle/search_ref.py)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+  """Plays moves of independent games with the python port until the deadline / move budget."""
+  (wid, args_d, seconds, max_moves) = job
+  os.environ["OMP_NUM_THREADS"] = "1"  # train.py:63
+  import torch
+  torch.set_num_threads(1)
+  from oracle.fcnet_ref import FCNetworkRef, random_state_dict
+  from oracle.search_ref import FlatSearch, play_move
+  A, S, D = args_d["actions"], args_d["sims"], args_d["obs_dim"]
+  net = FCNetworkRef(D, A)
+  net.load_state_dict(random_state_dict(D, A))
+  rng = np.random.default_rng(99 + wid)
+  search = FlatSearch(S, A)
+  moves, t0 = 0, time.perf_counter()
+  with torch.inference_mode():
+    while True:
+      obs = (rng.integers(0, 256, size=D).astype(np.float32) / 255.0)
+      play_move(search, net, obs, rng.dirichlet([0.25] * A), 1.0, rng.random())
+      moves += 1
+      if max_moves is not None and moves >= max_moves:
+        break
+      if max_moves is None and time.perf_counter() - t0 >= seconds:
+        break
+  return moves, time.perf_counter() - t0
+
+
+def host_cores():
+  try:
+    return len(os.sched_getaffinity(0))
+  except AttributeError:
+    return os.cpu_count() or 1
+
+
+def run_cpu_port(args, seconds=None, moves_per_worker=None, pool=None, cores=None):
+  """Returns (expansions/s aggregate, cores, moves, elapsed) for one bounded sample."""
+  import multiprocessing as mp
+  cores = cores or host_cores()
+  args_d = dict(actions=args.actions, sims=args.sims, obs_dim=args.obs_dim)
+  jobs = [(w, args_d, seconds, moves_per_worker) for w in range(cores)]
+  own = pool is None
+  if own:
+    pool = mp.get_context("fork").Pool(cores)
+  t0 = time.perf_counter()
+  res = pool.map(_cpu_worker, jobs)
+  elapsed = time.perf_counter() - t0
+  if own:
+    pool.close()
+    pool.join()
+  moves = sum(r[0] for r in res)
+  return moves * args.sims / elapsed, cores, moves, elapsed
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  import multiprocessing as mp
+  cores = host_cores()
+  pool = mp.get_context("fork").Pool(cores)
+  for _ in range(args.warmup):
+    run_cpu_port(args, moves_per_worker=1, pool=pool, cores=cores)
+  total_moves, t0 = 0, time.perf_counter()
+  for _ in range(args.steps):
+    _, _, moves, _ = run_cpu_port(args, moves_per_worker=args.ref_moves_per_step, pool=pool, cores=cores)
+    total_moves += moves
+  elapsed = time.perf_counter() - t0
+  pool.close()
+  pool.join()
+  value = total_moves * args.sims / elapsed
+  sample = "%d worker processes x %d moves x %d sims per step (A=%d, FCNetwork %d->50, B=1 torch CPU)" % (
+      cores, args.ref_moves_per_step, args.sims, args.actions, args.obs_dim)
+  line = {
+      "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / max(1, args.steps),
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 tree / f32 net",
+      "data": "synthetic",
+      "config": workload_config(args, 1, cpu=True),
+      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+  }
+  print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus, cpu=False):
+  return {"workload": "C4 synthetic Atari-scale search sweep: A=%d, %d games x %d sims per GPU, "
+                      "FCNetwork(%d->50), Dirichlet root noise, temperature 1" %
+                      (args.actions, args.games, args.sims, args.obs_dim),
+          "games_per_gpu": args.games, "num_simulations": args.sims, "action_space": args.actions,
+          "obs_dim": args.obs_dim, "parallelism": "games sharded x%d, no search collective" % n_gpus,
+          "l2": ("n/a (CPU)" if cpu else
+                 "L2 flushed (512 MiB memset) between timed steps, outside the per-step event pairs")}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+  Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+       "clocks_event_reasons.sw_power_cap")
+  NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+  def __init__(self, index):
+    self.rows, self.proc, self.index = [], None, index
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+          stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(",")])
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    time.sleep(0.15)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    for r in self.rows:
+      try:
+        sm.append(float(r[0]))
+        mx.append(float(r[1]))
+      except (ValueError, IndexError):
+        continue
+      for name, cell in zip(self.NAMES, r[3:7]):
+        if cell.lower().startswith("active"):
+          reasons.add(name)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+  path = os.path.join(REPO, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    d = json.load(open(path))
+    return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+            "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+  return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+
+  cpu_baseline = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # before CUDA is initialised (fork-safe); bounded sample of the same workload
+    v, cores, moves, el = run_cpu_port(args, seconds=args.cpu_baseline_seconds)
+    cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": "%d moves (= %d expansions) of the C4 workload in %.1f s on %d worker "
+                              "processes, python port of mcts.py + torch CPU FCNetwork at B=1" %
+                              (moves, moves * args.sims, el, cores)}
+
+  import torch
+  import torch.distributed as dist
+  from model_based_rl_b200 import _lib
+  from model_based_rl_b200.networks import FCNetwork, FCSearch, random_state_dict
+  if not torch.cuda.is_available():
+    raise RuntimeError("GPU was requested but torch.cuda.is_available() is False.")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  _lib.load()
+
+  cfg = search_config(args)
+  G, S, A = args.games, args.sims, args.actions
+  net = FCNetwork(args.obs_dim, A, dev, cfg)
+  net.load_weights(random_state_dict(args.obs_dim, A))
+  fs = FCSearch(cfg, net, G, use_graph=not args.no_graph)
+  obs, noise, uniforms, temperature = synthetic_inputs(args, rank, G)
+  pin = lambda a: torch.from_numpy(a).pin_memory()
+  h_obs, h_noise, h_u, h_t = pin(obs), pin(noise), pin(uniforms), pin(temperature)
+  fs.search_host(h_obs, h_noise, h_u, h_t)  # also leaves the inputs resident in HBM
+
+  flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+  # learner side at N > 1 (BASELINE config C4 "with learner allreduce"): one gradient-sized
+  # all-reduce per step on a side stream; the search itself has no collective.
+  grad = torch.zeros(sum(v.numel() for v in net.state_dict().values()), device=dev) if world > 1 else None
+  side = torch.cuda.Stream(device=dev) if world > 1 else None
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, steps):
+    pairs = []
+    for _ in range(steps):
+      flush.zero_()
+      if side is not None:
+        with torch.cuda.stream(side):
+          dist.all_reduce(grad)
+      s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      s.record()
+      fn()
+      e.record()
+      pairs.append((s, e))
+    if side is not None:
+      torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    return sum(s.elapsed_time(e) for s, e in pairs)
+
+  for _ in range(args.warmup):
+    fs.run()
+  clocks = ClockSampler(local)
+  if rank == 0:
+    clocks.start()
+  barrier()
+  ms_total = timed(fs.run, args.steps)
+  barrier()
+  # end-to-end: host buffers in, host buffers out, through the public call
+  ms_e2e = timed(lambda: fs.search_host(h_obs, h_noise, h_u, h_t), args.steps)
+  barrier()
+  clock_info = clocks.stop() if rank == 0 else None
+
+  # per-kernel durations (CUDA events around each launch of one un-graphed move)
+  kern = kernel_breakdown(fs, torch)
+  depth_mean = float(fs.eng.path_len.float().mean().item())
+
+  t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_total, ms_e2e = t.tolist()
+  targets = bench_targets(torch, _lib, dev) if rank == 0 else None
+
+  if rank == 0:
+    peaks = measured_peaks()
+    expansions = world * G * S * args.steps
+    value = expansions / (ms_total * 1e-3)
+    e2e = expansions / (ms_e2e * 1e-3)
+    # algorithmic bytes / flops per launch (DESIGN.md "Kernels")
+    d = kern["mean_depth"]
+    tree_bytes = G * (d * (28 * A + 33) + 16 * A + 86)
+    fc_flops = G * FC_FLOPS_PER_EXPANSION(A)
+    tree_t, fc_t = kern["tree_step_us"] * 1e-6, kern["fc_recurrent_us"] * 1e-6
+    roof_tree = {"kernel": "tree_step_kernel", "bound": "hbm", "achieved": tree_bytes / tree_t / 1e9,
+                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": None,
+                 "algorithmic_bytes_per_launch": tree_bytes, "avg_launch_us": kern["tree_step_us"]}
+    roof_fc = {"kernel": "fc_recurrent_f32_kernel", "bound": "tensor", "achieved": fc_flops / fc_t / 1e12,
+               "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "traffic": None,
+               "algorithmic_flops_per_launch": fc_flops, "avg_launch_us": kern["fc_recurrent_us"]}
+    for r in (roof_tree, roof_fc):
+      r["frac"] = r["achieved"] / r["peak"]
+      r["peak_source"] = peaks["source"]
+    dominant = roof_fc if fc_t >= tree_t else roof_tree
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 (tree) / f32 (network)",
+        "data": "synthetic", "config": workload_config(args, world),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": fs.h2d_bytes(),
+                "d2h_bytes_per_step": fs.d2h_bytes(), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": fs.launches_per_move * args.steps,
+        "clocks": clock_info, "roofline": dominant, "roofline_all": [roof_tree, roof_fc],
+        "kernel_share": kern, "mean_path_edges": depth_mean, "cuda_graph": not args.no_graph,
+        "targets": targets,
+    }
+    if cpu_baseline is not None:
+      line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def kernel_breakdown(fs, torch):
+  """Average device time of the two per-simulation kernels, CUDA events on the launching stream."""
+  from model_based_rl_b200 import _lib
+  from model_based_rl_b200.networks import HIDDEN
+  eng, net, S = fs.eng, fs.net, fs.S
+  stride = (S + 1) * HIDDEN
+  ev = lambda: torch.cuda.Event(enable_timing=True)
+  fc_pairs, tree_pairs, depth_sum = [], [], 0.0
+  torch.cuda.synchronize()
+  m0, m1 = ev(), ev()
+  m0.record()
+  _lib.check(net.lib.mz_fc_initial_f32(net.weights, fs.G, _lib.ptr(fs.obs), _lib.ptr(fs.hidden_f32),
+                                       stride, _lib.ptr(fs.init_value), _lib.ptr(fs.root_logits),
+                                       _lib.current_stream()), "init")
+  eng.set_root(fs.root_logits, fs.legal, fs.noise, fs.noise_frac, fs.to_play, None)
+  eng.step(-1)
+  depths = []
+  for sim in range(S):
+    depths.append(eng.path_len.clone())
+    a, b, c = ev(), ev(), ev()
+    a.record()
+    net.recurrent_into(fs.hidden_f32, stride, eng.leaf_parent, eng.leaf_action, fs.hidden_f32, stride,
+                       (sim + 1) * HIDDEN, fs.value, fs.reward, fs.logits)
+    b.record()
+    eng.step(sim, fs.value, fs.reward, fs.logits)
+    c.record()
+    fc_pairs.append((a, b))
+    tree_pairs.append((b, c))
+  eng.root_stats()
+  eng.select_action(fs.temperature, fs.uniforms, fs.legal)
+  m1.record()
+  torch.cuda.synchronize()
+  fc_us = 1e3 * sum(a.elapsed_time(b) for a, b in fc_pairs) / S
+  tree_us = 1e3 * sum(a.elapsed_time(b) for a, b in tree_pairs) / S
+  move_us = 1e3 * m0.elapsed_time(m1)
+  mean_depth = float(torch.stack(depths).float().mean().item())
+  return {"fc_recurrent_us": fc_us, "tree_step_us": tree_us, "ungraphed_move_us": move_us,
+          "fc_share": fc_us * S / move_us, "tree_share": tree_us * S / move_us, "mean_depth": mean_depth}
+
+
+def bench_targets(torch, _lib, dev):
+  """targets/s of the fused target kernel on the C3 (Breakout-ram) shape: window 200k positions,
+  B=512, K=5, td=10, A=4, obs 128 x u8, supports fused."""
+  lib = _lib.load()
+  rng = np.random.default_rng(5)
+  P, A, K, T, B, E = 200_000, 4, 5, 10, 512, 128
+  lens = rng.integers(200, 800, size=P // 200)
+  lens = lens[np.cumsum(lens) <= P]
+  starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+  t = lambda a: torch.from_numpy(a).to(dev)
+  obs = t(rng.integers(0, 256, size=(P, E), dtype=np.uint8))
+  rewards = t(np.sign(rng.normal(size=P) * (rng.random(P) < 0.1)).astype(np.float32))
+  actions = t(rng.integers(0, A, size=P, dtype=np.int32))
+  to_play = torch.ones(P, dtype=torch.int8, device=dev)
+  root_values = t(rng.normal(0, 2, size=P))
+  cv = rng.random((P, A)).astype(np.float32)
+  child_visits = t(cv / cv.sum(1, keepdims=True))
+  win = _lib.Window(A, E, 1, 0, obs.data_ptr(), actions.data_ptr(), rewards.data_ptr(),
+                    to_play.data_ptr(), root_values.data_ptr(), child_visits.data_ptr())
+  discounts = t(np.array([0.997**n for n in range(K + T)], np.float32))
+  tc = _lib.TargetCfg(B, K, T, 1, -15, 15, -15, 15, 0, 0, 0.997**T, discounts.data_ptr(), None, None)
+  n_batches = 64
+  sets = []
+  for _ in range(n_batches):
+    ci = rng.integers(0, len(lens), size=B)
+    step = (rng.random(B) * lens[ci]).astype(np.int64)
+    sets.append((t(starts[ci] + step), t(starts[ci]), t(lens[ci].astype(np.int32)),
+                 t(rng.integers(0, A, size=(B, K), dtype=np.int32))))
+  out = [torch.zeros((B, E), device=dev), torch.zeros((B, K), dtype=torch.int32, device=dev),
+         torch.zeros((B, K + 1), device=dev), torch.zeros((B, K + 1), device=dev),
+         torch.zeros((B, K + 1, A), device=dev), torch.zeros((B, K + 1, 31), device=dev),
+         torch.zeros((B, K + 1, 31), device=dev)]
+  stream = _lib.current_stream()
+
+  def launch(s):
+    _lib.check(lib.mz_build_targets(win, tc, _lib.ptr(s[0]), _lib.ptr(s[1]), _lib.ptr(s[2]),
+                                    _lib.ptr(s[3]), *[_lib.ptr(o) for o in out], stream), "targets")
+  for s in sets[:4]:
+    launch(s)
+  torch.cuda.synchronize()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for s in sets:
+    launch(s)
+  b.record()
+  torch.cuda.synchronize()
+  sec = a.elapsed_time(b) * 1e-3 / n_batches
+  bytes_per_sample = (E + 5 * (T + K) + (K + 1) * (8 + 4 * A) + 4 * K) + \
+                     (4 * E + 4 * K + (K + 1) * (4 * A + 8)) + (K + 1) * 2 * 31 * 4
+  return {"samples_per_s": B / sec, "target_positions_per_s": B * (K + 1) / sec, "us_per_batch": sec * 1e6,
+          "workload": "C3 Breakout-ram: window 200000, B=512, K=5, td=10, A=4, obs 128 u8, supports fused",
+          "algorithmic_bytes_per_sample": bytes_per_sample,
+          "achieved_gbs": B * bytes_per_sample / sec / 1e9}
+
+
+def main():
+  args = parse()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_b200(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,277 @@
+/*
+ * mzb200.h -- C ABI of libmzb200.so, the B200 (sm_100a) search-and-target engine.
+ *
+ * This is the drop-in boundary for the hot path of JimOhman/model-based-rl.
+ * The reference has no FFI layer -- its boundary is duck-typed Python -- so every entry point below
+ * names the reference function (file:line, relative to the reference repo) whose arithmetic it
+ * replaces.  The Python mirror of the reference classes (MCTS, Node, MinMaxStats,
+ * PrioritizedReplay, FCNetwork ...) in model-based-rl_b200/ binds these symbols with ctypes; see
+ * INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name starts
+ *     with `h_` (host).  The caller owns all memory; nothing here allocates or synchronises.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it (CUDA-graph capturable).
+ *   - return value: 0 on success, a negative MZ_ERR_* for rejected arguments, or a positive
+ *     cudaError_t from the launch.  There is no CPU fallback anywhere.
+ *   - search arithmetic is IEEE binary64 in the reference's operation order (no FMA contraction),
+ *     so visit counts / selected actions are bit-exact against the reference.
+ */
+#ifndef MZB200_H_
+#define MZB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(MZ_BUILDING) && defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define MZ_OK 0
+#define MZ_ERR_BAD_ARG (-1)
+#define MZ_ERR_UNSUPPORTED (-2)
+
+#define MZ_MAX_ACTIONS 32      /* one lane per action, one (sub-)warp per game */
+#define MZ_CHILD_UNEXPANDED (-1)
+#define MZ_CHILD_ILLEGAL (-2)  /* action absent from root.children (illegal move) */
+#define MZ_GAME_HEADER_BYTES 32
+
+/* ------------------------------------------------------------------------------------------- */
+/* Tree: flat fixed-capacity node pools, one contiguous block per game (HBM, L2 resident).       */
+/*                                                                                               */
+/* game block  = header (32 B) | node record x (S + 1)            node n is expanded by sim n-1   */
+/* header      = f64 minimum | f64 maximum | i32 root_to_play | i32 reserved   (MinMaxStats,      */
+/*               mcts.py:6-25)                                                                    */
+/* node record = f64 value_sum | i32 visit_count | f32 reward | f64 prior[A] | i16 child[A] | pad */
+/*               (mcts.py:28-37; prior[a]/child[a] describe the child reached by action a, whose  */
+/*               own statistics live in node record child[a])                                     */
+/* node_bytes  = round_up(16 + 10 * A, 16);  game_bytes = round_up(32 + (S+1) * node_bytes, 128)  */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct mz_tree {
+  int32_t num_games;        /* G */
+  int32_t num_simulations;  /* S  config.num_simulations   mcts.py:66 */
+  int32_t num_actions;      /* A  config.action_space      mcts.py:72 */
+  int32_t two_players;      /*    config.two_players       mcts.py:73 */
+  int32_t prior_sum_mode;   /* builtin sum() semantics of mcts.py:53: 1 = CPython >= 3.12
+                               (Neumaier-compensated), 0 = plain left-to-right */
+  int32_t hidden_words;     /* 4-byte words per hidden state (0 = no hidden pool) */
+  int32_t node_bytes;
+  int32_t reserved0;
+  int64_t game_bytes;
+  double discount;          /* config.discount             mcts.py:67 */
+  double init_value_score;  /* config.init_value_score     mcts.py:70 */
+  double min_bound;         /* known_bounds[0], +inf when None   mcts.py:9, 24 */
+  double max_bound;         /* known_bounds[1], -inf when None */
+  uint8_t* games;           /* [G] game blocks */
+  const double* pb_c_table; /* [(S+1)*(S+1)]: entry [N*(S+1)+n] =
+                               (log((N+pb_c_base+1)/pb_c_base)+pb_c_init) * (sqrt(N)/(n+1)), i.e. the
+                               two statements at mcts.py:116-117 evaluated on the host in binary64 */
+  uint32_t* hidden;         /* [G][S+1][hidden_words] hidden-state pool (Node.hidden_state) */
+  int16_t* path;            /* [G][S+2] node ids of the current search path (root first) */
+  int32_t* path_len;        /* [G] edges on the current path (= depth of the leaf) */
+  int32_t* leaf_parent;     /* [G] node id of search_path[-2]          mcts.py:94 */
+  int32_t* leaf_action;     /* [G] action that leaves it               mcts.py:96 */
+} mz_tree;
+
+/* Size helpers (host). */
+int32_t mz_tree_node_bytes(int32_t num_actions);
+int64_t mz_tree_game_bytes(int32_t num_simulations, int32_t num_actions);
+
+/* Host: fills h_table[(S+1)*(S+1)] for mz_tree.pb_c_table.  MCTS.ucb_score mcts.py:116-117. */
+int mz_fill_pb_c_table(int32_t num_simulations, double pb_c_base, double pb_c_init, double* h_table);
+
+/*
+ * Root set-up for every game: Node.expand over the legal actions (mcts.py:47-55, called at
+ * actors.py:142), Node.add_exploration_noise (mcts.py:57-61, actors.py:143) and
+ * MinMaxStats.reset (mcts.py:79).
+ *   root_logits [G][A] f32   initial_inference().policy_logits
+ *   legal_mask  [G] u32      bit a set <=> a in legal_actions; NULL = all legal
+ *   noise       [G][A] f64   Dirichlet sample, dense over the root's children in action order
+ *                            (what np.random.dirichlet returns at mcts.py:59); NULL = no noise
+ *   root_to_play[G] i8       game.to_play; NULL = 1
+ *   root_hidden [G][hidden_words] initial hidden state copied into pool slot 0; NULL = skip
+ */
+int mz_tree_set_root(const mz_tree* t, const float* root_logits, const uint32_t* legal_mask,
+                     const double* noise, double noise_frac, const int8_t* root_to_play,
+                     const uint32_t* root_hidden, void* stream);
+
+/*
+ * Same, for a root the caller has already expanded on the host (the B=1 drop-in path:
+ * root.expand + root.add_exploration_noise were run by the caller, actors.py:142-143):
+ *   root_priors [G][A] f64 = root.children[a].prior (ignored where the action is illegal).
+ */
+int mz_tree_set_root_priors(const mz_tree* t, const double* root_priors, const uint32_t* legal_mask,
+                            const int8_t* root_to_play, const uint32_t* root_hidden, void* stream);
+
+/*
+ * One descent per game: the `while node.expanded(): select_child` loop of MCTS.run
+ * (mcts.py:87-92) with MCTS.select_child / ucb_score (mcts.py:104-124).  Writes path, path_len,
+ * leaf_parent, leaf_action.  If gathered_hidden != NULL also copies the parent's hidden state to
+ * gathered_hidden[G][hidden_words] (the argument of recurrent_inference, mcts.py:94-96).
+ * trace_* (each [G], may be NULL) receive parent / action / depth for parity checks.
+ */
+int mz_tree_select(const mz_tree* t, uint32_t* gathered_hidden, int32_t* trace_parent,
+                   int32_t* trace_action, int32_t* trace_depth, void* stream);
+
+/*
+ * Expansion of the leaf reached by the last mz_tree_select with the network outputs, then backup:
+ * Node.expand(network_output, to_play, range(A)) (mcts.py:97, 47-55) and MCTS.backpropagate
+ * (mcts.py:99, 126-143).  `sim` is the simulation index (the new node gets id sim + 1).
+ *   value [G] f32, reward [G] f32, logits [G][A] f32: recurrent_inference outputs (eval mode)
+ *   new_hidden [G][hidden_words]: next hidden state to store in the pool; NULL if the network
+ *   kernel already wrote it there.
+ */
+int mz_tree_expand_backup(const mz_tree* t, int32_t sim, const float* value, const float* reward,
+                          const float* logits, const uint32_t* new_hidden, void* stream);
+
+/*
+ * Fused simulation boundary: expand + backup of simulation `sim` followed by the descent of
+ * simulation sim + 1 (skipped when sim + 1 == S), one launch, the game block staged once.
+ * sim == -1 runs only the first descent.  Same arguments as the two calls above.
+ */
+int mz_tree_step(const mz_tree* t, int32_t sim, const float* value, const float* reward,
+                 const float* logits, const uint32_t* new_hidden, uint32_t* gathered_hidden,
+                 int32_t* trace_parent, int32_t* trace_action, int32_t* trace_depth, void* stream);
+
+/*
+ * After the last simulation: what callers read from the root (actors.py:147, config.py:72-73,
+ * game.py:106-111).  Any output may be NULL.
+ *   visits [G][A] i32 (0 for illegal actions), child_visits [G][A] f64 = visits / sum(visits)
+ *   (Game.store_search_statistics game.py:107-110), root_value [G] f64 = Node.value() mcts.py:42-45,
+ *   minmax [G][2] f64.
+ */
+int mz_tree_root_stats(const mz_tree* t, int32_t* visits, double* child_visits, double* root_value,
+                       double* minmax, void* stream);
+
+/*
+ * Config.select_action (config.py:70-81) for G roots with host-supplied randomness.
+ *   visits [G][A] i32, legal_mask [G] u32 or NULL, temperature [G] f64, uniforms [G] f64 in [0,1)
+ *   T > 0 : p = visits**(1/T) / sum; action = children[searchsorted(cumsum(p)/cumsum(p)[-1], u,
+ *           'right')]  (what np.random.choice(len, p=p) does with one uniform draw)
+ *   T == 0: uniform over the argmax ties, tie index = floor(u * n_ties)
+ */
+int mz_select_action(int32_t num_games, int32_t num_actions, const int32_t* visits,
+                     const uint32_t* legal_mask, const double* temperature, const double* uniforms,
+                     int32_t* actions, void* stream);
+
+/* Debug / façade support: copy one game's tree into dense arrays (any output may be NULL):
+ * prior [S+1][A] f64, child [S+1][A] i32, vsum [S+1] f64, visit [S+1] i32, reward [S+1] f32. */
+int mz_tree_export(const mz_tree* t, int32_t game, double* prior, int32_t* child, double* vsum,
+                   int32_t* visit, float* reward, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* FCNetwork inference (networks.py:55-174), eval mode: hidden size 50, four 512-wide MLP heads, */
+/* LayerNorm+ReLU on the state, softmax-expectation + h^-1 on value/reward (config.py:27-33).    */
+/* ------------------------------------------------------------------------------------------- */
+#define MZ_FC_HIDDEN 50
+#define MZ_FC_WIDTH 512
+
+typedef struct mz_fc_weights { /* device pointers, float32.  First layers (*_w1) are stored
+                                  TRANSPOSED, [in][512]; second layers (*_w2) keep the
+                                  nn.Linear layout [out][512]. */
+  int32_t obs_dim, num_actions, value_bins, reward_bins;
+  int32_t value_min, reward_min;    /* support = [min, min + bins - 1]  config.py:12-19 */
+  int32_t no_target_transform;      /* config.no_target_transform   config.py:31 */
+  int32_t reserved;
+  const float *rep_w1, *rep_b1, *rep_w2, *rep_b2;  /* representation_head  networks.py:55-67 */
+  const float *dyn_w1, *dyn_b1, *dyn_w2, *dyn_b2;  /* transition_head      networks.py:70-80 */
+  const float *rew_w1, *rew_b1, *rew_w2, *rew_b2;  /* reward_head          networks.py:83-93 */
+  const float *val_w1, *val_b1, *val_w2, *val_b2;  /* value_head           networks.py:96-106 */
+  const float *pol_w1, *pol_b1, *pol_w2, *pol_b2;  /* policy_head          networks.py:109-119 */
+  const float *ln_w, *ln_b;                        /* LN                   networks.py:144 */
+} mz_fc_weights;
+
+/*
+ * float32 reference-precision path (CUDA cores).
+ * BaseNetwork.initial_inference (networks.py:26-29): obs [B][obs_dim] f32 ->
+ *   hidden [B][hidden_stride words] (first 50 used), value [B], logits [B][A].
+ */
+int mz_fc_initial_f32(const mz_fc_weights* w, int32_t batch, const float* obs, float* hidden,
+                      int64_t hidden_stride, float* value, float* logits, void* stream);
+/*
+ * BaseNetwork.recurrent_inference (networks.py:31-34).  Row b reads its input state from
+ *   hidden_in + b * in_row_stride + in_index[b] * 50   (in_index may be NULL = 0)
+ * and writes the next state to hidden_out + b * out_row_stride + out_offset, so it can gather from /
+ * scatter into the tree's hidden pool directly (in_index = leaf_parent, strides = (S+1)*50).
+ */
+int mz_fc_recurrent_f32(const mz_fc_weights* w, int32_t batch, const float* hidden_in,
+                        int64_t in_row_stride, const int32_t* in_index, const int32_t* actions,
+                        float* hidden_out, int64_t out_row_stride, int64_t out_offset, float* value,
+                        float* reward, float* logits, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Scalar transforms and supports (config.py:27-68), float32 in torch's op order.                */
+/* ------------------------------------------------------------------------------------------- */
+/* Config.scalar_transform config.py:51-54, elementwise h(x). */
+int mz_scalar_transform(int64_t n, const float* x, float* out, void* stream);
+/* Config.scalar_to_support config.py:56-68: x [n] -> support [n][bins] (two-hot). x is clamped in
+ * place like the reference's x.clamp_ when clamp_in_place != 0. */
+int mz_scalar_to_support(int64_t n, float* x, int32_t support_min, int32_t support_max,
+                         int32_t clamp_in_place, float* support, void* stream);
+/* Config.inverse_transform config.py:27-33: logits [n][bins] -> scalar [n]. */
+int mz_support_to_scalar(int64_t n, const float* logits, int32_t support_min, int32_t support_max,
+                         int32_t no_target_transform, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Replay window + fused target construction (replay_buffer.py:124-198, learners.py:186-192).    */
+/*                                                                                               */
+/* The window is a structure of arrays over "positions"; a chunk (one HistorySlice, game.py:5-16)*/
+/* occupies positions [chunk_start, chunk_start + chunk_len).                                    */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct mz_window {
+  int32_t num_actions;      /* A */
+  int32_t obs_elems;        /* elements per observation */
+  int32_t obs_is_u8;        /* 1: obs stored as uint8, 0: float32 */
+  int32_t reserved;
+  const void* obs;          /* [P][obs_elems] u8 or f32   history.observations */
+  const int32_t* actions;   /* [P]                        history.actions */
+  const float* rewards;     /* [P] f32(history.rewards): both uses (np.array(.., float32) at
+                               replay_buffer.py:187 and the float32 store at :193) round to f32 */
+  const int8_t* to_play;    /* [P]                        history.to_play */
+  const double* root_values;/* [P]                        history.root_values */
+  const float* child_visits;/* [P][A] f32(history.child_visits) */
+} mz_window;
+
+typedef struct mz_target_cfg {
+  int32_t batch;            /* B   config.batch_size */
+  int32_t num_unroll_steps; /* K   config.num_unroll_steps */
+  int32_t td_steps;         /* T   config.td_steps */
+  int32_t fuse_supports;    /* also emit h(x) + two-hot supports (learners.py:186-192) */
+  int32_t value_min, value_max, reward_min, reward_max; /* supports config.py:12-19 */
+  int32_t no_target_transform;
+  int32_t normalize_obs;    /* apply (obs - obs_min) / obs_range (learners.py:170-171) */
+  double disc_pow_td;       /* discount ** td_steps (replay_buffer.py:181) */
+  const float* discounts;   /* [K+T] f32(discount ** n) (replay_buffer.py:84) */
+  const float* obs_min;     /* [obs_elems] or NULL */
+  const float* obs_range;   /* [obs_elems] or NULL */
+} mz_target_cfg;
+
+/*
+ * For every sampled row b: position pos[b] (absolute window position of (history, step)), its
+ * chunk [chunk_start[b], chunk_start[b] + chunk_len[b]) (chunk_len = len(root_values)) and
+ * chunk_obs_len[b] is not needed (obs are indexed by position).
+ * Outputs: obs_out [B][obs_elems] f32, actions_out [B][K] i32 (padded from pad_actions [B][K]),
+ * t_rewards/t_values [B][K+1] f32, t_policies [B][K+1][A] f32, and when fuse_supports:
+ * value_support [B][K+1][Vbins], reward_support [B][K+1][Rbins].
+ */
+int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* pos,
+                     const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* pad_actions,
+                     float* obs_out, int32_t* actions_out, float* t_rewards, float* t_values,
+                     float* t_policies, float* value_support, float* reward_support, void* stream);
+
+/* Library identification. */
+const char* mz_version(void);
+int32_t mz_compiled_arch(void); /* 100 for sm_100a */
+
+#if defined(MZ_BUILDING) && defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MZB200_H_ */

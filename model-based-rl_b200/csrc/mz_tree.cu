@@ -1,0 +1,609 @@
+// Tree kernels: root set-up, pUCT descent, expand + backup, root statistics, action selection.
+//
+// One sub-warp of LPG lanes (LPG = 4, 8, 16 or 32, the smallest >= A) owns one game; lane `a`
+// owns action `a`.  All score arithmetic is IEEE binary64 in the reference's operation order
+// (explicit __d*_rn intrinsics; this file is also compiled with -fmad=false), so that argmaxes --
+// and therefore visit counts -- are bit-identical to mcts.py executed by CPython.
+//
+// Reference: mcts.py:6-145, config.py:70-81, game.py:106-111 (JimOhman/model-based-rl).
+#include <math.h>
+
+#include <type_traits>
+
+#include "mz_common.cuh"
+#include "mz_exp.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+
+
+// MinMaxStats.normalize mcts.py:16-21
+MZ_DEV double mm_normalize(double v, double mn, double mx) {
+  if (mx > mn) return __ddiv_rn(__dsub_rn(v, mn), __dsub_rn(mx, mn));
+  if (mx == mn) return 1.0;
+  return v;
+}
+
+// Node.expand priors mcts.py:52-55 for the lanes of one group: p_a = exp(logit_a) / sum(p) with the
+// sum evaluated like CPython's builtin sum() over the legal actions in ascending order.
+template <int LPG>
+MZ_DEV double group_priors(float logit, bool legal, int sum_mode) {
+  const double p = legal ? mz_exp((double)logit) : 0.0;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned group_shift = lane & ~(unsigned)(LPG - 1);
+  const unsigned group_mask = (LPG == 32 ? 0xffffffffu : ((1u << LPG) - 1u)) << group_shift;
+  const unsigned legal_bits = (__ballot_sync(MZ_FULL, legal) & group_mask) >> group_shift;
+  double f = 0.0, c = 0.0;
+  bool first = true;
+#pragma unroll 1
+  for (int a = 0; a < LPG; ++a) {
+    const double x = shfl_f64<LPG>(p, a);
+    if (!((legal_bits >> a) & 1u)) continue;
+    if (first) {
+      f = x;  // int 0 + x
+      first = false;
+    } else if (sum_mode == 0) {
+      f = __dadd_rn(f, x);
+    } else {  // Neumaier step, CPython >= 3.12 Python/bltinmodule.c
+      const double t = __dadd_rn(f, x);
+      if (fabs(f) >= fabs(x)) c = __dadd_rn(c, __dadd_rn(__dsub_rn(f, t), x));
+      else c = __dadd_rn(c, __dadd_rn(__dsub_rn(x, t), f));
+      f = t;
+    }
+  }
+  if (sum_mode != 0 && c != 0.0 && isfinite(c)) f = __dadd_rn(f, c);
+  return legal ? __ddiv_rn(p, f) : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// descent: while node.expanded(): select_child  (mcts.py:87-92, 104-124)
+// ------------------------------------------------------------------------------------------------
+template <int LPG>
+MZ_DEV void descend(const mz_tree& t, const MzGame& gm, bool valid, int sub, int16_t* path,
+                    int& out_depth, int& out_parent, int& out_action) {
+  const int A = t.num_actions, SP1 = t.num_simulations + 1;
+  const bool two = t.two_players != 0;
+  const double disc = t.discount, init_score = t.init_value_score;
+  const double mn = gm.mn(), mx = gm.mx();
+  int node = 0, depth = 0, parent = 0, action = 0;
+  int N = gm.node(0).visit();
+  bool done = !valid;
+  if (valid && sub == 0) path[0] = 0;
+  while (__any_sync(MZ_FULL, !done)) {
+    const MzNode nd = gm.node(node);
+    const bool lane_ok = sub < A;
+    double prior = 0.0;
+    int ch = MZ_CHILD_ILLEGAL;
+    if (lane_ok) {
+      prior = nd.prior()[sub];
+      ch = nd.child()[sub];
+    }
+    int n = 0;
+    double vs = 0.0;
+    float rw = 0.0f;
+    if (ch >= 0) {
+      const MzNode c = gm.node(ch);
+      n = c.visit();
+      vs = c.vsum();
+      rw = c.reward();
+    }
+    double score;
+    if (N == 0) {  // mcts.py:105-108: an unvisited (root) node ranks children by prior
+      score = prior;
+    } else {       // ucb_score mcts.py:115-124
+      const double pb_c = __ldg(&t.pb_c_table[(size_t)N * SP1 + n]);
+      const double prior_score = __dmul_rn(pb_c, prior);
+      double value_score = init_score;
+      if (n > 0) {
+        double value = __ddiv_rn(vs, (double)n);
+        if (two) value = -value;
+        value_score = mm_normalize(__dadd_rn((double)rw, __dmul_rn(disc, value)), mn, mx);
+      }
+      score = __dadd_rn(prior_score, value_score);
+    }
+    // max over (score, action) tuples: ties go to the larger action (mcts.py:106-112)
+    int best = (lane_ok && ch != MZ_CHILD_ILLEGAL) ? sub : -1;
+    double best_score = score;
+#pragma unroll
+    for (int m = LPG / 2; m > 0; m >>= 1) {
+      const double os = shfl_xor_f64<LPG>(best_score, m);
+      const int ob = __shfl_xor_sync(MZ_FULL, best, m, LPG);
+      const bool take = ob >= 0 && (best < 0 || os > best_score || (os == best_score && ob > best));
+      if (take) {
+        best_score = os;
+        best = ob;
+      }
+    }
+    const int src = best < 0 ? 0 : best;
+    const int ch_b = __shfl_sync(MZ_FULL, ch, src, LPG);
+    const int n_b = __shfl_sync(MZ_FULL, n, src, LPG);
+    if (!done) {
+      depth++;
+      if (ch_b < 0) {  // child not expanded: this is the leaf
+        parent = node;
+        action = best;
+        done = true;
+      } else {
+        node = ch_b;
+        N = n_b;
+        if (sub == 0) path[depth] = (int16_t)node;
+      }
+    }
+  }
+  out_depth = depth;
+  out_parent = parent;
+  out_action = action;
+}
+
+// ------------------------------------------------------------------------------------------------
+// expand (mcts.py:47-55) + backpropagate (mcts.py:126-143)
+// ------------------------------------------------------------------------------------------------
+template <int LPG>
+MZ_DEV void expand_backup(const mz_tree& t, const MzGame& gm, bool valid, int sub, int sim,
+                          float value_f, float reward_f, float logit, int16_t* path, int depth,
+                          int parent, int action) {
+  const int A = t.num_actions;
+  const bool two = t.two_players != 0;
+  const double disc = t.discount;
+  const int newn = sim + 1;
+  const MzNode nn = gm.node(newn);
+  const float node_reward_new = (reward_f != 0.0f) ? reward_f : 0.0f;  // `if network_output.reward:`
+
+  const double prior = group_priors<LPG>(logit, sub < A, t.prior_sum_mode);
+  if (valid) {
+    if (sub < A) {
+      nn.prior()[sub] = prior;
+      nn.child()[sub] = (int16_t)MZ_CHILD_UNEXPANDED;
+    }
+    if (sub == 0) {
+      nn.reward() = node_reward_new;
+      gm.node(parent).child()[action] = (int16_t)newn;
+      path[depth] = (int16_t)newn;
+    }
+  }
+
+  // backup.  Position k on the path holds node path[k] (k < depth) or the new node (k == depth).
+  double value = (double)value_f;
+  double lmin = INFINITY, lmax = -INFINITY;
+  int dmax = valid ? depth : 0;
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) dmax = max(dmax, __shfl_xor_sync(MZ_FULL, dmax, m));
+  for (int base = (dmax / LPG) * LPG; base >= 0; base -= LPG) {
+    const int k = base + sub;
+    const bool has = valid && k <= depth;
+    const int nid = has ? (k == depth ? newn : (int)path[k]) : 0;
+    const MzNode nd = gm.node(nid);
+    double vs = 0.0;
+    int vc = 0;
+    float rw = 0.0f;
+    if (has) {
+      if (k == depth) {
+        rw = node_reward_new;
+      } else {
+        vs = nd.vsum();
+        vc = nd.visit();
+        rw = nd.reward();
+      }
+    }
+    double myval = 0.0;
+#pragma unroll 1
+    for (int j = LPG - 1; j >= 0; --j) {
+      const int kk = base + j;
+      const float rj = __shfl_sync(MZ_FULL, rw, j, LPG);
+      if (valid && kk <= depth) {
+        if (sub == j) myval = value;
+        const bool same = two ? (((depth - kk) & 1) == 0) : true;
+        const double nr = (double)rj;
+        const double r = (two && same) ? -nr : nr;
+        value = __dadd_rn(r, __dmul_rn(disc, value));
+      }
+    }
+    if (has) {
+      const bool same = two ? (((depth - k) & 1) == 0) : true;
+      vs = __dadd_rn(vs, same ? myval : -myval);
+      vc += 1;
+      nd.vsum() = vs;
+      nd.visit() = vc;
+      if (k > 0) {
+        const double nv = __ddiv_rn(vs, (double)vc);
+        const double dq = __dmul_rn(disc, nv);
+        const double new_q = two ? __dsub_rn((double)rw, dq) : __dadd_rn((double)rw, dq);
+        lmin = fmin(lmin, new_q);
+        lmax = fmax(lmax, new_q);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = LPG / 2; m > 0; m >>= 1) {
+    lmin = fmin(lmin, shfl_xor_f64<LPG>(lmin, m));
+    lmax = fmax(lmax, shfl_xor_f64<LPG>(lmax, m));
+  }
+  if (valid && sub == 0) {
+    if (lmin < gm.mn()) gm.mn() = lmin;
+    if (lmax > gm.mx()) gm.mx() = lmax;
+  }
+}
+
+template <int LPG>
+MZ_DEV void copy_words(uint32_t* dst, const uint32_t* src, int words, int sub) {
+  for (int i = sub; i < words; i += LPG) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+template <int LPG>
+__global__ void __launch_bounds__(kThreads)
+set_root_kernel(mz_tree t, const float* __restrict__ root_logits,
+                const uint32_t* __restrict__ legal_mask, const double* __restrict__ noise,
+                double noise_frac, const int8_t* __restrict__ root_to_play,
+                const uint32_t* __restrict__ root_hidden, const double* __restrict__ root_priors) {
+  const int gidx = (blockIdx.x * kThreads + threadIdx.x) / LPG;
+  const int sub = threadIdx.x & (LPG - 1);
+  const bool valid = gidx < t.num_games;
+  const int g = valid ? gidx : t.num_games - 1;
+  const int A = t.num_actions;
+  const MzGame gm{t.games + (size_t)g * t.game_bytes, t.node_bytes, A};
+  const uint32_t lm = legal_mask ? legal_mask[g] : 0xffffffffu;
+  const bool legal = sub < A && ((lm >> sub) & 1u);
+  double prior;
+  if (root_priors) {  // the caller ran Node.expand / add_exploration_noise itself
+    prior = legal ? root_priors[(size_t)g * A + sub] : 0.0;
+  } else {
+    const float logit = sub < A ? root_logits[(size_t)g * A + sub] : 0.0f;
+    prior = group_priors<LPG>(logit, legal, t.prior_sum_mode);
+  }
+  if (noise && legal) {  // add_exploration_noise mcts.py:57-61; noise is dense over children
+    const int j = __popc(lm & ((1u << sub) - 1u));
+    const double nz = noise[(size_t)g * A + j];
+    prior = __dadd_rn(__dmul_rn(prior, __dsub_rn(1.0, noise_frac)), __dmul_rn(nz, noise_frac));
+  }
+  if (!valid) return;
+  const MzNode root = gm.node(0);
+  if (sub < A) {
+    root.prior()[sub] = prior;
+    root.child()[sub] = (int16_t)(legal ? MZ_CHILD_UNEXPANDED : MZ_CHILD_ILLEGAL);
+  }
+  if (sub == 0) {
+    root.vsum() = 0.0;
+    root.visit() = 0;
+    root.reward() = 0.0f;
+    gm.mn() = t.min_bound;  // MinMaxStats.reset mcts.py:79
+    gm.mx() = t.max_bound;
+    gm.root_to_play() = root_to_play ? (int32_t)root_to_play[g] : 1;
+  }
+  if (root_hidden && t.hidden_words > 0)
+    copy_words<LPG>(t.hidden + (size_t)g * (t.num_simulations + 1) * t.hidden_words,
+                    root_hidden + (size_t)g * t.hidden_words, t.hidden_words, sub);
+}
+
+// sim == -1: descent only.  do_select == 0: expand+backup only.
+template <int LPG>
+__global__ void __launch_bounds__(kThreads)
+tree_step_kernel(mz_tree t, int sim, int do_backup, int do_select, const float* __restrict__ value,
+                 const float* __restrict__ reward, const float* __restrict__ logits,
+                 const uint32_t* __restrict__ new_hidden, uint32_t* __restrict__ gathered_hidden,
+                 int32_t* __restrict__ trace_parent, int32_t* __restrict__ trace_action,
+                 int32_t* __restrict__ trace_depth) {
+  const int gidx = (blockIdx.x * kThreads + threadIdx.x) / LPG;
+  const int sub = threadIdx.x & (LPG - 1);
+  const bool valid = gidx < t.num_games;
+  const int g = valid ? gidx : t.num_games - 1;
+  const int A = t.num_actions, SP1 = t.num_simulations + 1, HW = t.hidden_words;
+  const MzGame gm{t.games + (size_t)g * t.game_bytes, t.node_bytes, A};
+  int16_t* path = t.path + (size_t)g * (t.num_simulations + 2);
+
+  if (do_backup) {
+    const int depth = t.path_len[g], parent = t.leaf_parent[g], action = t.leaf_action[g];
+    const float logit = sub < A ? logits[(size_t)g * A + sub] : 0.0f;
+    expand_backup<LPG>(t, gm, valid, sub, sim, value[g], reward[g], logit, path, depth, parent,
+                       action);
+    if (valid && new_hidden && HW > 0)
+      copy_words<LPG>(t.hidden + ((size_t)g * SP1 + sim + 1) * HW, new_hidden + (size_t)g * HW, HW,
+                      sub);
+    __syncwarp();
+  }
+  if (do_select) {
+    int depth, parent, action;
+    descend<LPG>(t, gm, valid, sub, path, depth, parent, action);
+    if (valid) {
+      if (sub == 0) {
+        t.path_len[g] = depth;
+        t.leaf_parent[g] = parent;
+        t.leaf_action[g] = action;
+        if (trace_parent) trace_parent[g] = parent;
+        if (trace_action) trace_action[g] = action;
+        if (trace_depth) trace_depth[g] = depth;
+      }
+      if (gathered_hidden && HW > 0)
+        copy_words<LPG>(gathered_hidden + (size_t)g * HW,
+                        t.hidden + ((size_t)g * SP1 + parent) * HW, HW, sub);
+    }
+  }
+}
+
+// game.py:106-111 + Node.value mcts.py:42-45
+__global__ void root_stats_kernel(mz_tree t, int32_t* __restrict__ visits,
+                                  double* __restrict__ child_visits, double* __restrict__ root_value,
+                                  double* __restrict__ minmax) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= t.num_games) return;
+  const int A = t.num_actions;
+  const MzGame gm{t.games + (size_t)g * t.game_bytes, t.node_bytes, A};
+  const MzNode root = gm.node(0);
+  int v[MZ_MAX_ACTIONS];
+  long long sum = 0;
+  for (int a = 0; a < A; ++a) {
+    const int ch = root.child()[a];
+    v[a] = ch >= 0 ? gm.node(ch).visit() : 0;
+    sum += v[a];
+  }
+  for (int a = 0; a < A; ++a) {
+    if (visits) visits[(size_t)g * A + a] = v[a];
+    if (child_visits) {
+      const bool exists = root.child()[a] != MZ_CHILD_ILLEGAL;
+      child_visits[(size_t)g * A + a] = exists ? __ddiv_rn((double)v[a], (double)sum) : 0.0;
+    }
+  }
+  if (root_value) {
+    const int n = root.visit();
+    root_value[g] = n == 0 ? 0.0 : __ddiv_rn(root.vsum(), (double)n);
+  }
+  if (minmax) {
+    minmax[2 * g] = gm.mn();
+    minmax[2 * g + 1] = gm.mx();
+  }
+}
+
+// numpy's float64 add.reduce over a contiguous row (pairwise sum with 8 accumulators, n <= 128)
+__device__ double np_pairwise_sum(const double* a, int n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+  }
+  double r[8];
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i;
+  for (i = 8; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+  return res;
+}
+
+// Config.select_action config.py:70-81
+__global__ void select_action_kernel(int G, int A, const int32_t* __restrict__ visits,
+                                     const uint32_t* __restrict__ legal_mask,
+                                     const double* __restrict__ temperature,
+                                     const double* __restrict__ uniforms,
+                                     int32_t* __restrict__ actions) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const uint32_t lm = legal_mask ? legal_mask[g] : 0xffffffffu;
+  int act[MZ_MAX_ACTIONS];
+  int cnt[MZ_MAX_ACTIONS];
+  int n = 0;
+  for (int a = 0; a < A; ++a)
+    if ((lm >> a) & 1u) {
+      act[n] = a;
+      cnt[n] = visits[(size_t)g * A + a];
+      ++n;
+    }
+  if (n == 0) {
+    actions[g] = -1;
+    return;
+  }
+  const double T = temperature[g], u = uniforms[g];
+  int idx = 0;
+  if (T != 0.0) {
+    double d[MZ_MAX_ACTIONS];
+    const double inv_t = __ddiv_rn(1.0, T);
+    for (int i = 0; i < n; ++i) d[i] = pow((double)cnt[i], inv_t);
+    const double s = np_pairwise_sum(d, n);
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {  // distribution / sum, then cumsum
+      const double p = __ddiv_rn(d[i], s);
+      acc = (i == 0) ? p : __dadd_rn(acc, p);
+      d[i] = acc;
+    }
+    const double last = d[n - 1];
+    for (int i = 0; i < n; ++i)
+      if (__ddiv_rn(d[i], last) <= u) idx = i + 1;  // searchsorted(side='right')
+    if (idx >= n) idx = n - 1;
+  } else {
+    int mx = cnt[0];
+    for (int i = 1; i < n; ++i) mx = max(mx, cnt[i]);
+    int ties = 0;
+    for (int i = 0; i < n; ++i) ties += (cnt[i] == mx);
+    int pick = (int)floor(__dmul_rn(u, (double)ties));
+    if (pick >= ties) pick = ties - 1;
+    for (int i = 0; i < n; ++i)
+      if (cnt[i] == mx && pick-- == 0) {
+        idx = i;
+        break;
+      }
+  }
+  actions[g] = act[idx];
+}
+
+__global__ void tree_export_kernel(mz_tree t, int game, double* prior, int32_t* child, double* vsum,
+                                   int32_t* visit, float* reward) {
+  const int A = t.num_actions, SP1 = t.num_simulations + 1;
+  const MzGame gm{t.games + (size_t)game * t.game_bytes, t.node_bytes, A};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < SP1 * A; i += gridDim.x * blockDim.x) {
+    const int n = i / A, a = i % A;
+    const MzNode nd = gm.node(n);
+    if (prior) prior[i] = nd.prior()[a];
+    if (child) child[i] = nd.child()[a];
+    if (a == 0) {
+      if (vsum) vsum[n] = nd.vsum();
+      if (visit) visit[n] = nd.visit();
+      if (reward) reward[n] = nd.reward();
+    }
+  }
+}
+
+int check_tree(const mz_tree* t) {
+  if (!t || !t->games || !t->pb_c_table || !t->path || !t->path_len || !t->leaf_parent ||
+      !t->leaf_action)
+    return MZ_ERR_BAD_ARG;
+  if (t->num_games < 1 || t->num_simulations < 1 || t->num_simulations > 32000) return MZ_ERR_BAD_ARG;
+  if (t->num_actions < 1 || t->num_actions > MZ_MAX_ACTIONS) return MZ_ERR_BAD_ARG;
+  if (t->node_bytes != mz_tree_node_bytes(t->num_actions)) return MZ_ERR_BAD_ARG;
+  if (t->game_bytes < mz_tree_game_bytes(t->num_simulations, t->num_actions)) return MZ_ERR_BAD_ARG;
+  if (t->hidden_words < 0 || (t->hidden_words > 0 && !t->hidden)) return MZ_ERR_BAD_ARG;
+  return MZ_OK;
+}
+
+template <typename F>
+int dispatch_lpg(int A, F&& f) {
+  if (A <= 4) return f(std::integral_constant<int, 4>());
+  if (A <= 8) return f(std::integral_constant<int, 8>());
+  if (A <= 16) return f(std::integral_constant<int, 16>());
+  return f(std::integral_constant<int, 32>());
+}
+
+int launch_step(const mz_tree* t, int sim, int do_backup, int do_select, const float* value,
+                const float* reward, const float* logits, const uint32_t* new_hidden,
+                uint32_t* gathered_hidden, int32_t* tp, int32_t* ta, int32_t* td, void* stream) {
+  return dispatch_lpg(t->num_actions, [&](auto lpg) {
+    constexpr int LPG = decltype(lpg)::value;
+    const int gpb = kThreads / LPG;
+    const int grid = (t->num_games + gpb - 1) / gpb;
+    tree_step_kernel<LPG><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        *t, sim, do_backup, do_select, value, reward, logits, new_hidden, gathered_hidden, tp, ta, td);
+    MZ_LAUNCH_CHECK();
+    return MZ_OK;
+  });
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t mz_tree_node_bytes(int32_t A) { return (16 + 10 * A + 15) / 16 * 16; }
+
+int64_t mz_tree_game_bytes(int32_t S, int32_t A) {
+  int64_t b = MZ_GAME_HEADER_BYTES + (int64_t)(S + 1) * mz_tree_node_bytes(A);
+  return (b + 127) / 128 * 128;
+}
+
+int mz_fill_pb_c_table(int32_t S, double pb_c_base, double pb_c_init, double* h_table) {
+  if (S < 1 || !h_table) return MZ_ERR_BAD_ARG;
+  const int SP1 = S + 1;
+  for (int N = 0; N < SP1; ++N) {
+    // mcts.py:116: math.log((N + base + 1) / base) + init   (host libm log, like CPython)
+    volatile double ratio = ((double)N + pb_c_base + 1.0) / pb_c_base;
+    volatile double pb_c = log(ratio) + pb_c_init;
+    volatile double sq = sqrt((double)N);
+    for (int n = 0; n < SP1; ++n) {
+      volatile double f = sq / (double)(n + 1);  // mcts.py:117
+      volatile double v = pb_c * f;
+      h_table[(size_t)N * SP1 + n] = v;
+    }
+  }
+  return MZ_OK;
+}
+
+int mz_tree_set_root(const mz_tree* t, const float* root_logits, const uint32_t* legal_mask,
+                     const double* noise, double noise_frac, const int8_t* root_to_play,
+                     const uint32_t* root_hidden, void* stream) {
+  int rc = check_tree(t);
+  if (rc) return rc;
+  if (!root_logits) return MZ_ERR_BAD_ARG;
+  return dispatch_lpg(t->num_actions, [&](auto lpg) {
+    constexpr int LPG = decltype(lpg)::value;
+    const int gpb = kThreads / LPG;
+    const int grid = (t->num_games + gpb - 1) / gpb;
+    set_root_kernel<LPG><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        *t, root_logits, legal_mask, noise, noise_frac, root_to_play, root_hidden, nullptr);
+    MZ_LAUNCH_CHECK();
+    return MZ_OK;
+  });
+}
+
+int mz_tree_set_root_priors(const mz_tree* t, const double* root_priors, const uint32_t* legal_mask,
+                            const int8_t* root_to_play, const uint32_t* root_hidden, void* stream) {
+  int rc = check_tree(t);
+  if (rc) return rc;
+  if (!root_priors) return MZ_ERR_BAD_ARG;
+  return dispatch_lpg(t->num_actions, [&](auto lpg) {
+    constexpr int LPG = decltype(lpg)::value;
+    const int gpb = kThreads / LPG;
+    const int grid = (t->num_games + gpb - 1) / gpb;
+    set_root_kernel<LPG><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        *t, nullptr, legal_mask, nullptr, 0.0, root_to_play, root_hidden, root_priors);
+    MZ_LAUNCH_CHECK();
+    return MZ_OK;
+  });
+}
+
+int mz_tree_select(const mz_tree* t, uint32_t* gathered_hidden, int32_t* trace_parent,
+                   int32_t* trace_action, int32_t* trace_depth, void* stream) {
+  int rc = check_tree(t);
+  if (rc) return rc;
+  return launch_step(t, -1, 0, 1, nullptr, nullptr, nullptr, nullptr, gathered_hidden, trace_parent,
+                     trace_action, trace_depth, stream);
+}
+
+int mz_tree_expand_backup(const mz_tree* t, int32_t sim, const float* value, const float* reward,
+                          const float* logits, const uint32_t* new_hidden, void* stream) {
+  int rc = check_tree(t);
+  if (rc) return rc;
+  if (sim < 0 || sim >= t->num_simulations || !value || !reward || !logits) return MZ_ERR_BAD_ARG;
+  return launch_step(t, sim, 1, 0, value, reward, logits, new_hidden, nullptr, nullptr, nullptr,
+                     nullptr, stream);
+}
+
+int mz_tree_step(const mz_tree* t, int32_t sim, const float* value, const float* reward,
+                 const float* logits, const uint32_t* new_hidden, uint32_t* gathered_hidden,
+                 int32_t* trace_parent, int32_t* trace_action, int32_t* trace_depth, void* stream) {
+  int rc = check_tree(t);
+  if (rc) return rc;
+  if (sim < -1 || sim >= t->num_simulations) return MZ_ERR_BAD_ARG;
+  const int do_backup = sim >= 0, do_select = sim + 1 < t->num_simulations;
+  if (do_backup && (!value || !reward || !logits)) return MZ_ERR_BAD_ARG;
+  return launch_step(t, sim, do_backup, do_select, value, reward, logits, new_hidden,
+                     gathered_hidden, trace_parent, trace_action, trace_depth, stream);
+}
+
+int mz_tree_root_stats(const mz_tree* t, int32_t* visits, double* child_visits, double* root_value,
+                       double* minmax, void* stream) {
+  int rc = check_tree(t);
+  if (rc) return rc;
+  const int threads = 128, grid = (t->num_games + threads - 1) / threads;
+  root_stats_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(*t, visits, child_visits, root_value,
+                                                               minmax);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+int mz_select_action(int32_t G, int32_t A, const int32_t* visits, const uint32_t* legal_mask,
+                     const double* temperature, const double* uniforms, int32_t* actions,
+                     void* stream) {
+  if (G < 1 || A < 1 || A > MZ_MAX_ACTIONS || !visits || !temperature || !uniforms || !actions)
+    return MZ_ERR_BAD_ARG;
+  const int threads = 128, grid = (G + threads - 1) / threads;
+  select_action_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(G, A, visits, legal_mask,
+                                                                  temperature, uniforms, actions);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+int mz_tree_export(const mz_tree* t, int32_t game, double* prior, int32_t* child, double* vsum,
+                   int32_t* visit, float* reward, void* stream) {
+  int rc = check_tree(t);
+  if (rc) return rc;
+  if (game < 0 || game >= t->num_games) return MZ_ERR_BAD_ARG;
+  tree_export_kernel<<<4, 128, 0, (cudaStream_t)stream>>>(*t, game, prior, child, vsum, visit, reward);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+const char* mz_version(void) { return "mzb200 0.1.0 (sm_100a)"; }
+int32_t mz_compiled_arch(void) { return 100; }
+
+}  // extern "C"

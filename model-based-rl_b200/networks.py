@@ -1,0 +1,308 @@
+"""Inference side of the reference's FCNetwork (networks.py:55-174) on hand-written kernels.
+
+`FCNetwork` here keeps the reference's interface -- initial_inference / recurrent_inference
+returning NetworkOutput(value, reward, policy_logits, hidden_state), load_weights / get_weights with
+the reference's state-dict keys -- but evaluates the whole network in one fused CUDA kernel per
+call (eval mode: value / reward are scalars after softmax-expectation + h^-1, config.py:27-33).
+Training (backward, train-mode support logits) stays with the reference's torch module; weights
+move between the two through the state dict.
+"""
+from collections import OrderedDict, namedtuple
+
+import torch
+
+from . import _lib
+
+NetworkOutput = namedtuple('network_output', ('value', 'reward', 'policy_logits', 'hidden_state'))
+
+HIDDEN = _lib.FC_HIDDEN
+
+# reference state-dict keys (networks.py:137-144) -> (struct field, transposed?)
+_KEYS = OrderedDict([
+    ('representation_head.fc1.weight', ('rep_w1', True)), ('representation_head.fc1.bias', ('rep_b1', False)),
+    ('representation_head.out.weight', ('rep_w2', False)), ('representation_head.out.bias', ('rep_b2', False)),
+    ('value_head.fc1.weight', ('val_w1', True)), ('value_head.fc1.bias', ('val_b1', False)),
+    ('value_head.value.weight', ('val_w2', False)), ('value_head.value.bias', ('val_b2', False)),
+    ('policy_head.fc1.weight', ('pol_w1', True)), ('policy_head.fc1.bias', ('pol_b1', False)),
+    ('policy_head.policy.weight', ('pol_w2', False)), ('policy_head.policy.bias', ('pol_b2', False)),
+    ('reward_head.fc1.weight', ('rew_w1', True)), ('reward_head.fc1.bias', ('rew_b1', False)),
+    ('reward_head.reward.weight', ('rew_w2', False)), ('reward_head.reward.bias', ('rew_b2', False)),
+    ('transition_head.fc1.weight', ('dyn_w1', True)), ('transition_head.fc1.bias', ('dyn_b1', False)),
+    ('transition_head.out.weight', ('dyn_w2', False)), ('transition_head.out.bias', ('dyn_b2', False)),
+    ('LN.weight', ('ln_w', False)), ('LN.bias', ('ln_b', False)),
+])
+
+
+class FCNetwork(object):
+  """Fused-kernel FCNetwork (inference).  `config` supplies value_support / reward_support /
+  no_support / no_target_transform exactly like the reference's Config (config.py:9-19)."""
+
+  accepts_device_actions = True
+  training = False
+
+  def __init__(self, input_dim, action_space, device, config):
+    _lib.require_cuda()
+    if getattr(config, 'no_support', False):
+      raise NotImplementedError("no_support networks are not on the B200 path")
+    self.lib = _lib.load()
+    self.device = _lib.normalize_device(device)
+    self.input_dim = int(input_dim)
+    self.action_space = int(action_space)
+    self.value_min, self.value_max = [int(v) for v in config.value_support]
+    self.reward_min, self.reward_max = [int(v) for v in config.reward_support]
+    self.value_bins = self.value_max - self.value_min + 1
+    self.reward_bins = self.reward_max - self.reward_min + 1
+    self.no_target_transform = bool(getattr(config, 'no_target_transform', False))
+    self._state = None    # reference-layout float32 tensors (device)
+    self._packed = None   # kernel-layout tensors, kept alive for the struct
+    self.weights = None   # _lib.FcWeights
+
+  # -- weights -----------------------------------------------------------------------------------
+  def load_weights(self, weights):
+    """Accepts the reference's state dict (networks.py:176-177)."""
+    missing = [k for k in _KEYS if k not in weights]
+    if missing:
+      raise KeyError("state dict is missing %s" % missing)
+    self._state = {k: torch.as_tensor(weights[k]).detach().to(self.device, torch.float32).contiguous()
+                   for k in _KEYS}
+    s = self._state
+    shapes = {
+        'representation_head.fc1.weight': (512, self.input_dim),
+        'transition_head.fc1.weight': (512, HIDDEN + self.action_space),
+        'reward_head.fc1.weight': (512, HIDDEN + self.action_space),
+        'value_head.fc1.weight': (512, HIDDEN), 'policy_head.fc1.weight': (512, HIDDEN),
+        'representation_head.out.weight': (HIDDEN, 512), 'transition_head.out.weight': (HIDDEN, 512),
+        'reward_head.reward.weight': (self.reward_bins, 512),
+        'value_head.value.weight': (self.value_bins, 512),
+        'policy_head.policy.weight': (self.action_space, 512), 'LN.weight': (HIDDEN,)}
+    for k, shp in shapes.items():
+      if tuple(s[k].shape) != shp:
+        raise ValueError("%s has shape %s, expected %s" % (k, tuple(s[k].shape), shp))
+    self._packed = {}
+    fields = {}
+    for k, (name, transposed) in _KEYS.items():
+      t = s[k].t().contiguous() if transposed else s[k]
+      self._packed[name] = t
+      fields[name] = t.data_ptr()
+    self.weights = _lib.FcWeights(self.input_dim, self.action_space, self.value_bins,
+                                  self.reward_bins, self.value_min, self.reward_min,
+                                  int(self.no_target_transform), 0,
+                                  *[fields[n] for n in _lib.FcWeights._names])
+
+  load_state_dict = load_weights
+
+  def get_weights(self):
+    return {k: v.cpu() for k, v in self._state.items()}
+
+  def state_dict(self):
+    return dict(self._state)
+
+  def to(self, device):
+    if torch.device(device).type != 'cuda':
+      raise RuntimeError("the B200 FCNetwork only runs on CUDA devices")
+    return self
+
+  def eval(self):
+    return self
+
+  # -- inference ---------------------------------------------------------------------------------
+  def initial_inference(self, observation, hidden_out=None, hidden_stride=None):
+    """BaseNetwork.initial_inference (networks.py:26-29).  observation [B, input_dim] float32."""
+    obs = observation.to(self.device, torch.float32).reshape(observation.shape[0], -1).contiguous()
+    B = obs.shape[0]
+    if hidden_out is None:
+      hidden_out = torch.empty((B, HIDDEN), dtype=torch.float32, device=self.device)
+      hidden_stride = HIDDEN
+    value = torch.empty((B, 1), dtype=torch.float32, device=self.device)
+    logits = torch.empty((B, self.action_space), dtype=torch.float32, device=self.device)
+    _lib.check(self.lib.mz_fc_initial_f32(self.weights, B, _lib.ptr(obs), _lib.ptr(hidden_out),
+                                          int(hidden_stride), _lib.ptr(value), _lib.ptr(logits),
+                                          _lib.current_stream()), "mz_fc_initial_f32")
+    return NetworkOutput(value, 0, logits, hidden_out)
+
+  def recurrent_inference(self, hidden_state, action):
+    """BaseNetwork.recurrent_inference (networks.py:31-34).  `action`: B ints (list or tensor)."""
+    h = hidden_state.to(self.device, torch.float32).contiguous()
+    B = h.shape[0]
+    a = torch.as_tensor(action, device=self.device).to(torch.int32).reshape(B).contiguous()
+    out = self._buffers(B)
+    self.recurrent_into(h, HIDDEN, None, a, out[3], HIDDEN, 0, out[0], out[1], out[2])
+    return NetworkOutput(out[0], out[1], out[2], out[3])
+
+  def recurrent_into(self, hidden_in, in_row_stride, in_index, actions, hidden_out, out_row_stride,
+                     out_offset, value, reward, logits):
+    """Raw form used by the search engine: gathers from / scatters into the tree's hidden pool."""
+    B = actions.shape[0]
+    _lib.check(self.lib.mz_fc_recurrent_f32(
+        self.weights, B, _lib.ptr(hidden_in), int(in_row_stride), _lib.ptr(in_index),
+        _lib.ptr(actions), _lib.ptr(hidden_out), int(out_row_stride), int(out_offset),
+        _lib.ptr(value), _lib.ptr(reward), _lib.ptr(logits), _lib.current_stream()),
+               "mz_fc_recurrent_f32")
+
+  def _buffers(self, B):
+    dev = self.device
+    return (torch.empty((B, 1), dtype=torch.float32, device=dev),
+            torch.empty((B, 1), dtype=torch.float32, device=dev),
+            torch.empty((B, self.action_space), dtype=torch.float32, device=dev),
+            torch.empty((B, HIDDEN), dtype=torch.float32, device=dev))
+
+
+class FCSearch(object):
+  """BatchedMCTS specialised to FCNetwork: the network kernel reads parent hidden states straight
+  from the tree's hidden pool and writes the new state into it, every launch of one move is captured
+  in a CUDA graph, and inputs / outputs are staged through pinned host buffers for the end-to-end
+  (host buffers in, host buffers out) call."""
+
+  def __init__(self, config, fcnet, num_games, noise_frac=None, use_graph=True):
+    from .mcts import BatchedMCTS
+    self.net = fcnet
+    self.eng = BatchedMCTS(config, num_games, hidden_words=HIDDEN, device=fcnet.device)
+    G, A, dev = self.eng.G, self.eng.A, fcnet.device
+    self.G, self.A, self.S = G, A, self.eng.S
+    self.noise_frac = float(getattr(config, 'root_exploration_fraction', 0.25)
+                            if noise_frac is None else noise_frac)
+    self.use_graph = use_graph
+    self.graph = None
+    self.obs = torch.zeros((G, fcnet.input_dim), dtype=torch.float32, device=dev)
+    self.noise = torch.zeros((G, A), dtype=torch.float64, device=dev)
+    self.legal = torch.full((G,), (1 << A) - 1, dtype=torch.int64, device=dev).to(torch.int32)
+    self.to_play = torch.ones(G, dtype=torch.int8, device=dev)
+    self.temperature = torch.ones(G, dtype=torch.float64, device=dev)
+    self.uniforms = torch.zeros(G, dtype=torch.float64, device=dev)
+    self.root_logits = torch.zeros((G, A), dtype=torch.float32, device=dev)
+    self.init_value = torch.zeros(G, dtype=torch.float32, device=dev)
+    self.value = torch.zeros(G, dtype=torch.float32, device=dev)
+    self.reward = torch.zeros(G, dtype=torch.float32, device=dev)
+    self.logits = torch.zeros((G, A), dtype=torch.float32, device=dev)
+    self.hidden_f32 = self.eng.hidden.view(torch.float32)
+    self.use_noise = True
+    self.launches_per_move = 0
+    self.record = None  # (value [S,G], reward [S,G], logits [S,G,A]) when enable_record() was called
+
+  def enable_record(self):
+    """Keep every simulation's network outputs (and the engine's parent/action/depth trace) so that
+    a checker can replay the search with identical network outputs."""
+    S, G, A, dev = self.S, self.G, self.A, self.net.device
+    self.record = (torch.zeros((S, G), dtype=torch.float32, device=dev),
+                   torch.zeros((S, G), dtype=torch.float32, device=dev),
+                   torch.zeros((S, G, A), dtype=torch.float32, device=dev))
+    self.eng.enable_trace()
+    self.graph = None
+
+  def _enqueue(self):
+    """All launches of one move on the current stream."""
+    eng, net, S = self.eng, self.net, self.S
+    lib = net.lib
+    n = 0
+    stride = (S + 1) * HIDDEN
+    _lib.check(lib.mz_fc_initial_f32(net.weights, self.G, _lib.ptr(self.obs),
+                                     _lib.ptr(self.hidden_f32), stride, _lib.ptr(self.init_value),
+                                     _lib.ptr(self.root_logits), _lib.current_stream()),
+               "mz_fc_initial_f32")
+    eng.set_root(self.root_logits, self.legal, self.noise if self.use_noise else None,
+                 self.noise_frac, self.to_play, None)
+    eng.step(-1)
+    n += 3
+    for sim in range(S):
+      if self.record is not None:
+        v, r, l = self.record[0][sim], self.record[1][sim], self.record[2][sim]
+      else:
+        v, r, l = self.value, self.reward, self.logits
+      net.recurrent_into(self.hidden_f32, stride, eng.leaf_parent, eng.leaf_action, self.hidden_f32,
+                         stride, (sim + 1) * HIDDEN, v, r, l)
+      eng.step(sim, v, r, l)
+      n += 2
+    eng.root_stats()
+    eng.select_action(self.temperature, self.uniforms, self.legal)
+    n += 2
+    self.launches_per_move = n
+
+  def run(self):
+    """One move for all games with inputs already in the device staging buffers."""
+    if not self.use_graph:
+      self._enqueue()
+      return
+    if self.graph is None:
+      # warm up once outside capture (lazy module loading, cudaFuncSetAttribute)
+      self._enqueue()
+      torch.cuda.synchronize()
+      self.graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self.graph):
+        self._enqueue()
+    self.graph.replay()
+
+  # -- end-to-end call: host buffers in, host buffers out ----------------------------------------
+  def _pinned(self):
+    if getattr(self, '_h', None) is None:
+      G, A = self.G, self.A
+      pin = dict(pin_memory=True)
+      self._h = dict(
+          obs=torch.zeros((G, self.net.input_dim), dtype=torch.float32, **pin),
+          noise=torch.zeros((G, A), dtype=torch.float64, **pin),
+          uniforms=torch.zeros(G, dtype=torch.float64, **pin),
+          temperature=torch.ones(G, dtype=torch.float64, **pin),
+          actions=torch.zeros(G, dtype=torch.int32, **pin),
+          root_value=torch.zeros(G, dtype=torch.float64, **pin),
+          child_visits=torch.zeros((G, A), dtype=torch.float64, **pin),
+          init_value=torch.zeros(G, dtype=torch.float32, **pin))
+    return self._h
+
+  def search_host(self, obs, noise=None, uniforms=None, temperature=None):
+    """The per-move body of Actor.play_game (actors.py:131-153) for G games.
+
+    Inputs are HOST arrays (numpy or CPU tensors): obs [G, input_dim] float32, Dirichlet noise
+    [G, A] float64, uniforms [G] float64 (action sampling), temperature [G] float64.  Returns
+    pinned host tensors: actions [G] i32, root_value [G] f64, child_visits [G, A] f64, and the
+    initial-inference value [G] f32 (the priority seed `error = root.value() - value`,
+    actors.py:147).  Host->device and device->host copies are part of the call.
+    """
+    h = self._pinned()
+    def stage(name, src, dst):
+      if src is None:
+        return
+      t = src if torch.is_tensor(src) else torch.from_numpy(src)
+      if not t.is_pinned():
+        h[name].copy_(t)
+        t = h[name]
+      dst.copy_(t, non_blocking=True)
+    stage('obs', obs, self.obs)
+    stage('noise', noise, self.noise)
+    stage('uniforms', uniforms, self.uniforms)
+    stage('temperature', temperature, self.temperature)
+    self.use_noise = noise is not None or self.use_noise
+    self.run()
+    h['actions'].copy_(self.eng.actions, non_blocking=True)
+    h['root_value'].copy_(self.eng.root_value, non_blocking=True)
+    h['child_visits'].copy_(self.eng.child_visits, non_blocking=True)
+    h['init_value'].copy_(self.init_value, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h['actions'], h['root_value'], h['child_visits'], h['init_value']
+
+  def h2d_bytes(self):
+    return (self.obs.numel() * 4 + self.noise.numel() * 8 + self.uniforms.numel() * 8 +
+            self.temperature.numel() * 8)
+
+  def d2h_bytes(self):
+    return self.G * 4 + self.G * 8 + self.G * self.A * 8 + self.G * 4
+
+
+def random_state_dict(input_dim, action_space, value_bins=31, reward_bins=31, seed=1234):
+  """Random-init weights of the FCNetwork architecture under the reference's state-dict keys
+  (torch's default nn.Linear initialisation, LayerNorm = identity affine).  For benchmarks and
+  smoke tests: there is no network access for checkpoints."""
+  import torch.nn as nn
+  gen_state = torch.random.get_rng_state()
+  torch.manual_seed(seed)
+  dims = [('representation_head', 'out', input_dim, HIDDEN), ('value_head', 'value', HIDDEN, value_bins),
+          ('policy_head', 'policy', HIDDEN, action_space),
+          ('reward_head', 'reward', HIDDEN + action_space, reward_bins),
+          ('transition_head', 'out', HIDDEN + action_space, HIDDEN)]
+  sd = {}
+  for head, out_name, d_in, d_out in dims:
+    fc1, out = nn.Linear(d_in, _lib.FC_WIDTH), nn.Linear(_lib.FC_WIDTH, d_out)
+    sd[head + '.fc1.weight'], sd[head + '.fc1.bias'] = fc1.weight.detach(), fc1.bias.detach()
+    sd['%s.%s.weight' % (head, out_name)] = out.weight.detach()
+    sd['%s.%s.bias' % (head, out_name)] = out.bias.detach()
+  sd['LN.weight'], sd['LN.bias'] = torch.ones(HIDDEN), torch.zeros(HIDDEN)
+  torch.random.set_rng_state(gen_state)
+  return sd

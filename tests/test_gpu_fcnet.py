@@ -1,0 +1,86 @@
+"""GPU tests of the fused FCNetwork kernels against the reference's torch module (golden outputs
+from networks.FCNetwork on CPU, float32) and of the FC-specialised search against the oracle."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import load
+
+pytestmark = pytest.mark.gpu
+
+# float32 kernels vs torch float32 (different summation order): stated tolerance
+RTOL, ATOL = 1e-4, 2e-5
+
+
+def _net_from_golden(g, obs_dim, A):
+  from model_based_rl_b200.networks import FCNetwork
+  cfg = types.SimpleNamespace(value_support=[-15, 15], reward_support=[-15, 15], no_support=False,
+                              no_target_transform=False)
+  net = FCNetwork(obs_dim, A, "cuda", cfg)
+  net.load_weights({k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("w_")})
+  return net
+
+
+@pytest.mark.parametrize("name,obs_dim,A", [("atari18", 128, 18), ("ttt", 9, 9)])
+def test_fc_f32_matches_torch_reference(name, obs_dim, A):
+  g = load("fcnet_" + name)
+  net = _net_from_golden(g, obs_dim, A)
+  obs = torch.from_numpy(g["obs"]).cuda()
+  init = net.initial_inference(obs)
+  torch.cuda.synchronize()
+  assert init.reward == 0
+  assert np.allclose(init.hidden_state.cpu().numpy(), g["init_hidden"], rtol=RTOL, atol=ATOL)
+  assert np.allclose(init.policy_logits.cpu().numpy(), g["init_logits"], rtol=RTOL, atol=ATOL)
+  # value goes through h^-1 in float32, which amplifies 1-ulp differences to ~1e-4
+  assert np.allclose(init.value.cpu().numpy(), g["init_value"], rtol=1e-3, atol=1e-3)
+  rec = net.recurrent_inference(torch.from_numpy(g["init_hidden"]).cuda(), g["actions"].tolist())
+  torch.cuda.synchronize()
+  assert np.allclose(rec.hidden_state.cpu().numpy(), g["rec_hidden"], rtol=RTOL, atol=ATOL)
+  assert np.allclose(rec.policy_logits.cpu().numpy(), g["rec_logits"], rtol=RTOL, atol=ATOL)
+  assert np.allclose(rec.value.cpu().numpy(), g["rec_value"], rtol=1e-3, atol=1e-3)
+  assert np.allclose(rec.reward.cpu().numpy(), g["rec_reward"], rtol=1e-3, atol=1e-3)
+  # state dict round trip keeps the reference's keys
+  sd = net.get_weights()
+  assert set(sd) == {k[2:] for k in g if k.startswith("w_")}
+  assert np.array_equal(sd["LN.weight"].numpy(), g["w_LN.weight"])
+
+
+def test_fc_search_replays_bit_exact_in_oracle():
+  """Full move with the real FC network (C4 shape, fewer games): the engine records what the
+  network returned for every simulation; the oracle replays the search with those outputs."""
+  from model_based_rl_b200.networks import FCSearch
+  g = load("fcnet_atari18")
+  net = _net_from_golden(g, 128, 18)
+  G, A, S = 256, 18, 50
+  cfg = types.SimpleNamespace(num_simulations=S, action_space=A, two_players=False, discount=0.997,
+                              pb_c_base=19652, pb_c_init=1.25, init_value_score=0.0,
+                              known_bounds=[None, None], root_exploration_fraction=0.25)
+  rng = np.random.default_rng(7)
+  obs = rng.normal(size=(G, 128)).astype(np.float32)
+  noise = rng.dirichlet([0.25] * A, size=G)
+  u = rng.random(G)
+  temp = rng.choice([0.0, 0.25, 1.0], size=G)
+  for use_graph in (False, True):
+    fs = FCSearch(cfg, net, G, use_graph=use_graph)
+    fs.enable_record()
+    actions, root_value, child_visits, init_value = fs.search_host(obs, noise, u, temp)
+    if use_graph:  # replay the captured graph once more: results must be identical
+      a2 = actions.clone()
+      actions, root_value, child_visits, init_value = fs.search_host(obs, noise, u, temp)
+      assert torch.equal(a2, actions)
+    ocfg = oracle.make_cfg(S, A, False, 0.997)
+    want = oracle.search(ocfg, fs.root_logits.cpu().numpy(), noise=noise, noise_frac=0.25,
+                         rec_value=fs.record[0].cpu().numpy().T, rec_reward=fs.record[1].cpu().numpy().T,
+                         rec_logits=fs.record[2].cpu().numpy().transpose(1, 0, 2))
+    assert np.array_equal(fs.eng.trace[0].cpu().numpy().T, want["trace_parent"])
+    assert np.array_equal(fs.eng.trace[1].cpu().numpy().T, want["trace_action"])
+    assert np.array_equal(fs.eng.visits.cpu().numpy(), want["visits"])
+    assert np.array_equal(root_value.numpy(), want["root_value"])
+    cv = want["visits"] / want["visits"].sum(1, keepdims=True)
+    assert np.array_equal(child_visits.numpy(), cv)
+    for i in range(G):
+      assert int(actions[i]) == oracle.select_action(want["visits"][i], temp[i], u[i])
+    assert fs.launches_per_move == 2 * S + 5

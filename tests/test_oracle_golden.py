@@ -97,3 +97,55 @@ def test_transforms():
   rel = np.abs(inv - g["inverse"]) / np.maximum(np.abs(g["inverse"]), 1.0)
   assert np.mean(rel <= 1e-5) > 0.97
   assert rel.max() < 5e-4
+
+
+# ---- the pure-Python port (oracle/search_ref.py, oracle/fcnet_ref.py) used as the CPU baseline ----
+@pytest.mark.parametrize("case", ["ttt", "lunar", "atari18"])
+def test_python_port_matches_reference_golden(case):
+  import torch
+  from oracle.search_ref import FlatSearch
+  from model_based_rl_b200.testing import HashNetwork
+  from helpers import search_case_cfg
+  g = load("search_" + case)
+  cfg = search_case_cfg(g)
+  hv = g["hashnet"]
+  net = HashNetwork(cfg["action_space"], float(hv[0]), float(hv[1]), float(hv[2]), int(hv[3]))
+  for gi in range(4):
+    fs = FlatSearch(**cfg)
+    init = net.initial_inference(torch.tensor([[int(g["root_state"][gi])]], dtype=torch.int64))
+    legal = [a for a in range(cfg["action_space"]) if (int(g["legal"][gi]) >> a) & 1]
+    noise = g["noise"][gi, :len(legal)] if int(g["use_noise"]) else None
+    fs.setup_root(init, int(g["to_play"][gi]), legal, noise, float(g["noise_frac"]))
+    fs.run(net)
+    assert fs.root_visits() == list(g["visits"][gi])
+    assert fs.root_value() == g["root_value"][gi]
+    assert fs.minmax == tuple(g["minmax"][gi])
+    assert [t[0] for t in fs.trace] == list(g["trace_parent"][gi])
+    assert [t[1] for t in fs.trace] == list(g["trace_action"][gi])
+    assert fs.child_visits() == list(g["visits"][gi] / g["visits"][gi].sum())
+
+
+def test_python_port_select_action():
+  from oracle.search_ref import select_action
+  g = load("select_action")
+  for i in range(len(g["A"])):
+    A, mask = int(g["A"][i]), int(g["legal"][i])
+    legal = [a for a in range(A) if (mask >> a) & 1]
+    assert select_action(list(g["visits"][i]), legal, g["temperature"][i], g["u"][i]) == g["action"][i]
+
+
+@pytest.mark.parametrize("name,obs_dim,A", [("atari18", 128, 18), ("ttt", 9, 9)])
+def test_fcnet_ref_matches_reference_golden(name, obs_dim, A):
+  import torch
+  from oracle.fcnet_ref import FCNetworkRef
+  g = load("fcnet_" + name)
+  net = FCNetworkRef(obs_dim, A)
+  net.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("w_")})
+  with torch.inference_mode():
+    init = net.initial_inference(torch.from_numpy(g["obs"]))
+    rec = net.recurrent_inference(torch.from_numpy(g["init_hidden"]), g["actions"].tolist())
+  for got, want in ((init.hidden_state, "init_hidden"), (init.policy_logits, "init_logits"),
+                    (init.value, "init_value"), (rec.hidden_state, "rec_hidden"),
+                    (rec.policy_logits, "rec_logits"), (rec.value, "rec_value"),
+                    (rec.reward, "rec_reward")):
+    assert np.allclose(got.numpy(), g[want], rtol=1e-6, atol=1e-6), want
