@@ -158,6 +158,10 @@ int mz_select_action(int32_t num_games, int32_t num_actions, const int32_t* visi
                      const uint32_t* legal_mask, const double* temperature, const double* uniforms,
                      int32_t* actions, void* stream);
 
+/* Diagnostic: out[i] = the device's math.exp restatement applied to (double)x[i] (mcts.py:52).
+ * Used by the tests to check bit-compatibility with the host libm. */
+int mz_exp_f32(int64_t n, const float* x, double* out, void* stream);
+
 /* Debug / façade support: copy one game's tree into dense arrays (any output may be NULL):
  * prior [S+1][A] f64, child [S+1][A] i32, vsum [S+1] f64, visit [S+1] i32, reward [S+1] f32. */
 int mz_tree_export(const mz_tree* t, int32_t game, double* prior, int32_t* child, double* vsum,

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "mz_tree_step": (C.c_int, [C.POINTER(Tree), C.c_int32, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "mz_tree_root_stats": (C.c_int, [C.POINTER(Tree), _V, _V, _V, _V, _V]),
     "mz_select_action": (C.c_int, [C.c_int32, C.c_int32, _V, _V, _V, _V, _V, _V]),
+    "mz_exp_f32": (C.c_int, [C.c_int64, _V, _V, _V]),
     "mz_tree_export": (C.c_int, [C.POINTER(Tree), C.c_int32, _V, _V, _V, _V, _V, _V]),
     "mz_fc_initial_f32": (C.c_int, [C.POINTER(FcWeights), C.c_int32, _V, _V, C.c_int64, _V, _V, _V]),
     "mz_fc_recurrent_f32": (C.c_int, [C.POINTER(FcWeights), C.c_int32, _V, C.c_int64, _V, _V, _V,

@@ -446,6 +446,12 @@ __global__ void tree_export_kernel(mz_tree t, int game, double* prior, int32_t* 
   }
 }
 
+__global__ void exp_f32_kernel(long long n, const float* __restrict__ x, double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = mz_exp((double)x[i]);
+}
+
 int check_tree(const mz_tree* t) {
   if (!t || !t->games || !t->pb_c_table || !t->path || !t->path_len || !t->leaf_parent ||
       !t->leaf_action)
@@ -599,6 +605,14 @@ int mz_tree_export(const mz_tree* t, int32_t game, double* prior, int32_t* child
   if (rc) return rc;
   if (game < 0 || game >= t->num_games) return MZ_ERR_BAD_ARG;
   tree_export_kernel<<<4, 128, 0, (cudaStream_t)stream>>>(*t, game, prior, child, vsum, visit, reward);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+int mz_exp_f32(int64_t n, const float* x, double* out, void* stream) {
+  if (n < 0 || (n > 0 && (!x || !out))) return MZ_ERR_BAD_ARG;
+  if (n == 0) return MZ_OK;
+  exp_f32_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(n, x, out);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }
