@@ -39,6 +39,7 @@ extern "C" {
 #define MZ_CHILD_UNEXPANDED (-1)
 #define MZ_CHILD_ILLEGAL (-2)  /* action absent from root.children (illegal move) */
 #define MZ_GAME_HEADER_BYTES 32
+#define MZ_NODE_STATS_BYTES 24
 
 /* ------------------------------------------------------------------------------------------- */
 /* Tree: flat fixed-capacity node pools, one contiguous block per game (HBM, L2 resident).       */
@@ -46,10 +47,12 @@ extern "C" {
 /* game block  = header (32 B) | node record x (S + 1)            node n is expanded by sim n-1   */
 /* header      = f64 minimum | f64 maximum | i32 root_to_play | i32 reserved   (MinMaxStats,      */
 /*               mcts.py:6-25)                                                                    */
-/* node record = f64 value_sum | i32 visit_count | f32 reward | f64 prior[A] | i16 child[A] | pad */
-/*               (mcts.py:28-37; prior[a]/child[a] describe the child reached by action a, whose  */
-/*               own statistics live in node record child[a])                                     */
-/* node_bytes  = round_up(16 + 10 * A, 16);  game_bytes = round_up(32 + (S+1) * node_bytes, 128)  */
+/* node record = f64 value_sum | f64 q | i32 visit_count | f32 reward | f64 prior[A] | i16 child[A]*/
+/*               | pad  (mcts.py:28-37; prior[a]/child[a] describe the child reached by action a, */
+/*               whose own statistics live in node record child[a]; q = reward -/+ discount *     */
+/*               value(), the quantity backpropagate feeds to MinMaxStats (mcts.py:136-141) and   */
+/*               ucb_score normalises (mcts.py:120-121), cached at backup time)                   */
+/* node_bytes  = round_up(24 + 10 * A, 16);  game_bytes = round_up(32 + (S+1) * node_bytes, 128)  */
 /* ------------------------------------------------------------------------------------------- */
 typedef struct mz_tree {
   int32_t num_games;        /* G */
@@ -108,13 +111,14 @@ int mz_tree_set_root_priors(const mz_tree* t, const double* root_priors, const u
                             const int8_t* root_to_play, const uint32_t* root_hidden, void* stream);
 
 /*
- * One descent per game: the `while node.expanded(): select_child` loop of MCTS.run
+ * One descent per game for simulation `sim` (nodes 0..sim exist): the `while node.expanded():
+ * select_child` loop of MCTS.run
  * (mcts.py:87-92) with MCTS.select_child / ucb_score (mcts.py:104-124).  Writes path, path_len,
  * leaf_parent, leaf_action.  If gathered_hidden != NULL also copies the parent's hidden state to
  * gathered_hidden[G][hidden_words] (the argument of recurrent_inference, mcts.py:94-96).
  * trace_* (each [G], may be NULL) receive parent / action / depth for parity checks.
  */
-int mz_tree_select(const mz_tree* t, uint32_t* gathered_hidden, int32_t* trace_parent,
+int mz_tree_select(const mz_tree* t, int32_t sim, uint32_t* gathered_hidden, int32_t* trace_parent,
                    int32_t* trace_action, int32_t* trace_depth, void* stream);
 
 /*
@@ -130,7 +134,8 @@ int mz_tree_expand_backup(const mz_tree* t, int32_t sim, const float* value, con
 
 /*
  * Fused simulation boundary: expand + backup of simulation `sim` followed by the descent of
- * simulation sim + 1 (skipped when sim + 1 == S), one launch, the game block staged once.
+ * simulation sim + 1 (skipped when sim + 1 == S), one launch; the live part of every game block is
+ * staged in shared memory by one bulk async copy (cp.async.bulk) and both phases run on that image.
  * sim == -1 runs only the first descent.  Same arguments as the two calls above.
  */
 int mz_tree_step(const mz_tree* t, int32_t sim, const float* value, const float* reward,

@@ -71,7 +71,7 @@ _SIGNATURES = {
     "mz_fill_pb_c_table": (C.c_int, [C.c_int32, C.c_double, C.c_double, _V]),
     "mz_tree_set_root": (C.c_int, [C.POINTER(Tree), _V, _V, _V, C.c_double, _V, _V, _V]),
     "mz_tree_set_root_priors": (C.c_int, [C.POINTER(Tree), _V, _V, _V, _V, _V]),
-    "mz_tree_select": (C.c_int, [C.POINTER(Tree), _V, _V, _V, _V, _V]),
+    "mz_tree_select": (C.c_int, [C.POINTER(Tree), C.c_int32, _V, _V, _V, _V, _V]),
     "mz_tree_expand_backup": (C.c_int, [C.POINTER(Tree), C.c_int32, _V, _V, _V, _V, _V]),
     "mz_tree_step": (C.c_int, [C.POINTER(Tree), C.c_int32, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "mz_tree_root_stats": (C.c_int, [C.POINTER(Tree), _V, _V, _V, _V, _V]),

@@ -19,10 +19,13 @@ struct MzNode {
   uint8_t* p;
   int A;
   MZ_DEV double& vsum() const { return *reinterpret_cast<double*>(p); }
-  MZ_DEV int32_t& visit() const { return *reinterpret_cast<int32_t*>(p + 8); }
-  MZ_DEV float& reward() const { return *reinterpret_cast<float*>(p + 12); }
-  MZ_DEV double* prior() const { return reinterpret_cast<double*>(p + 16); }
-  MZ_DEV int16_t* child() const { return reinterpret_cast<int16_t*>(p + 16 + 8 * A); }
+  MZ_DEV double& q() const { return *reinterpret_cast<double*>(p + 8); }
+  MZ_DEV int32_t& visit() const { return *reinterpret_cast<int32_t*>(p + 16); }
+  MZ_DEV float& reward() const { return *reinterpret_cast<float*>(p + 20); }
+  MZ_DEV double* prior() const { return reinterpret_cast<double*>(p + MZ_NODE_STATS_BYTES); }
+  MZ_DEV int16_t* child() const {
+    return reinterpret_cast<int16_t*>(p + MZ_NODE_STATS_BYTES + 8 * A);
+  }
 };
 
 struct MzGame {
@@ -51,4 +54,44 @@ MZ_DEV double shfl_xor_f64(double v, int m) {
   lo = __shfl_xor_sync(MZ_FULL, lo, m, W);
   hi = __shfl_xor_sync(MZ_FULL, hi, m, W);
   return __hiloint2double(hi, lo);
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA unit, no tensor map) -----------------------------------
+MZ_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+MZ_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+MZ_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+MZ_DEV void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+MZ_DEV void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+MZ_DEV bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+MZ_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared, `bytes` multiple of 16, both addresses 16-byte aligned; completes on `bar`
+MZ_DEV void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
 }

@@ -58,20 +58,30 @@ MZ_DEV double group_priors(float logit, bool legal, int sum_mode) {
 
 // ------------------------------------------------------------------------------------------------
 // descent: while node.expanded(): select_child  (mcts.py:87-92, 104-124)
+//
+// `rd` is the image the group reads the tree from: the game block staged in shared memory by one
+// bulk async copy (STAGED) or the block in global memory.  Per level: one load of (prior, child)
+// for the lane's action, one dependent load of the child's cached (q, visit), one pb_c table
+// lookup, a binary64 multiply / divide / add, and a two-step redux argmax.
 // ------------------------------------------------------------------------------------------------
+MZ_DEV unsigned long long sortable_key(double x) {  // monotone map double -> u64 (no NaNs)
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return b ^ ((unsigned long long)((long long)b >> 63) | 0x8000000000000000ull);
+}
+
 template <int LPG>
-MZ_DEV void descend(const mz_tree& t, const MzGame& gm, bool valid, int sub, int16_t* path,
-                    int& out_depth, int& out_parent, int& out_action) {
+MZ_DEV void descend(const mz_tree& t, const MzGame& rd, bool valid, int sub, unsigned gmask,
+                    int16_t* path, int& out_depth, int& out_parent, int& out_action) {
   const int A = t.num_actions, SP1 = t.num_simulations + 1;
-  const bool two = t.two_players != 0;
-  const double disc = t.discount, init_score = t.init_value_score;
-  const double mn = gm.mn(), mx = gm.mx();
+  const double init_score = t.init_value_score;
+  const double mn = rd.mn(), mx = rd.mx();
+  const unsigned gshift = (threadIdx.x & 31u) & ~(unsigned)(LPG - 1);
   int node = 0, depth = 0, parent = 0, action = 0;
-  int N = gm.node(0).visit();
+  int N = rd.node(0).visit();
   bool done = !valid;
   if (valid && sub == 0) path[0] = 0;
   while (__any_sync(MZ_FULL, !done)) {
-    const MzNode nd = gm.node(node);
+    const MzNode nd = rd.node(node);
     const bool lane_ok = sub < A;
     double prior = 0.0;
     int ch = MZ_CHILD_ILLEGAL;
@@ -80,13 +90,11 @@ MZ_DEV void descend(const mz_tree& t, const MzGame& gm, bool valid, int sub, int
       ch = nd.child()[sub];
     }
     int n = 0;
-    double vs = 0.0;
-    float rw = 0.0f;
+    double q = 0.0;
     if (ch >= 0) {
-      const MzNode c = gm.node(ch);
+      const MzNode c = rd.node(ch);
       n = c.visit();
-      vs = c.vsum();
-      rw = c.reward();
+      q = c.q();  // reward + discount * (+/-)value(), cached by the last backup through the child
     }
     double score;
     if (N == 0) {  // mcts.py:105-108: an unvisited (root) node ranks children by prior
@@ -94,30 +102,23 @@ MZ_DEV void descend(const mz_tree& t, const MzGame& gm, bool valid, int sub, int
     } else {       // ucb_score mcts.py:115-124
       const double pb_c = __ldg(&t.pb_c_table[(size_t)N * SP1 + n]);
       const double prior_score = __dmul_rn(pb_c, prior);
-      double value_score = init_score;
-      if (n > 0) {
-        double value = __ddiv_rn(vs, (double)n);
-        if (two) value = -value;
-        value_score = mm_normalize(__dadd_rn((double)rw, __dmul_rn(disc, value)), mn, mx);
-      }
+      const double value_score = n > 0 ? mm_normalize(q, mn, mx) : init_score;
       score = __dadd_rn(prior_score, value_score);
     }
-    // max over (score, action) tuples: ties go to the larger action (mcts.py:106-112)
-    int best = (lane_ok && ch != MZ_CHILD_ILLEGAL) ? sub : -1;
-    double best_score = score;
-#pragma unroll
-    for (int m = LPG / 2; m > 0; m >>= 1) {
-      const double os = shfl_xor_f64<LPG>(best_score, m);
-      const int ob = __shfl_xor_sync(MZ_FULL, best, m, LPG);
-      const bool take = ob >= 0 && (best < 0 || os > best_score || (os == best_score && ob > best));
-      if (take) {
-        best_score = os;
-        best = ob;
-      }
-    }
+    // max over (score, action) tuples, ties -> larger action (mcts.py:106-112): compare the
+    // order-preserving 64-bit keys with two 32-bit redux steps, then take the highest lane.
+    const bool cand = lane_ok && ch != MZ_CHILD_ILLEGAL;
+    const unsigned long long key = cand ? sortable_key(score) : 0ull;
+    const unsigned hi = (unsigned)(key >> 32);
+    const unsigned hi_max = __reduce_max_sync(gmask, hi);
+    const unsigned lo = (cand && hi == hi_max) ? (unsigned)key : 0u;
+    const unsigned lo_max = __reduce_max_sync(gmask, lo);
+    const bool is_max = cand && hi == hi_max && (unsigned)key == lo_max;
+    const unsigned winners = (__ballot_sync(gmask, is_max) & gmask) >> gshift;
+    const int best = winners ? 31 - __clz(winners) : -1;
     const int src = best < 0 ? 0 : best;
-    const int ch_b = __shfl_sync(MZ_FULL, ch, src, LPG);
-    const int n_b = __shfl_sync(MZ_FULL, n, src, LPG);
+    const int ch_b = __shfl_sync(gmask, ch, src, LPG);
+    const int n_b = __shfl_sync(gmask, n, src, LPG);
     if (!done) {
       depth++;
       if (ch_b < 0) {  // child not expanded: this is the leaf
@@ -137,28 +138,38 @@ MZ_DEV void descend(const mz_tree& t, const MzGame& gm, bool valid, int sub, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// expand (mcts.py:47-55) + backpropagate (mcts.py:126-143)
+// expand (mcts.py:47-55) + backpropagate (mcts.py:126-143).  Reads from `rd`; every store goes to
+// the global block `gl` and, when the image is staged, to `rd` as well (the descent of the next
+// simulation runs on it in the same launch).
 // ------------------------------------------------------------------------------------------------
-template <int LPG>
-MZ_DEV void expand_backup(const mz_tree& t, const MzGame& gm, bool valid, int sub, int sim,
-                          float value_f, float reward_f, float logit, int16_t* path, int depth,
-                          int parent, int action) {
+template <int LPG, bool STAGED>
+MZ_DEV void expand_backup(const mz_tree& t, const MzGame& rd, const MzGame& gl, bool valid, int sub,
+                          int sim, float value_f, float reward_f, float logit, int16_t* path,
+                          int depth, int parent, int action) {
   const int A = t.num_actions;
   const bool two = t.two_players != 0;
   const double disc = t.discount;
   const int newn = sim + 1;
-  const MzNode nn = gm.node(newn);
   const float node_reward_new = (reward_f != 0.0f) ? reward_f : 0.0f;  // `if network_output.reward:`
 
   const double prior = group_priors<LPG>(logit, sub < A, t.prior_sum_mode);
   if (valid) {
+    const MzNode ng = gl.node(newn), ns = rd.node(newn);
     if (sub < A) {
-      nn.prior()[sub] = prior;
-      nn.child()[sub] = (int16_t)MZ_CHILD_UNEXPANDED;
+      ng.prior()[sub] = prior;
+      ng.child()[sub] = (int16_t)MZ_CHILD_UNEXPANDED;
+      if (STAGED) {
+        ns.prior()[sub] = prior;
+        ns.child()[sub] = (int16_t)MZ_CHILD_UNEXPANDED;
+      }
     }
     if (sub == 0) {
-      nn.reward() = node_reward_new;
-      gm.node(parent).child()[action] = (int16_t)newn;
+      ng.reward() = node_reward_new;
+      gl.node(parent).child()[action] = (int16_t)newn;
+      if (STAGED) {
+        ns.reward() = node_reward_new;
+        rd.node(parent).child()[action] = (int16_t)newn;
+      }
       path[depth] = (int16_t)newn;
     }
   }
@@ -173,7 +184,7 @@ MZ_DEV void expand_backup(const mz_tree& t, const MzGame& gm, bool valid, int su
     const int k = base + sub;
     const bool has = valid && k <= depth;
     const int nid = has ? (k == depth ? newn : (int)path[k]) : 0;
-    const MzNode nd = gm.node(nid);
+    const MzNode nd = rd.node(nid);
     double vs = 0.0;
     int vc = 0;
     float rw = 0.0f;
@@ -203,14 +214,22 @@ MZ_DEV void expand_backup(const mz_tree& t, const MzGame& gm, bool valid, int su
       const bool same = two ? (((depth - k) & 1) == 0) : true;
       vs = __dadd_rn(vs, same ? myval : -myval);
       vc += 1;
-      nd.vsum() = vs;
-      nd.visit() = vc;
-      if (k > 0) {
+      double new_q = 0.0;
+      if (k > 0) {  // mcts.py:136-141
         const double nv = __ddiv_rn(vs, (double)vc);
         const double dq = __dmul_rn(disc, nv);
-        const double new_q = two ? __dsub_rn((double)rw, dq) : __dadd_rn((double)rw, dq);
+        new_q = two ? __dsub_rn((double)rw, dq) : __dadd_rn((double)rw, dq);
         lmin = fmin(lmin, new_q);
         lmax = fmax(lmax, new_q);
+      }
+      const MzNode ng = gl.node(nid);
+      ng.vsum() = vs;
+      ng.q() = new_q;
+      ng.visit() = vc;
+      if (STAGED) {
+        nd.vsum() = vs;
+        nd.q() = new_q;
+        nd.visit() = vc;
       }
     }
   }
@@ -220,8 +239,14 @@ MZ_DEV void expand_backup(const mz_tree& t, const MzGame& gm, bool valid, int su
     lmax = fmax(lmax, shfl_xor_f64<LPG>(lmax, m));
   }
   if (valid && sub == 0) {
-    if (lmin < gm.mn()) gm.mn() = lmin;
-    if (lmax > gm.mx()) gm.mx() = lmax;
+    if (lmin < rd.mn()) {
+      gl.mn() = lmin;
+      if (STAGED) rd.mn() = lmin;
+    }
+    if (lmax > rd.mx()) {
+      gl.mx() = lmax;
+      if (STAGED) rd.mx() = lmax;
+    }
   }
 }
 
@@ -267,6 +292,7 @@ set_root_kernel(mz_tree t, const float* __restrict__ root_logits,
   }
   if (sub == 0) {
     root.vsum() = 0.0;
+    root.q() = 0.0;
     root.visit() = 0;
     root.reward() = 0.0f;
     gm.mn() = t.min_bound;  // MinMaxStats.reset mcts.py:79
@@ -278,27 +304,54 @@ set_root_kernel(mz_tree t, const float* __restrict__ root_logits,
                     root_hidden + (size_t)g * t.hidden_words, t.hidden_words, sub);
 }
 
-// sim == -1: descent only.  do_select == 0: expand+backup only.
-template <int LPG>
+// One launch per simulation boundary: [expand + backup of simulation `sim`] then [descent of
+// simulation sim + 1].  STAGED: the live part of each game block (header + nodes 0..sim) is brought
+// into shared memory with one cp.async.bulk (TMA unit) per game and both phases run on that image.
+// blockDim.x = LPG * games_per_block.
+template <int LPG, bool STAGED>
 __global__ void __launch_bounds__(kThreads)
-tree_step_kernel(mz_tree t, int sim, int do_backup, int do_select, const float* __restrict__ value,
-                 const float* __restrict__ reward, const float* __restrict__ logits,
-                 const uint32_t* __restrict__ new_hidden, uint32_t* __restrict__ gathered_hidden,
-                 int32_t* __restrict__ trace_parent, int32_t* __restrict__ trace_action,
-                 int32_t* __restrict__ trace_depth) {
-  const int gidx = (blockIdx.x * kThreads + threadIdx.x) / LPG;
+tree_step_kernel(mz_tree t, int sim, int do_backup, int do_select, int live_nodes, int stage_bytes,
+                 const float* __restrict__ value, const float* __restrict__ reward,
+                 const float* __restrict__ logits, const uint32_t* __restrict__ new_hidden,
+                 uint32_t* __restrict__ gathered_hidden, int32_t* __restrict__ trace_parent,
+                 int32_t* __restrict__ trace_action, int32_t* __restrict__ trace_depth) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int gpb = blockDim.x / LPG;
+  const int grp = threadIdx.x / LPG;
+  const int gidx = blockIdx.x * gpb + grp;
   const int sub = threadIdx.x & (LPG - 1);
   const bool valid = gidx < t.num_games;
   const int g = valid ? gidx : t.num_games - 1;
   const int A = t.num_actions, SP1 = t.num_simulations + 1, HW = t.hidden_words;
-  const MzGame gm{t.games + (size_t)g * t.game_bytes, t.node_bytes, A};
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned gmask = (LPG == 32 ? 0xffffffffu : ((1u << LPG) - 1u)) << (lane & ~(unsigned)(LPG - 1));
+  const MzGame gl{t.games + (size_t)g * t.game_bytes, t.node_bytes, A};
+  MzGame rd = gl;
   int16_t* path = t.path + (size_t)g * (t.num_simulations + 2);
+
+  if (STAGED) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)gpb * stage_bytes);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < gpb; ++i) mbar_init(&bars[i], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    uint8_t* image = smem + (size_t)grp * stage_bytes;
+    // nodes 0..live_nodes-1 exist before this launch (a backup creates node `sim + 1` in place)
+    const uint32_t live = MZ_GAME_HEADER_BYTES + (uint32_t)live_nodes * (uint32_t)t.node_bytes;
+    if (sub == 0) {
+      mbar_arrive_expect_tx(&bars[grp], live);
+      bulk_copy_g2s(image, gl.base, live, &bars[grp]);
+    }
+    mbar_wait(&bars[grp], 0);
+    rd = MzGame{image, t.node_bytes, A};
+  }
 
   if (do_backup) {
     const int depth = t.path_len[g], parent = t.leaf_parent[g], action = t.leaf_action[g];
     const float logit = sub < A ? logits[(size_t)g * A + sub] : 0.0f;
-    expand_backup<LPG>(t, gm, valid, sub, sim, value[g], reward[g], logit, path, depth, parent,
-                       action);
+    expand_backup<LPG, STAGED>(t, rd, gl, valid, sub, sim, value[g], reward[g], logit, path, depth,
+                               parent, action);
     if (valid && new_hidden && HW > 0)
       copy_words<LPG>(t.hidden + ((size_t)g * SP1 + sim + 1) * HW, new_hidden + (size_t)g * HW, HW,
                       sub);
@@ -306,7 +359,7 @@ tree_step_kernel(mz_tree t, int sim, int do_backup, int do_select, const float* 
   }
   if (do_select) {
     int depth, parent, action;
-    descend<LPG>(t, gm, valid, sub, path, depth, parent, action);
+    descend<LPG>(t, rd, valid, sub, gmask, path, depth, parent, action);
     if (valid) {
       if (sub == 0) {
         t.path_len[g] = depth;
@@ -472,15 +525,45 @@ int dispatch_lpg(int A, F&& f) {
   return f(std::integral_constant<int, 32>());
 }
 
-int launch_step(const mz_tree* t, int sim, int do_backup, int do_select, const float* value,
+constexpr int kMaxStageSmem = 200 * 1024;
+
+template <int LPG, bool STAGED>
+int set_smem_attr_once() {
+  static int rc = -1;
+  if (rc < 0) {
+    cudaError_t e = cudaFuncSetAttribute(tree_step_kernel<LPG, STAGED>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStageSmem + 1024);
+    rc = (int)e;
+  }
+  return rc;
+}
+
+int launch_step(const mz_tree* t, int sim, int live_nodes, int do_backup, int do_select, const float* value,
                 const float* reward, const float* logits, const uint32_t* new_hidden,
                 uint32_t* gathered_hidden, int32_t* tp, int32_t* ta, int32_t* td, void* stream) {
   return dispatch_lpg(t->num_actions, [&](auto lpg) {
     constexpr int LPG = decltype(lpg)::value;
-    const int gpb = kThreads / LPG;
-    const int grid = (t->num_games + gpb - 1) / gpb;
-    tree_step_kernel<LPG><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-        *t, sim, do_backup, do_select, value, reward, logits, new_hidden, gathered_hidden, tp, ta, td);
+    // image: header + nodes 0..sim+1 (the new node is built in place)
+    const int nodes = live_nodes + (do_backup ? 1 : 0);
+    const int stage_bytes = MZ_GAME_HEADER_BYTES + nodes * t->node_bytes;
+    int gpb = kThreads / LPG;
+    while (gpb > 1 && (size_t)gpb * stage_bytes > 96 * 1024) gpb >>= 1;
+    const bool staged = (size_t)gpb * stage_bytes <= kMaxStageSmem;
+    if (staged) {
+      int rc = set_smem_attr_once<LPG, true>();
+      if (rc) return rc;
+      const int grid = (t->num_games + gpb - 1) / gpb;
+      const size_t smem = (size_t)gpb * stage_bytes + sizeof(uint64_t) * gpb;
+      tree_step_kernel<LPG, true><<<grid, gpb * LPG, smem, (cudaStream_t)stream>>>(
+          *t, sim, do_backup, do_select, live_nodes, stage_bytes, value, reward, logits, new_hidden,
+          gathered_hidden, tp, ta, td);
+    } else {  // tree too large for shared memory: run on the global block directly
+      gpb = kThreads / LPG;
+      const int grid = (t->num_games + gpb - 1) / gpb;
+      tree_step_kernel<LPG, false><<<grid, gpb * LPG, 0, (cudaStream_t)stream>>>(
+          *t, sim, do_backup, do_select, live_nodes, 0, value, reward, logits, new_hidden,
+          gathered_hidden, tp, ta, td);
+    }
     MZ_LAUNCH_CHECK();
     return MZ_OK;
   });
@@ -490,7 +573,7 @@ int launch_step(const mz_tree* t, int sim, int do_backup, int do_select, const f
 
 extern "C" {
 
-int32_t mz_tree_node_bytes(int32_t A) { return (16 + 10 * A + 15) / 16 * 16; }
+int32_t mz_tree_node_bytes(int32_t A) { return (MZ_NODE_STATS_BYTES + 10 * A + 15) / 16 * 16; }
 
 int64_t mz_tree_game_bytes(int32_t S, int32_t A) {
   int64_t b = MZ_GAME_HEADER_BYTES + (int64_t)(S + 1) * mz_tree_node_bytes(A);
@@ -547,12 +630,13 @@ int mz_tree_set_root_priors(const mz_tree* t, const double* root_priors, const u
   });
 }
 
-int mz_tree_select(const mz_tree* t, uint32_t* gathered_hidden, int32_t* trace_parent,
+int mz_tree_select(const mz_tree* t, int32_t sim, uint32_t* gathered_hidden, int32_t* trace_parent,
                    int32_t* trace_action, int32_t* trace_depth, void* stream) {
   int rc = check_tree(t);
   if (rc) return rc;
-  return launch_step(t, -1, 0, 1, nullptr, nullptr, nullptr, nullptr, gathered_hidden, trace_parent,
-                     trace_action, trace_depth, stream);
+  if (sim < 0 || sim >= t->num_simulations) return MZ_ERR_BAD_ARG;
+  return launch_step(t, sim, sim + 1, 0, 1, nullptr, nullptr, nullptr, nullptr, gathered_hidden,
+                     trace_parent, trace_action, trace_depth, stream);
 }
 
 int mz_tree_expand_backup(const mz_tree* t, int32_t sim, const float* value, const float* reward,
@@ -560,8 +644,8 @@ int mz_tree_expand_backup(const mz_tree* t, int32_t sim, const float* value, con
   int rc = check_tree(t);
   if (rc) return rc;
   if (sim < 0 || sim >= t->num_simulations || !value || !reward || !logits) return MZ_ERR_BAD_ARG;
-  return launch_step(t, sim, 1, 0, value, reward, logits, new_hidden, nullptr, nullptr, nullptr,
-                     nullptr, stream);
+  return launch_step(t, sim, sim + 1, 1, 0, value, reward, logits, new_hidden, nullptr, nullptr,
+                     nullptr, nullptr, stream);
 }
 
 int mz_tree_step(const mz_tree* t, int32_t sim, const float* value, const float* reward,
@@ -572,8 +656,8 @@ int mz_tree_step(const mz_tree* t, int32_t sim, const float* value, const float*
   if (sim < -1 || sim >= t->num_simulations) return MZ_ERR_BAD_ARG;
   const int do_backup = sim >= 0, do_select = sim + 1 < t->num_simulations;
   if (do_backup && (!value || !reward || !logits)) return MZ_ERR_BAD_ARG;
-  return launch_step(t, sim, do_backup, do_select, value, reward, logits, new_hidden,
-                     gathered_hidden, trace_parent, trace_action, trace_depth, stream);
+  return launch_step(t, sim, sim + 1 < 1 ? 1 : sim + 1, do_backup, do_select, value, reward, logits,
+                     new_hidden, gathered_hidden, trace_parent, trace_action, trace_depth, stream);
 }
 
 int mz_tree_root_stats(const mz_tree* t, int32_t* visits, double* child_visits, double* root_value,

@@ -211,7 +211,7 @@ class BatchedMCTS(object):
   def select(self, sim, gather=True):
     tp, ta, td = self._trace_ptrs(sim)
     g = self.gathered if gather else None
-    _lib.check(self.lib.mz_tree_select(self.tree, _lib.ptr(g), tp, ta, td, self._stream()),
+    _lib.check(self.lib.mz_tree_select(self.tree, int(sim), _lib.ptr(g), tp, ta, td, self._stream()),
                "mz_tree_select")
 
   def expand_backup(self, sim, value, reward, logits, new_hidden=None):

@@ -73,6 +73,6 @@ def test_tree_geometry_and_pb_c_table_host_helpers():
 def test_bad_arguments_are_rejected_without_a_gpu():
   lib = _lib.load()
   t = _lib.Tree()
-  assert lib.mz_tree_select(C.byref(t), None, None, None, None, None) == -1
+  assert lib.mz_tree_select(C.byref(t), 0, None, None, None, None, None) == -1
   assert lib.mz_scalar_transform(-1, None, None, None) == -1
   assert lib.mz_select_action(0, 4, None, None, None, None, None, None) == -1
