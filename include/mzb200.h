@@ -212,6 +212,22 @@ int mz_fc_recurrent_f32(const mz_fc_weights* w, int32_t batch, const float* hidd
                         float* hidden_out, int64_t out_row_stride, int64_t out_offset, float* value,
                         float* reward, float* logits, void* stream);
 
+/*
+ * bf16 tensor-core path (tcgen05.mma, accumulators in TMEM, fp32 accumulation) of
+ * recurrent_inference.  The weights are first re-packed once per weight update into the
+ * shared-memory image the MMA consumes:
+ *   packed: mz_fc_tc_packed_bytes(A) bytes, tail: mz_fc_tc_tail_floats() floats (caller-allocated).
+ * mz_fc_recurrent_tc has the arguments of mz_fc_recurrent_f32 plus the packed buffers; `w` is only
+ * read for its integer fields.  Limits: A <= 32, value/reward bins <= 32.
+ */
+int64_t mz_fc_tc_packed_bytes(int32_t num_actions);
+int32_t mz_fc_tc_tail_floats(void);
+int mz_fc_tc_pack(const mz_fc_weights* w, void* packed, float* tail, void* stream);
+int mz_fc_recurrent_tc(const mz_fc_weights* w, const void* packed, const float* tail, int32_t batch,
+                       const float* hidden_in, int64_t in_row_stride, const int32_t* in_index,
+                       const int32_t* actions, float* hidden_out, int64_t out_row_stride,
+                       int64_t out_offset, float* value, float* reward, float* logits, void* stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* Scalar transforms and supports (config.py:27-68), float32 in torch's op order.                */
 /* ------------------------------------------------------------------------------------------- */

@@ -40,8 +40,13 @@ class FCNetwork(object):
   accepts_device_actions = True
   training = False
 
-  def __init__(self, input_dim, action_space, device, config):
+  def __init__(self, input_dim, action_space, device, config, precision='bf16'):
+    """precision: 'bf16' = tcgen05 tensor-core kernel for recurrent_inference (bf16 operands, fp32
+    accumulation); 'f32' = CUDA-core float32 kernel (reference precision, used for parity)."""
     _lib.require_cuda()
+    if precision not in ('bf16', 'f32'):
+      raise ValueError("precision must be 'bf16' or 'f32'")
+    self.precision = precision
     if getattr(config, 'no_support', False):
       raise NotImplementedError("no_support networks are not on the B200 path")
     self.lib = _lib.load()
@@ -88,6 +93,18 @@ class FCNetwork(object):
                                   self.reward_bins, self.value_min, self.reward_min,
                                   int(self.no_target_transform), 0,
                                   *[fields[n] for n in _lib.FcWeights._names])
+    self._tc_packed = self._tc_tail = None
+    if self.precision == 'bf16':
+      if self.action_space > 32 or self.value_bins > 32 or self.reward_bins > 32:
+        raise NotImplementedError("the tensor-core kernel supports A <= 32 and supports <= 32 bins; "
+                                  "use precision='f32'")
+      nbytes = int(self.lib.mz_fc_tc_packed_bytes(self.action_space))
+      self._tc_packed = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+      self._tc_tail = torch.zeros(int(self.lib.mz_fc_tc_tail_floats()), dtype=torch.float32,
+                                  device=self.device)
+      _lib.check(self.lib.mz_fc_tc_pack(self.weights, _lib.ptr(self._tc_packed),
+                                        _lib.ptr(self._tc_tail), _lib.current_stream()),
+                 "mz_fc_tc_pack")
 
   load_state_dict = load_weights
 
@@ -133,6 +150,13 @@ class FCNetwork(object):
                      out_offset, value, reward, logits):
     """Raw form used by the search engine: gathers from / scatters into the tree's hidden pool."""
     B = actions.shape[0]
+    if self.precision == 'bf16':
+      _lib.check(self.lib.mz_fc_recurrent_tc(
+          self.weights, _lib.ptr(self._tc_packed), _lib.ptr(self._tc_tail), B, _lib.ptr(hidden_in),
+          int(in_row_stride), _lib.ptr(in_index), _lib.ptr(actions), _lib.ptr(hidden_out),
+          int(out_row_stride), int(out_offset), _lib.ptr(value), _lib.ptr(reward), _lib.ptr(logits),
+          _lib.current_stream()), "mz_fc_recurrent_tc")
+      return
     _lib.check(self.lib.mz_fc_recurrent_f32(
         self.weights, B, _lib.ptr(hidden_in), int(in_row_stride), _lib.ptr(in_index),
         _lib.ptr(actions), _lib.ptr(hidden_out), int(out_row_stride), int(out_offset),

@@ -15,11 +15,11 @@ pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-4, 2e-5
 
 
-def _net_from_golden(g, obs_dim, A):
+def _net_from_golden(g, obs_dim, A, precision="f32"):
   from model_based_rl_b200.networks import FCNetwork
   cfg = types.SimpleNamespace(value_support=[-15, 15], reward_support=[-15, 15], no_support=False,
                               no_target_transform=False)
-  net = FCNetwork(obs_dim, A, "cuda", cfg)
+  net = FCNetwork(obs_dim, A, "cuda", cfg, precision=precision)
   net.load_weights({k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("w_")})
   return net
 
@@ -48,12 +48,42 @@ def test_fc_f32_matches_torch_reference(name, obs_dim, A):
   assert np.array_equal(sd["LN.weight"].numpy(), g["w_LN.weight"])
 
 
+@pytest.mark.parametrize("name,obs_dim,A", [("atari18", 128, 18), ("ttt", 9, 9)])
+@pytest.mark.parametrize("batch", [64, 129, 1000])
+def test_fc_tensor_core_matches_f32(name, obs_dim, A, batch):
+  """tcgen05 bf16 kernel vs the float32 kernel (and, at B=64, torch's float32 golden).
+  Tolerance: bf16 operands (8-bit mantissa) through four layers, fp32 accumulation."""
+  g = load("fcnet_" + name)
+  f32 = _net_from_golden(g, obs_dim, A, "f32")
+  tc = _net_from_golden(g, obs_dim, A, "bf16")
+  rng = np.random.default_rng(batch)
+  if batch == 64:
+    hidden = torch.from_numpy(g["init_hidden"]).cuda()
+    actions = torch.from_numpy(g["actions"]).cuda()
+  else:
+    hidden = torch.from_numpy(np.maximum(rng.normal(0.3, 0.7, size=(batch, 50)), 0).astype(np.float32)).cuda()
+    actions = torch.from_numpy(rng.integers(0, A, size=batch, dtype=np.int32)).cuda()
+  a = f32.recurrent_inference(hidden, actions)
+  b = tc.recurrent_inference(hidden, actions)
+  torch.cuda.synchronize()
+  for name_, x, y in (("hidden", a.hidden_state, b.hidden_state), ("logits", a.policy_logits, b.policy_logits),
+                      ("value", a.value, b.value), ("reward", a.reward, b.reward)):
+    x, y = x.cpu().numpy(), y.cpu().numpy()
+    assert np.isfinite(y).all(), name_
+    err = np.abs(x - y).max()
+    scale = max(1.0, np.abs(x).max())
+    assert err <= 3e-2 * scale, "%s: max abs err %g (scale %g)" % (name_, err, scale)
+  if batch == 64:
+    assert np.allclose(b.policy_logits.cpu().numpy(), g["rec_logits"], rtol=0, atol=3e-2)
+    assert np.allclose(b.hidden_state.cpu().numpy(), g["rec_hidden"], rtol=0, atol=3e-2)
+
+
 def test_fc_search_replays_bit_exact_in_oracle():
   """Full move with the real FC network (C4 shape, fewer games): the engine records what the
   network returned for every simulation; the oracle replays the search with those outputs."""
   from model_based_rl_b200.networks import FCSearch
   g = load("fcnet_atari18")
-  net = _net_from_golden(g, 128, 18)
+  net = _net_from_golden(g, 128, 18, "bf16")
   G, A, S = 256, 18, 50
   cfg = types.SimpleNamespace(num_simulations=S, action_space=A, two_players=False, discount=0.997,
                               pb_c_base=19652, pb_c_init=1.25, init_value_score=0.0,
