@@ -49,6 +49,10 @@ def parse():
   p.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
   p.add_argument("--no-cpu-baseline", action="store_true")
   p.add_argument("--no-graph", action="store_true")
+  p.add_argument("--streams", type=int, default=2,
+                 help="game slices run on separate CUDA streams inside the move graph")
+  p.add_argument("--precision", choices=["bf16", "f32"], default="bf16",
+                 help="network kernel: bf16 tcgen05 tensor cores (default) or float32 CUDA cores")
   p.add_argument("--ref-moves-per-step", type=int, default=2,
                  help="reference arm: moves each worker plays per step")
   return p.parse_args()
@@ -258,9 +262,9 @@ def run_b200(args):
 
   cfg = search_config(args)
   G, S, A = args.games, args.sims, args.actions
-  net = FCNetwork(args.obs_dim, A, dev, cfg)
+  net = FCNetwork(args.obs_dim, A, dev, cfg, precision=args.precision)
   net.load_weights(random_state_dict(args.obs_dim, A))
-  fs = FCSearch(cfg, net, G, use_graph=not args.no_graph)
+  fs = FCSearch(cfg, net, G, use_graph=not args.no_graph, num_streams=args.streams)
   obs, noise, uniforms, temperature = synthetic_inputs(args, rank, G)
   pin = lambda a: torch.from_numpy(a).pin_memory()
   h_obs, h_noise, h_u, h_t = pin(obs), pin(noise), pin(uniforms), pin(temperature)
@@ -308,8 +312,11 @@ def run_b200(args):
   clock_info = clocks.stop() if rank == 0 else None
 
   # per-kernel durations (CUDA events around each launch of one un-graphed move)
-  kern = kernel_breakdown(fs, torch)
-  depth_mean = float(fs.eng.path_len.float().mean().item())
+  fs1 = FCSearch(cfg, net, G, use_graph=False, num_streams=1)  # un-graphed, one stream
+  for name in ("obs", "noise", "uniforms", "temperature"):
+    getattr(fs1, name).copy_(getattr(fs, name))
+  kern = kernel_breakdown(fs1, torch)
+  del fs1
 
   t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
   if world > 1:
@@ -330,7 +337,8 @@ def run_b200(args):
     roof_tree = {"kernel": "tree_step_kernel", "bound": "hbm", "achieved": tree_bytes / tree_t / 1e9,
                  "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": None,
                  "algorithmic_bytes_per_launch": tree_bytes, "avg_launch_us": kern["tree_step_us"]}
-    roof_fc = {"kernel": "fc_recurrent_f32_kernel", "bound": "tensor", "achieved": fc_flops / fc_t / 1e12,
+    roof_fc = {"kernel": "fc_recurrent_tc_kernel" if args.precision == "bf16" else "fc_recurrent_f32_kernel",
+               "bound": "tensor", "achieved": fc_flops / fc_t / 1e12,
                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "traffic": None,
                "algorithmic_flops_per_launch": fc_flops, "avg_launch_us": kern["fc_recurrent_us"]}
     for r in (roof_tree, roof_fc):
@@ -340,13 +348,14 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64 (tree) / f32 (network)",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 (tree) / %s (network)" % ("bf16 tcgen05, f32 accumulate" if args.precision == "bf16" else "f32"),
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": fs.h2d_bytes(),
                 "d2h_bytes_per_step": fs.d2h_bytes(), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": fs.launches_per_move * args.steps,
         "clocks": clock_info, "roofline": dominant, "roofline_all": [roof_tree, roof_fc],
-        "kernel_share": kern, "mean_path_edges": depth_mean, "cuda_graph": not args.no_graph,
+        "kernel_share": kern, "cuda_graph": not args.no_graph, "streams": len(fs.lanes),
         "targets": targets,
     }
     if cpu_baseline is not None:
@@ -357,43 +366,34 @@ def run_b200(args):
 
 
 def kernel_breakdown(fs, torch):
-  """Average device time of the two per-simulation kernels, CUDA events on the launching stream."""
-  from model_based_rl_b200 import _lib
-  from model_based_rl_b200.networks import HIDDEN
-  eng, net, S = fs.eng, fs.net, fs.S
-  stride = (S + 1) * HIDDEN
+  """Average device time of the two per-simulation kernels: CUDA events on the launching stream
+  around every launch of one un-graphed move (pre-marshalled launch list, so the host keeps ahead
+  of the device)."""
+  ln = fs.lanes[0]
+  S = fs.S
+  plan = ln._plan(fs.use_noise, fs.noise_frac, torch.cuda.current_stream().cuda_stream)
   ev = lambda: torch.cuda.Event(enable_timing=True)
-  fc_pairs, tree_pairs, depth_sum = [], [], 0.0
+  depth_sum = torch.zeros((), dtype=torch.float64, device=ln.eng.path_len.device)
+  for i, (fn, args) in enumerate(plan):  # warm-up pass; also collects the mean path length
+    fn(*args)
+    if 2 <= i < 2 + 2 * S and (i - 2) % 2 == 0:
+      depth_sum += ln.eng.path_len.double().mean()
   torch.cuda.synchronize()
-  m0, m1 = ev(), ev()
-  m0.record()
-  _lib.check(net.lib.mz_fc_initial_f32(net.weights, fs.G, _lib.ptr(fs.obs), _lib.ptr(fs.hidden_f32),
-                                       stride, _lib.ptr(fs.init_value), _lib.ptr(fs.root_logits),
-                                       _lib.current_stream()), "init")
-  eng.set_root(fs.root_logits, fs.legal, fs.noise, fs.noise_frac, fs.to_play, None)
-  eng.step(-1)
-  depths = []
-  for sim in range(S):
-    depths.append(eng.path_len.clone())
-    a, b, c = ev(), ev(), ev()
-    a.record()
-    net.recurrent_into(fs.hidden_f32, stride, eng.leaf_parent, eng.leaf_action, fs.hidden_f32, stride,
-                       (sim + 1) * HIDDEN, fs.value, fs.reward, fs.logits)
-    b.record()
-    eng.step(sim, fs.value, fs.reward, fs.logits)
-    c.record()
-    fc_pairs.append((a, b))
-    tree_pairs.append((b, c))
-  eng.root_stats()
-  eng.select_action(fs.temperature, fs.uniforms, fs.legal)
-  m1.record()
+  marks = [ev() for _ in range(len(plan) + 1)]
+  marks[0].record()
+  for i, (fn, args) in enumerate(plan):
+    rc = fn(*args)
+    assert rc == 0, (fn.__name__, rc)
+    marks[i + 1].record()
   torch.cuda.synchronize()
-  fc_us = 1e3 * sum(a.elapsed_time(b) for a, b in fc_pairs) / S
-  tree_us = 1e3 * sum(a.elapsed_time(b) for a, b in tree_pairs) / S
-  move_us = 1e3 * m0.elapsed_time(m1)
-  mean_depth = float(torch.stack(depths).float().mean().item())
-  return {"fc_recurrent_us": fc_us, "tree_step_us": tree_us, "ungraphed_move_us": move_us,
-          "fc_share": fc_us * S / move_us, "tree_share": tree_us * S / move_us, "mean_depth": mean_depth}
+  dur = [marks[i].elapsed_time(marks[i + 1]) * 1e3 for i in range(len(plan))]
+  fc_us = sum(dur[3 + 2 * s] for s in range(S)) / S
+  tree_us = sum(dur[4 + 2 * s] for s in range(S)) / S
+  move_us = marks[0].elapsed_time(marks[-1]) * 1e3
+  mean_depth = float(depth_sum.item()) / S
+  return {"fc_recurrent_us": fc_us, "tree_step_us": tree_us, "fc_initial_us": dur[0],
+          "ungraphed_move_us": move_us, "fc_share": fc_us * S / move_us,
+          "tree_share": tree_us * S / move_us, "mean_depth": mean_depth}
 
 
 def bench_targets(torch, _lib, dev):

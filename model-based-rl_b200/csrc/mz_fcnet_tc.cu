@@ -7,14 +7,17 @@
 //
 // The 512-wide hidden layers are processed in 16 chunks of 128 features.  Per chunk c:
 //   MMA1(c): D1[c&1] (TMEM, 128 lanes x 128 cols) = A(128 x K) * W1c^T          (tcgen05.mma)
-//   EPI(c) : D1[c&1] -> registers (tcgen05.ld) -> +bias, relu, bf16 -> A2[c&1] in shared memory
-//   MMA2(c): D2 (TMEM) += A2[c&1](128 x 128) * W2c^T
+//   EPI(c) : D1[c&1] -> registers (tcgen05.ld) -> relu, bf16 -> A2[c&1] back in TMEM (tcgen05.st)
+//   MMA2(c): D2 (TMEM) += A2[c&1](128 x 128, TMEM operand) * W2c^T
+// Keeping the layer-2 A operand in TMEM matters: with both operands in shared memory every
+// M = 128 instruction is bound by the 4 KB A read (~140 cycles measured, independent of N), which
+// made the 128 narrow (N = 32 / 64) layer-2 instructions the bottleneck.
 // Weight chunks are pre-packed in global memory as the exact shared-memory image the MMA reads
 // (UMMA canonical K-major layout, no swizzle) and streamed through a 3-stage ring with one
 // cp.async.bulk per chunk; the pipeline is driven by mbarriers (TMA -> MMA -> epilogue -> MMA).
 //
-// Warp roles (192 threads): warp 0 = TMEM allocation + bulk-copy producer, warp 1 = MMA issuer
-// (one thread), warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+// Warp roles (320 threads): warp 0 = TMEM allocation + bulk-copy producer, warp 1 = MMA issuer
+// (one thread), warps 2..9 = two epilogue groups of four warps (TMEM lane quarter = warp % 4).
 //
 // Reference semantics: networks.py:31-34, 122-174 (FCNetwork), config.py:27-33.
 #include <cuda_bf16.h>
@@ -31,19 +34,24 @@ constexpr int ROWS = 128;            // rows (games) per CTA = UMMA M
 constexpr int CHUNK = 128;           // hidden features per chunk = UMMA N of the first layer
 constexpr int NCHUNK = 16;           // 4 heads x 4 chunks
 constexpr int K3 = 64;               // padded K of the prediction first layer
-constexpr int STAGES = 3;
-constexpr int TC_THREADS = 192;
+constexpr int STAGES = 4;
+constexpr int EPI_THREADS = 256;       // two groups of four epilogue warps
+constexpr int TC_THREADS = 64 + EPI_THREADS;
 constexpr int N_REW = 32, N_HID = 64, N_VAL = 32, N_POL = 32;  // padded second-layer widths
 constexpr int TMEM_COLS = 512;
-constexpr int COL_D1 = 0;            // 2 x 128 columns
-constexpr int COL_D2A = 256;         // reward / value logits (32)
-constexpr int COL_D2B = 288;         // next hidden (64) / policy logits (32)
+// TMEM column map (512 columns x 128 lanes x 32 bit)
+constexpr int COL_D1 = 0;            // 2 x 128: first-layer accumulators (double buffered)
+constexpr int COL_A2 = 256;          // 2 x 64 : relu(first layer) as packed bf16 = A operand of layer 2
+constexpr int COL_D2A = 384;         // 32     : reward / value logits
+constexpr int COL_D2B = 416;         // 64     : next hidden / policy logits
+constexpr int COL_A3 = 480;          // 32     : h' as packed bf16 = A operand of the prediction layer
 
 // tail parameter block (float): second-layer biases and LayerNorm affine
 constexpr int T_REW_B = 0, T_DYN_B = 32, T_LN_W = 96, T_LN_B = 160, T_VAL_B = 224, T_POL_B = 256;
 constexpr int TAIL_FLOATS = 288;
 
-struct ChunkGeom {  // byte geometry of one packed chunk: [W1 | W2 | bias1]
+struct ChunkGeom {  // byte geometry of one packed chunk: [W1 | W2]; the first-layer bias is folded
+                    // into W1 as the weight of a constant-1 input column (index kin)
   int k;            // K of the first layer (K1 or K3)
   int n2;           // N of the second layer
   int w1_bytes, w2_bytes, bytes;
@@ -56,7 +64,7 @@ __host__ __device__ inline ChunkGeom chunk_geom(int c, int k1) {
   g.n2 = head == 0 ? N_REW : (head == 1 ? N_HID : (head == 2 ? N_VAL : N_POL));
   g.w1_bytes = CHUNK * g.k * 2;
   g.w2_bytes = g.n2 * CHUNK * 2;
-  g.bytes = g.w1_bytes + g.w2_bytes + CHUNK * 4;
+  g.bytes = g.w1_bytes + g.w2_bytes;
   return g;
 }
 __host__ __device__ inline size_t chunk_offset(int c, int k1) {
@@ -109,6 +117,31 @@ MZ_DEV void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_
       : "memory");
 }
 
+// same with the A operand in tensor memory (packed 16-bit pairs, lane = row)
+MZ_DEV void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+MZ_DEV void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+MZ_DEV void tmem_st32(uint32_t addr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
 // 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread i <-> lane base + i)
 MZ_DEV void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
   asm volatile(
@@ -154,7 +187,14 @@ struct TcParams {
   float* hidden_out;
   long long out_row_stride, out_offset;
   float *value, *reward, *logits;
+  long long* trace;  // optional per-phase clock64() stamps of CTA 0 (diagnostics), or nullptr
 };
+
+// trace slots: [0,64) epilogue thread (row 0), [64,192) MMA thread, [192,224) producer
+#define TC_STAMP(slot)                                              \
+  do {                                                              \
+    if (p.trace && blockIdx.x == 0) p.trace[(slot)] = clock64();    \
+  } while (0)
 
 // softmax(logits + bias) . support, then h^-1, all in registers (one thread per row)
 MZ_DEV float support_to_scalar_regs(const uint32_t (&v)[32], const float* bias, int bins, int mn,
@@ -174,42 +214,82 @@ MZ_DEV float support_to_scalar_regs(const uint32_t (&v)[32], const float* bias, 
   }
   float num = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) num += (float)(mn + j) * __fdiv_rn(x[j], den);
+  for (int j = 0; j < 32; ++j) num = fmaf((float)(mn + j), x[j], num);
+  num = num / den;
   return no_tt ? num : mz_inverse_scalar_transform_f(num);
+}
+
+// immediate-predicate MMA wrappers: the issuing thread is a single dependent instruction stream
+// (~5 cycles per SASS instruction), so the per-MMA instruction count is what bounds the issue rate.
+template <bool ACC>
+MZ_DEV void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  if (ACC)
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+template <bool ACC>
+MZ_DEV void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+  if (ACC)
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc) : "memory");
+}
+
+// layer 2 of chunk c: D2 (+)= A2 (TMEM) * W2c^T, N2 compile time; descriptors advance by an add
+template <int N2>
+MZ_DEV void issue_mma2(uint32_t d2, uint32_t a_tm, uint32_t b_addr, bool first_chunk_of_head) {
+  constexpr uint32_t LBO = (N2 / 8) * 128;
+  const uint32_t idesc = make_idesc(N2);
+  const uint64_t bd = make_desc(b_addr, LBO, 128);
+  if (first_chunk_of_head) umma_ts<false>(d2, a_tm, bd, idesc);
+  else umma_ts<true>(d2, a_tm, bd, idesc);
+#pragma unroll
+  for (int ks = 1; ks < CHUNK / 16; ++ks)
+    umma_ts<true>(d2, a_tm + ks * 8, bd + (uint64_t)((ks * 2 * LBO) >> 4), idesc);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 64) {  // wall-clock entry time of every CTA (ns)
+    unsigned long long tns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+    p.trace[256 + 2 * blockIdx.x] = (long long)tns;
+  }
   const int k1 = p.k1;
   const int stage_bytes = stage_bytes_for(k1);
   // carve shared memory
-  uint8_t* sA1 = smem;                                  // [128 x k1] bf16
-  uint8_t* sA2 = sA1 + ROWS * k1 * 2;                   // 2 x [128 x 128] bf16
-  uint8_t* sA3 = sA2 + 2 * ROWS * CHUNK * 2;            // [128 x 64] bf16
-  uint8_t* sW = sA3 + ROWS * K3 * 2;                    // STAGES x stage_bytes
+  uint8_t* sA1 = smem;                                  // [128 x k1] bf16 (A of the dynamics layer)
+  uint8_t* sW = sA1 + ROWS * k1 * 2;                    // STAGES x stage_bytes
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + STAGES * stage_bytes);
-  uint64_t* w_full = bars;            // [3]
-  uint64_t* w_empty = bars + 3;       // [3]
-  uint64_t* d1_full = bars + 6;       // [2]
-  uint64_t* d1_empty = bars + 8;      // [2]
-  uint64_t* a2_full = bars + 10;      // [2]
-  uint64_t* a2_empty = bars + 12;     // [2]
-  uint64_t* a1_ready = bars + 14;
-  uint64_t* a3_ready = bars + 15;
-  uint64_t* d2_full = bars + 16;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* w_full = bars;            // [STAGES]
+  uint64_t* w_empty = bars + 4;       // [STAGES]
+  uint64_t* d1_full = bars + 8;       // [2]
+  uint64_t* d1_empty = bars + 10;     // [2]
+  uint64_t* a2_full = bars + 12;      // [2]
+  uint64_t* a2_empty = bars + 14;     // [2]
+  uint64_t* a1_ready = bars + 16;
+  uint64_t* a3_ready = bars + 17;
+  uint64_t* d2_full = bars + 18;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 19);
+  float* sTail = reinterpret_cast<float*>(bars + 20);   // second-layer biases + LayerNorm affine
+  for (int i = threadIdx.x; i < TAIL_FLOATS; i += TC_THREADS) sTail[i] = p.tail[i];
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d1_full[i], 1);
-      mbar_init(&d1_empty[i], 128);
-      mbar_init(&a2_full[i], 128);
+      mbar_init(&d1_empty[i], EPI_THREADS);
+      mbar_init(&a2_full[i], EPI_THREADS);
       mbar_init(&a2_empty[i], 1);
     }
-    mbar_init(a1_ready, 128);
-    mbar_init(a3_ready, 128);
+    mbar_init(a1_ready, EPI_THREADS);
+    mbar_init(a3_ready, EPI_THREADS / 2);
     mbar_init(d2_full, 1);
     mbar_fence_init();
   }
@@ -221,6 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  if (threadIdx.x == 32) TC_STAMP(0);
 
   if (warp == 0) {
     // ===== producer: stream the 16 weight chunks through the ring =====
@@ -230,6 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
         const int st = c % STAGES, n = c / STAGES;
         const ChunkGeom g = chunk_geom(c, k1);
         mbar_wait(&w_empty[st], (n & 1) ^ 1);
+        TC_STAMP(192 + c);
         mbar_arrive_expect_tx(&w_full[st], (uint32_t)g.bytes);
         bulk_copy_g2s(sW + st * stage_bytes, p.chunks + off, (uint32_t)g.bytes, &w_full[st]);
         off += g.bytes;
@@ -238,187 +320,234 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   } else if (warp == 1) {
     // ===== MMA issuer (single thread) =====
     if (lane == 0) {
-      const uint32_t a1_addr = smem_u32(sA1), a2_addr = smem_u32(sA2), a3_addr = smem_u32(sA3);
+      const uint32_t a1_addr = smem_u32(sA1);
       const uint32_t w_addr = smem_u32(sW);
       const uint32_t idesc1 = make_idesc(CHUNK);
+      const uint32_t w1_bytes_dyn = CHUNK * k1 * 2, w1_bytes_pred = CHUNK * K3 * 2;
+      constexpr uint64_t KSTEP = (uint64_t)((2 * (CHUNK / 8) * 128) >> 4);  // two K core-matrix columns
       auto mma2 = [&](int c) {  // D2 += A2[c&1] * W2c^T
         const int st = c % STAGES, head = c >> 2;
-        const ChunkGeom g = chunk_geom(c, k1);
         mbar_wait(&a2_full[c & 1], (c >> 1) & 1);
         tc_fence_after();
-        const uint32_t d2 = tmem + ((head & 1) ? COL_D2B : COL_D2A);
-        const uint32_t idesc2 = make_idesc(g.n2);
-        const uint32_t a_base = a2_addr + (c & 1) * (ROWS * CHUNK * 2);
-        const uint32_t b_base = w_addr + st * stage_bytes + g.w1_bytes;
-        const uint32_t lbo_b = (g.n2 >> 3) * 128;
-#pragma unroll 1
-        for (int ks = 0; ks < CHUNK / 16; ++ks) {
-          const uint64_t ad = make_desc(a_base + ks * 2 * (ROWS / 8) * 128, (ROWS / 8) * 128, 128);
-          const uint64_t bd = make_desc(b_base + ks * 2 * lbo_b, lbo_b, 128);
-          umma_bf16(d2, ad, bd, idesc2, ((c & 3) != 0 || ks != 0) ? 1u : 0u);
-        }
+        TC_STAMP(64 + 8 * c + 4);
+        const uint32_t a_tm = tmem + COL_A2 + (c & 1) * (CHUNK / 2);
+        const uint32_t b_addr = w_addr + st * stage_bytes + (c < 8 ? w1_bytes_dyn : w1_bytes_pred);
+        if (head == 1) issue_mma2<N_HID>(tmem + COL_D2B, a_tm, b_addr, (c & 3) == 0);
+        else issue_mma2<32>(tmem + ((head & 1) ? COL_D2B : COL_D2A), a_tm, b_addr, (c & 3) == 0);
+        TC_STAMP(64 + 8 * c + 5);
         tc_commit(&w_empty[st]);       // chunk c's weights are no longer needed
         tc_commit(&a2_empty[c & 1]);   // A2 buffer may be overwritten
         if (c == 7 || c == 15) tc_commit(d2_full);
+        TC_STAMP(64 + 8 * c + 6);
       };
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
         const int st = c % STAGES;
-        const ChunkGeom g = chunk_geom(c, k1);
         if (c == 8) mma2(7);  // the prediction's A operand depends on the dynamics output
+        TC_STAMP(64 + 8 * c + 0);
         mbar_wait(&w_full[st], (c / STAGES) & 1);
         if (c == 0) mbar_wait(a1_ready, 0);
         if (c == 8) mbar_wait(a3_ready, 0);
         mbar_wait(&d1_empty[c & 1], ((c >> 1) & 1) ^ 1);
         tc_fence_after();
+        TC_STAMP(64 + 8 * c + 1);
         const uint32_t d1 = tmem + COL_D1 + (c & 1) * CHUNK;
-        const uint32_t a_base = c < 8 ? a1_addr : a3_addr;
-        const uint32_t b_base = w_addr + st * stage_bytes;
+        const uint64_t bd = make_desc(w_addr + st * stage_bytes, (CHUNK / 8) * 128, 128);
+        if (c < 8) {  // dynamics: A = [h | onehot | 1] from shared memory, K = k1
+          const uint64_t ad = make_desc(a1_addr, (ROWS / 8) * 128, 128);
+          umma_ss<false>(d1, ad, bd, idesc1);
 #pragma unroll 1
-        for (int ks = 0; ks < g.k / 16; ++ks) {
-          const uint64_t ad = make_desc(a_base + ks * 2 * (ROWS / 8) * 128, (ROWS / 8) * 128, 128);
-          const uint64_t bd = make_desc(b_base + ks * 2 * (CHUNK / 8) * 128, (CHUNK / 8) * 128, 128);
-          umma_bf16(d1, ad, bd, idesc1, ks != 0 ? 1u : 0u);
+          for (int ks = 1; ks < k1 / 16; ++ks) umma_ss<true>(d1, ad + ks * KSTEP, bd + ks * KSTEP, idesc1);
+        } else {      // prediction: A = [h' | 1] from tensor memory, K = 64
+          umma_ts<false>(d1, tmem + COL_A3, bd, idesc1);
+#pragma unroll
+          for (int ks = 1; ks < K3 / 16; ++ks)
+            umma_ts<true>(d1, tmem + COL_A3 + ks * 8, bd + ks * KSTEP, idesc1);
         }
+        TC_STAMP(64 + 8 * c + 2);
         tc_commit(&d1_full[c & 1]);
+        TC_STAMP(64 + 8 * c + 3);
         if (c > 0 && c != 8) mma2(c - 1);
       }
       mma2(NCHUNK - 1);
     }
   } else {
-    // ===== epilogue warps: one thread per row =====
+    // ===== epilogue warps: two groups of four warps; within a group one thread per row.
+    // Both groups split every chunk's 128 accumulator columns; for the row-wise work group 0 takes
+    // the state path (gather, LayerNorm, value), group 1 the action / reward / policy path. =====
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;              // 0 or 1
     const int row = quarter * 32 + lane;
     const int g = blockIdx.x * ROWS + row;
     const bool live = g < p.batch;
     const int gc = live ? g : p.batch - 1;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    const int a_off = (row >> 3) * 128 + (row & 7) * 16;  // + k_block * (ROWS/8) * 128
+    const bool stamp = (row == 0 && grp == 0);
 
-    // --- A1 = bf16([h | onehot(action) | 0]) ---
-    {
+    // --- A1 = bf16([h (50) | onehot(action) (A) | 1 (bias input) | 0]) ---
+    if (grp == 0) {
+      // k < 48: the warp walks its 32 rows, 24 lanes load one float2 each (coalesced 192 B per row);
+      // all loads of a batch of 16 rows are issued before the first store
+      const float* src = p.hidden_in + (size_t)gc * p.in_row_stride +
+                         (p.in_index ? (size_t)p.in_index[gc] * H : 0);
+      const unsigned long long my_src = (unsigned long long)src;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        float2 f2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const unsigned long long rs = __shfl_sync(MZ_FULL, my_src, b * 16 + i);
+          f2[i] = lane < 24 ? *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(rs) + 2 * lane)
+                            : make_float2(0.0f, 0.0f);
+        }
+        if (lane < 24) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            *reinterpret_cast<uint32_t*>(sA1 + canon_off(quarter * 32 + b * 16 + i, 2 * lane, ROWS)) =
+                pack_bf16(f2[i].x, f2[i].y);
+        }
+      }
+    } else {
+      // k >= 48: the row's own thread (last two state features, one-hot action, constant 1)
       const float* src = p.hidden_in + (size_t)gc * p.in_row_stride +
                          (p.in_index ? (size_t)p.in_index[gc] * H : 0);
       const int act = p.actions[gc];
-      for (int kb = 0; kb < k1 / 8; ++kb) {
+      const float2 h4849 = *reinterpret_cast<const float2*>(src + 48);
+      const int kbias = H + p.num_actions;
+      const int a_off = (row >> 3) * 128 + (row & 7) * 16;
+      for (int kb = 6; kb < k1 / 8; ++kb) {
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int k = kb * 8 + j;
-          f[j] = k < H ? src[k] : ((k - H) == act ? 1.0f : 0.0f);
+          f[j] = k == 48 ? h4849.x : (k == 49 ? h4849.y : (((k - H) == act || k == kbias) ? 1.0f : 0.0f));
         }
         uint4 q = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
                              pack_bf16(f[6], f[7]));
         *reinterpret_cast<uint4*>(sA1 + kb * (ROWS / 8) * 128 + a_off) = q;
       }
-      fence_async_smem();
-      mbar_arrive(a1_ready);
     }
+    if (lane == 0) TC_STAMP(224 + warp);
+    fence_async_smem();
+    if (lane == 0) TC_STAMP(236 + warp);
+    mbar_arrive(a1_ready);
+    if (stamp) TC_STAMP(1);
 
-    uint32_t v[32];
-    auto hidden_epilogue = [&](int c) {  // D1[c&1] -> relu(x + b1) -> bf16 -> A2[c&1]
-      const int st = c % STAGES;
-      const ChunkGeom gm = chunk_geom(c, k1);
-      const float* bias = reinterpret_cast<const float*>(sW + st * stage_bytes + gm.w1_bytes + gm.w2_bytes);
-      mbar_wait(&w_full[st], (c / STAGES) & 1);  // bias lives in the chunk image (async-proxy write)
+    uint32_t v[32], v2[32];
+    auto hidden_epilogue = [&](int c) {  // D1[c&1] -> relu -> bf16 -> A2[c&1] (this group's 64 columns)
       mbar_wait(&d1_full[c & 1], (c >> 1) & 1);
       tc_fence_after();
       mbar_wait(&a2_empty[c & 1], ((c >> 1) & 1) ^ 1);
-      uint8_t* dst = sA2 + (c & 1) * (ROWS * CHUNK * 2) + a_off;
-#pragma unroll 1
-      for (int qd = 0; qd < CHUNK / 32; ++qd) {
-        tmem_ld32(lane_addr + COL_D1 + (c & 1) * CHUNK + qd * 32, v);
-        tmem_wait_ld();
+      if (stamp) TC_STAMP(4 + 2 * c);
+      const uint32_t d1 = lane_addr + COL_D1 + (c & 1) * CHUNK + grp * 64;
+      const uint32_t a2 = lane_addr + COL_A2 + (c & 1) * (CHUNK / 2) + grp * 32;
+      tmem_ld32(d1, v);
+      tmem_ld32(d1 + 32, v2);
+      tmem_wait_ld();
+      uint32_t pk[32];
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            f[j] = fmaxf(__uint_as_float(v[kb * 8 + j]) + bias[qd * 32 + kb * 8 + j], 0.0f);
-          uint4 q = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                               pack_bf16(f[6], f[7]));
-          *reinterpret_cast<uint4*>(dst + (qd * 4 + kb) * (ROWS / 8) * 128) = q;
-        }
+      for (int j = 0; j < 16; ++j) {
+        pk[j] = pack_bf16(fmaxf(__uint_as_float(v[2 * j]), 0.0f), fmaxf(__uint_as_float(v[2 * j + 1]), 0.0f));
+        pk[16 + j] = pack_bf16(fmaxf(__uint_as_float(v2[2 * j]), 0.0f), fmaxf(__uint_as_float(v2[2 * j + 1]), 0.0f));
       }
-      fence_async_smem();
-      mbar_arrive(&a2_full[c & 1]);
+      tmem_st32(a2, pk);
+      tmem_wait_st();
       tc_fence_before();
+      mbar_arrive(&a2_full[c & 1]);
       mbar_arrive(&d1_empty[c & 1]);
+      if (stamp) TC_STAMP(5 + 2 * c);
     };
 
     for (int c = 0; c < 8; ++c) hidden_epilogue(c);
 
-    // --- dynamics outputs: reward scalar, h' = relu(LN(.)) ---
+    // --- dynamics outputs: group 1 -> reward scalar, group 0 -> h' = relu(LN(.)) -> pool + A3 ---
     mbar_wait(d2_full, 0);
     tc_fence_after();
-    tmem_ld32(lane_addr + COL_D2A, v);
-    tmem_wait_ld();
-    const float rew = support_to_scalar_regs(v, p.tail + T_REW_B, p.reward_bins, p.reward_min, p.no_tt);
-    if (live) p.reward[g] = rew;
-    {
+    if (stamp) TC_STAMP(40);
+    if (grp == 1) {
+      tmem_ld32(lane_addr + COL_D2A, v);
+      tmem_wait_ld();
+      const float rew = support_to_scalar_regs(v, sTail + T_REW_B, p.reward_bins, p.reward_min, p.no_tt);
+      if (live) p.reward[g] = rew;
+    } else {
       float hbuf[64];
       tmem_ld32(lane_addr + COL_D2B, v);
+      tmem_ld32(lane_addr + COL_D2B + 32, v2);
       tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) hbuf[j] = __uint_as_float(v[j]) + p.tail[T_DYN_B + j];
-      tmem_ld32(lane_addr + COL_D2B + 32, v);
-      tmem_wait_ld();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) hbuf[32 + j] = __uint_as_float(v[j]) + p.tail[T_DYN_B + 32 + j];
-      float s = 0.0f;
-#pragma unroll
-      for (int j = 0; j < H; ++j) s += hbuf[j];
-      const float mean = s / (float)H;
-      float qv = 0.0f;
-#pragma unroll
-      for (int j = 0; j < H; ++j) {
-        const float d = hbuf[j] - mean;
-        qv = fmaf(d, d, qv);
+      for (int j = 0; j < 32; ++j) {
+        hbuf[j] = __uint_as_float(v[j]) + sTail[T_DYN_B + j];
+        hbuf[32 + j] = __uint_as_float(v2[j]) + sTail[T_DYN_B + 32 + j];
       }
-      const float rstd = 1.0f / sqrtf(qv / (float)H + 1e-5f);
+      // LayerNorm over the 50 state features; four partial sums keep the dependency chains short
+      float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 48; j += 4) { s0 += hbuf[j]; s1 += hbuf[j + 1]; s2 += hbuf[j + 2]; s3 += hbuf[j + 3]; }
+      const float mean = ((s0 + s1) + (s2 + s3) + hbuf[48] + hbuf[49]) / (float)H;
+      float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 48; j += 4) {
+        const float d0 = hbuf[j] - mean, d1_ = hbuf[j + 1] - mean, d2_ = hbuf[j + 2] - mean, d3 = hbuf[j + 3] - mean;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1_, d1_, q1); q2 = fmaf(d2_, d2_, q2); q3 = fmaf(d3, d3, q3);
+      }
+      {
+        const float d0 = hbuf[48] - mean, d1_ = hbuf[49] - mean;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1_, d1_, q1);
+      }
+      const float rstd = 1.0f / sqrtf(((q0 + q1) + (q2 + q3)) / (float)H + 1e-5f);
 #pragma unroll
       for (int j = 0; j < 64; ++j)
-        hbuf[j] = j < H ? fmaxf((hbuf[j] - mean) * rstd * p.tail[T_LN_W + j] + p.tail[T_LN_B + j], 0.0f)
-                        : 0.0f;
-      if (live) {
-        float* dsth = p.hidden_out + (size_t)g * p.out_row_stride + p.out_offset;
+        hbuf[j] = j < H ? fmaxf((hbuf[j] - mean) * rstd * sTail[T_LN_W + j] + sTail[T_LN_B + j], 0.0f)
+                        : (j == H ? 1.0f : 0.0f);  // column H feeds the folded first-layer bias
+      {
+        uint32_t pk[32];
 #pragma unroll
-        for (int j = 0; j < H; ++j) dsth[j] = hbuf[j];
+        for (int j = 0; j < 32; ++j) pk[j] = pack_bf16(hbuf[2 * j], hbuf[2 * j + 1]);
+        tmem_st32(lane_addr + COL_A3, pk);
+        tmem_wait_st();
       }
-#pragma unroll
-      for (int kb = 0; kb < K3 / 8; ++kb) {
-        uint4 q = make_uint4(pack_bf16(hbuf[kb * 8 + 0], hbuf[kb * 8 + 1]),
-                             pack_bf16(hbuf[kb * 8 + 2], hbuf[kb * 8 + 3]),
-                             pack_bf16(hbuf[kb * 8 + 4], hbuf[kb * 8 + 5]),
-                             pack_bf16(hbuf[kb * 8 + 6], hbuf[kb * 8 + 7]));
-        *reinterpret_cast<uint4*>(sA3 + kb * (ROWS / 8) * 128 + a_off) = q;
-      }
-      fence_async_smem();
       tc_fence_before();
       mbar_arrive(a3_ready);
+      if (stamp) TC_STAMP(41);
+      if (live) {  // after the hand-off: the store to the pool is off the critical path
+        float2* dsth = reinterpret_cast<float2*>(p.hidden_out + (size_t)g * p.out_row_stride + p.out_offset);
+#pragma unroll
+        for (int j = 0; j < H / 2; ++j) dsth[j] = make_float2(hbuf[2 * j], hbuf[2 * j + 1]);
+      }
     }
 
     for (int c = 8; c < NCHUNK; ++c) hidden_epilogue(c);
 
-    // --- prediction outputs: value scalar, policy logits ---
+    // --- prediction outputs: group 0 -> value scalar, group 1 -> policy logits ---
     mbar_wait(d2_full, 1);
     tc_fence_after();
-    tmem_ld32(lane_addr + COL_D2A, v);
-    tmem_wait_ld();
-    const float val = support_to_scalar_regs(v, p.tail + T_VAL_B, p.value_bins, p.value_min, p.no_tt);
-    if (live) p.value[g] = val;
-    tmem_ld32(lane_addr + COL_D2B, v);
-    tmem_wait_ld();
-    if (live) {
-      float* dl = p.logits + (size_t)g * p.num_actions;
+    if (stamp) TC_STAMP(42);
+    if (grp == 0) {
+      tmem_ld32(lane_addr + COL_D2A, v);
+      tmem_wait_ld();
+      const float val = support_to_scalar_regs(v, sTail + T_VAL_B, p.value_bins, p.value_min, p.no_tt);
+      if (live) p.value[g] = val;
+    } else {
+      tmem_ld32(lane_addr + COL_D2B, v);
+      tmem_wait_ld();
+      if (live) {
+        float* dl = p.logits + (size_t)g * p.num_actions;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < p.num_actions) dl[j] = __uint_as_float(v[j]) + p.tail[T_POL_B + j];
+        for (int j = 0; j < 32; ++j)
+          if (j < p.num_actions) dl[j] = __uint_as_float(v[j]) + sTail[T_POL_B + j];
+      }
     }
     tc_fence_before();
+    if (stamp) TC_STAMP(43);
   }
 
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(44);
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 64) {
+    unsigned long long tns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+    p.trace[256 + 2 * blockIdx.x + 1] = (long long)tns;
+  }
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
@@ -440,7 +569,7 @@ __global__ void fc_tc_pack_kernel(mz_fc_weights w, int k1, uint8_t* chunks, floa
     // W1 chunk: B operand [CHUNK features x K], element (n, k) = w1t[k][f0 + n]
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CHUNK * g.k; i += gridDim.x * blockDim.x) {
       const int n = i / g.k, k = i % g.k;
-      const float x = k < kin ? w1t[(size_t)k * W + f0 + n] : 0.0f;
+      const float x = k < kin ? w1t[(size_t)k * W + f0 + n] : (k == kin ? b1[f0 + n] : 0.0f);
       *reinterpret_cast<__nv_bfloat16*>(base + canon_off(n, k, CHUNK)) = __float2bfloat16_rn(x);
     }
     // W2 chunk: B operand [n2 outputs x CHUNK], element (o, k) = w2[o][f0 + k]
@@ -449,8 +578,6 @@ __global__ void fc_tc_pack_kernel(mz_fc_weights w, int k1, uint8_t* chunks, floa
       const float x = o < nout ? w2[(size_t)o * W + f0 + k] : 0.0f;
       *reinterpret_cast<__nv_bfloat16*>(base + g.w1_bytes + canon_off(o, k, g.n2)) = __float2bfloat16_rn(x);
     }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CHUNK; i += gridDim.x * blockDim.x)
-      reinterpret_cast<float*>(base + g.w1_bytes + g.w2_bytes)[i] = b1[f0 + i];
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TAIL_FLOATS; i += gridDim.x * blockDim.x) {
     float x = 0.0f;
@@ -464,16 +591,23 @@ __global__ void fc_tc_pack_kernel(mz_fc_weights w, int k1, uint8_t* chunks, floa
   }
 }
 
-int k1_for(int A) { return (H + A + 15) / 16 * 16; }
+int k1_for(int A) { return (H + A + 1 + 15) / 16 * 16; }  // state + one-hot + bias column
+
+long long* g_tc_trace = nullptr;
 
 size_t tc_smem_bytes(int k1) {
-  return (size_t)ROWS * k1 * 2 + 2 * ROWS * CHUNK * 2 + ROWS * K3 * 2 + (size_t)STAGES * stage_bytes_for(k1) +
-         17 * sizeof(uint64_t) + 16;
+  return (size_t)ROWS * k1 * 2 + (size_t)STAGES * stage_bytes_for(k1) +
+         20 * sizeof(uint64_t) + TAIL_FLOATS * sizeof(float);
 }
 
 }  // namespace
 
 extern "C" {
+
+int mz_debug_set_tc_trace(int64_t* device_buffer) {
+  g_tc_trace = (long long*)device_buffer;
+  return MZ_OK;
+}
 
 int64_t mz_fc_tc_packed_bytes(int32_t num_actions) {
   if (num_actions < 1 || num_actions > 32) return MZ_ERR_UNSUPPORTED;
@@ -522,6 +656,7 @@ int mz_fc_recurrent_tc(const mz_fc_weights* w, const void* packed, const float* 
   p.value = value;
   p.reward = reward;
   p.logits = logits;
+  p.trace = g_tc_trace;
   const size_t smem = tc_smem_bytes(p.k1);
   static bool attr = false;
   if (!attr) {

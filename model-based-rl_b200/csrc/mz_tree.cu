@@ -28,7 +28,7 @@ MZ_DEV double mm_normalize(double v, double mn, double mx) {
 // Node.expand priors mcts.py:52-55 for the lanes of one group: p_a = exp(logit_a) / sum(p) with the
 // sum evaluated like CPython's builtin sum() over the legal actions in ascending order.
 template <int LPG>
-MZ_DEV double group_priors(float logit, bool legal, int sum_mode) {
+MZ_DEV double group_priors(float logit, bool legal, int sum_mode, int A) {
   const double p = legal ? mz_exp((double)logit) : 0.0;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned group_shift = lane & ~(unsigned)(LPG - 1);
@@ -37,7 +37,7 @@ MZ_DEV double group_priors(float logit, bool legal, int sum_mode) {
   double f = 0.0, c = 0.0;
   bool first = true;
 #pragma unroll 1
-  for (int a = 0; a < LPG; ++a) {
+  for (int a = 0; a < A; ++a) {
     const double x = shfl_f64<LPG>(p, a);
     if (!((legal_bits >> a) & 1u)) continue;
     if (first) {
@@ -152,7 +152,7 @@ MZ_DEV void expand_backup(const mz_tree& t, const MzGame& rd, const MzGame& gl, 
   const int newn = sim + 1;
   const float node_reward_new = (reward_f != 0.0f) ? reward_f : 0.0f;  // `if network_output.reward:`
 
-  const double prior = group_priors<LPG>(logit, sub < A, t.prior_sum_mode);
+  const double prior = group_priors<LPG>(logit, sub < A, t.prior_sum_mode, A);
   if (valid) {
     const MzNode ng = gl.node(newn), ns = rd.node(newn);
     if (sub < A) {
@@ -198,8 +198,9 @@ MZ_DEV void expand_backup(const mz_tree& t, const MzGame& rd, const MzGame& gl, 
       }
     }
     double myval = 0.0;
+    const int jtop = min(LPG - 1, dmax - base);  // deepest position any group of the warp holds
 #pragma unroll 1
-    for (int j = LPG - 1; j >= 0; --j) {
+    for (int j = jtop; j >= 0; --j) {
       const int kk = base + j;
       const float rj = __shfl_sync(MZ_FULL, rw, j, LPG);
       if (valid && kk <= depth) {
@@ -277,7 +278,7 @@ set_root_kernel(mz_tree t, const float* __restrict__ root_logits,
     prior = legal ? root_priors[(size_t)g * A + sub] : 0.0;
   } else {
     const float logit = sub < A ? root_logits[(size_t)g * A + sub] : 0.0f;
-    prior = group_priors<LPG>(logit, legal, t.prior_sum_mode);
+    prior = group_priors<LPG>(logit, legal, t.prior_sum_mode, A);
   }
   if (noise && legal) {  // add_exploration_noise mcts.py:57-61; noise is dense over children
     const int j = __popc(lm & ((1u << sub) - 1u));

@@ -7,6 +7,7 @@ call (eval mode: value / reward are scalars after softmax-expectation + h^-1, co
 Training (backward, train-mode support logits) stays with the reference's torch module; weights
 move between the two through the state dict.
 """
+import ctypes as C
 from collections import OrderedDict, namedtuple
 
 import torch
@@ -171,22 +172,97 @@ class FCNetwork(object):
             torch.empty((B, HIDDEN), dtype=torch.float32, device=dev))
 
 
+class _Lane(object):
+  """One slice of the games with its own tree engine, network output buffers and CUDA stream."""
+
+  def __init__(self, config, fcnet, lo, hi, parent, stream):
+    from .mcts import BatchedMCTS
+    self.lo, self.hi, self.stream = lo, hi, stream
+    self.net = fcnet
+    self.eng = BatchedMCTS(config, hi - lo, hidden_words=HIDDEN, device=fcnet.device)
+    G, A, dev = hi - lo, self.eng.A, fcnet.device
+    # inputs / outputs are views into the parent's whole-batch staging tensors
+    for name in ('obs', 'noise', 'legal', 'to_play', 'temperature', 'uniforms', 'root_logits',
+                 'init_value'):
+      setattr(self, name, getattr(parent, name)[lo:hi])
+    self.eng.visits = parent.visits[lo:hi]
+    self.eng.child_visits = parent.child_visits[lo:hi]
+    self.eng.root_value = parent.root_value[lo:hi]
+    self.eng.minmax = parent.minmax[lo:hi]
+    self.eng.actions = parent.actions[lo:hi]
+    self.value = torch.zeros(G, dtype=torch.float32, device=dev)
+    self.reward = torch.zeros(G, dtype=torch.float32, device=dev)
+    self.logits = torch.zeros((G, A), dtype=torch.float32, device=dev)
+    self.hidden_f32 = self.eng.hidden.view(torch.float32)
+    self.record = None
+
+  def _plan(self, use_noise, noise_frac, stream_ptr):
+    """The launch list of one move as (C function, ctypes args) pairs, built once per (stream,
+    noise setting): at ~100 launches per move the Python-side argument marshalling would
+    otherwise dominate the un-graphed path."""
+    key = (bool(use_noise), float(noise_frac), stream_ptr, self.record is not None)
+    if getattr(self, '_plan_key', None) == key:
+      return self._plan_list
+    eng, net, S, G = self.eng, self.net, self.eng.S, self.hi - self.lo
+    lib, P, st = net.lib, _lib.ptr, C.c_void_p(stream_ptr)
+    stride = (S + 1) * HIDDEN
+    tree = C.byref(eng.tree)
+    plan = [(lib.mz_fc_initial_f32, (net.weights, G, P(self.obs), P(self.hidden_f32), stride,
+                                     P(self.init_value), P(self.root_logits), st)),
+            (lib.mz_tree_set_root, (tree, P(self.root_logits), P(self.legal),
+                                    P(self.noise) if use_noise else None, float(noise_frac),
+                                    P(self.to_play), None, st)),
+            (lib.mz_tree_step, (tree, -1, None, None, None, None, None) + eng._trace_ptrs(0) + (st,))]
+    bf16 = net.precision == 'bf16'
+    for sim in range(S):
+      if self.record is not None:
+        v, r, l = self.record[0][sim], self.record[1][sim], self.record[2][sim]
+      else:
+        v, r, l = self.value, self.reward, self.logits
+      tail = (G, P(self.hidden_f32), stride, P(eng.leaf_parent), P(eng.leaf_action),
+              P(self.hidden_f32), stride, (sim + 1) * HIDDEN, P(v), P(r), P(l), st)
+      if bf16:
+        plan.append((lib.mz_fc_recurrent_tc, (net.weights, P(net._tc_packed), P(net._tc_tail)) + tail))
+      else:
+        plan.append((lib.mz_fc_recurrent_f32, (net.weights,) + tail))
+      plan.append((lib.mz_tree_step, (tree, sim, P(v), P(r), P(l), None, None) +
+                   eng._trace_ptrs(sim + 1) + (st,)))
+    plan.append((lib.mz_tree_root_stats, (tree, P(eng.visits), P(eng.child_visits), P(eng.root_value),
+                                          P(eng.minmax), st)))
+    plan.append((lib.mz_select_action, (G, eng.A, P(eng.visits), P(self.legal), P(self.temperature),
+                                        P(self.uniforms), P(eng.actions), st)))
+    self._plan_key, self._plan_list = key, plan
+    return plan
+
+  def enqueue(self, use_noise, noise_frac):
+    plan = self._plan(use_noise, noise_frac, torch.cuda.current_stream().cuda_stream)
+    for fn, args in plan:
+      rc = fn(*args)
+      if rc:
+        _lib.check(rc, fn.__name__)
+    return len(plan)
+
+
 class FCSearch(object):
-  """BatchedMCTS specialised to FCNetwork: the network kernel reads parent hidden states straight
-  from the tree's hidden pool and writes the new state into it, every launch of one move is captured
-  in a CUDA graph, and inputs / outputs are staged through pinned host buffers for the end-to-end
+  """The per-move body of Actor.play_game (actors.py:131-153) for G games with FCNetwork.
+
+  The network kernel reads parent hidden states straight from the tree's hidden pool and writes the
+  new state into it.  The games are split into `num_streams` slices that run the same launch
+  sequence on their own CUDA streams, so one slice's tree kernel overlaps another slice's network
+  kernel (the network kernel only occupies G/128 SMs); every launch of one move is captured in one
+  CUDA graph, and inputs / outputs are staged through pinned host buffers for the end-to-end
   (host buffers in, host buffers out) call."""
 
-  def __init__(self, config, fcnet, num_games, noise_frac=None, use_graph=True):
-    from .mcts import BatchedMCTS
+  def __init__(self, config, fcnet, num_games, noise_frac=None, use_graph=True, num_streams=1):
     self.net = fcnet
-    self.eng = BatchedMCTS(config, num_games, hidden_words=HIDDEN, device=fcnet.device)
-    G, A, dev = self.eng.G, self.eng.A, fcnet.device
-    self.G, self.A, self.S = G, A, self.eng.S
+    G, A, dev = int(num_games), int(config.action_space), fcnet.device
+    self.G, self.A, self.S = G, A, int(config.num_simulations)
     self.noise_frac = float(getattr(config, 'root_exploration_fraction', 0.25)
                             if noise_frac is None else noise_frac)
     self.use_graph = use_graph
     self.graph = None
+    self.use_noise = True
+    self.launches_per_move = 0
     self.obs = torch.zeros((G, fcnet.input_dim), dtype=torch.float32, device=dev)
     self.noise = torch.zeros((G, A), dtype=torch.float64, device=dev)
     self.legal = torch.full((G,), (1 << A) - 1, dtype=torch.int64, device=dev).to(torch.int32)
@@ -195,50 +271,59 @@ class FCSearch(object):
     self.uniforms = torch.zeros(G, dtype=torch.float64, device=dev)
     self.root_logits = torch.zeros((G, A), dtype=torch.float32, device=dev)
     self.init_value = torch.zeros(G, dtype=torch.float32, device=dev)
-    self.value = torch.zeros(G, dtype=torch.float32, device=dev)
-    self.reward = torch.zeros(G, dtype=torch.float32, device=dev)
-    self.logits = torch.zeros((G, A), dtype=torch.float32, device=dev)
-    self.hidden_f32 = self.eng.hidden.view(torch.float32)
-    self.use_noise = True
-    self.launches_per_move = 0
-    self.record = None  # (value [S,G], reward [S,G], logits [S,G,A]) when enable_record() was called
+    self.visits = torch.zeros((G, A), dtype=torch.int32, device=dev)
+    self.child_visits = torch.zeros((G, A), dtype=torch.float64, device=dev)
+    self.root_value = torch.zeros(G, dtype=torch.float64, device=dev)
+    self.minmax = torch.zeros((G, 2), dtype=torch.float64, device=dev)
+    self.actions = torch.zeros(G, dtype=torch.int32, device=dev)
+    ns = max(1, min(int(num_streams), G))
+    bounds = [(G * i) // ns for i in range(ns + 1)]
+    self.lanes = []
+    for i in range(ns):
+      stream = None if ns == 1 else torch.cuda.Stream(device=dev)
+      self.lanes.append(_Lane(config, fcnet, bounds[i], bounds[i + 1], self, stream))
+    self.eng = self.lanes[0].eng  # single-lane convenience (tests, kernel breakdown)
 
+  # -- recording for parity checks -----------------------------------------------------------------
   def enable_record(self):
-    """Keep every simulation's network outputs (and the engine's parent/action/depth trace) so that
-    a checker can replay the search with identical network outputs."""
-    S, G, A, dev = self.S, self.G, self.A, self.net.device
-    self.record = (torch.zeros((S, G), dtype=torch.float32, device=dev),
-                   torch.zeros((S, G), dtype=torch.float32, device=dev),
-                   torch.zeros((S, G, A), dtype=torch.float32, device=dev))
-    self.eng.enable_trace()
+    """Keep every simulation's network outputs (and the engines' parent/action/depth traces) so
+    that a checker can replay the search with identical network outputs."""
+    dev = self.net.device
+    for lane in self.lanes:
+      g = lane.hi - lane.lo
+      lane.record = (torch.zeros((self.S, g), dtype=torch.float32, device=dev),
+                     torch.zeros((self.S, g), dtype=torch.float32, device=dev),
+                     torch.zeros((self.S, g, self.A), dtype=torch.float32, device=dev))
+      lane.eng.enable_trace()
     self.graph = None
 
+  @property
+  def record(self):
+    if self.lanes[0].record is None:
+      return None
+    return tuple(torch.cat([lane.record[i] for lane in self.lanes], dim=1) for i in range(3))
+
+  @property
+  def trace(self):
+    return tuple(torch.cat([lane.eng.trace[i] for lane in self.lanes], dim=1) for i in range(3))
+
+  # -- launch sequence -----------------------------------------------------------------------------
   def _enqueue(self):
-    """All launches of one move on the current stream."""
-    eng, net, S = self.eng, self.net, self.S
-    lib = net.lib
+    """All launches of one move; lanes fork from / join back into the current stream."""
+    if len(self.lanes) == 1:
+      self.launches_per_move = self.lanes[0].enqueue(self.use_noise, self.noise_frac)
+      return
+    main = torch.cuda.current_stream()
+    fork = torch.cuda.Event()
+    fork.record(main)
     n = 0
-    stride = (S + 1) * HIDDEN
-    _lib.check(lib.mz_fc_initial_f32(net.weights, self.G, _lib.ptr(self.obs),
-                                     _lib.ptr(self.hidden_f32), stride, _lib.ptr(self.init_value),
-                                     _lib.ptr(self.root_logits), _lib.current_stream()),
-               "mz_fc_initial_f32")
-    eng.set_root(self.root_logits, self.legal, self.noise if self.use_noise else None,
-                 self.noise_frac, self.to_play, None)
-    eng.step(-1)
-    n += 3
-    for sim in range(S):
-      if self.record is not None:
-        v, r, l = self.record[0][sim], self.record[1][sim], self.record[2][sim]
-      else:
-        v, r, l = self.value, self.reward, self.logits
-      net.recurrent_into(self.hidden_f32, stride, eng.leaf_parent, eng.leaf_action, self.hidden_f32,
-                         stride, (sim + 1) * HIDDEN, v, r, l)
-      eng.step(sim, v, r, l)
-      n += 2
-    eng.root_stats()
-    eng.select_action(self.temperature, self.uniforms, self.legal)
-    n += 2
+    for lane in self.lanes:
+      lane.stream.wait_event(fork)
+      with torch.cuda.stream(lane.stream):
+        n += lane.enqueue(self.use_noise, self.noise_frac)
+        done = torch.cuda.Event()
+        done.record(lane.stream)
+      main.wait_event(done)
     self.launches_per_move = n
 
   def run(self):
@@ -295,9 +380,9 @@ class FCSearch(object):
     stage('temperature', temperature, self.temperature)
     self.use_noise = noise is not None or self.use_noise
     self.run()
-    h['actions'].copy_(self.eng.actions, non_blocking=True)
-    h['root_value'].copy_(self.eng.root_value, non_blocking=True)
-    h['child_visits'].copy_(self.eng.child_visits, non_blocking=True)
+    h['actions'].copy_(self.actions, non_blocking=True)
+    h['root_value'].copy_(self.root_value, non_blocking=True)
+    h['child_visits'].copy_(self.child_visits, non_blocking=True)
     h['init_value'].copy_(self.init_value, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return h['actions'], h['root_value'], h['child_visits'], h['init_value']

@@ -93,8 +93,8 @@ def test_fc_search_replays_bit_exact_in_oracle():
   noise = rng.dirichlet([0.25] * A, size=G)
   u = rng.random(G)
   temp = rng.choice([0.0, 0.25, 1.0], size=G)
-  for use_graph in (False, True):
-    fs = FCSearch(cfg, net, G, use_graph=use_graph)
+  for use_graph, streams in ((False, 1), (True, 1), (True, 3)):
+    fs = FCSearch(cfg, net, G, use_graph=use_graph, num_streams=streams)
     fs.enable_record()
     actions, root_value, child_visits, init_value = fs.search_host(obs, noise, u, temp)
     if use_graph:  # replay the captured graph once more: results must be identical
@@ -105,12 +105,12 @@ def test_fc_search_replays_bit_exact_in_oracle():
     want = oracle.search(ocfg, fs.root_logits.cpu().numpy(), noise=noise, noise_frac=0.25,
                          rec_value=fs.record[0].cpu().numpy().T, rec_reward=fs.record[1].cpu().numpy().T,
                          rec_logits=fs.record[2].cpu().numpy().transpose(1, 0, 2))
-    assert np.array_equal(fs.eng.trace[0].cpu().numpy().T, want["trace_parent"])
-    assert np.array_equal(fs.eng.trace[1].cpu().numpy().T, want["trace_action"])
-    assert np.array_equal(fs.eng.visits.cpu().numpy(), want["visits"])
+    assert np.array_equal(fs.trace[0].cpu().numpy().T, want["trace_parent"])
+    assert np.array_equal(fs.trace[1].cpu().numpy().T, want["trace_action"])
+    assert np.array_equal(fs.visits.cpu().numpy(), want["visits"])
     assert np.array_equal(root_value.numpy(), want["root_value"])
     cv = want["visits"] / want["visits"].sum(1, keepdims=True)
     assert np.array_equal(child_visits.numpy(), cv)
     for i in range(G):
       assert int(actions[i]) == oracle.select_action(want["visits"][i], temp[i], u[i])
-    assert fs.launches_per_move == 2 * S + 5
+    assert fs.launches_per_move == streams * (2 * S + 5)
