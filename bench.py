@@ -263,7 +263,11 @@ def run_b200(args):
   cfg = search_config(args)
   G, S, A = args.games, args.sims, args.actions
   net = FCNetwork(args.obs_dim, A, dev, cfg, precision=args.precision)
-  net.load_weights(random_state_dict(args.obs_dim, A))
+  sd = {k: v.to(dev) for k, v in random_state_dict(args.obs_dim, A, seed=1234 + rank).items()}
+  if world > 1:  # learner -> self-play ranks weight hand-off over NCCL (rank 0 plays the learner)
+    from model_based_rl_b200 import parallel
+    parallel.broadcast_weights(sd, src=0)
+  net.load_weights(sd)
   fs = FCSearch(cfg, net, G, use_graph=not args.no_graph, num_streams=args.streams)
   obs, noise, uniforms, temperature = synthetic_inputs(args, rank, G)
   pin = lambda a: torch.from_numpy(a).pin_memory()
