@@ -291,6 +291,36 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
                      float* obs_out, int32_t* actions_out, float* t_rewards, float* t_values,
                      float* t_policies, float* value_support, float* reward_support, void* stream);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Prioritized-replay sum-tree in HBM (SumTree, replay_buffer.py:6-66): float64 array-embedded    */
+/* heap of 2*max_capacity-1 sums, leaves at [max_capacity-1, 2*max_capacity-1).  Batches of       */
+/* updates run in parallel but every node receives its float64 additions in batch order, so the   */
+/* sums are bit-identical to the reference's one-leaf-at-a-time loop.                             */
+/* ------------------------------------------------------------------------------------------- */
+/* SumTree.update (replay_buffer.py:35-41) applied to n (tree index, priority) pairs in order
+ * (PrioritizedReplay.update, replay_buffer.py:200-203).  scratch: [n] f64 workspace. */
+int mz_sumtree_update(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
+                      const double* priority, double* scratch, void* stream);
+/* SumTree.add (replay_buffer.py:19-33): update + buffer[slot] = (step, history) for the n sampled
+ * steps of one chunk; step i of the chunk sits at window position chunk_start + i.  The ring
+ * arithmetic that picks the slots (position / capacity growth) stays on the host.
+ *   slot_pos/slot_start [max_capacity] i64, slot_len [max_capacity] i32: where each slot's
+ *   (history, step) lives in the replay window (see mz_window). */
+int mz_sumtree_add(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
+                   const double* priority, int64_t chunk_start, int32_t chunk_len, int64_t* slot_pos,
+                   int64_t* slot_start, int32_t* slot_len, double* scratch, void* stream);
+/* The sampling half of sample_batch (replay_buffer.py:134-145, 160-162) for n rows:
+ *   value_b = random.uniform(seg*b, seg*(b+1)) with seg = total/n, computed on the device from the
+ *   host-drawn u01[b] = random.random() (same binary64 operations as CPython's uniform());
+ *   SumTree.get_leaf (replay_buffer.py:43-62) -> tree_idx[n], priority[n]; when slot_pos != NULL
+ *   also the row's window position / chunk start / chunk length (inputs of mz_build_targets);
+ *   when is_weights != NULL: (num_memories * priority/total) ** -beta, divided by its maximum. */
+int mz_sumtree_sample(const double* tree, int64_t max_capacity, int32_t n, const double* u01,
+                      const int64_t* slot_pos, const int64_t* slot_start, const int32_t* slot_len,
+                      int64_t num_memories, double beta, int64_t* tree_idx, double* priority,
+                      int64_t* pos, int64_t* chunk_start, int32_t* chunk_len, double* is_weights,
+                      void* stream);
+
 /* Library identification. */
 const char* mz_version(void);
 int32_t mz_compiled_arch(void); /* 100 for sm_100a */

@@ -92,6 +92,11 @@ _SIGNATURES = {
     "mz_support_to_scalar": (C.c_int, [C.c_int64, _V, C.c_int32, C.c_int32, C.c_int32, _V, _V]),
     "mz_build_targets": (C.c_int, [C.POINTER(Window), C.POINTER(TargetCfg), _V, _V, _V, _V, _V, _V,
                                    _V, _V, _V, _V, _V, _V]),
+    "mz_sumtree_update": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, _V, _V]),
+    "mz_sumtree_add": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_int64, C.c_int32, _V, _V, _V,
+                                 _V, _V]),
+    "mz_sumtree_sample": (C.c_int, [_V, C.c_int64, C.c_int32, _V, _V, _V, _V, C.c_int64, C.c_double,
+                                    _V, _V, _V, _V, _V, _V, _V]),
     "mz_version": (C.c_char_p, []),
     "mz_compiled_arch": (C.c_int32, []),
 }

@@ -1,0 +1,340 @@
+"""Prioritized replay with a device-resident window and fused target construction.
+
+Mirrors the reference's `PrioritizedReplay` (replay_buffer.py:69-210): `save_history(history,
+ignore, terminal)`, `sample_batch()` -> `((observations, actions, (target_rewards, target_values,
+target_policies)), idxs, is_weights)`, `update(idxs, errors)`, `size()`, `get_throughput()`,
+`add_initial_throughput()`; the random draws come from the same generators in the same order
+(`random.uniform` per row, `np.random.randint` per padded action), so with equal seeds and equal
+contents it samples the same rows as the reference.
+
+What is different underneath: trajectories live in HBM as a structure of arrays over window
+positions instead of pickled Python lists, the per-row Python loop of
+`sample_batch` + `insert_target` (replay_buffer.py:138-158, 165-198) is one launch of
+`mz_build_targets`, and the sum-tree lives in HBM too: stratified `get_leaf`, importance weights and
+batched priority updates are CUDA kernels (`mz_sumtree_*`) whose float64 sums stay bit-identical
+to the reference's one-leaf-at-a-time loop.
+`sample_batch_device()` returns CUDA tensors (optionally with h(x) + two-hot supports fused,
+learners.py:186-192) for a learner that consumes them in place.
+"""
+import random
+from collections import deque
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class RingCursor(object):
+  """The slot ring of the reference's SumTree.add (replay_buffer.py:19-33): which slot the next
+  memory goes to, the growing capacity (`window_step`) and `num_memories`.  Pure host integers."""
+
+  def __init__(self, max_capacity, capacity_step):
+    self.max_capacity = int(max_capacity)
+    self.capacity_step = int(capacity_step)
+    self.capacity = self.capacity_step
+    self.prev_capacity = 0
+    self.num_memories = 0
+    self.position = 0
+
+  def take(self, n):
+    """Slots of the next n memories, in order."""
+    slots = np.empty(n, np.int64)
+    for i in range(n):
+      pos = self.position
+      slots[i] = pos
+      if pos >= self.prev_capacity:
+        self.num_memories += 1
+      self.position = (pos + 1) % self.capacity
+      if self.position == 0:
+        self.prev_capacity = self.capacity
+        self.capacity = min(self.max_capacity, self.capacity + self.capacity_step)
+    return slots
+
+
+class ReplayIndex(object):
+  """Device-resident SumTree: float64 sums in HBM plus, per slot, where its (history, step) lives
+  in the replay window.  The host keeps only the ring cursor and which chunk owns each slot."""
+
+  def __init__(self, max_capacity, capacity_step, device):
+    self.lib = _lib.load()
+    self.device = device
+    self.max_capacity = int(max_capacity)
+    self.ring = RingCursor(max_capacity, capacity_step)
+    self.tree = torch.zeros(2 * self.max_capacity - 1, dtype=torch.float64, device=device)
+    self.slot_pos = torch.zeros(self.max_capacity, dtype=torch.int64, device=device)
+    self.slot_start = torch.zeros(self.max_capacity, dtype=torch.int64, device=device)
+    self.slot_len = torch.zeros(self.max_capacity, dtype=torch.int32, device=device)
+    self.slot_chunk = np.full(self.max_capacity, -1, np.int64)  # host: liveness of window chunks
+
+  @property
+  def num_memories(self):
+    return self.ring.num_memories
+
+  @property
+  def total_priority(self):
+    return float(self.tree[0].item())
+
+  def _stage(self, tree_idx, priorities):
+    idx = torch.from_numpy(np.ascontiguousarray(tree_idx, np.int64)).to(self.device)
+    pri = torch.from_numpy(np.ascontiguousarray(priorities, np.float64)).to(self.device)
+    return idx, pri, torch.empty_like(pri)
+
+  def add(self, priorities, chunk_id, chunk_start, chunk_len):
+    """SumTree.add (replay_buffer.py:19-33); returns the chunk ids whose slots were overwritten."""
+    n = len(priorities)
+    if n == 0:
+      return []
+    slots = self.ring.take(n)
+    old = self.slot_chunk[slots]
+    self.slot_chunk[slots] = chunk_id
+    idx, pri, scratch = self._stage(slots + self.max_capacity - 1, priorities)
+    _lib.check(self.lib.mz_sumtree_add(_lib.ptr(self.tree), self.max_capacity, n, _lib.ptr(idx),
+                                       _lib.ptr(pri), int(chunk_start), int(chunk_len),
+                                       _lib.ptr(self.slot_pos), _lib.ptr(self.slot_start),
+                                       _lib.ptr(self.slot_len), _lib.ptr(scratch),
+                                       _lib.current_stream()), "mz_sumtree_add")
+    return [int(c) for c in old if c >= 0]
+
+  def update(self, tree_idx, priorities):
+    """SumTree.update for a batch, in order (replay_buffer.py:200-203)."""
+    if len(tree_idx) == 0:
+      return
+    idx, pri, scratch = self._stage(tree_idx, priorities)
+    _lib.check(self.lib.mz_sumtree_update(_lib.ptr(self.tree), self.max_capacity, len(tree_idx),
+                                          _lib.ptr(idx), _lib.ptr(pri), _lib.ptr(scratch),
+                                          _lib.current_stream()), "mz_sumtree_update")
+
+  def sample(self, u01, beta, with_weights):
+    """Stratified get_leaf for len(u01) rows -> device tensors (tree idx, priority, window
+    position, chunk start, chunk length, is_weights or None)."""
+    n = len(u01)
+    dev = self.device
+    d_u = torch.from_numpy(np.ascontiguousarray(u01, np.float64)).to(dev)
+    idx = torch.empty(n, dtype=torch.int64, device=dev)
+    pri = torch.empty(n, dtype=torch.float64, device=dev)
+    pos = torch.empty(n, dtype=torch.int64, device=dev)
+    cstart = torch.empty(n, dtype=torch.int64, device=dev)
+    clen = torch.empty(n, dtype=torch.int32, device=dev)
+    isw = torch.empty(n, dtype=torch.float64, device=dev) if with_weights else None
+    _lib.check(self.lib.mz_sumtree_sample(_lib.ptr(self.tree), self.max_capacity, n, _lib.ptr(d_u),
+                                          _lib.ptr(self.slot_pos), _lib.ptr(self.slot_start),
+                                          _lib.ptr(self.slot_len), self.ring.num_memories,
+                                          float(beta), _lib.ptr(idx), _lib.ptr(pri), _lib.ptr(pos),
+                                          _lib.ptr(cstart), _lib.ptr(clen), _lib.ptr(isw),
+                                          _lib.current_stream()), "mz_sumtree_sample")
+    return idx, pri, pos, cstart, clen, isw
+
+
+class PrioritizedReplay(object):
+
+  def __init__(self, config, device=None, window_positions=None):
+    _lib.require_cuda()
+    self.lib = _lib.load()
+    self.device = _lib.normalize_device(device)
+    self.batch_size = int(config.batch_size)
+    self.beta_increment_per_sampling = config.beta_increment_per_sampling
+    self.epsilon = config.epsilon
+    self.alpha = config.alpha
+    self.beta = config.beta
+    self.num_unroll_steps = int(config.num_unroll_steps)
+    self.td_steps = int(config.td_steps)
+    self.discount = config.discount
+    n_steps = self.num_unroll_steps + self.td_steps
+    self.discounts = np.array([self.discount**n for n in range(n_steps)], dtype=np.float32)
+    self.action_space = int(config.action_space)
+    self.obs_space = tuple(config.obs_space)
+    self.obs_elems = int(np.prod(self.obs_space))
+    self.target_length = self.num_unroll_steps + 1
+    self.value_support = tuple(getattr(config, 'value_support', (-15, 15)))
+    self.reward_support = tuple(getattr(config, 'reward_support', (-15, 15)))
+    self.no_target_transform = bool(getattr(config, 'no_target_transform', False))
+
+    capacity = int(config.window_size)
+    step = capacity if getattr(config, 'window_step', None) is None else int(config.window_step)
+    self.index = ReplayIndex(capacity, step, self.device)
+    self.throughput = {'frames': 0, 'games': 0}
+    if getattr(config, 'seed', None) is not None:
+      np.random.seed(config.seed)
+      random.seed(config.seed + 1)
+
+    # window arena: chunks are appended in a ring; a chunk stays until all its slots are overwritten
+    overlap = self.num_unroll_steps + self.td_steps
+    chunk_new = int(getattr(config, 'max_history_length', 500))
+    if window_positions is None:
+      window_positions = int(capacity * (1.0 + overlap / max(1, chunk_new)) * 1.25) + 4 * (chunk_new + overlap)
+    self.P = int(window_positions)
+    self._obs_dtype = None
+    self.w_obs = None
+    dev = self.device
+    self.w_actions = torch.zeros(self.P, dtype=torch.int32, device=dev)
+    self.w_rewards = torch.zeros(self.P, dtype=torch.float32, device=dev)
+    self.w_to_play = torch.ones(self.P, dtype=torch.int8, device=dev)
+    self.w_root_values = torch.zeros(self.P, dtype=torch.float64, device=dev)
+    self.w_child_visits = torch.zeros((self.P, self.action_space), dtype=torch.float32, device=dev)
+    self.d_discounts = torch.from_numpy(self.discounts).to(dev)
+    self._head = 0
+    self._chunks = deque()      # (chunk id, start, length) in arena order
+    self._live = {}             # chunk id -> referencing slots
+    self._next_chunk = 0
+
+  # -- reference API -------------------------------------------------------------------------------
+  def add_initial_throughput(self, frames, games):
+    self.throughput['frames'] += frames
+    self.throughput['games'] += games
+
+  def get_priorities(self, errors):
+    return np.power((np.abs(errors) + self.epsilon), self.alpha)
+
+  def save_history(self, history, ignore=None, terminal=False):
+    """replay_buffer.py:113-122.  `history` has the HistorySlice fields (game.py:5-16)."""
+    if ignore is not None:
+      errors = history.errors[:-ignore]
+      priorities = self.get_priorities(errors) if errors else []
+    else:
+      priorities = self.get_priorities(history.errors)
+    n = len(history.root_values)
+    if n:
+      start = self._upload(history, n)
+      cid = self._next_chunk
+      self._next_chunk += 1
+      self._chunks.append((cid, start, n))
+      self._live[cid] = len(priorities)
+      for old in self.index.add(priorities, cid, start, n):
+        if old in self._live:
+          self._live[old] -= 1
+    self.throughput['frames'] += len(priorities)
+    if terminal:
+      self.throughput['games'] += 1
+
+  def sample_batch(self):
+    """replay_buffer.py:124-163 with numpy outputs like the reference: same draws from `random` and
+    `np.random` in the same order (one random() per row, one randint per padded action)."""
+    B, K, A = self.batch_size, self.num_unroll_steps, self.action_space
+    self._step_beta()
+    u01 = [random.random() for _ in range(B)]  # random.uniform(s1, s2) draws exactly one random()
+    idx, pri, pos, cstart, clen, _ = self.index.sample(u01, self.beta, with_weights=False)
+    h_pos, h_cs, h_cl = pos.cpu().numpy(), cstart.cpu().numpy(), clen.cpu().numpy()
+    # padding actions are drawn only where the slice is short (replay_buffer.py:149-152)
+    n_real = np.clip(h_cl - (h_pos - h_cs), 0, K)
+    pads = np.zeros((B, K), np.int32)
+    for b in np.nonzero(n_real < K)[0]:
+      for j in range(K - int(n_real[b])):
+        pads[b, j] = np.random.randint(A)
+    out = self._targets(pos, cstart, clen, torch.from_numpy(pads).to(self.device), False)
+    obs, actions, t_rewards, t_values, t_policies = [t.cpu().numpy() for t in out]
+    obs = obs.reshape((B,) + self.obs_space)
+    priorities = pri.cpu().numpy()
+    sampling_probabilities = priorities / self.index.total_priority
+    is_weights = np.power(self.index.num_memories * sampling_probabilities, -self.beta)
+    is_weights /= is_weights.max()
+    batch = (obs, actions.tolist(), (t_rewards, t_values, t_policies))
+    return batch, idx.cpu().numpy().tolist(), is_weights
+
+  def sample_batch_device(self, fuse_supports=True):
+    """Same sampling with nothing leaving the GPU and no host synchronisation: returns
+    ((obs, actions [B,K] i32, t_rewards, t_values, t_policies[, value_support, reward_support]),
+    idxs (int64 CUDA tensor, accepted by `update`), is_weights (float64 CUDA tensor)).  The padding
+    actions are drawn for every row up front (one `np.random.randint(A, size=(B, K))`), which
+    consumes the numpy stream differently from the reference; the sampled rows are the same."""
+    B, K, A = self.batch_size, self.num_unroll_steps, self.action_space
+    self._step_beta()
+    u01 = [random.random() for _ in range(B)]
+    idx, pri, pos, cstart, clen, isw = self.index.sample(u01, self.beta, with_weights=True)
+    pads = torch.from_numpy(np.random.randint(A, size=(B, K)).astype(np.int32)).to(self.device)
+    out = self._targets(pos, cstart, clen, pads, fuse_supports)
+    return tuple(out), idx, isw
+
+  def update(self, idxs, errors):
+    """replay_buffer.py:200-203.  `idxs` may be the list `sample_batch` returned or the CUDA tensor
+    of `sample_batch_device`; `errors` a numpy array (learners.py:183) or a CUDA tensor."""
+    if torch.is_tensor(errors):
+      errors = errors.detach().cpu().numpy()
+    if torch.is_tensor(idxs):
+      idxs = idxs.cpu().numpy()
+    priorities = self.get_priorities(np.asarray(errors))
+    self.index.update(np.asarray(idxs, np.int64), priorities)
+
+  def size(self):
+    return self.index.num_memories
+
+  def get_throughput(self):
+    return self.throughput
+
+  # -- internals -----------------------------------------------------------------------------------
+  def _step_beta(self):
+    if self.index.num_memories == 0:
+      raise _lib.MzError("sample_batch on an empty replay buffer")
+    if self.beta < 1:
+      self.beta = np.min([1., self.beta + self.beta_increment_per_sampling])
+
+  def _targets(self, d_pos, d_cs, d_cl, d_pads, fuse_supports):
+    B, K, A = self.batch_size, self.num_unroll_steps, self.action_space
+    dev = self.device
+    vb = self.value_support[1] - self.value_support[0] + 1
+    rb = self.reward_support[1] - self.reward_support[0] + 1
+    out = [torch.empty((B, self.obs_elems), dtype=torch.float32, device=dev),
+           torch.empty((B, K), dtype=torch.int32, device=dev),
+           torch.empty((B, K + 1), dtype=torch.float32, device=dev),
+           torch.empty((B, K + 1), dtype=torch.float32, device=dev),
+           torch.empty((B, K + 1, A), dtype=torch.float32, device=dev)]
+    if fuse_supports:
+      out += [torch.empty((B, K + 1, vb), dtype=torch.float32, device=dev),
+              torch.empty((B, K + 1, rb), dtype=torch.float32, device=dev)]
+    win = _lib.Window(A, self.obs_elems, int(self._obs_dtype == torch.uint8), 0,
+                      self.w_obs.data_ptr(), self.w_actions.data_ptr(), self.w_rewards.data_ptr(),
+                      self.w_to_play.data_ptr(), self.w_root_values.data_ptr(),
+                      self.w_child_visits.data_ptr())
+    cfg = _lib.TargetCfg(B, K, self.td_steps, int(fuse_supports), self.value_support[0],
+                         self.value_support[1], self.reward_support[0], self.reward_support[1],
+                         int(self.no_target_transform), 0, float(self.discount**self.td_steps),
+                         self.d_discounts.data_ptr(), None, None)
+    ptrs = [_lib.ptr(t) for t in out] + ([None, None] if not fuse_supports else [])
+    _lib.check(self.lib.mz_build_targets(win, cfg, _lib.ptr(d_pos), _lib.ptr(d_cs), _lib.ptr(d_cl),
+                                         _lib.ptr(d_pads), *ptrs, _lib.current_stream()),
+               "mz_build_targets")
+    return out
+
+  def _alloc(self, n):
+    """Ring allocation of n consecutive window positions.  A chunk stays readable as long as a
+    sum-tree slot refers to it (the reference keeps the history object alive through
+    SumTree.buffer); chunks without slots are recycled when the ring comes round."""
+    if n > self.P:
+      raise _lib.MzError("history of %d steps does not fit the replay window arena (%d)" % (n, self.P))
+    if self._head + n > self.P:
+      self._head = 0
+    lo, hi = self._head, self._head + n
+    keep = deque()
+    for cid, s, ln in self._chunks:
+      if s < hi and s + ln > lo:
+        if self._live.get(cid, 0) > 0:
+          raise _lib.MzError("replay window arena is full of live histories; construct "
+                             "PrioritizedReplay with a larger window_positions")
+        self._live.pop(cid, None)
+      else:
+        keep.append((cid, s, ln))
+    self._chunks = keep
+    self._head = hi
+    return lo
+
+  def _upload(self, history, n):
+    obs = np.stack([np.asarray(o) for o in history.observations[:n]]).reshape(n, -1)
+    dt = torch.uint8 if obs.dtype == np.uint8 else torch.float32
+    if self.w_obs is None:
+      self._obs_dtype = dt
+      self.w_obs = torch.zeros((self.P, self.obs_elems), dtype=dt, device=self.device)
+    elif dt != self._obs_dtype:
+      raise TypeError("observations changed dtype between histories")
+    if obs.shape[1] != self.obs_elems:
+      raise ValueError("observation has %d elements, config.obs_space says %d" % (obs.shape[1], self.obs_elems))
+    start = self._alloc(n)
+    sl = slice(start, start + n)
+    dev = self.device
+    self.w_obs[sl] = torch.from_numpy(np.ascontiguousarray(obs if dt == torch.uint8 else obs.astype(np.float32))).to(dev)
+    self.w_actions[sl] = torch.from_numpy(np.asarray(history.actions, np.int32)).to(dev)
+    self.w_rewards[sl] = torch.from_numpy(np.asarray(history.rewards, np.float64).astype(np.float32)).to(dev)
+    self.w_to_play[sl] = torch.from_numpy(np.asarray(history.to_play, np.int8)).to(dev)
+    self.w_root_values[sl] = torch.from_numpy(np.asarray(history.root_values, np.float64)).to(dev)
+    self.w_child_visits[sl] = torch.from_numpy(
+        np.asarray(history.child_visits, np.float64).reshape(n, self.action_space).astype(np.float32)).to(dev)
+    return start

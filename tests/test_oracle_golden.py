@@ -149,3 +149,53 @@ def test_fcnet_ref_matches_reference_golden(name, obs_dim, A):
                     (rec.policy_logits, "rec_logits"), (rec.value, "rec_value"),
                     (rec.reward, "rec_reward")):
     assert np.allclose(got.numpy(), g[want], rtol=1e-6, atol=1e-6), want
+
+
+# ---- prioritized-replay index (oracle/replay_ref.py) against the reference's SumTree --------------
+@pytest.mark.parametrize("case", REPLAY_CASES)
+def test_replay_index_oracle_matches_reference_golden(case):
+  from oracle import replay_ref
+  g = load("replay_" + case)
+  tree = replay_ref.SumTreeRef(int(g["window_size"]), int(g["window_step"]))
+  eps, alpha = float(g["epsilon"]), float(g["alpha"])
+  for h in range(int(g["n_hist"])):
+    errors = g["h%d_errors" % h].tolist()
+    if g["ignores"][h] >= 0:
+      errors = errors[:-int(g["ignores"][h])]
+    tree.add(replay_ref.get_priorities(errors, eps, alpha) if errors else [], h)
+  for b in range(int(g["n_batches"])):
+    assert tree.total_priority == g["b%d_total_priority" % b]
+    assert tree.num_memories == int(g["b%d_num_memories" % b])
+    picks, w = replay_ref.sample_indices(tree, int(g["batch_size"]), g["b%d_frac" % b],
+                                         float(g["b%d_beta_after" % b]))
+    assert [p[0] for p in picks] == g["b%d_idxs" % b].tolist()
+    assert [p[2] for p in picks] == g["b%d_steps" % b].tolist()
+    assert [p[3] for p in picks] == g["b%d_hist" % b].tolist()
+    assert np.array_equal(np.array([p[1] for p in picks]), g["b%d_priorities" % b])
+    assert np.array_equal(w, g["b%d_is_weights" % b])
+    pri = replay_ref.get_priorities(g["b%d_update_errors" % b], eps, alpha)
+    for idx, p in zip(g["b%d_idxs" % b], pri):
+      tree.update(int(idx), p)
+    assert np.array_equal(tree.tree, g["b%d_tree_after_update" % b])
+
+
+@pytest.mark.parametrize("case", REPLAY_CASES)
+def test_ring_cursor_matches_reference_golden(case):
+  """Host ring arithmetic of the product facade (no GPU needed) vs the reference's num_memories and
+  sampled slots."""
+  from oracle import replay_ref
+  from model_based_rl_b200.replay_buffer import RingCursor
+  g = load("replay_" + case)
+  ring = RingCursor(int(g["window_size"]), int(g["window_step"]))
+  ref = replay_ref.SumTreeRef(int(g["window_size"]), int(g["window_step"]))
+  for h in range(int(g["n_hist"])):
+    n = len(g["h%d_errors" % h]) - max(0, int(g["ignores"][h]))
+    n = max(n, 0)
+    before = ref.position
+    ref.add([1.0] * n, h)
+    slots = ring.take(n)
+    if n:
+      assert slots[0] == before
+    assert (ring.position, ring.capacity, ring.prev_capacity, ring.num_memories) == \
+        (ref.position, ref.capacity, ref.prev_capacity, ref.num_memories)
+  assert ring.num_memories == int(g["b0_num_memories"])
