@@ -47,7 +47,7 @@ extern "C" {
 /* game block  = header (32 B) | node record x (S + 1)            node n is expanded by sim n-1   */
 /* header      = f64 minimum | f64 maximum | i32 root_to_play | i32 reserved   (MinMaxStats,      */
 /*               mcts.py:6-25)                                                                    */
-/* node record = f64 value_sum | f64 q | i32 visit_count | f32 reward | f64 prior[A] | i16 child[A]*/
+/* node record = f64 q | i32 visit_count | f32 reward | f64 value_sum | f64 prior[A] | i16 child[A]*/
 /*               | pad  (mcts.py:28-37; prior[a]/child[a] describe the child reached by action a, */
 /*               whose own statistics live in node record child[a]; q = reward -/+ discount *     */
 /*               value(), the quantity backpropagate feeds to MinMaxStats (mcts.py:136-141) and   */
@@ -320,6 +320,12 @@ int mz_sumtree_sample(const double* tree, int64_t max_capacity, int32_t n, const
                       int64_t num_memories, double beta, int64_t* tree_idx, double* priority,
                       int64_t* pos, int64_t* chunk_start, int32_t* chunk_len, double* is_weights,
                       void* stream);
+
+/* Diagnostics: compares the constant-divisor division used by the descent's MinMax normalisation
+ * with IEEE division on blocks*256*per_thread pseudo-random operand pairs; adds the number of
+ * differing results to *mismatches and the number of pairs checked to *tested (device u64). */
+int mz_debug_div_check(uint64_t seed, int32_t blocks, int32_t per_thread, uint64_t* mismatches,
+                       uint64_t* tested, void* stream);
 
 /* Library identification. */
 const char* mz_version(void);

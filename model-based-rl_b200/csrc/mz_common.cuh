@@ -18,10 +18,10 @@
 struct MzNode {
   uint8_t* p;
   int A;
-  MZ_DEV double& vsum() const { return *reinterpret_cast<double*>(p); }
-  MZ_DEV double& q() const { return *reinterpret_cast<double*>(p + 8); }
-  MZ_DEV int32_t& visit() const { return *reinterpret_cast<int32_t*>(p + 16); }
-  MZ_DEV float& reward() const { return *reinterpret_cast<float*>(p + 20); }
+  MZ_DEV double& q() const { return *reinterpret_cast<double*>(p); }
+  MZ_DEV int32_t& visit() const { return *reinterpret_cast<int32_t*>(p + 8); }
+  MZ_DEV float& reward() const { return *reinterpret_cast<float*>(p + 12); }
+  MZ_DEV double& vsum() const { return *reinterpret_cast<double*>(p + 16); }
   MZ_DEV double* prior() const { return reinterpret_cast<double*>(p + MZ_NODE_STATS_BYTES); }
   MZ_DEV int16_t* child() const {
     return reinterpret_cast<int16_t*>(p + MZ_NODE_STATS_BYTES + 8 * A);

@@ -94,6 +94,12 @@ MZ_DEV void tmem_dealloc(uint32_t addr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols)
                : "memory");
 }
+// one lane of a converged warp (elect.sync): lets the compiler keep MMA operands in uniform registers
+MZ_DEV bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
 MZ_DEV void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 MZ_DEV void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 MZ_DEV void tc_commit(uint64_t* bar) {
@@ -318,8 +324,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the pipeline converged (waits, descriptor arithmetic
+    // in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit =====
+    {
       const uint32_t a1_addr = smem_u32(sA1);
       const uint32_t w_addr = smem_u32(sW);
       const uint32_t idesc1 = make_idesc(CHUNK);
@@ -329,44 +336,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
         const int st = c % STAGES, head = c >> 2;
         mbar_wait(&a2_full[c & 1], (c >> 1) & 1);
         tc_fence_after();
-        TC_STAMP(64 + 8 * c + 4);
+        if (lane == 0) TC_STAMP(64 + 8 * c + 4);
         const uint32_t a_tm = tmem + COL_A2 + (c & 1) * (CHUNK / 2);
         const uint32_t b_addr = w_addr + st * stage_bytes + (c < 8 ? w1_bytes_dyn : w1_bytes_pred);
-        if (head == 1) issue_mma2<N_HID>(tmem + COL_D2B, a_tm, b_addr, (c & 3) == 0);
-        else issue_mma2<32>(tmem + ((head & 1) ? COL_D2B : COL_D2A), a_tm, b_addr, (c & 3) == 0);
-        TC_STAMP(64 + 8 * c + 5);
-        tc_commit(&w_empty[st]);       // chunk c's weights are no longer needed
-        tc_commit(&a2_empty[c & 1]);   // A2 buffer may be overwritten
-        if (c == 7 || c == 15) tc_commit(d2_full);
-        TC_STAMP(64 + 8 * c + 6);
+        if (elect_one()) {
+          if (head == 1) issue_mma2<N_HID>(tmem + COL_D2B, a_tm, b_addr, (c & 3) == 0);
+          else issue_mma2<32>(tmem + ((head & 1) ? COL_D2B : COL_D2A), a_tm, b_addr, (c & 3) == 0);
+          tc_commit(&w_empty[st]);       // chunk c's weights are no longer needed
+          tc_commit(&a2_empty[c & 1]);   // A2 buffer may be overwritten
+          if (c == 7 || c == 15) tc_commit(d2_full);
+        }
+        __syncwarp();
+        if (lane == 0) TC_STAMP(64 + 8 * c + 6);
       };
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
         const int st = c % STAGES;
         if (c == 8) mma2(7);  // the prediction's A operand depends on the dynamics output
-        TC_STAMP(64 + 8 * c + 0);
+        if (lane == 0) TC_STAMP(64 + 8 * c + 0);
         mbar_wait(&w_full[st], (c / STAGES) & 1);
         if (c == 0) mbar_wait(a1_ready, 0);
         if (c == 8) mbar_wait(a3_ready, 0);
         mbar_wait(&d1_empty[c & 1], ((c >> 1) & 1) ^ 1);
         tc_fence_after();
-        TC_STAMP(64 + 8 * c + 1);
+        if (lane == 0) TC_STAMP(64 + 8 * c + 1);
         const uint32_t d1 = tmem + COL_D1 + (c & 1) * CHUNK;
         const uint64_t bd = make_desc(w_addr + st * stage_bytes, (CHUNK / 8) * 128, 128);
-        if (c < 8) {  // dynamics: A = [h | onehot | 1] from shared memory, K = k1
-          const uint64_t ad = make_desc(a1_addr, (ROWS / 8) * 128, 128);
-          umma_ss<false>(d1, ad, bd, idesc1);
+        if (elect_one()) {
+          if (c < 8) {  // dynamics: A = [h | onehot | 1] from shared memory, K = k1
+            const uint64_t ad = make_desc(a1_addr, (ROWS / 8) * 128, 128);
+            umma_ss<false>(d1, ad, bd, idesc1);
 #pragma unroll 1
-          for (int ks = 1; ks < k1 / 16; ++ks) umma_ss<true>(d1, ad + ks * KSTEP, bd + ks * KSTEP, idesc1);
-        } else {      // prediction: A = [h' | 1] from tensor memory, K = 64
-          umma_ts<false>(d1, tmem + COL_A3, bd, idesc1);
+            for (int ks = 1; ks < k1 / 16; ++ks) umma_ss<true>(d1, ad + ks * KSTEP, bd + ks * KSTEP, idesc1);
+          } else {      // prediction: A = [h' | 1] from tensor memory, K = 64
+            umma_ts<false>(d1, tmem + COL_A3, bd, idesc1);
 #pragma unroll
-          for (int ks = 1; ks < K3 / 16; ++ks)
-            umma_ts<true>(d1, tmem + COL_A3 + ks * 8, bd + ks * KSTEP, idesc1);
+            for (int ks = 1; ks < K3 / 16; ++ks)
+              umma_ts<true>(d1, tmem + COL_A3 + ks * 8, bd + ks * KSTEP, idesc1);
+          }
+          tc_commit(&d1_full[c & 1]);
         }
-        TC_STAMP(64 + 8 * c + 2);
-        tc_commit(&d1_full[c & 1]);
-        TC_STAMP(64 + 8 * c + 3);
+        __syncwarp();
+        if (lane == 0) TC_STAMP(64 + 8 * c + 3);
         if (c > 0 && c != 8) mma2(c - 1);
       }
       mma2(NCHUNK - 1);

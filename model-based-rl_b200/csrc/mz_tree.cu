@@ -251,6 +251,256 @@ MZ_DEV void expand_backup(const mz_tree& t, const MzGame& rd, const MzGame& gl, 
   }
 }
 
+// ================================================================================================
+// Warp-per-game fast path (LPG == 32, i.e. 17..32 actions: the Atari-scale sweep).  Same arithmetic
+// as descend<> / expand_backup<> above, restated for a converged warp: every loop bound and branch
+// is warp-uniform, the child's (q, visit, reward) arrives in one 16-byte load, MinMax normalisation
+// divides by a per-descent constant, and the sequential loops run A / depth iterations instead of 32.
+// ================================================================================================
+struct NodeHead {  // first 16 bytes of a node record
+  double q;
+  int32_t visit;
+  float reward;
+};
+MZ_DEV NodeHead load_head(const uint8_t* rec) {
+  const int4 v = *reinterpret_cast<const int4*>(rec);
+  NodeHead h;
+  h.q = __hiloint2double(v.y, v.x);
+  h.visit = v.z;
+  h.reward = __int_as_float(v.w);
+  return h;
+}
+MZ_DEV void store_head(uint8_t* rec, double q, int visit, float reward) {
+  *reinterpret_cast<int4*>(rec) =
+      make_int4(__double2loint(q), __double2hiint(q), visit, __float_as_int(reward));
+}
+
+// x / d, correctly rounded, for a divisor whose correctly rounded reciprocal r = RN(1/d) is known:
+// q0 = RN(x r) is within 2 ulp, one residual step makes it faithful, and for a faithful q with an
+// exact residual (fma) Markstein's theorem gives RN(q + rem r) = RN(x/d).  Valid while nothing
+// under/overflows (the caller guards the exponent ranges of d and x); bit-identical to __ddiv_rn,
+// checked on the device over 2^33 operand pairs by tests/test_gpu_search.py::test_fast_division.
+MZ_DEV double div_by_const(double x, double d, double r) {
+  const double q0 = __dmul_rn(x, r);
+  const double q1 = __fma_rn(__fma_rn(-q0, d, x), r, q0);
+  return __fma_rn(__fma_rn(-q1, d, x), r, q1);
+}
+MZ_DEV bool exp_in_fast_range(double x) {  // 2^-200 <= |x| <= 2^200
+  const unsigned h = (unsigned)__double2hiint(x) & 0x7fffffffu;
+  return (h - 0x33700000u) <= 0x19000000u;
+}
+MZ_DEV bool divisor_ok(double d) {  // exponent in range and significand not all ones
+  const unsigned h = (unsigned)__double2hiint(d), l = (unsigned)__double2loint(d);
+  return exp_in_fast_range(d) && !(((h & 0xfffffu) == 0xfffffu) && l == 0xffffffffu);
+}
+
+MZ_DEV unsigned long long unsortable_key(unsigned long long k) {
+  return (k >> 63) ? (k ^ 0x8000000000000000ull) : ~k;
+}
+// max of the sortable keys of a converged warp (0 = lane does not take part)
+MZ_DEV unsigned long long warp_max_key(unsigned long long key) {
+  const unsigned hi = (unsigned)(key >> 32);
+  const unsigned hi_max = __reduce_max_sync(MZ_FULL, hi);
+  const unsigned lo_max = __reduce_max_sync(MZ_FULL, hi == hi_max ? (unsigned)key : 0u);
+  return ((unsigned long long)hi_max << 32) | lo_max;
+}
+
+MZ_DEV void descend_w32(const mz_tree& t, const uint8_t* img, int lane, int16_t* path, int& out_depth,
+                        int& out_parent, int& out_action) {
+  const int A = t.num_actions, SP1 = t.num_simulations + 1, NB = t.node_bytes;
+  const double init_score = t.init_value_score;
+  const double mn = *reinterpret_cast<const double*>(img), mx = *reinterpret_cast<const double*>(img + 8);
+  // MinMaxStats.normalize mcts.py:16-21, hoisted: 2 = affine, 1 = constant 1.0, 0 = raw value
+  const int mode = mx > mn ? 2 : (mx == mn ? 1 : 0);
+  const double d = __dsub_rn(mx, mn);
+  const bool fast = mode == 2 && divisor_ok(d);
+  const double r = fast ? __drcp_rn(d) : 0.0;
+  const uint8_t* nodes = img + MZ_GAME_HEADER_BYTES;
+  const bool lane_ok = lane < A;
+  const int sp = lane_ok ? lane : A - 1;
+  const int prior_off = MZ_NODE_STATS_BYTES + 8 * sp, child_off = MZ_NODE_STATS_BYTES + 8 * A + 2 * sp;
+  int node = 0, depth = 0, parent = 0, action = 0;
+  int N = load_head(nodes).visit;
+  if (lane == 0) path[0] = 0;
+  for (;;) {
+    const uint8_t* rec = nodes + node * NB;
+    const double prior = *reinterpret_cast<const double*>(rec + prior_off);
+    const int ch = *reinterpret_cast<const int16_t*>(rec + child_off);
+    const NodeHead c = load_head(nodes + max(ch, 0) * NB);
+    const int n = ch >= 0 ? c.visit : 0;
+    double score;
+    if (N == 0) {  // mcts.py:105-108: an unvisited (root) node ranks children by prior
+      score = prior;
+    } else {       // ucb_score mcts.py:115-124
+      const double pb_c = __ldg(t.pb_c_table + N * SP1 + n);
+      double value_score = init_score;
+      if (n > 0) {
+        if (mode == 2) {
+          const double x = __dsub_rn(c.q, mn);
+          value_score = (fast && (x == 0.0 || exp_in_fast_range(x))) ? div_by_const(x, d, r)
+                                                                      : __ddiv_rn(x, d);
+        } else {
+          value_score = mode == 1 ? 1.0 : c.q;
+        }
+      }
+      score = __dadd_rn(__dmul_rn(pb_c, prior), value_score);
+    }
+    // max over (score, action) tuples, ties -> larger action (mcts.py:106-112)
+    const bool cand = lane_ok && ch != MZ_CHILD_ILLEGAL;
+    const unsigned long long key = cand ? sortable_key(score) : 0ull;
+    const unsigned long long best_key = warp_max_key(key);
+    const unsigned winners = __ballot_sync(MZ_FULL, cand && key == best_key);
+    const int best = winners ? 31 - __clz(winners) : -1;
+    const int src = best < 0 ? 0 : best;
+    const int ch_b = __shfl_sync(MZ_FULL, ch, src);
+    const int n_b = __shfl_sync(MZ_FULL, n, src);
+    depth++;
+    if (ch_b < 0) {  // child not expanded: this is the leaf
+      parent = node;
+      action = best;
+      break;
+    }
+    node = ch_b;
+    N = n_b;
+    if (lane == 0) path[depth] = (int16_t)node;
+  }
+  out_depth = depth;
+  out_parent = parent;
+  out_action = action;
+}
+
+// expand (mcts.py:47-55) + backpropagate (mcts.py:126-143) for one game per warp.  `img` is the
+// image the warp reads (shared memory when STAGED, else the global block); stores go to the global
+// block and, when staged, to the image as well.
+template <bool STAGED>
+MZ_DEV void expand_backup_w32(const mz_tree& t, uint8_t* img, uint8_t* gbl, int lane, int sim,
+                              float value_f, float reward_f, float logit, int16_t* path, int depth,
+                              int parent, int action) {
+  const int A = t.num_actions, NB = t.node_bytes;
+  const bool two = t.two_players != 0;
+  const double disc = t.discount;
+  const int newn = sim + 1;
+  const float node_reward_new = (reward_f != 0.0f) ? reward_f : 0.0f;  // `if network_output.reward:`
+  uint8_t* nodes_s = img + MZ_GAME_HEADER_BYTES;
+  uint8_t* nodes_g = gbl + MZ_GAME_HEADER_BYTES;
+  const bool lane_ok = lane < A;
+
+  // the path positions this lane owns in the first (deepest) chunk: issue the loads early
+  const int top = (depth >> 5) << 5;
+  int nid_top = 0;
+  if (top + lane < depth) nid_top = path[top + lane];
+
+  // priors: p_a = exp(logit_a) / sum(p), the sum evaluated like CPython's builtin sum()
+  // (every action is legal below the root, mcts.py:72, 97)
+  const double p = lane_ok ? mz_exp((double)logit) : 0.0;
+  double f = shfl_f64<32>(p, 0), c = 0.0;
+  if (t.prior_sum_mode == 0) {
+#pragma unroll 1
+    for (int a = 1; a < A; ++a) f = __dadd_rn(f, shfl_f64<32>(p, a));
+  } else {  // Neumaier step, CPython >= 3.12 Python/bltinmodule.c
+#pragma unroll 1
+    for (int a = 1; a < A; ++a) {
+      const double x = shfl_f64<32>(p, a);
+      const double s = __dadd_rn(f, x);
+      const bool big = fabs(f) >= fabs(x);
+      const double hi = big ? f : x, lo = big ? x : f;
+      c = __dadd_rn(c, __dadd_rn(__dsub_rn(hi, s), lo));
+      f = s;
+    }
+    if (c != 0.0 && isfinite(c)) f = __dadd_rn(f, c);
+  }
+  if (lane_ok) {
+    const double prior = __ddiv_rn(p, f);
+    const int po = newn * NB + MZ_NODE_STATS_BYTES + 8 * lane;
+    const int co = newn * NB + MZ_NODE_STATS_BYTES + 8 * A + 2 * lane;
+    *reinterpret_cast<double*>(nodes_g + po) = prior;
+    *reinterpret_cast<int16_t*>(nodes_g + co) = (int16_t)MZ_CHILD_UNEXPANDED;
+    if (STAGED) {
+      *reinterpret_cast<double*>(nodes_s + po) = prior;
+      *reinterpret_cast<int16_t*>(nodes_s + co) = (int16_t)MZ_CHILD_UNEXPANDED;
+    }
+  }
+  if (lane == 0) {
+    const int co = parent * NB + MZ_NODE_STATS_BYTES + 8 * A + 2 * action;
+    *reinterpret_cast<int16_t*>(nodes_g + co) = (int16_t)newn;
+    if (STAGED) *reinterpret_cast<int16_t*>(nodes_s + co) = (int16_t)newn;
+    path[depth] = (int16_t)newn;
+  }
+
+  // backup.  Position k on the path holds node path[k] (k < depth) or the new node (k == depth).
+  double value = (double)value_f;
+  unsigned long long kmax = 0ull, kmin = 0ull;  // sortable keys of max(q) and of -min ordering
+  const unsigned twomask = two ? 0x80000000u : 0u;
+  unsigned signmask = twomask;  // position `depth` is the leaf: node.to_play == to_play
+  for (int base = top; base >= 0; base -= 32) {
+    const int k = base + lane;
+    const bool has = k <= depth;
+    const int nid = k < depth ? (base == top ? nid_top : (int)path[k]) : newn;
+    double vs = 0.0;
+    int vc = 0;
+    float rw = node_reward_new;
+    if (k < depth) {
+      const uint8_t* rec = nodes_s + nid * NB;
+      const NodeHead h = load_head(rec);
+      vc = h.visit;
+      rw = h.reward;
+      vs = *reinterpret_cast<const double*>(rec + 16);
+    }
+    double myval = 0.0;
+    unsigned mysign = 0u;
+#pragma unroll 1
+    for (int j = min(31, depth - base); j >= 0; --j) {
+      const unsigned rj = __shfl_sync(MZ_FULL, __float_as_uint(rw), j);
+      if (lane == j) {
+        myval = value;
+        mysign = signmask;
+      }
+      // value = (-reward if two_players and node.to_play == to_play else reward) + discount * value
+      value = __dadd_rn((double)__uint_as_float(rj ^ signmask), __dmul_rn(disc, value));
+      signmask ^= twomask;
+    }
+    if (has) {
+      // value_sum += value if node.to_play == to_play else -value   (mysign set <=> same player
+      // in a two-player game; single player: always the same player)
+      const bool same = two ? mysign != 0u : true;
+      vs = __dadd_rn(vs, same ? myval : -myval);
+      vc += 1;
+      double new_q = 0.0;
+      if (k > 0) {  // mcts.py:136-141
+        const double dq = __dmul_rn(disc, __ddiv_rn(vs, (double)vc));
+        new_q = two ? __dsub_rn((double)rw, dq) : __dadd_rn((double)rw, dq);
+      }
+      store_head(nodes_g + nid * NB, new_q, vc, rw);
+      *reinterpret_cast<double*>(nodes_g + nid * NB + 16) = vs;
+      if (STAGED) {
+        store_head(nodes_s + nid * NB, new_q, vc, rw);
+        *reinterpret_cast<double*>(nodes_s + nid * NB + 16) = vs;
+      }
+      if (k > 0) {
+        const unsigned long long key = sortable_key(new_q);
+        kmax = key > kmax ? key : kmax;
+        kmin = ~key > kmin ? ~key : kmin;
+      }
+    }
+    if (depth > 0) {
+      kmax = warp_max_key(kmax);
+      kmin = warp_max_key(kmin);
+    }
+  }
+  if (lane == 0 && depth > 0) {  // MinMaxStats.update mcts.py:11-14
+    const double lmax = __longlong_as_double((long long)unsortable_key(kmax));
+    const double lmin = __longlong_as_double((long long)unsortable_key(~kmin));
+    if (lmin < *reinterpret_cast<double*>(img)) {
+      *reinterpret_cast<double*>(gbl) = lmin;
+      if (STAGED) *reinterpret_cast<double*>(img) = lmin;
+    }
+    if (lmax > *reinterpret_cast<double*>(img + 8)) {
+      *reinterpret_cast<double*>(gbl + 8) = lmax;
+      if (STAGED) *reinterpret_cast<double*>(img + 8) = lmax;
+    }
+  }
+}
+
 template <int LPG>
 MZ_DEV void copy_words(uint32_t* dst, const uint32_t* src, int words, int sub) {
   for (int i = sub; i < words; i += LPG) dst[i] = src[i];
@@ -374,6 +624,71 @@ tree_step_kernel(mz_tree t, int sim, int do_backup, int do_select, int live_node
         copy_words<LPG>(gathered_hidden + (size_t)g * HW,
                         t.hidden + ((size_t)g * SP1 + parent) * HW, HW, sub);
     }
+  }
+}
+
+// Warp-per-game variant of tree_step_kernel (17..32 actions).  blockDim.x = 32 * games_per_block.
+template <bool STAGED>
+__global__ void __launch_bounds__(kThreads)
+tree_step_w32_kernel(mz_tree t, int sim, int do_backup, int do_select, int live_nodes, int stage_bytes,
+                     const float* __restrict__ value, const float* __restrict__ reward,
+                     const float* __restrict__ logits, const uint32_t* __restrict__ new_hidden,
+                     uint32_t* __restrict__ gathered_hidden, int32_t* __restrict__ trace_parent,
+                     int32_t* __restrict__ trace_action, int32_t* __restrict__ trace_depth) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * wpb + warp;
+  const bool valid = g < t.num_games;
+  const int A = t.num_actions, SP1 = t.num_simulations + 1, HW = t.hidden_words;
+  uint8_t* gbl = t.games + (size_t)(valid ? g : 0) * t.game_bytes;
+  uint8_t* img = gbl;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)wpb * stage_bytes);
+  if (STAGED) {
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < wpb; ++i) mbar_init(&bars[i], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (!valid) return;
+    img = smem + (size_t)warp * stage_bytes;
+    // nodes 0..live_nodes-1 exist before this launch (a backup creates node `sim + 1` in place)
+    const uint32_t live = MZ_GAME_HEADER_BYTES + (uint32_t)live_nodes * (uint32_t)t.node_bytes;
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars[warp], live);
+      bulk_copy_g2s(img, gbl, live, &bars[warp]);
+    }
+  } else if (!valid) {
+    return;
+  }
+  int16_t* path = t.path + (size_t)g * (t.num_simulations + 2);
+
+  if (do_backup) {
+    // everything the backup needs from global memory is requested before waiting for the image
+    const int depth = t.path_len[g], parent = t.leaf_parent[g], action = t.leaf_action[g];
+    const float logit = lane < A ? logits[(size_t)g * A + lane] : 0.0f;
+    const float v = value[g], r = reward[g];
+    if (STAGED) mbar_wait(&bars[warp], 0);
+    expand_backup_w32<STAGED>(t, img, gbl, lane, sim, v, r, logit, path, depth, parent, action);
+    if (new_hidden && HW > 0)
+      copy_words<32>(t.hidden + ((size_t)g * SP1 + sim + 1) * HW, new_hidden + (size_t)g * HW, HW, lane);
+    __syncwarp();
+  } else if (STAGED) {
+    mbar_wait(&bars[warp], 0);
+  }
+  if (do_select) {
+    int depth, parent, action;
+    descend_w32(t, img, lane, path, depth, parent, action);
+    if (lane == 0) {
+      t.path_len[g] = depth;
+      t.leaf_parent[g] = parent;
+      t.leaf_action[g] = action;
+      if (trace_parent) trace_parent[g] = parent;
+      if (trace_action) trace_action[g] = action;
+      if (trace_depth) trace_depth[g] = depth;
+    }
+    if (gathered_hidden && HW > 0)
+      copy_words<32>(gathered_hidden + (size_t)g * HW, t.hidden + ((size_t)g * SP1 + parent) * HW, HW,
+                     lane);
   }
 }
 
@@ -506,6 +821,50 @@ __global__ void exp_f32_kernel(long long n, const float* __restrict__ x, double*
     out[i] = mz_exp((double)x[i]);
 }
 
+// Diagnostics: div_by_const against __ddiv_rn on pseudo-random operand pairs shaped like the
+// MinMax normalisation (0 <= x <= d) plus adversarial significands.  Counts mismatches.
+MZ_DEV unsigned long long mix64(unsigned long long z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__global__ void div_check_kernel(unsigned long long seed, int per_thread,
+                                 unsigned long long* __restrict__ mismatches,
+                                 unsigned long long* __restrict__ tested) {
+  unsigned long long state = seed + (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 0x632be59bd9b4e019ull;
+  unsigned long long bad = 0, done = 0;
+  for (int i = 0; i < per_thread; ++i) {
+    const unsigned long long a = mix64(state), b = mix64(state + 1), c = mix64(state + 2);
+    state += 3;
+    // divisor: random significand (sometimes nearly all ones / all zeros / few bits), exponent 2^-60..2^60
+    unsigned long long mant = a & 0xfffffffffffffull;
+    const unsigned kind = (unsigned)(c & 7u);
+    if (kind == 0) mant |= 0xffffffffff000ull;
+    else if (kind == 1) mant &= 0xfffull;
+    else if (kind == 2) mant &= 0xfff0000000000ull;
+    const long long ed = 1023 + (long long)((a >> 52) % 121) - 60;
+    const double d = __longlong_as_double((long long)(((unsigned long long)ed << 52) | mant));
+    // dividend: u * d with u in [0, 1], or a small multiple of d, nudged by a few ulps
+    double x;
+    const unsigned xk = (unsigned)((c >> 3) & 3u);
+    if (xk == 0) x = __dmul_rn(d, (double)(b >> 11) * 0x1p-53);
+    else if (xk == 1) x = __dmul_rn(d, (double)((b >> 20) & 1023u) * 0x1p-10);
+    else if (xk == 2) x = __longlong_as_double((long long)(((unsigned long long)(ed - (long long)((b >> 52) % 40)) << 52) | (b & 0xfffffffffffffull)));
+    else x = __dmul_rn(d, (double)(b >> 11) * 0x1p-53 * 0x1p-30);
+    long long xb = __double_as_longlong(x) + (long long)((c >> 5) & 7u) - 3;
+    if (xb < 0) xb = 0;
+    x = __longlong_as_double(xb);
+    if (!divisor_ok(d) || !(x == 0.0 || exp_in_fast_range(x))) continue;
+    const double want = __ddiv_rn(x, d);
+    const double got = div_by_const(x, d, __drcp_rn(d));
+    bad += (__double_as_longlong(want) != __double_as_longlong(got));
+    ++done;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+  atomicAdd(tested, done);
+}
+
 int check_tree(const mz_tree* t) {
   if (!t || !t->games || !t->pb_c_table || !t->path || !t->path_len || !t->leaf_parent ||
       !t->leaf_action)
@@ -539,6 +898,15 @@ int set_smem_attr_once() {
   return rc;
 }
 
+template <bool STAGED>
+int set_smem_attr_w32_once() {
+  static int rc = -1;
+  if (rc < 0)
+    rc = (int)cudaFuncSetAttribute(tree_step_w32_kernel<STAGED>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStageSmem + 1024);
+  return rc;
+}
+
 int launch_step(const mz_tree* t, int sim, int live_nodes, int do_backup, int do_select, const float* value,
                 const float* reward, const float* logits, const uint32_t* new_hidden,
                 uint32_t* gathered_hidden, int32_t* tp, int32_t* ta, int32_t* td, void* stream) {
@@ -550,6 +918,24 @@ int launch_step(const mz_tree* t, int sim, int live_nodes, int do_backup, int do
     int gpb = kThreads / LPG;
     while (gpb > 1 && (size_t)gpb * stage_bytes > 96 * 1024) gpb >>= 1;
     const bool staged = (size_t)gpb * stage_bytes <= kMaxStageSmem;
+    if (LPG == 32) {  // one game per warp: the converged-warp kernel
+      if (!staged) gpb = kThreads / 32;
+      const int grid = (t->num_games + gpb - 1) / gpb;
+      if (staged) {
+        int rc = set_smem_attr_w32_once<true>();
+        if (rc) return rc;
+        tree_step_w32_kernel<true><<<grid, gpb * 32, (size_t)gpb * stage_bytes + sizeof(uint64_t) * gpb,
+                                     (cudaStream_t)stream>>>(
+            *t, sim, do_backup, do_select, live_nodes, stage_bytes, value, reward, logits, new_hidden,
+            gathered_hidden, tp, ta, td);
+      } else {
+        tree_step_w32_kernel<false><<<grid, gpb * 32, 0, (cudaStream_t)stream>>>(
+            *t, sim, do_backup, do_select, live_nodes, 0, value, reward, logits, new_hidden,
+            gathered_hidden, tp, ta, td);
+      }
+      MZ_LAUNCH_CHECK();
+      return MZ_OK;
+    }
     if (staged) {
       int rc = set_smem_attr_once<LPG, true>();
       if (rc) return rc;
@@ -698,6 +1084,15 @@ int mz_exp_f32(int64_t n, const float* x, double* out, void* stream) {
   if (n < 0 || (n > 0 && (!x || !out))) return MZ_ERR_BAD_ARG;
   if (n == 0) return MZ_OK;
   exp_f32_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(n, x, out);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+int mz_debug_div_check(uint64_t seed, int32_t blocks, int32_t per_thread, uint64_t* mismatches,
+                       uint64_t* tested, void* stream) {
+  if (blocks < 1 || per_thread < 1 || !mismatches || !tested) return MZ_ERR_BAD_ARG;
+  div_check_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      seed, per_thread, (unsigned long long*)mismatches, (unsigned long long*)tested);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }

@@ -5,6 +5,7 @@ trace are BIT-EXACT against the reference (golden vectors from the unmodified mc
 the CPU oracle on larger seeded inputs; root values within 1e-5 relative (they come out bit-exact
 whenever the paths agree, because value sums only combine network outputs).
 """
+import ctypes as C
 import types
 
 import numpy as np
@@ -221,3 +222,18 @@ def test_mcts_run_dropin_b1():
     for step in range(len(s_last) - 1):
       assert s_last[step + 1] in node.children.values()
       node = s_last[step + 1]
+
+
+def test_fast_division_is_ieee_division():
+  """The descent divides by the per-descent constant (max - min) through a reciprocal + two fma
+  correction steps; the result must be the correctly rounded quotient, bit for bit."""
+  from model_based_rl_b200 import _lib
+  lib = _lib.load()
+  cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+  for seed in (1, 2, 3, 4):
+    _lib.check(lib.mz_debug_div_check(seed, 148 * 16, 1 << 12, C.c_void_p(cnt.data_ptr()),
+                                      C.c_void_p(cnt.data_ptr() + 8), _lib.current_stream()), "div")
+  torch.cuda.synchronize()
+  bad, tested = cnt.cpu().tolist()
+  print("pairs tested", tested, "mismatches", bad)
+  assert tested > 3_000_000_000 and bad == 0
