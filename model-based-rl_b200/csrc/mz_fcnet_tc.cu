@@ -16,8 +16,9 @@
 // (UMMA canonical K-major layout, no swizzle) and streamed through a 3-stage ring with one
 // cp.async.bulk per chunk; the pipeline is driven by mbarriers (TMA -> MMA -> epilogue -> MMA).
 //
-// Warp roles (320 threads): warp 0 = TMEM allocation + bulk-copy producer, warp 1 = MMA issuer
-// (one thread), warps 2..9 = two epilogue groups of four warps (TMEM lane quarter = warp % 4).
+// Warp roles (352 threads): warp 0 = TMEM allocation + bulk-copy producer, warp 1 = layer-1 MMA
+// issuer, warps 2..9 = two epilogue groups of four warps (TMEM lane quarter = warp % 4), warp 10 =
+// layer-2 MMA issuer (each issuer: converged warp, one elected lane issues).
 //
 // Reference semantics: networks.py:31-34, 122-174 (FCNetwork), config.py:27-33.
 #include <cuda_bf16.h>
@@ -36,7 +37,9 @@ constexpr int NCHUNK = 16;           // 4 heads x 4 chunks
 constexpr int K3 = 64;               // padded K of the prediction first layer
 constexpr int STAGES = 4;
 constexpr int EPI_THREADS = 256;       // two groups of four epilogue warps
-constexpr int TC_THREADS = 64 + EPI_THREADS;
+constexpr int MMA2_WARP = 2 + EPI_THREADS / 32;  // second MMA-issuing warp (layer 2)
+constexpr int STORE_WARP = MMA2_WARP + 1;       // writes h' rows to the hidden pool, off the critical path
+constexpr int TC_THREADS = 64 + EPI_THREADS + 64;
 constexpr int N_REW = 32, N_HID = 64, N_VAL = 32, N_POL = 32;  // padded second-layer widths
 constexpr int TMEM_COLS = 512;
 // TMEM column map (512 columns x 128 lanes x 32 bit)
@@ -49,6 +52,7 @@ constexpr int COL_A3 = 480;          // 32     : h' as packed bf16 = A operand o
 // tail parameter block (float): second-layer biases and LayerNorm affine
 constexpr int T_REW_B = 0, T_DYN_B = 32, T_LN_W = 96, T_LN_B = 160, T_VAL_B = 224, T_POL_B = 256;
 constexpr int TAIL_FLOATS = 288;
+constexpr int OUT_STRIDE = 51;        // odd row stride of the output staging area (bank-conflict free)
 
 struct ChunkGeom {  // byte geometry of one packed chunk: [W1 | W2]; the first-layer bias is folded
                     // into W1 as the weight of a constant-1 input column (index kin)
@@ -206,21 +210,22 @@ struct TcParams {
 MZ_DEV float support_to_scalar_regs(const uint32_t (&v)[32], const float* bias, int bins, int mn,
                                     int no_tt) {
   float x[32];
-  float m = -INFINITY;
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four chains keep dependencies short
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     x[j] = __uint_as_float(v[j]) + bias[j];
-    if (j < bins) m = fmaxf(m, x[j]);
+    if (j < bins) m4[j & 3] = fmaxf(m4[j & 3], x[j]);
   }
-  float den = 0.0f;
+  const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  float den4[4] = {0.0f, 0.0f, 0.0f, 0.0f}, num4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     x[j] = j < bins ? __expf(x[j] - m) : 0.0f;
-    den += x[j];
+    den4[j & 3] += x[j];
+    num4[j & 3] = fmaf((float)(mn + j), x[j], num4[j & 3]);
   }
-  float num = 0.0f;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) num = fmaf((float)(mn + j), x[j], num);
+  const float den = (den4[0] + den4[1]) + (den4[2] + den4[3]);
+  float num = (num4[0] + num4[1]) + (num4[2] + num4[3]);
   num = num / den;
   return no_tt ? num : mz_inverse_scalar_transform_f(num);
 }
@@ -269,6 +274,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   }
   const int k1 = p.k1;
   const int stage_bytes = stage_bytes_for(k1);
+  // epilogue threads request their row's gather index / action before the set-up barrier
+  int pre_idx = 0, pre_act = 0;
+  if (warp >= 2 && warp < MMA2_WARP) {
+    const int g0 = blockIdx.x * ROWS + (warp & 3) * 32 + lane;
+    const int gc0 = g0 < p.batch ? g0 : p.batch - 1;
+    pre_idx = p.in_index ? p.in_index[gc0] : 0;
+    pre_act = p.actions[gc0];
+  }
   // carve shared memory
   uint8_t* sA1 = smem;                                  // [128 x k1] bf16 (A of the dynamics layer)
   uint8_t* sW = sA1 + ROWS * k1 * 2;                    // STAGES x stage_bytes
@@ -282,8 +295,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   uint64_t* a1_ready = bars + 16;
   uint64_t* a3_ready = bars + 17;
   uint64_t* d2_full = bars + 18;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 19);
-  float* sTail = reinterpret_cast<float*>(bars + 20);   // second-layer biases + LayerNorm affine
+  uint64_t* h_staged = bars + 19;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+  float* sTail = reinterpret_cast<float*>(bars + 21);   // second-layer biases + LayerNorm affine
+  float* sOut = sTail + TAIL_FLOATS;                    // [128][51]: row-major staging of h'
+  float* sLog = sOut + ROWS * OUT_STRIDE;               // [128][A]: row-major staging of the logits
   for (int i = threadIdx.x; i < TAIL_FLOATS; i += TC_THREADS) sTail[i] = p.tail[i];
 
   if (threadIdx.x == 0) {
@@ -297,6 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     mbar_init(a1_ready, EPI_THREADS);
     mbar_init(a3_ready, EPI_THREADS / 2);
     mbar_init(d2_full, 1);
+    mbar_init(h_staged, EPI_THREADS / 2);
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -324,63 +341,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: the whole warp walks the pipeline converged (waits, descriptor arithmetic
-    // in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit =====
-    {
-      const uint32_t a1_addr = smem_u32(sA1);
-      const uint32_t w_addr = smem_u32(sW);
-      const uint32_t idesc1 = make_idesc(CHUNK);
-      const uint32_t w1_bytes_dyn = CHUNK * k1 * 2, w1_bytes_pred = CHUNK * K3 * 2;
-      constexpr uint64_t KSTEP = (uint64_t)((2 * (CHUNK / 8) * 128) >> 4);  // two K core-matrix columns
-      auto mma2 = [&](int c) {  // D2 += A2[c&1] * W2c^T
-        const int st = c % STAGES, head = c >> 2;
-        mbar_wait(&a2_full[c & 1], (c >> 1) & 1);
-        tc_fence_after();
-        if (lane == 0) TC_STAMP(64 + 8 * c + 4);
-        const uint32_t a_tm = tmem + COL_A2 + (c & 1) * (CHUNK / 2);
-        const uint32_t b_addr = w_addr + st * stage_bytes + (c < 8 ? w1_bytes_dyn : w1_bytes_pred);
-        if (elect_one()) {
-          if (head == 1) issue_mma2<N_HID>(tmem + COL_D2B, a_tm, b_addr, (c & 3) == 0);
-          else issue_mma2<32>(tmem + ((head & 1) ? COL_D2B : COL_D2A), a_tm, b_addr, (c & 3) == 0);
-          tc_commit(&w_empty[st]);       // chunk c's weights are no longer needed
-          tc_commit(&a2_empty[c & 1]);   // A2 buffer may be overwritten
-          if (c == 7 || c == 15) tc_commit(d2_full);
-        }
-        __syncwarp();
-        if (lane == 0) TC_STAMP(64 + 8 * c + 6);
-      };
+    // ===== layer-1 MMA issuer: the whole warp walks the pipeline converged (waits, descriptor
+    // arithmetic in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit =====
+    const uint32_t a1_addr = smem_u32(sA1);
+    const uint32_t w_addr = smem_u32(sW);
+    const uint32_t idesc1 = make_idesc(CHUNK);
+    constexpr uint64_t KSTEP = (uint64_t)((2 * (CHUNK / 8) * 128) >> 4);  // two K core-matrix columns
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c) {
-        const int st = c % STAGES;
-        if (c == 8) mma2(7);  // the prediction's A operand depends on the dynamics output
-        if (lane == 0) TC_STAMP(64 + 8 * c + 0);
-        mbar_wait(&w_full[st], (c / STAGES) & 1);
-        if (c == 0) mbar_wait(a1_ready, 0);
-        if (c == 8) mbar_wait(a3_ready, 0);
-        mbar_wait(&d1_empty[c & 1], ((c >> 1) & 1) ^ 1);
-        tc_fence_after();
-        if (lane == 0) TC_STAMP(64 + 8 * c + 1);
-        const uint32_t d1 = tmem + COL_D1 + (c & 1) * CHUNK;
-        const uint64_t bd = make_desc(w_addr + st * stage_bytes, (CHUNK / 8) * 128, 128);
-        if (elect_one()) {
-          if (c < 8) {  // dynamics: A = [h | onehot | 1] from shared memory, K = k1
-            const uint64_t ad = make_desc(a1_addr, (ROWS / 8) * 128, 128);
-            umma_ss<false>(d1, ad, bd, idesc1);
+    for (int c = 0; c < NCHUNK; ++c) {
+      const int st = c % STAGES;
+      if (lane == 0) TC_STAMP(64 + 8 * c + 0);
+      mbar_wait(&w_full[st], (c / STAGES) & 1);
+      if (c == 0) mbar_wait(a1_ready, 0);
+      if (c == 8) mbar_wait(a3_ready, 0);
+      mbar_wait(&d1_empty[c & 1], ((c >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0) TC_STAMP(64 + 8 * c + 1);
+      const uint32_t d1 = tmem + COL_D1 + (c & 1) * CHUNK;
+      const uint64_t bd = make_desc(w_addr + st * stage_bytes, (CHUNK / 8) * 128, 128);
+      if (elect_one()) {
+        if (c < 8) {  // dynamics: A = [h | onehot | 1] from shared memory, K = k1
+          const uint64_t ad = make_desc(a1_addr, (ROWS / 8) * 128, 128);
+          umma_ss<false>(d1, ad, bd, idesc1);
 #pragma unroll 1
-            for (int ks = 1; ks < k1 / 16; ++ks) umma_ss<true>(d1, ad + ks * KSTEP, bd + ks * KSTEP, idesc1);
-          } else {      // prediction: A = [h' | 1] from tensor memory, K = 64
-            umma_ts<false>(d1, tmem + COL_A3, bd, idesc1);
+          for (int ks = 1; ks < k1 / 16; ++ks) umma_ss<true>(d1, ad + ks * KSTEP, bd + ks * KSTEP, idesc1);
+        } else {      // prediction: A = [h' | 1] from tensor memory, K = 64
+          umma_ts<false>(d1, tmem + COL_A3, bd, idesc1);
 #pragma unroll
-            for (int ks = 1; ks < K3 / 16; ++ks)
-              umma_ts<true>(d1, tmem + COL_A3 + ks * 8, bd + ks * KSTEP, idesc1);
-          }
-          tc_commit(&d1_full[c & 1]);
+          for (int ks = 1; ks < K3 / 16; ++ks)
+            umma_ts<true>(d1, tmem + COL_A3 + ks * 8, bd + ks * KSTEP, idesc1);
         }
-        __syncwarp();
-        if (lane == 0) TC_STAMP(64 + 8 * c + 3);
-        if (c > 0 && c != 8) mma2(c - 1);
+        tc_commit(&d1_full[c & 1]);
       }
-      mma2(NCHUNK - 1);
+      __syncwarp();
+      if (lane == 0) TC_STAMP(64 + 8 * c + 3);
+    }
+  } else if (warp == MMA2_WARP) {
+    // ===== layer-2 MMA issuer: D2 += A2[c&1] (TMEM) * W2c^T as soon as the epilogue has produced
+    // A2[c&1]; runs concurrently with the layer-1 issuer so neither waits behind the other =====
+    const uint32_t w_addr = smem_u32(sW);
+    const uint32_t w1_bytes_dyn = CHUNK * k1 * 2, w1_bytes_pred = CHUNK * K3 * 2;
+#pragma unroll 1
+    for (int c = 0; c < NCHUNK; ++c) {
+      const int st = c % STAGES, head = c >> 2;
+      mbar_wait(&a2_full[c & 1], (c >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) TC_STAMP(64 + 8 * c + 4);
+      const uint32_t a_tm = tmem + COL_A2 + (c & 1) * (CHUNK / 2);
+      const uint32_t b_addr = w_addr + st * stage_bytes + (c < 8 ? w1_bytes_dyn : w1_bytes_pred);
+      if (elect_one()) {
+        if (head == 1) issue_mma2<N_HID>(tmem + COL_D2B, a_tm, b_addr, (c & 3) == 0);
+        else issue_mma2<32>(tmem + ((head & 1) ? COL_D2B : COL_D2A), a_tm, b_addr, (c & 3) == 0);
+        tc_commit(&w_empty[st]);       // chunk c's weights are no longer needed
+        tc_commit(&a2_empty[c & 1]);   // A2 buffer may be overwritten
+        if (c == 7 || c == 15) tc_commit(d2_full);
+      }
+      __syncwarp();
+      if (lane == 0) TC_STAMP(64 + 8 * c + 6);
+    }
+  } else if (warp == STORE_WARP) {
+    // ===== h' rows: shared-memory staging area -> hidden pool, one contiguous 200-byte row per
+    // pair of store instructions (a per-thread row store would touch 32 lines per instruction) =====
+    mbar_wait(h_staged, 0);
+    const int rows_here = min(ROWS, p.batch - blockIdx.x * ROWS);
+#pragma unroll 4
+    for (int r = 0; r < rows_here; ++r) {
+      float* dst = p.hidden_out + (size_t)(blockIdx.x * ROWS + r) * p.out_row_stride + p.out_offset;
+      dst[lane] = sOut[r * OUT_STRIDE + lane];
+      if (lane < H - 32) dst[32 + lane] = sOut[r * OUT_STRIDE + 32 + lane];
     }
   } else {
     // ===== epilogue warps: two groups of four warps; within a group one thread per row.
@@ -399,8 +427,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     if (grp == 0) {
       // k < 48: the warp walks its 32 rows, 24 lanes load one float2 each (coalesced 192 B per row);
       // all loads of a batch of 16 rows are issued before the first store
-      const float* src = p.hidden_in + (size_t)gc * p.in_row_stride +
-                         (p.in_index ? (size_t)p.in_index[gc] * H : 0);
+      const float* src = p.hidden_in + (size_t)gc * p.in_row_stride + (size_t)pre_idx * H;
       const unsigned long long my_src = (unsigned long long)src;
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
@@ -420,9 +447,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       }
     } else {
       // k >= 48: the row's own thread (last two state features, one-hot action, constant 1)
-      const float* src = p.hidden_in + (size_t)gc * p.in_row_stride +
-                         (p.in_index ? (size_t)p.in_index[gc] * H : 0);
-      const int act = p.actions[gc];
+      const float* src = p.hidden_in + (size_t)gc * p.in_row_stride + (size_t)pre_idx * H;
+      const int act = pre_act;
       const float2 h4849 = *reinterpret_cast<const float2*>(src + 48);
       const int kbias = H + p.num_actions;
       const int a_off = (row >> 3) * 128 + (row & 7) * 16;
@@ -520,11 +546,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       tc_fence_before();
       mbar_arrive(a3_ready);
       if (stamp) TC_STAMP(41);
-      if (live) {  // after the hand-off: the store to the pool is off the critical path
-        float2* dsth = reinterpret_cast<float2*>(p.hidden_out + (size_t)g * p.out_row_stride + p.out_offset);
+      // after the hand-off: h' goes to the pool through shared memory so that every store
+      // instruction writes one contiguous 200-byte row (a per-thread row store touches 32 lines)
 #pragma unroll
-        for (int j = 0; j < H / 2; ++j) dsth[j] = make_float2(hbuf[2 * j], hbuf[2 * j + 1]);
-      }
+      for (int j = 0; j < H; ++j) sOut[row * OUT_STRIDE + j] = hbuf[j];
+      mbar_arrive(h_staged);  // the store warp takes it from here
     }
 
     for (int c = 8; c < NCHUNK; ++c) hidden_epilogue(c);
@@ -541,12 +567,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     } else {
       tmem_ld32(lane_addr + COL_D2B, v);
       tmem_wait_ld();
-      if (live) {
-        float* dl = p.logits + (size_t)g * p.num_actions;
+      // logits [rows][A] of this CTA are one contiguous block: stage row-major, store linearly
+      const int A = p.num_actions;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < p.num_actions) dl[j] = __uint_as_float(v[j]) + sTail[T_POL_B + j];
-      }
+      for (int j = 0; j < 32; ++j)
+        if (j < A) sLog[row * A + j] = __uint_as_float(v[j]) + sTail[T_POL_B + j];
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four warps of this group
+      const int rows_here = min(ROWS, p.batch - blockIdx.x * ROWS);
+      float* dl = p.logits + (size_t)blockIdx.x * ROWS * A;
+      for (int i = row; i < rows_here * A; i += ROWS) dl[i] = sLog[i];
     }
     tc_fence_before();
     if (stamp) TC_STAMP(43);
@@ -608,7 +637,7 @@ long long* g_tc_trace = nullptr;
 
 size_t tc_smem_bytes(int k1) {
   return (size_t)ROWS * k1 * 2 + (size_t)STAGES * stage_bytes_for(k1) +
-         20 * sizeof(uint64_t) + TAIL_FLOATS * sizeof(float);
+         21 * sizeof(uint64_t) + TAIL_FLOATS * sizeof(float) + ROWS * (OUT_STRIDE + 32) * sizeof(float);
 }
 
 }  // namespace
