@@ -321,6 +321,40 @@ int mz_sumtree_sample(const double* tree, int64_t max_capacity, int32_t n, const
                       int64_t* pos, int64_t* chunk_start, int32_t* chunk_len, double* is_weights,
                       void* stream);
 
+/* ------------------------------------------------------------------------------------------- */
+/* MuZeroNetwork (residual conv tower, networks.py:393-554) on tcgen05 tensor cores, bf16/f32 acc. */
+/* Activations: channels-last bf16 with a one-pixel zero border, 8 x 8 = 64 rows of 128 channels   */
+/* per game (interior 6 x 6), so a 3x3 tap is a row shift and the implicit GEMM needs no im2col.   */
+/* ------------------------------------------------------------------------------------------- */
+#define MZ_CONV_RELU 1      /* max(x, 0) */
+#define MZ_CONV_RESIDUAL 2  /* += residual before the ReLU            ResidualBlock.forward networks.py:384-391 */
+#define MZ_CONV_ACTION 4    /* += actions[g] / A * plane_term[pixel]  MuZeroNetwork.attach_action networks.py:536-541 */
+#define MZ_CONV_SCALE 8     /* also emit (x - min_c) / (max_c - min_c) MuZeroNetwork.scale_state networks.py:543-547 */
+/* Conv2d(128 -> 128, 3x3, padding 1) with BatchNorm2d (eval) folded into w_packed / bias.
+ *   x          [x_rows][128] bf16; game g's 64-row block starts at row x_row_base[g] (NULL: g * 64)
+ *              -- this is how the hidden-state pool is gathered in place (row = (g*(S+1)+parent)*64)
+ *   w_packed   [128][9*128] bf16, k = (ky*3 + kx)*128 + c_in;   bias [128] f32
+ *   plane_term [36][128] f32, actions [games] i32 (flags & MZ_CONV_ACTION)
+ *   residual [..][128] bf16 with game g's block at row res_row_base[g] (NULL: g * 64);
+ *   out [games*64][128] bf16, may be NULL with MZ_CONV_SCALE
+ *   out_scaled [..][128] bf16, block of game g at row scaled_row_base[g] (NULL: g * 64)
+ * games must be even (a tile is two games). */
+int mz_conv3x3_tc(int32_t games, const void* x, int64_t x_rows, const int32_t* x_row_base,
+                  const void* w_packed, const float* bias, int32_t flags, const float* plane_term,
+                  const int32_t* actions, int32_t num_actions, const void* residual,
+                  const int32_t* res_row_base, void* out, void* out_scaled,
+                  const int32_t* scaled_row_base, void* stream);
+/* Linear(6*6*128 -> n_out) (+ReLU) of the heads over the padded state: x [games][8192] bf16,
+ * w_packed [n_out][8192] bf16 in the padded channels-last order, out [games][ldo] f32;
+ * n_out % 128 == 0.  networks.py:436-439, 470-478. */
+int mz_conv_fc_tc(int32_t games, const void* x, const void* w_packed, const float* bias, int32_t n_out,
+                  int32_t relu, float* out, int32_t ldo, void* stream);
+/* Second head layer Linear(512 -> outs <= 32) on CUDA cores; to_scalar: Config.inverse_transform
+ * (config.py:27-33) -> one float per game. */
+int mz_conv_head(int32_t games, const float* hidden, int32_t ldh, const float* w2, const float* b2,
+                 int32_t outs, int32_t to_scalar, int32_t support_min, int32_t no_target_transform,
+                 float* out, int32_t ldo, void* stream);
+
 /* Diagnostics: compares the constant-divisor division used by the descent's MinMax normalisation
  * with IEEE division on blocks*256*per_thread pseudo-random operand pairs; adds the number of
  * differing results to *mismatches and the number of pairs checked to *tested (device u64). */

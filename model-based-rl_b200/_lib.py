@@ -97,6 +97,11 @@ _SIGNATURES = {
                                  _V, _V]),
     "mz_sumtree_sample": (C.c_int, [_V, C.c_int64, C.c_int32, _V, _V, _V, _V, C.c_int64, C.c_double,
                                     _V, _V, _V, _V, _V, _V, _V]),
+    "mz_conv3x3_tc": (C.c_int, [C.c_int32, _V, C.c_int64, _V, _V, _V, C.c_int32, _V, _V, C.c_int32, _V, _V,
+                                _V, _V, _V, _V]),
+    "mz_conv_fc_tc": (C.c_int, [C.c_int32, _V, _V, _V, C.c_int32, C.c_int32, _V, C.c_int32, _V]),
+    "mz_conv_head": (C.c_int, [C.c_int32, _V, C.c_int32, _V, _V, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_int32, _V, C.c_int32, _V]),
     "mz_debug_div_check": (C.c_int, [C.c_uint64, C.c_int32, C.c_int32, _V, _V, _V]),
     "mz_version": (C.c_char_p, []),
     "mz_compiled_arch": (C.c_int32, []),

@@ -1,0 +1,554 @@
+// MuZeroNetwork (residual conv tower on 6x6x128 hidden states) on the 5th-generation tensor cores.
+//
+// One persistent implicit-GEMM kernel serves every dense layer of recurrent_inference
+// (networks.py:393-554: MuZeroDynamics conv + 16 ResidualBlocks + reward head, MuZeroPrediction 16
+// ResidualBlocks + value / policy heads):
+//
+//   conv3x3 (pad 1, stride 1) with BatchNorm folded:  D[row, n] = sum_{tap, c} X[row + off(tap), c] *
+//       W[n, tap * 128 + c],   off(tap) = (ky - 1) * 8 + (kx - 1)
+//   on activations stored channels-last in bf16 with a one-pixel zero border: a game is 8 x 8 = 64
+//   rows of 128 channels (interior 6 x 6), so a tap is a pure row shift and the A operand of every
+//   tap is a TMA tile load at a shifted row coordinate -- no im2col buffer exists anywhere.
+//   Linear(6*6*128 -> 512) heads: the same kernel with one "tap", K = 64 * 128 (the border rows
+//   are zero, the weights are permuted to the padded channels-last order at pack time).
+//
+// Tile: 128 rows (two games, or 128 games for the heads) x 128 outputs, K blocks of 64 bf16 (one
+// 128-byte swizzle row).  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (tcgen05.mma,
+// accumulators in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1),
+// warps 2..5 = epilogue (tcgen05.ld, bias / action plane / residual / ReLU / per-pixel min-max
+// scaling, bf16 stores).  CTAs are persistent over tiles.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "mz_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int STAGES = 6;
+constexpr int STAGE_BYTES = (BM + BN) * BK * 2;  // 32 KB
+constexpr int CONV_THREADS = 192;                // producer, MMA, 4 epilogue warps
+constexpr int ACC_COLS = 256;                    // two accumulators of 128 fp32 columns
+
+enum : int {
+  EPI_RELU = 1,        // max(x, 0)
+  EPI_RESIDUAL = 2,    // += residual[row] before the ReLU
+  EPI_ACTION = 4,      // += action[g] / A * plane_term[pixel][n]   (MuZeroNetwork.attach_action)
+  EPI_SCALE = 8,       // also emit (x - min_c) / (max_c - min_c) per pixel (scale_state)
+  EPI_F32_OUT = 16,    // heads: fp32 row-major output [M][ldo], no border masking
+};
+
+struct ConvParams {
+  int mode_fc;               // 0: conv taps, 1: plain GEMM (heads)
+  int num_tiles_m, num_tiles_n, num_kblocks;
+  int rows_total;            // conv: games * 64; fc: games
+  int flags;
+  int num_actions;
+  const int32_t* row_base;   // conv: [games] first row of each game's 64-row block in the A tensor
+                             // (hidden-pool gather), or nullptr = g * 64
+  const float* bias;         // [N_total]
+  const float* plane_term;   // [36][128] (EPI_ACTION)
+  const int32_t* actions;    // [games]   (EPI_ACTION)
+  const __nv_bfloat16* residual;  // [..][128] (EPI_RESIDUAL); game g's block at res_row_base[g] or g * 64
+  const int32_t* res_row_base;
+  __nv_bfloat16* out;        // conv: [rows][128] bf16
+  __nv_bfloat16* out_scaled; // EPI_SCALE: rows of game g start at out_scaled + scaled_row_base[g] * 128
+  const int32_t* scaled_row_base;  // [games] or nullptr = g * 64
+  float* out_f32;            // EPI_F32_OUT: [M][ldo]
+  int ldo;
+};
+
+MZ_DEV bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
+MZ_DEV void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+MZ_DEV void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+MZ_DEV void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+MZ_DEV void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+MZ_DEV void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+MZ_DEV void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+MZ_DEV void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+MZ_DEV void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+MZ_DEV void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+MZ_DEV void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr)
+      : "memory");
+}
+template <bool ACC>
+MZ_DEV void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  if (ACC)
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+// K-major operand tile written by TMA with SWIZZLE_128B: rows of 128 bytes, 8-row atoms of 1024 B
+MZ_DEV uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;                        // leading byte offset: unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: one 8-row atom
+  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// D = f32, A = B = bf16, both K-major, M = 128, N = 128
+MZ_DEV uint32_t make_idesc_128x128() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+MZ_DEV uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;    // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.num_tiles_m * p.num_tiles_n;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, ACC_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / p.num_tiles_n, tn = tile % p.num_tiles_n;
+      int rb0, rb1;
+      if (p.mode_fc) {
+        rb0 = tm * BM;
+        rb1 = rb0 + 64;
+      } else {
+        const int g0 = tm * 2;
+        rb0 = p.row_base ? p.row_base[g0] : g0 * 64;
+        rb1 = p.row_base ? p.row_base[g0 + 1] : (g0 + 1) * 64;
+      }
+      for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
+        const int st = it % STAGES;
+        mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + st * STAGE_BYTES;
+          uint8_t* sb = sa + BM * BK * 2;
+          int shift = 0, ka = kb * BK;
+          if (!p.mode_fc) {  // k block = (tap, channel half)
+            const int tap = kb >> 1;
+            shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
+            ka = (kb & 1) * BK;
+          }
+          mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+          tma_load_2d(sa, &map_a, ka, rb0 + shift, &full[st]);
+          tma_load_2d(sa + 64 * BK * 2, &map_a, ka, rb1 + shift, &full[st]);
+          tma_load_2d(sb, &map_b, kb * BK, tn * BN, &full[st]);
+          tma_load_2d(sb + 64 * BK * 2, &map_b, kb * BK, tn * BN + 64, &full[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = make_idesc_128x128();
+    int it = 0, t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int acc = t & 1;
+      mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem + acc * BN;
+      for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
+        const int st = it % STAGES;
+        mbar_wait(&full[st], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + st * STAGE_BYTES);
+        const uint64_t ad = make_desc_sw128(sa), bd = make_desc_sw128(sa + BM * BK * 2);
+        if (elect_one()) {
+          if (kb == 0) umma_ss<false>(d, ad, bd, idesc);
+          else umma_ss<true>(d, ad, bd, idesc);
+#pragma unroll
+          for (int ks = 1; ks < BK / 16; ++ks)  // +32 bytes along K inside the 128-byte swizzle row
+            umma_ss<true>(d, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc);
+          tc_commit(&empty[st]);
+          if (kb == p.num_kblocks - 1) tc_commit(&acc_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue: thread = accumulator row =====
+    const int quarter = warp & 3;
+    const int r_in_tile = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int acc = t & 1;
+      const int tm = tile / p.num_tiles_n, tn = tile % p.num_tiles_n;
+      mbar_wait(&acc_full[acc], (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t d = lane_addr + acc * BN;
+      if (p.flags & EPI_F32_OUT) {
+        const int row = tm * BM + r_in_tile;
+        float* orow = p.out_f32 + (size_t)row * p.ldo + tn * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(d + c0, v);
+          tmem_wait_ld();
+          if (row < p.rows_total) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              o.x = __uint_as_float(v[j]) + p.bias[tn * BN + c0 + j];
+              o.y = __uint_as_float(v[j + 1]) + p.bias[tn * BN + c0 + j + 1];
+              o.z = __uint_as_float(v[j + 2]) + p.bias[tn * BN + c0 + j + 2];
+              o.w = __uint_as_float(v[j + 3]) + p.bias[tn * BN + c0 + j + 3];
+              if (p.flags & EPI_RELU) {
+                o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f);
+              }
+              *reinterpret_cast<float4*>(orow + c0 + j) = o;
+            }
+          }
+        }
+      } else {
+        const int g = tm * 2 + (r_in_tile >> 6);
+        const int pos = r_in_tile & 63, py = pos >> 3, px = pos & 7;
+        const bool interior = py >= 1 && py <= 6 && px >= 1 && px <= 6;
+        const size_t row = (size_t)g * 64 + pos;
+        const bool in_range = row < (size_t)p.rows_total;
+        float act_scale = 0.0f;
+        const float* plane = nullptr;
+        if ((p.flags & EPI_ACTION) && interior && in_range) {
+          act_scale = (float)p.actions[g] / (float)p.num_actions;
+          plane = p.plane_term + ((py - 1) * 6 + (px - 1)) * BN;
+        }
+        const size_t rrow = (p.res_row_base && in_range ? (size_t)p.res_row_base[g] : (size_t)g * 64) + pos;
+        const uint4* res = reinterpret_cast<const uint4*>(p.residual + rrow * BN);
+        uint4* orow = reinterpret_cast<uint4*>(p.out + row * BN);
+        const bool add_res = (p.flags & EPI_RESIDUAL) && interior && in_range;
+        // x[0..32) = layer output for channels c0..c0+31 of this row (zero on the border)
+        auto chunk = [&](int c0, float (&x)[32]) {
+          uint32_t v[32];
+          tmem_ld32(d + c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + p.bias[c0 + j];
+          if (plane) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fmaf(act_scale, __ldg(plane + c0 + j), x[j]);
+          }
+          if (add_res) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rv = res[(c0 >> 3) + q];
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[h]);
+                x[q * 8 + 2 * h] += __low2float(b2);
+                x[q * 8 + 2 * h + 1] += __high2float(b2);
+              }
+            }
+          }
+          if (p.flags & EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+          }
+          if (!interior) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = 0.0f;  // keep the zero border of the padded layout
+          }
+        };
+        float mn = INFINITY, mx = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float x[32];
+          chunk(c0, x);
+          if (p.flags & EPI_SCALE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              mn = fminf(mn, x[j]);
+              mx = fmaxf(mx, x[j]);
+            }
+          }
+          if (in_range && p.out) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              orow[(c0 >> 3) + q] = make_uint4(pack_bf16(x[q * 8], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                                               pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
+          }
+        }
+        if ((p.flags & EPI_SCALE) && in_range) {
+          // MuZeroNetwork.scale_state networks.py:543-547: second pass over the accumulator row
+          const size_t srow = (p.scaled_row_base ? (size_t)p.scaled_row_base[g] : (size_t)g * 64) + pos;
+          uint4* so = reinterpret_cast<uint4*>(p.out_scaled + srow * BN);
+          const float den = mx - mn;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            float x[32];
+            chunk(c0, x);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = interior ? (x[j] - mn) / den : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              so[(c0 >> 3) + q] = make_uint4(pack_bf16(x[q * 8], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                                             pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acc]);
+    }
+  }
+
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, ACC_COLS);
+  }
+}
+
+// ---- heads: relu(fc1) [G][512] -> Linear(512 -> bins) (+ softmax expectation + h^-1) --------------
+// One warp per game.  networks.py:438-440, 477-483; config.py:27-33.
+__global__ void conv_head_kernel(int G, const float* __restrict__ hidden, int ldh, const float* __restrict__ w2,
+                                 const float* __restrict__ b2, int outs, int to_scalar, int support_min,
+                                 int no_tt, float* __restrict__ out, int ldo);
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// [rows][cols] bf16 row-major (cols contiguous), box = 64 rows x 64 cols, 128-byte swizzle
+int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return MZ_ERR_UNSUPPORTED;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, 64};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MZ_OK : 1000 + (int)r;
+}
+
+constexpr size_t kConvSmem = 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * sizeof(uint64_t) + 16;
+
+int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, void* stream) {
+  static bool attr = false;
+  static int sms = 0;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kConvSmem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    attr = true;
+  }
+  const int tiles = p.num_tiles_m * p.num_tiles_n;
+  const int grid = tiles < sms ? tiles : sms;
+  conv_gemm_tc_kernel<<<grid, CONV_THREADS, kConvSmem, (cudaStream_t)stream>>>(ma, mb, p);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+__global__ void conv_head_kernel(int G, const float* __restrict__ hidden, int ldh, const float* __restrict__ w2,
+                                 const float* __restrict__ b2, int outs, int to_scalar, int support_min,
+                                 int no_tt, float* __restrict__ out, int ldo) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= G) return;
+  const float* h = hidden + (size_t)g * ldh;
+  float hv[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) hv[i] = h[lane + 32 * i];
+  float mine = 0.0f;  // lane o keeps output o
+  for (int o = 0; o < outs; ++o) {
+    const float* w = w2 + (size_t)o * 512;
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s = fmaf(hv[i], w[lane + 32 * i], s);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(MZ_FULL, s, m);
+    if (lane == o) mine = s + b2[o];
+  }
+  if (!to_scalar) {
+    if (lane < outs) out[(size_t)g * ldo + lane] = mine;
+    return;
+  }
+  // Config.inverse_transform config.py:27-33: softmax expectation over the support, then h^-1
+  float m = lane < outs ? mine : -INFINITY;
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) m = fmaxf(m, __shfl_xor_sync(MZ_FULL, m, k));
+  const float e = lane < outs ? expf(mine - m) : 0.0f;
+  float den = e, num = e * (float)(support_min + lane);
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) {
+    den += __shfl_xor_sync(MZ_FULL, den, k);
+    num += __shfl_xor_sync(MZ_FULL, num, k);
+  }
+  if (lane == 0) {
+    float x = num / den;
+    if (!no_tt) {
+      const float eps = 0.001f;
+      const float sgn = x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f);
+      const float t = (sqrtf(1.0f + 4.0f * eps * (fabsf(x) + 1.0f + eps)) - 1.0f) / (2.0f * eps);
+      x = sgn * (t * t - 1.0f);
+    }
+    out[(size_t)g * ldo] = x;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// 3x3 convolution (+ folded BatchNorm, bias, optional action plane / residual / ReLU / state scaling)
+// over `games` hidden states in the padded channels-last bf16 layout (64 rows x 128 channels per game).
+//   x            A tensor: [x_rows][128] bf16; game g's block starts at row x_row_base[g] (or g * 64)
+//   w_packed     [128][9 * 128] bf16, k = (ky * 3 + kx) * 128 + c_in
+//   bias         [128] f32;  plane_term [36][128] f32 and actions [games] when flags & 4
+//   residual (+ res_row_base like x), out [games * 64][128] bf16;  out_scaled + scaled_row_base like
+//   x when flags & 8
+int mz_conv3x3_tc(int32_t games, const void* x, int64_t x_rows, const int32_t* x_row_base,
+                  const void* w_packed, const float* bias, int32_t flags, const float* plane_term,
+                  const int32_t* actions, int32_t num_actions, const void* residual,
+                  const int32_t* res_row_base, void* out, void* out_scaled,
+                  const int32_t* scaled_row_base, void* stream) {
+  if (games < 1 || (games & 1) || !x || !w_packed || !bias || x_rows < 64) return MZ_ERR_BAD_ARG;
+  if ((flags & EPI_ACTION) && (!plane_term || !actions || num_actions < 1)) return MZ_ERR_BAD_ARG;
+  if ((flags & EPI_RESIDUAL) && !residual) return MZ_ERR_BAD_ARG;
+  if ((flags & EPI_SCALE) && !out_scaled) return MZ_ERR_BAD_ARG;
+  if (!(flags & EPI_SCALE) && !out) return MZ_ERR_BAD_ARG;
+  if (flags & EPI_F32_OUT) return MZ_ERR_BAD_ARG;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, x, (uint64_t)x_rows, 128);
+  if (rc) return rc;
+  rc = make_map(&mb, w_packed, 128, 9 * 128);
+  if (rc) return rc;
+  ConvParams p = {};
+  p.mode_fc = 0;
+  p.num_tiles_m = games / 2;
+  p.num_tiles_n = 1;
+  p.num_kblocks = 18;
+  p.rows_total = games * 64;
+  p.flags = flags;
+  p.num_actions = num_actions;
+  p.row_base = x_row_base;
+  p.bias = bias;
+  p.plane_term = plane_term;
+  p.actions = actions;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.res_row_base = res_row_base;
+  p.out = (__nv_bfloat16*)out;
+  p.out_scaled = (__nv_bfloat16*)out_scaled;
+  p.scaled_row_base = scaled_row_base;
+  return launch_conv(ma, mb, p, stream);
+}
+
+// Linear(64 * 128 -> n_out) over the padded channels-last state (border rows are zero), bias + ReLU:
+//   x [games][8192] bf16 (the activation buffer itself), w_packed [n_out][8192] bf16 (n_out % 128 == 0),
+//   out [games][ldo] f32.   networks.py:436-439, 470-478.
+int mz_conv_fc_tc(int32_t games, const void* x, const void* w_packed, const float* bias, int32_t n_out,
+                  int32_t relu, float* out, int32_t ldo, void* stream) {
+  if (games < 1 || !x || !w_packed || !bias || !out || n_out < 128 || (n_out % 128) || ldo < n_out)
+    return MZ_ERR_BAD_ARG;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, x, (uint64_t)games, 8192);
+  if (rc) return rc;
+  rc = make_map(&mb, w_packed, (uint64_t)n_out, 8192);
+  if (rc) return rc;
+  ConvParams p = {};
+  p.mode_fc = 1;
+  p.num_tiles_m = (games + BM - 1) / BM;
+  p.num_tiles_n = n_out / BN;
+  p.num_kblocks = 8192 / BK;
+  p.rows_total = games;
+  p.flags = EPI_F32_OUT | (relu ? EPI_RELU : 0);
+  p.bias = bias;
+  p.out_f32 = out;
+  p.ldo = ldo;
+  return launch_conv(ma, mb, p, stream);
+}
+
+// Second layer of a head on CUDA cores: out = hidden[g] . w2^T + b2 (outs <= 32); to_scalar != 0
+// applies Config.inverse_transform (softmax expectation over [support_min, support_min + outs) and
+// h^-1 unless no_target_transform) and writes one float per game.
+int mz_conv_head(int32_t games, const float* hidden, int32_t ldh, const float* w2, const float* b2,
+                 int32_t outs, int32_t to_scalar, int32_t support_min, int32_t no_target_transform,
+                 float* out, int32_t ldo, void* stream) {
+  if (games < 1 || !hidden || !w2 || !b2 || !out || outs < 1 || outs > 32 || ldh < 512) return MZ_ERR_BAD_ARG;
+  const int threads = 256, grid = (games * 32 + threads - 1) / threads;
+  conv_head_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(games, hidden, ldh, w2, b2, outs, to_scalar,
+                                                               support_min, no_target_transform, out, ldo);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,358 @@
+"""Inference side of the reference's MuZeroNetwork (networks.py:372-554) on tcgen05 tensor cores.
+
+`MuZeroNetwork` keeps the reference's constructor, `initial_inference` / `recurrent_inference`
+(NetworkOutput(value, reward, policy_logits, hidden_state), eval mode: scalars after the
+softmax-expectation + h^-1 of config.py:27-33) and `load_weights` / `get_weights` with the
+reference's state-dict keys.  Underneath, every dense layer of `recurrent_inference` -- 65 3x3
+convolutions with BatchNorm folded, the three Linear(4608 -> 512) heads -- is one launch of the
+implicit-GEMM kernel in csrc/mz_conv_tc.cu on bf16 activations in a padded channels-last layout
+(64 rows x 128 channels per game), and the hidden-state pool of the search is read and written in
+place through per-game row offsets.
+
+Round-1 limitation, stated in DESIGN.md: the representation tower (`initial_inference`, once per
+move, 96x96 inputs with strided convolutions and pooling) runs through torch operators in float32;
+its output enters the tensor-core path at the prediction tower.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .networks import NetworkOutput
+
+CH = 128          # channels of the hidden state
+ROWS = 64         # padded 8 x 8 positions per game
+K_FC = ROWS * CH  # 8192: flattened padded state
+RELU, RESIDUAL, ACTION, SCALE = 1, 2, 4, 8
+BN_EPS = 1e-5
+
+
+def to_padded(state):
+  """[B, 128, 6, 6] float -> [B * 64, 128] bf16 rows (zero border, channels last)."""
+  b = state.shape[0]
+  x = F.pad(state.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1))
+  return x.reshape(b * ROWS, CH).to(torch.bfloat16).contiguous()
+
+
+def from_padded(rows, b):
+  """[B * 64, 128] bf16 rows -> [B, 128, 6, 6] float32."""
+  x = rows.reshape(b, 8, 8, CH)[:, 1:7, 1:7, :]
+  return x.permute(0, 3, 1, 2).float().contiguous()
+
+
+class _Conv(object):
+  """One folded convolution: packed bf16 weights [128][1152], float32 bias (+ action-plane term)."""
+
+  def __init__(self, weight, conv_bias, bn, device):
+    w = weight.to(device, torch.float32)
+    if bn is not None:
+      gamma, beta, mean, var = [t.to(device, torch.float32) for t in bn]
+      scale = gamma / torch.sqrt(var + BN_EPS)
+      w = w * scale[:, None, None, None]
+      bias = beta - mean * scale
+      if conv_bias is not None:
+        bias = bias + conv_bias.to(device, torch.float32) * scale
+    else:
+      bias = conv_bias.to(device, torch.float32) if conv_bias is not None else torch.zeros(CH, device=device)
+    self.plane = None
+    if w.shape[1] == CH + 1:  # MuZeroDynamics.conv: the 129th input channel is the action plane
+      ones = torch.ones((1, 1, 6, 6), device=device)
+      # what a constant plane of ones contributes at each interior pixel (zero padding outside)
+      self.plane = F.conv2d(ones, w[:, CH:], None, 1, 1)[0].permute(1, 2, 0).reshape(36, CH).contiguous()
+      w = w[:, :CH]
+    self.w = w.permute(0, 2, 3, 1).reshape(CH, 9 * CH).to(torch.bfloat16).contiguous()
+    self.bias = bias.contiguous()
+
+
+def _pack_fc(weight, device):
+  """Linear(128*6*6 -> n) weight [n, c*36 + y*6 + x] -> [n, ((y+1)*8 + (x+1))*128 + c] bf16."""
+  n = weight.shape[0]
+  w = weight.to(device, torch.float32).reshape(n, CH, 6, 6).permute(0, 2, 3, 1)
+  out = torch.zeros((n, 8, 8, CH), dtype=torch.float32, device=device)
+  out[:, 1:7, 1:7, :] = w
+  return out.reshape(n, K_FC).to(torch.bfloat16).contiguous()
+
+
+class MuZeroNetwork(object):
+
+  accepts_device_actions = True
+  training = False
+
+  def __init__(self, input_channels, action_space, device, config):
+    _lib.require_cuda()
+    if getattr(config, 'no_support', False):
+      raise NotImplementedError("no_support networks are not on the B200 path")
+    self.lib = _lib.load()
+    self.device = _lib.normalize_device(device)
+    self.input_channels = int(input_channels)
+    self.action_space = int(action_space)
+    if self.action_space > 32:
+      raise NotImplementedError("the head kernel supports action_space <= 32")
+    self.value_min, self.value_max = [int(v) for v in config.value_support]
+    self.reward_min, self.reward_max = [int(v) for v in config.reward_support]
+    self.value_bins = self.value_max - self.value_min + 1
+    self.reward_bins = self.reward_max - self.reward_min + 1
+    self.no_target_transform = bool(getattr(config, 'no_target_transform', False))
+    self._state = None
+    self._bufs = {}
+
+  # -- weights -----------------------------------------------------------------------------------
+  def load_weights(self, weights):
+    """Accepts the reference's state dict (networks.py:549-550); folds BatchNorm (eval statistics)
+    into the convolutions and packs everything for the tensor-core kernels."""
+    dev = self.device
+    sd = {k: torch.as_tensor(v).detach() for k, v in weights.items()}
+    self._state = {k: v.to(dev) for k, v in sd.items()}
+
+    def bn(p):
+      return (sd[p + '.weight'], sd[p + '.bias'], sd[p + '.running_mean'], sd[p + '.running_var'])
+
+    def tower(p):
+      convs = []
+      for i in range(16):
+        b = '%s.resblocks.%d' % (p, i)
+        convs.append(_Conv(sd[b + '.conv1.weight'], None, bn(b + '.bn1'), dev))
+        convs.append(_Conv(sd[b + '.conv2.weight'], None, bn(b + '.bn2'), dev))
+      return convs
+
+    d, q = 'dynamics_head', 'prediction_head'
+    if sd[d + '.conv.weight'].shape != (CH, CH + 1, 3, 3):
+      raise ValueError("dynamics_head.conv.weight has shape %s" % (tuple(sd[d + '.conv.weight'].shape),))
+    self.dyn_conv = _Conv(sd[d + '.conv.weight'], sd[d + '.conv.bias'], bn(d + '.bn'), dev)
+    self.dyn_tower = tower(d)
+    self.pred_tower = tower(q)
+    f32 = lambda k: sd[k].to(dev, torch.float32).contiguous()
+    self.rew_fc1_w = _pack_fc(sd[d + '.fc1.weight'], dev)
+    self.rew_fc1_b = f32(d + '.fc1.bias')
+    self.rew_fc2_w, self.rew_fc2_b = f32(d + '.fc2.weight'), f32(d + '.fc2.bias')
+    # value and policy heads read the same state: one GEMM with 1024 outputs
+    self.vp_fc1_w = torch.cat((_pack_fc(sd[q + '.fc_value.weight'], dev),
+                               _pack_fc(sd[q + '.fc_policy.weight'], dev)), dim=0).contiguous()
+    self.vp_fc1_b = torch.cat((f32(q + '.fc_value.bias'), f32(q + '.fc_policy.bias'))).contiguous()
+    self.val_fc2_w, self.val_fc2_b = f32(q + '.fc_value_o.weight'), f32(q + '.fc_value_o.bias')
+    self.pol_fc2_w, self.pol_fc2_b = f32(q + '.fc_policy_o.weight'), f32(q + '.fc_policy_o.bias')
+    if self.rew_fc2_w.shape[0] != self.reward_bins or self.val_fc2_w.shape[0] != self.value_bins or \
+        self.pol_fc2_w.shape[0] != self.action_space:
+      raise ValueError("head widths do not match config supports / action_space")
+
+  load_state_dict = load_weights
+
+  def get_weights(self):
+    return {k: v.cpu() for k, v in self._state.items()}
+
+  def state_dict(self):
+    return dict(self._state)
+
+  def to(self, device):
+    if torch.device(device).type != 'cuda':
+      raise RuntimeError("the B200 MuZeroNetwork only runs on CUDA devices")
+    return self
+
+  def eval(self):
+    return self
+
+  def train(self, mode=True):
+    if mode:
+      raise NotImplementedError("training stays with the reference's torch module; this class is "
+                                "the inference path (load_weights moves parameters across)")
+    return self
+
+  # -- buffers ---------------------------------------------------------------------------------------
+  def buffers(self, games):
+    """Scratch activations for `games` (even) games: three padded bf16 buffers and the head
+    hidden layer [games][reward 512 | value 512 | policy 512] float32."""
+    b = self._bufs.get(games)
+    if b is None:
+      dev = self.device
+      b = dict(x=[torch.zeros((games * ROWS, CH), dtype=torch.bfloat16, device=dev) for _ in range(3)],
+               fc=torch.zeros((games, 1536), dtype=torch.float32, device=dev))
+      self._bufs[games] = b
+    return b
+
+  # -- launches --------------------------------------------------------------------------------------
+  def _conv(self, games, conv, x, x_rows, x_base, flags, out, residual=None, res_base=None, actions=None,
+            out_scaled=None, scaled_base=None):
+    P = _lib.ptr
+    _lib.check(self.lib.mz_conv3x3_tc(games, P(x), x_rows, P(x_base), P(conv.w), P(conv.bias), flags,
+                                      P(conv.plane) if flags & ACTION else None, P(actions),
+                                      self.action_space, P(residual), P(res_base), P(out), P(out_scaled),
+                                      P(scaled_base), _lib.current_stream()), "mz_conv3x3_tc")
+
+  def _tower(self, games, convs, x, x_rows, x_base, bufs, last_flags=0, out_scaled=None, scaled_base=None):
+    """16 ResidualBlocks (networks.py:372-391) starting from tensor `x` (optionally gathered through
+    x_base).  Returns the scratch buffer holding the (unscaled) output."""
+    cur, cur_rows, cur_base = x, x_rows, x_base
+    for i in range(16):
+      t, o = [b for b in bufs if b.data_ptr() != cur.data_ptr()][:2]
+      self._conv(games, convs[2 * i], cur, cur_rows, cur_base, RELU, t)
+      extra = last_flags if i == 15 else 0
+      self._conv(games, convs[2 * i + 1], t, games * ROWS, None, RELU | RESIDUAL | extra, o, residual=cur,
+                 res_base=cur_base, out_scaled=out_scaled if extra else None,
+                 scaled_base=scaled_base if extra else None)
+      cur, cur_rows, cur_base = o, games * ROWS, None
+    return cur
+
+  def run_recurrent(self, games, state, state_rows, state_base, actions, next_state, next_base, value,
+                    reward, logits):
+    """recurrent_inference (networks.py:31-34) for `games` (even) games on the current stream.
+      state      [state_rows][128] bf16, game g's padded block at row state_base[g] (None: g * 64)
+      actions    [games] int32 (device)
+      next_state [..][128] bf16, block of game g written at row next_base[g] (None: g * 64)
+      value, reward [games] f32, logits [games][A] f32 (device)"""
+    b = self.buffers(games)
+    X = b['x']
+    P = _lib.ptr
+    st = _lib.current_stream()
+    # dynamics: conv(129 -> 128) + bn + relu, 16 blocks, scale_state; reward head on the unscaled state
+    self._conv(games, self.dyn_conv, state, state_rows, state_base, RELU | ACTION, X[0], actions=actions)
+    raw = self._tower(games, self.dyn_tower, X[0], games * ROWS, None, X, last_flags=SCALE,
+                      out_scaled=next_state, scaled_base=next_base)
+    _lib.check(self.lib.mz_conv_fc_tc(games, P(raw), P(self.rew_fc1_w), P(self.rew_fc1_b), 512, 1,
+                                      P(b['fc']), 1536, st), "mz_conv_fc_tc")
+    _lib.check(self.lib.mz_conv_head(games, P(b['fc']), 1536, P(self.rew_fc2_w), P(self.rew_fc2_b),
+                                     self.reward_bins, 1, self.reward_min, int(self.no_target_transform),
+                                     P(reward), 1, st), "mz_conv_head")
+    # prediction on the scaled state
+    rows = next_state.shape[0]
+    self.run_prediction(games, next_state, rows, next_base, value, logits)
+
+  def run_prediction(self, games, state, state_rows, state_base, value, logits):
+    """prediction (networks.py:465-480 + inverse value transform) from a padded bf16 state."""
+    b = self.buffers(games)
+    P = _lib.ptr
+    st = _lib.current_stream()
+    out = self._tower(games, self.pred_tower, state, state_rows, state_base, b['x'])
+    fc_vp = b['fc'][:, 512:]
+    _lib.check(self.lib.mz_conv_fc_tc(games, P(out), P(self.vp_fc1_w), P(self.vp_fc1_b), 1024, 1,
+                                      C_ptr(fc_vp), 1536, st), "mz_conv_fc_tc")
+    _lib.check(self.lib.mz_conv_head(games, C_ptr(fc_vp), 1536, P(self.val_fc2_w), P(self.val_fc2_b),
+                                     self.value_bins, 1, self.value_min, int(self.no_target_transform),
+                                     P(value), 1, st), "mz_conv_head")
+    _lib.check(self.lib.mz_conv_head(games, C_ptr(b['fc'][:, 1024:]), 1536, P(self.pol_fc2_w),
+                                     P(self.pol_fc2_b), self.action_space, 0, 0, 0, P(logits),
+                                     self.action_space, st), "mz_conv_head")
+
+  # -- reference interface ---------------------------------------------------------------------------
+  def representation(self, observation):
+    """MuZeroRepresentation + scale_state (networks.py:412-426, 500-503); torch operators, float32."""
+    sd = self._state
+    obs = torch.as_tensor(observation).to(self.device, torch.float32)
+    p = 'representation_head.'
+
+    def bn(x, q):
+      return F.batch_norm(x, sd[q + '.running_mean'], sd[q + '.running_var'], sd[q + '.weight'],
+                          sd[q + '.bias'], False, 0.0, BN_EPS)
+
+    def block(x, q):
+      out = F.relu(bn(F.conv2d(x, sd[q + '.conv1.weight'], None, 1, 1), q + '.bn1'))
+      out = bn(F.conv2d(out, sd[q + '.conv2.weight'], None, 1, 1), q + '.bn2')
+      return F.relu(out + x)
+
+    out = F.conv2d(obs, sd[p + 'conv1.weight'], sd[p + 'conv1.bias'], 2, 1)
+    for i in range(2):
+      out = block(out, p + 'resblocks1.%d' % i)
+    out = F.conv2d(out, sd[p + 'conv2.weight'], sd[p + 'conv2.bias'], 2, 1)
+    for i in range(3):
+      out = block(out, p + 'resblocks2.%d' % i)
+    out = F.avg_pool2d(out, 3, 2, 1)
+    for i in range(3):
+      out = block(out, p + 'resblocks3.%d' % i)
+    out = F.avg_pool2d(out, 3, 2, 1)
+    for i in range(16):
+      out = block(out, p + 'resblocks.%d' % i)
+    mn = out.min(dim=1, keepdim=True)[0]
+    mx = out.max(dim=1, keepdim=True)[0]
+    return (out - mn) / (mx - mn)
+
+  def _even(self, b):
+    return b + (b & 1)
+
+  def initial_inference(self, observation):
+    """networks.py:26-29 (eval mode)."""
+    with torch.inference_mode():
+      hidden = self.representation(observation)
+      b = hidden.shape[0]
+      g = self._even(b)
+      rows = torch.zeros((g * ROWS, CH), dtype=torch.bfloat16, device=self.device)
+      rows[:b * ROWS] = to_padded(hidden)
+      value = torch.zeros(g, dtype=torch.float32, device=self.device)
+      logits = torch.zeros((g, self.action_space), dtype=torch.float32, device=self.device)
+      self.run_prediction(g, rows, g * ROWS, None, value, logits)
+    return NetworkOutput(value[:b].reshape(b, 1), 0, logits[:b], hidden)
+
+  def recurrent_inference(self, hidden_state, action):
+    """networks.py:31-34 (eval mode): hidden_state [B, 128, 6, 6], action: B ints (or an int32 CUDA
+    tensor)."""
+    with torch.inference_mode():
+      b = hidden_state.shape[0]
+      g = self._even(b)
+      dev = self.device
+      rows = torch.zeros((g * ROWS, CH), dtype=torch.bfloat16, device=dev)
+      rows[:b * ROWS] = to_padded(hidden_state.to(dev, torch.float32))
+      acts = torch.zeros(g, dtype=torch.int32, device=dev)
+      acts[:b] = torch.as_tensor(action, dtype=torch.int32).to(dev).reshape(-1)
+      nxt = torch.zeros((g * ROWS, CH), dtype=torch.bfloat16, device=dev)
+      value = torch.zeros(g, dtype=torch.float32, device=dev)
+      reward = torch.zeros(g, dtype=torch.float32, device=dev)
+      logits = torch.zeros((g, self.action_space), dtype=torch.float32, device=dev)
+      self.run_recurrent(g, rows, g * ROWS, None, acts, nxt, None, value, reward, logits)
+      hidden = from_padded(nxt[:b * ROWS], b)
+    return NetworkOutput(value[:b].reshape(b, 1), reward[:b].reshape(b, 1), logits[:b], hidden)
+
+
+def C_ptr(t):
+  """Pointer of a (possibly offset) view."""
+  import ctypes
+  return ctypes.c_void_p(t.data_ptr())
+
+
+def random_state_dict(input_channels, action_space, value_bins=31, reward_bins=31, seed=1234):
+  """Random-init weights of the MuZeroNetwork architecture under the reference's state-dict keys
+  (torch's default Conv2d / Linear initialisation, BatchNorm at its initial statistics)."""
+  import math
+  g = torch.Generator().manual_seed(seed)
+  sd = {}
+
+  def uniform(shape, bound):
+    return (torch.rand(shape, generator=g) * 2 - 1) * bound
+
+  def conv(p, cin, cout, bias):
+    bound = 1.0 / math.sqrt(cin * 9)
+    sd[p + '.weight'] = uniform((cout, cin, 3, 3), bound)
+    if bias:
+      sd[p + '.bias'] = uniform((cout,), bound)
+
+  def bn(p, c):
+    sd[p + '.weight'], sd[p + '.bias'] = torch.ones(c), torch.zeros(c)
+    sd[p + '.running_mean'], sd[p + '.running_var'] = torch.zeros(c), torch.ones(c)
+    sd[p + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.int64)
+
+  def blocks(p, n, c):
+    for i in range(n):
+      b = '%s.%d' % (p, i)
+      conv(b + '.conv1', c, c, False)
+      bn(b + '.bn1', c)
+      conv(b + '.conv2', c, c, False)
+      bn(b + '.bn2', c)
+
+  def linear(p, i, o):
+    bound = 1.0 / math.sqrt(i)
+    sd[p + '.weight'], sd[p + '.bias'] = uniform((o, i), bound), uniform((o,), bound)
+
+  r, q, d = 'representation_head', 'prediction_head', 'dynamics_head'
+  conv(r + '.conv1', input_channels, 64, True)
+  blocks(r + '.resblocks1', 2, 64)
+  conv(r + '.conv2', 64, 128, True)
+  blocks(r + '.resblocks2', 3, 128)
+  blocks(r + '.resblocks3', 3, 128)
+  blocks(r + '.resblocks', 16, 128)
+  blocks(q + '.resblocks', 16, 128)
+  linear(q + '.fc_value', 4608, 512)
+  linear(q + '.fc_value_o', 512, value_bins)
+  linear(q + '.fc_policy', 4608, 512)
+  linear(q + '.fc_policy_o', 512, action_space)
+  conv(d + '.conv', 129, 128, True)
+  bn(d + '.bn', 128)
+  blocks(d + '.resblocks', 16, 128)
+  linear(d + '.fc1', 4608, 512)
+  linear(d + '.fc2', 512, reward_bins)
+  return sd

@@ -455,12 +455,45 @@ def gen_fcnet(rng):
     print("fcnet", name, "params", sum(p.numel() for p in net.parameters()))
 
 
+def gen_muzero():
+  """MuZeroNetwork (networks.py:393-554) in eval mode on weights drawn by
+  oracle.muzero_ref.seeded_state_dict (23 M parameters are not committed, only the seed)."""
+  from oracle import muzero_ref
+  C_in, A, seed, B = 4, 18, 20261017, 2
+  cfg = make_config(action_space=A)
+  net = ref_networks.MuZeroNetwork(C_in, A, "cpu", cfg)
+  net.load_state_dict(muzero_ref.seeded_state_dict(C_in, A, seed))
+  net.eval()
+  g = torch.Generator().manual_seed(seed + 1)
+  obs = torch.rand((B, C_in, 96, 96), generator=g)
+  actions = [3, 17]
+  with torch.inference_mode():
+    init = net.initial_inference(obs)
+    rec = net.recurrent_inference(init.hidden_state, actions)
+    rec2 = net.recurrent_inference(rec.hidden_state, [0, 9])
+  np.savez_compressed(
+      os.path.join(HERE, "muzero_net.npz"), input_channels=np.int32(C_in), action_space=np.int32(A),
+      seed=np.int64(seed), obs=obs.numpy(), actions=np.array(actions, np.int32),
+      actions2=np.array([0, 9], np.int32), init_hidden=init.hidden_state.numpy(),
+      init_logits=init.policy_logits.numpy(), init_value=init.value.numpy(),
+      rec_hidden=rec.hidden_state.numpy(), rec_logits=rec.policy_logits.numpy(),
+      rec_value=rec.value.numpy(), rec_reward=rec.reward.numpy(),
+      rec2_hidden=rec2.hidden_state.numpy(), rec2_logits=rec2.policy_logits.numpy(),
+      rec2_value=rec2.value.numpy(), rec2_reward=rec2.reward.numpy())
+  print("muzero: value", init.value.flatten().tolist(), rec.value.flatten().tolist(), "reward",
+        rec.reward.flatten().tolist(), "hidden mean", float(rec.hidden_state.mean()))
+
+
 if __name__ == "__main__":
   torch.set_num_threads(1)
+  if len(sys.argv) > 1 and sys.argv[1] == "muzero":
+    gen_muzero()
+    sys.exit(0)
   rng = np.random.default_rng(20261017)
   gen_search(rng)
   gen_select_action(rng)
   gen_replay(rng)
   gen_transforms(rng)
   gen_fcnet(rng)
+  gen_muzero()
   print("python", sys.version.split()[0], "numpy", np.__version__, "torch", torch.__version__)

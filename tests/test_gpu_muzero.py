@@ -1,0 +1,157 @@
+"""GPU parity tests of the tensor-core MuZeroNetwork path (csrc/mz_conv_tc.cu) against the float32
+oracle (oracle/muzero_ref.py, pinned to the reference class by tests/test_oracle_golden.py) and the
+reference golden outputs.  Tolerances: bf16 operands (8-bit mantissa) through 33 / 65 layers with
+float32 accumulation -- stated per assertion."""
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import load
+
+pytestmark = pytest.mark.gpu
+
+CFG = types.SimpleNamespace(value_support=[-15, 15], reward_support=[-15, 15], no_support=False,
+                            no_target_transform=False)
+
+
+def _bf16(x):
+  return x.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("games,flags", [(2, 1), (6, 3), (300, 3), (4, 1 | 4), (4, 1 | 2 | 8)])
+def test_conv_kernel_matches_conv2d(games, flags):
+  """One launch of the implicit GEMM vs F.conv2d on the same bf16-rounded operands (float32 math):
+  only the accumulation order differs -> 2e-2 absolute on O(1) outputs after bf16 rounding of the
+  result."""
+  from model_based_rl_b200 import _lib, muzero
+  lib = _lib.load()
+  torch.manual_seed(games * 8 + flags)
+  dev = "cuda"
+  x = torch.rand((games, 128, 6, 6), device=dev)
+  cin = 129 if flags & 4 else 128
+  w = (torch.rand((128, cin, 3, 3), device=dev) * 2 - 1) * (3.0 / (cin * 9)) ** 0.5
+  bias = torch.randn(128, device=dev) * 0.1
+  conv = muzero._Conv(w, bias, None, dev)
+  rows = muzero.to_padded(x)
+  res = torch.rand((games, 128, 6, 6), device=dev)
+  res_rows = muzero.to_padded(res)
+  actions = torch.randint(0, 18, (games,), device=dev, dtype=torch.int32)
+  out = torch.full((games * 64, 128), 7.0, dtype=torch.bfloat16, device=dev)
+  scaled = torch.full((games * 64, 128), 7.0, dtype=torch.bfloat16, device=dev)
+  P = _lib.ptr
+  _lib.check(lib.mz_conv3x3_tc(games, P(rows), games * 64, None, P(conv.w), P(conv.bias), flags,
+                               P(conv.plane) if flags & 4 else None, P(actions), 18,
+                               P(res_rows) if flags & 2 else None, None, P(out),
+                               P(scaled) if flags & 8 else None, None, _lib.current_stream()), "conv")
+  torch.cuda.synchronize()
+  xin = _bf16(x)
+  wq = _bf16(conv.w.float().reshape(128, 3, 3, 128).permute(0, 3, 1, 2))
+  want = F.conv2d(xin, wq, None, 1, 1) + conv.bias[None, :, None, None]
+  if flags & 4:
+    plane = conv.plane.reshape(6, 6, 128).permute(2, 0, 1)
+    want = want + (actions.float() / 18)[:, None, None, None] * plane[None]
+  if flags & 2:
+    want = want + _bf16(res)
+  if flags & 1:
+    want = F.relu(want)
+  got = muzero.from_padded(out, games)
+  assert torch.allclose(got, want, rtol=1e-2, atol=2e-2), float((got - want).abs().max())
+  border = out.reshape(games, 8, 8, 128).float()
+  assert float(border[:, 0].abs().max()) == 0 and float(border[:, 7].abs().max()) == 0
+  assert float(border[:, :, 0].abs().max()) == 0 and float(border[:, :, 7].abs().max()) == 0
+  if flags & 8:
+    mn, mx = want.min(dim=1, keepdim=True)[0], want.max(dim=1, keepdim=True)[0]
+    want_s = (want - mn) / (mx - mn)
+    got_s = muzero.from_padded(scaled, games)
+    assert torch.allclose(got_s, want_s, rtol=1e-2, atol=2e-2), float((got_s - want_s).abs().max())
+
+
+def test_gathered_rows_and_fc_heads():
+  """x_row_base / scaled_row_base indirection (hidden-pool gather and scatter) and the Linear heads."""
+  from model_based_rl_b200 import _lib, muzero
+  lib = _lib.load()
+  dev = "cuda"
+  torch.manual_seed(5)
+  games, slots = 6, 5
+  pool = torch.zeros((games * slots * 64, 128), dtype=torch.bfloat16, device=dev)
+  x = torch.rand((games, 128, 6, 6), device=dev)
+  pick = torch.randint(0, slots, (games,), device=dev)
+  base = ((torch.arange(games, device=dev) * slots + pick) * 64).to(torch.int32)
+  rows = muzero.to_padded(x).reshape(games, 64, 128)
+  for g in range(games):
+    pool[int(base[g]):int(base[g]) + 64] = rows[g]
+  w = (torch.rand((128, 128, 3, 3), device=dev) * 2 - 1) * 0.05
+  conv = muzero._Conv(w, None, None, dev)
+  out = torch.zeros((games * 64, 128), dtype=torch.bfloat16, device=dev)
+  out_base = ((torch.arange(games, device=dev) * slots + (pick + 1) % slots) * 64).to(torch.int32)
+  P = _lib.ptr
+  _lib.check(lib.mz_conv3x3_tc(games, P(pool), pool.shape[0], P(base), P(conv.w), P(conv.bias), 1 | 2 | 8,
+                               None, None, 18, P(pool), P(base), P(out), P(pool), P(out_base),
+                               _lib.current_stream()), "conv")
+  torch.cuda.synchronize()
+  want = F.relu(F.conv2d(_bf16(x), _bf16(w), None, 1, 1) + _bf16(x))
+  assert torch.allclose(muzero.from_padded(out, games), want, rtol=1e-2, atol=2e-2)
+  mn, mx = want.min(dim=1, keepdim=True)[0], want.max(dim=1, keepdim=True)[0]
+  got_s = torch.stack([pool[int(out_base[g]):int(out_base[g]) + 64] for g in range(games)])
+  assert torch.allclose(muzero.from_padded(got_s.reshape(-1, 128), games), (want - mn) / (mx - mn),
+                        rtol=1e-2, atol=2e-2)
+  # heads: Linear(4608 -> 256) + ReLU over the padded rows, then Linear(512 -> 31) -> scalar
+  fcw = (torch.rand((256, 4608), device=dev) * 2 - 1) * 0.02
+  fcb = torch.randn(256, device=dev) * 0.1
+  hid = torch.zeros((games, 512), dtype=torch.float32, device=dev)
+  _lib.check(lib.mz_conv_fc_tc(games, P(out), P(muzero._pack_fc(fcw, dev)), P(fcb), 256, 1, P(hid), 512,
+                               _lib.current_stream()), "fc")
+  torch.cuda.synchronize()
+  flat = _bf16(muzero.from_padded(out, games)).reshape(games, -1)
+  want_h = F.relu(F.linear(flat, _bf16(fcw), fcb))
+  assert torch.allclose(hid[:, :256], want_h, rtol=1e-2, atol=1e-2)
+  w2 = torch.randn((31, 512), device=dev) * 0.05
+  b2 = torch.randn(31, device=dev) * 0.1
+  hid = torch.rand((games, 512), device=dev)
+  sc = torch.zeros(games, device=dev)
+  _lib.check(lib.mz_conv_head(games, P(hid), 512, P(w2), P(b2), 31, 1, -15, 0, P(sc), 1,
+                              _lib.current_stream()), "head")
+  torch.cuda.synchronize()
+  from oracle import muzero_ref
+  want_sc = muzero_ref.inverse_transform(F.linear(hid, w2, b2), -15, 15).flatten()
+  assert torch.allclose(sc, want_sc, rtol=1e-4, atol=1e-4)
+
+
+def test_network_matches_reference_golden():
+  """Whole network: initial_inference + two recurrent_inference steps on the golden weights."""
+  from model_based_rl_b200.muzero import MuZeroNetwork
+  from oracle import muzero_ref
+  g = load("muzero_net")
+  C_in, A = int(g["input_channels"]), int(g["action_space"])
+  net = MuZeroNetwork(C_in, A, "cuda", CFG)
+  net.load_weights(muzero_ref.seeded_state_dict(C_in, A, int(g["seed"])))
+  init = net.initial_inference(torch.from_numpy(g["obs"]))
+  # representation runs in float32 (torch operators): tight
+  assert np.allclose(init.hidden_state.cpu().numpy(), g["init_hidden"], rtol=1e-3, atol=1e-3)
+  rec = net.recurrent_inference(torch.from_numpy(g["init_hidden"]).cuda(), g["actions"].tolist())
+  rec2 = net.recurrent_inference(torch.from_numpy(g["rec_hidden"]).cuda(), g["actions2"].tolist())
+  torch.cuda.synchronize()
+  report = {}
+  for name, got, want in (("init_logits", init.policy_logits, g["init_logits"]),
+                          ("init_value", init.value, g["init_value"]),
+                          ("rec_hidden", rec.hidden_state, g["rec_hidden"]),
+                          ("rec_logits", rec.policy_logits, g["rec_logits"]),
+                          ("rec_value", rec.value, g["rec_value"]), ("rec_reward", rec.reward, g["rec_reward"]),
+                          ("rec2_hidden", rec2.hidden_state, g["rec2_hidden"]),
+                          ("rec2_logits", rec2.policy_logits, g["rec2_logits"]),
+                          ("rec2_value", rec2.value, g["rec2_value"]),
+                          ("rec2_reward", rec2.reward, g["rec2_reward"])):
+    err = np.abs(got.cpu().numpy() - want)
+    report[name] = (float(err.max()), float(err.mean()))
+  print(report)
+  # bf16 activations through 33 (dynamics) / 32 (prediction) convolutions: scaled states are in
+  # [0, 1] -> 0.06 absolute worst pixel, 0.01 mean; logits +-3 -> 0.15; scalars (|v| ~ 13) -> 0.3
+  assert report["rec_hidden"][0] < 0.06 and report["rec_hidden"][1] < 0.01
+  assert report["rec2_hidden"][0] < 0.06 and report["rec2_hidden"][1] < 0.01
+  for k in ("init_logits", "rec_logits", "rec2_logits"):
+    assert report[k][0] < 0.15, (k, report[k])
+  for k in ("init_value", "rec_value", "rec2_value", "rec_reward", "rec2_reward"):
+    assert report[k][0] < 0.3, (k, report[k])

@@ -199,3 +199,22 @@ def test_ring_cursor_matches_reference_golden(case):
     assert (ring.position, ring.capacity, ring.prev_capacity, ring.num_memories) == \
         (ref.position, ref.capacity, ref.prev_capacity, ref.num_memories)
   assert ring.num_memories == int(g["b0_num_memories"])
+
+
+# ---- MuZeroNetwork (oracle/muzero_ref.py) against the reference class in eval mode --------------
+def test_muzero_ref_matches_reference_golden():
+  import torch
+  from oracle import muzero_ref as mr
+  g = load("muzero_net")
+  C_in, A = int(g["input_channels"]), int(g["action_space"])
+  sd = mr.seeded_state_dict(C_in, A, int(g["seed"]))
+  torch.set_num_threads(max(1, torch.get_num_threads()))
+  with torch.inference_mode():
+    v0, pol0, h0 = mr.initial_inference(torch.from_numpy(g["obs"]), sd)
+    v1, r1, pol1, h1 = mr.recurrent_inference(h0, g["actions"].tolist(), sd, A)
+    v2, r2, pol2, h2 = mr.recurrent_inference(h1, g["actions2"].tolist(), sd, A)
+  for got, want in ((h0, "init_hidden"), (pol0, "init_logits"), (v0, "init_value"), (h1, "rec_hidden"),
+                    (pol1, "rec_logits"), (v1, "rec_value"), (r1, "rec_reward"), (h2, "rec2_hidden"),
+                    (pol2, "rec2_logits"), (v2, "rec2_value"), (r2, "rec2_reward")):
+    # same float32 operators in a different composition (functional vs nn.Module): 1e-4 relative
+    assert np.allclose(got.numpy(), g[want], rtol=1e-4, atol=1e-4), want
