@@ -53,6 +53,8 @@ def parse():
                  help="game slices run on separate CUDA streams inside the move graph")
   p.add_argument("--precision", choices=["bf16", "f32"], default="bf16",
                  help="network kernel: bf16 tcgen05 tensor cores (default) or float32 CUDA cores")
+  p.add_argument("--no-conv", action="store_true", help="skip the C5 MuZeroNetwork section")
+  p.add_argument("--conv-games", type=int, default=1024, help="C5: concurrent games per GPU")
   p.add_argument("--ref-moves-per-step", type=int, default=2,
                  help="reference arm: moves each worker plays per step")
   return p.parse_args()
@@ -327,6 +329,7 @@ def run_b200(args):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
   ms_total, ms_e2e = t.tolist()
   targets = bench_targets(torch, _lib, dev) if rank == 0 else None
+  conv = bench_conv(args, torch, _lib, dev) if rank == 0 and not args.no_conv else None
 
   if rank == 0:
     peaks = measured_peaks()
@@ -360,7 +363,7 @@ def run_b200(args):
         "gpu_launches": fs.launches_per_move * args.steps,
         "clocks": clock_info, "roofline": dominant, "roofline_all": [roof_tree, roof_fc],
         "kernel_share": kern, "cuda_graph": not args.no_graph, "streams": len(fs.lanes),
-        "targets": targets,
+        "targets": targets, "conv": conv,
     }
     if cpu_baseline is not None:
       line["cpu_baseline"] = cpu_baseline
@@ -398,6 +401,68 @@ def kernel_breakdown(fs, torch):
   return {"fc_recurrent_us": fc_us, "tree_step_us": tree_us, "fc_initial_us": dur[0],
           "ungraphed_move_us": move_us, "fc_share": fc_us * S / move_us,
           "tree_share": tree_us * S / move_us, "mean_depth": mean_depth}
+
+
+def bench_conv(args, torch, _lib, dev):
+  """C5 (BASELINE.json configs[4]): MuZeroNetwork residual conv tower, synthetic 96x96x32 frames,
+  A=18, 50 simulations, bf16 tensor-core recurrent_inference.  Reports whole-move expansions/s
+  through ConvSearch (representation included) and the tensor roofline of the conv kernel."""
+  from model_based_rl_b200.muzero import CH, ROWS, ConvSearch, MuZeroNetwork, random_state_dict
+  cfg = search_config(args)
+  G, S, A, C_in = args.conv_games, args.sims, args.actions, 32
+  net = MuZeroNetwork(C_in, A, dev, cfg)
+  net.load_weights(random_state_dict(C_in, A))
+  cs = ConvSearch(cfg, net, G)
+  rng = np.random.default_rng(77)
+  obs = torch.from_numpy(rng.random((G, C_in, 96, 96), dtype=np.float32)).to(dev)
+  noise, u = rng.dirichlet([0.25] * A, size=G), rng.random(G)
+  for _ in range(2):
+    cs.search(obs, noise, u)
+  torch.cuda.synchronize()
+  steps = 3
+  a, b, c = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+  ms_move = ms_search = 0.0
+  for _ in range(steps):
+    a.record()
+    cs.set_roots(obs)
+    b.record()
+    cs.run()
+    c.record()
+    torch.cuda.synchronize()
+    ms_move += a.elapsed_time(c)
+    ms_search += b.elapsed_time(c)
+  # one convolution launch alone (the dominant kernel: 65 of the 70 launches per simulation)
+  x = torch.rand((G * ROWS, CH), device=dev).to(torch.bfloat16)
+  out = net.buffers(G)["x"][0]
+  n = 20
+  for _ in range(3):
+    net._conv(G, net.dyn_tower[0], x, G * ROWS, None, 3, out, residual=x)
+  a.record()
+  for _ in range(n):
+    net._conv(G, net.dyn_tower[0], x, G * ROWS, None, 3, out, residual=x)
+  b.record()
+  torch.cuda.synchronize()
+  us_conv = a.elapsed_time(b) * 1e3 / n
+  peaks = measured_peaks()
+  flops = 2.0 * G * 36 * 128 * 1152  # algorithmic: interior pixels only (the padded rows are overhead)
+  roof = {"kernel": "conv_gemm_tc_kernel", "bound": "tensor", "achieved": flops / us_conv / 1e6,
+          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "traffic": None,
+          "algorithmic_flops_per_launch": flops, "avg_launch_us": us_conv,
+          "issued_tflops": 2.0 * G * 64 * 128 * 1152 / us_conv / 1e6, "peak_source": peaks["source"]}
+  roof["frac"] = roof["achieved"] / roof["peak"]
+  del cs
+  return {"workload": "C5 MuZeroNetwork residual conv (16+16 blocks, 128 ch, 6x6 state), %d games x %d "
+                      "sims, A=%d, synthetic 96x96x%d frames, bf16 tcgen05 recurrent_inference; "
+                      "representation tower in torch float32" % (G, S, A, C_in),
+          "expansions_per_s": G * S * steps / (ms_move * 1e-3),
+          "expansions_per_s_search_only": G * S * steps / (ms_search * 1e-3),
+          "ms_per_move": ms_move / steps, "ms_representation": (ms_move - ms_search) / steps,
+          "gpu_launches_per_move": cs_launches(G, S), "recurrent_tflops_useful":
+              G * S * steps * 0.705e9 / (ms_search * 1e-3) / 1e12, "roofline": roof}
+
+
+def cs_launches(G, S):
+  return 4 + S * (2 + 70)  # set_root, first descent, per sim: row base + 69 network + tree step, stats, action
 
 
 def bench_targets(torch, _lib, dev):

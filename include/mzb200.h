@@ -344,6 +344,11 @@ int mz_conv3x3_tc(int32_t games, const void* x, int64_t x_rows, const int32_t* x
                   const int32_t* actions, int32_t num_actions, const void* residual,
                   const int32_t* res_row_base, void* out, void* out_scaled,
                   const int32_t* scaled_row_base, void* stream);
+/* out[g] = (g * nodes_per_game + node[g]) * 64: row of hidden-pool slot [g][node[g]] in a pool laid
+ * out [G][nodes_per_game][64][128] bf16 -- the gather index for search_path[-2].hidden_state
+ * (mcts.py:94-96) as mz_conv3x3_tc's x_row_base. */
+int mz_conv_row_base(int32_t games, int32_t nodes_per_game, const int32_t* node, int32_t* out,
+                     void* stream);
 /* Linear(6*6*128 -> n_out) (+ReLU) of the heads over the padded state: x [games][8192] bf16,
  * w_packed [n_out][8192] bf16 in the padded channels-last order, out [games][ldo] f32;
  * n_out % 128 == 0.  networks.py:436-439, 470-478. */

@@ -465,9 +465,27 @@ __global__ void conv_head_kernel(int G, const float* __restrict__ hidden, int ld
   }
 }
 
+// out[g] = (g * nodes_per_game + node[g]) * 64: first row of a hidden-pool slot
+__global__ void conv_row_base_kernel(int G, int nodes_per_game, const int32_t* __restrict__ node,
+                                     int32_t* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G) out[g] = (g * nodes_per_game + node[g]) * 64;
+}
+
 }  // namespace
 
 extern "C" {
+
+// Row offsets of the hidden-pool slots [g][node[g]] (pool = [G][nodes_per_game][64 rows][128] bf16):
+// the gather index of recurrent_inference(search_path[-2].hidden_state, ...) (mcts.py:94-96).
+int mz_conv_row_base(int32_t games, int32_t nodes_per_game, const int32_t* node, int32_t* out,
+                     void* stream) {
+  if (games < 1 || nodes_per_game < 1 || !node || !out) return MZ_ERR_BAD_ARG;
+  if ((int64_t)games * nodes_per_game * 64 > 0x7fffffffLL) return MZ_ERR_UNSUPPORTED;
+  conv_row_base_kernel<<<(games + 255) / 256, 256, 0, (cudaStream_t)stream>>>(games, nodes_per_game, node, out);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
 
 // 3x3 convolution (+ folded BatchNorm, bias, optional action plane / residual / ReLU / state scaling)
 // over `games` hidden states in the padded channels-last bf16 layout (64 rows x 128 channels per game).

@@ -94,6 +94,7 @@ class MuZeroNetwork(object):
     self.no_target_transform = bool(getattr(config, 'no_target_transform', False))
     self._state = None
     self._bufs = {}
+    self.launches = 0  # kernels of csrc/mz_conv_tc.cu launched so far
 
   # -- weights -----------------------------------------------------------------------------------
   def load_weights(self, weights):
@@ -176,6 +177,7 @@ class MuZeroNetwork(object):
                                       P(conv.plane) if flags & ACTION else None, P(actions),
                                       self.action_space, P(residual), P(res_base), P(out), P(out_scaled),
                                       P(scaled_base), _lib.current_stream()), "mz_conv3x3_tc")
+    self.launches += 1
 
   def _tower(self, games, convs, x, x_rows, x_base, bufs, last_flags=0, out_scaled=None, scaled_base=None):
     """16 ResidualBlocks (networks.py:372-391) starting from tensor `x` (optionally gathered through
@@ -211,6 +213,7 @@ class MuZeroNetwork(object):
     _lib.check(self.lib.mz_conv_head(games, P(b['fc']), 1536, P(self.rew_fc2_w), P(self.rew_fc2_b),
                                      self.reward_bins, 1, self.reward_min, int(self.no_target_transform),
                                      P(reward), 1, st), "mz_conv_head")
+    self.launches += 2
     # prediction on the scaled state
     rows = next_state.shape[0]
     self.run_prediction(games, next_state, rows, next_base, value, logits)
@@ -230,6 +233,7 @@ class MuZeroNetwork(object):
     _lib.check(self.lib.mz_conv_head(games, C_ptr(b['fc'][:, 1024:]), 1536, P(self.pol_fc2_w),
                                      P(self.pol_fc2_b), self.action_space, 0, 0, 0, P(logits),
                                      self.action_space, st), "mz_conv_head")
+    self.launches += 3
 
   # -- reference interface ---------------------------------------------------------------------------
   def representation(self, observation):
@@ -297,6 +301,120 @@ class MuZeroNetwork(object):
       self.run_recurrent(g, rows, g * ROWS, None, acts, nxt, None, value, reward, logits)
       hidden = from_padded(nxt[:b * ROWS], b)
     return NetworkOutput(value[:b].reshape(b, 1), reward[:b].reshape(b, 1), logits[:b], hidden)
+
+
+class ConvSearch(object):
+  """The per-move body of Actor.play_game (actors.py:131-153) for G games with MuZeroNetwork.
+
+  Hidden states live in a bf16 pool [G][S+1][64 rows][128] (the padded layout the kernels read):
+  the first dynamics convolution gathers `search_path[-2].hidden_state` through per-game row offsets
+  and the last one writes the scaled next state into slot sim+1 -- no gather / scatter copies.  The
+  search part of a move (3 + 70 launches per simulation) is captured in one CUDA graph."""
+
+  def __init__(self, config, net, num_games, noise_frac=None, use_graph=True):
+    from .mcts import BatchedMCTS
+    G, A, dev = int(num_games), int(config.action_space), net.device
+    if G & 1:
+      raise ValueError("ConvSearch needs an even number of games (a kernel tile is two games)")
+    self.net, self.G, self.A, self.S = net, G, A, int(config.num_simulations)
+    self.noise_frac = float(getattr(config, 'root_exploration_fraction', 0.25)
+                            if noise_frac is None else noise_frac)
+    self.eng = BatchedMCTS(config, G, hidden_words=0, device=dev)
+    S = self.S
+    self.pool = torch.zeros((G * (S + 1) * ROWS, CH), dtype=torch.bfloat16, device=dev)
+    slot0 = torch.arange(G, device=dev, dtype=torch.int64) * (S + 1)
+    self.out_base = ((slot0[None, :] + torch.arange(1, S + 1, device=dev)[:, None]) * ROWS).to(torch.int32)
+    self.root_base = (slot0 * ROWS).to(torch.int32)
+    self.in_base = torch.zeros(G, dtype=torch.int32, device=dev)
+    self.noise = torch.zeros((G, A), dtype=torch.float64, device=dev)
+    self.legal = torch.full((G,), (1 << A) - 1, dtype=torch.int64, device=dev).to(torch.int32)
+    self.to_play = torch.ones(G, dtype=torch.int8, device=dev)
+    self.temperature = torch.ones(G, dtype=torch.float64, device=dev)
+    self.uniforms = torch.zeros(G, dtype=torch.float64, device=dev)
+    self.root_logits = torch.zeros((G, A), dtype=torch.float32, device=dev)
+    self.init_value = torch.zeros(G, dtype=torch.float32, device=dev)
+    self.value = torch.zeros(G, dtype=torch.float32, device=dev)
+    self.reward = torch.zeros(G, dtype=torch.float32, device=dev)
+    self.logits = torch.zeros((G, A), dtype=torch.float32, device=dev)
+    self.use_graph, self.graph, self.use_noise = use_graph, None, True
+    self.record = None
+    self.launches_per_move = 0
+
+  def enable_record(self):
+    dev, G, S, A = self.net.device, self.G, self.S, self.A
+    self.record = (torch.zeros((S, G), dtype=torch.float32, device=dev),
+                   torch.zeros((S, G), dtype=torch.float32, device=dev),
+                   torch.zeros((S, G, A), dtype=torch.float32, device=dev))
+    self.eng.enable_trace()
+    self.graph = None
+
+  @property
+  def trace(self):
+    return self.eng.trace
+
+  def set_roots(self, observation):
+    """initial_inference for every game: representation (torch operators, float32) -> pool slot 0,
+    prediction on the tensor cores -> root logits / value."""
+    with torch.inference_mode():
+      hidden = self.net.representation(observation)
+      self.pool.view(self.G, self.S + 1, ROWS, CH)[:, 0] = to_padded(hidden).view(self.G, ROWS, CH)
+      self.net.run_prediction(self.G, self.pool, self.pool.shape[0], self.root_base, self.init_value,
+                              self.root_logits)
+
+  def _enqueue(self):
+    eng, net, lib, P = self.eng, self.net, self.net.lib, _lib.ptr
+    st = _lib.current_stream()
+    tree = eng.tree
+    n0 = net.launches
+    _lib.check(lib.mz_tree_set_root(tree, P(self.root_logits), P(self.legal),
+                                    P(self.noise) if self.use_noise else None, self.noise_frac,
+                                    P(self.to_play), None, st), "mz_tree_set_root")
+    _lib.check(lib.mz_tree_step(tree, -1, None, None, None, None, None, *eng._trace_ptrs(0), st),
+               "mz_tree_step")
+    for sim in range(self.S):
+      if self.record is not None:
+        v, r, l = self.record[0][sim], self.record[1][sim], self.record[2][sim]
+      else:
+        v, r, l = self.value, self.reward, self.logits
+      _lib.check(lib.mz_conv_row_base(self.G, self.S + 1, P(eng.leaf_parent), P(self.in_base), st),
+                 "mz_conv_row_base")
+      net.run_recurrent(self.G, self.pool, self.pool.shape[0], self.in_base, eng.leaf_action, self.pool,
+                        self.out_base[sim], v, r, l)
+      _lib.check(lib.mz_tree_step(tree, sim, P(v), P(r), P(l), None, None, *eng._trace_ptrs(sim + 1), st),
+                 "mz_tree_step")
+    _lib.check(lib.mz_tree_root_stats(tree, P(eng.visits), P(eng.child_visits), P(eng.root_value),
+                                      P(eng.minmax), st), "mz_tree_root_stats")
+    _lib.check(lib.mz_select_action(self.G, self.A, P(eng.visits), P(self.legal), P(self.temperature),
+                                    P(self.uniforms), P(eng.actions), st), "mz_select_action")
+    self.launches_per_move = net.launches - n0 + 4 + 2 * self.S
+
+  def run(self):
+    """The search of one move (roots already set) on the current stream."""
+    if not self.use_graph:
+      self._enqueue()
+      return
+    if self.graph is None:
+      self._enqueue()  # warm-up outside capture (cudaFuncSetAttribute, lazy module loading)
+      torch.cuda.synchronize()
+      self.graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self.graph):
+        self._enqueue()
+    self.graph.replay()
+
+  def search(self, observation, noise=None, uniforms=None, temperature=None):
+    """observation [G, C, 96, 96] (device or host); returns device tensors (actions [G] i32,
+    root_value [G] f64, child_visits [G, A] f64, initial value [G] f32)."""
+    dev = self.net.device
+    if noise is not None:
+      self.noise.copy_(torch.as_tensor(noise), non_blocking=True)
+    if uniforms is not None:
+      self.uniforms.copy_(torch.as_tensor(uniforms), non_blocking=True)
+    if temperature is not None:
+      self.temperature.copy_(torch.as_tensor(temperature), non_blocking=True)
+    self.set_roots(torch.as_tensor(observation).to(dev, non_blocking=True))
+    self.run()
+    eng = self.eng
+    return eng.actions, eng.root_value, eng.child_visits, self.init_value
 
 
 def C_ptr(t):

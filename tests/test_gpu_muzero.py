@@ -155,3 +155,59 @@ def test_network_matches_reference_golden():
     assert report[k][0] < 0.15, (k, report[k])
   for k in ("init_value", "rec_value", "rec2_value", "rec_reward", "rec2_reward"):
     assert report[k][0] < 0.3, (k, report[k])
+
+
+def test_conv_search_replays_bit_exact_in_oracle():
+  """A full move with MuZeroNetwork in the loop (hidden pool gathered / scattered in place): the
+  engine records what the network returned for every simulation; the oracle replays the search with
+  those outputs and must reproduce parents, actions, visit counts and root values bit for bit.  The
+  recorded outputs themselves are checked against the float32 oracle network along one game's path."""
+  import oracle
+  from oracle import muzero_ref
+  from model_based_rl_b200.muzero import ConvSearch, MuZeroNetwork, from_padded
+  C_in, A, G, S = 4, 18, 8, 12
+  sd = muzero_ref.seeded_state_dict(C_in, A, 99)
+  net = MuZeroNetwork(C_in, A, "cuda", CFG)
+  net.load_weights(sd)
+  cfg = types.SimpleNamespace(num_simulations=S, action_space=A, two_players=False, discount=0.997,
+                              pb_c_base=19652, pb_c_init=1.25, init_value_score=0.0,
+                              known_bounds=[None, None], root_exploration_fraction=0.25)
+  rng = np.random.default_rng(3)
+  obs = torch.from_numpy(rng.random((G, C_in, 96, 96)).astype(np.float32))
+  noise = rng.dirichlet([0.25] * A, size=G)
+  u, temp = rng.random(G), rng.choice([0.0, 1.0], size=G)
+  for use_graph in (False, True):
+    cs = ConvSearch(cfg, net, G, use_graph=use_graph)
+    cs.enable_record()
+    actions, root_value, child_visits, init_value = cs.search(obs, noise, u, temp)
+    torch.cuda.synchronize()
+    if use_graph:
+      a2 = actions.clone()
+      actions, root_value, child_visits, init_value = cs.search(obs, noise, u, temp)
+      torch.cuda.synchronize()
+      assert torch.equal(a2, actions)
+    ocfg = oracle.make_cfg(S, A, False, 0.997)
+    want = oracle.search(ocfg, cs.root_logits.cpu().numpy(), noise=noise, noise_frac=0.25,
+                         rec_value=cs.record[0].cpu().numpy().T, rec_reward=cs.record[1].cpu().numpy().T,
+                         rec_logits=cs.record[2].cpu().numpy().transpose(1, 0, 2))
+    assert np.array_equal(cs.trace[0].cpu().numpy().T, want["trace_parent"])
+    assert np.array_equal(cs.trace[1].cpu().numpy().T, want["trace_action"])
+    assert np.array_equal(cs.eng.visits.cpu().numpy(), want["visits"])
+    assert np.array_equal(root_value.cpu().numpy(), want["root_value"])
+    for i in range(G):
+      assert int(actions[i]) == oracle.select_action(want["visits"][i], temp[i], u[i])
+  # the network outputs along game 0's simulations vs the float32 oracle network fed the same
+  # (bf16) parent states from the pool: one recurrent step each.  value / reward are h^-1 of the
+  # support expectation, whose slope grows with |x| (about 6 at |v| = 12): 0.05 + 5 % of |v|;
+  # logits 0.1, scaled states 0.05
+  sdc = {k: v.cuda() for k, v in sd.items()}
+  pool = cs.pool.view(G, S + 1, 64, 128)
+  parents, acts = cs.trace[0].cpu().numpy()[:, 0], cs.trace[1].cpu().numpy()[:, 0]
+  for sim in range(S):
+    h = from_padded(pool[0, int(parents[sim])].reshape(64, 128), 1)
+    v, r, pol, h2 = muzero_ref.recurrent_inference(h, [int(acts[sim])], sdc, A)
+    assert abs(float(v) - float(cs.record[0][sim, 0])) < 0.05 + 0.05 * abs(float(v))
+    assert abs(float(r) - float(cs.record[1][sim, 0])) < 0.05 + 0.05 * abs(float(r))
+    assert float((pol[0] - cs.record[2][sim, 0]).abs().max()) < 0.1
+    got_h = from_padded(pool[0, sim + 1].reshape(64, 128), 1)
+    assert float((got_h - h2).abs().max()) < 0.05
