@@ -305,52 +305,102 @@ MZ_DEV unsigned long long warp_max_key(unsigned long long key) {
   return ((unsigned long long)hi_max << 32) | lo_max;
 }
 
-MZ_DEV void descend_w32(const mz_tree& t, const uint8_t* img, int lane, int16_t* path, int& out_depth,
-                        int& out_parent, int& out_action) {
+// Loads for the descent.  STAGED: `base` is a 32-bit shared-memory address and the loads are
+// explicit ld.shared (no generic-address arithmetic in the loop); otherwise a generic pointer.
+template <bool STAGED>
+struct ImgLoad {
+  using Addr = typename std::conditional<STAGED, uint32_t, const uint8_t*>::type;
+  static MZ_DEV Addr base(const uint8_t* img) {
+    if constexpr (STAGED) return smem_u32(img);
+    else return img;
+  }
+  static MZ_DEV double f64(Addr a) {
+    if constexpr (STAGED) {
+      double v;
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+      return v;
+    } else {
+      return *reinterpret_cast<const double*>(a);
+    }
+  }
+  static MZ_DEV int s16(Addr a) {
+    if constexpr (STAGED) {
+      int v;
+      asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a));
+      return v;
+    } else {
+      return *reinterpret_cast<const int16_t*>(a);
+    }
+  }
+  static MZ_DEV NodeHead head(Addr a) {
+    int x, y, z, w;
+    if constexpr (STAGED) {
+      asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(a));
+    } else {
+      const int4 v = *reinterpret_cast<const int4*>(a);
+      x = v.x; y = v.y; z = v.z; w = v.w;
+    }
+    NodeHead h;
+    h.q = __hiloint2double(y, x);
+    h.visit = z;
+    h.reward = __int_as_float(w);
+    return h;
+  }
+};
+
+// (score, action) argmax over the lanes of a converged warp, ties -> larger action
+// (mcts.py:106-112): returns the winning lane or -1 when no lane is a candidate.
+MZ_DEV int warp_argmax(double score, bool cand) {
+  const unsigned long long key = cand ? sortable_key(score) : 0ull;
+  const unsigned long long best_key = warp_max_key(key);
+  const unsigned winners = __ballot_sync(MZ_FULL, cand && key == best_key);
+  return winners ? 31 - __clz(winners) : -1;
+}
+
+// MODE: MinMaxStats.normalize (mcts.py:16-21) hoisted out of the loop -- 2 = (v - min) / (max - min)
+// through the constant-divisor division, 3 = same through IEEE division, 1 = constant 1.0, 0 = raw.
+template <bool STAGED, int MODE>
+MZ_DEV void descend_loop(const mz_tree& t, typename ImgLoad<STAGED>::Addr nodes, int lane, int16_t* path,
+                         int N, double mn, double d, double r, int& out_depth, int& out_parent,
+                         int& out_action) {
+  using L = ImgLoad<STAGED>;
   const int A = t.num_actions, SP1 = t.num_simulations + 1, NB = t.node_bytes;
   const double init_score = t.init_value_score;
-  const double mn = *reinterpret_cast<const double*>(img), mx = *reinterpret_cast<const double*>(img + 8);
-  // MinMaxStats.normalize mcts.py:16-21, hoisted: 2 = affine, 1 = constant 1.0, 0 = raw value
-  const int mode = mx > mn ? 2 : (mx == mn ? 1 : 0);
-  const double d = __dsub_rn(mx, mn);
-  const bool fast = mode == 2 && divisor_ok(d);
-  const double r = fast ? __drcp_rn(d) : 0.0;
-  const uint8_t* nodes = img + MZ_GAME_HEADER_BYTES;
   const bool lane_ok = lane < A;
   const int sp = lane_ok ? lane : A - 1;
   const int prior_off = MZ_NODE_STATS_BYTES + 8 * sp, child_off = MZ_NODE_STATS_BYTES + 8 * A + 2 * sp;
-  int node = 0, depth = 0, parent = 0, action = 0;
-  int N = load_head(nodes).visit;
-  if (lane == 0) path[0] = 0;
+  const double* table = t.pb_c_table;
+  int node = 0, depth = 0, parent, action;
   for (;;) {
-    const uint8_t* rec = nodes + node * NB;
-    const double prior = *reinterpret_cast<const double*>(rec + prior_off);
-    const int ch = *reinterpret_cast<const int16_t*>(rec + child_off);
-    const NodeHead c = load_head(nodes + max(ch, 0) * NB);
+    const typename L::Addr rec = nodes + node * NB;
+    const double prior = L::f64(rec + prior_off);
+    int ch = L::s16(rec + child_off);
+    if (!lane_ok) ch = MZ_CHILD_ILLEGAL;
+    const NodeHead c = L::head(nodes + max(ch, 0) * NB);
     const int n = ch >= 0 ? c.visit : 0;
-    double score;
-    if (N == 0) {  // mcts.py:105-108: an unvisited (root) node ranks children by prior
-      score = prior;
-    } else {       // ucb_score mcts.py:115-124
-      const double pb_c = __ldg(t.pb_c_table + N * SP1 + n);
-      double value_score = init_score;
-      if (n > 0) {
-        if (mode == 2) {
-          const double x = __dsub_rn(c.q, mn);
-          value_score = (fast && (x == 0.0 || exp_in_fast_range(x))) ? div_by_const(x, d, r)
-                                                                      : __ddiv_rn(x, d);
+    // ucb_score mcts.py:115-124
+    const double pb_c = __ldg(table + N * SP1 + n);
+    double value_score = init_score;
+    if (n > 0) {
+      if (MODE == 0) {
+        value_score = c.q;
+      } else if (MODE == 1) {
+        value_score = 1.0;
+      } else {
+        const double x = __dsub_rn(c.q, mn);
+        if (MODE == 2) {
+          const unsigned hx = (unsigned)__double2hiint(x);  // x >= 0 because min <= q
+          if (__builtin_expect(hx - 0x33700000u > 0x19000000u, 0))  // 0, or outside [2^-200, 2^200]
+            value_score = (x == 0.0) ? 0.0 : __ddiv_rn(x, d);
+          else
+            value_score = div_by_const(x, d, r);
         } else {
-          value_score = mode == 1 ? 1.0 : c.q;
+          value_score = __ddiv_rn(x, d);
         }
       }
-      score = __dadd_rn(__dmul_rn(pb_c, prior), value_score);
     }
-    // max over (score, action) tuples, ties -> larger action (mcts.py:106-112)
-    const bool cand = lane_ok && ch != MZ_CHILD_ILLEGAL;
-    const unsigned long long key = cand ? sortable_key(score) : 0ull;
-    const unsigned long long best_key = warp_max_key(key);
-    const unsigned winners = __ballot_sync(MZ_FULL, cand && key == best_key);
-    const int best = winners ? 31 - __clz(winners) : -1;
+    const double score = __dadd_rn(__dmul_rn(pb_c, prior), value_score);
+    const int best = warp_argmax(score, ch != MZ_CHILD_ILLEGAL);
     const int src = best < 0 ? 0 : best;
     const int ch_b = __shfl_sync(MZ_FULL, ch, src);
     const int n_b = __shfl_sync(MZ_FULL, n, src);
@@ -367,6 +417,40 @@ MZ_DEV void descend_w32(const mz_tree& t, const uint8_t* img, int lane, int16_t*
   out_depth = depth;
   out_parent = parent;
   out_action = action;
+}
+
+template <bool STAGED>
+MZ_DEV void descend_w32(const mz_tree& t, const uint8_t* img, int lane, int16_t* path, int& out_depth,
+                        int& out_parent, int& out_action) {
+  using L = ImgLoad<STAGED>;
+  const int A = t.num_actions;
+  const typename L::Addr base = L::base(img);
+  const double mn = L::f64(base), mx = L::f64(base + 8);
+  const typename L::Addr nodes = base + MZ_GAME_HEADER_BYTES;
+  const int N = L::head(nodes).visit;
+  if (lane == 0) path[0] = 0;
+  if (N == 0) {
+    // mcts.py:105-108: an unvisited root (simulation 0) ranks its children by prior; none of them
+    // is expanded yet, so the first step already reaches the leaf
+    const bool lane_ok = lane < A;
+    const int sp = lane_ok ? lane : A - 1;
+    const double prior = L::f64(nodes + MZ_NODE_STATS_BYTES + 8 * sp);
+    const int ch = L::s16(nodes + MZ_NODE_STATS_BYTES + 8 * A + 2 * sp);
+    const int best = warp_argmax(prior, lane_ok && ch != MZ_CHILD_ILLEGAL);
+    out_depth = 1;
+    out_parent = 0;
+    out_action = best;
+    return;
+  }
+  const double d = __dsub_rn(mx, mn);
+  if (mx > mn) {
+    if (divisor_ok(d)) descend_loop<STAGED, 2>(t, nodes, lane, path, N, mn, d, __drcp_rn(d), out_depth, out_parent, out_action);
+    else descend_loop<STAGED, 3>(t, nodes, lane, path, N, mn, d, 0.0, out_depth, out_parent, out_action);
+  } else if (mx == mn) {
+    descend_loop<STAGED, 1>(t, nodes, lane, path, N, mn, d, 0.0, out_depth, out_parent, out_action);
+  } else {
+    descend_loop<STAGED, 0>(t, nodes, lane, path, N, mn, d, 0.0, out_depth, out_parent, out_action);
+  }
 }
 
 // expand (mcts.py:47-55) + backpropagate (mcts.py:126-143) for one game per warp.  `img` is the
@@ -677,7 +761,7 @@ tree_step_w32_kernel(mz_tree t, int sim, int do_backup, int do_select, int live_
   }
   if (do_select) {
     int depth, parent, action;
-    descend_w32(t, img, lane, path, depth, parent, action);
+    descend_w32<STAGED>(t, img, lane, path, depth, parent, action);
     if (lane == 0) {
       t.path_len[g] = depth;
       t.leaf_parent[g] = parent;
