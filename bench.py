@@ -49,7 +49,7 @@ def parse():
   p.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
   p.add_argument("--no-cpu-baseline", action="store_true")
   p.add_argument("--no-graph", action="store_true")
-  p.add_argument("--streams", type=int, default=2,
+  p.add_argument("--streams", type=int, default=4,
                  help="game slices run on separate CUDA streams inside the move graph")
   p.add_argument("--precision", choices=["bf16", "f32"], default="bf16",
                  help="network kernel: bf16 tcgen05 tensor cores (default) or float32 CUDA cores")
