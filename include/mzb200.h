@@ -231,6 +231,17 @@ int mz_fc_recurrent_tc(const mz_fc_weights* w, const void* packed, const float* 
                        const int32_t* actions, float* hidden_out, int64_t out_row_stride,
                        int64_t out_offset, float* value, float* reward, float* logits, void* stream);
 
+/* BaseNetwork.initial_inference (networks.py:26-29) on the same tensor-core kernel: representation
+ * head (obs [B][obs_dim] f32, K = obs_dim + bias column) -> LayerNorm + ReLU -> prediction heads.
+ * Its own packed image / tail (mz_fc_tc_initial_packed_bytes, mz_fc_tc_pack_initial);
+ * MZ_ERR_UNSUPPORTED when obs_dim is too wide for the shared-memory budget (use mz_fc_initial_f32).
+ * hidden_out row g at hidden_out + g * out_row_stride (the tree's hidden pool, slot 0). */
+int64_t mz_fc_tc_initial_packed_bytes(int32_t obs_dim);
+int mz_fc_tc_pack_initial(const mz_fc_weights* w, void* packed, float* tail, void* stream);
+int mz_fc_initial_tc(const mz_fc_weights* w, const void* packed, const float* tail, int32_t batch,
+                     const float* obs, float* hidden_out, int64_t out_row_stride, float* value,
+                     float* logits, void* stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* Scalar transforms and supports (config.py:27-68), float32 in torch's op order.                */
 /* ------------------------------------------------------------------------------------------- */

@@ -87,6 +87,9 @@ _SIGNATURES = {
     "mz_fc_tc_pack": (C.c_int, [C.POINTER(FcWeights), _V, _V, _V]),
     "mz_fc_recurrent_tc": (C.c_int, [C.POINTER(FcWeights), _V, _V, C.c_int32, _V, C.c_int64, _V, _V, _V,
                                      C.c_int64, C.c_int64, _V, _V, _V, _V]),
+    "mz_fc_tc_initial_packed_bytes": (C.c_int64, [C.c_int32]),
+    "mz_fc_tc_pack_initial": (C.c_int, [C.POINTER(FcWeights), _V, _V, _V]),
+    "mz_fc_initial_tc": (C.c_int, [C.POINTER(FcWeights), _V, _V, C.c_int32, _V, _V, C.c_int64, _V, _V, _V]),
     "mz_scalar_transform": (C.c_int, [C.c_int64, _V, _V, _V]),
     "mz_scalar_to_support": (C.c_int, [C.c_int64, _V, C.c_int32, C.c_int32, C.c_int32, _V, _V]),
     "mz_support_to_scalar": (C.c_int, [C.c_int64, _V, C.c_int32, C.c_int32, C.c_int32, _V, _V]),

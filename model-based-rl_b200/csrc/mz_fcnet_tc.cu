@@ -35,7 +35,7 @@ constexpr int ROWS = 128;            // rows (games) per CTA = UMMA M
 constexpr int CHUNK = 128;           // hidden features per chunk = UMMA N of the first layer
 constexpr int NCHUNK = 16;           // 4 heads x 4 chunks
 constexpr int K3 = 64;               // padded K of the prediction first layer
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;        // weight-ring depth (recurrent: 4; initial inference, larger chunks: 2)
 constexpr int EPI_THREADS = 256;       // two groups of four epilogue warps
 constexpr int MMA2_WARP = 2 + EPI_THREADS / 32;  // second MMA-issuing warp (layer 2)
 constexpr int STORE_WARP = MMA2_WARP + 1;       // writes h' rows to the hidden pool, off the critical path
@@ -76,7 +76,10 @@ __host__ __device__ inline size_t chunk_offset(int c, int k1) {
   for (int i = 0; i < c; ++i) off += chunk_geom(i, k1).bytes;
   return off;
 }
-__host__ __device__ inline int stage_bytes_for(int k1) { return chunk_geom(4, k1).bytes; }  // largest
+__host__ __device__ inline int stage_bytes_for(int k1) {  // largest chunk: a k1-wide head or a prediction head
+  const int a = chunk_geom(4, k1).bytes, b = chunk_geom(8, k1).bytes;
+  return a > b ? a : b;
+}
 
 // canonical K-major, no swizzle: 8 x 8 core matrices of 128 contiguous bytes,
 // core (row_group, k_block) at ((k_block * row_groups) + row_group) * 128
@@ -198,6 +201,12 @@ struct TcParams {
   long long out_row_stride, out_offset;
   float *value, *reward, *logits;
   long long* trace;  // optional per-phase clock64() stamps of CTA 0 (diagnostics), or nullptr
+  // initial_inference mode (networks.py:26-29): chunk0 = 4 skips the reward head, the first head is
+  // the representation (A1 = [obs | 1], K = k1), then LayerNorm / ReLU and the prediction heads
+  int chunk0;        // 0: recurrent_inference (16 chunks), 4: initial_inference (12 chunks)
+  int stages;        // weight-ring depth actually used (<= MAX_STAGES)
+  const float* obs;  // [batch][obs_dim] (initial mode)
+  int obs_dim;
 };
 
 // trace slots: [0,64) epilogue thread (row 0), [64,192) MMA thread, [192,224) producer
@@ -279,12 +288,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   if (warp >= 2 && warp < MMA2_WARP) {
     const int g0 = blockIdx.x * ROWS + (warp & 3) * 32 + lane;
     const int gc0 = g0 < p.batch ? g0 : p.batch - 1;
-    pre_idx = p.in_index ? p.in_index[gc0] : 0;
-    pre_act = p.actions[gc0];
+    if (!p.obs) {
+      pre_idx = p.in_index ? p.in_index[gc0] : 0;
+      pre_act = p.actions[gc0];
+    }
   }
   // carve shared memory
   uint8_t* sA1 = smem;                                  // [128 x k1] bf16 (A of the dynamics layer)
   uint8_t* sW = sA1 + ROWS * k1 * 2;                    // STAGES x stage_bytes
+  const int STAGES = p.stages, c0 = p.chunk0, nch = NCHUNK - c0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + STAGES * stage_bytes);
   uint64_t* w_full = bars;            // [STAGES]
   uint64_t* w_empty = bars + 4;       // [STAGES]
@@ -303,7 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   for (int i = threadIdx.x; i < TAIL_FLOATS; i += TC_THREADS) sTail[i] = p.tail[i];
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d1_full[i], 1);
       mbar_init(&d1_empty[i], EPI_THREADS);
@@ -330,9 +342,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     // ===== producer: stream the 16 weight chunks through the ring =====
     if (lane == 0) {
       size_t off = 0;
-      for (int c = 0; c < NCHUNK; ++c) {
+      for (int c = 0; c < nch; ++c) {
         const int st = c % STAGES, n = c / STAGES;
-        const ChunkGeom g = chunk_geom(c, k1);
+        const ChunkGeom g = chunk_geom(c + c0, k1);
         mbar_wait(&w_empty[st], (n & 1) ^ 1);
         TC_STAMP(192 + c);
         mbar_arrive_expect_tx(&w_full[st], (uint32_t)g.bytes);
@@ -348,19 +360,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     const uint32_t idesc1 = make_idesc(CHUNK);
     constexpr uint64_t KSTEP = (uint64_t)((2 * (CHUNK / 8) * 128) >> 4);  // two K core-matrix columns
 #pragma unroll 1
-    for (int c = 0; c < NCHUNK; ++c) {
-      const int st = c % STAGES;
+    for (int c = 0; c < nch; ++c) {
+      const int st = c % STAGES, cc = c + c0;
       if (lane == 0) TC_STAMP(64 + 8 * c + 0);
       mbar_wait(&w_full[st], (c / STAGES) & 1);
       if (c == 0) mbar_wait(a1_ready, 0);
-      if (c == 8) mbar_wait(a3_ready, 0);
+      if (cc == 8) mbar_wait(a3_ready, 0);
       mbar_wait(&d1_empty[c & 1], ((c >> 1) & 1) ^ 1);
       tc_fence_after();
       if (lane == 0) TC_STAMP(64 + 8 * c + 1);
       const uint32_t d1 = tmem + COL_D1 + (c & 1) * CHUNK;
       const uint64_t bd = make_desc(w_addr + st * stage_bytes, (CHUNK / 8) * 128, 128);
       if (elect_one()) {
-        if (c < 8) {  // dynamics: A = [h | onehot | 1] from shared memory, K = k1
+        if (cc < 8) {  // dynamics / representation: A = [h | onehot | 1] or [obs | 1] from shared memory, K = k1
           const uint64_t ad = make_desc(a1_addr, (ROWS / 8) * 128, 128);
           umma_ss<false>(d1, ad, bd, idesc1);
 #pragma unroll 1
@@ -382,19 +394,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     const uint32_t w_addr = smem_u32(sW);
     const uint32_t w1_bytes_dyn = CHUNK * k1 * 2, w1_bytes_pred = CHUNK * K3 * 2;
 #pragma unroll 1
-    for (int c = 0; c < NCHUNK; ++c) {
-      const int st = c % STAGES, head = c >> 2;
+    for (int c = 0; c < nch; ++c) {
+      const int st = c % STAGES, cc = c + c0, head = cc >> 2;
       mbar_wait(&a2_full[c & 1], (c >> 1) & 1);
       tc_fence_after();
       if (lane == 0) TC_STAMP(64 + 8 * c + 4);
       const uint32_t a_tm = tmem + COL_A2 + (c & 1) * (CHUNK / 2);
-      const uint32_t b_addr = w_addr + st * stage_bytes + (c < 8 ? w1_bytes_dyn : w1_bytes_pred);
+      const uint32_t b_addr = w_addr + st * stage_bytes + (cc < 8 ? w1_bytes_dyn : w1_bytes_pred);
       if (elect_one()) {
-        if (head == 1) issue_mma2<N_HID>(tmem + COL_D2B, a_tm, b_addr, (c & 3) == 0);
-        else issue_mma2<32>(tmem + ((head & 1) ? COL_D2B : COL_D2A), a_tm, b_addr, (c & 3) == 0);
+        if (head == 1) issue_mma2<N_HID>(tmem + COL_D2B, a_tm, b_addr, (cc & 3) == 0);
+        else issue_mma2<32>(tmem + ((head & 1) ? COL_D2B : COL_D2A), a_tm, b_addr, (cc & 3) == 0);
         tc_commit(&w_empty[st]);       // chunk c's weights are no longer needed
         tc_commit(&a2_empty[c & 1]);   // A2 buffer may be overwritten
-        if (c == 7 || c == 15) tc_commit(d2_full);
+        if (cc == 7 || cc == 15) tc_commit(d2_full);
       }
       __syncwarp();
       if (lane == 0) TC_STAMP(64 + 8 * c + 6);
@@ -423,8 +435,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     const bool stamp = (row == 0 && grp == 0);
 
-    // --- A1 = bf16([h (50) | onehot(action) (A) | 1 (bias input) | 0]) ---
-    if (grp == 0) {
+    if (p.obs) {
+      // --- initial_inference: A1 = bf16([obs (obs_dim) | 1 (bias input) | 0]); each warp walks 16 of
+      // its quarter's rows, lanes stride over the columns (coalesced row reads) ---
+      const int r0 = quarter * 32 + grp * 16;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int r = r0 + i;
+        const int gr = min(blockIdx.x * ROWS + r, p.batch - 1);
+        const float* orow = p.obs + (size_t)gr * p.obs_dim;
+        for (int k = lane; k < k1; k += 32) {
+          const float x = k < p.obs_dim ? __ldg(orow + k) : (k == p.obs_dim ? 1.0f : 0.0f);
+          *reinterpret_cast<__nv_bfloat16*>(sA1 + canon_off(r, k, ROWS)) = __float2bfloat16_rn(x);
+        }
+      }
+    } else if (grp == 0) {
+      // --- A1 = bf16([h (50) | onehot(action) (A) | 1 (bias input) | 0]) ---
       // k < 48: the warp walks its 32 rows, 24 lanes load one float2 each (coalesced 192 B per row);
       // all loads of a batch of 16 rows are issued before the first store
       const float* src = p.hidden_in + (size_t)gc * p.in_row_stride + (size_t)pre_idx * H;
@@ -495,17 +521,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       if (stamp) TC_STAMP(5 + 2 * c);
     };
 
-    for (int c = 0; c < 8; ++c) hidden_epilogue(c);
+    for (int c = 0; c < 8 - c0; ++c) hidden_epilogue(c);
 
     // --- dynamics outputs: group 1 -> reward scalar, group 0 -> h' = relu(LN(.)) -> pool + A3 ---
     mbar_wait(d2_full, 0);
     tc_fence_after();
     if (stamp) TC_STAMP(40);
     if (grp == 1) {
-      tmem_ld32(lane_addr + COL_D2A, v);
-      tmem_wait_ld();
-      const float rew = support_to_scalar_regs(v, sTail + T_REW_B, p.reward_bins, p.reward_min, p.no_tt);
-      if (live) p.reward[g] = rew;
+      if (c0 == 0) {  // initial_inference has no reward (networks.py:29 returns 0)
+        tmem_ld32(lane_addr + COL_D2A, v);
+        tmem_wait_ld();
+        const float rew = support_to_scalar_regs(v, sTail + T_REW_B, p.reward_bins, p.reward_min, p.no_tt);
+        if (live) p.reward[g] = rew;
+      }
     } else {
       float hbuf[64];
       tmem_ld32(lane_addr + COL_D2B, v);
@@ -553,7 +581,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       mbar_arrive(h_staged);  // the store warp takes it from here
     }
 
-    for (int c = 8; c < NCHUNK; ++c) hidden_epilogue(c);
+    for (int c = 8 - c0; c < nch; ++c) hidden_epilogue(c);
 
     // --- prediction outputs: group 0 -> value scalar, group 1 -> policy logits ---
     mbar_wait(d2_full, 1);
@@ -595,16 +623,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
 }
 
 // ---- packing: f32 reference-layout weights -> bf16 chunk images + tail parameters ---------------
-__global__ void fc_tc_pack_kernel(mz_fc_weights w, int k1, uint8_t* chunks, float* tail) {
+// chunk0 = 0: the recurrent image (reward, transition, value, policy heads); chunk0 = 4: the
+// initial-inference image (representation in place of the transition head, then value, policy)
+__global__ void fc_tc_pack_kernel(mz_fc_weights w, int k1, int chunk0, uint8_t* chunks, float* tail) {
   const int A = w.num_actions;
-  for (int c = 0; c < NCHUNK; ++c) {
+  const bool init = chunk0 != 0;
+  for (int c = chunk0; c < NCHUNK; ++c) {
     const ChunkGeom g = chunk_geom(c, k1);
-    uint8_t* base = chunks + chunk_offset(c, k1);
+    uint8_t* base = chunks + (chunk_offset(c, k1) - chunk_offset(chunk0, k1));
     const int head = c >> 2, f0 = (c & 3) * CHUNK;
-    const float* w1t = head == 0 ? w.rew_w1 : (head == 1 ? w.dyn_w1 : (head == 2 ? w.val_w1 : w.pol_w1));
-    const float* b1 = head == 0 ? w.rew_b1 : (head == 1 ? w.dyn_b1 : (head == 2 ? w.val_b1 : w.pol_b1));
-    const float* w2 = head == 0 ? w.rew_w2 : (head == 1 ? w.dyn_w2 : (head == 2 ? w.val_w2 : w.pol_w2));
-    const int kin = head < 2 ? H + A : H;          // real input width of the first layer
+    const float* dyn_w1 = init ? w.rep_w1 : w.dyn_w1;
+    const float* dyn_b1 = init ? w.rep_b1 : w.dyn_b1;
+    const float* dyn_w2 = init ? w.rep_w2 : w.dyn_w2;
+    const float* w1t = head == 0 ? w.rew_w1 : (head == 1 ? dyn_w1 : (head == 2 ? w.val_w1 : w.pol_w1));
+    const float* b1 = head == 0 ? w.rew_b1 : (head == 1 ? dyn_b1 : (head == 2 ? w.val_b1 : w.pol_b1));
+    const float* w2 = head == 0 ? w.rew_w2 : (head == 1 ? dyn_w2 : (head == 2 ? w.val_w2 : w.pol_w2));
+    const int kin = head < 2 ? (init ? w.obs_dim : H + A) : H;  // real input width of the first layer
     const int nout = head == 0 ? w.reward_bins : (head == 1 ? H : (head == 2 ? w.value_bins : A));
     // W1 chunk: B operand [CHUNK features x K], element (n, k) = w1t[k][f0 + n]
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CHUNK * g.k; i += gridDim.x * blockDim.x) {
@@ -622,7 +656,7 @@ __global__ void fc_tc_pack_kernel(mz_fc_weights w, int k1, uint8_t* chunks, floa
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TAIL_FLOATS; i += gridDim.x * blockDim.x) {
     float x = 0.0f;
     if (i < T_DYN_B) x = i < w.reward_bins ? w.rew_b2[i] : 0.0f;
-    else if (i < T_LN_W) x = (i - T_DYN_B) < H ? w.dyn_b2[i - T_DYN_B] : 0.0f;
+    else if (i < T_LN_W) x = (i - T_DYN_B) < H ? (init ? w.rep_b2 : w.dyn_b2)[i - T_DYN_B] : 0.0f;
     else if (i < T_LN_B) x = (i - T_LN_W) < H ? w.ln_w[i - T_LN_W] : 0.0f;
     else if (i < T_VAL_B) x = (i - T_LN_B) < H ? w.ln_b[i - T_LN_B] : 0.0f;
     else if (i < T_POL_B) x = (i - T_VAL_B) < w.value_bins ? w.val_b2[i - T_VAL_B] : 0.0f;
@@ -635,9 +669,29 @@ int k1_for(int A) { return (H + A + 1 + 15) / 16 * 16; }  // state + one-hot + b
 
 long long* g_tc_trace = nullptr;
 
-size_t tc_smem_bytes(int k1) {
-  return (size_t)ROWS * k1 * 2 + (size_t)STAGES * stage_bytes_for(k1) +
+int k1_obs(int obs_dim) { return (obs_dim + 1 + 15) / 16 * 16; }  // observation + bias column
+
+size_t tc_smem_bytes(int k1, int stages) {
+  return (size_t)ROWS * k1 * 2 + (size_t)stages * stage_bytes_for(k1) +
          21 * sizeof(uint64_t) + TAIL_FLOATS * sizeof(float) + ROWS * (OUT_STRIDE + 32) * sizeof(float);
+}
+
+constexpr size_t kTcMaxSmem = 232448;
+
+int launch_tc(const TcParams& p, void* stream) {
+  const size_t smem = tc_smem_bytes(p.k1, p.stages);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(fc_recurrent_tc_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcMaxSmem);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  if (smem > kTcMaxSmem) return MZ_ERR_UNSUPPORTED;
+  const int grid = (p.batch + ROWS - 1) / ROWS;
+  fc_recurrent_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
 }
 
 }  // namespace
@@ -661,7 +715,7 @@ int mz_fc_tc_pack(const mz_fc_weights* w, void* packed, float* tail, void* strea
   if (w->num_actions < 1 || w->num_actions > 32 || w->value_bins < 1 || w->value_bins > 32 ||
       w->reward_bins < 1 || w->reward_bins > 32)
     return MZ_ERR_UNSUPPORTED;
-  fc_tc_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(*w, k1_for(w->num_actions), (uint8_t*)packed, tail);
+  fc_tc_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(*w, k1_for(w->num_actions), 0, (uint8_t*)packed, tail);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }
@@ -697,19 +751,63 @@ int mz_fc_recurrent_tc(const mz_fc_weights* w, const void* packed, const float* 
   p.reward = reward;
   p.logits = logits;
   p.trace = g_tc_trace;
-  const size_t smem = tc_smem_bytes(p.k1);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(fc_recurrent_tc_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
-  if (smem > 232448) return MZ_ERR_UNSUPPORTED;
-  const int grid = (batch + ROWS - 1) / ROWS;
-  fc_recurrent_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+  p.chunk0 = 0;
+  p.stages = MAX_STAGES;
+  p.obs = nullptr;
+  p.obs_dim = 0;
+  return launch_tc(p, stream);
+}
+
+/* Initial-inference image: representation head (K = obs_dim + bias column) + value + policy. */
+int64_t mz_fc_tc_initial_packed_bytes(int32_t obs_dim) {
+  if (obs_dim < 1) return MZ_ERR_BAD_ARG;
+  const int k1 = k1_obs(obs_dim);
+  if (tc_smem_bytes(k1, 2) > kTcMaxSmem) return MZ_ERR_UNSUPPORTED;
+  return (int64_t)(chunk_offset(NCHUNK, k1) - chunk_offset(4, k1));
+}
+
+int mz_fc_tc_pack_initial(const mz_fc_weights* w, void* packed, float* tail, void* stream) {
+  if (!w || !packed || !tail) return MZ_ERR_BAD_ARG;
+  if (w->num_actions < 1 || w->num_actions > 32 || w->value_bins < 1 || w->value_bins > 32)
+    return MZ_ERR_UNSUPPORTED;
+  if (tc_smem_bytes(k1_obs(w->obs_dim), 2) > kTcMaxSmem) return MZ_ERR_UNSUPPORTED;
+  fc_tc_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(*w, k1_obs(w->obs_dim), 4, (uint8_t*)packed, tail);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
+}
+
+int mz_fc_initial_tc(const mz_fc_weights* w, const void* packed, const float* tail, int32_t batch,
+                     const float* obs, float* hidden_out, int64_t out_row_stride, float* value,
+                     float* logits, void* stream) {
+  if (!w || !packed || !tail || batch < 1 || !obs || !hidden_out || !value || !logits) return MZ_ERR_BAD_ARG;
+  if (w->num_actions < 1 || w->num_actions > 32 || w->value_bins > 32) return MZ_ERR_UNSUPPORTED;
+  TcParams p;
+  p.chunks = (const uint8_t*)packed;
+  p.tail = tail;
+  p.k1 = k1_obs(w->obs_dim);
+  p.num_actions = w->num_actions;
+  p.value_bins = w->value_bins;
+  p.reward_bins = w->reward_bins;
+  p.value_min = w->value_min;
+  p.reward_min = w->reward_min;
+  p.no_tt = w->no_target_transform;
+  p.batch = batch;
+  p.hidden_in = nullptr;
+  p.in_row_stride = 0;
+  p.in_index = nullptr;
+  p.actions = nullptr;
+  p.hidden_out = hidden_out;
+  p.out_row_stride = out_row_stride;
+  p.out_offset = 0;
+  p.value = value;
+  p.reward = nullptr;
+  p.logits = logits;
+  p.trace = nullptr;
+  p.chunk0 = 4;
+  p.stages = 2;
+  p.obs = obs;
+  p.obs_dim = w->obs_dim;
+  return launch_tc(p, stream);
 }
 
 }  // extern "C"

@@ -106,6 +106,16 @@ class FCNetwork(object):
       _lib.check(self.lib.mz_fc_tc_pack(self.weights, _lib.ptr(self._tc_packed),
                                         _lib.ptr(self._tc_tail), _lib.current_stream()),
                  "mz_fc_tc_pack")
+      # initial_inference image (representation + prediction heads); observations too wide for
+      # the kernel's shared-memory budget stay on the float32 kernel
+      self._tc_init_packed = self._tc_init_tail = None
+      nbytes = int(self.lib.mz_fc_tc_initial_packed_bytes(self.input_dim))
+      if nbytes > 0:
+        self._tc_init_packed = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self._tc_init_tail = torch.zeros_like(self._tc_tail)
+        _lib.check(self.lib.mz_fc_tc_pack_initial(self.weights, _lib.ptr(self._tc_init_packed),
+                                                  _lib.ptr(self._tc_init_tail), _lib.current_stream()),
+                   "mz_fc_tc_pack_initial")
 
   load_state_dict = load_weights
 
@@ -133,10 +143,20 @@ class FCNetwork(object):
       hidden_stride = HIDDEN
     value = torch.empty((B, 1), dtype=torch.float32, device=self.device)
     logits = torch.empty((B, self.action_space), dtype=torch.float32, device=self.device)
-    _lib.check(self.lib.mz_fc_initial_f32(self.weights, B, _lib.ptr(obs), _lib.ptr(hidden_out),
-                                          int(hidden_stride), _lib.ptr(value), _lib.ptr(logits),
-                                          _lib.current_stream()), "mz_fc_initial_f32")
+    fn, args = self.initial_call(B, obs, hidden_out, hidden_stride, value, logits, _lib.current_stream())
+    _lib.check(fn(*args), fn.__name__)
     return NetworkOutput(value, 0, logits, hidden_out)
+
+  def initial_call(self, B, obs, hidden_out, hidden_stride, value, logits, stream):
+    """(C function, arguments) of initial_inference: the tensor-core kernel when the network runs
+    in bf16 and the observation fits it, else the float32 CUDA-core kernel."""
+    P = _lib.ptr
+    if self.precision == 'bf16' and getattr(self, '_tc_init_packed', None) is not None:
+      return self.lib.mz_fc_initial_tc, (self.weights, P(self._tc_init_packed), P(self._tc_init_tail), B,
+                                         P(obs), P(hidden_out), int(hidden_stride), P(value), P(logits),
+                                         stream)
+    return self.lib.mz_fc_initial_f32, (self.weights, B, P(obs), P(hidden_out), int(hidden_stride),
+                                        P(value), P(logits), stream)
 
   def recurrent_inference(self, hidden_state, action):
     """BaseNetwork.recurrent_inference (networks.py:31-34).  `action`: B ints (list or tensor)."""
@@ -207,8 +227,7 @@ class _Lane(object):
     lib, P, st = net.lib, _lib.ptr, C.c_void_p(stream_ptr)
     stride = (S + 1) * HIDDEN
     tree = C.byref(eng.tree)
-    plan = [(lib.mz_fc_initial_f32, (net.weights, G, P(self.obs), P(self.hidden_f32), stride,
-                                     P(self.init_value), P(self.root_logits), st)),
+    plan = [net.initial_call(G, self.obs, self.hidden_f32, stride, self.init_value, self.root_logits, st),
             (lib.mz_tree_set_root, (tree, P(self.root_logits), P(self.legal),
                                     P(self.noise) if use_noise else None, float(noise_frac),
                                     P(self.to_play), None, st)),

@@ -78,6 +78,33 @@ def test_fc_tensor_core_matches_f32(name, obs_dim, A, batch):
     assert np.allclose(b.hidden_state.cpu().numpy(), g["rec_hidden"], rtol=0, atol=3e-2)
 
 
+@pytest.mark.parametrize("name,obs_dim,A", [("atari18", 128, 18), ("ttt", 9, 9)])
+@pytest.mark.parametrize("batch", [64, 300])
+def test_fc_initial_tensor_core_matches_f32(name, obs_dim, A, batch):
+  """initial_inference on the tcgen05 kernel (representation + prediction heads) vs the float32
+  kernel and, at B=64, the reference golden.  Same bf16 tolerance as the recurrent kernel."""
+  g = load("fcnet_" + name)
+  f32 = _net_from_golden(g, obs_dim, A, "f32")
+  tc = _net_from_golden(g, obs_dim, A, "bf16")
+  assert tc._tc_init_packed is not None
+  rng = np.random.default_rng(batch)
+  obs = (torch.from_numpy(g["obs"]) if batch == 64 else
+         torch.from_numpy(rng.random((batch, obs_dim)).astype(np.float32))).cuda()
+  a = f32.initial_inference(obs)
+  b = tc.initial_inference(obs)
+  torch.cuda.synchronize()
+  assert b.reward == 0
+  for name_, x, y in (("hidden", a.hidden_state, b.hidden_state), ("logits", a.policy_logits, b.policy_logits),
+                      ("value", a.value, b.value)):
+    x, y = x.cpu().numpy(), y.cpu().numpy()
+    assert np.isfinite(y).all(), name_
+    err = np.abs(x - y).max()
+    assert err <= 3e-2 * max(1.0, np.abs(x).max()), "%s: max abs err %g" % (name_, err)
+  if batch == 64:
+    assert np.allclose(b.hidden_state.cpu().numpy(), g["init_hidden"], rtol=0, atol=3e-2)
+    assert np.allclose(b.policy_logits.cpu().numpy(), g["init_logits"], rtol=0, atol=3e-2)
+
+
 def test_fc_search_replays_bit_exact_in_oracle():
   """Full move with the real FC network (C4 shape, fewer games): the engine records what the
   network returned for every simulation; the oracle replays the search with those outputs."""
