@@ -377,6 +377,11 @@ int mz_conv_head(int32_t games, const float* hidden, int32_t ldh, const float* w
 int mz_debug_div_check(uint64_t seed, int32_t blocks, int32_t per_thread, uint64_t* mismatches,
                        uint64_t* tested, void* stream);
 
+/* The per-simulation kernels (tree step, recurrent network) are launched as programmatic dependents
+ * (their prologues overlap the predecessor's tail; griddepcontrol.wait before the first dependent
+ * read).  enable = 0 switches back to plain stream-ordered launches.  Default: enabled. */
+int mz_set_programmatic_launch(int32_t enable);
+
 /* Library identification. */
 const char* mz_version(void);
 int32_t mz_compiled_arch(void); /* 100 for sm_100a */

@@ -40,6 +40,33 @@ struct MzGame {
   }
 };
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// A kernel launched with the programmatic-stream-serialization attribute may start while its
+// predecessor in the stream is still running; everything it does before pdl_wait() must neither read
+// what the predecessor writes nor write what it reads.  pdl_trigger() lets the NEXT kernel start its
+// own prologue; it is issued after pdl_wait() so that overlap never spans more than one kernel.
+// Both are no-ops for a plain launch.
+MZ_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+MZ_DEV void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_mz_pdl;  // 1: the per-simulation kernels are launched as programmatic dependents
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t mz_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             bool dependent, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (dependent && g_mz_pdl) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- 64-bit shuffles ---------------------------------------------------------------------------
 template <int W>
 MZ_DEV double shfl_f64(double v, int src) {

@@ -165,6 +165,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  // launched as a programmatic dependent: the set-up above overlapped the previous layer's tail;
+  // activations, residuals and row offsets written by earlier kernels are only touched below
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -414,7 +418,9 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& 
   }
   const int tiles = p.num_tiles_m * p.num_tiles_n;
   const int grid = tiles < sms ? tiles : sms;
-  conv_gemm_tc_kernel<<<grid, CONV_THREADS, kConvSmem, (cudaStream_t)stream>>>(ma, mb, p);
+  cudaError_t e = mz_launch(conv_gemm_tc_kernel, dim3(grid), dim3(CONV_THREADS), kConvSmem,
+                            (cudaStream_t)stream, true, ma, mb, p);
+  if (e != cudaSuccess) return (int)e;
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }

@@ -286,6 +286,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   // epilogue threads request their row's gather index / action before the set-up barrier
   int pre_idx = 0, pre_act = 0;
   if (warp >= 2 && warp < MMA2_WARP) {
+    // everything this kernel reads from its predecessor (gather index, actions, hidden states) is
+    // read by the epilogue warps, after this point; weights, barriers and TMEM do not depend on it
+    pdl_wait();
+    pdl_trigger();
     const int g0 = blockIdx.x * ROWS + (warp & 3) * 32 + lane;
     const int gc0 = g0 < p.batch ? g0 : p.batch - 1;
     if (!p.obs) {
@@ -689,7 +693,9 @@ int launch_tc(const TcParams& p, void* stream) {
   }
   if (smem > kTcMaxSmem) return MZ_ERR_UNSUPPORTED;
   const int grid = (p.batch + ROWS - 1) / ROWS;
-  fc_recurrent_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+  cudaError_t e = mz_launch(fc_recurrent_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream,
+                            p.obs == nullptr, p);
+  if (e != cudaSuccess) return (int)e;
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }

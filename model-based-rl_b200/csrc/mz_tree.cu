@@ -13,6 +13,8 @@
 #include "mz_common.cuh"
 #include "mz_exp.cuh"
 
+int g_mz_pdl = 1;
+
 namespace {
 
 constexpr int kThreads = 128;
@@ -749,6 +751,8 @@ tree_step_w32_kernel(mz_tree t, int sim, int do_backup, int do_select, int live_
   if (do_backup) {
     // everything the backup needs from global memory is requested before waiting for the image
     const int depth = t.path_len[g], parent = t.leaf_parent[g], action = t.leaf_action[g];
+    pdl_wait();     // the network kernel's outputs (and nothing before this line) depend on it
+    pdl_trigger();
     const float logit = lane < A ? logits[(size_t)g * A + lane] : 0.0f;
     const float v = value[g], r = reward[g];
     if (STAGED) mbar_wait(&bars[warp], 0);
@@ -756,8 +760,10 @@ tree_step_w32_kernel(mz_tree t, int sim, int do_backup, int do_select, int live_
     if (new_hidden && HW > 0)
       copy_words<32>(t.hidden + ((size_t)g * SP1 + sim + 1) * HW, new_hidden + (size_t)g * HW, HW, lane);
     __syncwarp();
-  } else if (STAGED) {
-    mbar_wait(&bars[warp], 0);
+  } else {
+    pdl_wait();
+    pdl_trigger();
+    if (STAGED) mbar_wait(&bars[warp], 0);
   }
   if (do_select) {
     int depth, parent, action;
@@ -1008,14 +1014,16 @@ int launch_step(const mz_tree* t, int sim, int live_nodes, int do_backup, int do
       if (staged) {
         int rc = set_smem_attr_w32_once<true>();
         if (rc) return rc;
-        tree_step_w32_kernel<true><<<grid, gpb * 32, (size_t)gpb * stage_bytes + sizeof(uint64_t) * gpb,
-                                     (cudaStream_t)stream>>>(
-            *t, sim, do_backup, do_select, live_nodes, stage_bytes, value, reward, logits, new_hidden,
-            gathered_hidden, tp, ta, td);
+        cudaError_t e = mz_launch(tree_step_w32_kernel<true>, dim3(grid), dim3(gpb * 32),
+                                  (size_t)gpb * stage_bytes + sizeof(uint64_t) * gpb, (cudaStream_t)stream,
+                                  do_backup != 0, *t, sim, do_backup, do_select, live_nodes, stage_bytes, value,
+                                  reward, logits, new_hidden, gathered_hidden, tp, ta, td);
+        if (e != cudaSuccess) return (int)e;
       } else {
-        tree_step_w32_kernel<false><<<grid, gpb * 32, 0, (cudaStream_t)stream>>>(
-            *t, sim, do_backup, do_select, live_nodes, 0, value, reward, logits, new_hidden,
-            gathered_hidden, tp, ta, td);
+        cudaError_t e = mz_launch(tree_step_w32_kernel<false>, dim3(grid), dim3(gpb * 32), 0,
+                                  (cudaStream_t)stream, do_backup != 0, *t, sim, do_backup, do_select,
+                                  live_nodes, 0, value, reward, logits, new_hidden, gathered_hidden, tp, ta, td);
+        if (e != cudaSuccess) return (int)e;
       }
       MZ_LAUNCH_CHECK();
       return MZ_OK;
@@ -1178,6 +1186,11 @@ int mz_debug_div_check(uint64_t seed, int32_t blocks, int32_t per_thread, uint64
   div_check_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       seed, per_thread, (unsigned long long*)mismatches, (unsigned long long*)tested);
   MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+int mz_set_programmatic_launch(int32_t enable) {
+  g_mz_pdl = enable ? 1 : 0;
   return MZ_OK;
 }
 
