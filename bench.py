@@ -436,10 +436,10 @@ def bench_conv(args, torch, _lib, dev):
   out = net.buffers(G)["x"][0]
   n = 20
   for _ in range(3):
-    net._conv(G, net.dyn_tower[0], x, G * ROWS, None, 3, out, residual=x)
+    net._conv(G, net.dyn_tower[0], x, 3, out, residual=x)
   a.record()
   for _ in range(n):
-    net._conv(G, net.dyn_tower[0], x, G * ROWS, None, 3, out, residual=x)
+    net._conv(G, net.dyn_tower[0], x, 3, out, residual=x)
   b.record()
   torch.cuda.synchronize()
   us_conv = a.elapsed_time(b) * 1e3 / n
@@ -448,7 +448,7 @@ def bench_conv(args, torch, _lib, dev):
   roof = {"kernel": "conv_gemm_tc_kernel", "bound": "tensor", "achieved": flops / us_conv / 1e6,
           "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "traffic": None,
           "algorithmic_flops_per_launch": flops, "avg_launch_us": us_conv,
-          "issued_tflops": 2.0 * G * 64 * 128 * 1152 / us_conv / 1e6, "peak_source": peaks["source"]}
+          "issued_tflops": 2.0 * G * ROWS * 128 * 1152 / us_conv / 1e6, "peak_source": peaks["source"]}
   roof["frac"] = roof["achieved"] / roof["peak"]
   del cs
   return {"workload": "C5 MuZeroNetwork residual conv (16+16 blocks, 128 ch, 6x6 state), %d games x %d "

@@ -334,34 +334,31 @@ int mz_sumtree_sample(const double* tree, int64_t max_capacity, int32_t n, const
 
 /* ------------------------------------------------------------------------------------------- */
 /* MuZeroNetwork (residual conv tower, networks.py:393-554) on tcgen05 tensor cores, bf16/f32 acc. */
-/* Activations: channels-last bf16 with a one-pixel zero border, 8 x 8 = 64 rows of 128 channels   */
-/* per game (interior 6 x 6), so a 3x3 tap is a row shift and the implicit GEMM needs no im2col.   */
+/* Activations: flat [games * 49][128] bf16, channels last, shared zero padding: a game is one zero  */
+/* row of 7 followed by 6 image rows of (6 pixels + 1 zero), so every out-of-image 3x3 neighbour     */
+/* is a zero row and a tap is a row shift of dy*7 + dx: the implicit GEMM needs no im2col.           */
 /* ------------------------------------------------------------------------------------------- */
+#define MZ_CONV_ROWS_PER_GAME 49
 #define MZ_CONV_RELU 1      /* max(x, 0) */
 #define MZ_CONV_RESIDUAL 2  /* += residual before the ReLU            ResidualBlock.forward networks.py:384-391 */
 #define MZ_CONV_ACTION 4    /* += actions[g] / A * plane_term[pixel]  MuZeroNetwork.attach_action networks.py:536-541 */
 #define MZ_CONV_SCALE 8     /* also emit (x - min_c) / (max_c - min_c) MuZeroNetwork.scale_state networks.py:543-547 */
 /* Conv2d(128 -> 128, 3x3, padding 1) with BatchNorm2d (eval) folded into w_packed / bias.
- *   x          [x_rows][128] bf16; game g's 64-row block starts at row x_row_base[g] (NULL: g * 64)
- *              -- this is how the hidden-state pool is gathered in place (row = (g*(S+1)+parent)*64)
+ *   x, residual, out, out_scaled [games*49][128] bf16 (out may be NULL with MZ_CONV_SCALE)
  *   w_packed   [128][9*128] bf16, k = (ky*3 + kx)*128 + c_in;   bias [128] f32
  *   plane_term [36][128] f32, actions [games] i32 (flags & MZ_CONV_ACTION)
- *   residual [..][128] bf16 with game g's block at row res_row_base[g] (NULL: g * 64);
- *   out [games*64][128] bf16, may be NULL with MZ_CONV_SCALE
- *   out_scaled [..][128] bf16, block of game g at row scaled_row_base[g] (NULL: g * 64)
- * games must be even (a tile is two games). */
-int mz_conv3x3_tc(int32_t games, const void* x, int64_t x_rows, const int32_t* x_row_base,
-                  const void* w_packed, const float* bias, int32_t flags, const float* plane_term,
-                  const int32_t* actions, int32_t num_actions, const void* residual,
-                  const int32_t* res_row_base, void* out, void* out_scaled,
-                  const int32_t* scaled_row_base, void* stream);
-/* out[g] = (g * nodes_per_game + node[g]) * 64: row of hidden-pool slot [g][node[g]] in a pool laid
- * out [G][nodes_per_game][64][128] bf16 -- the gather index for search_path[-2].hidden_state
- * (mcts.py:94-96) as mz_conv3x3_tc's x_row_base. */
-int mz_conv_row_base(int32_t games, int32_t nodes_per_game, const int32_t* node, int32_t* out,
-                     void* stream);
-/* Linear(6*6*128 -> n_out) (+ReLU) of the heads over the padded state: x [games][8192] bf16,
- * w_packed [n_out][8192] bf16 in the padded channels-last order, out [games][ldo] f32;
+ *   pool_out, pool_row_base [games]: with MZ_CONV_SCALE the scaled rows of game g are also written
+ *   to rows pool_row_base[g] .. +49 of pool_out (the hidden-pool slot of the node being expanded). */
+int mz_conv3x3_tc(int32_t games, const void* x, const void* w_packed, const float* bias, int32_t flags,
+                  const float* plane_term, const int32_t* actions, int32_t num_actions,
+                  const void* residual, void* out, void* out_scaled, void* pool_out,
+                  const int32_t* pool_row_base, void* stream);
+/* out rows [g*49, g*49+49) = pool slot [g][node[g]] of a pool laid out [G][nodes_per_game][49][128]
+ * bf16: the gather of search_path[-2].hidden_state (mcts.py:94-96) into the flat layout. */
+int mz_conv_gather(int32_t games, int32_t nodes_per_game, const int32_t* node, const void* pool, void* out,
+                   void* stream);
+/* Linear(6*6*128 -> n_out) (+ReLU) of the heads over the padded state: x [games][6272] bf16,
+ * w_packed [n_out][6272] bf16 in the padded channels-last order, out [games][ldo] f32;
  * n_out % 128 == 0.  networks.py:436-439, 470-478. */
 int mz_conv_fc_tc(int32_t games, const void* x, const void* w_packed, const float* bias, int32_t n_out,
                   int32_t relu, float* out, int32_t ldo, void* stream);

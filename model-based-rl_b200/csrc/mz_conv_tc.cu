@@ -6,10 +6,13 @@
 //
 //   conv3x3 (pad 1, stride 1) with BatchNorm folded:  D[row, n] = sum_{tap, c} X[row + off(tap), c] *
 //       W[n, tap * 128 + c],   off(tap) = (ky - 1) * 8 + (kx - 1)
-//   on activations stored channels-last in bf16 with a one-pixel zero border: a game is 8 x 8 = 64
-//   rows of 128 channels (interior 6 x 6), so a tap is a pure row shift and the A operand of every
-//   tap is a TMA tile load at a shifted row coordinate -- no im2col buffer exists anywhere.
-//   Linear(6*6*128 -> 512) heads: the same kernel with one "tap", K = 64 * 128 (the border rows
+//   on activations stored channels-last in bf16 with shared zero padding: a game is 49 rows of 128
+//   channels -- one zero row of 7, then 6 image rows of 6 pixels + 1 zero -- so every 3x3 neighbour
+//   of a pixel that falls outside the image lands on a zero row (of this game or the next one), a tap
+//   is a pure row shift of the flat [games * 49][128] matrix, and the A operand of every tap is a
+//   TMA tile load at a shifted row coordinate -- no im2col buffer exists anywhere.  36 of 49 rows
+//   are real pixels.  Tiles are 128 consecutive rows (they do not align with games).
+//   Linear(6*6*128 -> 512) heads: the same kernel with one "tap", K = 49 * 128 (the padding rows
 //   are zero, the weights are permuted to the padded channels-last order at pack time).
 //
 // Tile: 128 rows (two games, or 128 games for the heads) x 128 outputs, K blocks of 64 bf16 (one
@@ -26,6 +29,7 @@
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int GROWS = 49;                        // rows per game: 7 zero | 6 x (6 pixels + 1 zero)
 constexpr int STAGES = 6;
 constexpr int STAGE_BYTES = (BM + BN) * BK * 2;  // 32 KB
 constexpr int CONV_THREADS = 192;                // producer, MMA, 4 epilogue warps
@@ -45,16 +49,14 @@ struct ConvParams {
   int rows_total;            // conv: games * 64; fc: games
   int flags;
   int num_actions;
-  const int32_t* row_base;   // conv: [games] first row of each game's 64-row block in the A tensor
-                             // (hidden-pool gather), or nullptr = g * 64
   const float* bias;         // [N_total]
   const float* plane_term;   // [36][128] (EPI_ACTION)
   const int32_t* actions;    // [games]   (EPI_ACTION)
-  const __nv_bfloat16* residual;  // [..][128] (EPI_RESIDUAL); game g's block at res_row_base[g] or g * 64
-  const int32_t* res_row_base;
+  const __nv_bfloat16* residual;  // [rows][128] (EPI_RESIDUAL)
   __nv_bfloat16* out;        // conv: [rows][128] bf16
-  __nv_bfloat16* out_scaled; // EPI_SCALE: rows of game g start at out_scaled + scaled_row_base[g] * 128
-  const int32_t* scaled_row_base;  // [games] or nullptr = g * 64
+  __nv_bfloat16* out_scaled; // EPI_SCALE: [rows][128] scaled state (flat, input of the prediction tower)
+  __nv_bfloat16* pool_out;   // EPI_SCALE, optional: the same rows scattered into the hidden pool,
+  const int32_t* pool_row_base;  //   game g's 49 rows starting at row pool_row_base[g]
   float* out_f32;            // EPI_F32_OUT: [M][ldo]
   int ldo;
 };
@@ -175,15 +177,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.num_tiles_n, tn = tile % p.num_tiles_n;
-      int rb0, rb1;
-      if (p.mode_fc) {
-        rb0 = tm * BM;
-        rb1 = rb0 + 64;
-      } else {
-        const int g0 = tm * 2;
-        rb0 = p.row_base ? p.row_base[g0] : g0 * 64;
-        rb1 = p.row_base ? p.row_base[g0 + 1] : (g0 + 1) * 64;
-      }
+      const int rb0 = tm * BM, rb1 = rb0 + 64;
       for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
         const int st = it % STAGES;
         mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
@@ -193,7 +187,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           int shift = 0, ka = kb * BK;
           if (!p.mode_fc) {  // k block = (tap, channel half)
             const int tap = kb >> 1;
-            shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
+            shift = (tap / 3 - 1) * 7 + (tap % 3 - 1);
             ka = (kb & 1) * BK;
           }
           mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
@@ -268,19 +262,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         }
       } else {
-        const int g = tm * 2 + (r_in_tile >> 6);
-        const int pos = r_in_tile & 63, py = pos >> 3, px = pos & 7;
-        const bool interior = py >= 1 && py <= 6 && px >= 1 && px <= 6;
-        const size_t row = (size_t)g * 64 + pos;
-        const bool in_range = row < (size_t)p.rows_total;
+        const int R = tm * BM + r_in_tile;  // flat row
+        const int g = R / GROWS, pos = R - g * GROWS;
+        const int py = (pos - 7) / 7, px = (pos - 7) - py * 7;
+        const bool interior = pos >= 7 && px < 6;
+        const size_t row = (size_t)R;
+        const bool in_range = R < p.rows_total;
         float act_scale = 0.0f;
         const float* plane = nullptr;
         if ((p.flags & EPI_ACTION) && interior && in_range) {
           act_scale = (float)p.actions[g] / (float)p.num_actions;
-          plane = p.plane_term + ((py - 1) * 6 + (px - 1)) * BN;
+          plane = p.plane_term + (py * 6 + px) * BN;
         }
-        const size_t rrow = (p.res_row_base && in_range ? (size_t)p.res_row_base[g] : (size_t)g * 64) + pos;
-        const uint4* res = reinterpret_cast<const uint4*>(p.residual + rrow * BN);
+        const uint4* res = reinterpret_cast<const uint4*>(p.residual + row * BN);
         uint4* orow = reinterpret_cast<uint4*>(p.out + row * BN);
         const bool add_res = (p.flags & EPI_RESIDUAL) && interior && in_range;
         // x[0..32) = layer output for channels c0..c0+31 of this row (zero on the border)
@@ -335,10 +329,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                                                pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
           }
         }
-        if ((p.flags & EPI_SCALE) && in_range) {
-          // MuZeroNetwork.scale_state networks.py:543-547: second pass over the accumulator row
-          const size_t srow = (p.scaled_row_base ? (size_t)p.scaled_row_base[g] : (size_t)g * 64) + pos;
-          uint4* so = reinterpret_cast<uint4*>(p.out_scaled + srow * BN);
+        if (p.flags & EPI_SCALE) {
+          // MuZeroNetwork.scale_state networks.py:543-547: second pass over the accumulator row.
+          // tcgen05.ld is warp-collective: every lane walks the pass, only the stores are predicated
+          // (tiles do not align with games, so `in_range` is not warp-uniform)
+          uint4* so = reinterpret_cast<uint4*>(p.out_scaled + row * BN);
+          uint4* po = (p.pool_out && in_range)
+                          ? reinterpret_cast<uint4*>(p.pool_out + ((size_t)p.pool_row_base[g] + pos) * BN)
+                          : nullptr;
           const float den = mx - mn;
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -346,10 +344,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             chunk(c0, x);
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = interior ? (x[j] - mn) / den : 0.0f;
+            if (in_range) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              so[(c0 >> 3) + q] = make_uint4(pack_bf16(x[q * 8], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
-                                             pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
+              for (int q = 0; q < 4; ++q) {
+                const uint4 o = make_uint4(pack_bf16(x[q * 8], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                                           pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
+                so[(c0 >> 3) + q] = o;
+                if (po) po[(c0 >> 3) + q] = o;
+              }
+            }
           }
         }
       }
@@ -471,88 +474,96 @@ __global__ void conv_head_kernel(int G, const float* __restrict__ hidden, int ld
   }
 }
 
-// out[g] = (g * nodes_per_game + node[g]) * 64: first row of a hidden-pool slot
-__global__ void conv_row_base_kernel(int G, int nodes_per_game, const int32_t* __restrict__ node,
-                                     int32_t* __restrict__ out) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < G) out[g] = (g * nodes_per_game + node[g]) * 64;
+// out rows [g * 49, g * 49 + 49) = pool slot [g][node[g]] (pool = [G][nodes_per_game][49][128] bf16):
+// the gather of search_path[-2].hidden_state (mcts.py:94-96) into the flat layout the GEMM tiles.
+// One warp per row (256 B), 16-byte loads.
+__global__ void conv_gather_kernel(int G, int nodes_per_game, const int32_t* __restrict__ node,
+                                   const uint4* __restrict__ pool, uint4* __restrict__ out) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= G * GROWS) return;
+  const int g = w / GROWS, r = w - g * GROWS;
+  const size_t src = ((size_t)g * nodes_per_game + node[g]) * GROWS + r;
+  if (lane < 16) out[(size_t)w * 16 + lane] = pool[src * 16 + lane];
 }
 
 }  // namespace
 
 extern "C" {
 
-// Row offsets of the hidden-pool slots [g][node[g]] (pool = [G][nodes_per_game][64 rows][128] bf16):
-// the gather index of recurrent_inference(search_path[-2].hidden_state, ...) (mcts.py:94-96).
-int mz_conv_row_base(int32_t games, int32_t nodes_per_game, const int32_t* node, int32_t* out,
-                     void* stream) {
-  if (games < 1 || nodes_per_game < 1 || !node || !out) return MZ_ERR_BAD_ARG;
-  if ((int64_t)games * nodes_per_game * 64 > 0x7fffffffLL) return MZ_ERR_UNSUPPORTED;
-  conv_row_base_kernel<<<(games + 255) / 256, 256, 0, (cudaStream_t)stream>>>(games, nodes_per_game, node, out);
+// Gathers hidden-pool slots [g][node[g]] into the flat activation layout: out [games * 49][128] bf16.
+int mz_conv_gather(int32_t games, int32_t nodes_per_game, const int32_t* node, const void* pool, void* out,
+                   void* stream) {
+  if (games < 1 || nodes_per_game < 1 || !node || !pool || !out) return MZ_ERR_BAD_ARG;
+  const long long warps = (long long)games * GROWS;
+  conv_gather_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      games, nodes_per_game, node, (const uint4*)pool, (uint4*)out);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }
 
 // 3x3 convolution (+ folded BatchNorm, bias, optional action plane / residual / ReLU / state scaling)
-// over `games` hidden states in the padded channels-last bf16 layout (64 rows x 128 channels per game).
-//   x            A tensor: [x_rows][128] bf16; game g's block starts at row x_row_base[g] (or g * 64)
+// over `games` hidden states in the flat padded channels-last bf16 layout (49 rows x 128 channels per
+// game).
+//   x, residual, out, out_scaled   [games * 49][128] bf16
 //   w_packed     [128][9 * 128] bf16, k = (ky * 3 + kx) * 128 + c_in
 //   bias         [128] f32;  plane_term [36][128] f32 and actions [games] when flags & 4
-//   residual (+ res_row_base like x), out [games * 64][128] bf16;  out_scaled + scaled_row_base like
-//   x when flags & 8
-int mz_conv3x3_tc(int32_t games, const void* x, int64_t x_rows, const int32_t* x_row_base,
-                  const void* w_packed, const float* bias, int32_t flags, const float* plane_term,
-                  const int32_t* actions, int32_t num_actions, const void* residual,
-                  const int32_t* res_row_base, void* out, void* out_scaled,
-                  const int32_t* scaled_row_base, void* stream) {
-  if (games < 1 || (games & 1) || !x || !w_packed || !bias || x_rows < 64) return MZ_ERR_BAD_ARG;
+//   pool_out + pool_row_base: with flags & 8 the scaled rows of game g are also written at rows
+//   pool_row_base[g] .. + 49 of pool_out (the hidden pool slot of the new node)
+int mz_conv3x3_tc(int32_t games, const void* x, const void* w_packed, const float* bias, int32_t flags,
+                  const float* plane_term, const int32_t* actions, int32_t num_actions,
+                  const void* residual, void* out, void* out_scaled, void* pool_out,
+                  const int32_t* pool_row_base, void* stream) {
+  if (games < 1 || !x || !w_packed || !bias) return MZ_ERR_BAD_ARG;
   if ((flags & EPI_ACTION) && (!plane_term || !actions || num_actions < 1)) return MZ_ERR_BAD_ARG;
   if ((flags & EPI_RESIDUAL) && !residual) return MZ_ERR_BAD_ARG;
   if ((flags & EPI_SCALE) && !out_scaled) return MZ_ERR_BAD_ARG;
   if (!(flags & EPI_SCALE) && !out) return MZ_ERR_BAD_ARG;
+  if (pool_out && !pool_row_base) return MZ_ERR_BAD_ARG;
   if (flags & EPI_F32_OUT) return MZ_ERR_BAD_ARG;
+  const long long rows = (long long)games * GROWS;
+  if (rows > 0x7fffffffLL - 2 * BM) return MZ_ERR_UNSUPPORTED;
   CUtensorMap ma, mb;
-  int rc = make_map(&ma, x, (uint64_t)x_rows, 128);
+  int rc = make_map(&ma, x, (uint64_t)rows, 128);
   if (rc) return rc;
   rc = make_map(&mb, w_packed, 128, 9 * 128);
   if (rc) return rc;
   ConvParams p = {};
   p.mode_fc = 0;
-  p.num_tiles_m = games / 2;
+  p.num_tiles_m = (int)((rows + BM - 1) / BM);
   p.num_tiles_n = 1;
   p.num_kblocks = 18;
-  p.rows_total = games * 64;
+  p.rows_total = (int)rows;
   p.flags = flags;
   p.num_actions = num_actions;
-  p.row_base = x_row_base;
   p.bias = bias;
   p.plane_term = plane_term;
   p.actions = actions;
   p.residual = (const __nv_bfloat16*)residual;
-  p.res_row_base = res_row_base;
   p.out = (__nv_bfloat16*)out;
   p.out_scaled = (__nv_bfloat16*)out_scaled;
-  p.scaled_row_base = scaled_row_base;
+  p.pool_out = (__nv_bfloat16*)pool_out;
+  p.pool_row_base = pool_row_base;
   return launch_conv(ma, mb, p, stream);
 }
 
-// Linear(64 * 128 -> n_out) over the padded channels-last state (border rows are zero), bias + ReLU:
-//   x [games][8192] bf16 (the activation buffer itself), w_packed [n_out][8192] bf16 (n_out % 128 == 0),
+// Linear(49 * 128 -> n_out) over the padded channels-last state (padding rows are zero), bias + ReLU:
+//   x [games][6272] bf16 (the activation buffer itself), w_packed [n_out][6272] bf16 (n_out % 128 == 0),
 //   out [games][ldo] f32.   networks.py:436-439, 470-478.
 int mz_conv_fc_tc(int32_t games, const void* x, const void* w_packed, const float* bias, int32_t n_out,
                   int32_t relu, float* out, int32_t ldo, void* stream) {
   if (games < 1 || !x || !w_packed || !bias || !out || n_out < 128 || (n_out % 128) || ldo < n_out)
     return MZ_ERR_BAD_ARG;
   CUtensorMap ma, mb;
-  int rc = make_map(&ma, x, (uint64_t)games, 8192);
+  constexpr int KFC = GROWS * 128;
+  int rc = make_map(&ma, x, (uint64_t)games, KFC);
   if (rc) return rc;
-  rc = make_map(&mb, w_packed, (uint64_t)n_out, 8192);
+  rc = make_map(&mb, w_packed, (uint64_t)n_out, KFC);
   if (rc) return rc;
   ConvParams p = {};
   p.mode_fc = 1;
   p.num_tiles_m = (games + BM - 1) / BM;
   p.num_tiles_n = n_out / BN;
-  p.num_kblocks = 8192 / BK;
+  p.num_kblocks = KFC / BK;
   p.rows_total = games;
   p.flags = EPI_F32_OUT | (relu ? EPI_RELU : 0);
   p.bias = bias;

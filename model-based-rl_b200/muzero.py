@@ -5,9 +5,10 @@
 softmax-expectation + h^-1 of config.py:27-33) and `load_weights` / `get_weights` with the
 reference's state-dict keys.  Underneath, every dense layer of `recurrent_inference` -- 65 3x3
 convolutions with BatchNorm folded, the three Linear(4608 -> 512) heads -- is one launch of the
-implicit-GEMM kernel in csrc/mz_conv_tc.cu on bf16 activations in a padded channels-last layout
-(64 rows x 128 channels per game), and the hidden-state pool of the search is read and written in
-place through per-game row offsets.
+implicit-GEMM kernel in csrc/mz_conv_tc.cu on bf16 activations in a flat padded channels-last layout
+(49 rows x 128 channels per game: a zero row of 7, then 6 image rows of 6 pixels + 1 zero); the
+hidden-state pool of the search holds states in the same layout, is gathered by one small copy
+kernel per simulation and written in place by the last dynamics convolution.
 
 Round-1 limitation, stated in DESIGN.md: the representation tower (`initial_inference`, once per
 move, 96x96 inputs with strided convolutions and pooling) runs through torch operators in float32;
@@ -20,23 +21,30 @@ from . import _lib
 from .networks import NetworkOutput
 
 CH = 128          # channels of the hidden state
-ROWS = 64         # padded 8 x 8 positions per game
-K_FC = ROWS * CH  # 8192: flattened padded state
+ROWS = 49         # rows per game: 7 zero | 6 x (6 pixels + 1 zero)
+K_FC = ROWS * CH  # 6272: flattened padded state
 RELU, RESIDUAL, ACTION, SCALE = 1, 2, 4, 8
 BN_EPS = 1e-5
 
 
 def to_padded(state):
-  """[B, 128, 6, 6] float -> [B * 64, 128] bf16 rows (zero border, channels last)."""
+  """[B, 128, 6, 6] float -> [B * 49, 128] bf16 rows (shared zero padding, channels last)."""
   b = state.shape[0]
-  x = F.pad(state.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1))
+  x = F.pad(state.permute(0, 2, 3, 1), (0, 0, 0, 1))         # [B, 6, 7, C]: zero after each image row
+  x = F.pad(x.reshape(b, 42, CH), (0, 0, 7, 0))               # [B, 49, C]: zero row of 7 in front
   return x.reshape(b * ROWS, CH).to(torch.bfloat16).contiguous()
 
 
 def from_padded(rows, b):
-  """[B * 64, 128] bf16 rows -> [B, 128, 6, 6] float32."""
-  x = rows.reshape(b, 8, 8, CH)[:, 1:7, 1:7, :]
+  """[B * 49, 128] bf16 rows -> [B, 128, 6, 6] float32."""
+  x = rows.reshape(b, ROWS, CH)[:, 7:].reshape(b, 6, 7, CH)[:, :, :6, :]
   return x.permute(0, 3, 1, 2).float().contiguous()
+
+
+def padding_rows(rows, b):
+  """The 13 padding rows of every game (must stay zero)."""
+  x = rows.reshape(b, ROWS, CH)
+  return torch.cat((x[:, :7], x[:, 7:].reshape(b, 6, 7, CH)[:, :, 6]), dim=1)
 
 
 class _Conv(object):
@@ -64,11 +72,11 @@ class _Conv(object):
 
 
 def _pack_fc(weight, device):
-  """Linear(128*6*6 -> n) weight [n, c*36 + y*6 + x] -> [n, ((y+1)*8 + (x+1))*128 + c] bf16."""
+  """Linear(128*6*6 -> n) weight [n, c*36 + y*6 + x] -> [n, (7 + y*7 + x)*128 + c] bf16."""
   n = weight.shape[0]
   w = weight.to(device, torch.float32).reshape(n, CH, 6, 6).permute(0, 2, 3, 1)
-  out = torch.zeros((n, 8, 8, CH), dtype=torch.float32, device=device)
-  out[:, 1:7, 1:7, :] = w
+  out = torch.zeros((n, ROWS, CH), dtype=torch.float32, device=device)
+  out[:, 7:].view(n, 6, 7, CH)[:, :, :6, :] = w
   return out.reshape(n, K_FC).to(torch.bfloat16).contiguous()
 
 
@@ -159,71 +167,71 @@ class MuZeroNetwork(object):
 
   # -- buffers ---------------------------------------------------------------------------------------
   def buffers(self, games):
-    """Scratch activations for `games` (even) games: three padded bf16 buffers and the head
-    hidden layer [games][reward 512 | value 512 | policy 512] float32."""
+    """Scratch activations for `games` games: three flat padded bf16 buffers (+ one for the scaled
+    state) and the head hidden layer [games][reward 512 | value 512 | policy 512] float32."""
     b = self._bufs.get(games)
     if b is None:
       dev = self.device
       b = dict(x=[torch.zeros((games * ROWS, CH), dtype=torch.bfloat16, device=dev) for _ in range(3)],
+               scaled=torch.zeros((games * ROWS, CH), dtype=torch.bfloat16, device=dev),
                fc=torch.zeros((games, 1536), dtype=torch.float32, device=dev))
       self._bufs[games] = b
     return b
 
   # -- launches --------------------------------------------------------------------------------------
-  def _conv(self, games, conv, x, x_rows, x_base, flags, out, residual=None, res_base=None, actions=None,
-            out_scaled=None, scaled_base=None):
+  def _conv(self, games, conv, x, flags, out, residual=None, actions=None, out_scaled=None, pool_out=None,
+            pool_base=None):
     P = _lib.ptr
-    _lib.check(self.lib.mz_conv3x3_tc(games, P(x), x_rows, P(x_base), P(conv.w), P(conv.bias), flags,
+    _lib.check(self.lib.mz_conv3x3_tc(games, P(x), P(conv.w), P(conv.bias), flags,
                                       P(conv.plane) if flags & ACTION else None, P(actions),
-                                      self.action_space, P(residual), P(res_base), P(out), P(out_scaled),
-                                      P(scaled_base), _lib.current_stream()), "mz_conv3x3_tc")
+                                      self.action_space, P(residual), P(out), P(out_scaled), P(pool_out),
+                                      P(pool_base), _lib.current_stream()), "mz_conv3x3_tc")
     self.launches += 1
 
-  def _tower(self, games, convs, x, x_rows, x_base, bufs, last_flags=0, out_scaled=None, scaled_base=None):
-    """16 ResidualBlocks (networks.py:372-391) starting from tensor `x` (optionally gathered through
-    x_base).  Returns the scratch buffer holding the (unscaled) output."""
-    cur, cur_rows, cur_base = x, x_rows, x_base
+  def _tower(self, games, convs, x, bufs, last_flags=0, out_scaled=None, pool_out=None, pool_base=None):
+    """16 ResidualBlocks (networks.py:372-391) starting from the flat tensor `x`.  Returns the scratch
+    buffer holding the (unscaled) output."""
+    cur = x
     for i in range(16):
       t, o = [b for b in bufs if b.data_ptr() != cur.data_ptr()][:2]
-      self._conv(games, convs[2 * i], cur, cur_rows, cur_base, RELU, t)
+      self._conv(games, convs[2 * i], cur, RELU, t)
       extra = last_flags if i == 15 else 0
-      self._conv(games, convs[2 * i + 1], t, games * ROWS, None, RELU | RESIDUAL | extra, o, residual=cur,
-                 res_base=cur_base, out_scaled=out_scaled if extra else None,
-                 scaled_base=scaled_base if extra else None)
-      cur, cur_rows, cur_base = o, games * ROWS, None
+      self._conv(games, convs[2 * i + 1], t, RELU | RESIDUAL | extra, o, residual=cur,
+                 out_scaled=out_scaled if extra else None, pool_out=pool_out if extra else None,
+                 pool_base=pool_base if extra else None)
+      cur = o
     return cur
 
-  def run_recurrent(self, games, state, state_rows, state_base, actions, next_state, next_base, value,
-                    reward, logits):
-    """recurrent_inference (networks.py:31-34) for `games` (even) games on the current stream.
-      state      [state_rows][128] bf16, game g's padded block at row state_base[g] (None: g * 64)
+  def run_recurrent(self, games, state, actions, value, reward, logits, pool_out=None, pool_base=None):
+    """recurrent_inference (networks.py:31-34) for `games` games on the current stream.
+      state      [games * 49][128] bf16 (flat padded layout)
       actions    [games] int32 (device)
-      next_state [..][128] bf16, block of game g written at row next_base[g] (None: g * 64)
-      value, reward [games] f32, logits [games][A] f32 (device)"""
+      value, reward [games] f32, logits [games][A] f32 (device)
+      pool_out / pool_base: also write game g's scaled next state at rows pool_base[g].. of pool_out
+    Returns the flat scaled next state (a scratch buffer owned by the network)."""
     b = self.buffers(games)
-    X = b['x']
+    X, scaled = b['x'], b['scaled']
     P = _lib.ptr
     st = _lib.current_stream()
     # dynamics: conv(129 -> 128) + bn + relu, 16 blocks, scale_state; reward head on the unscaled state
-    self._conv(games, self.dyn_conv, state, state_rows, state_base, RELU | ACTION, X[0], actions=actions)
-    raw = self._tower(games, self.dyn_tower, X[0], games * ROWS, None, X, last_flags=SCALE,
-                      out_scaled=next_state, scaled_base=next_base)
+    self._conv(games, self.dyn_conv, state, RELU | ACTION, X[0], actions=actions)
+    raw = self._tower(games, self.dyn_tower, X[0], X, last_flags=SCALE, out_scaled=scaled,
+                      pool_out=pool_out, pool_base=pool_base)
     _lib.check(self.lib.mz_conv_fc_tc(games, P(raw), P(self.rew_fc1_w), P(self.rew_fc1_b), 512, 1,
                                       P(b['fc']), 1536, st), "mz_conv_fc_tc")
     _lib.check(self.lib.mz_conv_head(games, P(b['fc']), 1536, P(self.rew_fc2_w), P(self.rew_fc2_b),
                                      self.reward_bins, 1, self.reward_min, int(self.no_target_transform),
                                      P(reward), 1, st), "mz_conv_head")
     self.launches += 2
-    # prediction on the scaled state
-    rows = next_state.shape[0]
-    self.run_prediction(games, next_state, rows, next_base, value, logits)
+    self.run_prediction(games, scaled, value, logits)  # prediction on the scaled state
+    return scaled
 
-  def run_prediction(self, games, state, state_rows, state_base, value, logits):
-    """prediction (networks.py:465-480 + inverse value transform) from a padded bf16 state."""
+  def run_prediction(self, games, state, value, logits):
+    """prediction (networks.py:465-480 + inverse value transform) from a flat padded bf16 state."""
     b = self.buffers(games)
     P = _lib.ptr
     st = _lib.current_stream()
-    out = self._tower(games, self.pred_tower, state, state_rows, state_base, b['x'])
+    out = self._tower(games, self.pred_tower, state, b['x'])
     fc_vp = b['fc'][:, 512:]
     _lib.check(self.lib.mz_conv_fc_tc(games, P(out), P(self.vp_fc1_w), P(self.vp_fc1_b), 1024, 1,
                                       C_ptr(fc_vp), 1536, st), "mz_conv_fc_tc")
@@ -267,55 +275,43 @@ class MuZeroNetwork(object):
     mx = out.max(dim=1, keepdim=True)[0]
     return (out - mn) / (mx - mn)
 
-  def _even(self, b):
-    return b + (b & 1)
-
   def initial_inference(self, observation):
     """networks.py:26-29 (eval mode)."""
     with torch.inference_mode():
       hidden = self.representation(observation)
       b = hidden.shape[0]
-      g = self._even(b)
-      rows = torch.zeros((g * ROWS, CH), dtype=torch.bfloat16, device=self.device)
-      rows[:b * ROWS] = to_padded(hidden)
-      value = torch.zeros(g, dtype=torch.float32, device=self.device)
-      logits = torch.zeros((g, self.action_space), dtype=torch.float32, device=self.device)
-      self.run_prediction(g, rows, g * ROWS, None, value, logits)
-    return NetworkOutput(value[:b].reshape(b, 1), 0, logits[:b], hidden)
+      value = torch.zeros(b, dtype=torch.float32, device=self.device)
+      logits = torch.zeros((b, self.action_space), dtype=torch.float32, device=self.device)
+      self.run_prediction(b, to_padded(hidden), value, logits)
+    return NetworkOutput(value.reshape(b, 1), 0, logits, hidden)
 
   def recurrent_inference(self, hidden_state, action):
     """networks.py:31-34 (eval mode): hidden_state [B, 128, 6, 6], action: B ints (or an int32 CUDA
     tensor)."""
     with torch.inference_mode():
       b = hidden_state.shape[0]
-      g = self._even(b)
       dev = self.device
-      rows = torch.zeros((g * ROWS, CH), dtype=torch.bfloat16, device=dev)
-      rows[:b * ROWS] = to_padded(hidden_state.to(dev, torch.float32))
-      acts = torch.zeros(g, dtype=torch.int32, device=dev)
-      acts[:b] = torch.as_tensor(action, dtype=torch.int32).to(dev).reshape(-1)
-      nxt = torch.zeros((g * ROWS, CH), dtype=torch.bfloat16, device=dev)
-      value = torch.zeros(g, dtype=torch.float32, device=dev)
-      reward = torch.zeros(g, dtype=torch.float32, device=dev)
-      logits = torch.zeros((g, self.action_space), dtype=torch.float32, device=dev)
-      self.run_recurrent(g, rows, g * ROWS, None, acts, nxt, None, value, reward, logits)
-      hidden = from_padded(nxt[:b * ROWS], b)
-    return NetworkOutput(value[:b].reshape(b, 1), reward[:b].reshape(b, 1), logits[:b], hidden)
+      rows = to_padded(hidden_state.to(dev, torch.float32))
+      acts = torch.as_tensor(action, dtype=torch.int32).to(dev).reshape(-1).contiguous()
+      value = torch.zeros(b, dtype=torch.float32, device=dev)
+      reward = torch.zeros(b, dtype=torch.float32, device=dev)
+      logits = torch.zeros((b, self.action_space), dtype=torch.float32, device=dev)
+      nxt = self.run_recurrent(b, rows, acts, value, reward, logits)
+      hidden = from_padded(nxt, b)
+    return NetworkOutput(value.reshape(b, 1), reward.reshape(b, 1), logits, hidden)
 
 
 class ConvSearch(object):
   """The per-move body of Actor.play_game (actors.py:131-153) for G games with MuZeroNetwork.
 
-  Hidden states live in a bf16 pool [G][S+1][64 rows][128] (the padded layout the kernels read):
-  the first dynamics convolution gathers `search_path[-2].hidden_state` through per-game row offsets
-  and the last one writes the scaled next state into slot sim+1 -- no gather / scatter copies.  The
-  search part of a move (3 + 70 launches per simulation) is captured in one CUDA graph."""
+  Hidden states live in a bf16 pool [G][S+1][49 rows][128] (the padded layout the kernels read):
+  one copy kernel per simulation gathers `search_path[-2].hidden_state` into the flat activation
+  buffer and the last dynamics convolution writes the scaled next state straight into slot sim+1.
+  The search part of a move (72 launches per simulation) is captured in one CUDA graph."""
 
   def __init__(self, config, net, num_games, noise_frac=None, use_graph=True):
     from .mcts import BatchedMCTS
     G, A, dev = int(num_games), int(config.action_space), net.device
-    if G & 1:
-      raise ValueError("ConvSearch needs an even number of games (a kernel tile is two games)")
     self.net, self.G, self.A, self.S = net, G, A, int(config.num_simulations)
     self.noise_frac = float(getattr(config, 'root_exploration_fraction', 0.25)
                             if noise_frac is None else noise_frac)
@@ -325,7 +321,7 @@ class ConvSearch(object):
     slot0 = torch.arange(G, device=dev, dtype=torch.int64) * (S + 1)
     self.out_base = ((slot0[None, :] + torch.arange(1, S + 1, device=dev)[:, None]) * ROWS).to(torch.int32)
     self.root_base = (slot0 * ROWS).to(torch.int32)
-    self.in_base = torch.zeros(G, dtype=torch.int32, device=dev)
+    self.gathered = torch.zeros((G * ROWS, CH), dtype=torch.bfloat16, device=dev)
     self.noise = torch.zeros((G, A), dtype=torch.float64, device=dev)
     self.legal = torch.full((G,), (1 << A) - 1, dtype=torch.int64, device=dev).to(torch.int32)
     self.to_play = torch.ones(G, dtype=torch.int8, device=dev)
@@ -356,10 +352,9 @@ class ConvSearch(object):
     """initial_inference for every game: representation (torch operators, float32) -> pool slot 0,
     prediction on the tensor cores -> root logits / value."""
     with torch.inference_mode():
-      hidden = self.net.representation(observation)
-      self.pool.view(self.G, self.S + 1, ROWS, CH)[:, 0] = to_padded(hidden).view(self.G, ROWS, CH)
-      self.net.run_prediction(self.G, self.pool, self.pool.shape[0], self.root_base, self.init_value,
-                              self.root_logits)
+      rows = to_padded(self.net.representation(observation))
+      self.pool.view(self.G, self.S + 1, ROWS, CH)[:, 0] = rows.view(self.G, ROWS, CH)
+      self.net.run_prediction(self.G, rows, self.init_value, self.root_logits)
 
   def _enqueue(self):
     eng, net, lib, P = self.eng, self.net, self.net.lib, _lib.ptr
@@ -376,10 +371,10 @@ class ConvSearch(object):
         v, r, l = self.record[0][sim], self.record[1][sim], self.record[2][sim]
       else:
         v, r, l = self.value, self.reward, self.logits
-      _lib.check(lib.mz_conv_row_base(self.G, self.S + 1, P(eng.leaf_parent), P(self.in_base), st),
-                 "mz_conv_row_base")
-      net.run_recurrent(self.G, self.pool, self.pool.shape[0], self.in_base, eng.leaf_action, self.pool,
-                        self.out_base[sim], v, r, l)
+      _lib.check(lib.mz_conv_gather(self.G, self.S + 1, P(eng.leaf_parent), P(self.pool), P(self.gathered),
+                                    st), "mz_conv_gather")
+      net.run_recurrent(self.G, self.gathered, eng.leaf_action, v, r, l, pool_out=self.pool,
+                        pool_base=self.out_base[sim])
       _lib.check(lib.mz_tree_step(tree, sim, P(v), P(r), P(l), None, None, *eng._trace_ptrs(sim + 1), st),
                  "mz_tree_step")
     _lib.check(lib.mz_tree_root_stats(tree, P(eng.visits), P(eng.child_visits), P(eng.root_value),

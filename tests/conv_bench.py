@@ -22,10 +22,10 @@ def ev(fn, n=5):
   return a.elapsed_time(b) / n * 1e3
 bufs = net.buffers(G)["x"]
 conv = net.dyn_tower[0]
-t_conv = ev(lambda: net._conv(G, conv, x, G * ROWS, None, 1, bufs[0]), 20)
-t_res = ev(lambda: net._conv(G, conv, x, G * ROWS, None, 3, bufs[0], residual=x), 20)
-t_rec = ev(lambda: net.run_recurrent(G, x, G * ROWS, None, acts, nxt, None, v, r, l))
+t_conv = ev(lambda: net._conv(G, conv, x, 1, bufs[0]), 20)
+t_res = ev(lambda: net._conv(G, conv, x, 3, bufs[0], residual=x), 20)
+t_rec = ev(lambda: net.run_recurrent(G, x, acts, v, r, l))
 flops_conv = 2.0 * G * 36 * 128 * 1152
-flops_issued = 2.0 * G * 64 * 128 * 1152
+flops_issued = 2.0 * G * ROWS * 128 * 1152
 print("G=%d conv3x3: %.1f us (%.0f TFLOP/s useful, %.0f issued), with residual %.1f us" % (G, t_conv, flops_conv / t_conv / 1e6, flops_issued / t_conv / 1e6, t_res))
 print("recurrent_inference: %.1f us total = %.2f us/game ; useful %.0f TFLOP/s" % (t_rec, t_rec / G, G * 0.705e9 / t_rec / 1e6))

@@ -21,11 +21,11 @@ def _bf16(x):
   return x.to(torch.bfloat16).float()
 
 
-@pytest.mark.parametrize("games,flags", [(2, 1), (6, 3), (300, 3), (4, 1 | 4), (4, 1 | 2 | 8)])
+@pytest.mark.parametrize("games,flags", [(1, 1), (2, 1), (7, 3), (300, 3), (5, 1 | 4), (4, 1 | 2 | 8)])
 def test_conv_kernel_matches_conv2d(games, flags):
   """One launch of the implicit GEMM vs F.conv2d on the same bf16-rounded operands (float32 math):
   only the accumulation order differs -> 2e-2 absolute on O(1) outputs after bf16 rounding of the
-  result."""
+  result.  Game counts that do not fill a 128-row tile, tiles that straddle games."""
   from model_based_rl_b200 import _lib, muzero
   lib = _lib.load()
   torch.manual_seed(games * 8 + flags)
@@ -39,13 +39,13 @@ def test_conv_kernel_matches_conv2d(games, flags):
   res = torch.rand((games, 128, 6, 6), device=dev)
   res_rows = muzero.to_padded(res)
   actions = torch.randint(0, 18, (games,), device=dev, dtype=torch.int32)
-  out = torch.full((games * 64, 128), 7.0, dtype=torch.bfloat16, device=dev)
-  scaled = torch.full((games * 64, 128), 7.0, dtype=torch.bfloat16, device=dev)
+  out = torch.full((games * 49, 128), 7.0, dtype=torch.bfloat16, device=dev)
+  scaled = torch.full((games * 49, 128), 7.0, dtype=torch.bfloat16, device=dev)
   P = _lib.ptr
-  _lib.check(lib.mz_conv3x3_tc(games, P(rows), games * 64, None, P(conv.w), P(conv.bias), flags,
+  _lib.check(lib.mz_conv3x3_tc(games, P(rows), P(conv.w), P(conv.bias), flags,
                                P(conv.plane) if flags & 4 else None, P(actions), 18,
-                               P(res_rows) if flags & 2 else None, None, P(out),
-                               P(scaled) if flags & 8 else None, None, _lib.current_stream()), "conv")
+                               P(res_rows) if flags & 2 else None, P(out),
+                               P(scaled) if flags & 8 else None, None, None, _lib.current_stream()), "conv")
   torch.cuda.synchronize()
   xin = _bf16(x)
   wq = _bf16(conv.w.float().reshape(128, 3, 3, 128).permute(0, 3, 1, 2))
@@ -59,45 +59,49 @@ def test_conv_kernel_matches_conv2d(games, flags):
     want = F.relu(want)
   got = muzero.from_padded(out, games)
   assert torch.allclose(got, want, rtol=1e-2, atol=2e-2), float((got - want).abs().max())
-  border = out.reshape(games, 8, 8, 128).float()
-  assert float(border[:, 0].abs().max()) == 0 and float(border[:, 7].abs().max()) == 0
-  assert float(border[:, :, 0].abs().max()) == 0 and float(border[:, :, 7].abs().max()) == 0
+  assert float(muzero.padding_rows(out, games).float().abs().max()) == 0  # the padding stays zero
   if flags & 8:
     mn, mx = want.min(dim=1, keepdim=True)[0], want.max(dim=1, keepdim=True)[0]
     want_s = (want - mn) / (mx - mn)
     got_s = muzero.from_padded(scaled, games)
     assert torch.allclose(got_s, want_s, rtol=1e-2, atol=2e-2), float((got_s - want_s).abs().max())
+    assert float(muzero.padding_rows(scaled, games).float().abs().max()) == 0
 
 
-def test_gathered_rows_and_fc_heads():
-  """x_row_base / scaled_row_base indirection (hidden-pool gather and scatter) and the Linear heads."""
+def test_pool_gather_scatter_and_fc_heads():
+  """mz_conv_gather (hidden-pool gather), the pool scatter of the scaling epilogue, the Linear heads."""
   from model_based_rl_b200 import _lib, muzero
   lib = _lib.load()
   dev = "cuda"
   torch.manual_seed(5)
   games, slots = 6, 5
-  pool = torch.zeros((games * slots * 64, 128), dtype=torch.bfloat16, device=dev)
+  pool = torch.zeros((games * slots * 49, 128), dtype=torch.bfloat16, device=dev)
   x = torch.rand((games, 128, 6, 6), device=dev)
-  pick = torch.randint(0, slots, (games,), device=dev)
-  base = ((torch.arange(games, device=dev) * slots + pick) * 64).to(torch.int32)
-  rows = muzero.to_padded(x).reshape(games, 64, 128)
+  pick = torch.randint(0, slots, (games,), device=dev, dtype=torch.int32)
+  rows = muzero.to_padded(x).reshape(games, 49, 128)
+  pv = pool.view(games, slots, 49, 128)
   for g in range(games):
-    pool[int(base[g]):int(base[g]) + 64] = rows[g]
+    pv[g, int(pick[g])] = rows[g]
+  flat = torch.zeros((games * 49, 128), dtype=torch.bfloat16, device=dev)
+  P = _lib.ptr
+  _lib.check(lib.mz_conv_gather(games, slots, P(pick), P(pool), P(flat), _lib.current_stream()), "gather")
+  torch.cuda.synchronize()
+  assert torch.equal(flat, rows.reshape(-1, 128))
   w = (torch.rand((128, 128, 3, 3), device=dev) * 2 - 1) * 0.05
   conv = muzero._Conv(w, None, None, dev)
-  out = torch.zeros((games * 64, 128), dtype=torch.bfloat16, device=dev)
-  out_base = ((torch.arange(games, device=dev) * slots + (pick + 1) % slots) * 64).to(torch.int32)
-  P = _lib.ptr
-  _lib.check(lib.mz_conv3x3_tc(games, P(pool), pool.shape[0], P(base), P(conv.w), P(conv.bias), 1 | 2 | 8,
-                               None, None, 18, P(pool), P(base), P(out), P(pool), P(out_base),
-                               _lib.current_stream()), "conv")
+  out = torch.zeros((games * 49, 128), dtype=torch.bfloat16, device=dev)
+  scaled = torch.zeros_like(out)
+  dst = (pick + 1) % slots
+  out_base = ((torch.arange(games, device=dev) * slots + dst) * 49).to(torch.int32)
+  _lib.check(lib.mz_conv3x3_tc(games, P(flat), P(conv.w), P(conv.bias), 1 | 2 | 8, None, None, 18, P(flat),
+                               P(out), P(scaled), P(pool), P(out_base), _lib.current_stream()), "conv")
   torch.cuda.synchronize()
   want = F.relu(F.conv2d(_bf16(x), _bf16(w), None, 1, 1) + _bf16(x))
   assert torch.allclose(muzero.from_padded(out, games), want, rtol=1e-2, atol=2e-2)
   mn, mx = want.min(dim=1, keepdim=True)[0], want.max(dim=1, keepdim=True)[0]
-  got_s = torch.stack([pool[int(out_base[g]):int(out_base[g]) + 64] for g in range(games)])
-  assert torch.allclose(muzero.from_padded(got_s.reshape(-1, 128), games), (want - mn) / (mx - mn),
-                        rtol=1e-2, atol=2e-2)
+  assert torch.allclose(muzero.from_padded(scaled, games), (want - mn) / (mx - mn), rtol=1e-2, atol=2e-2)
+  got_pool = torch.stack([pv[g, int(dst[g])] for g in range(games)]).reshape(-1, 128)
+  assert torch.equal(got_pool, scaled)
   # heads: Linear(4608 -> 256) + ReLU over the padded rows, then Linear(512 -> 31) -> scalar
   fcw = (torch.rand((256, 4608), device=dev) * 2 - 1) * 0.02
   fcb = torch.randn(256, device=dev) * 0.1
@@ -105,8 +109,8 @@ def test_gathered_rows_and_fc_heads():
   _lib.check(lib.mz_conv_fc_tc(games, P(out), P(muzero._pack_fc(fcw, dev)), P(fcb), 256, 1, P(hid), 512,
                                _lib.current_stream()), "fc")
   torch.cuda.synchronize()
-  flat = _bf16(muzero.from_padded(out, games)).reshape(games, -1)
-  want_h = F.relu(F.linear(flat, _bf16(fcw), fcb))
+  flat_in = _bf16(muzero.from_padded(out, games)).reshape(games, -1)
+  want_h = F.relu(F.linear(flat_in, _bf16(fcw), fcb))
   assert torch.allclose(hid[:, :256], want_h, rtol=1e-2, atol=1e-2)
   w2 = torch.randn((31, 512), device=dev) * 0.05
   b2 = torch.randn(31, device=dev) * 0.1
@@ -165,7 +169,7 @@ def test_conv_search_replays_bit_exact_in_oracle():
   import oracle
   from oracle import muzero_ref
   from model_based_rl_b200.muzero import ConvSearch, MuZeroNetwork, from_padded
-  C_in, A, G, S = 4, 18, 8, 12
+  C_in, A, G, S = 4, 18, 7, 12
   sd = muzero_ref.seeded_state_dict(C_in, A, 99)
   net = MuZeroNetwork(C_in, A, "cuda", CFG)
   net.load_weights(sd)
@@ -201,13 +205,13 @@ def test_conv_search_replays_bit_exact_in_oracle():
   # support expectation, whose slope grows with |x| (about 6 at |v| = 12): 0.05 + 5 % of |v|;
   # logits 0.1, scaled states 0.05
   sdc = {k: v.cuda() for k, v in sd.items()}
-  pool = cs.pool.view(G, S + 1, 64, 128)
+  pool = cs.pool.view(G, S + 1, 49, 128)
   parents, acts = cs.trace[0].cpu().numpy()[:, 0], cs.trace[1].cpu().numpy()[:, 0]
   for sim in range(S):
-    h = from_padded(pool[0, int(parents[sim])].reshape(64, 128), 1)
+    h = from_padded(pool[0, int(parents[sim])].reshape(49, 128), 1)
     v, r, pol, h2 = muzero_ref.recurrent_inference(h, [int(acts[sim])], sdc, A)
     assert abs(float(v) - float(cs.record[0][sim, 0])) < 0.05 + 0.05 * abs(float(v))
     assert abs(float(r) - float(cs.record[1][sim, 0])) < 0.05 + 0.05 * abs(float(r))
     assert float((pol[0] - cs.record[2][sim, 0]).abs().max()) < 0.1
-    got_h = from_padded(pool[0, sim + 1].reshape(64, 128), 1)
+    got_h = from_padded(pool[0, sim + 1].reshape(49, 128), 1)
     assert float((got_h - h2).abs().max()) < 0.05
