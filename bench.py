@@ -54,7 +54,7 @@ def parse():
   p.add_argument("--precision", choices=["bf16", "f32"], default="bf16",
                  help="network kernel: bf16 tcgen05 tensor cores (default) or float32 CUDA cores")
   p.add_argument("--no-conv", action="store_true", help="skip the C5 MuZeroNetwork section")
-  p.add_argument("--conv-games", type=int, default=1024, help="C5: concurrent games per GPU")
+  p.add_argument("--conv-games", type=int, default=4096, help="C5: concurrent games per GPU")
   p.add_argument("--ref-moves-per-step", type=int, default=2,
                  help="reference arm: moves each worker plays per step")
   return p.parse_args()

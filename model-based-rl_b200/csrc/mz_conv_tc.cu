@@ -143,8 +143,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* acc_full = empty + STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);  // [num_tiles_n * 128] (<= 1024 floats)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.num_tiles_m * p.num_tiles_n;
+  for (int i = threadIdx.x; i < p.num_tiles_n * BN; i += CONV_THREADS) s_bias[i] = p.bias[i];
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -235,6 +237,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int acc = t & 1;
       const int tm = tile / p.num_tiles_n, tn = tile % p.num_tiles_n;
+      // residual rows are requested before waiting for the accumulator: they arrive while the MMAs
+      // of this tile are still running
+      uint4 resv[BN / 8];
+      if (!(p.flags & EPI_F32_OUT) && (p.flags & EPI_RESIDUAL)) {
+        const int Rp = tm * BM + r_in_tile;
+        const int gp = Rp / GROWS, posp = Rp - gp * GROWS;
+        const bool intp = posp >= 7 && ((posp - 7) % 7) < 6 && Rp < p.rows_total;
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)Rp * BN);
+#pragma unroll
+        for (int q = 0; q < BN / 8; ++q) resv[q] = intp ? rp[q] : make_uint4(0u, 0u, 0u, 0u);
+      }
       mbar_wait(&acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
       const uint32_t d = lane_addr + acc * BN;
@@ -250,10 +263,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 o;
-              o.x = __uint_as_float(v[j]) + p.bias[tn * BN + c0 + j];
-              o.y = __uint_as_float(v[j + 1]) + p.bias[tn * BN + c0 + j + 1];
-              o.z = __uint_as_float(v[j + 2]) + p.bias[tn * BN + c0 + j + 2];
-              o.w = __uint_as_float(v[j + 3]) + p.bias[tn * BN + c0 + j + 3];
+              o.x = __uint_as_float(v[j]) + s_bias[tn * BN + c0 + j];
+              o.y = __uint_as_float(v[j + 1]) + s_bias[tn * BN + c0 + j + 1];
+              o.z = __uint_as_float(v[j + 2]) + s_bias[tn * BN + c0 + j + 2];
+              o.w = __uint_as_float(v[j + 3]) + s_bias[tn * BN + c0 + j + 3];
               if (p.flags & EPI_RELU) {
                 o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f);
               }
@@ -274,7 +287,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           act_scale = (float)p.actions[g] / (float)p.num_actions;
           plane = p.plane_term + (py * 6 + px) * BN;
         }
-        const uint4* res = reinterpret_cast<const uint4*>(p.residual + row * BN);
         uint4* orow = reinterpret_cast<uint4*>(p.out + row * BN);
         const bool add_res = (p.flags & EPI_RESIDUAL) && interior && in_range;
         // x[0..32) = layer output for channels c0..c0+31 of this row (zero on the border)
@@ -283,7 +295,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           tmem_ld32(d + c0, v);
           tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + p.bias[c0 + j];
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
           if (plane) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = fmaf(act_scale, __ldg(plane + c0 + j), x[j]);
@@ -291,7 +303,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (add_res) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 rv = res[(c0 >> 3) + q];
+              const uint4 rv = resv[(c0 >> 3) + q];
               const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
               for (int h = 0; h < 4; ++h) {
@@ -311,7 +323,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         };
         float mn = INFINITY, mx = -INFINITY;
-#pragma unroll 1
+#pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
           float x[32];
           chunk(c0, x);
@@ -338,7 +350,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                           ? reinterpret_cast<uint4*>(p.pool_out + ((size_t)p.pool_row_base[g] + pos) * BN)
                           : nullptr;
           const float den = mx - mn;
-#pragma unroll 1
+#pragma unroll
           for (int c0 = 0; c0 < BN; c0 += 32) {
             float x[32];
             chunk(c0, x);
@@ -405,7 +417,8 @@ int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
   return r == CUDA_SUCCESS ? MZ_OK : 1000 + (int)r;
 }
 
-constexpr size_t kConvSmem = 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * sizeof(uint64_t) + 16;
+constexpr size_t kConvSmem = 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * sizeof(uint64_t) + 16 +
+                             1024 * sizeof(float);
 
 int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, void* stream) {
   static bool attr = false;
