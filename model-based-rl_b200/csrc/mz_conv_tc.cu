@@ -30,10 +30,14 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int GROWS = 49;                        // rows per game: 7 zero | 6 x (6 pixels + 1 zero)
-constexpr int STAGES = 6;
-constexpr int STAGE_BYTES = (BM + BN) * BK * 2;  // 32 KB
+// M tiles per work item (they share every weight-tile load).  Measured at 4096 games: TU = 2 with 4
+// stages 60.5 us per convolution vs TU = 1 with 6 stages 63.7 us, but 24.1 vs 21.9 us at 1024 games
+// (coarser work items) and no gain once the residual epilogue is on: kept at 1.
+constexpr int TU = 1;
+constexpr int STAGES = TU == 1 ? 6 : 4;
+constexpr int STAGE_BYTES = (TU * BM + BN) * BK * 2;  // 32 KB (48 KB with TU = 2)
 constexpr int CONV_THREADS = 192;                // producer, MMA, 4 epilogue warps
-constexpr int ACC_COLS = 256;                    // two accumulators of 128 fp32 columns
+constexpr int ACC_COLS = 2 * TU * BN;            // double-buffered accumulators of TU x 128 fp32 columns
 
 enum : int {
   EPI_RELU = 1,        // max(x, 0)
@@ -145,7 +149,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);  // [num_tiles_n * 128] (<= 1024 floats)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.num_tiles_m * p.num_tiles_n;
+  const int num_tiles = ((p.num_tiles_m + TU - 1) / TU) * p.num_tiles_n;  // work items
   for (int i = threadIdx.x; i < p.num_tiles_n * BN; i += CONV_THREADS) s_bias[i] = p.bias[i];
 
   if (threadIdx.x == 0) {
@@ -178,14 +182,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ===== TMA producer =====
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile / p.num_tiles_n, tn = tile % p.num_tiles_n;
-      const int rb0 = tm * BM, rb1 = rb0 + 64;
+      const int gm = tile / p.num_tiles_n, tn = tile % p.num_tiles_n;
+      const int rb0 = gm * TU * BM;
       for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
         const int st = it % STAGES;
         mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + st * STAGE_BYTES;
-          uint8_t* sb = sa + BM * BK * 2;
+          uint8_t* sb = sa + TU * BM * BK * 2;
           int shift = 0, ka = kb * BK;
           if (!p.mode_fc) {  // k block = (tap, channel half)
             const int tap = kb >> 1;
@@ -193,8 +197,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             ka = (kb & 1) * BK;
           }
           mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
-          tma_load_2d(sa, &map_a, ka, rb0 + shift, &full[st]);
-          tma_load_2d(sa + 64 * BK * 2, &map_a, ka, rb1 + shift, &full[st]);
+#pragma unroll
+          for (int h = 0; h < 2 * TU; ++h)  // rows beyond the tensor (odd tail, halo) arrive as zeros
+            tma_load_2d(sa + h * 64 * BK * 2, &map_a, ka, rb0 + h * 64 + shift, &full[st]);
           tma_load_2d(sb, &map_b, kb * BK, tn * BN, &full[st]);
           tma_load_2d(sb + 64 * BK * 2, &map_b, kb * BK, tn * BN + 64, &full[st]);
         }
@@ -209,19 +214,24 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int acc = t & 1;
       mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d = tmem + acc * BN;
+      const uint32_t d0 = tmem + acc * TU * BN;
       for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
         const int st = it % STAGES;
         mbar_wait(&full[st], (it / STAGES) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + st * STAGE_BYTES);
-        const uint64_t ad = make_desc_sw128(sa), bd = make_desc_sw128(sa + BM * BK * 2);
+        const uint64_t bd = make_desc_sw128(sa + TU * BM * BK * 2);
         if (elect_one()) {
-          if (kb == 0) umma_ss<false>(d, ad, bd, idesc);
-          else umma_ss<true>(d, ad, bd, idesc);
 #pragma unroll
-          for (int ks = 1; ks < BK / 16; ++ks)  // +32 bytes along K inside the 128-byte swizzle row
-            umma_ss<true>(d, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc);
+          for (int u = 0; u < TU; ++u) {  // both M tiles against the same weight tile
+            const uint32_t d = d0 + u * BN;
+            const uint64_t ad = make_desc_sw128(sa + u * BM * BK * 2);
+            if (kb == 0) umma_ss<false>(d, ad, bd, idesc);
+            else umma_ss<true>(d, ad, bd, idesc);
+#pragma unroll
+            for (int ks = 1; ks < BK / 16; ++ks)  // +32 bytes along K inside the 128-byte swizzle row
+              umma_ss<true>(d, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc);
+          }
           tc_commit(&empty[st]);
           if (kb == p.num_kblocks - 1) tc_commit(&acc_full[acc]);
         }
@@ -236,9 +246,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     int t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int acc = t & 1;
-      const int tm = tile / p.num_tiles_n, tn = tile % p.num_tiles_n;
+      const int gm = tile / p.num_tiles_n, tn = tile % p.num_tiles_n;
+#pragma unroll 1
+      for (int u = 0; u < TU; ++u) {
+      const int tm = gm * TU + u;
       // residual rows are requested before waiting for the accumulator: they arrive while the MMAs
-      // of this tile are still running
+      // of this work item are still running (second tile: while the first is being written out)
       uint4 resv[BN / 8];
       if (!(p.flags & EPI_F32_OUT) && (p.flags & EPI_RESIDUAL)) {
         const int Rp = tm * BM + r_in_tile;
@@ -248,9 +261,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
         for (int q = 0; q < BN / 8; ++q) resv[q] = intp ? rp[q] : make_uint4(0u, 0u, 0u, 0u);
       }
-      mbar_wait(&acc_full[acc], (t >> 1) & 1);
-      tc_fence_after();
-      const uint32_t d = lane_addr + acc * BN;
+      if (u == 0) {
+        mbar_wait(&acc_full[acc], (t >> 1) & 1);
+        tc_fence_after();
+      }
+      const uint32_t d = lane_addr + (acc * TU + u) * BN;
       if (p.flags & EPI_F32_OUT) {
         const int row = tm * BM + r_in_tile;
         float* orow = p.out_f32 + (size_t)row * p.ldo + tn * BN;
@@ -368,6 +383,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         }
       }
+      }  // u
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
     }
@@ -432,7 +448,7 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     attr = true;
   }
-  const int tiles = p.num_tiles_m * p.num_tiles_n;
+  const int tiles = ((p.num_tiles_m + TU - 1) / TU) * p.num_tiles_n;
   const int grid = tiles < sms ? tiles : sms;
   cudaError_t e = mz_launch(conv_gemm_tc_kernel, dim3(grid), dim3(CONV_THREADS), kConvSmem,
                             (cudaStream_t)stream, true, ma, mb, p);
