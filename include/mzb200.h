@@ -343,13 +343,15 @@ int mz_sumtree_sample(const double* tree, int64_t max_capacity, int32_t n, const
 #define MZ_CONV_RESIDUAL 2  /* += residual before the ReLU            ResidualBlock.forward networks.py:384-391 */
 #define MZ_CONV_ACTION 4    /* += actions[g] / A * plane_term[pixel]  MuZeroNetwork.attach_action networks.py:536-541 */
 #define MZ_CONV_SCALE 8     /* also emit (x - min_c) / (max_c - min_c) MuZeroNetwork.scale_state networks.py:543-547 */
-/* Conv2d(128 -> 128, 3x3, padding 1) with BatchNorm2d (eval) folded into w_packed / bias.
- *   x, residual, out, out_scaled [games*49][128] bf16 (out may be NULL with MZ_CONV_SCALE)
+/* Conv2d(128 -> 128, 3x3, padding 1) with BatchNorm2d (eval) folded into w_packed / bias, on
+ * width x width images (6 for the hidden state; 12 / 24 inside the representation tower) in the same
+ * flat padded layout with (width + 1)^2 rows per game.
+ *   x, residual, out, out_scaled [games*(width+1)^2][128] bf16 (out may be NULL with MZ_CONV_SCALE)
  *   w_packed   [128][9*128] bf16, k = (ky*3 + kx)*128 + c_in;   bias [128] f32
  *   plane_term [36][128] f32, actions [games] i32 (flags & MZ_CONV_ACTION)
  *   pool_out, pool_row_base [games]: with MZ_CONV_SCALE the scaled rows of game g are also written
  *   to rows pool_row_base[g] .. +49 of pool_out (the hidden-pool slot of the node being expanded). */
-int mz_conv3x3_tc(int32_t games, const void* x, const void* w_packed, const float* bias, int32_t flags,
+int mz_conv3x3_tc(int32_t games, int32_t width, const void* x, const void* w_packed, const float* bias, int32_t flags,
                   const float* plane_term, const int32_t* actions, int32_t num_actions,
                   const void* residual, void* out, void* out_scaled, void* pool_out,
                   const int32_t* pool_row_base, void* stream);

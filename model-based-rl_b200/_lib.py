@@ -100,7 +100,8 @@ _SIGNATURES = {
                                  _V, _V]),
     "mz_sumtree_sample": (C.c_int, [_V, C.c_int64, C.c_int32, _V, _V, _V, _V, C.c_int64, C.c_double,
                                     _V, _V, _V, _V, _V, _V, _V]),
-    "mz_conv3x3_tc": (C.c_int, [C.c_int32, _V, _V, _V, C.c_int32, _V, _V, C.c_int32, _V, _V, _V, _V, _V, _V]),
+    "mz_conv3x3_tc": (C.c_int, [C.c_int32, C.c_int32, _V, _V, _V, C.c_int32, _V, _V, C.c_int32, _V, _V, _V, _V,
+                                _V, _V]),
     "mz_conv_gather": (C.c_int, [C.c_int32, C.c_int32, _V, _V, _V, _V]),
     "mz_conv_fc_tc": (C.c_int, [C.c_int32, _V, _V, _V, C.c_int32, C.c_int32, _V, C.c_int32, _V]),
     "mz_conv_head": (C.c_int, [C.c_int32, _V, C.c_int32, _V, _V, C.c_int32, C.c_int32, C.c_int32,

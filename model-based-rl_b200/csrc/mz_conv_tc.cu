@@ -53,6 +53,7 @@ struct ConvParams {
   int rows_total;            // conv: games * 64; fc: games
   int flags;
   int num_actions;
+  int wp, grows;             // conv: padded row width (W + 1) and rows per game (wp * wp)
   const float* bias;         // [N_total]
   const float* plane_term;   // [36][128] (EPI_ACTION)
   const int32_t* actions;    // [games]   (EPI_ACTION)
@@ -193,7 +194,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           int shift = 0, ka = kb * BK;
           if (!p.mode_fc) {  // k block = (tap, channel half)
             const int tap = kb >> 1;
-            shift = (tap / 3 - 1) * 7 + (tap % 3 - 1);
+            shift = (tap / 3 - 1) * p.wp + (tap % 3 - 1);
             ka = (kb & 1) * BK;
           }
           mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
@@ -255,8 +256,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint4 resv[BN / 8];
       if (!(p.flags & EPI_F32_OUT) && (p.flags & EPI_RESIDUAL)) {
         const int Rp = tm * BM + r_in_tile;
-        const int gp = Rp / GROWS, posp = Rp - gp * GROWS;
-        const bool intp = posp >= 7 && ((posp - 7) % 7) < 6 && Rp < p.rows_total;
+        const int gp = Rp / p.grows, posp = Rp - gp * p.grows;
+        const bool intp = posp >= p.wp && ((posp - p.wp) % p.wp) < p.wp - 1 && Rp < p.rows_total;
         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)Rp * BN);
 #pragma unroll
         for (int q = 0; q < BN / 8; ++q) resv[q] = intp ? rp[q] : make_uint4(0u, 0u, 0u, 0u);
@@ -291,16 +292,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
       } else {
         const int R = tm * BM + r_in_tile;  // flat row
-        const int g = R / GROWS, pos = R - g * GROWS;
-        const int py = (pos - 7) / 7, px = (pos - 7) - py * 7;
-        const bool interior = pos >= 7 && px < 6;
+        const int g = R / p.grows, pos = R - g * p.grows;
+        const int py = (pos - p.wp) / p.wp, px = (pos - p.wp) - py * p.wp;
+        const bool interior = pos >= p.wp && px < p.wp - 1;
         const size_t row = (size_t)R;
         const bool in_range = R < p.rows_total;
         float act_scale = 0.0f;
         const float* plane = nullptr;
         if ((p.flags & EPI_ACTION) && interior && in_range) {
           act_scale = (float)p.actions[g] / (float)p.num_actions;
-          plane = p.plane_term + (py * 6 + px) * BN;
+          plane = p.plane_term + (py * (p.wp - 1) + px) * BN;
         }
         uint4* orow = reinterpret_cast<uint4*>(p.out + row * BN);
         const bool add_res = (p.flags & EPI_RESIDUAL) && interior && in_range;
@@ -531,25 +532,27 @@ int mz_conv_gather(int32_t games, int32_t nodes_per_game, const int32_t* node, c
 }
 
 // 3x3 convolution (+ folded BatchNorm, bias, optional action plane / residual / ReLU / state scaling)
-// over `games` hidden states in the flat padded channels-last bf16 layout (49 rows x 128 channels per
-// game).
-//   x, residual, out, out_scaled   [games * 49][128] bf16
+// over `games` images of width x width pixels in the flat padded channels-last bf16 layout
+// ((width + 1)^2 rows x 128 channels per game: a zero row, then `width` image rows of `width`
+// pixels + 1 zero; 49 rows for the 6 x 6 hidden state).
+//   x, residual, out, out_scaled   [games * (width + 1)^2][128] bf16
 //   w_packed     [128][9 * 128] bf16, k = (ky * 3 + kx) * 128 + c_in
 //   bias         [128] f32;  plane_term [36][128] f32 and actions [games] when flags & 4
 //   pool_out + pool_row_base: with flags & 8 the scaled rows of game g are also written at rows
 //   pool_row_base[g] .. + 49 of pool_out (the hidden pool slot of the new node)
-int mz_conv3x3_tc(int32_t games, const void* x, const void* w_packed, const float* bias, int32_t flags,
+int mz_conv3x3_tc(int32_t games, int32_t width, const void* x, const void* w_packed, const float* bias, int32_t flags,
                   const float* plane_term, const int32_t* actions, int32_t num_actions,
                   const void* residual, void* out, void* out_scaled, void* pool_out,
                   const int32_t* pool_row_base, void* stream) {
-  if (games < 1 || !x || !w_packed || !bias) return MZ_ERR_BAD_ARG;
+  if (games < 1 || width < 1 || width > 255 || !x || !w_packed || !bias) return MZ_ERR_BAD_ARG;
   if ((flags & EPI_ACTION) && (!plane_term || !actions || num_actions < 1)) return MZ_ERR_BAD_ARG;
   if ((flags & EPI_RESIDUAL) && !residual) return MZ_ERR_BAD_ARG;
   if ((flags & EPI_SCALE) && !out_scaled) return MZ_ERR_BAD_ARG;
   if (!(flags & EPI_SCALE) && !out) return MZ_ERR_BAD_ARG;
   if (pool_out && !pool_row_base) return MZ_ERR_BAD_ARG;
   if (flags & EPI_F32_OUT) return MZ_ERR_BAD_ARG;
-  const long long rows = (long long)games * GROWS;
+  const int wp = width + 1, grows = wp * wp;
+  const long long rows = (long long)games * grows;
   if (rows > 0x7fffffffLL - 2 * BM) return MZ_ERR_UNSUPPORTED;
   CUtensorMap ma, mb;
   int rc = make_map(&ma, x, (uint64_t)rows, 128);
@@ -564,6 +567,8 @@ int mz_conv3x3_tc(int32_t games, const void* x, const void* w_packed, const floa
   p.rows_total = (int)rows;
   p.flags = flags;
   p.num_actions = num_actions;
+  p.wp = wp;
+  p.grows = grows;
   p.bias = bias;
   p.plane_term = plane_term;
   p.actions = actions;

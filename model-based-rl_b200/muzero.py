@@ -10,9 +10,10 @@ implicit-GEMM kernel in csrc/mz_conv_tc.cu on bf16 activations in a flat padded 
 hidden-state pool of the search holds states in the same layout, is gathered by one small copy
 kernel per simulation and written in place by the last dynamics convolution.
 
-Round-1 limitation, stated in DESIGN.md: the representation tower (`initial_inference`, once per
-move, 96x96 inputs with strided convolutions and pooling) runs through torch operators in float32;
-its output enters the tensor-core path at the prediction tower.
+Representation tower (`initial_inference`, once per move): the 128-channel stages -- 3 + 3 + 16
+residual blocks at 24 x 24, 12 x 12 and 6 x 6 pixels, 44 of its 50 convolutions -- run on the same
+kernel; the stem (two strided convolutions, the two 64-channel blocks at 48 x 48) and the two
+average pools are torch operators in float32 (round-1 limitation, stated in DESIGN.md).
 """
 import torch
 import torch.nn.functional as F
@@ -28,23 +29,23 @@ BN_EPS = 1e-5
 
 
 def to_padded(state):
-  """[B, 128, 6, 6] float -> [B * 49, 128] bf16 rows (shared zero padding, channels last)."""
-  b = state.shape[0]
-  x = F.pad(state.permute(0, 2, 3, 1), (0, 0, 0, 1))         # [B, 6, 7, C]: zero after each image row
-  x = F.pad(x.reshape(b, 42, CH), (0, 0, 7, 0))               # [B, 49, C]: zero row of 7 in front
-  return x.reshape(b * ROWS, CH).to(torch.bfloat16).contiguous()
+  """[B, 128, W, W] float -> [B * (W + 1)^2, 128] bf16 rows: channels last, one zero row on top and one
+  zero pixel after every image row (the zero padding neighbouring games share)."""
+  b, w = state.shape[0], state.shape[-1]
+  x = F.pad(state.permute(0, 2, 3, 1), (0, 0, 0, 1, 1, 0))    # [B, W + 1, W + 1, C]
+  return x.reshape(b * (w + 1) * (w + 1), CH).to(torch.bfloat16).contiguous()
 
 
-def from_padded(rows, b):
-  """[B * 49, 128] bf16 rows -> [B, 128, 6, 6] float32."""
-  x = rows.reshape(b, ROWS, CH)[:, 7:].reshape(b, 6, 7, CH)[:, :, :6, :]
+def from_padded(rows, b, width=6):
+  """[B * (W + 1)^2, 128] bf16 rows -> [B, 128, W, W] float32."""
+  x = rows.reshape(b, width + 1, width + 1, CH)[:, 1:, :width, :]
   return x.permute(0, 3, 1, 2).float().contiguous()
 
 
-def padding_rows(rows, b):
-  """The 13 padding rows of every game (must stay zero)."""
-  x = rows.reshape(b, ROWS, CH)
-  return torch.cat((x[:, :7], x[:, 7:].reshape(b, 6, 7, CH)[:, :, 6]), dim=1)
+def padding_rows(rows, b, width=6):
+  """The padding rows of every game (must stay zero)."""
+  x = rows.reshape(b, width + 1, width + 1, CH)
+  return torch.cat((x[:, 0], x[:, 1:, width]), dim=1)
 
 
 class _Conv(object):
@@ -123,6 +124,22 @@ class MuZeroNetwork(object):
         convs.append(_Conv(sd[b + '.conv2.weight'], None, bn(b + '.bn2'), dev))
       return convs
 
+    # representation tower: the 128-channel stages (3 + 3 + 16 blocks at 24 / 12 / 6 pixels) run on the
+    # tensor-core kernel; the stem (strided convolutions, the 64-channel blocks) and the two average
+    # pools stay torch operators
+    r = 'representation_head'
+
+    def blocks(p, n):
+      convs = []
+      for i in range(n):
+        b = '%s.%d' % (p, i)
+        convs.append(_Conv(sd[b + '.conv1.weight'], None, bn(b + '.bn1'), dev))
+        convs.append(_Conv(sd[b + '.conv2.weight'], None, bn(b + '.bn2'), dev))
+      return convs
+
+    self.rep_blocks2 = blocks(r + '.resblocks2', 3)
+    self.rep_blocks3 = blocks(r + '.resblocks3', 3)
+    self.rep_tower = blocks(r + '.resblocks', 16)
     d, q = 'dynamics_head', 'prediction_head'
     if sd[d + '.conv.weight'].shape != (CH, CH + 1, 3, 3):
       raise ValueError("dynamics_head.conv.weight has shape %s" % (tuple(sd[d + '.conv.weight'].shape),))
@@ -166,39 +183,43 @@ class MuZeroNetwork(object):
     return self
 
   # -- buffers ---------------------------------------------------------------------------------------
-  def buffers(self, games):
-    """Scratch activations for `games` games: three flat padded bf16 buffers (+ one for the scaled
-    state) and the head hidden layer [games][reward 512 | value 512 | policy 512] float32."""
-    b = self._bufs.get(games)
+  def buffers(self, games, width=6):
+    """Scratch activations for `games` games of width x width pixels: three flat padded bf16 buffers
+    (+ one for the scaled state) and the head hidden layer [games][reward 512 | value 512 | policy
+    512] float32."""
+    b = self._bufs.get((games, width))
     if b is None:
       dev = self.device
-      b = dict(x=[torch.zeros((games * ROWS, CH), dtype=torch.bfloat16, device=dev) for _ in range(3)],
-               scaled=torch.zeros((games * ROWS, CH), dtype=torch.bfloat16, device=dev),
-               fc=torch.zeros((games, 1536), dtype=torch.float32, device=dev))
-      self._bufs[games] = b
+      rows = games * (width + 1) * (width + 1)
+      b = dict(x=[torch.zeros((rows, CH), dtype=torch.bfloat16, device=dev) for _ in range(3)])
+      if width == 6:
+        b['scaled'] = torch.zeros((rows, CH), dtype=torch.bfloat16, device=dev)
+        b['fc'] = torch.zeros((games, 1536), dtype=torch.float32, device=dev)
+      self._bufs[(games, width)] = b
     return b
 
   # -- launches --------------------------------------------------------------------------------------
   def _conv(self, games, conv, x, flags, out, residual=None, actions=None, out_scaled=None, pool_out=None,
-            pool_base=None):
+            pool_base=None, width=6):
     P = _lib.ptr
-    _lib.check(self.lib.mz_conv3x3_tc(games, P(x), P(conv.w), P(conv.bias), flags,
+    _lib.check(self.lib.mz_conv3x3_tc(games, width, P(x), P(conv.w), P(conv.bias), flags,
                                       P(conv.plane) if flags & ACTION else None, P(actions),
                                       self.action_space, P(residual), P(out), P(out_scaled), P(pool_out),
                                       P(pool_base), _lib.current_stream()), "mz_conv3x3_tc")
     self.launches += 1
 
-  def _tower(self, games, convs, x, bufs, last_flags=0, out_scaled=None, pool_out=None, pool_base=None):
-    """16 ResidualBlocks (networks.py:372-391) starting from the flat tensor `x`.  Returns the scratch
-    buffer holding the (unscaled) output."""
-    cur = x
-    for i in range(16):
+  def _tower(self, games, convs, x, bufs, last_flags=0, out_scaled=None, pool_out=None, pool_base=None,
+             width=6):
+    """len(convs) / 2 ResidualBlocks (networks.py:372-391) starting from the flat tensor `x`.  Returns
+    the scratch buffer holding the (unscaled) output."""
+    cur, n = x, len(convs) // 2
+    for i in range(n):
       t, o = [b for b in bufs if b.data_ptr() != cur.data_ptr()][:2]
-      self._conv(games, convs[2 * i], cur, RELU, t)
-      extra = last_flags if i == 15 else 0
+      self._conv(games, convs[2 * i], cur, RELU, t, width=width)
+      extra = last_flags if i == n - 1 else 0
       self._conv(games, convs[2 * i + 1], t, RELU | RESIDUAL | extra, o, residual=cur,
                  out_scaled=out_scaled if extra else None, pool_out=pool_out if extra else None,
-                 pool_base=pool_base if extra else None)
+                 pool_base=pool_base if extra else None, width=width)
       cur = o
     return cur
 
@@ -244,10 +265,12 @@ class MuZeroNetwork(object):
     self.launches += 3
 
   # -- reference interface ---------------------------------------------------------------------------
-  def representation(self, observation):
-    """MuZeroRepresentation + scale_state (networks.py:412-426, 500-503); torch operators, float32."""
+  def representation_rows(self, observation):
+    """MuZeroRepresentation + scale_state (networks.py:412-426, 500-503) -> the scaled 6 x 6 state in
+    the flat padded bf16 layout (a scratch buffer owned by the network)."""
     sd = self._state
     obs = torch.as_tensor(observation).to(self.device, torch.float32)
+    g = obs.shape[0]
     p = 'representation_head.'
 
     def bn(x, q):
@@ -259,31 +282,35 @@ class MuZeroNetwork(object):
       out = bn(F.conv2d(out, sd[q + '.conv2.weight'], None, 1, 1), q + '.bn2')
       return F.relu(out + x)
 
+    # stem: torch operators, float32
     out = F.conv2d(obs, sd[p + 'conv1.weight'], sd[p + 'conv1.bias'], 2, 1)
     for i in range(2):
       out = block(out, p + 'resblocks1.%d' % i)
     out = F.conv2d(out, sd[p + 'conv2.weight'], sd[p + 'conv2.bias'], 2, 1)
-    for i in range(3):
-      out = block(out, p + 'resblocks2.%d' % i)
-    out = F.avg_pool2d(out, 3, 2, 1)
-    for i in range(3):
-      out = block(out, p + 'resblocks3.%d' % i)
-    out = F.avg_pool2d(out, 3, 2, 1)
-    for i in range(16):
-      out = block(out, p + 'resblocks.%d' % i)
-    mn = out.min(dim=1, keepdim=True)[0]
-    mx = out.max(dim=1, keepdim=True)[0]
-    return (out - mn) / (mx - mn)
+    # 128-channel stages: tensor-core kernel, bf16 activations; pooling in between stays torch
+    for convs in (self.rep_blocks2, self.rep_blocks3):
+      w = out.shape[-1]
+      rows = self._tower(g, convs, to_padded(out), self.buffers(g, w)['x'], width=w)
+      out = F.avg_pool2d(from_padded(rows, g, w), 3, 2, 1)
+    b = self.buffers(g)
+    self._tower(g, self.rep_tower, to_padded(out), b['x'], last_flags=SCALE, out_scaled=b['scaled'])
+    return b['scaled']
+
+  def representation(self, observation):
+    """networks.py:500-503: [B, C, 96, 96] -> scaled hidden state [B, 128, 6, 6] float32."""
+    with torch.inference_mode():
+      rows = self.representation_rows(observation)
+      return from_padded(rows, rows.shape[0] // ROWS)
 
   def initial_inference(self, observation):
     """networks.py:26-29 (eval mode)."""
     with torch.inference_mode():
-      hidden = self.representation(observation)
-      b = hidden.shape[0]
+      rows = self.representation_rows(observation).clone()  # the scratch buffer is reused below
+      b = rows.shape[0] // ROWS
       value = torch.zeros(b, dtype=torch.float32, device=self.device)
       logits = torch.zeros((b, self.action_space), dtype=torch.float32, device=self.device)
-      self.run_prediction(b, to_padded(hidden), value, logits)
-    return NetworkOutput(value.reshape(b, 1), 0, logits, hidden)
+      self.run_prediction(b, rows, value, logits)
+    return NetworkOutput(value.reshape(b, 1), 0, logits, from_padded(rows, b))
 
   def recurrent_inference(self, hidden_state, action):
     """networks.py:31-34 (eval mode): hidden_state [B, 128, 6, 6], action: B ints (or an int32 CUDA
@@ -352,9 +379,14 @@ class ConvSearch(object):
     """initial_inference for every game: representation (torch operators, float32) -> pool slot 0,
     prediction on the tensor cores -> root logits / value."""
     with torch.inference_mode():
-      rows = to_padded(self.net.representation(observation))
+      rows = self.net.representation_rows(observation)
       self.pool.view(self.G, self.S + 1, ROWS, CH)[:, 0] = rows.view(self.G, ROWS, CH)
-      self.net.run_prediction(self.G, rows, self.init_value, self.root_logits)
+      self.net.run_prediction(self.G, self.pool_root(), self.init_value, self.root_logits)
+
+  def pool_root(self):
+    """Flat copy of the roots' states (slot 0 of every game)."""
+    self.gathered.view(self.G, ROWS, CH).copy_(self.pool.view(self.G, self.S + 1, ROWS, CH)[:, 0])
+    return self.gathered
 
   def _enqueue(self):
     eng, net, lib, P = self.eng, self.net, self.net.lib, _lib.ptr

@@ -42,7 +42,7 @@ def test_conv_kernel_matches_conv2d(games, flags):
   out = torch.full((games * 49, 128), 7.0, dtype=torch.bfloat16, device=dev)
   scaled = torch.full((games * 49, 128), 7.0, dtype=torch.bfloat16, device=dev)
   P = _lib.ptr
-  _lib.check(lib.mz_conv3x3_tc(games, P(rows), P(conv.w), P(conv.bias), flags,
+  _lib.check(lib.mz_conv3x3_tc(games, 6, P(rows), P(conv.w), P(conv.bias), flags,
                                P(conv.plane) if flags & 4 else None, P(actions), 18,
                                P(res_rows) if flags & 2 else None, P(out),
                                P(scaled) if flags & 8 else None, None, None, _lib.current_stream()), "conv")
@@ -66,6 +66,28 @@ def test_conv_kernel_matches_conv2d(games, flags):
     got_s = muzero.from_padded(scaled, games)
     assert torch.allclose(got_s, want_s, rtol=1e-2, atol=2e-2), float((got_s - want_s).abs().max())
     assert float(muzero.padding_rows(scaled, games).float().abs().max()) == 0
+
+
+@pytest.mark.parametrize("width,games", [(12, 3), (24, 2)])
+def test_conv_kernel_other_widths(width, games):
+  """The same kernel on the 12 x 12 and 24 x 24 stages of the representation tower."""
+  from model_based_rl_b200 import _lib, muzero
+  lib = _lib.load()
+  torch.manual_seed(width)
+  dev = "cuda"
+  x = torch.rand((games, 128, width, width), device=dev)
+  w = (torch.rand((128, 128, 3, 3), device=dev) * 2 - 1) * (3.0 / 1152) ** 0.5
+  conv = muzero._Conv(w, torch.randn(128, device=dev) * 0.1, None, dev)
+  rows = muzero.to_padded(x)
+  out = torch.full_like(rows, 7.0)
+  P = _lib.ptr
+  _lib.check(lib.mz_conv3x3_tc(games, width, P(rows), P(conv.w), P(conv.bias), 1 | 2, None, None, 18, P(rows),
+                               P(out), None, None, None, _lib.current_stream()), "conv")
+  torch.cuda.synchronize()
+  want = F.relu(F.conv2d(_bf16(x), _bf16(w), None, 1, 1) + conv.bias[None, :, None, None] + _bf16(x))
+  got = muzero.from_padded(out, games, width)
+  assert torch.allclose(got, want, rtol=1e-2, atol=2e-2), float((got - want).abs().max())
+  assert float(muzero.padding_rows(out, games, width).float().abs().max()) == 0
 
 
 def test_pool_gather_scatter_and_fc_heads():
@@ -93,7 +115,7 @@ def test_pool_gather_scatter_and_fc_heads():
   scaled = torch.zeros_like(out)
   dst = (pick + 1) % slots
   out_base = ((torch.arange(games, device=dev) * slots + dst) * 49).to(torch.int32)
-  _lib.check(lib.mz_conv3x3_tc(games, P(flat), P(conv.w), P(conv.bias), 1 | 2 | 8, None, None, 18, P(flat),
+  _lib.check(lib.mz_conv3x3_tc(games, 6, P(flat), P(conv.w), P(conv.bias), 1 | 2 | 8, None, None, 18, P(flat),
                                P(out), P(scaled), P(pool), P(out_base), _lib.current_stream()), "conv")
   torch.cuda.synchronize()
   want = F.relu(F.conv2d(_bf16(x), _bf16(w), None, 1, 1) + _bf16(x))
@@ -133,8 +155,10 @@ def test_network_matches_reference_golden():
   net = MuZeroNetwork(C_in, A, "cuda", CFG)
   net.load_weights(muzero_ref.seeded_state_dict(C_in, A, int(g["seed"])))
   init = net.initial_inference(torch.from_numpy(g["obs"]))
-  # representation runs in float32 (torch operators): tight
-  assert np.allclose(init.hidden_state.cpu().numpy(), g["init_hidden"], rtol=1e-3, atol=1e-3)
+  # representation: float32 stem, then 22 residual blocks in bf16 on the tensor cores
+  err = np.abs(init.hidden_state.cpu().numpy() - g["init_hidden"])
+  print("init_hidden", float(err.max()), float(err.mean()))
+  assert err.max() < 0.06 and err.mean() < 0.01
   rec = net.recurrent_inference(torch.from_numpy(g["init_hidden"]).cuda(), g["actions"].tolist())
   rec2 = net.recurrent_inference(torch.from_numpy(g["rec_hidden"]).cuda(), g["actions2"].tolist())
   torch.cuda.synchronize()
