@@ -231,6 +231,11 @@ int mz_fc_recurrent_tc(const mz_fc_weights* w, const void* packed, const float* 
                        const int32_t* actions, float* hidden_out, int64_t out_row_stride,
                        int64_t out_offset, float* value, float* reward, float* logits, void* stream);
 
+/* 1 (default): mz_fc_recurrent_tc runs as clusters of two CTAs per 128 rows -- rank 0 evaluates the
+ * reward and value heads, rank 1 the transition and policy heads, h' crosses through distributed
+ * shared memory; 0: one CTA evaluates all four heads. */
+int mz_fc_tc_set_split(int32_t enable);
+
 /* BaseNetwork.initial_inference (networks.py:26-29) on the same tensor-core kernel: representation
  * head (obs [B][obs_dim] f32, K = obs_dim + bias column) -> LayerNorm + ReLU -> prediction heads.
  * Its own packed image / tail (mz_fc_tc_initial_packed_bytes, mz_fc_tc_pack_initial);

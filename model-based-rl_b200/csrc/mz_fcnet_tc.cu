@@ -188,6 +188,43 @@ MZ_DEV uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
+// ---- thread-block cluster helpers (distributed shared memory hand-off of h') --------------------
+MZ_DEV uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+MZ_DEV void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+MZ_DEV uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {  // same offset in the peer CTA's shared memory
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+MZ_DEV void st_cluster_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+MZ_DEV void mbar_arrive_remote(uint32_t cluster_addr) {  // release at cluster scope
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+MZ_DEV void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
 struct TcParams {
   const uint8_t* chunks;  // packed weights
   const float* tail;
@@ -207,6 +244,10 @@ struct TcParams {
   int stages;        // weight-ring depth actually used (<= MAX_STAGES)
   const float* obs;  // [batch][obs_dim] (initial mode)
   int obs_dim;
+  // split != 0: the kernel runs as clusters of two CTAs per 128 rows; rank 0 evaluates the reward and
+  // value heads, rank 1 the transition and policy heads (8 chunks each instead of 16) and hands h'
+  // to rank 0 through distributed shared memory
+  int split;
 };
 
 // trace slots: [0,64) epilogue thread (row 0), [64,192) MMA thread, [192,224) producer
@@ -283,6 +324,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   }
   const int k1 = p.k1;
   const int stage_bytes = stage_bytes_for(k1);
+  const bool split = p.split != 0;
+  const int rank = split ? (int)cluster_ctarank() : 0;
+  const int tile = split ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // which 128 rows
   // epilogue threads request their row's gather index / action before the set-up barrier
   int pre_idx = 0, pre_act = 0;
   if (warp >= 2 && warp < MMA2_WARP) {
@@ -290,7 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     // read by the epilogue warps, after this point; weights, barriers and TMEM do not depend on it
     pdl_wait();
     pdl_trigger();
-    const int g0 = blockIdx.x * ROWS + (warp & 3) * 32 + lane;
+    const int g0 = tile * ROWS + (warp & 3) * 32 + lane;
     const int gc0 = g0 < p.batch ? g0 : p.batch - 1;
     if (!p.obs) {
       pre_idx = p.in_index ? p.in_index[gc0] : 0;
@@ -300,8 +344,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   // carve shared memory
   uint8_t* sA1 = smem;                                  // [128 x k1] bf16 (A of the dynamics layer)
   uint8_t* sW = sA1 + ROWS * k1 * 2;                    // STAGES x stage_bytes
-  const int STAGES = p.stages, c0 = p.chunk0, nch = NCHUNK - c0;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + STAGES * stage_bytes);
+  const int STAGES = p.stages, c0 = p.chunk0;
+  const int nch = split ? NCHUNK / 2 : NCHUNK - c0;  // chunks this CTA runs
+  const int c_mid = split ? 4 : 8 - c0;               // first chunk of the prediction phase
+  // running chunk index -> canonical chunk id (head = id >> 2: reward, transition, value, policy)
+  auto canon = [&](int c) { return split ? (c < 4 ? 4 * rank + c : 8 + 4 * rank + (c - 4)) : c + c0; };
+  const bool own_reward = !split || rank == 0, own_hidden = !split || rank == 1;
+  const bool own_value = own_reward, own_logits = own_hidden;
+  uint8_t* sA3 = sW + STAGES * stage_bytes;             // [128 x 64] bf16: h' (A of the prediction layer)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA3 + ROWS * K3 * 2);
   uint64_t* w_full = bars;            // [STAGES]
   uint64_t* w_empty = bars + 4;       // [STAGES]
   uint64_t* d1_full = bars + 8;       // [2]
@@ -312,10 +363,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   uint64_t* a3_ready = bars + 17;
   uint64_t* d2_full = bars + 18;
   uint64_t* h_staged = bars + 19;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
-  float* sTail = reinterpret_cast<float*>(bars + 21);   // second-layer biases + LayerNorm affine
+  uint64_t* a3_remote = bars + 20;    // rank 0 of a split pair: h' rows have arrived from rank 1
+  uint64_t* h_stored = bars + 21;     // the store warp is done with sOut (the logits reuse it)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
+  float* sTail = reinterpret_cast<float*>(bars + 23);   // second-layer biases + LayerNorm affine
   float* sOut = sTail + TAIL_FLOATS;                    // [128][51]: row-major staging of h'
-  float* sLog = sOut + ROWS * OUT_STRIDE;               // [128][A]: row-major staging of the logits
+  float* sLog = sOut;                                   // [128][A]: the logits reuse it at the very end
   for (int i = threadIdx.x; i < TAIL_FLOATS; i += TC_THREADS) sTail[i] = p.tail[i];
 
   if (threadIdx.x == 0) {
@@ -330,6 +383,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     mbar_init(a3_ready, EPI_THREADS / 2);
     mbar_init(d2_full, 1);
     mbar_init(h_staged, EPI_THREADS / 2);
+    mbar_init(a3_remote, EPI_THREADS / 2);
+    mbar_init(h_stored, 1);
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -339,21 +394,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (split) cluster_sync_all();  // the peer's barriers exist before anything is sent to them
   const uint32_t tmem = *tmem_ptr;
   if (threadIdx.x == 32) TC_STAMP(0);
 
   if (warp == 0) {
     // ===== producer: stream the 16 weight chunks through the ring =====
     if (lane == 0) {
-      size_t off = 0;
+      const size_t base = chunk_offset(c0, k1);
       for (int c = 0; c < nch; ++c) {
         const int st = c % STAGES, n = c / STAGES;
-        const ChunkGeom g = chunk_geom(c + c0, k1);
+        const int cc = canon(c);
+        const ChunkGeom g = chunk_geom(cc, k1);
         mbar_wait(&w_empty[st], (n & 1) ^ 1);
         TC_STAMP(192 + c);
         mbar_arrive_expect_tx(&w_full[st], (uint32_t)g.bytes);
-        bulk_copy_g2s(sW + st * stage_bytes, p.chunks + off, (uint32_t)g.bytes, &w_full[st]);
-        off += g.bytes;
+        bulk_copy_g2s(sW + st * stage_bytes, p.chunks + (chunk_offset(cc, k1) - base), (uint32_t)g.bytes,
+                      &w_full[st]);
       }
     }
   } else if (warp == 1) {
@@ -365,11 +422,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     constexpr uint64_t KSTEP = (uint64_t)((2 * (CHUNK / 8) * 128) >> 4);  // two K core-matrix columns
 #pragma unroll 1
     for (int c = 0; c < nch; ++c) {
-      const int st = c % STAGES, cc = c + c0;
+      const int st = c % STAGES, cc = canon(c);
       if (lane == 0) TC_STAMP(64 + 8 * c + 0);
       mbar_wait(&w_full[st], (c / STAGES) & 1);
       if (c == 0) mbar_wait(a1_ready, 0);
-      if (cc == 8) mbar_wait(a3_ready, 0);
+      if (c == c_mid) mbar_wait(a3_ready, 0);
       mbar_wait(&d1_empty[c & 1], ((c >> 1) & 1) ^ 1);
       tc_fence_after();
       if (lane == 0) TC_STAMP(64 + 8 * c + 1);
@@ -381,11 +438,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
           umma_ss<false>(d1, ad, bd, idesc1);
 #pragma unroll 1
           for (int ks = 1; ks < k1 / 16; ++ks) umma_ss<true>(d1, ad + ks * KSTEP, bd + ks * KSTEP, idesc1);
-        } else {      // prediction: A = [h' | 1] from tensor memory, K = 64
-          umma_ts<false>(d1, tmem + COL_A3, bd, idesc1);
+        } else {      // prediction: A = [h' | 1] from shared memory (written locally or by the peer CTA), K = 64
+          const uint64_t ad = make_desc(smem_u32(sA3), (ROWS / 8) * 128, 128);
+          umma_ss<false>(d1, ad, bd, idesc1);
 #pragma unroll
-          for (int ks = 1; ks < K3 / 16; ++ks)
-            umma_ts<true>(d1, tmem + COL_A3 + ks * 8, bd + ks * KSTEP, idesc1);
+          for (int ks = 1; ks < K3 / 16; ++ks) umma_ss<true>(d1, ad + ks * KSTEP, bd + ks * KSTEP, idesc1);
         }
         tc_commit(&d1_full[c & 1]);
       }
@@ -399,7 +456,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     const uint32_t w1_bytes_dyn = CHUNK * k1 * 2, w1_bytes_pred = CHUNK * K3 * 2;
 #pragma unroll 1
     for (int c = 0; c < nch; ++c) {
-      const int st = c % STAGES, cc = c + c0, head = cc >> 2;
+      const int st = c % STAGES, cc = canon(c), head = cc >> 2;
       mbar_wait(&a2_full[c & 1], (c >> 1) & 1);
       tc_fence_after();
       if (lane == 0) TC_STAMP(64 + 8 * c + 4);
@@ -410,7 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
         else issue_mma2<32>(tmem + ((head & 1) ? COL_D2B : COL_D2A), a_tm, b_addr, (cc & 3) == 0);
         tc_commit(&w_empty[st]);       // chunk c's weights are no longer needed
         tc_commit(&a2_empty[c & 1]);   // A2 buffer may be overwritten
-        if (cc == 7 || cc == 15) tc_commit(d2_full);
+        if (c == c_mid - 1 || c == nch - 1) tc_commit(d2_full);
       }
       __syncwarp();
       if (lane == 0) TC_STAMP(64 + 8 * c + 6);
@@ -418,13 +475,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   } else if (warp == STORE_WARP) {
     // ===== h' rows: shared-memory staging area -> hidden pool, one contiguous 200-byte row per
     // pair of store instructions (a per-thread row store would touch 32 lines per instruction) =====
+    if (own_hidden) {
     mbar_wait(h_staged, 0);
-    const int rows_here = min(ROWS, p.batch - blockIdx.x * ROWS);
+    const int rows_here = min(ROWS, p.batch - tile * ROWS);
 #pragma unroll 4
     for (int r = 0; r < rows_here; ++r) {
-      float* dst = p.hidden_out + (size_t)(blockIdx.x * ROWS + r) * p.out_row_stride + p.out_offset;
+      float* dst = p.hidden_out + (size_t)(tile * ROWS + r) * p.out_row_stride + p.out_offset;
       dst[lane] = sOut[r * OUT_STRIDE + lane];
       if (lane < H - 32) dst[32 + lane] = sOut[r * OUT_STRIDE + 32 + lane];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(h_stored);
     }
   } else {
     // ===== epilogue warps: two groups of four warps; within a group one thread per row.
@@ -433,7 +494,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2;              // 0 or 1
     const int row = quarter * 32 + lane;
-    const int g = blockIdx.x * ROWS + row;
+    const int g = tile * ROWS + row;
     const bool live = g < p.batch;
     const int gc = live ? g : p.batch - 1;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
@@ -446,7 +507,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
 #pragma unroll 4
       for (int i = 0; i < 16; ++i) {
         const int r = r0 + i;
-        const int gr = min(blockIdx.x * ROWS + r, p.batch - 1);
+        const int gr = min(tile * ROWS + r, p.batch - 1);
         const float* orow = p.obs + (size_t)gr * p.obs_dim;
         for (int k = lane; k < k1; k += 32) {
           const float x = k < p.obs_dim ? __ldg(orow + k) : (k == p.obs_dim ? 1.0f : 0.0f);
@@ -525,20 +586,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       if (stamp) TC_STAMP(5 + 2 * c);
     };
 
-    for (int c = 0; c < 8 - c0; ++c) hidden_epilogue(c);
+    for (int c = 0; c < c_mid; ++c) hidden_epilogue(c);
 
     // --- dynamics outputs: group 1 -> reward scalar, group 0 -> h' = relu(LN(.)) -> pool + A3 ---
     mbar_wait(d2_full, 0);
     tc_fence_after();
     if (stamp) TC_STAMP(40);
     if (grp == 1) {
-      if (c0 == 0) {  // initial_inference has no reward (networks.py:29 returns 0)
+      if (c0 == 0 && own_reward) {  // initial_inference has no reward (networks.py:29 returns 0)
         tmem_ld32(lane_addr + COL_D2A, v);
         tmem_wait_ld();
         const float rew = support_to_scalar_regs(v, sTail + T_REW_B, p.reward_bins, p.reward_min, p.no_tt);
         if (live) p.reward[g] = rew;
       }
-    } else {
+    } else if (own_hidden) {
       float hbuf[64];
       tmem_ld32(lane_addr + COL_D2B, v);
       tmem_ld32(lane_addr + COL_D2B + 32, v2);
@@ -569,44 +630,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
         hbuf[j] = j < H ? fmaxf((hbuf[j] - mean) * rstd * sTail[T_LN_W + j] + sTail[T_LN_B + j], 0.0f)
                         : (j == H ? 1.0f : 0.0f);  // column H feeds the folded first-layer bias
       {
-        uint32_t pk[32];
+        // h' as the bf16 A operand of the prediction layer: this row of the canonical K-major image,
+        // in this CTA's shared memory and -- in a split pair -- in the peer's as well
+        const uint32_t a3 = smem_u32(sA3);
+        const uint32_t a3_peer = split ? map_to_cta(a3, 0) : 0u;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pk[j] = pack_bf16(hbuf[2 * j], hbuf[2 * j + 1]);
-        tmem_st32(lane_addr + COL_A3, pk);
-        tmem_wait_st();
+        for (int kb = 0; kb < K3 / 8; ++kb) {
+          const uint4 q = make_uint4(pack_bf16(hbuf[8 * kb], hbuf[8 * kb + 1]), pack_bf16(hbuf[8 * kb + 2], hbuf[8 * kb + 3]),
+                                     pack_bf16(hbuf[8 * kb + 4], hbuf[8 * kb + 5]), pack_bf16(hbuf[8 * kb + 6], hbuf[8 * kb + 7]));
+          const uint32_t off = (uint32_t)canon_off(row, 8 * kb, ROWS);
+          *reinterpret_cast<uint4*>(sA3 + off) = q;
+          if (split) st_cluster_v4(a3_peer + off, q);
+        }
       }
-      tc_fence_before();
+      fence_async_smem();
       mbar_arrive(a3_ready);
+      if (split) mbar_arrive_remote(map_to_cta(smem_u32(a3_remote), 0));
       if (stamp) TC_STAMP(41);
       // after the hand-off: h' goes to the pool through shared memory so that every store
       // instruction writes one contiguous 200-byte row (a per-thread row store touches 32 lines)
 #pragma unroll
       for (int j = 0; j < H; ++j) sOut[row * OUT_STRIDE + j] = hbuf[j];
       mbar_arrive(h_staged);  // the store warp takes it from here
+    } else {
+      // rank 0 of a split pair: wait for the peer's rows (cluster-scope acquire), make them visible
+      // to the tensor-core (async) proxy, release the local layer-1 issuer
+      mbar_wait_cluster(a3_remote, 0);
+      fence_async_smem();
+      mbar_arrive(a3_ready);
     }
 
-    for (int c = 8 - c0; c < nch; ++c) hidden_epilogue(c);
+    for (int c = c_mid; c < nch; ++c) hidden_epilogue(c);
 
     // --- prediction outputs: group 0 -> value scalar, group 1 -> policy logits ---
     mbar_wait(d2_full, 1);
     tc_fence_after();
     if (stamp) TC_STAMP(42);
     if (grp == 0) {
-      tmem_ld32(lane_addr + COL_D2A, v);
-      tmem_wait_ld();
-      const float val = support_to_scalar_regs(v, sTail + T_VAL_B, p.value_bins, p.value_min, p.no_tt);
-      if (live) p.value[g] = val;
-    } else {
+      if (own_value) {
+        tmem_ld32(lane_addr + COL_D2A, v);
+        tmem_wait_ld();
+        const float val = support_to_scalar_regs(v, sTail + T_VAL_B, p.value_bins, p.value_min, p.no_tt);
+        if (live) p.value[g] = val;
+      }
+    } else if (own_logits) {
       tmem_ld32(lane_addr + COL_D2B, v);
       tmem_wait_ld();
       // logits [rows][A] of this CTA are one contiguous block: stage row-major, store linearly
       const int A = p.num_actions;
+      mbar_wait(h_stored, 0);  // the staging area is free again
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j < A) sLog[row * A + j] = __uint_as_float(v[j]) + sTail[T_POL_B + j];
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four warps of this group
-      const int rows_here = min(ROWS, p.batch - blockIdx.x * ROWS);
-      float* dl = p.logits + (size_t)blockIdx.x * ROWS * A;
+      const int rows_here = min(ROWS, p.batch - tile * ROWS);
+      float* dl = p.logits + (size_t)tile * ROWS * A;
       for (int i = row; i < rows_here * A; i += ROWS) dl[i] = sLog[i];
     }
     tc_fence_before();
@@ -672,12 +750,14 @@ __global__ void fc_tc_pack_kernel(mz_fc_weights w, int k1, int chunk0, uint8_t* 
 int k1_for(int A) { return (H + A + 1 + 15) / 16 * 16; }  // state + one-hot + bias column
 
 long long* g_tc_trace = nullptr;
+int g_tc_split = 1;  // recurrent kernel: two-CTA clusters, heads split between the CTAs
 
 int k1_obs(int obs_dim) { return (obs_dim + 1 + 15) / 16 * 16; }  // observation + bias column
 
 size_t tc_smem_bytes(int k1, int stages) {
   return (size_t)ROWS * k1 * 2 + (size_t)stages * stage_bytes_for(k1) +
-         21 * sizeof(uint64_t) + TAIL_FLOATS * sizeof(float) + ROWS * (OUT_STRIDE + 32) * sizeof(float);
+         (size_t)ROWS * K3 * 2 + 23 * sizeof(uint64_t) + TAIL_FLOATS * sizeof(float) +
+         ROWS * OUT_STRIDE * sizeof(float);
 }
 
 constexpr size_t kTcMaxSmem = 232448;
@@ -692,9 +772,29 @@ int launch_tc(const TcParams& p, void* stream) {
     attr = true;
   }
   if (smem > kTcMaxSmem) return MZ_ERR_UNSUPPORTED;
-  const int grid = (p.batch + ROWS - 1) / ROWS;
-  cudaError_t e = mz_launch(fc_recurrent_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream,
-                            p.obs == nullptr, p);
+  const int tiles = (p.batch + ROWS - 1) / ROWS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.split ? 2 * tiles : tiles);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute lattr[2];
+  int na = 0;
+  if (p.split) {
+    lattr[na].id = cudaLaunchAttributeClusterDimension;
+    lattr[na].val.clusterDim.x = 2;
+    lattr[na].val.clusterDim.y = 1;
+    lattr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (p.obs == nullptr && g_mz_pdl) {
+    lattr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    lattr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = lattr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fc_recurrent_tc_kernel, p);
   if (e != cudaSuccess) return (int)e;
   MZ_LAUNCH_CHECK();
   return MZ_OK;
@@ -703,6 +803,11 @@ int launch_tc(const TcParams& p, void* stream) {
 }  // namespace
 
 extern "C" {
+
+int mz_fc_tc_set_split(int32_t enable) {
+  g_tc_split = enable ? 1 : 0;
+  return MZ_OK;
+}
 
 int mz_debug_set_tc_trace(int64_t* device_buffer) {
   g_tc_trace = (long long*)device_buffer;
@@ -761,6 +866,7 @@ int mz_fc_recurrent_tc(const mz_fc_weights* w, const void* packed, const float* 
   p.stages = MAX_STAGES;
   p.obs = nullptr;
   p.obs_dim = 0;
+  p.split = g_tc_split;
   return launch_tc(p, stream);
 }
 
@@ -813,6 +919,7 @@ int mz_fc_initial_tc(const mz_fc_weights* w, const void* packed, const float* ta
   p.stages = 2;
   p.obs = obs;
   p.obs_dim = w->obs_dim;
+  p.split = 0;
   return launch_tc(p, stream);
 }
 
