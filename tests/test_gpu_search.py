@@ -144,6 +144,12 @@ def _run_engine_vs_oracle(G, A, S, two_players, seed, fused, **kw):
     (65, 32, 20, False, True, {}),
     (33, 1, 10, False, True, {}),
     (129, 6, 64, True, True, {}),
+    # warp-per-game kernel (17..32 actions): one game, two players + known bounds + legal subsets,
+    # long searches (paths deeper than one 32-lane chunk, non-staged fallback for big trees)
+    (1, 18, 50, False, True, {}),
+    (200, 20, 100, True, True, dict(known_bounds=(-1.0, 1.0), legal_subsets=True)),
+    (37, 17, 200, False, True, {}),
+    (3, 32, 700, True, True, {}),
 ])
 def test_search_matches_oracle_seeded(G, A, S, two, fused, kw):
   res, want = _run_engine_vs_oracle(G, A, S, two, 1234 + A, fused, **kw)
