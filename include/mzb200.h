@@ -348,7 +348,8 @@ int mz_sumtree_sample(const double* tree, int64_t max_capacity, int32_t n, const
 #define MZ_CONV_RESIDUAL 2  /* += residual before the ReLU            ResidualBlock.forward networks.py:384-391 */
 #define MZ_CONV_ACTION 4    /* += actions[g] / A * plane_term[pixel]  MuZeroNetwork.attach_action networks.py:536-541 */
 #define MZ_CONV_SCALE 8     /* also emit (x - min_c) / (max_c - min_c) MuZeroNetwork.scale_state networks.py:543-547 */
-/* Conv2d(128 -> 128, 3x3, padding 1) with BatchNorm2d (eval) folded into w_packed / bias, on
+/* Conv2d(C -> C, 3x3, padding 1), C = channels = 128 (or 64: resblocks1 of the representation,
+ * rows of 64 channels, w_packed [64][9*64]) with BatchNorm2d (eval) folded into w_packed / bias, on
  * width x width images (6 for the hidden state; 12 / 24 inside the representation tower) in the same
  * flat padded layout with (width + 1)^2 rows per game.
  *   x, residual, out, out_scaled [games*(width+1)^2][128] bf16 (out may be NULL with MZ_CONV_SCALE)
@@ -356,10 +357,20 @@ int mz_sumtree_sample(const double* tree, int64_t max_capacity, int32_t n, const
  *   plane_term [36][128] f32, actions [games] i32 (flags & MZ_CONV_ACTION)
  *   pool_out, pool_row_base [games]: with MZ_CONV_SCALE the scaled rows of game g are also written
  *   to rows pool_row_base[g] .. +49 of pool_out (the hidden-pool slot of the node being expanded). */
-int mz_conv3x3_tc(int32_t games, int32_t width, const void* x, const void* w_packed, const float* bias, int32_t flags,
+int mz_conv3x3_tc(int32_t games, int32_t width, int32_t channels, const void* x, const void* w_packed,
+                  const float* bias, int32_t flags,
                   const float* plane_term, const int32_t* actions, int32_t num_actions,
                   const void* residual, void* out, void* out_scaled, void* pool_out,
                   const int32_t* pool_row_base, void* stream);
+/* Strided convolutions of MuZeroRepresentation (conv1, conv2: networks.py:399, 402) = im2col of the
+ * stride-2 patches + GEMM whose output rows land in the padded layout; AvgPool2d(3, 2, 1)
+ * (networks.py:406, 409) between padded layouts.  Padding rows of the outputs are never written:
+ * zero the buffers once. */
+int mz_conv_im2col_s2(int32_t games, int32_t w_in, int32_t channels, int32_t k_pad, const void* in, void* out,
+                      void* stream);
+int mz_conv_gemm_to_padded(int32_t games, int32_t out_w, int32_t k, int32_t n_out, const void* a, const void* w,
+                           const float* bias, int32_t relu, void* out, void* stream);
+int mz_conv_avgpool(int32_t games, int32_t w_in, int32_t channels, const void* in, void* out, void* stream);
 /* out rows [g*49, g*49+49) = pool slot [g][node[g]] of a pool laid out [G][nodes_per_game][49][128]
  * bf16: the gather of search_path[-2].hidden_state (mcts.py:94-96) into the flat layout. */
 int mz_conv_gather(int32_t games, int32_t nodes_per_game, const int32_t* node, const void* pool, void* out,

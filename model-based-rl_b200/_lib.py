@@ -101,8 +101,12 @@ _SIGNATURES = {
                                  _V, _V]),
     "mz_sumtree_sample": (C.c_int, [_V, C.c_int64, C.c_int32, _V, _V, _V, _V, C.c_int64, C.c_double,
                                     _V, _V, _V, _V, _V, _V, _V]),
-    "mz_conv3x3_tc": (C.c_int, [C.c_int32, C.c_int32, _V, _V, _V, C.c_int32, _V, _V, C.c_int32, _V, _V, _V, _V,
-                                _V, _V]),
+    "mz_conv3x3_tc": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _V, _V, _V, C.c_int32, _V, _V, C.c_int32, _V,
+                                _V, _V, _V, _V, _V]),
+    "mz_conv_im2col_s2": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _V, _V, _V]),
+    "mz_conv_gemm_to_padded": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _V, _V, _V, C.c_int32, _V,
+                                         _V]),
+    "mz_conv_avgpool": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _V, _V, _V]),
     "mz_conv_gather": (C.c_int, [C.c_int32, C.c_int32, _V, _V, _V, _V]),
     "mz_conv_fc_tc": (C.c_int, [C.c_int32, _V, _V, _V, C.c_int32, C.c_int32, _V, C.c_int32, _V]),
     "mz_conv_head": (C.c_int, [C.c_int32, _V, C.c_int32, _V, _V, C.c_int32, C.c_int32, C.c_int32,

@@ -45,6 +45,7 @@ enum : int {
   EPI_ACTION = 4,      // += action[g] / A * plane_term[pixel][n]   (MuZeroNetwork.attach_action)
   EPI_SCALE = 8,       // also emit (x - min_c) / (max_c - min_c) per pixel (scale_state)
   EPI_F32_OUT = 16,    // heads: fp32 row-major output [M][ldo], no border masking
+  EPI_TO_PADDED = 32,  // plain GEMM whose row r = (game, y, x): bf16 rows scattered into the padded layout
 };
 
 struct ConvParams {
@@ -54,6 +55,9 @@ struct ConvParams {
   int flags;
   int num_actions;
   int wp, grows;             // conv: padded row width (W + 1) and rows per game (wp * wp)
+  int ncols;                 // output channels per tile = channels per activation row: 64 or 128
+  int kb_per_tap;            // conv: K blocks of 64 input channels per tap (1 or 2)
+  int out_w;                 // EPI_TO_PADDED: GEMM row r = (game, y, x) of an out_w x out_w image
   const float* bias;         // [N_total]
   const float* plane_term;   // [36][128] (EPI_ACTION)
   const int32_t* actions;    // [games]   (EPI_ACTION)
@@ -129,9 +133,9 @@ MZ_DEV uint64_t make_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
   return d;
 }
-// D = f32, A = B = bf16, both K-major, M = 128, N = 128
-MZ_DEV uint32_t make_idesc_128x128() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// D = f32, A = B = bf16, both K-major, M = 128, N = n
+MZ_DEV uint32_t make_idesc_128xN(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 MZ_DEV uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
@@ -151,7 +155,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);  // [num_tiles_n * 128] (<= 1024 floats)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = ((p.num_tiles_m + TU - 1) / TU) * p.num_tiles_n;  // work items
-  for (int i = threadIdx.x; i < p.num_tiles_n * BN; i += CONV_THREADS) s_bias[i] = p.bias[i];
+  const int NC = p.ncols;
+  for (int i = threadIdx.x; i < p.num_tiles_n * NC; i += CONV_THREADS) s_bias[i] = p.bias[i];
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -192,24 +197,24 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           uint8_t* sa = smem + st * STAGE_BYTES;
           uint8_t* sb = sa + TU * BM * BK * 2;
           int shift = 0, ka = kb * BK;
-          if (!p.mode_fc) {  // k block = (tap, channel half)
-            const int tap = kb >> 1;
+          if (!p.mode_fc) {  // k block = (tap, block of 64 input channels)
+            const int tap = kb / p.kb_per_tap;
             shift = (tap / 3 - 1) * p.wp + (tap % 3 - 1);
-            ka = (kb & 1) * BK;
+            ka = (kb - tap * p.kb_per_tap) * BK;
           }
-          mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+          mbar_arrive_expect_tx(&full[st], (uint32_t)((TU * BM + NC) * BK * 2));
 #pragma unroll
           for (int h = 0; h < 2 * TU; ++h)  // rows beyond the tensor (odd tail, halo) arrive as zeros
             tma_load_2d(sa + h * 64 * BK * 2, &map_a, ka, rb0 + h * 64 + shift, &full[st]);
-          tma_load_2d(sb, &map_b, kb * BK, tn * BN, &full[st]);
-          tma_load_2d(sb + 64 * BK * 2, &map_b, kb * BK, tn * BN + 64, &full[st]);
+          tma_load_2d(sb, &map_b, kb * BK, tn * NC, &full[st]);
+          if (NC > 64) tma_load_2d(sb + 64 * BK * 2, &map_b, kb * BK, tn * NC + 64, &full[st]);
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = make_idesc_128x128();
+    const uint32_t idesc = make_idesc_128xN(p.ncols);
     int it = 0, t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int acc = t & 1;
@@ -258,35 +263,47 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int Rp = tm * BM + r_in_tile;
         const int gp = Rp / p.grows, posp = Rp - gp * p.grows;
         const bool intp = posp >= p.wp && ((posp - p.wp) % p.wp) < p.wp - 1 && Rp < p.rows_total;
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)Rp * BN);
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)Rp * NC);
 #pragma unroll
-        for (int q = 0; q < BN / 8; ++q) resv[q] = intp ? rp[q] : make_uint4(0u, 0u, 0u, 0u);
+        for (int q = 0; q < BN / 8; ++q) resv[q] = (intp && q * 8 < NC) ? rp[q] : make_uint4(0u, 0u, 0u, 0u);
       }
       if (u == 0) {
         mbar_wait(&acc_full[acc], (t >> 1) & 1);
         tc_fence_after();
       }
       const uint32_t d = lane_addr + (acc * TU + u) * BN;
-      if (p.flags & EPI_F32_OUT) {
+      if (p.flags & (EPI_F32_OUT | EPI_TO_PADDED)) {
         const int row = tm * BM + r_in_tile;
-        float* orow = p.out_f32 + (size_t)row * p.ldo + tn * BN;
+        const bool ok = row < p.rows_total;
+        float* orow = p.out_f32 + (size_t)row * p.ldo + tn * NC;
+        __nv_bfloat16* prow = nullptr;
+        if ((p.flags & EPI_TO_PADDED) && ok) {  // GEMM row = (game, y, x) -> row of the padded layout
+          const int ww = p.out_w * p.out_w, wpo = p.out_w + 1;
+          const int gg = row / ww, rem = row - gg * ww, yy = rem / p.out_w, xx = rem - yy * p.out_w;
+          prow = p.out + ((size_t)gg * wpo * wpo + wpo + yy * wpo + xx) * NC;
+        }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < NC; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(d + c0, v);
           tmem_wait_ld();
-          if (row < p.rows_total) {
+          if (ok) {
+            float x[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o;
-              o.x = __uint_as_float(v[j]) + s_bias[tn * BN + c0 + j];
-              o.y = __uint_as_float(v[j + 1]) + s_bias[tn * BN + c0 + j + 1];
-              o.z = __uint_as_float(v[j + 2]) + s_bias[tn * BN + c0 + j + 2];
-              o.w = __uint_as_float(v[j + 3]) + s_bias[tn * BN + c0 + j + 3];
-              if (p.flags & EPI_RELU) {
-                o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f);
-              }
-              *reinterpret_cast<float4*>(orow + c0 + j) = o;
+            for (int j = 0; j < 32; ++j) {
+              x[j] = __uint_as_float(v[j]) + s_bias[tn * NC + c0 + j];
+              if (p.flags & EPI_RELU) x[j] = fmaxf(x[j], 0.0f);
+            }
+            if (prow) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                reinterpret_cast<uint4*>(prow + c0)[q] =
+                    make_uint4(pack_bf16(x[q * 8], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                               pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
             }
           }
         }
@@ -301,9 +318,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const float* plane = nullptr;
         if ((p.flags & EPI_ACTION) && interior && in_range) {
           act_scale = (float)p.actions[g] / (float)p.num_actions;
-          plane = p.plane_term + (py * (p.wp - 1) + px) * BN;
+          plane = p.plane_term + (py * (p.wp - 1) + px) * NC;
         }
-        uint4* orow = reinterpret_cast<uint4*>(p.out + row * BN);
+        uint4* orow = reinterpret_cast<uint4*>(p.out + row * NC);
         const bool add_res = (p.flags & EPI_RESIDUAL) && interior && in_range;
         // x[0..32) = layer output for channels c0..c0+31 of this row (zero on the border)
         auto chunk = [&](int c0, float (&x)[32]) {
@@ -341,6 +358,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         float mn = INFINITY, mx = -INFINITY;
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (c0 >= NC) break;
           float x[32];
           chunk(c0, x);
           if (p.flags & EPI_SCALE) {
@@ -361,13 +379,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           // MuZeroNetwork.scale_state networks.py:543-547: second pass over the accumulator row.
           // tcgen05.ld is warp-collective: every lane walks the pass, only the stores are predicated
           // (tiles do not align with games, so `in_range` is not warp-uniform)
-          uint4* so = reinterpret_cast<uint4*>(p.out_scaled + row * BN);
+          uint4* so = reinterpret_cast<uint4*>(p.out_scaled + row * NC);
           uint4* po = (p.pool_out && in_range)
-                          ? reinterpret_cast<uint4*>(p.pool_out + ((size_t)p.pool_row_base[g] + pos) * BN)
+                          ? reinterpret_cast<uint4*>(p.pool_out + ((size_t)p.pool_row_base[g] + pos) * NC)
                           : nullptr;
           const float den = mx - mn;
 #pragma unroll
           for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (c0 >= NC) break;
             float x[32];
             chunk(c0, x);
 #pragma unroll
@@ -516,9 +535,117 @@ __global__ void conv_gather_kernel(int G, int nodes_per_game, const int32_t* __r
   if (lane < 16) out[(size_t)w * 16 + lane] = pool[src * 16 + lane];
 }
 
+// Stride-2 3x3 patches of a padded channels-last image as GEMM rows: out[(g, y, x)][tap * C + c] =
+// in[g][2y + ky - 1][2x + kx - 1][c].  The zero padding is physically present in the layout, so the
+// gather needs no bounds checks.  One thread per 16-byte chunk.
+__global__ void conv_im2col_s2_kernel(int games, int w_in, int C, int k_pad, const uint4* __restrict__ in,
+                                      uint4* __restrict__ out) {
+  const int w_out = w_in / 2, wp = w_in + 1, cpr = C / 8, kchunks = k_pad / 8;
+  const long long total = (long long)games * w_out * w_out * kchunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kc = (int)(i % kchunks);
+    const long long r = i / kchunks;
+    const int x = (int)(r % w_out), y = (int)((r / w_out) % w_out), g = (int)(r / ((long long)w_out * w_out));
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    const int tap = kc / cpr;
+    if (tap < 9) {
+      const int cc = kc - tap * cpr, ky = tap / 3, kx = tap - 3 * ky;
+      const long long src = (long long)g * wp * wp + wp + (long long)(2 * y + ky - 1) * wp + (2 * x + kx - 1);
+      if (src >= 0) v = in[src * cpr + cc];  // row -1 of game 0 lies before the buffer: zero padding
+    }
+    out[i] = v;
+  }
+}
+
+// AvgPool2d(3, stride 2, padding 1, count_include_pad) between two padded channels-last layouts.
+__global__ void conv_avgpool_kernel(int games, int w_in, int C, const uint4* __restrict__ in,
+                                    uint4* __restrict__ out) {
+  const int w_out = w_in / 2, wp = w_in + 1, wpo = w_out + 1, cpr = C / 8;
+  const long long total = (long long)games * w_out * w_out * cpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % cpr);
+    const long long r = i / cpr;
+    const int x = (int)(r % w_out), y = (int)((r / w_out) % w_out), g = (int)(r / ((long long)w_out * w_out));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap - 3 * ky;
+      const long long src = (long long)g * wp * wp + wp + (long long)(2 * y + ky - 1) * wp + (2 * x + kx - 1);
+      const uint4 v = src >= 0 ? in[src * cpr + cc] : make_uint4(0u, 0u, 0u, 0u);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[h]);
+        acc[2 * h] += __low2float(b2);
+        acc[2 * h + 1] += __high2float(b2);
+      }
+    }
+    const float s = 1.0f / 9.0f;
+    const long long dst = (long long)g * wpo * wpo + wpo + (long long)y * wpo + x;
+    out[dst * cpr + cc] = make_uint4(pack_bf16(acc[0] * s, acc[1] * s), pack_bf16(acc[2] * s, acc[3] * s),
+                                     pack_bf16(acc[4] * s, acc[5] * s), pack_bf16(acc[6] * s, acc[7] * s));
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+// Stride-2 convolution, step 1: patches -> GEMM rows.  in: padded channels-last image
+// [games * (w_in + 1)^2][C] bf16; out: [games * (w_in / 2)^2][k_pad] bf16 with k = tap * C + c
+// (columns >= 9 C are zero).  C % 8 == 0, k_pad % 64 == 0.
+int mz_conv_im2col_s2(int32_t games, int32_t w_in, int32_t channels, int32_t k_pad, const void* in, void* out,
+                      void* stream) {
+  if (games < 1 || w_in < 2 || (w_in & 1) || channels < 8 || (channels % 8) || k_pad < 9 * channels ||
+      (k_pad % 64) || !in || !out)
+    return MZ_ERR_BAD_ARG;
+  conv_im2col_s2_kernel<<<148 * 16, 256, 0, (cudaStream_t)stream>>>(games, w_in, channels, k_pad,
+                                                                    (const uint4*)in, (uint4*)out);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+// Stride-2 convolution, step 2 (and any Linear layer whose output is an image): out[(g, y, x)] =
+// a[(g, y, x)] . w^T + bias (+ReLU) as bf16 rows of the padded layout of an out_w x out_w image with
+// n_out (64 or 128) channels.  a [rows][k] bf16, w [n_out][k] bf16, k % 64 == 0.  The padding rows of
+// `out` are not touched (zero them once).
+int mz_conv_gemm_to_padded(int32_t games, int32_t out_w, int32_t k, int32_t n_out, const void* a, const void* w,
+                           const float* bias, int32_t relu, void* out, void* stream) {
+  if (games < 1 || out_w < 1 || k < 64 || (k % 64) || (n_out != 64 && n_out != 128) || !a || !w || !bias || !out)
+    return MZ_ERR_BAD_ARG;
+  const long long rows = (long long)games * out_w * out_w;
+  if (rows > 0x7fffffffLL - 2 * BM) return MZ_ERR_UNSUPPORTED;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, a, (uint64_t)rows, (uint64_t)k);
+  if (rc) return rc;
+  rc = make_map(&mb, w, (uint64_t)n_out, (uint64_t)k);
+  if (rc) return rc;
+  ConvParams p = {};
+  p.mode_fc = 1;
+  p.num_tiles_m = (int)((rows + BM - 1) / BM);
+  p.num_tiles_n = 1;
+  p.ncols = n_out;
+  p.kb_per_tap = 1;
+  p.num_kblocks = k / BK;
+  p.rows_total = (int)rows;
+  p.flags = EPI_TO_PADDED | (relu ? EPI_RELU : 0);
+  p.bias = bias;
+  p.out = (__nv_bfloat16*)out;
+  p.out_w = out_w;
+  return launch_conv(ma, mb, p, stream);
+}
+
+// AvgPool2d(kernel 3, stride 2, padding 1) (networks.py:406, 409) between padded channels-last layouts:
+// in [games * (w_in + 1)^2][C] -> out [games * (w_in / 2 + 1)^2][C] (padding rows of `out` untouched).
+int mz_conv_avgpool(int32_t games, int32_t w_in, int32_t channels, const void* in, void* out, void* stream) {
+  if (games < 1 || w_in < 2 || (w_in & 1) || channels < 8 || (channels % 8) || !in || !out) return MZ_ERR_BAD_ARG;
+  conv_avgpool_kernel<<<148 * 16, 256, 0, (cudaStream_t)stream>>>(games, w_in, channels, (const uint4*)in,
+                                                                  (uint4*)out);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
 
 // Gathers hidden-pool slots [g][node[g]] into the flat activation layout: out [games * 49][128] bf16.
 int mz_conv_gather(int32_t games, int32_t nodes_per_game, const int32_t* node, const void* pool, void* out,
@@ -540,11 +667,13 @@ int mz_conv_gather(int32_t games, int32_t nodes_per_game, const int32_t* node, c
 //   bias         [128] f32;  plane_term [36][128] f32 and actions [games] when flags & 4
 //   pool_out + pool_row_base: with flags & 8 the scaled rows of game g are also written at rows
 //   pool_row_base[g] .. + 49 of pool_out (the hidden pool slot of the new node)
-int mz_conv3x3_tc(int32_t games, int32_t width, const void* x, const void* w_packed, const float* bias, int32_t flags,
+int mz_conv3x3_tc(int32_t games, int32_t width, int32_t channels, const void* x, const void* w_packed,
+                  const float* bias, int32_t flags,
                   const float* plane_term, const int32_t* actions, int32_t num_actions,
                   const void* residual, void* out, void* out_scaled, void* pool_out,
                   const int32_t* pool_row_base, void* stream) {
   if (games < 1 || width < 1 || width > 255 || !x || !w_packed || !bias) return MZ_ERR_BAD_ARG;
+  if (channels != 64 && channels != 128) return MZ_ERR_UNSUPPORTED;
   if ((flags & EPI_ACTION) && (!plane_term || !actions || num_actions < 1)) return MZ_ERR_BAD_ARG;
   if ((flags & EPI_RESIDUAL) && !residual) return MZ_ERR_BAD_ARG;
   if ((flags & EPI_SCALE) && !out_scaled) return MZ_ERR_BAD_ARG;
@@ -555,15 +684,17 @@ int mz_conv3x3_tc(int32_t games, int32_t width, const void* x, const void* w_pac
   const long long rows = (long long)games * grows;
   if (rows > 0x7fffffffLL - 2 * BM) return MZ_ERR_UNSUPPORTED;
   CUtensorMap ma, mb;
-  int rc = make_map(&ma, x, (uint64_t)rows, 128);
+  int rc = make_map(&ma, x, (uint64_t)rows, (uint64_t)channels);
   if (rc) return rc;
-  rc = make_map(&mb, w_packed, 128, 9 * 128);
+  rc = make_map(&mb, w_packed, (uint64_t)channels, 9 * (uint64_t)channels);
   if (rc) return rc;
   ConvParams p = {};
   p.mode_fc = 0;
   p.num_tiles_m = (int)((rows + BM - 1) / BM);
   p.num_tiles_n = 1;
-  p.num_kblocks = 18;
+  p.ncols = channels;
+  p.kb_per_tap = channels / BK;
+  p.num_kblocks = 9 * p.kb_per_tap;
   p.rows_total = (int)rows;
   p.flags = flags;
   p.num_actions = num_actions;
@@ -597,6 +728,8 @@ int mz_conv_fc_tc(int32_t games, const void* x, const void* w_packed, const floa
   p.mode_fc = 1;
   p.num_tiles_m = (games + BM - 1) / BM;
   p.num_tiles_n = n_out / BN;
+  p.ncols = BN;
+  p.kb_per_tap = 1;
   p.num_kblocks = KFC / BK;
   p.rows_total = games;
   p.flags = EPI_F32_OUT | (relu ? EPI_RELU : 0);

@@ -10,10 +10,10 @@ implicit-GEMM kernel in csrc/mz_conv_tc.cu on bf16 activations in a flat padded 
 hidden-state pool of the search holds states in the same layout, is gathered by one small copy
 kernel per simulation and written in place by the last dynamics convolution.
 
-Representation tower (`initial_inference`, once per move): the 128-channel stages -- 3 + 3 + 16
-residual blocks at 24 x 24, 12 x 12 and 6 x 6 pixels, 44 of its 50 convolutions -- run on the same
-kernel; the stem (two strided convolutions, the two 64-channel blocks at 48 x 48) and the two
-average pools are torch operators in float32 (round-1 limitation, stated in DESIGN.md).
+Representation tower (`initial_inference`, once per move): the residual blocks at 48 x 48 (64
+channels), 24 x 24, 12 x 12 and 6 x 6 pixels run on the same implicit-GEMM kernel, the two strided
+convolutions as im2col + the kernel's plain-GEMM mode, the two average pools as a small kernel; the
+only torch operation left is the layout change of the raw observation.
 """
 import torch
 import torch.nn.functional as F
@@ -31,25 +31,26 @@ BN_EPS = 1e-5
 def to_padded(state):
   """[B, 128, W, W] float -> [B * (W + 1)^2, 128] bf16 rows: channels last, one zero row on top and one
   zero pixel after every image row (the zero padding neighbouring games share)."""
-  b, w = state.shape[0], state.shape[-1]
+  b, c, w = state.shape[0], state.shape[1], state.shape[-1]
   x = F.pad(state.permute(0, 2, 3, 1), (0, 0, 0, 1, 1, 0))    # [B, W + 1, W + 1, C]
-  return x.reshape(b * (w + 1) * (w + 1), CH).to(torch.bfloat16).contiguous()
+  return x.reshape(b * (w + 1) * (w + 1), c).to(torch.bfloat16).contiguous()
 
 
 def from_padded(rows, b, width=6):
-  """[B * (W + 1)^2, 128] bf16 rows -> [B, 128, W, W] float32."""
-  x = rows.reshape(b, width + 1, width + 1, CH)[:, 1:, :width, :]
+  """[B * (W + 1)^2, C] bf16 rows -> [B, C, W, W] float32."""
+  x = rows.reshape(b, width + 1, width + 1, rows.shape[-1])[:, 1:, :width, :]
   return x.permute(0, 3, 1, 2).float().contiguous()
 
 
 def padding_rows(rows, b, width=6):
   """The padding rows of every game (must stay zero)."""
-  x = rows.reshape(b, width + 1, width + 1, CH)
+  x = rows.reshape(b, width + 1, width + 1, rows.shape[-1])
   return torch.cat((x[:, 0], x[:, 1:, width]), dim=1)
 
 
 class _Conv(object):
-  """One folded convolution: packed bf16 weights [128][1152], float32 bias (+ action-plane term)."""
+  """One folded convolution: packed bf16 weights [C][9 C] (C = 64 or 128), float32 bias (+ action-plane
+  term of MuZeroDynamics.conv)."""
 
   def __init__(self, weight, conv_bias, bn, device):
     w = weight.to(device, torch.float32)
@@ -61,15 +62,35 @@ class _Conv(object):
       if conv_bias is not None:
         bias = bias + conv_bias.to(device, torch.float32) * scale
     else:
-      bias = conv_bias.to(device, torch.float32) if conv_bias is not None else torch.zeros(CH, device=device)
+      bias = (conv_bias.to(device, torch.float32) if conv_bias is not None
+              else torch.zeros(w.shape[0], device=device))
+    self.channels = c = int(w.shape[0])
     self.plane = None
     if w.shape[1] == CH + 1:  # MuZeroDynamics.conv: the 129th input channel is the action plane
       ones = torch.ones((1, 1, 6, 6), device=device)
       # what a constant plane of ones contributes at each interior pixel (zero padding outside)
       self.plane = F.conv2d(ones, w[:, CH:], None, 1, 1)[0].permute(1, 2, 0).reshape(36, CH).contiguous()
       w = w[:, :CH]
-    self.w = w.permute(0, 2, 3, 1).reshape(CH, 9 * CH).to(torch.bfloat16).contiguous()
+    self.w = w.permute(0, 2, 3, 1).reshape(c, 9 * c).to(torch.bfloat16).contiguous()
     self.bias = bias.contiguous()
+
+
+class _StridedConv(object):
+  """Conv2d(Cin -> Cout, 3x3, stride 2, padding 1, bias) as im2col + GEMM: weights [Cout][k_pad] bf16
+  with k = (ky * 3 + kx) * Cin_pad + c (input channels padded to a multiple of 8, K to one of 64)."""
+
+  def __init__(self, weight, bias, device):
+    w = weight.to(device, torch.float32)
+    cout, cin = int(w.shape[0]), int(w.shape[1])
+    self.cin_pad = (cin + 7) // 8 * 8
+    self.cout = cout
+    self.k_pad = (9 * self.cin_pad + 63) // 64 * 64
+    wp = torch.zeros((cout, 3, 3, self.cin_pad), dtype=torch.float32, device=device)
+    wp[..., :cin] = w.permute(0, 2, 3, 1)
+    full = torch.zeros((cout, self.k_pad), dtype=torch.float32, device=device)
+    full[:, :9 * self.cin_pad] = wp.reshape(cout, 9 * self.cin_pad)
+    self.w = full.to(torch.bfloat16).contiguous()
+    self.bias = bias.to(device, torch.float32).contiguous()
 
 
 def _pack_fc(weight, device):
@@ -124,9 +145,8 @@ class MuZeroNetwork(object):
         convs.append(_Conv(sd[b + '.conv2.weight'], None, bn(b + '.bn2'), dev))
       return convs
 
-    # representation tower: the 128-channel stages (3 + 3 + 16 blocks at 24 / 12 / 6 pixels) run on the
-    # tensor-core kernel; the stem (strided convolutions, the 64-channel blocks) and the two average
-    # pools stay torch operators
+    # representation tower: every layer runs on this library's kernels (strided convolutions as
+    # im2col + GEMM, residual blocks on the implicit-GEMM kernel, average pools)
     r = 'representation_head'
 
     def blocks(p, n):
@@ -137,6 +157,9 @@ class MuZeroNetwork(object):
         convs.append(_Conv(sd[b + '.conv2.weight'], None, bn(b + '.bn2'), dev))
       return convs
 
+    self.rep_conv1 = _StridedConv(sd[r + '.conv1.weight'], sd[r + '.conv1.bias'], dev)
+    self.rep_blocks1 = blocks(r + '.resblocks1', 2)   # 64 channels at 48 x 48
+    self.rep_conv2 = _StridedConv(sd[r + '.conv2.weight'], sd[r + '.conv2.bias'], dev)
     self.rep_blocks2 = blocks(r + '.resblocks2', 3)
     self.rep_blocks3 = blocks(r + '.resblocks3', 3)
     self.rep_tower = blocks(r + '.resblocks', 16)
@@ -183,26 +206,26 @@ class MuZeroNetwork(object):
     return self
 
   # -- buffers ---------------------------------------------------------------------------------------
-  def buffers(self, games, width=6):
+  def buffers(self, games, width=6, channels=CH):
     """Scratch activations for `games` games of width x width pixels: three flat padded bf16 buffers
     (+ one for the scaled state) and the head hidden layer [games][reward 512 | value 512 | policy
     512] float32."""
-    b = self._bufs.get((games, width))
+    b = self._bufs.get((games, width, channels))
     if b is None:
       dev = self.device
       rows = games * (width + 1) * (width + 1)
-      b = dict(x=[torch.zeros((rows, CH), dtype=torch.bfloat16, device=dev) for _ in range(3)])
+      b = dict(x=[torch.zeros((rows, channels), dtype=torch.bfloat16, device=dev) for _ in range(3)])
       if width == 6:
         b['scaled'] = torch.zeros((rows, CH), dtype=torch.bfloat16, device=dev)
         b['fc'] = torch.zeros((games, 1536), dtype=torch.float32, device=dev)
-      self._bufs[(games, width)] = b
+      self._bufs[(games, width, channels)] = b
     return b
 
   # -- launches --------------------------------------------------------------------------------------
   def _conv(self, games, conv, x, flags, out, residual=None, actions=None, out_scaled=None, pool_out=None,
             pool_base=None, width=6):
     P = _lib.ptr
-    _lib.check(self.lib.mz_conv3x3_tc(games, width, P(x), P(conv.w), P(conv.bias), flags,
+    _lib.check(self.lib.mz_conv3x3_tc(games, width, conv.channels, P(x), P(conv.w), P(conv.bias), flags,
                                       P(conv.plane) if flags & ACTION else None, P(actions),
                                       self.action_space, P(residual), P(out), P(out_scaled), P(pool_out),
                                       P(pool_base), _lib.current_stream()), "mz_conv3x3_tc")
@@ -265,35 +288,58 @@ class MuZeroNetwork(object):
     self.launches += 3
 
   # -- reference interface ---------------------------------------------------------------------------
+  IM2COL_BYTES = 384 << 20  # scratch budget for the patch matrix of a strided convolution
+
+  def _strided(self, games, conv, x, w_in, out):
+    """Conv2d(stride 2) over `games` padded images x [games * (w_in + 1)^2][Cin_pad] -> rows of the
+    padded (w_in / 2)-pixel layout `out` (im2col + GEMM, a chunk of games at a time)."""
+    P, st = _lib.ptr, _lib.current_stream()
+    w_out, cin = w_in // 2, conv.cin_pad
+    per_game = w_out * w_out * conv.k_pad * 2
+    chunk = max(1, min(games, self.IM2COL_BYTES // per_game))
+    cols = self._bufs.get(('im2col', chunk * per_game))
+    if cols is None:
+      cols = torch.empty(chunk * per_game, dtype=torch.uint8, device=self.device)
+      self._bufs[('im2col', chunk * per_game)] = cols
+    in_rows, out_rows = (w_in + 1) * (w_in + 1), (w_out + 1) * (w_out + 1)
+    for g0 in range(0, games, chunk):
+      n = min(chunk, games - g0)
+      _lib.check(self.lib.mz_conv_im2col_s2(n, w_in, cin, conv.k_pad, C_ptr(x[g0 * in_rows:]), P(cols), st),
+                 "mz_conv_im2col_s2")
+      _lib.check(self.lib.mz_conv_gemm_to_padded(n, w_out, conv.k_pad, conv.cout, P(cols), P(conv.w),
+                                                 P(conv.bias), 0, C_ptr(out[g0 * out_rows:]), st),
+                 "mz_conv_gemm_to_padded")
+    self.launches += 2 * ((games + chunk - 1) // chunk)
+
+  def _pool(self, games, x, w_in, out):
+    _lib.check(self.lib.mz_conv_avgpool(games, w_in, CH, _lib.ptr(x), _lib.ptr(out), _lib.current_stream()),
+               "mz_conv_avgpool")
+    self.launches += 1
+
   def representation_rows(self, observation):
     """MuZeroRepresentation + scale_state (networks.py:412-426, 500-503) -> the scaled 6 x 6 state in
-    the flat padded bf16 layout (a scratch buffer owned by the network)."""
-    sd = self._state
+    the flat padded bf16 layout (a scratch buffer owned by the network).  Only the layout change of
+    the raw observation (NCHW float -> padded channels-last bf16) is a torch operation."""
     obs = torch.as_tensor(observation).to(self.device, torch.float32)
-    g = obs.shape[0]
-    p = 'representation_head.'
-
-    def bn(x, q):
-      return F.batch_norm(x, sd[q + '.running_mean'], sd[q + '.running_var'], sd[q + '.weight'],
-                          sd[q + '.bias'], False, 0.0, BN_EPS)
-
-    def block(x, q):
-      out = F.relu(bn(F.conv2d(x, sd[q + '.conv1.weight'], None, 1, 1), q + '.bn1'))
-      out = bn(F.conv2d(out, sd[q + '.conv2.weight'], None, 1, 1), q + '.bn2')
-      return F.relu(out + x)
-
-    # stem: torch operators, float32
-    out = F.conv2d(obs, sd[p + 'conv1.weight'], sd[p + 'conv1.bias'], 2, 1)
-    for i in range(2):
-      out = block(out, p + 'resblocks1.%d' % i)
-    out = F.conv2d(out, sd[p + 'conv2.weight'], sd[p + 'conv2.bias'], 2, 1)
-    # 128-channel stages: tensor-core kernel, bf16 activations; pooling in between stays torch
-    for convs in (self.rep_blocks2, self.rep_blocks3):
-      w = out.shape[-1]
-      rows = self._tower(g, convs, to_padded(out), self.buffers(g, w)['x'], width=w)
-      out = F.avg_pool2d(from_padded(rows, g, w), 3, 2, 1)
+    g, cin, w0 = obs.shape[0], obs.shape[1], obs.shape[-1]
+    if w0 != 96 or obs.shape[-2] != 96:
+      raise ValueError("MuZeroRepresentation expects 96 x 96 observations")
+    c1 = self.rep_conv1
+    if cin < c1.cin_pad:
+      obs = F.pad(obs, (0, 0, 0, 0, 0, c1.cin_pad - cin))
+    x = to_padded(obs)                                          # [g * 97^2][cin_pad]
+    b48 = self.buffers(g, 48, 64)['x']
+    self._strided(g, c1, x, 96, b48[0])                         # conv1: 96 -> 48, 64 channels
+    s1 = self._tower(g, self.rep_blocks1, b48[0], b48, width=48)
+    b24 = self.buffers(g, 24)['x']
+    self._strided(g, self.rep_conv2, s1, 48, b24[0])            # conv2: 48 -> 24, 128 channels
+    s2 = self._tower(g, self.rep_blocks2, b24[0], b24, width=24)
+    b12 = self.buffers(g, 12)['x']
+    self._pool(g, s2, 24, b12[0])
+    s3 = self._tower(g, self.rep_blocks3, b12[0], b12, width=12)
     b = self.buffers(g)
-    self._tower(g, self.rep_tower, to_padded(out), b['x'], last_flags=SCALE, out_scaled=b['scaled'])
+    self._pool(g, s3, 12, b['x'][0])
+    self._tower(g, self.rep_tower, b['x'][0], b['x'], last_flags=SCALE, out_scaled=b['scaled'])
     return b['scaled']
 
   def representation(self, observation):

@@ -42,7 +42,7 @@ def test_conv_kernel_matches_conv2d(games, flags):
   out = torch.full((games * 49, 128), 7.0, dtype=torch.bfloat16, device=dev)
   scaled = torch.full((games * 49, 128), 7.0, dtype=torch.bfloat16, device=dev)
   P = _lib.ptr
-  _lib.check(lib.mz_conv3x3_tc(games, 6, P(rows), P(conv.w), P(conv.bias), flags,
+  _lib.check(lib.mz_conv3x3_tc(games, 6, 128, P(rows), P(conv.w), P(conv.bias), flags,
                                P(conv.plane) if flags & 4 else None, P(actions), 18,
                                P(res_rows) if flags & 2 else None, P(out),
                                P(scaled) if flags & 8 else None, None, None, _lib.current_stream()), "conv")
@@ -68,26 +68,59 @@ def test_conv_kernel_matches_conv2d(games, flags):
     assert float(muzero.padding_rows(scaled, games).float().abs().max()) == 0
 
 
-@pytest.mark.parametrize("width,games", [(12, 3), (24, 2)])
-def test_conv_kernel_other_widths(width, games):
-  """The same kernel on the 12 x 12 and 24 x 24 stages of the representation tower."""
+@pytest.mark.parametrize("width,games,ch", [(12, 3, 128), (24, 2, 128), (48, 2, 64)])
+def test_conv_kernel_other_widths(width, games, ch):
+  """The same kernel on the 12 x 12 / 24 x 24 (128 channels) and 48 x 48 (64 channels) stages of the
+  representation tower."""
   from model_based_rl_b200 import _lib, muzero
   lib = _lib.load()
   torch.manual_seed(width)
   dev = "cuda"
-  x = torch.rand((games, 128, width, width), device=dev)
-  w = (torch.rand((128, 128, 3, 3), device=dev) * 2 - 1) * (3.0 / 1152) ** 0.5
-  conv = muzero._Conv(w, torch.randn(128, device=dev) * 0.1, None, dev)
+  x = torch.rand((games, ch, width, width), device=dev)
+  w = (torch.rand((ch, ch, 3, 3), device=dev) * 2 - 1) * (3.0 / (9 * ch)) ** 0.5
+  conv = muzero._Conv(w, torch.randn(ch, device=dev) * 0.1, None, dev)
   rows = muzero.to_padded(x)
   out = torch.full_like(rows, 7.0)
   P = _lib.ptr
-  _lib.check(lib.mz_conv3x3_tc(games, width, P(rows), P(conv.w), P(conv.bias), 1 | 2, None, None, 18, P(rows),
+  _lib.check(lib.mz_conv3x3_tc(games, width, ch, P(rows), P(conv.w), P(conv.bias), 1 | 2, None, None, 18, P(rows),
                                P(out), None, None, None, _lib.current_stream()), "conv")
   torch.cuda.synchronize()
   want = F.relu(F.conv2d(_bf16(x), _bf16(w), None, 1, 1) + conv.bias[None, :, None, None] + _bf16(x))
   got = muzero.from_padded(out, games, width)
   assert torch.allclose(got, want, rtol=1e-2, atol=2e-2), float((got - want).abs().max())
   assert float(muzero.padding_rows(out, games, width).float().abs().max()) == 0
+
+
+@pytest.mark.parametrize("cin,cout,w_in,games", [(4, 64, 96, 2), (32, 64, 96, 1), (64, 128, 48, 3)])
+def test_strided_conv_and_avgpool(cin, cout, w_in, games):
+  """Conv2d(stride 2) as im2col + GEMM into the padded layout, and AvgPool2d(3, 2, 1), vs torch on the
+  same bf16-rounded operands."""
+  from model_based_rl_b200 import muzero
+  dev = "cuda"
+  torch.manual_seed(cin + w_in)
+  net = muzero.MuZeroNetwork(cin, 18, dev, CFG)
+  x = torch.rand((games, cin, w_in, w_in), device=dev)
+  w = (torch.rand((cout, cin, 3, 3), device=dev) * 2 - 1) * (3.0 / (9 * cin)) ** 0.5
+  bias = torch.randn(cout, device=dev) * 0.1
+  conv = muzero._StridedConv(w, bias, dev)
+  xp = F.pad(x, (0, 0, 0, 0, 0, conv.cin_pad - cin))
+  rows = muzero.to_padded(xp)
+  w_out = w_in // 2
+  out = torch.zeros((games * (w_out + 1) ** 2, cout), dtype=torch.bfloat16, device=dev)
+  net._strided(games, conv, rows, w_in, out)
+  torch.cuda.synchronize()
+  want = F.conv2d(_bf16(x), _bf16(w), bias, 2, 1)
+  got = muzero.from_padded(out, games, w_out)
+  assert torch.allclose(got, want, rtol=1e-2, atol=2e-2), float((got - want).abs().max())
+  assert float(muzero.padding_rows(out, games, w_out).float().abs().max()) == 0
+  if cout == 128:
+    pooled = torch.zeros((games * (w_out // 2 + 1) ** 2, 128), dtype=torch.bfloat16, device=dev)
+    net._pool(games, out, w_out, pooled)
+    torch.cuda.synchronize()
+    want_p = F.avg_pool2d(muzero.from_padded(out, games, w_out), 3, 2, 1)
+    got_p = muzero.from_padded(pooled, games, w_out // 2)
+    assert torch.allclose(got_p, want_p, rtol=1e-2, atol=1e-2)
+    assert float(muzero.padding_rows(pooled, games, w_out // 2).float().abs().max()) == 0
 
 
 def test_pool_gather_scatter_and_fc_heads():
@@ -115,7 +148,7 @@ def test_pool_gather_scatter_and_fc_heads():
   scaled = torch.zeros_like(out)
   dst = (pick + 1) % slots
   out_base = ((torch.arange(games, device=dev) * slots + dst) * 49).to(torch.int32)
-  _lib.check(lib.mz_conv3x3_tc(games, 6, P(flat), P(conv.w), P(conv.bias), 1 | 2 | 8, None, None, 18, P(flat),
+  _lib.check(lib.mz_conv3x3_tc(games, 6, 128, P(flat), P(conv.w), P(conv.bias), 1 | 2 | 8, None, None, 18, P(flat),
                                P(out), P(scaled), P(pool), P(out_base), _lib.current_stream()), "conv")
   torch.cuda.synchronize()
   want = F.relu(F.conv2d(_bf16(x), _bf16(w), None, 1, 1) + _bf16(x))
