@@ -452,9 +452,8 @@ def bench_conv(args, torch, _lib, dev):
   roof["frac"] = roof["achieved"] / roof["peak"]
   del cs
   return {"workload": "C5 MuZeroNetwork residual conv (16+16 blocks, 128 ch, 6x6 state), %d games x %d "
-                      "sims, A=%d, synthetic 96x96x%d frames, bf16 tcgen05 recurrent_inference and 128-channel "
-                      "representation stages; representation stem (strided / 64-channel convolutions, "
-                      "pools) in torch float32" % (G, S, A, C_in),
+                      "sims, A=%d, synthetic 96x96x%d frames, bf16 tcgen05 initial_inference (representation "
+                      "tower included) and recurrent_inference" % (G, S, A, C_in),
           "expansions_per_s": G * S * steps / (ms_move * 1e-3),
           "expansions_per_s_search_only": G * S * steps / (ms_search * 1e-3),
           "ms_per_move": ms_move / steps, "ms_representation": (ms_move - ms_search) / steps,
