@@ -135,11 +135,14 @@ def load():
   global _lib
   if _lib is not None:
     return _lib
-  if not os.path.exists(LIB_PATH):
+  path = os.environ.get("MZB200_LIB", LIB_PATH)  # A/B builds of the same ABI (diagnostics)
+  if not os.path.exists(path):
     raise MzError("libmzb200.so is not built (%s); run `python -c 'import __graft_entry__ as g; "
-                  "g.build()'` -- this package has no CPU fallback" % LIB_PATH)
-  lib = C.CDLL(LIB_PATH)
+                  "g.build()'` -- this package has no CPU fallback" % path)
+  lib = C.CDLL(path)
   for name, (res, args) in _SIGNATURES.items():
+    if name.startswith("mz_debug_") and not hasattr(lib, name) and path != LIB_PATH:
+      continue
     fn = getattr(lib, name)  # AttributeError if the symbol is not exported
     fn.restype = res
     fn.argtypes = args

@@ -29,3 +29,4 @@ flops_conv = 2.0 * G * 36 * 128 * 1152
 flops_issued = 2.0 * G * ROWS * 128 * 1152
 print("G=%d conv3x3: %.1f us (%.0f TFLOP/s useful, %.0f issued), with residual %.1f us" % (G, t_conv, flops_conv / t_conv / 1e6, flops_issued / t_conv / 1e6, t_res))
 print("recurrent_inference: %.1f us total = %.2f us/game ; useful %.0f TFLOP/s" % (t_rec, t_rec / G, G * 0.705e9 / t_rec / 1e6))
+
