@@ -341,12 +341,17 @@ def run_b200(args):
     tree_bytes = G * (d * (28 * A + 33) + 16 * A + 86)
     fc_flops = G * FC_FLOPS_PER_EXPANSION(A)
     tree_t, fc_t = kern["tree_step_us"] * 1e-6, kern["fc_recurrent_us"] * 1e-6
-    roof_tree = {"kernel": "tree_step_kernel", "bound": "hbm", "achieved": tree_bytes / tree_t / 1e9,
-                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": None,
+    # dram__bytes_read + write per launch from the ncu --set full captures of the default workload
+    # (profiles/r01h_ncu_summary.md, r01m_ncu_summary.md); null for any other configuration
+    default_cfg = (G, S, A, args.obs_dim) == (4096, 50, 18, 128)
+    roof_tree = {"kernel": "tree_step_w32_kernel" if A > 16 else "tree_step_kernel", "bound": "hbm",
+                 "achieved": tree_bytes / tree_t / 1e9,
+                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": 43.2e6 if default_cfg else None,
                  "algorithmic_bytes_per_launch": tree_bytes, "avg_launch_us": kern["tree_step_us"]}
     roof_fc = {"kernel": "fc_recurrent_tc_kernel" if args.precision == "bf16" else "fc_recurrent_f32_kernel",
                "bound": "tensor", "achieved": fc_flops / fc_t / 1e12,
-               "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "traffic": None,
+               "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+               "traffic": 1.9e6 if default_cfg else None,
                "algorithmic_flops_per_launch": fc_flops, "avg_launch_us": kern["fc_recurrent_us"]}
     for r in (roof_tree, roof_fc):
       r["frac"] = r["achieved"] / r["peak"]
@@ -446,7 +451,8 @@ def bench_conv(args, torch, _lib, dev):
   peaks = measured_peaks()
   flops = 2.0 * G * 36 * 128 * 1152  # algorithmic: interior pixels only (the padded rows are overhead)
   roof = {"kernel": "conv_gemm_tc_kernel", "bound": "tensor", "achieved": flops / us_conv / 1e6,
-          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "traffic": None,
+          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+          "traffic": 108.1e6 if (G, C_in) == (4096, 32) else None,  # ncu, profiles/r01m_ncu_summary.md
           "algorithmic_flops_per_launch": flops, "avg_launch_us": us_conv,
           "issued_tflops": 2.0 * G * ROWS * 128 * 1152 / us_conv / 1e6, "peak_source": peaks["source"]}
   roof["frac"] = roof["achieved"] / roof["peak"]
