@@ -1,0 +1,139 @@
+"""Batched self-play: the body of Actor.play_game (actors.py:125-176) for G games in lock step.
+
+Per move: observations -> `initial_inference` -> root expansion over the legal actions + Dirichlet
+noise -> batched search on the GPU (`BatchedMCTS.search`, any network with the reference's interface)
+-> `select_action` with per-game temperature -> environment step -> `Game.apply` /
+`store_search_statistics` bookkeeping (game.py:75-115) -> history slices pushed to the replay buffer
+with the reference's chunking rules (`max_history_length`, the `num_unroll_steps + td_steps` overlap,
+`ignore` for running games, actors.py:160-169).  A finished game is replaced by a new one at once, so
+the batch always holds G live games.
+
+Random draws (Dirichlet noise per root, one uniform per action selection) come from numpy unless the
+caller passes them in -- which is how the parity test replays the reference.
+"""
+import collections
+
+import numpy as np
+import torch
+
+from .mcts import BatchedMCTS
+
+HistorySlice = collections.namedtuple(
+    "HistorySlice", "observations child_visits root_values actions rewards errors dones steps env_states "
+    "to_play")  # game.py:5-16
+
+
+class _Game(object):
+  """The per-game bookkeeping of game.Game (game.py:56-126) without the environment."""
+
+  def __init__(self, first_observation):
+    self.observations = [first_observation]
+    self.child_visits, self.root_values, self.actions, self.rewards = [], [], [], []
+    self.errors, self.dones, self.steps, self.to_play_hist = [], [], [], []
+    self.previous_collect_to = 0
+    self.history_idx = 0
+    self.step = 0
+    self.to_play = 1
+    self.sum_rewards = 0
+    self.sum_values = 0.0
+    self.max_value = -np.inf
+
+  def slice(self, collect_from):  # History.get_slice + get_history_sequence (game.py:40-51, 123-126)
+    s = slice(collect_from, None)
+    out = HistorySlice(self.observations[s], self.child_visits[s], self.root_values[s], self.actions[s],
+                       self.rewards[s], self.errors[s], self.dones[s], self.steps[s],
+                       [None] * len(self.actions[s]), self.to_play_hist[s])
+    self.previous_collect_to = self.history_idx
+    return out
+
+
+class BatchedActor(object):
+
+  def __init__(self, config, network, env, replay_buffer=None, device=None, temperature=1.0):
+    self.config, self.network, self.env, self.replay = config, network, env, replay_buffer
+    self.G, self.A = env.num_games, int(config.action_space)
+    self.device = torch.device("cuda" if device is None else device)
+    self.eng = None  # built on the first move (the hidden-state width comes from the network)
+    self.temperature = np.broadcast_to(np.asarray(temperature, np.float64), (self.G,)).copy()
+    self.games = [_Game(o) for o in env.reset()]
+    self.experiences_collected = 0
+    self.games_played = 0
+    self.results = collections.Counter()
+    self.saved = []  # (game index, history, ignore, terminal) when no replay buffer is attached
+
+  # -- one move for every game -------------------------------------------------------------------------
+  def play_move(self, noise=None, uniforms=None):
+    cfg, env, G, A = self.config, self.env, self.G, self.A
+    obs = np.stack([np.float32(g.observations[-1]) for g in self.games])      # get_observation(-1)
+    if getattr(cfg, "norm_obs", False):
+      obs = (obs - cfg.obs_min) / cfg.obs_range
+    with torch.inference_mode():
+      init = self.network.initial_inference(torch.from_numpy(obs).to(self.device))
+    legal = env.legal_mask()
+    to_play = np.array([g.to_play for g in self.games], np.int8)
+    if noise is None:  # Node.add_exploration_noise (mcts.py:57-61): one draw per root over its children
+      noise = np.zeros((G, A))
+      for i in range(G):
+        n = bin(int(legal[i])).count("1")
+        noise[i, :n] = np.random.dirichlet([cfg.root_dirichlet_alpha] * n)
+    if uniforms is None:
+      uniforms = np.random.random(G)
+    hidden = init.hidden_state
+    if self.eng is None:
+      words = hidden[0].numel() * hidden.element_size() // 4
+      self.eng = BatchedMCTS(cfg, G, hidden_words=words, device=self.device)
+    eng = self.eng
+    eng.search(self.network, init.policy_logits.reshape(G, A).float().contiguous(), hidden, legal_mask=legal,
+               noise=noise, noise_frac=cfg.root_exploration_fraction, to_play=to_play)
+    actions = eng.select_action(self.temperature, uniforms, legal)
+    actions = actions.cpu().numpy()
+    root_value = eng.root_value.cpu().numpy()
+    child_visits = eng.child_visits.cpu().numpy()
+    init_value = init.value.reshape(G).double().cpu().numpy()
+    errors = root_value - init_value                                          # actors.py:147
+
+    next_obs, reward, done, result = env.step(actions)
+    finished = []
+    overlap = cfg.num_unroll_steps + cfg.td_steps
+    for i, g in enumerate(self.games):
+      g.errors.append(float(errors[i]))
+      # Game.apply (game.py:75-104)
+      g.steps.append(g.step)
+      g.sum_rewards += int(reward[i])
+      g.step = int(env.elapsed[i])
+      g.history_idx += 1
+      g.observations.append(next_obs[i])
+      g.actions.append(int(actions[i]))
+      g.dones.append(bool(done[i]))
+      g.rewards.append(int(reward[i]))
+      g.to_play_hist.append(g.to_play)
+      if cfg.two_players:
+        g.to_play *= -1
+      # Game.store_search_statistics (game.py:106-115)
+      g.child_visits.append(child_visits[i].tolist())
+      g.root_values.append(float(root_value[i]))
+      g.sum_values += float(root_value[i])
+      g.max_value = max(g.max_value, float(root_value[i]))
+      self.experiences_collected += 1
+      terminal = bool(done[i])  # episode_life is off for the vectorised environments
+      # actors.py:160-169
+      if (g.history_idx - g.previous_collect_to) == cfg.max_history_length or terminal:
+        if not g.dones[g.previous_collect_to - 1]:
+          collect_from = max(0, g.previous_collect_to - overlap)
+        else:
+          collect_from = g.previous_collect_to
+        history = g.slice(collect_from)
+        ignore = overlap if not done[i] else None
+        if self.replay is not None:
+          self.replay.save_history(history, ignore=ignore, terminal=terminal)
+        else:
+          self.saved.append((i, history, ignore, terminal))
+      if terminal or g.step >= cfg.max_steps:
+        finished.append(i)
+        if result[i] >= 0:
+          self.results[int(result[i])] += 1
+    if finished:  # run_selfplay: a new game replaces the finished one (actors.py:94-97)
+      self.games_played += len(finished)
+      for i, o in zip(finished, env.reset(finished)):
+        self.games[i] = _Game(o)
+    return actions, root_value, child_visits, errors, done

@@ -93,3 +93,15 @@ class HashNetwork(object):
     nxt = _splitmix64(state ^ ((a + 1) * _KACT))
     value, reward, logits = self._outputs(nxt)
     return NetworkOutput(value, reward, logits, nxt)
+
+
+class ObsHashNetwork(HashNetwork):
+  """HashNetwork whose root state is a hash of the observation row (for driver-level parity tests):
+  state = sum_i (obs_i + 2) * 5^i over the first 24 entries, exact in int64."""
+
+  def initial_inference(self, observation):
+    obs = torch.as_tensor(observation).to(self.device).reshape(observation.shape[0], -1)
+    n = min(obs.shape[1], 24)
+    w = torch.tensor([5 ** i for i in range(n)], dtype=torch.int64, device=obs.device)
+    state = ((obs[:, :n].to(torch.int64) + 2) * w).sum(dim=1, keepdim=True)
+    return super().initial_inference(state)

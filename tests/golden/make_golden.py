@@ -484,10 +484,98 @@ def gen_muzero():
         rec.reward.flatten().tolist(), "hidden mean", float(rec.hidden_state.mean()))
 
 
+def gen_selfplay():
+  """Self-play of Tic-Tac-Toe: the move body and the history hand-off of Actor.play_game
+  (actors.py:125-176) restated around the reference's Game, TicTacToe, Node, MCTS and
+  Config.select_action (actors.py itself needs ray / gym).  The network is the obs-hash stand-in, the
+  random draws are recorded.  One fixture row per move; one row per history pushed to the replay."""
+  from custom_environments.tic_tac_toe import TicTacToe
+  from model_based_rl_b200.testing import ObsHashNetwork
+  A, S, K, T, MAXH, G = 9, 12, 2, 2, 3, 8
+  cfg = make_config(action_space=A, num_simulations=S, two_players=True, discount=1.0,
+                    known_bounds=[-1, 1], num_unroll_steps=K, td_steps=T, obs_space=(9,))
+  net = ObsHashNetwork(A, 0.8, 0.5, 2.0, 3)
+  engine = ref_mcts.MCTS(cfg)
+  rng = np.random.default_rng(777)
+  fake = _U()
+  real_choice, real_dirichlet = np.random.choice, np.random.dirichlet
+  moves, saves, envs = [], [], []
+  np.random.choice = fake
+  try:
+    for gi in range(G):
+      env = TicTacToe()
+      game = ref_game.Game(env, cfg)
+      temperature = [1.0, 0.5, 0.0, 0.25][gi % 4]
+      mv = 0
+      while not game.terminal:
+        root = ref_mcts.Node(0)
+        obs = np.float32(game.get_observation(-1))
+        init = net.initial_inference(torch.from_numpy(obs).unsqueeze(0))
+        legal = env.legal_actions()
+        root.expand(init, game.to_play, legal)
+        noise = rng.dirichlet([cfg.root_dirichlet_alpha] * len(legal))
+        np.random.dirichlet = lambda alpha, noise=noise: noise.copy()
+        root.add_exploration_noise(cfg.root_dirichlet_alpha, cfg.root_exploration_fraction)
+        np.random.dirichlet = real_dirichlet
+        engine.run(root, net)
+        error = root.value() - init.value.item()
+        game.history.errors.append(error)
+        fake.u = float(rng.random())
+        action = cfg.select_action(root, temperature)
+        game.apply(action)
+        game.store_search_statistics(root)
+        dense = np.zeros(A)
+        dense[:len(legal)] = noise
+        moves.append(dict(game=gi, move=mv, obs=obs, legal=sum(1 << int(a) for a in legal), noise=dense,
+                          u=fake.u, temperature=temperature, action=action, error=error,
+                          root_value=game.history.root_values[-1],
+                          child_visits=np.array(game.history.child_visits[-1]),
+                          reward=game.history.rewards[-1], done=game.history.dones[-1],
+                          to_play=game.history.to_play[-1], next_obs=np.float32(game.history.observations[-1])))
+        save_history = (game.history_idx - game.previous_collect_to) == MAXH
+        if save_history or game.done or game.terminal:
+          overlap = K + T
+          if not game.history.dones[game.previous_collect_to - 1]:
+            collect_from = max(0, game.previous_collect_to - overlap)
+          else:
+            collect_from = game.previous_collect_to
+          h = game.get_history_sequence(collect_from)
+          ignore = overlap if not game.done else None
+          saves.append(dict(game=gi, move=mv, collect_from=collect_from, n=len(h.root_values),
+                            n_obs=len(h.observations), ignore=-1 if ignore is None else ignore,
+                            terminal=game.terminal, actions=list(h.actions), errors=list(h.errors)))
+        mv += 1
+      envs.append(dict(result=game.info["result"], length=game.step))
+  finally:
+    np.random.choice = real_choice
+    np.random.dirichlet = real_dirichlet
+  out = dict(A=np.int32(A), S=np.int32(S), K=np.int32(K), T=np.int32(T), max_history_length=np.int32(MAXH),
+             n_games=np.int32(G), hashnet=np.array([0.8, 0.5, 2.0, 3.0]))
+  for k in ("game", "move", "legal", "action"):
+    out["m_" + k] = np.array([m[k] for m in moves], np.int64)
+  for k in ("u", "temperature", "error", "root_value", "reward"):
+    out["m_" + k] = np.array([m[k] for m in moves], np.float64)
+  out["m_done"] = np.array([m["done"] for m in moves], bool)
+  out["m_to_play"] = np.array([m["to_play"] for m in moves], np.int8)
+  for k in ("obs", "noise", "child_visits", "next_obs"):
+    out["m_" + k] = np.stack([m[k] for m in moves])
+  for k in ("game", "move", "collect_from", "n", "n_obs", "ignore"):
+    out["s_" + k] = np.array([s_[k] for s_ in saves], np.int64)
+  out["s_terminal"] = np.array([s_["terminal"] for s_ in saves], bool)
+  out["s_actions"] = np.array([";".join(map(str, s_["actions"])) for s_ in saves])
+  out["g_result"] = np.array([e["result"] for e in envs])
+  out["g_length"] = np.array([e["length"] for e in envs], np.int32)
+  np.savez_compressed(os.path.join(HERE, "selfplay_ttt.npz"), **out)
+  print("selfplay: moves", len(moves), "saves", len(saves), "results", [e["result"] for e in envs])
+
+
 if __name__ == "__main__":
   torch.set_num_threads(1)
   if len(sys.argv) > 1 and sys.argv[1] == "muzero":
     gen_muzero()
+    sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == "selfplay":
+    gen_selfplay()
     sys.exit(0)
   rng = np.random.default_rng(20261017)
   gen_search(rng)
@@ -496,4 +584,5 @@ if __name__ == "__main__":
   gen_transforms(rng)
   gen_fcnet(rng)
   gen_muzero()
+  gen_selfplay()
   print("python", sys.version.split()[0], "numpy", np.__version__, "torch", torch.__version__)

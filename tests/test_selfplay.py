@@ -1,0 +1,147 @@
+"""Batched self-play driver (model_based_rl_b200/selfplay.py, environments.py) against a fixture
+produced by the reference's own Game / TicTacToe / MCTS / select_action (tests/golden/make_golden.py,
+gen_selfplay)."""
+import types
+
+import numpy as np
+import pytest
+
+from helpers import load
+
+
+def _moves_of(g, game):
+  idx = np.nonzero(g["m_game"] == game)[0]
+  return idx[np.argsort(g["m_move"][idx])]
+
+
+def test_vector_tictactoe_matches_reference_env():
+  """Host environment: observations, rewards, terminal flags, legal moves and results."""
+  from model_based_rl_b200.environments import RESULTS, VectorTicTacToe
+  g = load("selfplay_ttt")
+  n_games = int(g["n_games"])
+  env = VectorTicTacToe(n_games)
+  first = env.reset()
+  alive = np.ones(n_games, bool)
+  cursor = [list(_moves_of(g, i)) for i in range(n_games)]
+  for i in range(n_games):
+    assert np.array_equal(first[i], g["m_obs"][cursor[i][0]])
+  while alive.any():
+    rows = [cursor[i][0] if alive[i] else None for i in range(n_games)]
+    legal = env.legal_mask()
+    actions = np.zeros(n_games, np.int64)
+    for i, r in enumerate(rows):
+      if r is None:  # a finished slot keeps playing legal filler moves on a fresh board
+        actions[i] = int(env.legal_actions(i)[0])
+      else:
+        assert int(legal[i]) == int(g["m_legal"][r])
+        actions[i] = int(g["m_action"][r])
+    obs, reward, done, result = env.step(actions)
+    for i, r in enumerate(rows):
+      if r is None:
+        if done[i]:
+          env.reset([i])
+        continue
+      assert bool(done[i]) == bool(g["m_done"][r]) and int(reward[i]) == int(g["m_reward"][r])
+      cursor[i].pop(0)
+      if done[i]:
+        assert RESULTS[int(result[i])] == str(g["g_result"][i])
+        assert int(env.elapsed[i]) == int(g["g_length"][i])
+        alive[i] = False
+        env.reset([i])
+      else:
+        assert np.array_equal(obs[i].astype(np.float32), g["m_next_obs"][r])
+
+
+@pytest.mark.gpu
+def test_batched_actor_replays_reference_selfplay():
+  """Eight games in lock step on the GPU reproduce the reference's sequential games move for move:
+  actions, root values, child-visit distributions, priority seeds, and the history slices handed to
+  the replay buffer (chunking at max_history_length, overlap, ignore, terminal)."""
+  import torch
+  from model_based_rl_b200.environments import VectorTicTacToe
+  from model_based_rl_b200.selfplay import BatchedActor
+  from model_based_rl_b200.testing import ObsHashNetwork
+  g = load("selfplay_ttt")
+  n_games, A, S = int(g["n_games"]), int(g["A"]), int(g["S"])
+  hv = g["hashnet"]
+  cfg = types.SimpleNamespace(
+      num_simulations=S, action_space=A, two_players=True, discount=1.0, pb_c_base=19652, pb_c_init=1.25,
+      init_value_score=0.0, known_bounds=[-1, 1], root_dirichlet_alpha=0.25, root_exploration_fraction=0.25,
+      num_unroll_steps=int(g["K"]), td_steps=int(g["T"]), max_history_length=int(g["max_history_length"]),
+      max_steps=10 ** 9)
+  net = ObsHashNetwork(A, float(hv[0]), float(hv[1]), float(hv[2]), int(hv[3]), device="cuda")
+  temps = np.array([[1.0, 0.5, 0.0, 0.25][i % 4] for i in range(n_games)])
+  actor = BatchedActor(cfg, net, VectorTicTacToe(n_games), device="cuda", temperature=temps)
+  cursor = [list(_moves_of(g, i)) for i in range(n_games)]
+  rng = np.random.default_rng(0)
+  checked = 0
+  while any(cursor):
+    noise = rng.dirichlet([0.25] * A, size=n_games)
+    u = rng.random(n_games)
+    rows = [c[0] if c else None for c in cursor]
+    for i, r in enumerate(rows):
+      if r is not None:
+        noise[i], u[i] = g["m_noise"][r], g["m_u"][r]
+    actions, root_value, child_visits, errors, done = actor.play_move(noise, u)
+    for i, r in enumerate(rows):
+      if r is None:
+        continue
+      assert int(actions[i]) == int(g["m_action"][r]), (i, r)
+      assert root_value[i] == g["m_root_value"][r]                      # bit-exact search
+      assert np.array_equal(child_visits[i], g["m_child_visits"][r])
+      assert errors[i] == g["m_error"][r]
+      assert bool(done[i]) == bool(g["m_done"][r])
+      cursor[i].pop(0)
+      checked += 1
+  assert checked == len(g["m_game"])
+  # history hand-off: the first game of every slot, in order
+  for i in range(n_games):
+    want = np.nonzero(g["s_game"] == i)[0]
+    got = [s for s in actor.saved if s[0] == i][:len(want)]
+    assert len(got) == len(want)
+    for (_, h, ignore, terminal), w in zip(got, want):
+      assert len(h.root_values) == int(g["s_n"][w]) and len(h.observations) == int(g["s_n_obs"][w])
+      assert (-1 if ignore is None else ignore) == int(g["s_ignore"][w])
+      assert bool(terminal) == bool(g["s_terminal"][w])
+      assert ";".join(map(str, h.actions)) == str(g["s_actions"][w])
+  assert actor.games_played >= n_games and sum(actor.results.values()) >= n_games
+
+
+@pytest.mark.gpu
+def test_actor_feeds_prioritized_replay():
+  """End to end: batched self-play -> PrioritizedReplay (device window + sum-tree) -> sampled batch
+  whose targets match the oracle's insert_target for the history each row came from."""
+  import oracle
+  from model_based_rl_b200.environments import VectorTicTacToe
+  from model_based_rl_b200.replay_buffer import PrioritizedReplay
+  from model_based_rl_b200.selfplay import BatchedActor
+  from model_based_rl_b200.testing import ObsHashNetwork
+  A, G = 9, 64
+  cfg = types.SimpleNamespace(
+      num_simulations=10, action_space=A, two_players=True, discount=1.0, pb_c_base=19652, pb_c_init=1.25,
+      init_value_score=0.0, known_bounds=[-1, 1], root_dirichlet_alpha=0.25, root_exploration_fraction=0.25,
+      num_unroll_steps=3, td_steps=4, max_history_length=500, max_steps=10 ** 9, batch_size=32,
+      beta_increment_per_sampling=0.001, epsilon=0.01, alpha=1.0, beta=0.4, obs_space=(9,), window_size=2048,
+      window_step=None, seed=3)
+  rb = PrioritizedReplay(cfg)
+  kept = []
+  real_save = rb.save_history
+  rb.save_history = lambda h, ignore=None, terminal=False: (kept.append(h), real_save(h, ignore, terminal))[1]
+  net = ObsHashNetwork(A, 0.8, 0.5, 2.0, 3, device="cuda")
+  actor = BatchedActor(cfg, net, VectorTicTacToe(G), replay_buffer=rb, device="cuda")
+  np.random.seed(1)
+  for _ in range(12):
+    actor.play_move()
+  assert actor.games_played >= G and rb.size() == sum(len(h.root_values) for h in kept)
+  (obs, actions, (t_r, t_v, t_p)), idxs, is_w = rb.sample_batch()
+  assert obs.shape == (32, 9) and t_p.shape == (32, 4, A) and len(actions) == 32 and is_w.max() == 1.0
+  for b in range(32):  # locate the (history, step) of the row through its slot and check the targets
+    slot = idxs[b] - (2048 - 1)
+    h = kept[int(rb.index.slot_chunk[slot])]
+    steps = [s for s in range(len(h.root_values)) if np.array_equal(np.float32(h.observations[s]), obs[b])]
+    ok = False
+    for step in steps:
+      r, v, p = oracle.insert_target(np.array(h.rewards, np.float64), np.array(h.to_play, np.int8),
+                                     np.array(h.root_values), np.array(h.child_visits), 3, 4, 1.0, step)
+      ok |= bool(np.array_equal(t_r[b], r) and np.array_equal(t_p[b], p) and np.allclose(t_v[b], v, rtol=1e-5, atol=1e-6))
+    assert ok, b
