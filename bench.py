@@ -54,6 +54,7 @@ def parse():
   p.add_argument("--precision", choices=["bf16", "f32"], default="bf16",
                  help="network kernel: bf16 tcgen05 tensor cores (default) or float32 CUDA cores")
   p.add_argument("--no-conv", action="store_true", help="skip the C5 MuZeroNetwork section")
+  p.add_argument("--no-sweep", action="store_true", help="skip the larger-batch throughput probe")
   p.add_argument("--conv-games", type=int, default=4096, help="C5: concurrent games per GPU")
   p.add_argument("--ref-moves-per-step", type=int, default=2,
                  help="reference arm: moves each worker plays per step")
@@ -328,6 +329,21 @@ def run_b200(args):
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
   ms_total, ms_e2e = t.tolist()
+  sweep = None
+  if rank == 0 and world == 1 and not args.no_sweep:
+    # the same move at larger batches: at 4096 games a step is bound by the latency of the two
+    # per-simulation kernels in series; the kernels' own throughput shows when more games are in flight
+    sweep = {}
+    for g2 in (4 * G,):
+      fs2 = FCSearch(cfg, net, g2, use_graph=not args.no_graph, num_streams=args.streams)
+      o2, n2, u2, t2 = synthetic_inputs(args, rank, g2)
+      fs2.search_host(pin(o2), pin(n2), pin(u2), pin(t2))
+      for _ in range(args.warmup):
+        fs2.run()
+      torch.cuda.synchronize()
+      ms2 = timed(fs2.run, 5)
+      sweep[str(g2)] = {"expansions_per_s": g2 * S * 5 / (ms2 * 1e-3), "ms_per_step": ms2 / 5}
+      del fs2
   targets = bench_targets(torch, _lib, dev) if rank == 0 else None
   conv = bench_conv(args, torch, _lib, dev) if rank == 0 and not args.no_conv else None
 
@@ -368,7 +384,7 @@ def run_b200(args):
         "gpu_launches": fs.launches_per_move * args.steps,
         "clocks": clock_info, "roofline": dominant, "roofline_all": [roof_tree, roof_fc],
         "kernel_share": kern, "cuda_graph": not args.no_graph, "streams": len(fs.lanes),
-        "targets": targets, "conv": conv,
+        "games_sweep": sweep, "targets": targets, "conv": conv,
     }
     if cpu_baseline is not None:
       line["cpu_baseline"] = cpu_baseline
