@@ -402,8 +402,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     // ===== producer: stream the 16 weight chunks through the ring =====
     if (lane == 0) {
       const size_t base = chunk_offset(c0, k1);
-      for (int c = 0; c < nch; ++c) {
-        const int st = c % STAGES, n = c / STAGES;
+      int st = 0, n = 0;  // ring slot and round, advanced incrementally (STAGES is a run-time value)
+      for (int c = 0; c < nch; ++c, st = (st + 1 == STAGES ? 0 : st + 1), n += (st == 0)) {
         const int cc = canon(c);
         const ChunkGeom g = chunk_geom(cc, k1);
         mbar_wait(&w_empty[st], (n & 1) ^ 1);
@@ -421,10 +421,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     const uint32_t idesc1 = make_idesc(CHUNK);
     constexpr uint64_t KSTEP = (uint64_t)((2 * (CHUNK / 8) * 128) >> 4);  // two K core-matrix columns
 #pragma unroll 1
-    for (int c = 0; c < nch; ++c) {
-      const int st = c % STAGES, cc = canon(c);
+    int st = 0, round = 0;
+    for (int c = 0; c < nch; ++c, st = (st + 1 == STAGES ? 0 : st + 1), round += (st == 0)) {
+      const int cc = canon(c);
       if (lane == 0) TC_STAMP(64 + 8 * c + 0);
-      mbar_wait(&w_full[st], (c / STAGES) & 1);
+      mbar_wait(&w_full[st], round & 1);
       if (c == 0) mbar_wait(a1_ready, 0);
       if (c == c_mid) mbar_wait(a3_ready, 0);
       mbar_wait(&d1_empty[c & 1], ((c >> 1) & 1) ^ 1);
@@ -455,8 +456,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     const uint32_t w_addr = smem_u32(sW);
     const uint32_t w1_bytes_dyn = CHUNK * k1 * 2, w1_bytes_pred = CHUNK * K3 * 2;
 #pragma unroll 1
-    for (int c = 0; c < nch; ++c) {
-      const int st = c % STAGES, cc = canon(c), head = cc >> 2;
+    int st = 0;
+    for (int c = 0; c < nch; ++c, st = (st + 1 == STAGES ? 0 : st + 1)) {
+      const int cc = canon(c), head = cc >> 2;
       mbar_wait(&a2_full[c & 1], (c >> 1) & 1);
       tc_fence_after();
       if (lane == 0) TC_STAMP(64 + 8 * c + 4);
