@@ -223,6 +223,7 @@ int mz_fc_recurrent_f32(const mz_fc_weights* w, int32_t batch, const float* hidd
 int64_t mz_fc_tc_packed_bytes(int32_t num_actions);
 /* Diagnostics: when set to a device buffer of >= 512 int64, CTA 0 of every following
  * mz_fc_recurrent_tc launch stores clock64() stamps of its pipeline phases there (NULL disables). */
+int mz_debug_set_tc_trace_block(int32_t block); /* which CTA writes the stamps (default 0) */
 int mz_debug_set_tc_trace(int64_t* device_buffer);
 int32_t mz_fc_tc_tail_floats(void);
 int mz_fc_tc_pack(const mz_fc_weights* w, void* packed, float* tail, void* stream);

@@ -248,12 +248,13 @@ struct TcParams {
   // value heads, rank 1 the transition and policy heads (8 chunks each instead of 16) and hands h'
   // to rank 0 through distributed shared memory
   int split;
+  int trace_block;   // which CTA writes the diagnostic stamps
 };
 
 // trace slots: [0,64) epilogue thread (row 0), [64,192) MMA thread, [192,224) producer
 #define TC_STAMP(slot)                                              \
   do {                                                              \
-    if (p.trace && blockIdx.x == 0) p.trace[(slot)] = clock64();    \
+    if (p.trace && blockIdx.x == p.trace_block) p.trace[(slot)] = clock64();    \
   } while (0)
 
 // softmax(logits + bias) . support, then h^-1, all in registers (one thread per row)
@@ -634,20 +635,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       {
         // h' as the bf16 A operand of the prediction layer: this row of the canonical K-major image,
         // in this CTA's shared memory and -- in a split pair -- in the peer's as well
-        const uint32_t a3 = smem_u32(sA3);
-        const uint32_t a3_peer = split ? map_to_cta(a3, 0) : 0u;
+        uint4 q[K3 / 8];
 #pragma unroll
         for (int kb = 0; kb < K3 / 8; ++kb) {
-          const uint4 q = make_uint4(pack_bf16(hbuf[8 * kb], hbuf[8 * kb + 1]), pack_bf16(hbuf[8 * kb + 2], hbuf[8 * kb + 3]),
-                                     pack_bf16(hbuf[8 * kb + 4], hbuf[8 * kb + 5]), pack_bf16(hbuf[8 * kb + 6], hbuf[8 * kb + 7]));
-          const uint32_t off = (uint32_t)canon_off(row, 8 * kb, ROWS);
-          *reinterpret_cast<uint4*>(sA3 + off) = q;
-          if (split) st_cluster_v4(a3_peer + off, q);
+          q[kb] = make_uint4(pack_bf16(hbuf[8 * kb], hbuf[8 * kb + 1]), pack_bf16(hbuf[8 * kb + 2], hbuf[8 * kb + 3]),
+                             pack_bf16(hbuf[8 * kb + 4], hbuf[8 * kb + 5]), pack_bf16(hbuf[8 * kb + 6], hbuf[8 * kb + 7]));
+          *reinterpret_cast<uint4*>(sA3 + canon_off(row, 8 * kb, ROWS)) = q[kb];
+        }
+        // release the local prediction layer first, then ship the same rows to the peer
+        fence_async_smem();
+        mbar_arrive(a3_ready);
+        if (split) {
+          const uint32_t a3_peer = map_to_cta(smem_u32(sA3), 0);
+#pragma unroll
+          for (int kb = 0; kb < K3 / 8; ++kb) st_cluster_v4(a3_peer + (uint32_t)canon_off(row, 8 * kb, ROWS), q[kb]);
+          mbar_arrive_remote(map_to_cta(smem_u32(a3_remote), 0));
         }
       }
-      fence_async_smem();
-      mbar_arrive(a3_ready);
-      if (split) mbar_arrive_remote(map_to_cta(smem_u32(a3_remote), 0));
       if (stamp) TC_STAMP(41);
       // after the hand-off: h' goes to the pool through shared memory so that every store
       // instruction writes one contiguous 200-byte row (a per-thread row store touches 32 lines)
@@ -752,6 +756,7 @@ __global__ void fc_tc_pack_kernel(mz_fc_weights w, int k1, int chunk0, uint8_t* 
 int k1_for(int A) { return (H + A + 1 + 15) / 16 * 16; }  // state + one-hot + bias column
 
 long long* g_tc_trace = nullptr;
+int g_tc_trace_block = 0;
 int g_tc_split = 1;  // recurrent kernel: two-CTA clusters, heads split between the CTAs
 
 int k1_obs(int obs_dim) { return (obs_dim + 1 + 15) / 16 * 16; }  // observation + bias column
@@ -808,6 +813,11 @@ extern "C" {
 
 int mz_fc_tc_set_split(int32_t enable) {
   g_tc_split = enable ? 1 : 0;
+  return MZ_OK;
+}
+
+int mz_debug_set_tc_trace_block(int32_t block) {
+  g_tc_trace_block = block;
   return MZ_OK;
 }
 
@@ -869,6 +879,7 @@ int mz_fc_recurrent_tc(const mz_fc_weights* w, const void* packed, const float* 
   p.obs = nullptr;
   p.obs_dim = 0;
   p.split = g_tc_split;
+  p.trace_block = g_tc_trace_block;
   return launch_tc(p, stream);
 }
 
@@ -922,6 +933,7 @@ int mz_fc_initial_tc(const mz_fc_weights* w, const void* packed, const float* ta
   p.obs = obs;
   p.obs_dim = w->obs_dim;
   p.split = 0;
+  p.trace_block = 0;
   return launch_tc(p, stream);
 }
 

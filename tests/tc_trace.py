@@ -12,9 +12,12 @@ lib = _lib.load()
 trace = torch.zeros(512, dtype=torch.int64, device="cuda")
 h = torch.rand(B, 50, device="cuda"); a = torch.randint(0, A, (B,), device="cuda", dtype=torch.int32)
 for _ in range(3): net.recurrent_inference(h, a)
+BLOCK = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+lib.mz_debug_set_tc_trace_block(BLOCK)
 lib.mz_debug_set_tc_trace(_lib.ptr(trace))
 net.recurrent_inference(h, a); torch.cuda.synchronize()
 lib.mz_debug_set_tc_trace(None)
+print("trace of CTA", BLOCK)
 t = trace.cpu().numpy(); t0 = t[0]
 rel = lambda i: (t[i] - t0) if t[i] else -1
 print("epilogue: A1 ready", rel(1))
