@@ -345,6 +345,7 @@ def run_b200(args):
       sweep[str(g2)] = {"expansions_per_s": g2 * S * 5 / (ms2 * 1e-3), "ms_per_step": ms2 / 5}
       del fs2
   targets = bench_targets(torch, _lib, dev) if rank == 0 else None
+  learner = bench_learner(torch, _lib, dev, world, barrier)  # every rank: the step all-reduces at N > 1
   conv = bench_conv(args, torch, _lib, dev) if rank == 0 and not args.no_conv else None
 
   if rank == 0:
@@ -384,7 +385,8 @@ def run_b200(args):
         "gpu_launches": fs.launches_per_move * args.steps,
         "clocks": clock_info, "roofline": dominant, "roofline_all": [roof_tree, roof_fc],
         "kernel_share": kern, "cuda_graph": not args.no_graph, "streams": len(fs.lanes),
-        "games_sweep": sweep, "targets": targets, "conv": conv,
+        "games_sweep": sweep, "targets": targets, "learner": learner,
+        "conv": conv,
     }
     if cpu_baseline is not None:
       line["cpu_baseline"] = cpu_baseline
@@ -540,6 +542,73 @@ def bench_targets(torch, _lib, dev):
           "workload": "C3 Breakout-ram: window 200000, B=512, K=5, td=10, A=4, obs 128 u8, supports fused",
           "algorithmic_bytes_per_sample": bytes_per_sample,
           "achieved_gbs": B * bytes_per_sample / sec / 1e9}
+
+
+def bench_learner(torch, _lib, dev, world, barrier):
+  """Learner.update_weights on the C3 shape: B=512, K=5, A=4, 128-float
+  observations, AdamW; device-resident synthetic batch.  Reports whole steps/s (network forward +
+  backward on cuBLAS, the fused loss, the optimiser, the gradient all-reduce at N > 1; max over
+  ranks) and the fused loss kernel alone against HBM."""
+  import types
+  import torch.distributed as dist
+  from model_based_rl_b200 import learners
+  B, K, A, E = 512, 5, 4, 128
+  cfg = types.SimpleNamespace(value_support=[-15, 15], reward_support=[-15, 15], no_support=False,
+                              no_target_transform=False, num_unroll_steps=K, optimizer="AdamW", lr_init=0.0008,
+                              momentum=0.9, weight_decay=1e-4, clip_grad=0, lr_scheduler=None, norm_obs=False)
+  g = torch.Generator(device=dev).manual_seed(7)
+  r = lambda *shape: torch.rand(*shape, device=dev, generator=g)
+  pol = r(B, K + 1, A)
+  batch = ((r(B, E), torch.randint(0, A, (B, K), device=dev, generator=g),
+            ((r(B, K + 1) < 0.1).float(), 4 * torch.randn(B, K + 1, device=dev, generator=g),
+             pol / pol.sum(-1, keepdim=True))), None, r(B).double())
+  torch.manual_seed(11)
+  net = learners.FCNetworkTrain(E, A, dev, cfg)
+  lr = learners.Learner(cfg, net)
+  lr.send_weights()
+  for _ in range(5):
+    lr.update_weights(batch)
+  barrier()
+  steps = 30
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(steps):
+    lr.update_weights(batch)
+  b.record()
+  torch.cuda.synchronize()
+  t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_step = float(t.item()) / steps
+  # the loss kernel alone
+  V = 31
+  vl, rl, pl = torch.randn(K + 1, B, V, device=dev), torch.randn(K, B, V, device=dev), torch.randn(K + 1, B, A, device=dev)
+  (_, _, (t_r, t_v, t_p)), _, w = batch
+  outs = [torch.empty_like(vl), torch.empty_like(rl), torch.empty_like(pl), torch.empty(3, B, dtype=torch.float64, device=dev),
+          torch.empty(3, dtype=torch.float64, device=dev), torch.empty(B, device=dev)]
+  c = _lib.LossCfg(B, K, A, -15, 15, -15, 15, 0)
+  lib, stream = _lib.load(), _lib.current_stream()
+
+  def launch():
+    _lib.check(lib.mz_unroll_loss(c, _lib.ptr(vl), _lib.ptr(rl), _lib.ptr(pl), _lib.ptr(t_v.contiguous()),
+                                  _lib.ptr(t_r), _lib.ptr(t_p), _lib.ptr(w), *[_lib.ptr(o) for o in outs], stream),
+               "mz_unroll_loss")
+  for _ in range(5):
+    launch()
+  torch.cuda.synchronize()
+  a.record()
+  for _ in range(100):
+    launch()
+  b.record()
+  torch.cuda.synchronize()
+  us = a.elapsed_time(b) * 10.0
+  logit_bytes = 4 * (vl.numel() + rl.numel() + pl.numel())
+  alg = 2 * logit_bytes + 4 * (2 * B * (K + 1) + t_p.numel()) + 8 * B + 8 * 3 * B + 4 * B
+  return {"steps_per_s": 1e3 / ms_step, "samples_per_s": world * B * 1e3 / ms_step, "ms_per_step": ms_step,
+          "workload": "C3 learner step: B=512 per GPU, K=5, A=4, obs 128 f32, FCNetwork, AdamW, f32 GEMMs (cuBLAS) + "
+                      "fused unroll loss; gradient all-reduce over %d rank(s)" % world,
+          "loss_kernel": {"us_per_launch": us, "algorithmic_bytes": alg, "achieved_gbs": alg / us / 1e3,
+                          "launches": 2}}
 
 
 def main():

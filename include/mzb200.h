@@ -387,6 +387,32 @@ int mz_conv_head(int32_t games, const float* hidden, int32_t ldh, const float* w
                  int32_t outs, int32_t to_scalar, int32_t support_min, int32_t no_target_transform,
                  float* out, int32_t ldo, void* stream);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Learner unroll loss (Learner.update_weights, learners.py:182-213; utils.py:53-56)              */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct mz_loss_cfg {
+  int32_t batch;            /* B */
+  int32_t num_unroll_steps; /* K (1..31) */
+  int32_t num_actions;      /* A */
+  int32_t value_min, value_max, reward_min, reward_max; /* supports (config.py:93-94) */
+  int32_t no_target_transform;                          /* skip h(x) (learners.py:185-187) */
+} mz_loss_cfg;
+/* One fused pass over the logits of all unroll steps (train-mode network outputs):
+ *   value_logits [K+1][B][V], reward_logits [K][B][R] (steps 1..K), policy_logits [K+1][B][A] f32;
+ *   t_values / t_rewards [B][K+1] f32 raw scalars as sample_batch returns them (h(x), config.py:51-54,
+ *   and the two-hot projection, config.py:56-68, happen inside), t_policies [B][K+1][A] f32,
+ *   is_weights [B] f64 (NULL = ones).
+ * Outputs: losses [3] f64 = (is_weights * loss).mean() for reward, value, policy (learners.py:208-210);
+ *   row_losses [3][B] f64 workspace (the weighted per-row losses); new_errors [B] f32 =
+ *   inverse_value_transform(value_logits[0]) - t_values[:, 0] (learners.py:182-183; may be NULL);
+ *   d_*_logits: gradient of (reward + value + policy loss) * 1/K (the hook of learners.py:213) with
+ *   respect to each logit, same shapes as the inputs (each may be NULL). */
+int mz_unroll_loss(const mz_loss_cfg* c, const float* value_logits, const float* reward_logits,
+                   const float* policy_logits, const float* t_values, const float* t_rewards,
+                   const float* t_policies, const double* is_weights, float* d_value_logits,
+                   float* d_reward_logits, float* d_policy_logits, double* row_losses, double* losses,
+                   float* new_errors, void* stream);
+
 /* Diagnostics: compares the constant-divisor division used by the descent's MinMax normalisation
  * with IEEE division on blocks*256*per_thread pseudo-random operand pairs; adds the number of
  * differing results to *mismatches and the number of pairs checked to *tested (device u64). */

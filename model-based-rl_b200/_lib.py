@@ -63,6 +63,13 @@ class TargetCfg(C.Structure):
               ("obs_range", C.c_void_p)]
 
 
+class LossCfg(C.Structure):
+  """struct mz_loss_cfg"""
+  _fields_ = [("batch", C.c_int32), ("num_unroll_steps", C.c_int32), ("num_actions", C.c_int32),
+              ("value_min", C.c_int32), ("value_max", C.c_int32), ("reward_min", C.c_int32),
+              ("reward_max", C.c_int32), ("no_target_transform", C.c_int32)]
+
+
 _V = C.c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)
@@ -112,6 +119,7 @@ _SIGNATURES = {
     "mz_conv_fc_tc": (C.c_int, [C.c_int32, _V, _V, _V, C.c_int32, C.c_int32, _V, C.c_int32, _V]),
     "mz_conv_head": (C.c_int, [C.c_int32, _V, C.c_int32, _V, _V, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, _V, C.c_int32, _V]),
+    "mz_unroll_loss": (C.c_int, [C.POINTER(LossCfg), _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "mz_debug_div_check": (C.c_int, [C.c_uint64, C.c_int32, C.c_int32, _V, _V, _V]),
     "mz_set_programmatic_launch": (C.c_int, [C.c_int32]),
     "mz_version": (C.c_char_p, []),

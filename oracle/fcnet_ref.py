@@ -51,7 +51,9 @@ class FCNetworkRef(nn.Module):
     self.eval()
 
   def _predict(self, h):
-    value = support_to_scalar(self.value_head(h), *self.vs, self.no_tt)
+    value = self.value_head(h)
+    if not self.training:  # train mode keeps the support logits (networks.py:151-154)
+      value = support_to_scalar(value, *self.vs, self.no_tt)
     return self.policy_head(h), value
 
   def initial_inference(self, observation):
@@ -63,7 +65,9 @@ class FCNetworkRef(nn.Module):
     a = torch.as_tensor(action, dtype=torch.int64).reshape(-1, 1)
     onehot = torch.zeros((a.shape[0], self.action_space), dtype=torch.float32).scatter_(1, a, 1.0)
     x = torch.cat((hidden_state, onehot), dim=1)
-    reward = support_to_scalar(self.reward_head(x), *self.rs, self.no_tt)
+    reward = self.reward_head(x)
+    if not self.training:
+      reward = support_to_scalar(reward, *self.rs, self.no_tt)
     h = F.relu(self.LN(self.transition_head(x)))
     logits, value = self._predict(h)
     return NetworkOutput(value, reward, logits, h)

@@ -569,6 +569,119 @@ def gen_selfplay():
   print("selfplay: moves", len(moves), "saves", len(saves), "results", [e["result"] for e in envs])
 
 
+# --------------------------------------------------------------------------------------------
+# learner step (learners.py:164-230)
+# --------------------------------------------------------------------------------------------
+LEARNER_CASES = {
+    # name: (obs_dim, A, B, K, optimizer, clip_grad, no_target_transform)
+    "breakout": (128, 4, 48, 5, "RMSprop", 0, False),
+    "ttt": (9, 9, 16, 3, "AdamW", 5, False),
+    "lunar_raw": (8, 4, 24, 5, "SGD", 0, True),
+}
+
+
+def reference_update_weights(net, cfg, optimizer, batch, clip_grad):
+  """The body of Learner.update_weights (learners.py:164-230) around the reference's FCNetwork and
+  Config; the two loss closures are utils.get_loss_functions' (utils.py:53-56; utils.py needs gym)."""
+  def ce(logits, target):
+    return (-target * torch.nn.LogSoftmax(dim=1)(logits)).sum(1)
+
+  (observations, actions, targets), idxs, is_weights = batch
+  target_rewards, target_values, target_policies = targets
+  observations = torch.from_numpy(observations)
+  value, reward, policy_logits, hidden_state = net.initial_inference(observations)
+  with torch.no_grad():
+    target_policies = torch.from_numpy(target_policies)
+    target_values = torch.from_numpy(target_values)
+    target_rewards = torch.from_numpy(target_rewards)
+    is_weights = torch.from_numpy(is_weights)
+    init_value = cfg.inverse_value_transform(value)
+    new_errors = (init_value.squeeze() - target_values[:, 0]).cpu().numpy()
+    if not cfg.no_target_transform:
+      target_values = cfg.scalar_transform(target_values)
+      target_rewards = cfg.scalar_transform(target_rewards)
+    target_values = cfg.value_phi(target_values)
+    target_rewards = cfg.reward_phi(target_rewards)
+  reward_loss = 0
+  value_loss = ce(value.squeeze(), target_values[:, 0])
+  policy_loss = ce(policy_logits.squeeze(), target_policies[:, 0])
+  for i, action in enumerate(zip(*actions), 1):
+    value, reward, policy_logits, hidden_state = net.recurrent_inference(hidden_state, action)
+    hidden_state.register_hook(lambda grad: grad * 0.5)
+    reward_loss += ce(reward.squeeze(), target_rewards[:, i])
+    value_loss += ce(value.squeeze(), target_values[:, i])
+    policy_loss += ce(policy_logits.squeeze(), target_policies[:, i])
+  reward_loss = (is_weights * reward_loss).mean()
+  value_loss = (is_weights * value_loss).mean()
+  policy_loss = (is_weights * policy_loss).mean()
+  full = reward_loss + value_loss + policy_loss
+  full.register_hook(lambda grad: grad * (1 / cfg.num_unroll_steps))
+  optimizer.zero_grad()
+  full.backward()
+  grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+  if clip_grad:
+    torch.nn.utils.clip_grad_norm_(net.parameters(), clip_grad)
+  optimizer.step()
+  return (reward_loss.item(), value_loss.item(), policy_loss.item()), new_errors, grads
+
+
+def gen_learner():
+  """Two consecutive Learner.update_weights steps per case; optimisers as utils.get_optimizer
+  (utils.py:72-83) with the reference's default hyper-parameters (config.py:183-188)."""
+  for name, (obs_dim, A, B, K, opt_name, clip, no_tt) in LEARNER_CASES.items():
+    rng = np.random.default_rng({"breakout": 1, "ttt": 2, "lunar_raw": 3}[name])
+    torch.manual_seed(4321)
+    cfg = make_config(action_space=A, num_unroll_steps=K, batch_size=B, no_target_transform=no_tt)
+    net = ref_networks.FCNetwork(obs_dim, A, torch.device("cpu"), cfg)
+    with torch.no_grad():
+      net.LN.weight.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, size=50).astype(np.float32)))
+      net.LN.bias.copy_(torch.from_numpy(rng.normal(0, 0.1, size=50).astype(np.float32)))
+    net.train()
+    lr, mom, wd = 0.0008, 0.9, 1e-4
+    if opt_name == "RMSprop":
+      opt = torch.optim.RMSprop(net.parameters(), lr=lr, momentum=mom, eps=0.01, weight_decay=wd)
+    elif opt_name == "AdamW":
+      opt = torch.optim.AdamW(net.parameters(), lr=lr, weight_decay=wd, eps=0.00015)
+    else:
+      opt = torch.optim.SGD(net.parameters(), lr=lr, momentum=mom, weight_decay=wd)
+    save = {"w0_" + k: v.numpy().copy() for k, v in net.state_dict().items()}
+    save.update(obs_dim=np.int32(obs_dim), action_space=np.int32(A), batch=np.int32(B), K=np.int32(K),
+                optimizer=np.array(opt_name), clip_grad=np.int32(clip), no_target_transform=np.int32(no_tt),
+                lr=np.float64(lr), momentum=np.float64(mom), weight_decay=np.float64(wd))
+    for step in range(2):
+      obs = rng.normal(size=(B, obs_dim)).astype(np.float32)
+      actions = [[int(a) for a in rng.integers(0, A, size=K)] for _ in range(B)]
+      t_values = (rng.normal(0, 6, size=(B, K + 1)) * (rng.random((B, K + 1)) < 0.9)).astype(np.float32)
+      t_values[0, 0], t_values[1, 1], t_values[2, 2] = 40.0, -3.0, 2.0  # clamp + integers
+      t_rewards = np.sign(rng.normal(size=(B, K + 1)) * (rng.random((B, K + 1)) < 0.3)).astype(np.float32)
+      t_rewards[3, 1] = 0.37
+      pol = rng.random((B, K + 1, A)) ** 3
+      pol /= pol.sum(-1, keepdims=True)
+      past_end = rng.random((B, K + 1)) < 0.15  # positions past the end of the episode: zeros
+      pol[past_end] = 0.0
+      t_policies = pol.astype(np.float32)
+      is_w = rng.uniform(0.05, 1.0, size=B)
+      is_w /= is_w.max()
+      batch = ((obs, actions, (t_rewards.copy(), t_values.copy(), t_policies.copy())), None, is_w)
+      losses, errs, grads = reference_update_weights(net, cfg, opt, batch, clip)
+      save.update({"s%d_obs" % step: obs, "s%d_actions" % step: np.array(actions, np.int32),
+                   "s%d_t_values" % step: t_values, "s%d_t_rewards" % step: t_rewards,
+                   "s%d_t_policies" % step: t_policies, "s%d_is_weights" % step: is_w,
+                   "s%d_losses" % step: np.array(losses, np.float64), "s%d_new_errors" % step: errs})
+      for k, g in grads.items():
+        g = g.numpy()
+        save["s%d_gnorm_%s" % (step, k)] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        if g.size <= 2048:
+          save["s%d_g_%s" % (step, k)] = g
+        else:
+          save["s%d_g_%s" % (step, k)] = g.reshape(-1)[::max(1, g.size // 1024)].copy()
+      for k, v in net.state_dict().items():
+        v = v.numpy()
+        save["s%d_w_%s" % (step, k)] = v.copy() if v.size <= 2048 else v.reshape(-1)[::max(1, v.size // 1024)].copy()
+    np.savez_compressed(os.path.join(HERE, "learner_%s.npz" % name), **save)
+    print("learner", name, "losses", losses)
+
+
 if __name__ == "__main__":
   torch.set_num_threads(1)
   if len(sys.argv) > 1 and sys.argv[1] == "muzero":
@@ -576,6 +689,9 @@ if __name__ == "__main__":
     sys.exit(0)
   if len(sys.argv) > 1 and sys.argv[1] == "selfplay":
     gen_selfplay()
+    sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == "learner":
+    gen_learner()
     sys.exit(0)
   rng = np.random.default_rng(20261017)
   gen_search(rng)
@@ -585,4 +701,5 @@ if __name__ == "__main__":
   gen_fcnet(rng)
   gen_muzero()
   gen_selfplay()
+  gen_learner()
   print("python", sys.version.split()[0], "numpy", np.__version__, "torch", torch.__version__)
