@@ -564,22 +564,26 @@ def bench_learner(torch, _lib, dev, world, barrier):
              pol / pol.sum(-1, keepdim=True))), None, r(B).double())
   torch.manual_seed(11)
   net = learners.FCNetworkTrain(E, A, dev, cfg)
-  lr = learners.Learner(cfg, net)
-  lr.send_weights()
-  for _ in range(5):
-    lr.update_weights(batch)
-  barrier()
-  steps = 30
   a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  a.record()
-  for _ in range(steps):
-    lr.update_weights(batch)
-  b.record()
-  torch.cuda.synchronize()
-  t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-  if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  ms_step = float(t.item()) / steps
+  ms = {}
+  for mode in ("eager", "graph"):
+    net = learners.FCNetworkTrain(E, A, dev, cfg)
+    lr = learners.Learner(cfg, net, use_graph=(mode == "graph"))
+    lr.send_weights()
+    for _ in range(5):
+      lr.update_weights(batch)
+    barrier()
+    steps = 30
+    a.record()
+    for _ in range(steps):
+      lr.update_weights(batch)
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms[mode] = float(t.item()) / steps
+  ms_step = ms["graph"]
   # the loss kernel alone
   V = 31
   vl, rl, pl = torch.randn(K + 1, B, V, device=dev), torch.randn(K, B, V, device=dev), torch.randn(K + 1, B, A, device=dev)
@@ -605,6 +609,7 @@ def bench_learner(torch, _lib, dev, world, barrier):
   logit_bytes = 4 * (vl.numel() + rl.numel() + pl.numel())
   alg = 2 * logit_bytes + 4 * (2 * B * (K + 1) + t_p.numel()) + 8 * B + 8 * 3 * B + 4 * B
   return {"steps_per_s": 1e3 / ms_step, "samples_per_s": world * B * 1e3 / ms_step, "ms_per_step": ms_step,
+          "ms_per_step_eager": ms["eager"], "cuda_graph": True,
           "workload": "C3 learner step: B=512 per GPU, K=5, A=4, obs 128 f32, FCNetwork, AdamW, f32 GEMMs (cuBLAS) + "
                       "fused unroll loss; gradient all-reduce over %d rank(s)" % world,
           "loss_kernel": {"us_per_launch": us, "algorithmic_bytes": alg, "achieved_gbs": alg / us / 1e3,

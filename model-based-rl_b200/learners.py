@@ -151,19 +151,30 @@ def unroll_loss(config, values, rewards, policies, t_values, t_rewards, t_polici
 # ------------------------------------------------------------------------------------------------
 # optimisers / schedules (utils.py:72-128)
 # ------------------------------------------------------------------------------------------------
-def get_optimizer(config, parameters):
+def get_optimizer(config, parameters, capturable=False, lr=None):
+  """utils.py:72-83.  capturable: optimiser state (step counters) lives on the device so that the
+  step can sit inside a CUDA graph; lr may then be a device tensor a schedule updates in place."""
   name = config.optimizer
+  lr = config.lr_init if lr is None else lr
+  cap = dict(capturable=True) if capturable else {}
   if name == 'RMSprop':
-    return torch.optim.RMSprop(parameters, lr=config.lr_init, momentum=config.momentum, eps=0.01,
-                               weight_decay=config.weight_decay)
+    return torch.optim.RMSprop(parameters, lr=lr, momentum=config.momentum, eps=0.01,
+                               weight_decay=config.weight_decay, **cap)
   if name == 'Adam':
-    return torch.optim.Adam(parameters, lr=config.lr_init, weight_decay=config.weight_decay, eps=0.00015)
+    return torch.optim.Adam(parameters, lr=lr, weight_decay=config.weight_decay, eps=0.00015, **cap)
   if name == 'AdamW':
-    return torch.optim.AdamW(parameters, lr=config.lr_init, weight_decay=config.weight_decay, eps=0.00015)
+    return torch.optim.AdamW(parameters, lr=lr, weight_decay=config.weight_decay, eps=0.00015, **cap)
   if name == 'SGD':
-    return torch.optim.SGD(parameters, lr=config.lr_init, momentum=config.momentum,
-                           weight_decay=config.weight_decay)
+    return torch.optim.SGD(parameters, lr=lr, momentum=config.momentum, weight_decay=config.weight_decay)
   raise NotImplementedError(name)
+
+
+def _set_lr(optimizer, lr):
+  for group in optimizer.param_groups:
+    if torch.is_tensor(group["lr"]):
+      group["lr"].fill_(lr)  # read by the captured optimiser step
+    else:
+      group["lr"] = lr
 
 
 class MuZeroLR(object):
@@ -177,8 +188,7 @@ class MuZeroLR(object):
   def step(self):
     self.lr_step += 1
     self.lr = self.lr_init * self.lr_decay_rate ** (self.lr_step / self.lr_decay_steps)
-    for group in self.optimizer.param_groups:
-      group["lr"] = self.lr
+    _set_lr(self.optimizer, self.lr)
 
 
 class WarmUpLR(object):
@@ -187,15 +197,13 @@ class WarmUpLR(object):
   def __init__(self, optimizer, config):
     self.optimizer, self.max_lr, self.warm_up_steps, self.lr_step = optimizer, config.lr_init, 5000, 0
     self.lr = (1 / self.warm_up_steps) * self.max_lr
-    for group in self.optimizer.param_groups:
-      group["lr"] = self.lr
+    _set_lr(self.optimizer, self.lr)
 
   def step(self):
     self.lr_step += 1
     if self.lr_step <= self.warm_up_steps:
       self.lr = (self.lr_step / self.warm_up_steps) * self.max_lr
-      for group in self.optimizer.param_groups:
-        group["lr"] = self.lr
+      _set_lr(self.optimizer, self.lr)
 
 
 def get_lr_scheduler(config, optimizer):
@@ -223,9 +231,16 @@ class Learner(object):
   search_network: optional `networks.FCNetwork` that `send_weights()` refreshes;
   loss_fn(config, values, rewards, policies, t_values, t_rewards, t_policies, is_weights) ->
   (losses[3], new_errors): defaults to the CUDA kernel (`unroll_loss`); the gloo tests of the
-  data-parallel step pass the oracle's torch restatement because they run without a GPU."""
+  data-parallel step pass the oracle's torch restatement because they run without a GPU.
 
-  def __init__(self, config, network, replay_buffer=None, search_network=None, state=None, loss_fn=None):
+  use_graph: the step's ~400 small launches (5 MLPs x (K+1) steps forward and backward, the loss, the
+  optimiser) are captured once in CUDA graphs and replayed on static input buffers: graph 1 = forward
+  + fused loss + backward, graph 2 = gradient clipping + optimiser step (device-side step counters,
+  learning rate in a device scalar the schedule updates in place); between them, at N > 1, the eager
+  gradient all-reduce.  The first step runs eagerly (it initialises the optimiser state)."""
+
+  def __init__(self, config, network, replay_buffer=None, search_network=None, state=None, loss_fn=None,
+               use_graph=False):
     self.config = config
     self.network = network
     self.network.train()
@@ -238,11 +253,20 @@ class Learner(object):
     self.loss_fn = loss_fn
     self.replay_buffer = replay_buffer
     self.search_network = search_network
-    self.optimizer = get_optimizer(config, self.network.parameters())
+    self.use_graph = bool(use_graph)
+    if self.use_graph and self.device.type != 'cuda':
+      raise RuntimeError("use_graph needs a CUDA device")
+    # SGD has no capturable mode: its step is graph-safe only while lr is a constant
+    scheduled = getattr(config, 'lr_scheduler', None) is not None
+    self._graph_opt = self.use_graph and not (config.optimizer == 'SGD' and scheduled)
+    lr = torch.tensor(float(config.lr_init), device=self.device) if (self._graph_opt and scheduled) else None
+    self.optimizer = get_optimizer(config, self.network.parameters(),
+                                   capturable=self._graph_opt and config.optimizer != 'SGD', lr=lr)
     self.lr_scheduler = get_lr_scheduler(config, self.optimizer)
+    self._graphs = None
     self.training_step = 0
     self.losses_to_log = {'reward': 0., 'value': 0., 'policy': 0.}
-    self.last_losses = None
+    self.last_losses = self.last_errors = None
     if getattr(config, 'norm_obs', False):
       lo = torch.tensor(config.obs_range[::2], dtype=torch.float32, device=self.device)
       hi = torch.tensor(config.obs_range[1::2], dtype=torch.float32, device=self.device)
@@ -281,20 +305,7 @@ class Learner(object):
       return x.to(self.device, dtype).contiguous()
     return torch.as_tensor(x, dtype=dtype).to(self.device).contiguous()
 
-  def update_weights(self, batch):
-    batch, idxs, is_weights = batch
-    observations, actions, targets = batch
-    target_rewards, target_values, target_policies = targets
-
-    observations = self._dev(observations, torch.float32)
-    if getattr(self.config, 'norm_obs', False):
-      observations = (observations - self.obs_min) / self.obs_range
-    target_policies = self._dev(target_policies, torch.float32)
-    target_values = self._dev(target_values, torch.float32)
-    target_rewards = self._dev(target_rewards, torch.float32)
-    is_weights = self._dev(is_weights, torch.float64)
-    actions = self._dev(actions, torch.int64)  # [B][K]
-
+  def _forward_backward(self, observations, actions, target_values, target_rewards, target_policies, is_weights):
     out = self.network.initial_inference(observations)
     values, rewards, policies = [out.value], [], [out.policy_logits]
     hidden_state = out.hidden_state
@@ -305,24 +316,78 @@ class Learner(object):
       values.append(out.value)
       rewards.append(out.reward)
       policies.append(out.policy_logits)
-
     losses, new_errors = self.loss_fn(self.config, values, rewards, policies, target_values, target_rewards,
                                       target_policies, is_weights)
-    if self.replay_buffer is not None:
-      self.replay_buffer.update(idxs, new_errors.detach().cpu().numpy())
-
     full_weighted_loss = losses.sum()  # the 1/K hook of learners.py:213 lives inside the loss
-    self.optimizer.zero_grad()
     full_weighted_loss.backward()
-    parallel.allreduce_gradients(list(self.network.parameters()), average=True)
+    return losses.detach(), new_errors.detach()
+
+  def _apply_gradients(self):
     if getattr(self.config, 'clip_grad', 0):
       torch.nn.utils.clip_grad_norm_(self.network.parameters(), self.config.clip_grad)
     self.optimizer.step()
+
+  def update_weights(self, batch):
+    batch, idxs, is_weights = batch
+    observations, actions, targets = batch
+    target_rewards, target_values, target_policies = targets
+
+    observations = self._dev(observations, torch.float32)
+    if getattr(self.config, 'norm_obs', False):
+      observations = (observations - self.obs_min) / self.obs_range
+    inputs = (observations, self._dev(actions, torch.int64), self._dev(target_values, torch.float32),
+              self._dev(target_rewards, torch.float32), self._dev(target_policies, torch.float32),
+              self._dev(is_weights, torch.float64))
+
+    if not self.use_graph or self._graphs is None and not self._warm:
+      # eager step (always the first one: it creates the optimiser state the graphs reuse)
+      self.optimizer.zero_grad(set_to_none=self.use_graph)
+      losses, new_errors = self._forward_backward(*inputs)
+      self._feed_back(idxs, new_errors)
+      parallel.allreduce_gradients(list(self.network.parameters()), average=True)
+      self._apply_gradients()
+      self._warm = True
+    else:
+      if self._graphs is None or any(a.shape != b.shape for a, b in zip(self._static, inputs)):
+        self._capture(inputs)
+      for dst, src in zip(self._static, inputs):
+        dst.copy_(src, non_blocking=True)
+      fwd_bwd, apply = self._graphs
+      fwd_bwd.replay()
+      losses, new_errors = self._static_out
+      self._feed_back(idxs, new_errors)
+      parallel.allreduce_gradients(list(self.network.parameters()), average=True)
+      if apply is not None:
+        apply.replay()
+      else:
+        self._apply_gradients()
     if self.lr_scheduler is not None:
       self.lr_scheduler.step()
-
-    self.last_losses, self.last_errors = losses.detach(), new_errors.detach()
+    self.last_losses, self.last_errors = losses, new_errors
     return self.last_losses
+
+  _warm = False
+
+  def _feed_back(self, idxs, new_errors):
+    if self.replay_buffer is not None:  # learners.py:182-184
+      self.replay_buffer.update(idxs, new_errors.cpu().numpy())
+
+  def _capture(self, inputs):
+    """Captures the step for this batch shape.  Gradients are released first so that the captured
+    backward allocates them inside the graph's pool: every replay rewrites the same .grad storage,
+    which the (captured or eager) optimiser step then reads."""
+    self._static = tuple(torch.empty_like(t).copy_(t) for t in inputs)
+    self.optimizer.zero_grad(set_to_none=True)
+    torch.cuda.synchronize()
+    fwd_bwd = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(fwd_bwd):
+      self._static_out = self._forward_backward(*self._static)
+    apply = None
+    if self._graph_opt:
+      apply = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(apply, pool=fwd_bwd.pool()):
+        self._apply_gradients()
+    self._graphs = (fwd_bwd, apply)
 
   def log_losses(self):
     """Host read of the last step's losses into the running sums (learners.py:226-228); kept out of

@@ -10,6 +10,7 @@ move between the two through the state dict.
 import ctypes as C
 from collections import OrderedDict, namedtuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -372,14 +373,18 @@ class FCSearch(object):
           actions=torch.zeros(G, dtype=torch.int32, **pin),
           root_value=torch.zeros(G, dtype=torch.float64, **pin),
           child_visits=torch.zeros((G, A), dtype=torch.float64, **pin),
-          init_value=torch.zeros(G, dtype=torch.float32, **pin))
+          init_value=torch.zeros(G, dtype=torch.float32, **pin),
+          legal=torch.zeros(G, dtype=torch.int32, **pin),
+          to_play=torch.ones(G, dtype=torch.int8, **pin))
     return self._h
 
-  def search_host(self, obs, noise=None, uniforms=None, temperature=None):
+  def search_host(self, obs, noise=None, uniforms=None, temperature=None, legal=None, to_play=None):
     """The per-move body of Actor.play_game (actors.py:131-153) for G games.
 
     Inputs are HOST arrays (numpy or CPU tensors): obs [G, input_dim] float32, Dirichlet noise
-    [G, A] float64, uniforms [G] float64 (action sampling), temperature [G] float64.  Returns
+    [G, A] float64 (row g: one value per legal action of game g, in action order), uniforms [G]
+    float64 (action sampling), temperature [G] float64, and optionally the roots' legal-action bit
+    masks [G] (bit a = action a is legal, actors.py:141-142) and to_play [G] (+1 / -1).  Returns
     pinned host tensors: actions [G] i32, root_value [G] f64, child_visits [G, A] f64, and the
     initial-inference value [G] f32 (the priority seed `error = root.value() - value`,
     actors.py:147).  Host->device and device->host copies are part of the call.
@@ -397,6 +402,10 @@ class FCSearch(object):
     stage('noise', noise, self.noise)
     stage('uniforms', uniforms, self.uniforms)
     stage('temperature', temperature, self.temperature)
+    if legal is not None:
+      stage('legal', np.ascontiguousarray(np.asarray(legal).astype(np.int64).astype(np.int32)), self.legal)
+    if to_play is not None:
+      stage('to_play', np.ascontiguousarray(np.asarray(to_play, dtype=np.int8)), self.to_play)
     self.use_noise = noise is not None or self.use_noise
     self.run()
     h['actions'].copy_(self.actions, non_blocking=True)

@@ -8,6 +8,11 @@ with the reference's chunking rules (`max_history_length`, the `num_unroll_steps
 `ignore` for running games, actors.py:160-169).  A finished game is replaced by a new one at once, so
 the batch always holds G live games.
 
+With `search=` an `FCSearch` built on the same network (networks.py), the whole move -- initial
+inference, root set-up, the S simulations, root statistics and action selection -- is the engine's
+single CUDA-graph replay behind `search_host` (host arrays in, host arrays out) instead of one
+`recurrent_inference` call per simulation.
+
 Random draws (Dirichlet noise per root, one uniform per action selection) come from numpy unless the
 caller passes them in -- which is how the parity test replays the reference.
 """
@@ -49,8 +54,11 @@ class _Game(object):
 
 class BatchedActor(object):
 
-  def __init__(self, config, network, env, replay_buffer=None, device=None, temperature=1.0):
+  def __init__(self, config, network, env, replay_buffer=None, device=None, temperature=1.0, search=None):
     self.config, self.network, self.env, self.replay = config, network, env, replay_buffer
+    self.search = search
+    if search is not None and search.G != env.num_games:
+      raise ValueError("the search engine was built for %d games, the environment has %d" % (search.G, env.num_games))
     self.G, self.A = env.num_games, int(config.action_space)
     self.device = torch.device("cuda" if device is None else device)
     self.eng = None  # built on the first move (the hidden-state width comes from the network)
@@ -67,8 +75,6 @@ class BatchedActor(object):
     obs = np.stack([np.float32(g.observations[-1]) for g in self.games])      # get_observation(-1)
     if getattr(cfg, "norm_obs", False):
       obs = (obs - cfg.obs_min) / cfg.obs_range
-    with torch.inference_mode():
-      init = self.network.initial_inference(torch.from_numpy(obs).to(self.device))
     legal = env.legal_mask()
     to_play = np.array([g.to_play for g in self.games], np.int8)
     if noise is None:  # Node.add_exploration_noise (mcts.py:57-61): one draw per root over its children
@@ -78,6 +84,14 @@ class BatchedActor(object):
         noise[i, :n] = np.random.dirichlet([cfg.root_dirichlet_alpha] * n)
     if uniforms is None:
       uniforms = np.random.random(G)
+    if self.search is not None:
+      actions, root_value, child_visits, init_value = self.search.search_host(
+          np.ascontiguousarray(obs, dtype=np.float32), noise, uniforms, self.temperature, legal=legal, to_play=to_play)
+      actions, root_value = actions.numpy().copy(), root_value.numpy().copy()
+      child_visits, init_value = child_visits.numpy().copy(), init_value.double().numpy()
+      return self._advance(actions, root_value, child_visits, root_value - init_value)
+    with torch.inference_mode():
+      init = self.network.initial_inference(torch.from_numpy(obs).to(self.device))
     hidden = init.hidden_state
     if self.eng is None:
       words = hidden[0].numel() * hidden.element_size() // 4
@@ -90,8 +104,11 @@ class BatchedActor(object):
     root_value = eng.root_value.cpu().numpy()
     child_visits = eng.child_visits.cpu().numpy()
     init_value = init.value.reshape(G).double().cpu().numpy()
-    errors = root_value - init_value                                          # actors.py:147
+    return self._advance(actions, root_value, child_visits, root_value - init_value)  # actors.py:147
 
+  def _advance(self, actions, root_value, child_visits, errors):
+    """Environment step and the Game / History bookkeeping of every game (actors.py:150-176)."""
+    cfg, env = self.config, self.env
     next_obs, reward, done, result = env.step(actions)
     finished = []
     overlap = cfg.num_unroll_steps + cfg.td_steps

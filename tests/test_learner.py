@@ -143,7 +143,7 @@ def test_lr_schedules():
   sch.step()
   assert abs(opt.param_groups[0]["lr"] - 0.2 / 5000) < 1e-15
   with pytest.raises(NotImplementedError):
-    learners.get_optimizer(types.SimpleNamespace(optimizer="LBFGS"), p)
+    learners.get_optimizer(types.SimpleNamespace(optimizer="LBFGS", lr_init=0.1), p)
 
 
 # -- world size 2 (gloo, CPU): data-parallel learner step ---------------------------------------
@@ -357,3 +357,36 @@ def test_gpu_learner_loop_with_replay_and_search_network():
   assert again.training_step == 4
   for a, b in zip(again.network.state_dict().values(), net.state_dict().values()):
     assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,scheduler", [("breakout", None), ("ttt", "MuZeroLR"), ("lunar_raw", None),
+                                            ("lunar_raw", "WarmUpLR")])
+def test_gpu_learner_cuda_graph_step_equals_eager_step(case, scheduler):
+  """use_graph=True (forward + loss + backward in one CUDA graph, clipping + optimiser in a second)
+  follows the eager learner over five steps on alternating batches, and the reference's golden after
+  the first two.  Capturable Adam / RMSprop evaluate their bias corrections in float32 on the device:
+  1e-6 absolute on the weights."""
+  from model_based_rl_b200 import learners
+  torch.backends.cuda.matmul.allow_tf32 = False
+  g = helpers.load("learner_" + case)
+  nets, ls = [], []
+  for use_graph in (False, True):
+    cfg = _config(g)
+    cfg.lr_scheduler, cfg.lr_decay_rate, cfg.lr_decay_steps = scheduler, 0.1, 3
+    net = learners.FCNetworkTrain(int(g["obs_dim"]), int(g["action_space"]), "cuda", cfg)
+    net.load_weights(_weights(g))
+    nets.append(net)
+    ls.append(learners.Learner(cfg, net, use_graph=use_graph))
+  for step in range(5):
+    la = ls[0].update_weights(_batch(g, step % 2))
+    lb = ls[1].update_weights(_batch(g, step % 2))
+    np.testing.assert_allclose(lb.cpu().numpy(), la.cpu().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(ls[1].last_errors.cpu().numpy(), ls[0].last_errors.cpu().numpy(), rtol=0, atol=2e-3)
+    if scheduler is None and step < 2:
+      np.testing.assert_allclose(lb.cpu().numpy(), g["s%d_losses" % step], rtol=1e-4)
+    for (k, a), b in zip(nets[0].state_dict().items(), nets[1].state_dict().values()):
+      np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=0, atol=1e-6, err_msg="step %d %s" % (step, k))
+  assert ls[1]._graphs is not None
+  if scheduler is not None:
+    assert abs(float(ls[1].optimizer.param_groups[0]["lr"]) - float(ls[0].optimizer.param_groups[0]["lr"])) < 1e-9

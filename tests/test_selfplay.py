@@ -145,3 +145,45 @@ def test_actor_feeds_prioritized_replay():
                                      np.array(h.root_values), np.array(h.child_visits), 3, 4, 1.0, step)
       ok |= bool(np.array_equal(t_r[b], r) and np.array_equal(t_p[b], p) and np.allclose(t_v[b], v, rtol=1e-5, atol=1e-6))
     assert ok, b
+
+
+@pytest.mark.gpu
+def test_fast_path_through_fcsearch_equals_generic_path():
+  """BatchedActor(search=FCSearch): the whole move behind one search_host call (CUDA graph, legal masks
+  and to_play staged from the host) plays exactly the games the generic per-simulation path plays with
+  the same FCNetwork (float32 kernels on both sides): actions, root values, child visits, priority
+  seeds and the histories handed over, bit for bit."""
+  import torch
+  from model_based_rl_b200.environments import VectorTicTacToe
+  from model_based_rl_b200.networks import FCNetwork, FCSearch, random_state_dict
+  from model_based_rl_b200.selfplay import BatchedActor
+  A, G, S = 9, 96, 25
+  cfg = types.SimpleNamespace(
+      num_simulations=S, action_space=A, two_players=True, discount=1.0, pb_c_base=19652, pb_c_init=1.25,
+      init_value_score=0.0, known_bounds=[-1, 1], root_dirichlet_alpha=0.25, root_exploration_fraction=0.25,
+      num_unroll_steps=3, td_steps=4, max_history_length=500, max_steps=10 ** 9,
+      value_support=[-15, 15], reward_support=[-15, 15], no_support=False, no_target_transform=False)
+  net = FCNetwork(9, A, "cuda", cfg, precision="f32")
+  net.load_weights(random_state_dict(9, A, seed=7))
+  temps = np.array([[1.0, 0.5, 0.0, 0.25][i % 4] for i in range(G)])
+  slow = BatchedActor(cfg, net, VectorTicTacToe(G), device="cuda", temperature=temps)
+  fast = BatchedActor(cfg, net, VectorTicTacToe(G), device="cuda", temperature=temps,
+                      search=FCSearch(cfg, net, G, use_graph=True, num_streams=2))
+  rng = np.random.default_rng(11)
+  for move in range(14):
+    noise = np.zeros((G, A))
+    legal = slow.env.legal_mask()
+    assert np.array_equal(legal, fast.env.legal_mask())
+    for i in range(G):
+      n = bin(int(legal[i])).count("1")
+      noise[i, :n] = rng.dirichlet([0.25] * n)
+    u = rng.random(G)
+    a = slow.play_move(noise.copy(), u.copy())
+    b = fast.play_move(noise.copy(), u.copy())
+    for x, y, name in zip(a, b, ("actions", "root_value", "child_visits", "errors", "done")):
+      assert np.array_equal(np.asarray(x), np.asarray(y)), (move, name)
+  assert fast.games_played == slow.games_played >= G
+  assert len(fast.saved) == len(slow.saved)
+  for (i, h, ign, term), (j, h2, ign2, term2) in zip(fast.saved, slow.saved):
+    assert (i, ign, term) == (j, ign2, term2) and h.actions == h2.actions and h.root_values == h2.root_values
+    assert h.child_visits == h2.child_visits and h.errors == h2.errors and h.to_play == h2.to_play
