@@ -162,7 +162,7 @@ def run_reference(args):
       "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }
-  print(json.dumps(line), flush=True)
+  emit(line)
 
 
 def workload_config(args, n_gpus, cpu=False):
@@ -390,7 +390,7 @@ def run_b200(args):
     }
     if cpu_baseline is not None:
       line["cpu_baseline"] = cpu_baseline
-    print(json.dumps(line), flush=True)
+    emit(line)
   if world > 1:
     dist.destroy_process_group()
 
@@ -616,7 +616,21 @@ def bench_learner(torch, _lib, dev, world, barrier):
                           "launches": 2}}
 
 
+def emit(line):
+  """The ONE JSON line goes to the real stdout; everything else this process (or a library: NCCL prints
+  its version banner on fd 1) writes to stdout lands on stderr."""
+  _REAL_STDOUT.write(json.dumps(line) + "\n")
+  _REAL_STDOUT.flush()
+
+
+_REAL_STDOUT = sys.stdout
+
+
 def main():
+  global _REAL_STDOUT
+  sys.stdout.flush()
+  _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+  os.dup2(2, 1)
   args = parse()
   if args.impl == "reference":
     run_reference(args)
