@@ -111,6 +111,7 @@ _SIGNATURES = {
                                     _V, _V, _V, _V, _V, _V, _V]),
     "mz_conv3x3_tc": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _V, _V, _V, C.c_int32, _V, _V, C.c_int32, _V,
                                 _V, _V, _V, _V, _V]),
+    "mz_conv_set_pair": (C.c_int, [C.c_int32]),
     "mz_conv_im2col_s2": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _V, _V, _V]),
     "mz_conv_gemm_to_padded": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _V, _V, _V, C.c_int32, _V,
                                          _V]),

@@ -416,6 +416,319 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+
+// ================================================================================================
+// CTA-pair variant for the 128-channel 3x3 convolutions (63 of the 65 convolutions of one
+// recurrent_inference): clusters of two CTAs issue tcgen05.mma.cta_group::2 with M = 256 (128 rows per
+// CTA), N = 128, and keep the WHOLE weight matrix resident in shared memory -- each CTA holds the 64
+// output channels the pair's B operand assigns to it (18 K blocks x 8 KB = 144 KB), loaded once per
+// launch and before griddepcontrol.wait (weights do not depend on the previous layer).  Per K block a
+// CTA then only streams its 16 KB activation tile: 16 KB written by TMA + 24 KB read by the tensor core
+// (A 16 KB + its half of B 8 KB) = 40 KB against 64 KB for the single-CTA kernel, whose 128 x 128 tile
+// with both operands streamed is shared-memory-bandwidth bound.
+//
+// Protocol (CUTLASS' 2-SM scheme): every TMA load of either CTA completes its bytes on the LEADER's
+// (cluster rank 0) barrier (.cta_group::2, peer bit of the barrier address cleared); only the leader's
+// MMA warp issues MMAs; tcgen05.commit multicasts its arrival to the same barrier offset in both CTAs
+// (stage release, accumulator ready); epilogue threads of both CTAs arrive on the leader's
+// accumulator-empty barrier (remote arrive for the peer).
+// ================================================================================================
+constexpr int P_STAGES = 4;
+constexpr int P_A_BYTES = BM * BK * 2;                  // 16 KB activation tile per K block
+constexpr int P_KBLOCKS = 18;                           // 9 taps x 2 blocks of 64 input channels
+constexpr int P_BH_BYTES = 64 * BK * 2;                 // 8 KB: this CTA's 64 output channels of one K block
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;          // shared::cluster address -> same offset in the even CTA
+
+MZ_DEV uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+MZ_DEV void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+MZ_DEV void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+MZ_DEV void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+MZ_DEV void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+MZ_DEV void tmem_dealloc_pair(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+MZ_DEV void tc_commit_pair(uint64_t* bar) {  // arrives on `bar`'s offset in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+template <bool ACC>
+MZ_DEV void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  if (ACC)
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+MZ_DEV void mbar_arrive_leader(uint64_t* bar, uint32_t rank) {  // release at cluster scope
+  if (rank == 0) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+  } else {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  }
+}
+MZ_DEV void mbar_wait_cluster_acq(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+// D = f32, A = B = bf16, both K-major, M = 256 over the CTA pair, N = 128
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_b = smem;                                        // [18][64 rows][64 k] bf16, 128-byte swizzle
+  uint8_t* s_a = smem + P_KBLOCKS * P_BH_BYTES;               // [P_STAGES][128 rows][64 k]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_a + P_STAGES * P_A_BYTES);
+  uint64_t* empty = full + P_STAGES;
+  uint64_t* acc_full = empty + P_STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2] (used in the leader only)
+  uint64_t* b_full = acc_empty + 2;        // [1] (used in the leader only)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);  // [128]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_pairs = (p.num_tiles_m + 1) >> 1;
+  constexpr int NC = BN;
+  for (int i = threadIdx.x; i < NC; i += CONV_THREADS) s_bias[i] = p.bias[i];
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 256);  // the epilogue threads of both CTAs
+    }
+    mbar_init(b_full, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  __syncthreads();
+  cluster_sync();  // both CTAs' barriers exist before anything is signalled across the pair
+  if (warp == 0) {
+    tmem_alloc_pair(tmem_ptr, 2 * BN);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      // resident weights: rows [rank * 64, +64) of W[128][1152], one 8 KB box per K block
+      if (rank == 0) mbar_arrive_expect_tx(b_full, 2u * P_KBLOCKS * P_BH_BYTES);
+      for (int kb = 0; kb < P_KBLOCKS; ++kb)
+        tma_load_2d_pair(s_b + kb * P_BH_BYTES, &map_b, kb * BK, (int)rank * 64, b_full);
+    }
+    __syncwarp();
+    pdl_wait();  // activations of the previous layer are only touched below
+    pdl_trigger();
+    int it = 0;
+    for (int pt = cluster_id; pt < num_pairs; pt += num_clusters) {
+      const int rb0 = (2 * pt + (int)rank) * BM;
+      for (int kb = 0; kb < P_KBLOCKS; ++kb, ++it) {
+        const int st = it % P_STAGES;
+        mbar_wait(&empty[st], ((it / P_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = s_a + st * P_A_BYTES;
+          const int tap = kb >> 1;
+          const int shift = (tap / 3 - 1) * p.wp + (tap % 3 - 1);
+          const int ka = (kb & 1) * BK;
+          if (rank == 0) mbar_arrive_expect_tx(&full[st], 2u * P_A_BYTES);
+          tma_load_2d_pair(sa, &map_a, ka, rb0 + shift, &full[st]);
+          tma_load_2d_pair(sa + 64 * BK * 2, &map_a, ka, rb0 + 64 + shift, &full[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    pdl_wait();
+    pdl_trigger();
+    if (rank == 0) {
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+      int it = 0, t = 0;
+      for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++t) {
+        const int acc = t & 1;
+        mbar_wait_cluster_acq(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + acc * BN;
+        for (int kb = 0; kb < P_KBLOCKS; ++kb, ++it) {
+          const int st = it % P_STAGES;
+          mbar_wait(&full[st], (it / P_STAGES) & 1);
+          tc_fence_after();
+          const uint64_t ad = make_desc_sw128(smem_u32(s_a + st * P_A_BYTES));
+          const uint64_t bd = make_desc_sw128(smem_u32(s_b + kb * P_BH_BYTES));
+          if (elect_one()) {
+            if (kb == 0) umma_ss_pair<false>(d, ad, bd, kIdescPair);
+            else umma_ss_pair<true>(d, ad, bd, kIdescPair);
+#pragma unroll
+            for (int ks = 1; ks < BK / 16; ++ks)
+              umma_ss_pair<true>(d, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), kIdescPair);
+            tc_commit_pair(&empty[st]);
+            if (kb == P_KBLOCKS - 1) tc_commit_pair(&acc_full[acc]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: thread = accumulator row of this CTA's half of the pair tile =====
+    pdl_wait();
+    pdl_trigger();
+    const int quarter = warp & 3;
+    const int r_in_tile = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    int t = 0;
+    for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++t) {
+      const int acc = t & 1;
+      const int tm = 2 * pt + (int)rank;
+      const int R = tm * BM + r_in_tile;  // flat row
+      const int g = R / p.grows, pos = R - g * p.grows;
+      const int py = (pos - p.wp) / p.wp, px = (pos - p.wp) - py * p.wp;
+      const bool interior = pos >= p.wp && px < p.wp - 1;
+      const bool in_range = R < p.rows_total;
+      const bool add_res = (p.flags & EPI_RESIDUAL) && interior && in_range;
+      uint4 resv[BN / 8];
+      if (p.flags & EPI_RESIDUAL) {  // requested before the accumulator wait
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)R * NC);
+#pragma unroll
+        for (int q = 0; q < BN / 8; ++q) resv[q] = add_res ? rp[q] : make_uint4(0u, 0u, 0u, 0u);
+      }
+      float act_scale = 0.0f;
+      const float* plane = nullptr;
+      if ((p.flags & EPI_ACTION) && interior && in_range) {
+        act_scale = (float)p.actions[g] / (float)p.num_actions;
+        plane = p.plane_term + (py * (p.wp - 1) + px) * NC;
+      }
+      mbar_wait(&acc_full[acc], (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t d = lane_addr + acc * BN;
+      uint4* orow = reinterpret_cast<uint4*>(p.out + (size_t)R * NC);
+      auto chunk = [&](int c0, float (&x)[32]) {
+        uint32_t v[32];
+        tmem_ld32(d + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+        if (plane) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = fmaf(act_scale, __ldg(plane + c0 + j), x[j]);
+        }
+        if (add_res) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 rv = resv[(c0 >> 3) + q];
+            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[h]);
+              x[q * 8 + 2 * h] += __low2float(b2);
+              x[q * 8 + 2 * h + 1] += __high2float(b2);
+            }
+          }
+        }
+        if (p.flags & EPI_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+        }
+        if (!interior) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = 0.0f;  // keep the zero border of the padded layout
+        }
+      };
+      float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float x[32];
+        chunk(c0, x);
+        if (p.flags & EPI_SCALE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            mn = fminf(mn, x[j]);
+            mx = fmaxf(mx, x[j]);
+          }
+        }
+        if (in_range && p.out) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            orow[(c0 >> 3) + q] = make_uint4(pack_bf16(x[q * 8], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                                             pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
+        }
+      }
+      if (p.flags & EPI_SCALE) {  // MuZeroNetwork.scale_state networks.py:543-547 (second pass)
+        uint4* so = reinterpret_cast<uint4*>(p.out_scaled + (size_t)R * NC);
+        uint4* po = (p.pool_out && in_range)
+                        ? reinterpret_cast<uint4*>(p.pool_out + ((size_t)p.pool_row_base[g] + pos) * NC)
+                        : nullptr;
+        const float den = mx - mn;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float x[32];
+          chunk(c0, x);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = interior ? (x[j] - mn) / den : 0.0f;
+          if (in_range) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 o = make_uint4(pack_bf16(x[q * 8], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
+                                         pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
+              so[(c0 >> 3) + q] = o;
+              if (po) po[(c0 >> 3) + q] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_leader(&acc_empty[acc], rank);
+    }
+  }
+
+  // neither CTA may leave while its peer can still signal its barriers or read its shared memory
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem, 2 * BN);
+  }
+}
+
 // ---- heads: relu(fc1) [G][512] -> Linear(512 -> bins) (+ softmax expectation + h^-1) --------------
 // One warp per game.  networks.py:438-440, 477-483; config.py:27-33.
 __global__ void conv_head_kernel(int G, const float* __restrict__ hidden, int ldh, const float* __restrict__ w2,
@@ -472,6 +785,44 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& 
   const int grid = tiles < sms ? tiles : sms;
   cudaError_t e = mz_launch(conv_gemm_tc_kernel, dim3(grid), dim3(CONV_THREADS), kConvSmem,
                             (cudaStream_t)stream, true, ma, mb, p);
+  if (e != cudaSuccess) return (int)e;
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+constexpr size_t kPairSmem = 1024 + (size_t)P_KBLOCKS * P_BH_BYTES + (size_t)P_STAGES * P_A_BYTES +
+                             (2 * P_STAGES + 5) * sizeof(uint64_t) + 16 + BN * sizeof(float);
+int g_conv_pair = 1;  // 128-channel 3x3 convolutions on the CTA-pair kernel (0: single-CTA kernel)
+
+int launch_conv_pair(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, void* stream) {
+  static bool attr = false;
+  static int sms = 0;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kPairSmem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    attr = true;
+  }
+  const int pairs = (p.num_tiles_m + 1) / 2;
+  const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(CONV_THREADS);
+  cfg.dynamicSmemBytes = kPairSmem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 2;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = g_mz_pdl ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_pair_tc_kernel, ma, mb, p);
   if (e != cudaSuccess) return (int)e;
   MZ_LAUNCH_CHECK();
   return MZ_OK;
@@ -708,7 +1059,13 @@ int mz_conv3x3_tc(int32_t games, int32_t width, int32_t channels, const void* x,
   p.out_scaled = (__nv_bfloat16*)out_scaled;
   p.pool_out = (__nv_bfloat16*)pool_out;
   p.pool_row_base = pool_row_base;
+  if (channels == 128 && g_conv_pair) return launch_conv_pair(ma, mb, p, stream);
   return launch_conv(ma, mb, p, stream);
+}
+
+int mz_conv_set_pair(int32_t enable) {
+  g_conv_pair = enable ? 1 : 0;
+  return MZ_OK;
 }
 
 // Linear(49 * 128 -> n_out) over the padded channels-last state (padding rows are zero), bias + ReLU:

@@ -68,6 +68,45 @@ def test_conv_kernel_matches_conv2d(games, flags):
     assert float(muzero.padding_rows(scaled, games).float().abs().max()) == 0
 
 
+@pytest.mark.parametrize("games,width,flags", [(1, 6, 1), (2, 6, 3), (3, 6, 3), (301, 6, 1 | 2 | 8), (5, 6, 1 | 4),
+                                               (3, 12, 3), (2, 24, 1)])
+def test_conv_pair_kernel_equals_single_cta_kernel(games, width, flags):
+  """The CTA-pair kernel (tcgen05.mma.cta_group::2, M = 256, resident weights) against the single-CTA
+  kernel on the same operands: same K order and float32 accumulation, same epilogue -> identical bits.
+  Odd tile counts (the pair's second half past the end), tiles straddling games, every epilogue."""
+  from model_based_rl_b200 import _lib, muzero
+  lib = _lib.load()
+  torch.manual_seed(games * 31 + flags + width)
+  dev = "cuda"
+  wp = width + 1
+  x = torch.rand((games, 128, width, width), device=dev)
+  cin = 129 if flags & 4 else 128
+  w = (torch.rand((128, cin, 3, 3), device=dev) * 2 - 1) * (3.0 / (cin * 9)) ** 0.5
+  conv = muzero._Conv(w, torch.randn(128, device=dev) * 0.1, None, dev)
+  rows = muzero.to_padded(x)
+  res_rows = muzero.to_padded(torch.rand((games, 128, width, width), device=dev))
+  actions = torch.randint(0, 18, (games,), device=dev, dtype=torch.int32)
+  P = _lib.ptr
+  outs = []
+  try:
+    for pair in (0, 1):
+      lib.mz_conv_set_pair(pair)
+      out = torch.full((games * wp * wp, 128), 7.0, dtype=torch.bfloat16, device=dev)
+      scaled = torch.full((games * wp * wp, 128), 7.0, dtype=torch.bfloat16, device=dev)
+      for _ in range(2):  # the second launch reuses barriers / TMEM of a warm SM
+        _lib.check(lib.mz_conv3x3_tc(games, width, 128, P(rows), P(conv.w), P(conv.bias), flags,
+                                     P(conv.plane) if flags & 4 else None, P(actions), 18,
+                                     P(res_rows) if flags & 2 else None, P(out),
+                                     P(scaled) if flags & 8 else None, None, None, _lib.current_stream()), "conv")
+      torch.cuda.synchronize()
+      outs.append((out, scaled))
+  finally:
+    lib.mz_conv_set_pair(1)
+  assert torch.equal(outs[0][0], outs[1][0]), float((outs[0][0].float() - outs[1][0].float()).abs().max())
+  if flags & 8:
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("width,games,ch", [(12, 3, 128), (24, 2, 128), (48, 2, 64)])
 def test_conv_kernel_other_widths(width, games, ch):
   """The same kernel on the 12 x 12 / 24 x 24 (128 channels) and 48 x 48 (64 channels) stages of the
