@@ -364,9 +364,10 @@ int mz_conv3x3_tc(int32_t games, int32_t width, int32_t channels, const void* x,
                   const void* residual, void* out, void* out_scaled, void* pool_out,
                   const int32_t* pool_row_base, void* stream);
 /* 128-channel convolutions run on clusters of two CTAs (tcgen05.mma.cta_group::2, M = 256, the weight
- * matrix resident in the pair's shared memory); enable = 0 selects the single-CTA kernel (A/B runs,
- * diagnostics).  Default: enabled. */
-int mz_conv_set_pair(int32_t enable);
+ * matrix resident in the pair's shared memory).  mode 0 selects the single-CTA kernel, 1 the pair kernel
+ * with one activation load per tap, 2 (default) the pair kernel with one activation row window per tile
+ * for images of width <= 6 (the taps become row offsets of the A descriptor) and mode 1 for wider ones. */
+int mz_conv_set_pair(int32_t mode);
 /* Strided convolutions of MuZeroRepresentation (conv1, conv2: networks.py:399, 402) = im2col of the
  * stride-2 patches + GEMM whose output rows land in the padded layout; AvgPool2d(3, 2, 1)
  * (networks.py:406, 409) between padded layouts.  Padding rows of the outputs are never written:

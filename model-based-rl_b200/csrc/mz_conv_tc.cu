@@ -437,6 +437,19 @@ constexpr int P_STAGES = 4;
 constexpr int P_A_BYTES = BM * BK * 2;                  // 16 KB activation tile per K block
 constexpr int P_KBLOCKS = 18;                           // 9 taps x 2 blocks of 64 input channels
 constexpr int P_BH_BYTES = 64 * BK * 2;                 // 8 KB: this CTA's 64 output channels of one K block
+// Window mode (padded row width <= 7, i.e. the 6 x 6 hidden state): the nine taps of a tile read row
+// windows shifted by at most 8 rows, so ONE load of rows [tile - 8, tile + 136) per block of 64 input
+// channels serves all of them -- the tap is a row offset in the A descriptor's start address (the
+// 128-byte swizzle is a function of the shared-memory address bits, so TMA's placement and the tensor
+// core's reads agree at any row offset; setting the descriptor's matrix-base-offset field for the
+// shifted start gives wrong results -- measured).  2 x 18 KB written per tile instead of 18 x 16 KB.
+constexpr int P_WIN_PAD = 8;                            // rows before / after the tile
+constexpr int P_WIN_ROWS = BM + 2 * P_WIN_PAD;          // 144
+constexpr int P_WIN_HALF = P_WIN_ROWS * BK * 2;         // 18 KB: one block of 64 channels
+constexpr int P_WIN_BYTES = 2 * P_WIN_HALF;             // 36 KB per tile
+constexpr int P_WIN_STAGES = 2;
+constexpr int P_A_REGION = P_WIN_STAGES * P_WIN_BYTES > P_STAGES * P_A_BYTES ? P_WIN_STAGES * P_WIN_BYTES
+                                                                             : P_STAGES * P_A_BYTES;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;          // shared::cluster address -> same offset in the even CTA
 
 MZ_DEV uint32_t cluster_rank() {
@@ -502,12 +515,12 @@ constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    ConvParams p) {
+                    const __grid_constant__ CUtensorMap map_w, ConvParams p, int window) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_b = smem;                                        // [18][64 rows][64 k] bf16, 128-byte swizzle
   uint8_t* s_a = smem + P_KBLOCKS * P_BH_BYTES;               // [P_STAGES][128 rows][64 k]
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_a + P_STAGES * P_A_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_a + P_A_REGION);
   uint64_t* empty = full + P_STAGES;
   uint64_t* acc_full = empty + P_STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2] (used in the leader only)
@@ -534,6 +547,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     mbar_fence_init();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_w);
   }
   __syncthreads();
   cluster_sync();  // both CTAs' barriers exist before anything is signalled across the pair
@@ -560,6 +574,19 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     int it = 0;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters) {
       const int rb0 = (2 * pt + (int)rank) * BM;
+      if (window) {  // one stage = the tile's row window for both blocks of 64 channels
+        const int st = it % P_WIN_STAGES;
+        mbar_wait(&empty[st], ((it / P_WIN_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = s_a + st * P_WIN_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(&full[st], 2u * P_WIN_BYTES);
+          tma_load_2d_pair(sa, &map_w, 0, rb0 - P_WIN_PAD, &full[st]);
+          tma_load_2d_pair(sa + P_WIN_HALF, &map_w, BK, rb0 - P_WIN_PAD, &full[st]);
+        }
+        __syncwarp();
+        ++it;
+        continue;
+      }
       for (int kb = 0; kb < P_KBLOCKS; ++kb, ++it) {
         const int st = it % P_STAGES;
         mbar_wait(&empty[st], ((it / P_STAGES) & 1) ^ 1);
@@ -588,6 +615,32 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         mbar_wait_cluster_acq(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem + acc * BN;
+        if (window) {
+          const int st = it % P_WIN_STAGES;
+          mbar_wait(&full[st], (it / P_WIN_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t win = smem_u32(s_a + st * P_WIN_BYTES);
+          if (elect_one()) {
+#pragma unroll 1
+            for (int kb = 0; kb < P_KBLOCKS; ++kb) {  // same K order as the per-tap pipeline
+              const int tap = kb >> 1;
+              const int shift = (tap / 3 - 1) * p.wp + (tap % 3 - 1);
+              const uint32_t a_addr = win + (kb & 1) * P_WIN_HALF + (uint32_t)((P_WIN_PAD + shift) * (BK * 2));
+              const uint64_t ad = make_desc_sw128(a_addr);  // no matrix base offset: measured, bit-identical
+              const uint64_t bd = make_desc_sw128(smem_u32(s_b + kb * P_BH_BYTES));
+              if (kb == 0) umma_ss_pair<false>(d, ad, bd, kIdescPair);
+              else umma_ss_pair<true>(d, ad, bd, kIdescPair);
+#pragma unroll
+              for (int ks = 1; ks < BK / 16; ++ks)
+                umma_ss_pair<true>(d, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), kIdescPair);
+            }
+            tc_commit_pair(&empty[st]);
+            tc_commit_pair(&acc_full[acc]);
+          }
+          __syncwarp();
+          ++it;
+          continue;
+        }
         for (int kb = 0; kb < P_KBLOCKS; ++kb, ++it) {
           const int st = it % P_STAGES;
           mbar_wait(&full[st], (it / P_STAGES) & 1);
@@ -753,12 +806,12 @@ EncodeTiledFn get_encode() {
 }
 
 // [rows][cols] bf16 row-major (cols contiguous), box = 64 rows x 64 cols, 128-byte swizzle
-int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
+int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows = 64) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return MZ_ERR_UNSUPPORTED;
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, 64};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -790,11 +843,15 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& 
   return MZ_OK;
 }
 
-constexpr size_t kPairSmem = 1024 + (size_t)P_KBLOCKS * P_BH_BYTES + (size_t)P_STAGES * P_A_BYTES +
+constexpr size_t kPairSmem = 1024 + (size_t)P_KBLOCKS * P_BH_BYTES + (size_t)P_A_REGION +
                              (2 * P_STAGES + 5) * sizeof(uint64_t) + 16 + BN * sizeof(float);
-int g_conv_pair = 1;  // 128-channel 3x3 convolutions on the CTA-pair kernel (0: single-CTA kernel)
+// 128-channel 3x3 convolutions: 0 = single-CTA kernel, 1 = CTA-pair kernel with one activation load per
+// tap, 2 = CTA-pair kernel with one row window per tile where the image is narrow enough (wider images
+// fall back to 1)
+int g_conv_pair = 2;
 
-int launch_conv_pair(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, void* stream) {
+int launch_conv_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, const ConvParams& p,
+                     int window, void* stream) {
   static bool attr = false;
   static int sms = 0;
   if (!attr) {
@@ -822,7 +879,7 @@ int launch_conv_pair(const CUtensorMap& ma, const CUtensorMap& mb, const ConvPar
   attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = g_mz_pdl ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_pair_tc_kernel, ma, mb, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_pair_tc_kernel, ma, mb, mw, p, window);
   if (e != cudaSuccess) return (int)e;
   MZ_LAUNCH_CHECK();
   return MZ_OK;
@@ -1059,12 +1116,21 @@ int mz_conv3x3_tc(int32_t games, int32_t width, int32_t channels, const void* x,
   p.out_scaled = (__nv_bfloat16*)out_scaled;
   p.pool_out = (__nv_bfloat16*)pool_out;
   p.pool_row_base = pool_row_base;
-  if (channels == 128 && g_conv_pair) return launch_conv_pair(ma, mb, p, stream);
+  if (channels == 128 && g_conv_pair) {
+    const int window = (g_conv_pair >= 2 && wp + 1 <= P_WIN_PAD) ? 1 : 0;
+    CUtensorMap mw = ma;
+    if (window) {
+      rc = make_map(&mw, x, (uint64_t)rows, (uint64_t)channels, P_WIN_ROWS);
+      if (rc) return rc;
+    }
+    return launch_conv_pair(ma, mb, mw, p, window, stream);
+  }
   return launch_conv(ma, mb, p, stream);
 }
 
-int mz_conv_set_pair(int32_t enable) {
-  g_conv_pair = enable ? 1 : 0;
+int mz_conv_set_pair(int32_t mode) {
+  if (mode < 0 || mode > 2) return MZ_ERR_BAD_ARG;
+  g_conv_pair = mode;
   return MZ_OK;
 }
 

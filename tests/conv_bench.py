@@ -6,7 +6,7 @@ from model_based_rl_b200 import _lib
 from model_based_rl_b200.muzero import MuZeroNetwork, random_state_dict, ROWS, CH
 cfg = types.SimpleNamespace(value_support=[-15, 15], reward_support=[-15, 15], no_support=False, no_target_transform=False)
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-_lib.load().mz_conv_set_pair(int(os.environ.get("MZ_CONV_PAIR", "1")))  # 0: single-CTA kernel (A/B runs)
+_lib.load().mz_conv_set_pair(int(os.environ.get("MZ_CONV_PAIR", "2")))  # 0: single-CTA kernel (A/B runs)
 net = MuZeroNetwork(32, 18, "cuda", cfg)
 net.load_weights(random_state_dict(32, 18))
 x = torch.rand((G * ROWS, CH), device="cuda").to(torch.bfloat16)

@@ -71,8 +71,8 @@ def test_conv_kernel_matches_conv2d(games, flags):
 @pytest.mark.parametrize("games,width,flags", [(1, 6, 1), (2, 6, 3), (3, 6, 3), (301, 6, 1 | 2 | 8), (5, 6, 1 | 4),
                                                (3, 12, 3), (2, 24, 1)])
 def test_conv_pair_kernel_equals_single_cta_kernel(games, width, flags):
-  """The CTA-pair kernel (tcgen05.mma.cta_group::2, M = 256, resident weights) against the single-CTA
-  kernel on the same operands: same K order and float32 accumulation, same epilogue -> identical bits.
+  """The CTA-pair kernel (tcgen05.mma.cta_group::2, M = 256, resident weights), with one activation load
+  per tap (mode 1) and with one row window per tile (mode 2), against the single-CTA kernel on the same operands: same K order and float32 accumulation, same epilogue -> identical bits.
   Odd tile counts (the pair's second half past the end), tiles straddling games, every epilogue."""
   from model_based_rl_b200 import _lib, muzero
   lib = _lib.load()
@@ -89,8 +89,8 @@ def test_conv_pair_kernel_equals_single_cta_kernel(games, width, flags):
   P = _lib.ptr
   outs = []
   try:
-    for pair in (0, 1):
-      lib.mz_conv_set_pair(pair)
+    for pair in (0, 1, 2):
+      assert lib.mz_conv_set_pair(pair) == 0
       out = torch.full((games * wp * wp, 128), 7.0, dtype=torch.bfloat16, device=dev)
       scaled = torch.full((games * wp * wp, 128), 7.0, dtype=torch.bfloat16, device=dev)
       for _ in range(2):  # the second launch reuses barriers / TMEM of a warm SM
@@ -101,10 +101,11 @@ def test_conv_pair_kernel_equals_single_cta_kernel(games, width, flags):
       torch.cuda.synchronize()
       outs.append((out, scaled))
   finally:
-    lib.mz_conv_set_pair(1)
-  assert torch.equal(outs[0][0], outs[1][0]), float((outs[0][0].float() - outs[1][0].float()).abs().max())
-  if flags & 8:
-    assert torch.equal(outs[0][1], outs[1][1])
+    lib.mz_conv_set_pair(2)
+  for mode in (1, 2):
+    assert torch.equal(outs[0][0], outs[mode][0]), (mode, float((outs[0][0].float() - outs[mode][0].float()).abs().max()))
+    if flags & 8:
+      assert torch.equal(outs[0][1], outs[mode][1]), mode
 
 
 @pytest.mark.parametrize("width,games,ch", [(12, 3, 128), (24, 2, 128), (48, 2, 64)])
