@@ -491,24 +491,15 @@ MZ_DEV void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint
     asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
 }
-MZ_DEV void mbar_arrive_leader(uint64_t* bar, uint32_t rank) {  // release at cluster scope
-  if (rank == 0) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-  } else {
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-  }
-}
-MZ_DEV void mbar_wait_cluster_acq(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
+// Accumulator hand-back to the leader's MMA warp.  Relaxed on purpose: what the arrival has to order is
+// the epilogue's TMEM reads (complete after tcgen05.wait::ld, ordered by tcgen05.fence::before_thread_sync),
+// not its global stores -- a releasing arrive compiles to MEMBAR + ERRBAR (.cta) or MEMBAR.ALL.GPU +
+// CCTL.IVALL (.cluster) and made every epilogue warp wait for its output rows to drain (ncu: 18 % of the
+// kernel's stall samples).
+MZ_DEV void mbar_arrive_leader(uint64_t* bar, uint32_t rank) {
+  uint32_t addr = smem_u32(bar);
+  if (rank != 0) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(addr) : "r"(smem_u32(bar)), "r"(0));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 // D = f32, A = B = bf16, both K-major, M = 256 over the CTA pair, N = 128
 constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -541,7 +532,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 256);  // the epilogue threads of both CTAs
+      mbar_init(&acc_empty[i], 8);  // one arrival per epilogue warp of both CTAs
     }
     mbar_init(b_full, 1);
     mbar_fence_init();
@@ -612,7 +603,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int it = 0, t = 0;
       for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++t) {
         const int acc = t & 1;
-        mbar_wait_cluster_acq(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+        mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem + acc * BN;
         if (window) {
@@ -768,7 +759,8 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
       }
       tc_fence_before();
-      mbar_arrive_leader(&acc_empty[acc], rank);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&acc_empty[acc], rank);
     }
   }
 
