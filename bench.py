@@ -468,9 +468,9 @@ def bench_conv(args, torch, _lib, dev):
   us_conv = a.elapsed_time(b) * 1e3 / n
   peaks = measured_peaks()
   flops = 2.0 * G * 36 * 128 * 1152  # algorithmic: interior pixels only (the padded rows are overhead)
-  roof = {"kernel": "conv_gemm_tc_kernel", "bound": "tensor", "achieved": flops / us_conv / 1e6,
+  roof = {"kernel": "conv_pair_tc_kernel", "bound": "tensor", "achieved": flops / us_conv / 1e6,
           "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-          "traffic": 108.1e6 if (G, C_in) == (4096, 32) else None,  # ncu, profiles/r01m_ncu_summary.md
+          "traffic": 56.5e6 if (G, C_in) == (4096, 32) else None,  # ncu, profiles/r01o_ncu_summary.md
           "algorithmic_flops_per_launch": flops, "avg_launch_us": us_conv,
           "issued_tflops": 2.0 * G * ROWS * 128 * 1152 / us_conv / 1e6, "peak_source": peaks["source"]}
   roof["frac"] = roof["achieved"] / roof["peak"]

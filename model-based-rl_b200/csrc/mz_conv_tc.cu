@@ -165,7 +165,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], 4);  // one (relaxed) arrival per epilogue warp
     }
     mbar_fence_init();
     tma_prefetch_desc(&map_a);
@@ -404,8 +404,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
       }
       }  // u
+      // relaxed: the hand-back orders TMEM reads (tcgen05.wait::ld + fence), not this warp's global stores
       tc_fence_before();
-      mbar_arrive(&acc_empty[acc]);
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[acc])) : "memory");
     }
   }
 
