@@ -70,9 +70,13 @@ def search_config(args):
       reward_support=[-15, 15], no_support=False, no_target_transform=False)
 
 
-def synthetic_inputs(args, rank, games):
+def synthetic_inputs(args, rank, games, as_bytes=False):
+  """Observations are `obs_dim` bytes per game (Breakout-ram style, README.md:56); the float32 form is
+  the reference's `--obs_range 0 255 --norm_obs` normalisation of the same bytes."""
   rng = np.random.default_rng(1234 + rank)
-  obs = (rng.integers(0, 256, size=(games, args.obs_dim)).astype(np.float32) / 255.0)
+  obs = rng.integers(0, 256, size=(games, args.obs_dim)).astype(np.uint8)
+  if not as_bytes:
+    obs = obs.astype(np.float32) / np.float32(255.0)
   noise = rng.dirichlet([0.25] * args.actions, size=games)
   uniforms = rng.random(games)
   temperature = np.ones(games)
@@ -275,7 +279,12 @@ def run_b200(args):
   obs, noise, uniforms, temperature = synthetic_inputs(args, rank, G)
   pin = lambda a: torch.from_numpy(a).pin_memory()
   h_obs, h_noise, h_u, h_t = pin(obs), pin(noise), pin(uniforms), pin(temperature)
+  # end to end the observations cross PCIe as the bytes the emulator produces; the device normalises them
+  h_obs_u8 = pin(synthetic_inputs(args, rank, G, as_bytes=True)[0])
+  fs.search_host(h_obs_u8, h_noise, h_u, h_t)
+  obs_from_bytes = fs.obs.clone()
   fs.search_host(h_obs, h_noise, h_u, h_t)  # also leaves the inputs resident in HBM
+  assert torch.equal(obs_from_bytes, fs.obs), "device-side normalisation differs from numpy's"
 
   flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
   # learner side at N > 1 (BASELINE config C4 "with learner allreduce"): one gradient-sized
@@ -314,7 +323,7 @@ def run_b200(args):
   ms_total = timed(fs.run, args.steps)
   barrier()
   # end-to-end: host buffers in, host buffers out, through the public call
-  ms_e2e = timed(lambda: fs.search_host(h_obs, h_noise, h_u, h_t), args.steps)
+  ms_e2e = timed(lambda: fs.search_host(h_obs_u8, h_noise, h_u, h_t), args.steps)
   barrier()
   clock_info = clocks.stop() if rank == 0 else None
 
@@ -380,7 +389,9 @@ def run_b200(args):
         "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 (tree) / %s (network)" % ("bf16 tcgen05, f32 accumulate" if args.precision == "bf16" else "f32"),
         "data": "synthetic", "config": workload_config(args, world),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": fs.h2d_bytes(),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": fs.h2d_bytes(1),
+                "inputs": "pinned host: uint8 observations (normalised on the device), float64 noise / uniforms / "
+                          "temperatures",
                 "d2h_bytes_per_step": fs.d2h_bytes(), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": fs.launches_per_move * args.steps,
         "clocks": clock_info, "roofline": dominant, "roofline_all": [roof_tree, roof_fc],

@@ -194,6 +194,12 @@ typedef struct mz_fc_weights { /* device pointers, float32.  First layers (*_w1)
   const float *ln_w, *ln_b;                        /* LN                   networks.py:144 */
 } mz_fc_weights;
 
+/* Observation ingest for byte observations (Breakout-ram: 128 bytes, README.md:56 `--obs_range 0 255
+ * --norm_obs`): out[r][k] = (float(obs[r][k]) - obs_min[k]) / obs_range[k] in float32, the arithmetic of
+ * actors.py:127-129 / learners.py:170-171.  obs_min / obs_range [obs_dim] f32; NULL = 0 / 255. */
+int mz_obs_normalize_u8(int64_t rows, int32_t obs_dim, const uint8_t* obs, const float* obs_min,
+                        const float* obs_range, float* out, void* stream);
+
 /*
  * float32 reference-precision path (CUDA cores).
  * BaseNetwork.initial_inference (networks.py:26-29): obs [B][obs_dim] f32 ->

@@ -85,6 +85,7 @@ _SIGNATURES = {
     "mz_select_action": (C.c_int, [C.c_int32, C.c_int32, _V, _V, _V, _V, _V, _V]),
     "mz_exp_f32": (C.c_int, [C.c_int64, _V, _V, _V]),
     "mz_tree_export": (C.c_int, [C.POINTER(Tree), C.c_int32, _V, _V, _V, _V, _V, _V]),
+    "mz_obs_normalize_u8": (C.c_int, [C.c_int64, C.c_int32, _V, _V, _V, _V, _V]),
     "mz_fc_initial_f32": (C.c_int, [C.POINTER(FcWeights), C.c_int32, _V, _V, C.c_int64, _V, _V, _V]),
     "mz_fc_recurrent_f32": (C.c_int, [C.POINTER(FcWeights), C.c_int32, _V, C.c_int64, _V, _V, _V,
                                       C.c_int64, C.c_int64, _V, _V, _V, _V]),

@@ -211,7 +211,30 @@ int check_weights(const mz_fc_weights* w, bool need_rep) {
 
 }  // namespace
 
+// Observation ingest: the learner / actor normalisation `(obs - obs_min) / obs_range` (actors.py:127-129,
+// learners.py:170-171; float32 numpy arithmetic) for byte observations, on the device, so that only the
+// bytes cross PCIe.  One rounding per operation like numpy.
+__global__ void obs_normalize_u8_kernel(long long n, int obs_dim, const uint8_t* __restrict__ in,
+                                        const float* __restrict__ obs_min, const float* __restrict__ obs_range,
+                                        float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % obs_dim);
+    const float x = (float)in[i];
+    out[i] = __fdiv_rn(__fsub_rn(x, obs_min ? obs_min[k] : 0.0f), obs_range ? obs_range[k] : 255.0f);
+  }
+}
+
 extern "C" {
+
+int mz_obs_normalize_u8(int64_t rows, int32_t obs_dim, const uint8_t* obs, const float* obs_min,
+                        const float* obs_range, float* out, void* stream) {
+  if (rows < 1 || obs_dim < 1 || !obs || !out) return MZ_ERR_BAD_ARG;
+  const long long n = (long long)rows * obs_dim;
+  const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  obs_normalize_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, obs_dim, obs, obs_min, obs_range, out);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
 
 int mz_fc_initial_f32(const mz_fc_weights* w, int32_t batch, const float* obs, float* hidden,
                       int64_t hidden_stride, float* value, float* logits, void* stream) {

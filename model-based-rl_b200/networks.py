@@ -374,6 +374,7 @@ class FCSearch(object):
           root_value=torch.zeros(G, dtype=torch.float64, **pin),
           child_visits=torch.zeros((G, A), dtype=torch.float64, **pin),
           init_value=torch.zeros(G, dtype=torch.float32, **pin),
+          obs_u8=torch.zeros((G, self.net.input_dim), dtype=torch.uint8, **pin),
           legal=torch.zeros(G, dtype=torch.int32, **pin),
           to_play=torch.ones(G, dtype=torch.int8, **pin))
     return self._h
@@ -381,7 +382,9 @@ class FCSearch(object):
   def search_host(self, obs, noise=None, uniforms=None, temperature=None, legal=None, to_play=None):
     """The per-move body of Actor.play_game (actors.py:131-153) for G games.
 
-    Inputs are HOST arrays (numpy or CPU tensors): obs [G, input_dim] float32, Dirichlet noise
+    Inputs are HOST arrays (numpy or CPU tensors): obs [G, input_dim] float32 -- or uint8, in which
+    case only the bytes cross PCIe and `(obs - obs_min) / obs_range` (actors.py:127-129, set with
+    `set_obs_normalization`, default 0 / 255) runs on the device in the same float32 arithmetic --, Dirichlet noise
     [G, A] float64 (row g: one value per legal action of game g, in action order), uniforms [G]
     float64 (action sampling), temperature [G] float64, and optionally the roots' legal-action bit
     masks [G] (bit a = action a is legal, actors.py:141-142) and to_play [G] (+1 / -1).  Returns
@@ -398,7 +401,17 @@ class FCSearch(object):
         h[name].copy_(t)
         t = h[name]
       dst.copy_(t, non_blocking=True)
-    stage('obs', obs, self.obs)
+    t_obs = obs if torch.is_tensor(obs) else torch.from_numpy(obs)
+    if t_obs.dtype == torch.uint8:
+      if getattr(self, 'obs_u8', None) is None:
+        self.obs_u8 = torch.zeros((self.G, self.net.input_dim), dtype=torch.uint8, device=self.obs.device)
+      stage('obs_u8', t_obs, self.obs_u8)
+      mn, rg = getattr(self, '_obs_norm', (None, None))
+      _lib.check(self.net.lib.mz_obs_normalize_u8(self.G, self.net.input_dim, _lib.ptr(self.obs_u8), _lib.ptr(mn),
+                                                  _lib.ptr(rg), _lib.ptr(self.obs), _lib.current_stream()),
+                 "mz_obs_normalize_u8")
+    else:
+      stage('obs', t_obs, self.obs)
     stage('noise', noise, self.noise)
     stage('uniforms', uniforms, self.uniforms)
     stage('temperature', temperature, self.temperature)
@@ -415,8 +428,15 @@ class FCSearch(object):
     torch.cuda.current_stream().synchronize()
     return h['actions'], h['root_value'], h['child_visits'], h['init_value']
 
-  def h2d_bytes(self):
-    return (self.obs.numel() * 4 + self.noise.numel() * 8 + self.uniforms.numel() * 8 +
+  def set_obs_normalization(self, obs_min, obs_range):
+    """Per-feature float32 obs_min / obs_range (config.obs_range[::2], max - min: actors.py:60-63) for
+    uint8 observations handed to `search_host`."""
+    dev = self.obs.device
+    self._obs_norm = (torch.as_tensor(obs_min, dtype=torch.float32).to(dev).contiguous(),
+                      torch.as_tensor(obs_range, dtype=torch.float32).to(dev).contiguous())
+
+  def h2d_bytes(self, obs_bytes_per_element=4):
+    return (self.obs.numel() * obs_bytes_per_element + self.noise.numel() * 8 + self.uniforms.numel() * 8 +
             self.temperature.numel() * 8)
 
   def d2h_bytes(self):

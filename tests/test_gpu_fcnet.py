@@ -141,3 +141,38 @@ def test_fc_search_replays_bit_exact_in_oracle():
     for i in range(G):
       assert int(actions[i]) == oracle.select_action(want["visits"][i], temp[i], u[i])
     assert fs.launches_per_move == streams * (2 * S + 5)
+
+
+@pytest.mark.gpu
+def test_search_host_uint8_observations_equal_float_observations():
+  """Byte observations normalised on the device ((x - min) / range in float32, actors.py:127-129) give
+  the same search, bit for bit, as the host-normalised float32 observations -- default 0 / 255 and an
+  explicit per-feature range."""
+  import types
+  import numpy as np
+  import torch
+  from model_based_rl_b200.networks import FCNetwork, FCSearch, random_state_dict
+  G, A, S, D = 200, 4, 12, 128
+  cfg = types.SimpleNamespace(
+      num_simulations=S, action_space=A, two_players=False, discount=0.997, pb_c_base=19652, pb_c_init=1.25,
+      init_value_score=0.0, known_bounds=[None, None], root_exploration_fraction=0.25,
+      value_support=[-15, 15], reward_support=[-15, 15], no_support=False, no_target_transform=False)
+  net = FCNetwork(D, A, "cuda", cfg)
+  net.load_weights(random_state_dict(D, A))
+  fs = FCSearch(cfg, net, G, num_streams=2)
+  rng = np.random.default_rng(3)
+  obs_u8 = rng.integers(0, 256, size=(G, D)).astype(np.uint8)
+  noise, u, temp = rng.dirichlet([0.25] * A, size=G), rng.random(G), np.ones(G)
+  for mn, rg in ((None, None), (rng.integers(0, 4, D).astype(np.float32), rng.integers(200, 256, D).astype(np.float32))):
+    if mn is None:
+      want_obs = obs_u8.astype(np.float32) / np.float32(255)
+    else:
+      fs.set_obs_normalization(mn, rg)
+      want_obs = (obs_u8.astype(np.float32) - mn) / rg
+    a = [t.clone() for t in fs.search_host(want_obs, noise, u, temp)]
+    visits_a = fs.visits.clone()
+    b = [t.clone() for t in fs.search_host(obs_u8, noise, u, temp)]
+    assert np.array_equal(fs.obs.cpu().numpy(), want_obs)
+    assert torch.equal(visits_a, fs.visits)
+    for x, y in zip(a, b):
+      assert torch.equal(x, y)
