@@ -39,7 +39,7 @@ def unroll_loss_ref(config, values, rewards, policies, t_values, t_rewards, t_po
   vmin, vmax = [int(v) for v in config.value_support]
   rmin, rmax = [int(v) for v in config.reward_support]
   no_tt = bool(getattr(config, 'no_target_transform', False))
-  K = len(rewards)
+  K = len(rewards)  # lists of per-step logits or stacked [steps, B, bins] tensors
   with torch.no_grad():
     init_value = support_to_scalar(values[0], vmin, vmax, no_tt)
     new_errors = init_value.squeeze(1) - t_values[:, 0]

@@ -93,6 +93,22 @@ def test_oracle_learner_step_matches_reference_golden(case):
   _check_against_golden(g, learner, net, tol=1e-6)
 
 
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("batched", [True, False])
+def test_product_network_unroll_matches_reference_golden(case, batched):
+  """The product's torch module through Learner on the CPU with the oracle loss: the batched-heads unroll
+  (FCNetworkTrain.unroll: one head evaluation over all K+1 hidden states) and the step-by-step path both
+  reproduce the reference's two steps (losses 1e-6 relative, weights 1e-6 absolute: GEMM row blocking
+  differs with the batch shape)."""
+  from model_based_rl_b200 import learners
+  g = helpers.load("learner_" + case)
+  cfg = _config(g)
+  net = learners.FCNetworkTrain(int(g["obs_dim"]), int(g["action_space"]), "cpu", cfg)
+  net.load_weights(_weights(g))
+  learner = learners.Learner(cfg, net, loss_fn=learner_ref.unroll_loss_ref, batched_heads=batched)
+  _check_against_golden(g, learner, net, tol=1e-6)
+
+
 def test_product_train_network_has_reference_keys_and_outputs():
   """FCNetworkTrain (torch module of the product) == the oracle network on the golden weights."""
   from model_based_rl_b200 import learners
