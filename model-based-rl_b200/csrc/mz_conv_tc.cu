@@ -676,6 +676,14 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)R * NC);
 #pragma unroll
         for (int q = 0; q < BN / 8; ++q) resv[q] = add_res ? rp[q] : make_uint4(0u, 0u, 0u, 0u);
+        // the residual is the block's input, written two launches ago: usually evicted from L2 by now.
+        // Start the next tile's rows towards L2 while this tile is processed.
+        const long long Rn = (long long)R + (long long)num_clusters * 2 * BM;
+        if (Rn < p.rows_total) {
+          const uint8_t* np_ = reinterpret_cast<const uint8_t*>(p.residual + (size_t)Rn * NC);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(np_));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + 128));
+        }
       }
       float act_scale = 0.0f;
       const float* plane = nullptr;
