@@ -373,6 +373,7 @@ MZ_DEV void descend_loop(const mz_tree& t, typename ImgLoad<STAGED>::Addr nodes,
   const int prior_off = MZ_NODE_STATS_BYTES + 8 * sp, child_off = MZ_NODE_STATS_BYTES + 8 * A + 2 * sp;
   const double* table = t.pb_c_table;
   int node = 0, depth = 0, parent, action;
+  const double* row = table + N * SP1;  // pb_c[N][.] of the node being expanded (warp-uniform)
   for (;;) {
     const typename L::Addr rec = nodes + node * NB;
     const double prior = L::f64(rec + prior_off);
@@ -381,26 +382,24 @@ MZ_DEV void descend_loop(const mz_tree& t, typename ImgLoad<STAGED>::Addr nodes,
     const NodeHead c = L::head(nodes + max(ch, 0) * NB);
     const int n = ch >= 0 ? c.visit : 0;
     // ucb_score mcts.py:115-124
-    const double pb_c = __ldg(table + N * SP1 + n);
-    double value_score = init_score;
-    if (n > 0) {
-      if (MODE == 0) {
-        value_score = c.q;
-      } else if (MODE == 1) {
-        value_score = 1.0;
-      } else {
-        const double x = __dsub_rn(c.q, mn);
-        if (MODE == 2) {
-          const unsigned hx = (unsigned)__double2hiint(x);  // x >= 0 because min <= q
-          if (__builtin_expect(hx - 0x33700000u > 0x19000000u, 0))  // 0, or outside [2^-200, 2^200]
-            value_score = (x == 0.0) ? 0.0 : __ddiv_rn(x, d);
-          else
-            value_score = div_by_const(x, d, r);
-        } else {
-          value_score = __ddiv_rn(x, d);
-        }
-      }
+    const double pb_c = __ldg(row + n);
+    double value_score;
+    if (MODE == 0) {
+      value_score = c.q;
+    } else if (MODE == 1) {
+      value_score = 1.0;
+    } else if (MODE == 3) {
+      value_score = __ddiv_rn(__dsub_rn(c.q, mn), d);
+    } else {
+      // every lane evaluates the constant-divisor division (lanes without a visited child discard it);
+      // only a visited child outside [2^-200, 2^200] (or exactly at the minimum) takes the IEEE path
+      const double x = __dsub_rn(c.q, mn);
+      value_score = div_by_const(x, d, r);
+      const unsigned hx = (unsigned)__double2hiint(x);  // x >= 0 because min <= q
+      if (__builtin_expect(n > 0 && hx - 0x33700000u > 0x19000000u, 0))
+        value_score = (x == 0.0) ? 0.0 : __ddiv_rn(x, d);
     }
+    if (n <= 0) value_score = init_score;
     const double score = __dadd_rn(__dmul_rn(pb_c, prior), value_score);
     const int best = warp_argmax(score, ch != MZ_CHILD_ILLEGAL);
     const int src = best < 0 ? 0 : best;
@@ -413,8 +412,8 @@ MZ_DEV void descend_loop(const mz_tree& t, typename ImgLoad<STAGED>::Addr nodes,
       break;
     }
     node = ch_b;
-    N = n_b;
-    if (lane == 0) path[depth] = (int16_t)node;
+    row = table + n_b * SP1;
+    path[depth] = (int16_t)node;  // every lane stores the same value to the same address
   }
   out_depth = depth;
   out_parent = parent;

@@ -1,6 +1,7 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r01o_tests.log 2>&1; echo tests_rc=$?; tail -3 gpurun_out/r01o_tests.log
-timeout 400 python bench.py > gpurun_out/r01o_bench.json 2> gpurun_out/r01o_bench.err; echo bench_rc=$?
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_pair_tc -s 30 -c 1 -o gpurun_out/r01o_conv_pair python tests/conv_bench.py 4096 > gpurun_out/r01o_ncu_conv.log 2>&1; echo ncu1_rc=$?
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:unroll_loss_kernel -s 5 -c 1 -o gpurun_out/r01o_unroll_loss python bench.py --no-conv --no-sweep --no-cpu-baseline --steps 2 --warmup 1 > gpurun_out/r01o_ncu_loss.log 2>&1; echo ncu2_rc=$?
-ls -la gpurun_out/
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r01p_tests.log 2>&1; echo tests_rc=$?; tail -3 gpurun_out/r01p_tests.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 400 python bench.py > gpurun_out/r01p_bench.json 2> gpurun_out/r01p_bench.err; echo bench_rc=$?
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r01p_ref.json 2> gpurun_out/r01p_ref.err; echo ref_rc=$?
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r01p_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-sweep --conv-games 1024 > gpurun_out/r01p_ncu_bench.log 2>&1; echo ncu_rc=$?
+ls -la gpurun_out/ | tail -8
