@@ -284,18 +284,22 @@ class FCSearch(object):
     self.use_noise = True
     self.launches_per_move = 0
     self.obs = torch.zeros((G, fcnet.input_dim), dtype=torch.float32, device=dev)
-    self.noise = torch.zeros((G, A), dtype=torch.float64, device=dev)
-    self.legal = torch.full((G,), (1 << A) - 1, dtype=torch.int64, device=dev).to(torch.int32)
-    self.to_play = torch.ones(G, dtype=torch.int8, device=dev)
-    self.temperature = torch.ones(G, dtype=torch.float64, device=dev)
-    self.uniforms = torch.zeros(G, dtype=torch.float64, device=dev)
+    # host-visible inputs / outputs live in two blobs so that the end-to-end call moves each with ONE copy
+    self._in_specs = [('noise', torch.float64, (G, A)), ('uniforms', torch.float64, (G,)),
+                      ('temperature', torch.float64, (G,)), ('legal', torch.int32, (G,)),
+                      ('to_play', torch.int8, (G,)), ('obs_u8', torch.uint8, (G, fcnet.input_dim))]
+    self._out_specs = [('root_value', torch.float64, (G,)), ('child_visits', torch.float64, (G, A)),
+                       ('actions', torch.int32, (G,)), ('init_value', torch.float32, (G,))]
+    self._in_dev, views = _carve(self._in_specs, device=dev)
+    self.__dict__.update(views)
+    self._out_dev, views = _carve(self._out_specs, device=dev)
+    self.__dict__.update(views)
+    self.legal.fill_((1 << A) - 1)
+    self.to_play.fill_(1)
+    self.temperature.fill_(1.0)
     self.root_logits = torch.zeros((G, A), dtype=torch.float32, device=dev)
-    self.init_value = torch.zeros(G, dtype=torch.float32, device=dev)
     self.visits = torch.zeros((G, A), dtype=torch.int32, device=dev)
-    self.child_visits = torch.zeros((G, A), dtype=torch.float64, device=dev)
-    self.root_value = torch.zeros(G, dtype=torch.float64, device=dev)
     self.minmax = torch.zeros((G, 2), dtype=torch.float64, device=dev)
-    self.actions = torch.zeros(G, dtype=torch.int32, device=dev)
     ns = max(1, min(int(num_streams), G))
     bounds = [(G * i) // ns for i in range(ns + 1)]
     self.lanes = []
@@ -363,21 +367,37 @@ class FCSearch(object):
   # -- end-to-end call: host buffers in, host buffers out ----------------------------------------
   def _pinned(self):
     if getattr(self, '_h', None) is None:
-      G, A = self.G, self.A
-      pin = dict(pin_memory=True)
-      self._h = dict(
-          obs=torch.zeros((G, self.net.input_dim), dtype=torch.float32, **pin),
-          noise=torch.zeros((G, A), dtype=torch.float64, **pin),
-          uniforms=torch.zeros(G, dtype=torch.float64, **pin),
-          temperature=torch.ones(G, dtype=torch.float64, **pin),
-          actions=torch.zeros(G, dtype=torch.int32, **pin),
-          root_value=torch.zeros(G, dtype=torch.float64, **pin),
-          child_visits=torch.zeros((G, A), dtype=torch.float64, **pin),
-          init_value=torch.zeros(G, dtype=torch.float32, **pin),
-          obs_u8=torch.zeros((G, self.net.input_dim), dtype=torch.uint8, **pin),
-          legal=torch.zeros(G, dtype=torch.int32, **pin),
-          to_play=torch.ones(G, dtype=torch.int8, **pin))
+      self._in_host, h = _carve(self._in_specs, pin_memory=True)
+      self._out_host, out = _carve(self._out_specs, pin_memory=True)
+      h.update(out)
+      h['obs'] = torch.zeros((self.G, self.net.input_dim), dtype=torch.float32, pin_memory=True)
+      h['legal'].fill_((1 << self.A) - 1)
+      h['to_play'].fill_(1)
+      h['temperature'].fill_(1.0)
+      self._h = h
     return self._h
+
+  def pinned_inputs(self):
+    """Pinned host views of the per-move inputs (one contiguous blob): 'obs_u8' [G, input_dim] uint8,
+    'noise' [G, A] f64, 'uniforms' [G] f64, 'temperature' [G] f64, 'legal' [G] i32 bit masks, 'to_play'
+    [G] i8.  Write the move's inputs here and call `search_pinned()`: no host-side staging copy."""
+    h = self._pinned()
+    return {name: h[name] for name, _, _ in self._in_specs}
+
+  def search_pinned(self):
+    """search_host for inputs already written into `pinned_inputs()` (byte observations): ONE
+    host->device copy of the input blob, normalisation + the move's graph, ONE device->host copy of the
+    output blob.  Returns the pinned (actions, root_value, child_visits, init_value)."""
+    h = self._pinned()
+    self._in_dev.copy_(self._in_host, non_blocking=True)
+    mn, rg = getattr(self, '_obs_norm', (None, None))
+    _lib.check(self.net.lib.mz_obs_normalize_u8(self.G, self.net.input_dim, _lib.ptr(self.obs_u8), _lib.ptr(mn),
+                                                _lib.ptr(rg), _lib.ptr(self.obs), _lib.current_stream()),
+               "mz_obs_normalize_u8")
+    self.run()
+    self._out_host.copy_(self._out_dev, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h['actions'], h['root_value'], h['child_visits'], h['init_value']
 
   def search_host(self, obs, noise=None, uniforms=None, temperature=None, legal=None, to_play=None):
     """The per-move body of Actor.play_game (actors.py:131-153) for G games.
@@ -403,8 +423,6 @@ class FCSearch(object):
       dst.copy_(t, non_blocking=True)
     t_obs = obs if torch.is_tensor(obs) else torch.from_numpy(obs)
     if t_obs.dtype == torch.uint8:
-      if getattr(self, 'obs_u8', None) is None:
-        self.obs_u8 = torch.zeros((self.G, self.net.input_dim), dtype=torch.uint8, device=self.obs.device)
       stage('obs_u8', t_obs, self.obs_u8)
       mn, rg = getattr(self, '_obs_norm', (None, None))
       _lib.check(self.net.lib.mz_obs_normalize_u8(self.G, self.net.input_dim, _lib.ptr(self.obs_u8), _lib.ptr(mn),
@@ -421,10 +439,7 @@ class FCSearch(object):
       stage('to_play', np.ascontiguousarray(np.asarray(to_play, dtype=np.int8)), self.to_play)
     self.use_noise = noise is not None or self.use_noise
     self.run()
-    h['actions'].copy_(self.actions, non_blocking=True)
-    h['root_value'].copy_(self.root_value, non_blocking=True)
-    h['child_visits'].copy_(self.child_visits, non_blocking=True)
-    h['init_value'].copy_(self.init_value, non_blocking=True)
+    self._out_host.copy_(self._out_dev, non_blocking=True)  # the four outputs share one blob
     torch.cuda.current_stream().synchronize()
     return h['actions'], h['root_value'], h['child_visits'], h['init_value']
 
@@ -440,7 +455,31 @@ class FCSearch(object):
             self.temperature.numel() * 8)
 
   def d2h_bytes(self):
-    return self.G * 4 + self.G * 8 + self.G * self.A * 8 + self.G * 4
+    return self._out_dev.numel()
+
+  def h2d_blob_bytes(self):
+    return self._in_dev.numel()
+
+
+def _carve(specs, **alloc):
+  """One uint8 blob + typed views into it, every view 8-byte aligned."""
+  offs, off = [], 0
+  for _, dtype, shape in specs:
+    off = (off + 7) // 8 * 8
+    offs.append(off)
+    n = 1
+    for d in shape:
+      n *= d
+    off += n * torch.empty((), dtype=dtype).element_size()
+  blob = torch.zeros((off + 7) // 8 * 8, dtype=torch.uint8, **alloc)
+  views = {}
+  for (name, dtype, shape), o in zip(specs, offs):
+    n = 1
+    for d in shape:
+      n *= d
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    views[name] = blob[o:o + nbytes].view(dtype).view(shape)
+  return blob, views
 
 
 def random_state_dict(input_dim, action_space, value_bins=31, reward_bins=31, seed=1234):

@@ -176,3 +176,46 @@ def test_search_host_uint8_observations_equal_float_observations():
     assert torch.equal(visits_a, fs.visits)
     for x, y in zip(a, b):
       assert torch.equal(x, y)
+
+
+@pytest.mark.gpu
+def test_search_pinned_equals_search_host():
+  """Inputs written into the engine's pinned blob views + one copy per direction give what the per-array
+  call gives (legal masks and to_play included)."""
+  import types
+  import numpy as np
+  import torch
+  from model_based_rl_b200.networks import FCNetwork, FCSearch, random_state_dict
+  G, A, S, D = 130, 9, 10, 9
+  cfg = types.SimpleNamespace(
+      num_simulations=S, action_space=A, two_players=True, discount=1.0, pb_c_base=19652, pb_c_init=1.25,
+      init_value_score=0.0, known_bounds=[-1, 1], root_exploration_fraction=0.25,
+      value_support=[-15, 15], reward_support=[-15, 15], no_support=False, no_target_transform=False)
+  net = FCNetwork(D, A, "cuda", cfg, precision="f32")
+  net.load_weights(random_state_dict(D, A))
+  rng = np.random.default_rng(9)
+  obs_u8 = rng.integers(0, 3, size=(G, D)).astype(np.uint8)
+  legal = rng.integers(1, 1 << A, size=G).astype(np.int32)
+  to_play = rng.choice([-1, 1], size=G).astype(np.int8)
+  noise = np.zeros((G, A))
+  for i in range(G):
+    n = bin(int(legal[i])).count("1")
+    noise[i, :n] = rng.dirichlet([0.25] * n)
+  u, temp = rng.random(G), rng.choice([0.0, 0.5, 1.0], size=G)
+  outs = []
+  for mode in ("host", "pinned"):
+    fs = FCSearch(cfg, net, G, num_streams=2)
+    fs.set_obs_normalization(np.ones(D, np.float32), np.full(D, 2.0, np.float32))
+    if mode == "host":
+      r = fs.search_host(obs_u8, noise, u, temp, legal=legal, to_play=to_play)
+    else:
+      pin = fs.pinned_inputs()
+      for name, src in (("obs_u8", obs_u8), ("noise", noise), ("uniforms", u), ("temperature", temp),
+                        ("legal", legal), ("to_play", to_play)):
+        pin[name].copy_(torch.from_numpy(src))
+      r = fs.search_pinned()
+    outs.append([t.clone() for t in r] + [fs.visits.cpu()])
+    for g in range(G):
+      assert (int(legal[g]) >> int(r[0][g])) & 1  # only legal actions are played
+  for x, y in zip(*outs):
+    assert torch.equal(x, y)
