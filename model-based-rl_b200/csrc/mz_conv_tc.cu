@@ -521,6 +521,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* b_full = acc_empty + 2;        // [1] (used in the leader only)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);  // [128]
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_bias + BN) + 15) & ~(uintptr_t)15);  // [4 epilogue warps][32 rows][64 B]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -661,21 +662,45 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int quarter = warp & 3;
     const int r_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    // Row-per-thread global accesses cost 32 L1 wavefronts per warp instruction (32 rows x 16 bytes) and made
+    // the epilogue, not the MMA issuer, set the tile period of the residual variant (4 k L1 cycles per tile for
+    // loads + stores against 4.6 k cycles of MMA).  Rows therefore cross a 2 KB per-warp staging area in shared
+    // memory: global side = 8 rows x 64 contiguous bytes per instruction (lane -> row 8 i + lane / 4, 16-byte
+    // piece lane % 4), thread side = its own row; pieces are XOR-swizzled so both sides are conflict free.
+    const uint32_t stage = smem_u32(s_stage) + (uint32_t)quarter * 2048u;
+    const int c_row = lane >> 2, c_piece = lane & 3;  // coalesced side: row within a group of 8, piece
+    auto swz = [](int r, int k) { return (uint32_t)(r * 64 + ((k ^ ((r >> 1) & 3)) << 4)); };
+    auto sts = [](uint32_t a, uint4 v) {
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    };
+    auto lds = [](uint32_t a) {
+      uint4 v;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+      return v;
+    };
     int t = 0;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++t) {
       const int acc = t & 1;
       const int tm = 2 * pt + (int)rank;
-      const int R = tm * BM + r_in_tile;  // flat row
+      const int R = tm * BM + r_in_tile;  // flat row of this thread
       const int g = R / p.grows, pos = R - g * p.grows;
       const int py = (pos - p.wp) / p.wp, px = (pos - p.wp) - py * p.wp;
       const bool interior = pos >= p.wp && px < p.wp - 1;
       const bool in_range = R < p.rows_total;
       const bool add_res = (p.flags & EPI_RESIDUAL) && interior && in_range;
-      uint4 resv[BN / 8];
+      const int Rw = tm * BM + quarter * 32;  // first row of this warp
+      // residual rows of the warp, coalesced: resg[c * 4 + i] = row 8 i + lane / 4, channels 32 c + 8 (lane % 4) ..
+      uint4 resg[BN / 8];
       if (p.flags & EPI_RESIDUAL) {  // requested before the accumulator wait
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)R * NC);
 #pragma unroll
-        for (int q = 0; q < BN / 8; ++q) resv[q] = add_res ? rp[q] : make_uint4(0u, 0u, 0u, 0u);
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int Rq = Rw + 8 * i + c_row;
+            resg[c * 4 + i] = Rq < p.rows_total
+                                  ? *reinterpret_cast<const uint4*>(p.residual + (size_t)Rq * NC + c * 32 + c_piece * 8)
+                                  : make_uint4(0u, 0u, 0u, 0u);
+          }
         // the residual is the block's input, written two launches ago: usually evicted from L2 by now.
         // Start the next tile's rows towards L2 while this tile is processed.
         const long long Rn = (long long)R + (long long)num_clusters * 2 * BM;
@@ -694,8 +719,18 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_wait(&acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
       const uint32_t d = lane_addr + acc * BN;
-      uint4* orow = reinterpret_cast<uint4*>(p.out + (size_t)R * NC);
+      // x[0..32) = layer output for channels c0..c0+31 of this thread's row (zero on the border)
       auto chunk = [&](int c0, float (&x)[32]) {
+        uint4 own[4];
+        if (p.flags & EPI_RESIDUAL) {  // the warp's residual rows for these 32 channels -> this thread's row
+          const int c = c0 >> 5;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sts(stage + swz(8 * i + c_row, c_piece), resg[c * 4 + i]);
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) own[k] = lds(stage + swz(lane, k));
+          __syncwarp();
+        }
         uint32_t v[32];
         tmem_ld32(d + c0, v);
         tmem_wait_ld();
@@ -708,8 +743,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (add_res) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 rv = resv[(c0 >> 3) + q];
-            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+            const uint32_t w[4] = {own[q].x, own[q].y, own[q].z, own[q].w};
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[h]);
@@ -727,6 +761,28 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           for (int j = 0; j < 32; ++j) x[j] = 0.0f;  // keep the zero border of the padded layout
         }
       };
+      // this thread's 32 packed channels -> staging -> 8 rows x 64 contiguous bytes per store instruction
+      auto store_rows = [&](__nv_bfloat16* base, int c0, const float (&x)[32], const int32_t* row_base) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sts(stage + swz(lane, k), make_uint4(pack_bf16(x[k * 8], x[k * 8 + 1]), pack_bf16(x[k * 8 + 2], x[k * 8 + 3]),
+                                               pack_bf16(x[k * 8 + 4], x[k * 8 + 5]), pack_bf16(x[k * 8 + 6], x[k * 8 + 7])));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 o = lds(stage + swz(8 * i + c_row, c_piece));
+          const int Rq = Rw + 8 * i + c_row;
+          if (Rq < p.rows_total) {
+            size_t orow_q = (size_t)Rq;
+            if (row_base) {  // scatter into the hidden pool: game g's rows start at row_base[g]
+              const int gq = Rq / p.grows;
+              orow_q = (size_t)row_base[gq] + (size_t)(Rq - gq * p.grows);
+            }
+            *reinterpret_cast<uint4*>(base + orow_q * NC + c0 + c_piece * 8) = o;
+          }
+        }
+        __syncwarp();
+      };
       float mn = INFINITY, mx = -INFINITY;
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -739,18 +795,9 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mx = fmaxf(mx, x[j]);
           }
         }
-        if (in_range && p.out) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            orow[(c0 >> 3) + q] = make_uint4(pack_bf16(x[q * 8], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
-                                             pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
-        }
+        if (p.out) store_rows(p.out, c0, x, nullptr);
       }
       if (p.flags & EPI_SCALE) {  // MuZeroNetwork.scale_state networks.py:543-547 (second pass)
-        uint4* so = reinterpret_cast<uint4*>(p.out_scaled + (size_t)R * NC);
-        uint4* po = (p.pool_out && in_range)
-                        ? reinterpret_cast<uint4*>(p.pool_out + ((size_t)p.pool_row_base[g] + pos) * NC)
-                        : nullptr;
         const float den = mx - mn;
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -758,15 +805,8 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           chunk(c0, x);
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = interior ? (x[j] - mn) / den : 0.0f;
-          if (in_range) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 o = make_uint4(pack_bf16(x[q * 8], x[q * 8 + 1]), pack_bf16(x[q * 8 + 2], x[q * 8 + 3]),
-                                         pack_bf16(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16(x[q * 8 + 6], x[q * 8 + 7]));
-              so[(c0 >> 3) + q] = o;
-              if (po) po[(c0 >> 3) + q] = o;
-            }
-          }
+          store_rows(p.out_scaled, c0, x, nullptr);
+          if (p.pool_out) store_rows(p.pool_out, c0, x, p.pool_row_base);
         }
       }
       tc_fence_before();
@@ -847,7 +887,7 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& 
 }
 
 constexpr size_t kPairSmem = 1024 + (size_t)P_KBLOCKS * P_BH_BYTES + (size_t)P_A_REGION +
-                             (2 * P_STAGES + 5) * sizeof(uint64_t) + 16 + BN * sizeof(float);
+                             (2 * P_STAGES + 5) * sizeof(uint64_t) + 16 + BN * sizeof(float) + 16 + 4 * 2048;
 // 128-channel 3x3 convolutions: 0 = single-CTA kernel, 1 = CTA-pair kernel with one activation load per
 // tap, 2 = CTA-pair kernel with one row window per tile where the image is narrow enough (wider images
 // fall back to 1)
