@@ -453,6 +453,7 @@ constexpr int P_WIN_BYTES = 2 * P_WIN_HALF;             // 36 KB per tile
 constexpr int P_WIN_STAGES = 2;
 constexpr int P_A_REGION = P_WIN_STAGES * P_WIN_BYTES > P_STAGES * P_A_BYTES ? P_WIN_STAGES * P_WIN_BYTES
                                                                              : P_STAGES * P_A_BYTES;
+constexpr int P_ACC = 2;                                // accumulator buffers in TMEM (4 measured: no gain, the tile period is the MMA time at the power-capped clock)
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;          // shared::cluster address -> same offset in the even CTA
 
 MZ_DEV uint32_t cluster_rank() {
@@ -516,9 +517,9 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* s_a = smem + P_KBLOCKS * P_BH_BYTES;               // [P_STAGES][128 rows][64 k]
   uint64_t* full = reinterpret_cast<uint64_t*>(s_a + P_A_REGION);
   uint64_t* empty = full + P_STAGES;
-  uint64_t* acc_full = empty + P_STAGES;   // [2]
-  uint64_t* acc_empty = acc_full + 2;      // [2] (used in the leader only)
-  uint64_t* b_full = acc_empty + 2;        // [1] (used in the leader only)
+  uint64_t* acc_full = empty + P_STAGES;   // [P_ACC]
+  uint64_t* acc_empty = acc_full + P_ACC;  // [P_ACC] (used in the leader only)
+  uint64_t* b_full = acc_empty + P_ACC;    // [1] (used in the leader only)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);  // [128]
   uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_bias + BN) + 15) & ~(uintptr_t)15);  // [4 epilogue warps][32 rows][64 B]
@@ -534,7 +535,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < P_ACC; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 8);  // one arrival per epilogue warp of both CTAs
     }
@@ -547,7 +548,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   cluster_sync();  // both CTAs' barriers exist before anything is signalled across the pair
   if (warp == 0) {
-    tmem_alloc_pair(tmem_ptr, 2 * BN);
+    tmem_alloc_pair(tmem_ptr, P_ACC * BN);
     tmem_relinquish_pair();
   }
   tc_fence_before();
@@ -606,8 +607,8 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tc_fence_after();
       int it = 0, t = 0;
       for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++t) {
-        const int acc = t & 1;
-        mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+        const int acc = t % P_ACC;
+        mbar_wait(&acc_empty[acc], ((t / P_ACC) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem + acc * BN;
         if (window) {
@@ -680,7 +681,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     };
     int t = 0;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++t) {
-      const int acc = t & 1;
+      const int acc = t % P_ACC;
       const int tm = 2 * pt + (int)rank;
       const int R = tm * BM + r_in_tile;  // flat row of this thread
       const int g = R / p.grows, pos = R - g * p.grows;
@@ -716,7 +717,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         act_scale = (float)p.actions[g] / (float)p.num_actions;
         plane = p.plane_term + (py * (p.wp - 1) + px) * NC;
       }
-      mbar_wait(&acc_full[acc], (t >> 1) & 1);
+      mbar_wait(&acc_full[acc], (t / P_ACC) & 1);
       tc_fence_after();
       const uint32_t d = lane_addr + acc * BN;
       // x[0..32) = layer output for channels c0..c0+31 of this thread's row (zero on the border)
@@ -821,7 +822,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   cluster_sync();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc_pair(tmem, 2 * BN);
+    tmem_dealloc_pair(tmem, P_ACC * BN);
   }
 }
 
@@ -887,7 +888,7 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& 
 }
 
 constexpr size_t kPairSmem = 1024 + (size_t)P_KBLOCKS * P_BH_BYTES + (size_t)P_A_REGION +
-                             (2 * P_STAGES + 5) * sizeof(uint64_t) + 16 + BN * sizeof(float) + 16 + 4 * 2048;
+                             (2 * P_STAGES + 2 * P_ACC + 1) * sizeof(uint64_t) + 16 + BN * sizeof(float) + 16 + 4 * 2048;
 // 128-channel 3x3 convolutions: 0 = single-CTA kernel, 1 = CTA-pair kernel with one activation load per
 // tap, 2 = CTA-pair kernel with one row window per tile where the image is narrow enough (wider images
 // fall back to 1)
