@@ -356,6 +356,19 @@ def run_b200(args):
       ms2 = timed(fs2.run, 5)
       sweep[str(g2)] = {"expansions_per_s": g2 * S * 5 / (ms2 * 1e-3), "ms_per_step": ms2 / 5}
       del fs2
+      # the two kernels' own rooflines at this batch (one slice, un-graphed, CUDA events per launch)
+      fs3 = FCSearch(cfg, net, g2, use_graph=False, num_streams=1)
+      for name, src in (("obs", o2), ("noise", n2), ("uniforms", u2), ("temperature", t2)):
+        getattr(fs3, name).copy_(torch.from_numpy(src).to(dev))
+      k2 = kernel_breakdown(fs3, torch)
+      del fs3
+      pk = measured_peaks()
+      tb = g2 * (k2["mean_depth"] * (28 * A + 33) + 16 * A + 86)
+      sweep[str(g2)]["kernels"] = {
+          "tree_step_us": k2["tree_step_us"], "fc_recurrent_us": k2["fc_recurrent_us"],
+          "tree_hbm_frac": tb / (k2["tree_step_us"] * 1e-6) / 1e9 / pk["hbm_gbs"],
+          "fc_tensor_frac": g2 * FC_FLOPS_PER_EXPANSION(A) / (k2["fc_recurrent_us"] * 1e-6) / 1e12 /
+                            pk["bf16_tflops_sustained"]}
   targets = bench_targets(torch, _lib, dev) if rank == 0 else None
   learner = bench_learner(torch, _lib, dev, world, barrier)  # every rank: the step all-reduces at N > 1
   conv = bench_conv(args, torch, _lib, dev) if rank == 0 and not args.no_conv else None
