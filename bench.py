@@ -53,6 +53,8 @@ def parse():
                  help="game slices run on separate CUDA streams inside the move graph")
   p.add_argument("--precision", choices=["bf16", "f32"], default="bf16",
                  help="network kernel: bf16 tcgen05 tensor cores (default) or float32 CUDA cores")
+  p.add_argument("--wide-step-max-games", type=int, default=None,
+                 help="diagnostics: mz_tree_set_wide_step_max_games (trees with <= 16 actions)")
   p.add_argument("--no-conv", action="store_true", help="skip the C5 MuZeroNetwork section")
   p.add_argument("--no-sweep", action="store_true", help="skip the larger-batch throughput probe")
   p.add_argument("--conv-games", type=int, default=4096, help="C5: concurrent games per GPU")
@@ -266,6 +268,8 @@ def run_b200(args):
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
   _lib.load()
+  if args.wide_step_max_games is not None:
+    _lib.load().mz_tree_set_wide_step_max_games(args.wide_step_max_games)
 
   cfg = search_config(args)
   G, S, A = args.games, args.sims, args.actions

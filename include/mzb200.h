@@ -430,6 +430,11 @@ int mz_unroll_loss(const mz_loss_cfg* c, const float* value_logits, const float*
 int mz_debug_div_check(uint64_t seed, int32_t blocks, int32_t per_thread, uint64_t* mismatches,
                        uint64_t* tested, void* stream);
 
+/* mz_tree_step with at most 16 actions: batches of up to `max_games` games run on the warp-per-game kernel,
+ * larger ones on the sub-warp-per-game kernels (8 / 4 / 2 games per warp).  Default: INT32_MAX -- the
+ * warp-per-game kernel measured faster at every batch size; 0 = always sub-warps.  Results are identical. */
+int mz_tree_set_wide_step_max_games(int32_t max_games);
+
 /* The per-simulation kernels (tree step, recurrent network) are launched as programmatic dependents
  * (their prologues overlap the predecessor's tail; griddepcontrol.wait before the first dependent
  * read).  enable = 0 switches back to plain stream-ordered launches.  Default: enabled. */

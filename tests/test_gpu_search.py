@@ -50,8 +50,19 @@ def _run_golden(g):
   return eng, res
 
 
+@pytest.fixture(params=["wide", "subwarp"])
+def step_kernel(request):
+  """Trees with <= 16 actions have two step kernels (warp per game, the default; sub-warp per game beyond
+  mz_tree_set_wide_step_max_games): run the parity tests through both."""
+  from model_based_rl_b200 import _lib
+  lib = _lib.load()
+  lib.mz_tree_set_wide_step_max_games(0x7fffffff if request.param == "wide" else 0)
+  yield request.param
+  lib.mz_tree_set_wide_step_max_games(0x7fffffff)
+
+
 @pytest.mark.parametrize("case", SEARCH_CASES)
-def test_search_matches_reference_golden(case):
+def test_search_matches_reference_golden(case, step_kernel):
   g = load("search_" + case)
   eng, res = _run_golden(g)
   assert np.array_equal(res.visits.cpu().numpy(), g["visits"])
@@ -151,7 +162,7 @@ def _run_engine_vs_oracle(G, A, S, two_players, seed, fused, **kw):
     (37, 17, 200, False, True, {}),
     (3, 32, 700, True, True, {}),
 ])
-def test_search_matches_oracle_seeded(G, A, S, two, fused, kw):
+def test_search_matches_oracle_seeded(G, A, S, two, fused, kw, step_kernel):
   res, want = _run_engine_vs_oracle(G, A, S, two, 1234 + A, fused, **kw)
   assert np.array_equal(res.visits.cpu().numpy(), want["visits"])
   assert np.array_equal(res.trace_parent.cpu().numpy().T, want["trace_parent"])
