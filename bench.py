@@ -373,6 +373,7 @@ def run_b200(args):
           "tree_hbm_frac": tb / (k2["tree_step_us"] * 1e-6) / 1e9 / pk["hbm_gbs"],
           "fc_tensor_frac": g2 * FC_FLOPS_PER_EXPANSION(A) / (k2["fc_recurrent_us"] * 1e-6) / 1e12 /
                             pk["bf16_tflops_sustained"]}
+  others = bench_other_configs(args, torch, dev, timed) if rank == 0 and world == 1 and not args.no_sweep else None
   targets = bench_targets(torch, _lib, dev) if rank == 0 else None
   learner = bench_learner(torch, _lib, dev, world, barrier)  # every rank: the step all-reduces at N > 1
   conv = bench_conv(args, torch, _lib, dev) if rank == 0 and not args.no_conv else None
@@ -416,7 +417,7 @@ def run_b200(args):
         "gpu_launches": fs.launches_per_move * args.steps,
         "clocks": clock_info, "roofline": dominant, "roofline_all": [roof_tree, roof_fc],
         "kernel_share": kern, "cuda_graph": not args.no_graph, "streams": len(fs.lanes),
-        "games_sweep": sweep, "targets": targets, "learner": learner,
+        "games_sweep": sweep, "other_configs": others, "targets": targets, "learner": learner,
         "conv": conv,
     }
     if cpu_baseline is not None:
@@ -424,6 +425,37 @@ def run_b200(args):
     emit(line)
   if world > 1:
     dist.destroy_process_group()
+
+
+def bench_other_configs(args, torch, dev, timed):
+  """The FCNetwork configurations of BASELINE.json besides C4, same move, resident inputs (parity-test
+  shapes; reported for orientation): C1 Tic-Tac-Toe (two players, known bounds -1 1), C2 LunarLander,
+  C3 Breakout-ram."""
+  import argparse
+  from model_based_rl_b200.networks import FCNetwork, FCSearch, random_state_dict
+  out = {}
+  for name, G, A, S, D, two, bounds in (("C1_tictactoe", 4096, 9, 30, 9, True, [-1, 1]),
+                                        ("C2_lunarlander", 1024, 4, 30, 8, False, [None, None]),
+                                        ("C3_breakout_ram", 4096, 4, 50, 128, False, [None, None])):
+    a2 = argparse.Namespace(**vars(args))
+    a2.games, a2.actions, a2.sims, a2.obs_dim = G, A, S, D
+    cfg = search_config(a2)
+    cfg.two_players, cfg.known_bounds = two, bounds
+    if two:
+      cfg.discount = 1.0
+    net = FCNetwork(D, A, dev, cfg, precision=args.precision)
+    net.load_weights({k: v.to(dev) for k, v in random_state_dict(D, A, seed=99).items()})
+    fs = FCSearch(cfg, net, G, use_graph=not args.no_graph, num_streams=args.streams)
+    obs, noise, u, t = synthetic_inputs(a2, 0, G)
+    fs.search_host(obs, noise, u, t)
+    for _ in range(3):
+      fs.run()
+    torch.cuda.synchronize()
+    ms = timed(fs.run, 5)
+    out[name] = {"games": G, "actions": A, "sims": S, "obs_dim": D, "expansions_per_s": G * S * 5 / (ms * 1e-3),
+                 "ms_per_move": ms / 5}
+    del fs
+  return out
 
 
 def kernel_breakdown(fs, torch):
