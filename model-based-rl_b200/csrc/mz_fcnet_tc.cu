@@ -207,6 +207,13 @@ MZ_DEV void st_cluster_v4(uint32_t addr, uint4 v) {
                "r"(v.w)
                : "memory");
 }
+// 16 bytes into the peer's shared memory; the store itself reports its bytes to the peer's mbarrier, so the
+// sender needs neither a cluster-scope fence (MEMBAR.ALL.GPU + ERRBAR in SASS) nor a separate arrival.
+MZ_DEV void st_async_v4(uint32_t addr, uint4 v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
+               : "memory");
+}
 MZ_DEV void mbar_arrive_remote(uint32_t cluster_addr) {  // release at cluster scope
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -384,7 +391,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     mbar_init(a3_ready, EPI_THREADS / 2);
     mbar_init(d2_full, 1);
     mbar_init(h_staged, EPI_THREADS / 2);
-    mbar_init(a3_remote, EPI_THREADS / 2);
+    mbar_init(a3_remote, 1);
+    if (split && rank == 0) mbar_arrive_expect_tx(a3_remote, ROWS * K3 * 2);  // the peer's st.async bytes
     mbar_init(h_stored, 1);
     mbar_fence_init();
   }
@@ -648,8 +656,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
         if (split) {
           const uint32_t a3_peer = map_to_cta(smem_u32(sA3), 0);
 #pragma unroll
-          for (int kb = 0; kb < K3 / 8; ++kb) st_cluster_v4(a3_peer + (uint32_t)canon_off(row, 8 * kb, ROWS), q[kb]);
-          mbar_arrive_remote(map_to_cta(smem_u32(a3_remote), 0));
+          const uint32_t bar_peer = map_to_cta(smem_u32(a3_remote), 0);
+#pragma unroll
+          for (int kb = 0; kb < K3 / 8; ++kb)
+            st_async_v4(a3_peer + (uint32_t)canon_off(row, 8 * kb, ROWS), q[kb], bar_peer);
         }
       }
       if (stamp) TC_STAMP(41);
