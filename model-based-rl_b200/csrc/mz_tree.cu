@@ -782,35 +782,36 @@ tree_step_w32_kernel(mz_tree t, int sim, int do_backup, int do_select, int live_
 }
 
 // game.py:106-111 + Node.value mcts.py:42-45
+// One warp per game, lane = action (the per-action loads are two dependent L2 accesses: child index ->
+// child's visit count; a thread per game serialised 2 A of them).
 __global__ void root_stats_kernel(mz_tree t, int32_t* __restrict__ visits,
                                   double* __restrict__ child_visits, double* __restrict__ root_value,
                                   double* __restrict__ minmax) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= t.num_games) return;
   const int A = t.num_actions;
   const MzGame gm{t.games + (size_t)g * t.game_bytes, t.node_bytes, A};
   const MzNode root = gm.node(0);
-  int v[MZ_MAX_ACTIONS];
-  long long sum = 0;
-  for (int a = 0; a < A; ++a) {
-    const int ch = root.child()[a];
-    v[a] = ch >= 0 ? gm.node(ch).visit() : 0;
-    sum += v[a];
+  int ch = MZ_CHILD_ILLEGAL, v = 0;
+  if (lane < A) {
+    ch = root.child()[lane];
+    v = ch >= 0 ? gm.node(ch).visit() : 0;
   }
-  for (int a = 0; a < A; ++a) {
-    if (visits) visits[(size_t)g * A + a] = v[a];
-    if (child_visits) {
-      const bool exists = root.child()[a] != MZ_CHILD_ILLEGAL;
-      child_visits[(size_t)g * A + a] = exists ? __ddiv_rn((double)v[a], (double)sum) : 0.0;
+  const int sum = __reduce_add_sync(MZ_FULL, v);  // integer: order does not matter
+  if (lane < A) {
+    if (visits) visits[(size_t)g * A + lane] = v;
+    if (child_visits)
+      child_visits[(size_t)g * A + lane] = ch != MZ_CHILD_ILLEGAL ? __ddiv_rn((double)v, (double)sum) : 0.0;
+  }
+  if (lane == 0) {
+    if (root_value) {
+      const int n = root.visit();
+      root_value[g] = n == 0 ? 0.0 : __ddiv_rn(root.vsum(), (double)n);
     }
-  }
-  if (root_value) {
-    const int n = root.visit();
-    root_value[g] = n == 0 ? 0.0 : __ddiv_rn(root.vsum(), (double)n);
-  }
-  if (minmax) {
-    minmax[2 * g] = gm.mn();
-    minmax[2 * g + 1] = gm.mx();
+    if (minmax) {
+      minmax[2 * g] = gm.mn();
+      minmax[2 * g + 1] = gm.mx();
+    }
   }
 }
 
@@ -832,59 +833,64 @@ __device__ double np_pairwise_sum(const double* a, int n) {
   return res;
 }
 
-// Config.select_action config.py:70-81
+// Config.select_action config.py:70-81.  One warp per game: the legal actions are compacted to lanes
+// 0..n-1 (action order, like the dict of children); pow, the two divisions and the comparison run one
+// candidate per lane, the two float64 sums keep numpy's order (pairwise add.reduce, sequential cumsum).
 __global__ void select_action_kernel(int G, int A, const int32_t* __restrict__ visits,
                                      const uint32_t* __restrict__ legal_mask,
                                      const double* __restrict__ temperature,
                                      const double* __restrict__ uniforms,
                                      int32_t* __restrict__ actions) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double s_d[4][MZ_MAX_ACTIONS];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * 4 + w;
   if (g >= G) return;
-  const uint32_t lm = legal_mask ? legal_mask[g] : 0xffffffffu;
-  int act[MZ_MAX_ACTIONS];
-  int cnt[MZ_MAX_ACTIONS];
-  int n = 0;
-  for (int a = 0; a < A; ++a)
-    if ((lm >> a) & 1u) {
-      act[n] = a;
-      cnt[n] = visits[(size_t)g * A + a];
-      ++n;
-    }
+  uint32_t lm = legal_mask ? legal_mask[g] : 0xffffffffu;
+  if (A < 32) lm &= (1u << A) - 1u;
+  const int n = __popc(lm);
   if (n == 0) {
-    actions[g] = -1;
+    if (lane == 0) actions[g] = -1;
     return;
   }
+  // lane i < n holds the i-th legal action
+  const int my_act = lane < n ? __fns(lm, 0, lane + 1) : 0;
+  const int cnt = lane < n ? visits[(size_t)g * A + my_act] : 0;
   const double T = temperature[g], u = uniforms[g];
+  double* d = s_d[w];
   int idx = 0;
   if (T != 0.0) {
-    double d[MZ_MAX_ACTIONS];
     const double inv_t = __ddiv_rn(1.0, T);
-    for (int i = 0; i < n; ++i) d[i] = pow((double)cnt[i], inv_t);
-    const double s = np_pairwise_sum(d, n);
-    double acc = 0.0;
-    for (int i = 0; i < n; ++i) {  // distribution / sum, then cumsum
-      const double p = __ddiv_rn(d[i], s);
-      acc = (i == 0) ? p : __dadd_rn(acc, p);
-      d[i] = acc;
+    if (lane < n) d[lane] = pow((double)cnt, inv_t);
+    __syncwarp();
+    double s = 0.0;
+    if (lane == 0) s = np_pairwise_sum(d, n);
+    s = shfl_f64<32>(s, 0);
+    __syncwarp();
+    if (lane < n) d[lane] = __ddiv_rn(d[lane], s);  // distribution / sum
+    __syncwarp();
+    if (lane == 0) {  // cumsum
+      double acc = d[0];
+      for (int i = 1; i < n; ++i) {
+        acc = __dadd_rn(acc, d[i]);
+        d[i] = acc;
+      }
     }
+    __syncwarp();
     const double last = d[n - 1];
-    for (int i = 0; i < n; ++i)
-      if (__ddiv_rn(d[i], last) <= u) idx = i + 1;  // searchsorted(side='right')
+    const bool le = lane < n && __ddiv_rn(d[lane], last) <= u;  // searchsorted(side='right')
+    const unsigned m = __ballot_sync(MZ_FULL, le);
+    idx = m ? 32 - __clz(m) : 0;  // (last index with cdf <= u) + 1, as the sequential scan leaves it
     if (idx >= n) idx = n - 1;
   } else {
-    int mx = cnt[0];
-    for (int i = 1; i < n; ++i) mx = max(mx, cnt[i]);
-    int ties = 0;
-    for (int i = 0; i < n; ++i) ties += (cnt[i] == mx);
+    const int mx = __reduce_max_sync(MZ_FULL, lane < n ? cnt : -1);
+    const unsigned tie = __ballot_sync(MZ_FULL, lane < n && cnt == mx);
+    const int ties = __popc(tie);
     int pick = (int)floor(__dmul_rn(u, (double)ties));
     if (pick >= ties) pick = ties - 1;
-    for (int i = 0; i < n; ++i)
-      if (cnt[i] == mx && pick-- == 0) {
-        idx = i;
-        break;
-      }
+    idx = __fns(tie, 0, pick + 1);  // the pick-th tie in action order
   }
-  actions[g] = act[idx];
+  const int chosen = __shfl_sync(MZ_FULL, my_act, idx);
+  if (lane == 0) actions[g] = chosen;
 }
 
 __global__ void tree_export_kernel(mz_tree t, int game, double* prior, int32_t* child, double* vsum,
@@ -1150,7 +1156,7 @@ int mz_tree_root_stats(const mz_tree* t, int32_t* visits, double* child_visits, 
                        double* minmax, void* stream) {
   int rc = check_tree(t);
   if (rc) return rc;
-  const int threads = 128, grid = (t->num_games + threads - 1) / threads;
+  const int threads = 128, grid = (t->num_games + 3) / 4;  // a warp per game
   root_stats_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(*t, visits, child_visits, root_value,
                                                                minmax);
   MZ_LAUNCH_CHECK();
@@ -1162,7 +1168,7 @@ int mz_select_action(int32_t G, int32_t A, const int32_t* visits, const uint32_t
                      void* stream) {
   if (G < 1 || A < 1 || A > MZ_MAX_ACTIONS || !visits || !temperature || !uniforms || !actions)
     return MZ_ERR_BAD_ARG;
-  const int threads = 128, grid = (G + threads - 1) / threads;
+  const int threads = 128, grid = (G + 3) / 4;  // a warp per game
   select_action_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(G, A, visits, legal_mask,
                                                                   temperature, uniforms, actions);
   MZ_LAUNCH_CHECK();
