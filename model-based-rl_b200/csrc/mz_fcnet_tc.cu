@@ -383,14 +383,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d1_full[i], 1);
-      mbar_init(&d1_empty[i], EPI_THREADS);
-      mbar_init(&a2_full[i], EPI_THREADS);
+      mbar_init(&d1_empty[i], EPI_THREADS / 32);  // one arrival per epilogue warp (after __syncwarp): 512
+      mbar_init(&a2_full[i], EPI_THREADS / 32);   // per-thread arrivals per chunk serialise on the barrier word
       mbar_init(&a2_empty[i], 1);
     }
-    mbar_init(a1_ready, EPI_THREADS);
-    mbar_init(a3_ready, EPI_THREADS / 2);
+    mbar_init(a1_ready, EPI_THREADS / 32);
+    mbar_init(a3_ready, EPI_THREADS / 64);
     mbar_init(d2_full, 1);
-    mbar_init(h_staged, EPI_THREADS / 2);
+    mbar_init(h_staged, EPI_THREADS / 64);
     mbar_init(a3_remote, 1);
     if (split && rank == 0) mbar_arrive_expect_tx(a3_remote, ROWS * K3 * 2);  // the peer's st.async bytes
     mbar_init(h_stored, 1);
@@ -569,7 +569,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     if (lane == 0) TC_STAMP(224 + warp);
     fence_async_smem();
     if (lane == 0) TC_STAMP(236 + warp);
-    mbar_arrive(a1_ready);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a1_ready);
     if (stamp) TC_STAMP(1);
 
     uint32_t v[32], v2[32];
@@ -592,8 +593,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       tmem_st32(a2, pk);
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&a2_full[c & 1]);
-      mbar_arrive(&d1_empty[c & 1]);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&a2_full[c & 1]);
+        mbar_arrive(&d1_empty[c & 1]);
+      }
       if (stamp) TC_STAMP(5 + 2 * c);
     };
 
@@ -652,7 +656,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
         }
         // release the local prediction layer first, then ship the same rows to the peer
         fence_async_smem();
-        mbar_arrive(a3_ready);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a3_ready);
         if (split) {
           const uint32_t a3_peer = map_to_cta(smem_u32(sA3), 0);
 #pragma unroll
@@ -667,13 +672,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       // instruction writes one contiguous 200-byte row (a per-thread row store touches 32 lines)
 #pragma unroll
       for (int j = 0; j < H; ++j) sOut[row * OUT_STRIDE + j] = hbuf[j];
-      mbar_arrive(h_staged);  // the store warp takes it from here
+      __syncwarp();
+      if (lane == 0) mbar_arrive(h_staged);  // the store warp takes it from here
     } else {
       // rank 0 of a split pair: wait for the peer's rows (cluster-scope acquire), make them visible
       // to the tensor-core (async) proxy, release the local layer-1 issuer
       mbar_wait_cluster(a3_remote, 0);
       fence_async_smem();
-      mbar_arrive(a3_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a3_ready);
     }
 
     for (int c = c_mid; c < nch; ++c) hidden_epilogue(c);
