@@ -525,33 +525,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
           *reinterpret_cast<__nv_bfloat16*>(sA1 + canon_off(r, k, ROWS)) = __float2bfloat16_rn(x);
         }
       }
-    } else if (grp == 0) {
+    } else {
       // --- A1 = bf16([h (50) | onehot(action) (A) | 1 (bias input) | 0]) ---
-      // k < 48: the warp walks its 32 rows, 24 lanes load one float2 each (coalesced 192 B per row);
-      // all loads of a batch of 16 rows are issued before the first store
+      // k < 48: both warps of a quarter walk 16 of its 32 rows each, 24 lanes load one float2 per row
+      // (coalesced 192 B); all 16 row loads are in flight before the first store (one L2 round trip)
       const float* src = p.hidden_in + (size_t)gc * p.in_row_stride + (size_t)pre_idx * H;
-      const unsigned long long my_src = (unsigned long long)src;
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
+      float2 h4849 = make_float2(0.0f, 0.0f);
+      if (grp == 1) h4849 = *reinterpret_cast<const float2*>(src + 48);  // in flight with the row loads below
+      {
+        const unsigned long long my_src = (unsigned long long)src;
         float2 f2[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const unsigned long long rs = __shfl_sync(MZ_FULL, my_src, b * 16 + i);
+          const unsigned long long rs = __shfl_sync(MZ_FULL, my_src, grp * 16 + i);
           f2[i] = lane < 24 ? *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(rs) + 2 * lane)
                             : make_float2(0.0f, 0.0f);
         }
         if (lane < 24) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            *reinterpret_cast<uint32_t*>(sA1 + canon_off(quarter * 32 + b * 16 + i, 2 * lane, ROWS)) =
+            *reinterpret_cast<uint32_t*>(sA1 + canon_off(quarter * 32 + grp * 16 + i, 2 * lane, ROWS)) =
                 pack_bf16(f2[i].x, f2[i].y);
         }
       }
-    } else {
+      if (grp == 1) {
       // k >= 48: the row's own thread (last two state features, one-hot action, constant 1)
-      const float* src = p.hidden_in + (size_t)gc * p.in_row_stride + (size_t)pre_idx * H;
       const int act = pre_act;
-      const float2 h4849 = *reinterpret_cast<const float2*>(src + 48);
       const int kbias = H + p.num_actions;
       const int a_off = (row >> 3) * 128 + (row & 7) * 16;
       for (int kb = 6; kb < k1 / 8; ++kb) {
@@ -564,6 +563,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
         uint4 q = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
                              pack_bf16(f[6], f[7]));
         *reinterpret_cast<uint4*>(sA1 + kb * (ROWS / 8) * 128 + a_off) = q;
+      }
       }
     }
     if (lane == 0) TC_STAMP(224 + warp);
