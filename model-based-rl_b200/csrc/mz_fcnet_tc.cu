@@ -47,7 +47,6 @@ constexpr int COL_D1 = 0;            // 2 x 128: first-layer accumulators (doubl
 constexpr int COL_A2 = 256;          // 2 x 64 : relu(first layer) as packed bf16 = A operand of layer 2
 constexpr int COL_D2A = 384;         // 32     : reward / value logits
 constexpr int COL_D2B = 416;         // 64     : next hidden / policy logits
-constexpr int COL_A3 = 480;          // 32     : h' as packed bf16 = A operand of the prediction layer
 
 // tail parameter block (float): second-layer biases and LayerNorm affine
 constexpr int T_REW_B = 0, T_DYN_B = 32, T_LN_W = 96, T_LN_B = 160, T_VAL_B = 224, T_POL_B = 256;
@@ -117,31 +116,6 @@ MZ_DEV void tc_commit(uint64_t* bar) {
 MZ_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 MZ_DEV void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> f32, issued by one thread
-MZ_DEV void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                      uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// same with the A operand in tensor memory (packed 16-bit pairs, lane = row)
-MZ_DEV void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                         uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-      "}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 MZ_DEV void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 MZ_DEV void tmem_st32(uint32_t addr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -202,20 +176,12 @@ MZ_DEV uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {  // same offset 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-MZ_DEV void st_cluster_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z),
-               "r"(v.w)
-               : "memory");
-}
 // 16 bytes into the peer's shared memory; the store itself reports its bytes to the peer's mbarrier, so the
 // sender needs neither a cluster-scope fence (MEMBAR.ALL.GPU + ERRBAR in SASS) nor a separate arrival.
 MZ_DEV void st_async_v4(uint32_t addr, uint4 v, uint32_t remote_bar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
                : "memory");
-}
-MZ_DEV void mbar_arrive_remote(uint32_t cluster_addr) {  // release at cluster scope
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 MZ_DEV void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope
   uint32_t ok = 0;
@@ -429,7 +395,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     const uint32_t w_addr = smem_u32(sW);
     const uint32_t idesc1 = make_idesc(CHUNK);
     constexpr uint64_t KSTEP = (uint64_t)((2 * (CHUNK / 8) * 128) >> 4);  // two K core-matrix columns
-#pragma unroll 1
     int st = 0, round = 0;
     for (int c = 0; c < nch; ++c, st = (st + 1 == STAGES ? 0 : st + 1), round += (st == 0)) {
       const int cc = canon(c);
@@ -464,7 +429,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
     // A2[c&1]; runs concurrently with the layer-1 issuer so neither waits behind the other =====
     const uint32_t w_addr = smem_u32(sW);
     const uint32_t w1_bytes_dyn = CHUNK * k1 * 2, w1_bytes_pred = CHUNK * K3 * 2;
-#pragma unroll 1
     int st = 0;
     for (int c = 0; c < nch; ++c, st = (st + 1 == STAGES ? 0 : st + 1)) {
       const int cc = canon(c), head = cc >> 2;
@@ -660,7 +624,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
         if (lane == 0) mbar_arrive(a3_ready);
         if (split) {
           const uint32_t a3_peer = map_to_cta(smem_u32(sA3), 0);
-#pragma unroll
           const uint32_t bar_peer = map_to_cta(smem_u32(a3_remote), 0);
 #pragma unroll
           for (int kb = 0; kb < K3 / 8; ++kb)
