@@ -552,30 +552,30 @@ def cs_launches(G, S):
   return 4 + S * (2 + 70)  # set_root, first descent, per sim: row base + 69 network + tree step, stats, action
 
 
-def bench_targets(torch, _lib, dev):
-  """targets/s of the fused target kernel on the C3 (Breakout-ram) shape: window 200k positions,
-  B=512, K=5, td=10, A=4, obs 128 x u8, supports fused."""
+def _targets_case(torch, _lib, dev, rng, P, A, K, T, B, E, obs_u8, n_sets, reps, discount=0.997):
+  """Times mz_build_targets (supports fused) on one synthetic replay window; returns (seconds per launch,
+  algorithmic bytes per sampled row: SURVEY.md section 8d's formula)."""
   lib = _lib.load()
-  rng = np.random.default_rng(5)
-  P, A, K, T, B, E = 200_000, 4, 5, 10, 512, 128
   lens = rng.integers(200, 800, size=P // 200)
   lens = lens[np.cumsum(lens) <= P]
   starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
   t = lambda a: torch.from_numpy(a).to(dev)
-  obs = t(rng.integers(0, 256, size=(P, E), dtype=np.uint8))
+  if obs_u8:
+    obs = t(rng.integers(0, 256, size=(P, E), dtype=np.uint8))
+  else:
+    obs = t(rng.normal(size=(P, E)).astype(np.float32))
   rewards = t(np.sign(rng.normal(size=P) * (rng.random(P) < 0.1)).astype(np.float32))
   actions = t(rng.integers(0, A, size=P, dtype=np.int32))
   to_play = torch.ones(P, dtype=torch.int8, device=dev)
   root_values = t(rng.normal(0, 2, size=P))
   cv = rng.random((P, A)).astype(np.float32)
   child_visits = t(cv / cv.sum(1, keepdims=True))
-  win = _lib.Window(A, E, 1, 0, obs.data_ptr(), actions.data_ptr(), rewards.data_ptr(),
+  win = _lib.Window(A, E, 1 if obs_u8 else 0, 0, obs.data_ptr(), actions.data_ptr(), rewards.data_ptr(),
                     to_play.data_ptr(), root_values.data_ptr(), child_visits.data_ptr())
-  discounts = t(np.array([0.997**n for n in range(K + T)], np.float32))
-  tc = _lib.TargetCfg(B, K, T, 1, -15, 15, -15, 15, 0, 0, 0.997**T, discounts.data_ptr(), None, None)
-  n_batches = 64
+  discounts = t(np.array([discount**n for n in range(K + T)], np.float32))
+  tc = _lib.TargetCfg(B, K, T, 1, -15, 15, -15, 15, 0, 0, discount**T, discounts.data_ptr(), None, None)
   sets = []
-  for _ in range(n_batches):
+  for _ in range(n_sets):
     ci = rng.integers(0, len(lens), size=B)
     step = (rng.random(B) * lens[ci]).astype(np.int64)
     sets.append((t(starts[ci] + step), t(starts[ci]), t(lens[ci].astype(np.int32)),
@@ -594,17 +594,44 @@ def bench_targets(torch, _lib, dev):
   torch.cuda.synchronize()
   a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   a.record()
-  for s in sets:
-    launch(s)
+  for _ in range(reps):
+    for s in sets:
+      launch(s)
   b.record()
   torch.cuda.synchronize()
-  sec = a.elapsed_time(b) * 1e-3 / n_batches
-  bytes_per_sample = (E + 5 * (T + K) + (K + 1) * (8 + 4 * A) + 4 * K) + \
+  sec = a.elapsed_time(b) * 1e-3 / (n_sets * reps)
+  in_bytes = E * (1 if obs_u8 else 4)
+  bytes_per_sample = (in_bytes + 5 * (T + K) + (K + 1) * (8 + 4 * A) + 4 * K) + \
                      (4 * E + 4 * K + (K + 1) * (4 * A + 8)) + (K + 1) * 2 * 31 * 4
-  return {"samples_per_s": B / sec, "target_positions_per_s": B * (K + 1) / sec, "us_per_batch": sec * 1e6,
-          "workload": "C3 Breakout-ram: window 200000, B=512, K=5, td=10, A=4, obs 128 u8, supports fused",
-          "algorithmic_bytes_per_sample": bytes_per_sample,
-          "achieved_gbs": B * bytes_per_sample / sec / 1e9}
+  return sec, bytes_per_sample
+
+
+def bench_targets(torch, _lib, dev):
+  """targets/s of the fused target kernel.  Headline: the C3 (Breakout-ram) learner batch -- window 200k
+  positions, B=512, K=5, td=10, A=4, obs 128 x u8, supports fused (one launch per batch: launch bound).
+  `bulk`: the same kernel producing 128 learner batches (65 536 rows) per launch, outputs larger than L2 --
+  the regime where HBM bounds it -- for the C3 shape and the C2 (LunarLander, td_steps=1000) shape."""
+  rng = np.random.default_rng(5)
+  peaks = measured_peaks()
+  hbm = peaks["hbm_gbs"]
+  P, A, K, T, B, E = 200_000, 4, 5, 10, 512, 128
+  sec, bps = _targets_case(torch, _lib, dev, rng, P, A, K, T, B, E, True, 64, 1)
+  res = {"samples_per_s": B / sec, "target_positions_per_s": B * (K + 1) / sec, "us_per_batch": sec * 1e6,
+         "workload": "C3 Breakout-ram: window 200000, B=512, K=5, td=10, A=4, obs 128 u8, supports fused",
+         "algorithmic_bytes_per_sample": bps, "achieved_gbs": B * bps / sec / 1e9}
+  bulk = {}
+  for name, (A2, T2, E2, u8, disc) in {"C3_breakout_ram": (4, 10, 128, True, 0.997),
+                                       "C2_lunarlander_td1000": (4, 1000, 8, False, 0.997)}.items():
+    Bb = 128 * 512
+    sec, bps = _targets_case(torch, _lib, dev, rng, P, A2, K, T2, Bb, E2, u8, 4, 5, disc)
+    gbs = Bb * bps / sec / 1e9
+    bulk[name] = {"rows_per_launch": Bb, "us_per_launch": sec * 1e6, "samples_per_s": Bb / sec,
+                  "algorithmic_bytes_per_sample": bps,
+                  "roofline": {"kernel": "build_targets_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm,
+                               "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+                               "peak_source": peaks["source"]}}
+  res["bulk"] = bulk
+  return res
 
 
 def bench_learner(torch, _lib, dev, world, barrier):

@@ -313,6 +313,10 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
                      const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* pad_actions,
                      float* obs_out, int32_t* actions_out, float* t_rewards, float* t_values,
                      float* t_policies, float* value_support, float* reward_support, void* stream);
+/* Two kernels serve mz_build_targets: lane-per-unroll-position (K + 1 <= 16 and td_steps <= 64: a warp owns
+ * 32 / (K + 1) consecutive rows) and warp-per-row (everything else, e.g. td_steps = 1000).  which = 1 forces
+ * the warp-per-row kernel (parity tests run both on the same inputs), 0 restores the choice by shape. */
+int mz_debug_set_targets_kernel(int32_t which);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Prioritized-replay sum-tree in HBM (SumTree, replay_buffer.py:6-66): float64 array-embedded    */

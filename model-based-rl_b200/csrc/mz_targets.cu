@@ -12,112 +12,449 @@
 
 namespace {
 
-constexpr int kTgtThreads = 128;
-constexpr int kTgtWarps = kTgtThreads / 32;
+constexpr int kTgtWarps = 8;  // sampled rows per CTA
+constexpr int kTgtThreads = kTgtWarps * 32;
 
+struct TgtBins {  // two-hot bins of one scalar target
+  int lo, hi;
+  float p_lo, p_hi;
+};
+
+// One row of [n_pos][bins] two-hot supports, written by a whole warp as 8-byte stores when the row
+// base allows it (a row is (K+1) * bins floats; 256 contiguous bytes per warp instruction).
+// idx / bins through a multiply-shift (exact while idx * bins < 2^20; plain division otherwise).
+MZ_DEV void write_supports(float* __restrict__ dst, const TgtBins* __restrict__ th, int n_pos, int bins,
+                           int lane) {
+  const int total = n_pos * bins;
+  const bool fast = (long long)total * bins < (1 << 20);
+  const unsigned magic = (1u << 20) / (unsigned)bins + 1u;
+  auto elem = [&](int idx) {
+    const int i = fast ? (int)(((unsigned)idx * magic) >> 20) : idx / bins;
+    const int j = idx - i * bins;
+    const TgtBins t = th[i];
+    return j == t.lo ? t.p_lo : (j == t.hi ? t.p_hi : 0.0f);  // low bin wins (config.py:64-67)
+  };
+  if (((total & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+    float2* d2 = reinterpret_cast<float2*>(dst);
+    for (int e = lane; e < (total >> 1); e += 32) d2[e] = make_float2(elem(2 * e), elem(2 * e + 1));
+  } else {
+    for (int e = lane; e < total; e += 32) dst[e] = elem(e);
+  }
+}
+
+constexpr int kTgtFastK = 7;  // up to 8 unroll positions keep their sums in registers
+
+// n-step sums of NP unroll positions in one pass over the staged window: acc[i] = sum_j (+-)rewards[step+i+j]
+// * discounts[j], j < min(T, len - (step+i)); the sign flips where to_play differs from the position's
+// (replay_buffer.py:187-189).  Exact float32 products accumulated in binary64; returns position `lane`'s sum.
+template <int NP>
+MZ_DEV double nstep_sums(const float* s_rew, const int8_t* s_tp, const float* s_disc, int K, int T, int step,
+                         int len, int win, int lane) {
+  double acc[NP];
+  int tp_i[NP], n_i[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    acc[i] = 0.0;
+    const bool in = i <= K && step + i < len;
+    n_i[i] = in ? min(T, len - step - i) : 0;
+    tp_i[i] = in ? s_tp[i] : 0;
+  }
+  for (int m = lane; m < win; m += 32) {
+    const float r = s_rew[m];
+    const int tp = s_tp[m];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int j = m - i;
+      if (j >= 0 && j < n_i[i]) acc[i] += (double)(tp != tp_i[i] ? -r : r) * (double)s_disc[j];
+    }
+  }
+  double mine_acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    if (i <= K) {  // warp-uniform
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) acc[i] += shfl_xor_f64<32>(acc[i], m);
+      if (lane == i) mine_acc = acc[i];
+    }
+  }
+  return mine_acc;
+}
+
+
+// One warp per sampled row, kTgtWarps rows per CTA.  Every global load of a row (observation, reward /
+// to_play window, bootstrap root values, child-visit rows) is issued before the first dependent use, so a
+// row costs two DRAM round trips (index arrays, then everything else); all stores are warp-contiguous.
+// The n-step sums of all K+1 positions come out of ONE pass over the staged window (a window element
+// contributes to every position it is in range of); lane i then finishes position i.
 __global__ void __launch_bounds__(kTgtThreads)
 build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ pos_arr,
                      const int64_t* __restrict__ chunk_start, const int32_t* __restrict__ chunk_len,
                      const int32_t* __restrict__ pad_actions, float* __restrict__ obs_out,
                      int32_t* __restrict__ actions_out, float* __restrict__ t_rewards,
                      float* __restrict__ t_values, float* __restrict__ t_policies,
-                     float* __restrict__ value_support, float* __restrict__ reward_support) {
-  extern __shared__ unsigned char smem_raw[];
-  const int b = blockIdx.x;
-  const int K = c.num_unroll_steps, T = c.td_steps, A = w.num_actions;
-  const int64_t pos = pos_arr[b];
-  const int step = (int)(pos - chunk_start[b]);
-  const int len = chunk_len[b];  // len(root_values) == len(rewards) == len(to_play)
+                     float* __restrict__ value_support, float* __restrict__ reward_support,
+                     int warp_smem_bytes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kTgtWarps + warp;
+  const int K = c.num_unroll_steps, T = c.td_steps, A = w.num_actions, E = w.obs_elems;
+  // the discount table f32(discount ** n) (replay_buffer.py:84) is shared by the CTA's rows
+  float* s_disc = reinterpret_cast<float*>(smem_raw);
+  for (int j = threadIdx.x; j < K + T; j += kTgtThreads) s_disc[j] = c.discounts[j];
+  const bool row_ok = b < c.batch;
+  int64_t pos = 0;
+  int step = 0, len = 0;
+  if (row_ok) {
+    pos = pos_arr[b];
+    step = (int)(pos - chunk_start[b]);
+    len = chunk_len[b];  // len(root_values) == len(rewards) == len(to_play)
+  }
+  __syncthreads();
+  if (!row_ok) return;  // warps are independent from here on
 
-  // stage the reward / to_play window [step, min(step + K + T, len)) in shared memory
+  unsigned char* mine = smem_raw + ((size_t)(K + T) * sizeof(float) + 15) / 16 * 16 + (size_t)warp * warp_smem_bytes;
+  float* s_rew = reinterpret_cast<float*>(mine);                       // [K+T] rewards from `step` on
+  float* s_val = s_rew + (K + T);                                      // [K+1] value targets
+  float* s_lastr = s_val + (K + 1);                                    // [K+1] reward targets
+  TgtBins* s_vth = reinterpret_cast<TgtBins*>(s_lastr + (K + 1));      // [K+1]
+  TgtBins* s_rth = s_vth + (K + 1);                                    // [K+1]
+  int8_t* s_tp = reinterpret_cast<int8_t*>(s_rth + (K + 1));           // [K+T]
+
+  // ---- loads -------------------------------------------------------------------------------------
+  // reward / to_play window [step, min(step + K + T, len))
   const int win = max(0, min(K + T, len - step));
-  float* s_rew = reinterpret_cast<float*>(smem_raw);
-  int8_t* s_tp = reinterpret_cast<int8_t*>(s_rew + (K + T));
-  float* s_val = reinterpret_cast<float*>(s_tp + ((K + T + 3) / 4) * 4);  // [K+1] values
-  float* s_lastr = s_val + (K + 1);                                       // [K+1] rewards
-  for (int j = threadIdx.x; j < win; j += kTgtThreads) {
+  for (int j = lane; j < win; j += 32) {
     s_rew[j] = w.rewards[pos + j];
     s_tp[j] = w.to_play[pos + j];
   }
-  __syncthreads();
+  const float prev_reward = (step > 0 && step <= len) ? w.rewards[pos - 1] : 0.0f;
+  // bootstrap of position `lane`: root_values[step + lane + T] where it exists (replay_buffer.py:180-183)
+  double root = 0.0;
+  if (lane <= K && step + lane + T < len) root = w.root_values[pos + lane + T];
+  // positions that still lie inside the chunk: step + i < len
+  const int n_in = max(0, min(K + 1, len - step));
 
   // observation: np.float32(history.observations[step])  (replay_buffer.py:147)
   {
-    const int E = w.obs_elems;
     float* dst = obs_out + (size_t)b * E;
-    if (w.obs_is_u8) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(w.obs) + (size_t)pos * E;
-      for (int e = threadIdx.x; e < E; e += kTgtThreads) {
-        float v = (float)src[e];
-        if (c.normalize_obs) v = __fdiv_rn(__fsub_rn(v, c.obs_min[e]), c.obs_range[e]);
-        dst[e] = v;
+    if ((E & 3) == 0) {
+      float4* dst4 = reinterpret_cast<float4*>(dst);
+      const float4* mn4 = reinterpret_cast<const float4*>(c.obs_min);
+      const float4* rg4 = reinterpret_cast<const float4*>(c.obs_range);
+      const bool vec_norm = c.normalize_obs && (((reinterpret_cast<uintptr_t>(c.obs_min) |
+                                                  reinterpret_cast<uintptr_t>(c.obs_range)) & 15) == 0);
+      for (int e = lane; e < (E >> 2); e += 32) {
+        float4 v;
+        if (w.obs_is_u8) {
+          const uint32_t q = reinterpret_cast<const uint32_t*>(
+              reinterpret_cast<const uint8_t*>(w.obs) + (size_t)pos * E)[e];
+          v = make_float4((float)(q & 255u), (float)((q >> 8) & 255u), (float)((q >> 16) & 255u),
+                          (float)(q >> 24));
+        } else {
+          v = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w.obs) + (size_t)pos * E)[e];
+        }
+        if (c.normalize_obs) {
+          float4 mn, rg;
+          if (vec_norm) {
+            mn = mn4[e];
+            rg = rg4[e];
+          } else {
+            mn = make_float4(c.obs_min[4 * e], c.obs_min[4 * e + 1], c.obs_min[4 * e + 2], c.obs_min[4 * e + 3]);
+            rg = make_float4(c.obs_range[4 * e], c.obs_range[4 * e + 1], c.obs_range[4 * e + 2],
+                             c.obs_range[4 * e + 3]);
+          }
+          v.x = __fdiv_rn(__fsub_rn(v.x, mn.x), rg.x);
+          v.y = __fdiv_rn(__fsub_rn(v.y, mn.y), rg.y);
+          v.z = __fdiv_rn(__fsub_rn(v.z, mn.z), rg.z);
+          v.w = __fdiv_rn(__fsub_rn(v.w, mn.w), rg.w);
+        }
+        dst4[e] = v;
       }
     } else {
-      const float* src = reinterpret_cast<const float*>(w.obs) + (size_t)pos * E;
-      for (int e = threadIdx.x; e < E; e += kTgtThreads) {
-        float v = src[e];
+      for (int e = lane; e < E; e += 32) {
+        float v = w.obs_is_u8 ? (float)reinterpret_cast<const uint8_t*>(w.obs)[(size_t)pos * E + e]
+                              : reinterpret_cast<const float*>(w.obs)[(size_t)pos * E + e];
         if (c.normalize_obs) v = __fdiv_rn(__fsub_rn(v, c.obs_min[e]), c.obs_range[e]);
         dst[e] = v;
       }
     }
+  }
+  // policy targets: child_visits[step + i] for the positions inside the chunk (one contiguous run of
+  // n_in * A floats), zeros after the end (absorbing policy, replay_buffer.py:90)
+  {
+    float* pol = t_policies + (size_t)b * (K + 1) * A;
+    const float* src = w.child_visits + (size_t)pos * A;
+    const int n_real = n_in * A;
+    for (int e = lane; e < (K + 1) * A; e += 32) pol[e] = e < n_real ? src[e] : 0.0f;
   }
   // actions: history.actions[step:step+K], padded with random actions (replay_buffer.py:149-152)
-  if (threadIdx.x < K) {
-    const int k = threadIdx.x;
+  {
     const int n_real = max(0, min(K, len - step));
-    actions_out[(size_t)b * K + k] =
-        k < n_real ? w.actions[pos + k] : pad_actions[(size_t)b * K + (k - n_real)];
+    for (int k = lane; k < K; k += 32)
+      actions_out[(size_t)b * K + k] = k < n_real ? w.actions[pos + k] : pad_actions[(size_t)b * K + (k - n_real)];
   }
+  __syncwarp();
 
-  // insert_target (replay_buffer.py:165-198): one warp per unroll position
-  for (int i = warp; i <= K; i += kTgtWarps) {
-    const int ci = step + i;
-    float last_reward = 0.0f;
-    if (ci > 0 && ci <= len) last_reward = (i > 0) ? s_rew[i - 1] : w.rewards[pos - 1];
-    float value = 0.0f;
-    float* pol = t_policies + ((size_t)b * (K + 1) + i) * A;
-    if (ci < len) {
-      const int tp = s_tp[i];
-      const int n = min(T, len - ci);
-      double acc = 0.0;  // exact products of float32 pairs, accumulated in binary64
-      for (int j = lane; j < n; j += 32) {
-        float r = s_rew[i + j];
-        if (s_tp[i + j] != tp) r = -r;
-        acc += (double)r * (double)c.discounts[j];
+  // ---- insert_target (replay_buffer.py:165-198) -----------------------------------------------------
+  if (K <= kTgtFastK) {
+    const double mine_acc = K < 6 ? nstep_sums<6>(s_rew, s_tp, s_disc, K, T, step, len, win, lane)
+                                  : nstep_sums<kTgtFastK + 1>(s_rew, s_tp, s_disc, K, T, step, len, win, lane);
+    if (lane <= K) {
+      const int ci = step + lane;
+      float value = 0.0f;
+      if (ci < len) {
+        const double boot = (ci + T < len) ? __dmul_rn(root, c.disc_pow_td) : 0.0;
+        value = __fadd_rn((float)boot, (float)mine_acc);  // numpy 2: python float + np.float32 -> float32
       }
-#pragma unroll
-      for (int m = 16; m > 0; m >>= 1) acc += shfl_xor_f64<32>(acc, m);
-      const double boot = (ci + T < len) ? __dmul_rn(w.root_values[pos + i + T], c.disc_pow_td) : 0.0;
-      value = __fadd_rn((float)boot, (float)acc);  // numpy 2: python float + np.float32 -> float32
-      for (int a = lane; a < A; a += 32) pol[a] = w.child_visits[(size_t)(pos + i) * A + a];
-    } else {
-      for (int a = lane; a < A; a += 32) pol[a] = 0.0f;  // absorbing policy (replay_buffer.py:90)
+      float last_reward = 0.0f;
+      if (ci > 0 && ci <= len) last_reward = (lane > 0) ? s_rew[lane - 1] : prev_reward;
+      s_val[lane] = value;
+      s_lastr[lane] = last_reward;
     }
-    if (lane == 0) {
-      t_rewards[(size_t)b * (K + 1) + i] = last_reward;
-      t_values[(size_t)b * (K + 1) + i] = value;
-      s_val[i] = value;
-      s_lastr[i] = last_reward;
+  } else {
+    for (int i = 0; i <= K; ++i) {
+      const int ci = step + i;
+      float value = 0.0f;
+      if (ci < len) {
+        const double root_i = (ci + T < len && lane == 0) ? w.root_values[pos + i + T] : 0.0;
+        const int tp = s_tp[i];
+        const int n = min(T, len - ci);
+        double acc = 0.0;
+        for (int j = lane; j < n; j += 32) {
+          float r = s_rew[i + j];
+          if (s_tp[i + j] != tp) r = -r;
+          acc += (double)r * (double)s_disc[j];
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) acc += shfl_xor_f64<32>(acc, m);
+        const double boot = (ci + T < len) ? __dmul_rn(root_i, c.disc_pow_td) : 0.0;
+        value = __fadd_rn((float)boot, (float)acc);
+      }
+      if (lane == 0) {
+        float last_reward = 0.0f;
+        if (ci > 0 && ci <= len) last_reward = (i > 0) ? s_rew[i - 1] : prev_reward;
+        s_val[i] = value;
+        s_lastr[i] = last_reward;
+      }
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i <= K; i += 32) {
+    const float v = s_val[i], r = s_lastr[i];
+    t_values[(size_t)b * (K + 1) + i] = v;
+    t_rewards[(size_t)b * (K + 1) + i] = r;
+    if (c.fuse_supports) {
+      // learners.py:186-192: h(x) then two-hot projection of values and rewards
+      const MzTwoHot tv = mz_two_hot(c.no_target_transform ? v : mz_scalar_transform_f(v), c.value_min, c.value_max);
+      const MzTwoHot tr = mz_two_hot(c.no_target_transform ? r : mz_scalar_transform_f(r), c.reward_min, c.reward_max);
+      s_vth[i] = TgtBins{tv.lo, tv.hi, tv.p_lo, tv.p_hi};
+      s_rth[i] = TgtBins{tr.lo, tr.hi, tr.p_lo, tr.p_hi};
     }
   }
   if (!c.fuse_supports) return;
-  __syncthreads();
-  // learners.py:186-192: h(x) then two-hot projection of values and rewards
+  __syncwarp();
   const int vb = c.value_max - c.value_min + 1, rb = c.reward_max - c.reward_min + 1;
-  for (int idx = threadIdx.x; idx < (K + 1) * vb; idx += kTgtThreads) {
-    const int i = idx / vb, j = idx % vb;
-    float x = s_val[i];
-    if (!c.no_target_transform) x = mz_scalar_transform_f(x);
-    const MzTwoHot th = mz_two_hot(x, c.value_min, c.value_max);
-    value_support[((size_t)b * (K + 1) + i) * vb + j] = j == th.lo ? th.p_lo : (j == th.hi ? th.p_hi : 0.0f);
+  write_supports(value_support + (size_t)b * (K + 1) * vb, s_vth, K + 1, vb, lane);
+  write_supports(reward_support + (size_t)b * (K + 1) * rb, s_rth, K + 1, rb, lane);
+}
+
+// ---- lane-per-position variant ---------------------------------------------------------------------
+// For the learner's usual shapes (K + 1 <= 16 unroll positions, td_steps <= 64) a warp owns R = 32 / (K + 1)
+// consecutive sampled rows and lane (r, i) owns unroll position i of row r: its n-step sum is a short serial
+// loop over the (L1-resident) reward window, the bootstrap / reward / two-hot arithmetic runs once per lane
+// with no idle lanes, and the outputs of the warp's rows -- contiguous in every output array -- leave as
+// warp-wide runs.  The two-hot supports are zero-filled with 8-byte stores and the two non-zero bins of every
+// position scattered afterwards (high bin first: the low bin wins on integers, config.py:64-67).
+// ~120 instructions per row against ~1000 for the warp-per-row kernel above.
+constexpr int kRowsMaxPos = 16;
+constexpr int kRowsMaxTd = 64;
+constexpr int kRowsGroup = 4;  // rows whose loads are in flight together
+
+__global__ void __launch_bounds__(kTgtThreads)
+build_targets_rows_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ pos_arr,
+                          const int64_t* __restrict__ chunk_start, const int32_t* __restrict__ chunk_len,
+                          const int32_t* __restrict__ pad_actions, float* __restrict__ obs_out,
+                          int32_t* __restrict__ actions_out, float* __restrict__ t_rewards,
+                          float* __restrict__ t_values, float* __restrict__ t_policies,
+                          float* __restrict__ value_support, float* __restrict__ reward_support) {
+  __shared__ int64_t s_pos[kTgtWarps][kRowsMaxPos];
+  __shared__ int32_t s_rem[kTgtWarps][kRowsMaxPos];  // len - step of the row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = c.num_unroll_steps, T = c.td_steps, A = w.num_actions, E = w.obs_elems;
+  const int NP = K + 1, R = 32 / NP;
+  const int row0 = (blockIdx.x * kTgtWarps + warp) * R;
+  if (row0 >= c.batch) return;
+  const int nrows = min(R, c.batch - row0);
+  const int r = lane / NP, i = lane - r * NP;
+  const bool active = r < nrows;
+  const int b = row0 + r;
+  int64_t pos = 0;
+  int step = 0, len = 0;
+  if (active) {
+    pos = pos_arr[b];
+    step = (int)(pos - chunk_start[b]);
+    len = chunk_len[b];  // len(root_values) == len(rewards) == len(to_play)
+    if (i == 0) {
+      s_pos[warp][r] = pos;
+      s_rem[warp][r] = len - step;
+    }
   }
-  for (int idx = threadIdx.x; idx < (K + 1) * rb; idx += kTgtThreads) {
-    const int i = idx / rb, j = idx % rb;
-    float x = s_lastr[i];
-    if (!c.no_target_transform) x = mz_scalar_transform_f(x);
-    const MzTwoHot th = mz_two_hot(x, c.reward_min, c.reward_max);
-    reward_support[((size_t)b * (K + 1) + i) * rb + j] = j == th.lo ? th.p_lo : (j == th.hi ? th.p_hi : 0.0f);
+  __syncwarp();
+
+  // ---- observations: np.float32(history.observations[step]) (replay_buffer.py:147).  Rows go in groups of
+  // kRowsGroup: all loads of a group are issued before its first store (one DRAM round trip per group)
+  {
+    const bool vec = (E & 3) == 0 && ((reinterpret_cast<uintptr_t>(w.obs) | reinterpret_cast<uintptr_t>(obs_out)) & 15) == 0 &&
+                     (!c.normalize_obs || ((reinterpret_cast<uintptr_t>(c.obs_min) | reinterpret_cast<uintptr_t>(c.obs_range)) & 15) == 0);
+    const uint8_t* obs_u8 = reinterpret_cast<const uint8_t*>(w.obs);
+    const float* obs_f32 = reinterpret_cast<const float*>(w.obs);
+    for (int rr0 = 0; rr0 < nrows; rr0 += kRowsGroup) {
+      int64_t p[kRowsGroup];
+#pragma unroll
+      for (int u = 0; u < kRowsGroup; ++u) p[u] = s_pos[warp][min(rr0 + u, nrows - 1)];
+      if (vec && w.obs_is_u8) {
+        for (int e = lane; e < (E >> 2); e += 32) {
+          uint32_t q[kRowsGroup];
+#pragma unroll
+          for (int u = 0; u < kRowsGroup; ++u) q[u] = __ldg(reinterpret_cast<const uint32_t*>(obs_u8 + (size_t)p[u] * E) + e);
+#pragma unroll
+          for (int u = 0; u < kRowsGroup; ++u) {
+            if (rr0 + u >= nrows) break;
+            float4 v = make_float4((float)(q[u] & 255u), (float)((q[u] >> 8) & 255u), (float)((q[u] >> 16) & 255u),
+                                   (float)(q[u] >> 24));
+            if (c.normalize_obs) {
+              const float4 mn = reinterpret_cast<const float4*>(c.obs_min)[e];
+              const float4 rg = reinterpret_cast<const float4*>(c.obs_range)[e];
+              v.x = __fdiv_rn(__fsub_rn(v.x, mn.x), rg.x);
+              v.y = __fdiv_rn(__fsub_rn(v.y, mn.y), rg.y);
+              v.z = __fdiv_rn(__fsub_rn(v.z, mn.z), rg.z);
+              v.w = __fdiv_rn(__fsub_rn(v.w, mn.w), rg.w);
+            }
+            reinterpret_cast<float4*>(obs_out + (size_t)(row0 + rr0 + u) * E)[e] = v;
+          }
+        }
+      } else if (vec) {
+        for (int e = lane; e < (E >> 2); e += 32) {
+          float4 q[kRowsGroup];
+#pragma unroll
+          for (int u = 0; u < kRowsGroup; ++u) q[u] = __ldg(reinterpret_cast<const float4*>(obs_f32 + (size_t)p[u] * E) + e);
+#pragma unroll
+          for (int u = 0; u < kRowsGroup; ++u) {
+            if (rr0 + u >= nrows) break;
+            float4 v = q[u];
+            if (c.normalize_obs) {
+              const float4 mn = reinterpret_cast<const float4*>(c.obs_min)[e];
+              const float4 rg = reinterpret_cast<const float4*>(c.obs_range)[e];
+              v.x = __fdiv_rn(__fsub_rn(v.x, mn.x), rg.x);
+              v.y = __fdiv_rn(__fsub_rn(v.y, mn.y), rg.y);
+              v.z = __fdiv_rn(__fsub_rn(v.z, mn.z), rg.z);
+              v.w = __fdiv_rn(__fsub_rn(v.w, mn.w), rg.w);
+            }
+            reinterpret_cast<float4*>(obs_out + (size_t)(row0 + rr0 + u) * E)[e] = v;
+          }
+        }
+      } else {
+        for (int e = lane; e < E; e += 32) {
+          float q[kRowsGroup];
+#pragma unroll
+          for (int u = 0; u < kRowsGroup; ++u)
+            q[u] = w.obs_is_u8 ? (float)__ldg(obs_u8 + (size_t)p[u] * E + e) : __ldg(obs_f32 + (size_t)p[u] * E + e);
+#pragma unroll
+          for (int u = 0; u < kRowsGroup; ++u) {
+            if (rr0 + u >= nrows) break;
+            float v = q[u];
+            if (c.normalize_obs) v = __fdiv_rn(__fsub_rn(v, c.obs_min[e]), c.obs_range[e]);
+            obs_out[(size_t)(row0 + rr0 + u) * E + e] = v;
+          }
+        }
+      }
+    }
+  }
+  // ---- policy targets: child_visits of the positions inside the chunk, zeros after its end
+  // (replay_buffer.py:90, 184, 196); the (K+1) * A floats of a row are one contiguous run on both sides
+  for (int rr0 = 0; rr0 < nrows; rr0 += kRowsGroup) {
+    const float* src[kRowsGroup];
+    int n_real[kRowsGroup];
+#pragma unroll
+    for (int u = 0; u < kRowsGroup; ++u) {
+      const int rr = min(rr0 + u, nrows - 1);
+      src[u] = w.child_visits + (size_t)s_pos[warp][rr] * A;
+      n_real[u] = max(0, min(NP, s_rem[warp][rr])) * A;
+    }
+    for (int e = lane; e < NP * A; e += 32) {
+      float q[kRowsGroup];
+#pragma unroll
+      for (int u = 0; u < kRowsGroup; ++u) q[u] = e < n_real[u] ? __ldg(src[u] + e) : 0.0f;
+#pragma unroll
+      for (int u = 0; u < kRowsGroup; ++u) {
+        if (rr0 + u >= nrows) break;
+        t_policies[(size_t)(row0 + rr0 + u) * NP * A + e] = q[u];
+      }
+    }
+  }
+  // ---- actions: history.actions[step:step+K], padded with random actions (replay_buffer.py:149-152)
+  if (active && i < K) {
+    const int n_real = max(0, min(K, len - step));
+    actions_out[(size_t)b * K + i] = i < n_real ? w.actions[pos + i] : pad_actions[(size_t)b * K + (i - n_real)];
+  }
+
+  // ---- insert_target (replay_buffer.py:165-198) for position i of row r
+  const int ci = step + i;
+  float value = 0.0f, last_reward = 0.0f;
+  if (active) {
+    if (ci < len) {
+      const double root = (ci + T < len) ? w.root_values[pos + i + T] : 0.0;  // replay_buffer.py:180-183
+      const int n = min(T, len - ci);
+      const float* rw = w.rewards + pos + i;
+      const int8_t* tp = w.to_play + pos + i;
+      const int tp0 = __ldg(tp);
+      double acc = 0.0;  // exact products of float32 pairs, accumulated in binary64
+      for (int j0 = 0; j0 < n; j0 += 8) {  // eight window elements in flight
+        float x[8];
+        int t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = min(j0 + u, n - 1);
+          x[u] = __ldg(rw + j);
+          t[u] = __ldg(tp + j);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (j0 + u < n)  // replay_buffer.py:187-189
+            acc += (double)(t[u] != tp0 ? -x[u] : x[u]) * (double)__ldg(c.discounts + j0 + u);
+        }
+      }
+      const double boot = (ci + T < len) ? __dmul_rn(root, c.disc_pow_td) : 0.0;
+      value = __fadd_rn((float)boot, (float)acc);  // numpy 2: python float + np.float32 -> float32
+    }
+    if (ci > 0 && ci <= len) last_reward = w.rewards[pos + i - 1];
+    t_values[(size_t)b * NP + i] = value;
+    t_rewards[(size_t)b * NP + i] = last_reward;
+  }
+  if (!c.fuse_supports) return;
+
+  // ---- learners.py:186-192: h(x) then two-hot projection of values and rewards
+  const int vb = c.value_max - c.value_min + 1, rb = c.reward_max - c.reward_min + 1;
+  auto zero_fill = [&](float* dst, int n) {
+    if (((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+      for (int e = lane; e < (n >> 1); e += 32) reinterpret_cast<float2*>(dst)[e] = make_float2(0.0f, 0.0f);
+    } else {
+      for (int e = lane; e < n; e += 32) dst[e] = 0.0f;
+    }
+  };
+  zero_fill(value_support + (size_t)row0 * NP * vb, nrows * NP * vb);
+  zero_fill(reward_support + (size_t)row0 * NP * rb, nrows * NP * rb);
+  __syncwarp();  // orders the fills before the scatters of the other lanes
+  if (active) {
+    const MzTwoHot tv = mz_two_hot(c.no_target_transform ? value : mz_scalar_transform_f(value), c.value_min, c.value_max);
+    const MzTwoHot tr = mz_two_hot(c.no_target_transform ? last_reward : mz_scalar_transform_f(last_reward), c.reward_min,
+                                   c.reward_max);
+    float* pv = value_support + ((size_t)b * NP + i) * vb;
+    pv[tv.hi] = tv.p_hi;
+    pv[tv.lo] = tv.p_lo;
+    float* pr = reward_support + ((size_t)b * NP + i) * rb;
+    pr[tr.hi] = tr.p_hi;
+    pr[tr.lo] = tr.p_lo;
   }
 }
 
@@ -166,7 +503,14 @@ int grid_for(long long n, int threads) {
 
 }  // namespace
 
+int g_targets_kernel = 0;  // 0: by shape, 1: always the warp-per-row kernel (tests)
+
 extern "C" {
+
+int mz_debug_set_targets_kernel(int32_t which) {
+  g_targets_kernel = which;
+  return MZ_OK;
+}
 
 int mz_scalar_transform(int64_t n, const float* x, float* out, void* stream) {
   if (n < 0 || (n > 0 && (!x || !out))) return MZ_ERR_BAD_ARG;
@@ -216,8 +560,18 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
   if (c->normalize_obs && (!c->obs_min || !c->obs_range)) return MZ_ERR_BAD_ARG;
   if (!w->obs || !w->actions || !w->rewards || !w->to_play || !w->root_values || !w->child_visits)
     return MZ_ERR_BAD_ARG;
-  const int KT = c->num_unroll_steps + c->td_steps;
-  const size_t smem = sizeof(float) * KT + ((KT + 3) / 4) * 4 + sizeof(float) * 2 * (c->num_unroll_steps + 1);
+  const int K1 = c->num_unroll_steps + 1, KT = c->num_unroll_steps + c->td_steps;
+  if (K1 <= kRowsMaxPos && c->td_steps <= kRowsMaxTd && g_targets_kernel != 1) {
+    const int rows_per_cta = kTgtWarps * (32 / K1);
+    build_targets_rows_kernel<<<(c->batch + rows_per_cta - 1) / rows_per_cta, kTgtThreads, 0, (cudaStream_t)stream>>>(
+        *w, *c, pos, chunk_start, chunk_len, pad_actions, obs_out, actions_out, t_rewards, t_values, t_policies,
+        value_support, reward_support);
+    MZ_LAUNCH_CHECK();
+    return MZ_OK;
+  }
+  // per warp: rewards [K+T] f32, values / rewards [K+1] f32 each, two-hot bins 2 x [K+1] x 16 B, to_play [K+T]
+  const int warp_smem = (int)((sizeof(float) * (KT + 2 * K1) + 2 * sizeof(TgtBins) * K1 + KT + 15) / 16 * 16);
+  const size_t smem = (size_t)warp_smem * kTgtWarps + (sizeof(float) * KT + 15) / 16 * 16;  // + discount table
   if (smem > 200 * 1024) return MZ_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
@@ -226,9 +580,9 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  build_targets_kernel<<<c->batch, kTgtThreads, smem, (cudaStream_t)stream>>>(
+  build_targets_kernel<<<(c->batch + kTgtWarps - 1) / kTgtWarps, kTgtThreads, smem, (cudaStream_t)stream>>>(
       *w, *c, pos, chunk_start, chunk_len, pad_actions, obs_out, actions_out, t_rewards, t_values,
-      t_policies, value_support, reward_support);
+      t_policies, value_support, reward_support, warp_smem);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }

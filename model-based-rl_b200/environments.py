@@ -62,3 +62,38 @@ class VectorTicTacToe(object):
     self.turn *= -1
     obs = self.turn[:, None] * self.board
     return obs.copy(), reward, won | draw, result
+
+
+class SyntheticFrames(object):
+  """G independent synthetic single-player episodes with image observations [C, H, W] float32 in [0, 1)
+  (the shape BASELINE.json's conv configuration names): every action is legal, rewards are seeded noise
+  in {-1, 0, 1}, an episode ends after `episode_length` steps.  Stands in for the Atari wrappers
+  (wrappers.py), which are environment code and not on the GPU hot path."""
+
+  two_players = False
+
+  def __init__(self, num_games, num_actions, obs_shape, episode_length=8, seed=0):
+    self.num_games, self.num_actions, self.obs_shape = int(num_games), int(num_actions), tuple(obs_shape)
+    self.episode_length = int(episode_length)
+    self.rng = np.random.default_rng(seed)
+    self.elapsed = np.zeros(self.num_games, dtype=np.int32)
+
+  def _frames(self, n):
+    return self.rng.random((n,) + self.obs_shape, dtype=np.float32)
+
+  def reset(self, which=None):
+    idx = np.arange(self.num_games) if which is None else np.asarray(which)
+    self.elapsed[idx] = 0
+    return self._frames(len(idx))
+
+  def legal_mask(self):
+    return np.full(self.num_games, (1 << self.num_actions) - 1, dtype=np.uint32)
+
+  def step(self, actions):
+    actions = np.asarray(actions)
+    if ((actions < 0) | (actions >= self.num_actions)).any():
+      raise ValueError("action outside the action space")
+    self.elapsed += 1
+    reward = self.rng.integers(-1, 2, size=self.num_games).astype(np.int32)
+    done = self.elapsed >= self.episode_length
+    return self._frames(self.num_games), reward, done, np.full(self.num_games, -1)

@@ -15,6 +15,7 @@ channels), 24 x 24, 12 x 12 and 6 x 6 pixels run on the same implicit-GEMM kerne
 convolutions as im2col + the kernel's plain-GEMM mode, the two average pools as a small kernel; the
 only torch operation left is the layout change of the raw observation.
 """
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -488,6 +489,33 @@ class ConvSearch(object):
     self.run()
     eng = self.eng
     return eng.actions, eng.root_value, eng.child_visits, self.init_value
+
+
+  def search_host(self, obs, noise=None, uniforms=None, temperature=None, legal=None, to_play=None):
+    """Same call as `FCSearch.search_host` (networks.py), so `selfplay.BatchedActor(search=...)` drives either
+    engine: HOST arrays in -- frames [G, C, 96, 96] float32, Dirichlet noise [G, A] float64 (row g: one value
+    per legal action of game g), uniforms / temperature [G] float64, optional legal-action bit masks [G] and
+    to_play [G] -- and pinned host tensors out: actions [G] i32, root_value [G] f64, child_visits [G, A] f64,
+    initial-inference value [G] f32 (actors.py:131-153).  Both copies are part of the call."""
+    dev = self.net.device
+    if getattr(self, '_host_out', None) is None:
+      G, A = self.G, self.A
+      self._host_out = (torch.zeros(G, dtype=torch.int32).pin_memory(), torch.zeros(G, dtype=torch.float64).pin_memory(),
+                        torch.zeros((G, A), dtype=torch.float64).pin_memory(), torch.zeros(G, dtype=torch.float32).pin_memory())
+    if legal is not None:
+      self.legal.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(legal).astype(np.int64).astype(np.int32))),
+                       non_blocking=True)
+    if to_play is not None:
+      self.to_play.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(to_play, dtype=np.int8))), non_blocking=True)
+    self.use_noise = noise is not None or self.use_noise
+    obs = torch.as_tensor(obs)
+    if obs.dtype != torch.float32:
+      raise TypeError("search_host expects float32 frames")
+    outs = self.search(obs, noise, uniforms, temperature)
+    for h, d in zip(self._host_out, outs):
+      h.copy_(d, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return self._host_out
 
 
 def C_ptr(t):

@@ -312,3 +312,45 @@ def test_conv_search_replays_bit_exact_in_oracle():
     assert float((pol[0] - cs.record[2][sim, 0]).abs().max()) < 0.1
     got_h = from_padded(pool[0, sim + 1].reshape(49, 128), 1)
     assert float((got_h - h2).abs().max()) < 0.05
+
+
+def test_selfplay_driver_through_conv_search():
+  """BatchedActor(search=ConvSearch): the per-move body of Actor.play_game (actors.py:125-176) with
+  MuZeroNetwork behind the same `search_host` call as FCSearch.  Moves are compared with a second actor
+  that drives the generic path (BatchedMCTS + one recurrent_inference call per simulation) on an identical
+  environment and identical draws; history slices reach the sink with the reference's chunking rules."""
+  from model_based_rl_b200.environments import SyntheticFrames
+  from model_based_rl_b200.muzero import ConvSearch, MuZeroNetwork
+  from model_based_rl_b200.selfplay import BatchedActor
+  from oracle import muzero_ref
+  C_in, A, G, S = 4, 6, 5, 6
+  net = MuZeroNetwork(C_in, A, "cuda", CFG)
+  net.load_weights(muzero_ref.seeded_state_dict(C_in, A, 7))
+  cfg = types.SimpleNamespace(num_simulations=S, action_space=A, two_players=False, discount=0.997,
+                              pb_c_base=19652, pb_c_init=1.25, init_value_score=0.0, known_bounds=[None, None],
+                              root_exploration_fraction=0.25, root_dirichlet_alpha=0.25, num_unroll_steps=2,
+                              td_steps=2, max_history_length=3, max_steps=100, norm_obs=False)
+  fast = BatchedActor(cfg, net, SyntheticFrames(G, A, (C_in, 96, 96), episode_length=4, seed=11),
+                      search=ConvSearch(cfg, net, G))
+  slow = BatchedActor(cfg, net, SyntheticFrames(G, A, (C_in, 96, 96), episode_length=4, seed=11))
+  rng = np.random.default_rng(5)
+  for move in range(6):
+    noise, u = rng.dirichlet([0.25] * A, size=G), rng.random(G)
+    a1, v1, cv1, e1, d1 = fast.play_move(noise=noise, uniforms=u)
+    a2, v2, cv2, e2, d2 = slow.play_move(noise=noise, uniforms=u)
+    # both paths evaluate the same bf16 network; the generic path round-trips hidden states through the
+    # reference's [G, 128, 6, 6] float32 layout, so values agree to rounding and visit counts almost always
+    assert np.allclose(v1, v2, atol=5e-2), (move, v1, v2)
+    assert np.abs(cv1 - cv2).max() <= 2.0 / S + 1e-12
+    assert np.array_equal(d1, d2)
+    assert cv1.shape == (G, A) and np.allclose(cv1.sum(1), 1.0)
+    assert ((a1 >= 0) & (a1 < A)).all()
+    # keep the two environments in lock step whatever the sampled actions were
+    slow.env.rng = np.random.default_rng(100 + move)
+    fast.env.rng = np.random.default_rng(100 + move)
+  assert fast.games_played == G and fast.experiences_collected == 6 * G
+  # chunking: max_history_length = 3 -> one slice after 3 moves (ignore = overlap), one at the terminal move
+  kinds = [(ign, term) for (_, _, ign, term) in fast.saved]
+  assert kinds.count((4, False)) == G and kinds.count((None, True)) == G
+  first = [h for (i, h, ign, term) in fast.saved if i == 0][0]
+  assert len(first.actions) == 3 and len(first.observations) == 4 and first.observations[0].shape == (C_in, 96, 96)

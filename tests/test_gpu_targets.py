@@ -33,9 +33,19 @@ def _window_from_golden(g):
   return dev, np.array(starts, np.int64), np.array(lens, np.int32)
 
 
+@pytest.fixture(params=[0, 1], ids=["kernel_by_shape", "warp_per_row_kernel"])
+def targets_kernel(request):
+  """Both kernels behind mz_build_targets (include/mzb200.h) run every case they are able to."""
+  from model_based_rl_b200 import _lib
+  lib = _lib.load()
+  lib.mz_debug_set_targets_kernel(request.param)
+  yield request.param
+  lib.mz_debug_set_targets_kernel(0)
+
+
 @pytest.mark.parametrize("case", REPLAY_CASES)
 @pytest.mark.parametrize("fuse", [False, True])
-def test_build_targets_matches_reference(case, fuse):
+def test_build_targets_matches_reference(case, fuse, targets_kernel):
   from model_based_rl_b200 import _lib
   from model_based_rl_b200.config import Config
   lib = _lib.load()
@@ -158,3 +168,79 @@ def test_full_size_target_properties():
   beyond = (step[:, None] + np.arange(K + 1)[None, :]) >= lens[ci][:, None]
   assert (o1[4].cpu().numpy()[beyond] == 0).all() and (o1[3].cpu().numpy()[beyond] == 0).all()
   assert np.allclose(o1[4].cpu().numpy()[~beyond].sum(-1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [
+    # A, K, T, B, E, obs_u8, normalise, two players
+    (4, 5, 10, 13, 7, True, True, False),      # odd byte observations, batch not a multiple of the CTA's rows
+    (9, 5, 10, 64, 9, False, False, True),     # Tic-Tac-Toe shape: sign flips by to_play
+    (3, 0, 3, 5, 4, False, True, False),       # no unroll steps
+    (2, 40, 1000, 9, 8, False, False, True),   # more unroll positions than lanes, LunarLander's td_steps
+    (18, 5, 1, 33, 12, True, False, False),    # td_steps = 1
+    (4, 15, 64, 7, 128, True, False, True),    # the lane-per-position kernel's limits: 16 positions, td_steps 64
+    (6, 9, 7, 31, 16, False, True, True),      # three rows per warp, two idle lanes
+])
+def test_build_targets_ragged_shapes_match_oracle(shape, targets_kernel):
+  """Every row of a batch against oracle.insert_target (replay_buffer.py:165-198) on short ragged chunks:
+  positions at and past the chunk end, first position of a chunk, shapes off the vectorised paths."""
+  import oracle
+  from model_based_rl_b200 import _lib
+  from model_based_rl_b200.config import Config
+  A, K, T, B, E, u8, norm, two = shape
+  lib = _lib.load()
+  rng = np.random.default_rng(A * 1000 + K * 10 + T)
+  lens = rng.integers(1, 60, size=40).astype(np.int32)
+  lens[:3] = [1, 2, K + T + 5]
+  starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+  P = int(lens.sum())
+  obs_np = rng.integers(0, 256, size=(P, E), dtype=np.uint8) if u8 else rng.normal(size=(P, E)).astype(np.float32)
+  rewards = (rng.normal(size=P) * (rng.random(P) < 0.5)).astype(np.float32)
+  to_play = (rng.choice([-1, 1], size=P) if two else np.ones(P)).astype(np.int8)
+  root_values = rng.normal(0, 2, size=P)
+  cv = rng.random((P, A)).astype(np.float32)
+  cv /= cv.sum(1, keepdims=True)
+  actions = rng.integers(0, A, size=P, dtype=np.int32)
+  disc = 0.997
+  ci = rng.integers(0, len(lens), size=B)
+  ci[:3] = [0, 1, 2]
+  step = (rng.random(B) * lens[ci]).astype(np.int64)
+  step[2] = 0
+  step[-1] = lens[ci[-1]] - 1
+  pads_np = rng.integers(0, A, size=(B, max(K, 1)), dtype=np.int32)[:, :K].copy()
+  omin = rng.normal(size=E).astype(np.float32)
+  orng = (rng.random(E) + 0.5).astype(np.float32)
+  d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+  t_obs, t_act, t_rew, t_tp, t_rv, t_cv = d(obs_np), d(actions), d(rewards), d(to_play), d(root_values), d(cv)
+  t_min, t_rng = d(omin), d(orng)
+  discounts = d(np.array([disc**n for n in range(K + T)], np.float32))
+  win = _lib.Window(A, E, int(u8), 0, t_obs.data_ptr(), t_act.data_ptr(), t_rew.data_ptr(), t_tp.data_ptr(),
+                    t_rv.data_ptr(), t_cv.data_ptr())
+  tc = _lib.TargetCfg(B, K, T, 1, -15, 15, -15, 15, 0, int(norm), disc**T, discounts.data_ptr(),
+                      t_min.data_ptr() if norm else None, t_rng.data_ptr() if norm else None)
+  pos, cs, cl = d(starts[ci] + step), d(starts[ci]), d(lens[ci])
+  pads = d(pads_np) if K else torch.zeros(1, dtype=torch.int32, device="cuda")
+  out = [torch.full((B, E), -7.0, device="cuda"), torch.full((B, max(K, 1)), -7, dtype=torch.int32, device="cuda")[:, :K].contiguous(),
+         torch.full((B, K + 1), -7.0, device="cuda"), torch.full((B, K + 1), -7.0, device="cuda"),
+         torch.full((B, K + 1, A), -7.0, device="cuda"), torch.full((B, K + 1, 31), -7.0, device="cuda"),
+         torch.full((B, K + 1, 31), -7.0, device="cuda")]
+  ptrs = [_lib.ptr(o) if o.numel() else _lib.ptr(pads) for o in out]
+  _lib.check(lib.mz_build_targets(win, tc, _lib.ptr(pos), _lib.ptr(cs), _lib.ptr(cl), _lib.ptr(pads), *ptrs,
+                                  _lib.current_stream()), "mz_build_targets")
+  torch.cuda.synchronize()
+  obs, acts, tr, tv, tp, vs, rs = [o.cpu().numpy() for o in out]
+  for b in range(B):
+    lo, n, s = int(starts[ci[b]]), int(lens[ci[b]]), int(step[b])
+    sl = slice(lo, lo + n)
+    wr, wv, wp = oracle.insert_target(rewards[sl], to_play[sl], root_values[sl], cv[sl], K, T, disc, s)
+    assert np.array_equal(tr[b], wr), (b, tr[b], wr)
+    assert np.array_equal(tp[b], wp)
+    assert np.max(np.abs(tv[b] - wv) / np.maximum(np.abs(wv), 1.0)) <= 1e-5
+    want_obs = obs_np[lo + s].astype(np.float32)
+    if norm:
+      want_obs = (want_obs - omin) / orng
+    assert np.array_equal(obs[b], want_obs)
+    real = actions[lo + s:lo + min(s + K, n)]
+    assert np.array_equal(acts[b], np.concatenate([real, pads_np[b, :K - len(real)]]))
+  cfgobj = Config(dict(value_support=[-15, 15], reward_support=[-15, 15], no_target_transform=False))
+  assert torch.equal(out[5], cfgobj.value_phi(Config.scalar_transform(out[3])))
+  assert torch.equal(out[6], cfgobj.reward_phi(Config.scalar_transform(out[2])))
