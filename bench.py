@@ -193,7 +193,41 @@ class ClockSampler(object):
   def __init__(self, index):
     self.rows, self.proc, self.index = [], None, index
 
+  def _nvml_loop(self):
+    """Samples through NVML every 2 ms: the timed region of the default run lasts ~50 ms, which
+    `nvidia-smi -lms 100` sees once."""
+    nv, h = self.nv, self.handle
+    bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+    get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+    while not self.stop_flag:
+      try:
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mask = int(get_reasons(h))
+        row = [str(sm), str(mx), ""] + ["Active" if mask & b else "Not Active" for b in
+                                        (bits[n] for n in self.NAMES)]
+        self.rows.append(row)
+      except Exception:
+        pass
+      time.sleep(0.002)
+
   def start(self):
+    self.stop_flag, self.nv = False, None
+    try:
+      import pynvml as nv
+      nv.nvmlInit()
+      self.handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+      self.nv = nv
+      self.how = "nvml, 2 ms"
+      self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+      self.thread.start()
+      return
+    except Exception:
+      self.nv = None
+    self.how = "nvidia-smi -lms 100"
     try:
       self.proc = subprocess.Popen(
           ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -209,14 +243,18 @@ class ClockSampler(object):
       self.rows.append([c.strip() for c in line.split(",")])
 
   def stop(self):
-    if self.proc is None:
+    if self.nv is not None:
+      self.stop_flag = True
+      self.thread.join(timeout=1)
+    elif self.proc is None:
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    time.sleep(0.15)
-    self.proc.terminate()
-    try:
-      self.proc.wait(timeout=2)
-    except subprocess.TimeoutExpired:
-      self.proc.kill()
+    else:
+      time.sleep(0.15)
+      self.proc.terminate()
+      try:
+        self.proc.wait(timeout=2)
+      except subprocess.TimeoutExpired:
+        self.proc.kill()
     sm, mx, reasons = [], [], set()
     for r in self.rows:
       try:
@@ -228,7 +266,7 @@ class ClockSampler(object):
         if cell.lower().startswith("active"):
           reasons.add(name)
     return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-            "samples": len(sm), "reasons": sorted(reasons)}
+            "samples": len(sm), "sampler": self.how, "reasons": sorted(reasons)}
 
 
 def measured_peaks():

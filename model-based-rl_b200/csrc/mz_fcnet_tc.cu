@@ -162,6 +162,13 @@ MZ_DEV uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
+// relu + round-to-nearest bf16 pair in one instruction (F2FP.RELU.BF16.PACK_AB)
+MZ_DEV uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 // ---- thread-block cluster helpers (distributed shared memory hand-off of h') --------------------
 MZ_DEV uint32_t cluster_ctarank() {
   uint32_t r;
@@ -230,28 +237,43 @@ struct TcParams {
     if (p.trace && blockIdx.x == p.trace_block) p.trace[(slot)] = clock64();    \
   } while (0)
 
-// softmax(logits + bias) . support, then h^-1, all in registers (one thread per row)
-MZ_DEV float support_to_scalar_regs(const uint32_t (&v)[32], const float* bias, int bins, int mn,
-                                    int no_tt) {
-  float x[32];
+MZ_DEV float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// softmax(logits + bias) . support, then h^-1, all in registers (one thread per row).  The thread is one
+// in-order instruction stream, so the instruction count is the cost: packed float32x2 arithmetic (FADD2 /
+// FFMA2) halves it.  The bias of the padding columns (j >= bins) is -inf (fc_tc_pack_kernel), which drops
+// them from the maximum and gives them weight exp2(-inf) = 0 without a per-column predicate.
+MZ_DEV float support_to_scalar_regs(const uint32_t (&v)[32], const float* bias, int mn, int no_tt) {
+  float2 x[16];
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 b = b4[k];
+    x[2 * k] = __fadd2_rn(make_float2(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1])), make_float2(b.x, b.y));
+    x[2 * k + 1] = __fadd2_rn(make_float2(__uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3])), make_float2(b.z, b.w));
+  }
   float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four chains keep dependencies short
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    x[j] = __uint_as_float(v[j]) + bias[j];
-    if (j < bins) m4[j & 3] = fmaxf(m4[j & 3], x[j]);
-  }
+  for (int k = 0; k < 16; ++k) m4[k & 3] = fmaxf(m4[k & 3], fmaxf(x[k].x, x[k].y));
   const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-  float den4[4] = {0.0f, 0.0f, 0.0f, 0.0f}, num4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  const float l2e = 1.4426950408889634f;
+  const float2 scale = make_float2(l2e, l2e), shift = make_float2(-m * l2e, -m * l2e);
+  float2 den[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+  float2 num[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    x[j] = j < bins ? __expf(x[j] - m) : 0.0f;
-    den4[j & 3] += x[j];
-    num4[j & 3] = fmaf((float)(mn + j), x[j], num4[j & 3]);
+  for (int k = 0; k < 16; ++k) {
+    const float2 t = __ffma2_rn(x[k], scale, shift);  // (x - m) * log2(e)
+    const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+    den[k & 1] = __fadd2_rn(den[k & 1], e);
+    num[k & 1] = __ffma2_rn(e, make_float2((float)(2 * k), (float)(2 * k + 1)), num[k & 1]);
   }
-  const float den = (den4[0] + den4[1]) + (den4[2] + den4[3]);
-  float num = (num4[0] + num4[1]) + (num4[2] + num4[3]);
-  num = num / den;
-  return no_tt ? num : mz_inverse_scalar_transform_f(num);
+  const float2 d2 = __fadd2_rn(den[0], den[1]), n2 = __fadd2_rn(num[0], num[1]);
+  const float mean = __fdividef(n2.x + n2.y, d2.x + d2.y) + (float)mn;  // sum_j (mn + j) softmax_j
+  return no_tt ? mean : mz_inverse_scalar_transform_f(mean);
 }
 
 // immediate-predicate MMA wrappers: the issuing thread is a single dependent instruction stream
@@ -340,7 +362,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
   uint64_t* a3_remote = bars + 20;    // rank 0 of a split pair: h' rows have arrived from rank 1
   uint64_t* h_stored = bars + 21;     // the store warp is done with sOut (the logits reuse it)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
-  float* sTail = reinterpret_cast<float*>(bars + 23);   // second-layer biases + LayerNorm affine
+  float* sTail = reinterpret_cast<float*>(bars + 24);   // 16-byte aligned: second-layer biases + LayerNorm affine
   float* sOut = sTail + TAIL_FLOATS;                    // [128][51]: row-major staging of h'
   float* sLog = sOut;                                   // [128][A]: the logits reuse it at the very end
   for (int i = threadIdx.x; i < TAIL_FLOATS; i += TC_THREADS) sTail[i] = p.tail[i];
@@ -551,8 +573,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       uint32_t pk[32];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        pk[j] = pack_bf16(fmaxf(__uint_as_float(v[2 * j]), 0.0f), fmaxf(__uint_as_float(v[2 * j + 1]), 0.0f));
-        pk[16 + j] = pack_bf16(fmaxf(__uint_as_float(v2[2 * j]), 0.0f), fmaxf(__uint_as_float(v2[2 * j + 1]), 0.0f));
+        pk[j] = pack_bf16_relu(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        pk[16 + j] = pack_bf16_relu(__uint_as_float(v2[2 * j]), __uint_as_float(v2[2 * j + 1]));
       }
       tmem_st32(a2, pk);
       tmem_wait_st();
@@ -575,7 +597,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       if (c0 == 0 && own_reward) {  // initial_inference has no reward (networks.py:29 returns 0)
         tmem_ld32(lane_addr + COL_D2A, v);
         tmem_wait_ld();
-        const float rew = support_to_scalar_regs(v, sTail + T_REW_B, p.reward_bins, p.reward_min, p.no_tt);
+        const float rew = support_to_scalar_regs(v, sTail + T_REW_B, p.reward_min, p.no_tt);
         if (live) p.reward[g] = rew;
       }
     } else if (own_hidden) {
@@ -583,31 +605,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       tmem_ld32(lane_addr + COL_D2B, v);
       tmem_ld32(lane_addr + COL_D2B + 32, v2);
       tmem_wait_ld();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        hbuf[j] = __uint_as_float(v[j]) + sTail[T_DYN_B + j];
-        hbuf[32 + j] = __uint_as_float(v2[j]) + sTail[T_DYN_B + 32 + j];
-      }
-      // LayerNorm over the 50 state features; four partial sums keep the dependency chains short
-      float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll
-      for (int j = 0; j < 48; j += 4) { s0 += hbuf[j]; s1 += hbuf[j + 1]; s2 += hbuf[j + 2]; s3 += hbuf[j + 3]; }
-      const float mean = ((s0 + s1) + (s2 + s3) + hbuf[48] + hbuf[49]) / (float)H;
-      float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
-#pragma unroll
-      for (int j = 0; j < 48; j += 4) {
-        const float d0 = hbuf[j] - mean, d1_ = hbuf[j + 1] - mean, d2_ = hbuf[j + 2] - mean, d3 = hbuf[j + 3] - mean;
-        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1_, d1_, q1); q2 = fmaf(d2_, d2_, q2); q3 = fmaf(d3, d3, q3);
-      }
+      // LayerNorm over the 50 state features in packed float32x2 arithmetic (25 pairs; this thread is one
+      // in-order stream on the kernel's critical path, the instruction count is its cost)
+      float2 h2[H / 2];
       {
-        const float d0 = hbuf[48] - mean, d1_ = hbuf[49] - mean;
-        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1_, d1_, q1);
-      }
-      const float rstd = 1.0f / sqrtf(((q0 + q1) + (q2 + q3)) / (float)H + 1e-5f);
+        const float4* b4 = reinterpret_cast<const float4*>(sTail + T_DYN_B);
 #pragma unroll
-      for (int j = 0; j < 64; ++j)
-        hbuf[j] = j < H ? fmaxf((hbuf[j] - mean) * rstd * sTail[T_LN_W + j] + sTail[T_LN_B + j], 0.0f)
-                        : (j == H ? 1.0f : 0.0f);  // column H feeds the folded first-layer bias
+        for (int k = 0; k < 8; ++k) {
+          const float4 b = b4[k];
+          h2[2 * k] = __fadd2_rn(make_float2(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1])), make_float2(b.x, b.y));
+          h2[2 * k + 1] = __fadd2_rn(make_float2(__uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3])), make_float2(b.z, b.w));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 b = b4[8 + k];
+          h2[16 + 2 * k] = __fadd2_rn(make_float2(__uint_as_float(v2[4 * k]), __uint_as_float(v2[4 * k + 1])), make_float2(b.x, b.y));
+          h2[16 + 2 * k + 1] = __fadd2_rn(make_float2(__uint_as_float(v2[4 * k + 2]), __uint_as_float(v2[4 * k + 3])), make_float2(b.z, b.w));
+        }
+        const float2 b = *reinterpret_cast<const float2*>(sTail + T_DYN_B + 48);
+        h2[24] = __fadd2_rn(make_float2(__uint_as_float(v2[16]), __uint_as_float(v2[17])), b);
+      }
+      float2 s2[4] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+#pragma unroll
+      for (int k = 0; k < H / 2; ++k) s2[k & 3] = __fadd2_rn(s2[k & 3], h2[k]);
+      const float2 st = __fadd2_rn(__fadd2_rn(s2[0], s2[1]), __fadd2_rn(s2[2], s2[3]));
+      const float mean = (st.x + st.y) * (1.0f / (float)H);
+      const float2 nmean = make_float2(-mean, -mean);
+      float2 q2[4] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+#pragma unroll
+      for (int k = 0; k < H / 2; ++k) {
+        h2[k] = __fadd2_rn(h2[k], nmean);
+        q2[k & 3] = __ffma2_rn(h2[k], h2[k], q2[k & 3]);
+      }
+      const float2 qt = __fadd2_rn(__fadd2_rn(q2[0], q2[1]), __fadd2_rn(q2[2], q2[3]));
+      const float rstd = rsqrtf((qt.x + qt.y) * (1.0f / (float)H) + 1e-5f);
+      const float2 rstd2 = make_float2(rstd, rstd);
+      {
+        const float2* w2 = reinterpret_cast<const float2*>(sTail + T_LN_W);
+        const float2* b2 = reinterpret_cast<const float2*>(sTail + T_LN_B);
+#pragma unroll
+        for (int k = 0; k < H / 2; ++k) {
+          const float2 y = __ffma2_rn(__fmul2_rn(h2[k], rstd2), w2[k], b2[k]);
+          hbuf[2 * k] = fmaxf(y.x, 0.0f);
+          hbuf[2 * k + 1] = fmaxf(y.y, 0.0f);
+        }
+      }
+      hbuf[H] = 1.0f;  // column H feeds the folded first-layer bias
+#pragma unroll
+      for (int j = H + 1; j < 64; ++j) hbuf[j] = 0.0f;
       {
         // h' as the bf16 A operand of the prediction layer: this row of the canonical K-major image,
         // in this CTA's shared memory and -- in a split pair -- in the peer's as well
@@ -656,7 +701,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams
       if (own_value) {
         tmem_ld32(lane_addr + COL_D2A, v);
         tmem_wait_ld();
-        const float val = support_to_scalar_regs(v, sTail + T_VAL_B, p.value_bins, p.value_min, p.no_tt);
+        const float val = support_to_scalar_regs(v, sTail + T_VAL_B, p.value_min, p.no_tt);
         if (live) p.value[g] = val;
       }
     } else if (own_logits) {
@@ -723,11 +768,11 @@ __global__ void fc_tc_pack_kernel(mz_fc_weights w, int k1, int chunk0, uint8_t* 
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TAIL_FLOATS; i += gridDim.x * blockDim.x) {
     float x = 0.0f;
-    if (i < T_DYN_B) x = i < w.reward_bins ? w.rew_b2[i] : 0.0f;
+    if (i < T_DYN_B) x = i < w.reward_bins ? w.rew_b2[i] : -INFINITY;  // padding columns: see support_to_scalar_regs
     else if (i < T_LN_W) x = (i - T_DYN_B) < H ? (init ? w.rep_b2 : w.dyn_b2)[i - T_DYN_B] : 0.0f;
     else if (i < T_LN_B) x = (i - T_LN_W) < H ? w.ln_w[i - T_LN_W] : 0.0f;
     else if (i < T_VAL_B) x = (i - T_LN_B) < H ? w.ln_b[i - T_LN_B] : 0.0f;
-    else if (i < T_POL_B) x = (i - T_VAL_B) < w.value_bins ? w.val_b2[i - T_VAL_B] : 0.0f;
+    else if (i < T_POL_B) x = (i - T_VAL_B) < w.value_bins ? w.val_b2[i - T_VAL_B] : -INFINITY;
     else x = (i - T_POL_B) < A ? w.pol_b2[i - T_POL_B] : 0.0f;
     tail[i] = x;
   }
@@ -743,7 +788,7 @@ int k1_obs(int obs_dim) { return (obs_dim + 1 + 15) / 16 * 16; }  // observation
 
 size_t tc_smem_bytes(int k1, int stages) {
   return (size_t)ROWS * k1 * 2 + (size_t)stages * stage_bytes_for(k1) +
-         (size_t)ROWS * K3 * 2 + 23 * sizeof(uint64_t) + TAIL_FLOATS * sizeof(float) +
+         (size_t)ROWS * K3 * 2 + 24 * sizeof(uint64_t) + TAIL_FLOATS * sizeof(float) +
          ROWS * OUT_STRIDE * sizeof(float);
 }
 

@@ -282,7 +282,10 @@ build_targets_rows_kernel(mz_window w, mz_target_cfg c, const int64_t* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = c.num_unroll_steps, T = c.td_steps, A = w.num_actions, E = w.obs_elems;
   const int NP = K + 1, R = 32 / NP;
-  const int row0 = (blockIdx.x * kTgtWarps + warp) * R;
+  // two warps share a group of R rows: role 0 moves observations / policies / actions, role 1 builds the
+  // value / reward targets and their supports.  The two dependent-load chains run side by side.
+  const int role = warp & 1;
+  const int row0 = (blockIdx.x * (kTgtWarps / 2) + (warp >> 1)) * R;
   if (row0 >= c.batch) return;
   const int nrows = min(R, c.batch - row0);
   const int r = lane / NP, i = lane - r * NP;
@@ -303,7 +306,7 @@ build_targets_rows_kernel(mz_window w, mz_target_cfg c, const int64_t* __restric
 
   // ---- observations: np.float32(history.observations[step]) (replay_buffer.py:147).  Rows go in groups of
   // kRowsGroup: all loads of a group are issued before its first store (one DRAM round trip per group)
-  {
+  if (role == 0) {
     const bool vec = (E & 3) == 0 && ((reinterpret_cast<uintptr_t>(w.obs) | reinterpret_cast<uintptr_t>(obs_out)) & 15) == 0 &&
                      (!c.normalize_obs || ((reinterpret_cast<uintptr_t>(c.obs_min) | reinterpret_cast<uintptr_t>(c.obs_range)) & 15) == 0);
     const uint8_t* obs_u8 = reinterpret_cast<const uint8_t*>(w.obs);
@@ -372,7 +375,7 @@ build_targets_rows_kernel(mz_window w, mz_target_cfg c, const int64_t* __restric
   }
   // ---- policy targets: child_visits of the positions inside the chunk, zeros after its end
   // (replay_buffer.py:90, 184, 196); the (K+1) * A floats of a row are one contiguous run on both sides
-  for (int rr0 = 0; rr0 < nrows; rr0 += kRowsGroup) {
+  for (int rr0 = 0; rr0 < nrows && role == 0; rr0 += kRowsGroup) {
     const float* src[kRowsGroup];
     int n_real[kRowsGroup];
 #pragma unroll
@@ -393,11 +396,12 @@ build_targets_rows_kernel(mz_window w, mz_target_cfg c, const int64_t* __restric
     }
   }
   // ---- actions: history.actions[step:step+K], padded with random actions (replay_buffer.py:149-152)
-  if (active && i < K) {
+  if (role == 0 && active && i < K) {
     const int n_real = max(0, min(K, len - step));
     actions_out[(size_t)b * K + i] = i < n_real ? w.actions[pos + i] : pad_actions[(size_t)b * K + (i - n_real)];
   }
 
+  if (role == 0) return;
   // ---- insert_target (replay_buffer.py:165-198) for position i of row r
   const int ci = step + i;
   float value = 0.0f, last_reward = 0.0f;
@@ -562,7 +566,7 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
     return MZ_ERR_BAD_ARG;
   const int K1 = c->num_unroll_steps + 1, KT = c->num_unroll_steps + c->td_steps;
   if (K1 <= kRowsMaxPos && c->td_steps <= kRowsMaxTd && g_targets_kernel != 1) {
-    const int rows_per_cta = kTgtWarps * (32 / K1);
+    const int rows_per_cta = (kTgtWarps / 2) * (32 / K1);
     build_targets_rows_kernel<<<(c->batch + rows_per_cta - 1) / rows_per_cta, kTgtThreads, 0, (cudaStream_t)stream>>>(
         *w, *c, pos, chunk_start, chunk_len, pad_actions, obs_out, actions_out, t_rewards, t_values, t_policies,
         value_support, reward_support);

@@ -354,8 +354,15 @@ struct ImgLoad {
 // (mcts.py:106-112): returns the winning lane or -1 when no lane is a candidate.
 MZ_DEV int warp_argmax(double score, bool cand) {
   const unsigned long long key = cand ? sortable_key(score) : 0ull;
-  const unsigned long long best_key = warp_max_key(key);
-  const unsigned winners = __ballot_sync(MZ_FULL, cand && key == best_key);
+  const unsigned hi = (unsigned)(key >> 32);
+  const unsigned hi_max = __reduce_max_sync(MZ_FULL, hi);
+  unsigned winners = __ballot_sync(MZ_FULL, cand && hi == hi_max);
+  if (__popc(winners) > 1) {  // warp-uniform and rare: the scores agree in sign, exponent and 20 mantissa bits
+    const unsigned lo = (unsigned)key;
+    const bool top = cand && hi == hi_max;
+    const unsigned lo_max = __reduce_max_sync(MZ_FULL, top ? lo : 0u);
+    winners = __ballot_sync(MZ_FULL, top && lo == lo_max);
+  }
   return winners ? 31 - __clz(winners) : -1;
 }
 

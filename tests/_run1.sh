@@ -1,5 +1,8 @@
 set -x
-timeout 300 python -m pytest tests/test_gpu_targets.py tests/test_gpu_search.py -x -q 2>&1 | tail -8
-timeout 120 python tests/targets_bench.py 2>&1 | grep -v "^ *\"\(kernel\|bound\|unit\|traffic\|peak\|peak_source\|workload\|algorithmic\)" | tail -40
-timeout 120 python tests/tree_probe.py 1024 2>&1 | grep "games 1024"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:tree_step_w32 -s 40 -c 1 -o gpurun_out/r01s_tree python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph --no-conv --no-sweep --streams 1 --games 1024 > gpurun_out/r01s_ncu_tree.log 2>&1; echo ncu_rc=$?
+timeout 600 python -m pytest tests/test_gpu_fcnet.py tests/test_gpu_search.py -x -q 2>&1 | tail -3
+timeout 120 python tests/tc_trace.py 0 2>&1 | grep "d2_full\|A1 ready\|chunk  [0147]" | head -12
+for st in 4 2 3 5 6 8 4; do
+timeout 200 python bench.py --no-conv --no-cpu-baseline --no-sweep --streams $st --steps 30 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('streams', d['streams'], 'value %.1fM'%(d['value']/1e6), 'ms %.4f'%d['ms_per_step'], 'e2e %.1fM'%(d['e2e']['value']/1e6), 'fc %.2f tree %.2f'%(d['kernel_share']['fc_recurrent_us'], d['kernel_share']['tree_step_us']))"
+done
