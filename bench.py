@@ -413,6 +413,7 @@ def run_b200(args):
                             pk["bf16_tflops_sustained"]}
   others = bench_other_configs(args, torch, dev, timed) if rank == 0 and world == 1 and not args.no_sweep else None
   targets = bench_targets(torch, _lib, dev) if rank == 0 else None
+  replay = bench_replay(torch, _lib, dev, cpu_baseline=not args.no_cpu_baseline) if rank == 0 else None
   learner = bench_learner(torch, _lib, dev, world, barrier)  # every rank: the step all-reduces at N > 1
   conv = bench_conv(args, torch, _lib, dev) if rank == 0 and not args.no_conv else None
 
@@ -455,7 +456,7 @@ def run_b200(args):
         "gpu_launches": fs.launches_per_move * args.steps,
         "clocks": clock_info, "roofline": dominant, "roofline_all": [roof_tree, roof_fc],
         "kernel_share": kern, "cuda_graph": not args.no_graph, "streams": len(fs.lanes),
-        "games_sweep": sweep, "other_configs": others, "targets": targets, "learner": learner,
+        "games_sweep": sweep, "other_configs": others, "targets": targets, "replay": replay, "learner": learner,
         "conv": conv,
     }
     if cpu_baseline is not None:
@@ -670,6 +671,77 @@ def bench_targets(torch, _lib, dev):
                                "peak_source": peaks["source"]}}
   res["bulk"] = bulk
   return res
+
+
+def bench_replay(torch, _lib, dev, cpu_baseline=True):
+  """The replay facade end to end on the C3 (Breakout-ram) shape: PrioritizedReplay filled through
+  save_history with synthetic 500-step chunks (window 200 000, B = 512, K = 5, td = 10, A = 4, 128-byte
+  observations), then `sample_batch()` (the reference's numpy tuple: sum-tree sampling + target kernel +
+  device-to-host copies), `sample_batch_device()` (nothing leaves the GPU) and `update()`.  Beside it the
+  CPU port of the same row loop (oracle SumTree + oracle insert_target, one process -- the reference's
+  replay buffer is a single Ray actor)."""
+  import types
+  from model_based_rl_b200.replay_buffer import PrioritizedReplay
+  from model_based_rl_b200.selfplay import HistorySlice
+  rng = np.random.default_rng(9)
+  W, A, K, T, B, E, L = 200_000, 4, 5, 10, 512, 128, 500
+  cfg = types.SimpleNamespace(batch_size=B, beta_increment_per_sampling=0.001, epsilon=0.01, alpha=1.0, beta=0.4,
+                              num_unroll_steps=K, td_steps=T, discount=0.997, action_space=A, obs_space=(E,),
+                              window_size=W, window_step=None, max_history_length=L, seed=3)
+  rb = PrioritizedReplay(cfg, device=dev)
+  hist = []
+  n_chunks = W // L
+  for _ in range(n_chunks):
+    obs = list(rng.integers(0, 256, size=(L + 1, E), dtype=np.uint8))
+    cv = rng.random((L, A))
+    h = HistorySlice(obs, (cv / cv.sum(1, keepdims=True)).tolist(), rng.normal(0, 2, size=L).tolist(),
+                     rng.integers(0, A, size=L).tolist(),
+                     np.sign(rng.normal(size=L) * (rng.random(L) < 0.1)).astype(np.int64).tolist(),
+                     np.abs(rng.normal(size=L)).tolist(), [False] * L, list(range(L)), [None] * L, [1] * L)
+    rb.save_history(h, ignore=None, terminal=True)
+    if len(hist) < 40:
+      hist.append(h)
+  torch.cuda.synchronize()
+
+  def wall(fn, n):
+    fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+      fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / n
+  t_host = wall(rb.sample_batch, 20)
+  t_dev = wall(lambda: rb.sample_batch_device(True), 50)
+  _, idxs, _ = rb.sample_batch()
+  errs = np.abs(rng.normal(size=B)).astype(np.float32)
+  t_upd = wall(lambda: rb.update(idxs, errs), 20)
+  out = {"workload": "C3 Breakout-ram replay: window %d filled by save_history, B=%d, K=%d, td=%d, A=%d, obs %d u8" % (W, B, K, T, A, E),
+         "size": rb.size(),
+         "sample_batch_samples_per_s": B / t_host, "sample_batch_ms": t_host * 1e3,
+         "sample_batch_device_samples_per_s": B / t_dev, "sample_batch_device_ms": t_dev * 1e3,
+         "update_ms": t_upd * 1e3}
+  if cpu_baseline:
+    import oracle
+    from oracle import replay_ref
+    tree = replay_ref.SumTreeRef(len(hist) * L, len(hist) * L)
+    for i, h in enumerate(hist):
+      tree.add(replay_ref.get_priorities(np.asarray(h.errors), cfg.epsilon, cfg.alpha), i)
+    arrs = [(np.asarray(h.rewards, np.float64), np.asarray(h.to_play, np.int8), np.asarray(h.root_values),
+             np.asarray(h.child_visits)) for h in hist]
+    t0, rows = time.perf_counter(), 0
+    while time.perf_counter() - t0 < 2.0:
+      picks, _ = replay_ref.sample_indices(tree, B, rng.random(B), 0.4)
+      for (_, _, step, hid) in picks:
+        r, tp, rv, cv = arrs[hid]
+        oracle.insert_target(r, tp, rv, cv, K, T, cfg.discount, step)
+        np.float32(hist[hid].observations[step])
+      rows += B
+    dt = time.perf_counter() - t0
+    out["cpu_baseline"] = {"value": rows / dt, "unit": "samples/s", "cores": 1, "kind": "port",
+                           "sample": "%d rows in %.1f s: python SumTree descent + C insert_target per row "
+                                     "(the reference's sample_batch is a per-row Python loop in one Ray actor)" % (rows, dt)}
+  return out
 
 
 def bench_learner(torch, _lib, dev, world, barrier):

@@ -270,7 +270,7 @@ constexpr int kRowsMaxPos = 16;
 constexpr int kRowsMaxTd = 64;
 constexpr int kRowsGroup = 4;  // rows whose loads are in flight together
 
-__global__ void __launch_bounds__(kTgtThreads)
+__global__ void __launch_bounds__(kTgtThreads, 4)
 build_targets_rows_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ pos_arr,
                           const int64_t* __restrict__ chunk_start, const int32_t* __restrict__ chunk_len,
                           const int32_t* __restrict__ pad_actions, float* __restrict__ obs_out,

@@ -187,3 +187,22 @@ def test_fast_path_through_fcsearch_equals_generic_path():
   for (i, h, ign, term), (j, h2, ign2, term2) in zip(fast.saved, slow.saved):
     assert (i, ign, term) == (j, ign2, term2) and h.actions == h2.actions and h.root_values == h2.root_values
     assert h.child_visits == h2.child_visits and h.errors == h2.errors and h.to_play == h2.to_play
+
+
+def test_synthetic_frames_environment_contract():
+  """environments.SyntheticFrames: the vector-environment contract BatchedActor relies on (reset / step /
+  legal_mask / elapsed), deterministic under its seed."""
+  from model_based_rl_b200.environments import SyntheticFrames
+  a, b = SyntheticFrames(3, 6, (2, 8, 8), episode_length=2, seed=4), SyntheticFrames(3, 6, (2, 8, 8), episode_length=2, seed=4)
+  o1, o2 = a.reset(), b.reset()
+  assert o1.shape == (3, 2, 8, 8) and o1.dtype == np.float32 and np.array_equal(o1, o2)
+  assert (a.legal_mask() == 63).all()
+  obs, reward, done, result = a.step(np.array([0, 5, 3]))
+  obs2, reward2, done2, _ = b.step(np.array([1, 1, 1]))
+  assert np.array_equal(obs, obs2) and np.array_equal(reward, reward2)  # frames do not depend on the actions
+  assert set(np.unique(reward)) <= {-1, 0, 1} and not done.any() and (result == -1).all()
+  _, _, done, _ = a.step(np.array([0, 0, 0]))
+  assert done.all() and (a.elapsed == 2).all()
+  assert a.reset([1]).shape == (1, 2, 8, 8) and a.elapsed.tolist() == [2, 0, 2]
+  with pytest.raises(ValueError):
+    a.step(np.array([0, 6, 0]))
