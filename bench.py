@@ -664,10 +664,14 @@ def bench_targets(torch, _lib, dev):
     Bb = 128 * 512
     sec, bps = _targets_case(torch, _lib, dev, rng, P, A2, K, T2, Bb, E2, u8, 4, 5, disc)
     gbs = Bb * bps / sec / 1e9
+    rows_kernel = T2 <= 64  # mz_build_targets picks the lane-per-position kernel for K + 1 <= 16, td_steps <= 64
     bulk[name] = {"rows_per_launch": Bb, "us_per_launch": sec * 1e6, "samples_per_s": Bb / sec,
                   "algorithmic_bytes_per_sample": bps,
-                  "roofline": {"kernel": "build_targets_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm,
-                               "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+                  "roofline": {"kernel": "build_targets_rows_kernel" if rows_kernel else "build_targets_kernel",
+                               "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                               # ncu dram read + write of one launch, profiles/r01s_summary.md (part of the
+                               # written lines is still dirty in L2 when the launch ends)
+                               "traffic": 103.4e6 if name == "C3_breakout_ram" else None,
                                "peak_source": peaks["source"]}}
   res["bulk"] = bulk
   return res

@@ -310,7 +310,7 @@ MZ_DEV void issue_mma2(uint32_t d2, uint32_t a_tm, uint32_t b_addr, bool first_c
     umma_ts<true>(d2, a_tm + ks * 8, bd + (uint64_t)((ks * 2 * LBO) >> 4), idesc);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) fc_recurrent_tc_kernel(TcParams p) {
+__global__ void __maxnreg__(152) fc_recurrent_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.trace && threadIdx.x == 0 && blockIdx.x < 64) {  // wall-clock entry time of every CTA (ns)

@@ -48,24 +48,39 @@ constexpr int kTgtFastK = 7;  // up to 8 unroll positions keep their sums in reg
 // * discounts[j], j < min(T, len - (step+i)); the sign flips where to_play differs from the position's
 // (replay_buffer.py:187-189).  Exact float32 products accumulated in binary64; returns position `lane`'s sum.
 template <int NP>
-MZ_DEV double nstep_sums(const float* s_rew, const int8_t* s_tp, const float* s_disc, int K, int T, int step,
-                         int len, int win, int lane) {
+MZ_DEV double nstep_sums(const float* s_rew, const int8_t* s_tp, const double* s_disc, int K, int T, int step,
+                         int len, int win, int lane, bool one_player) {
   double acc[NP];
   int tp_i[NP], n_i[NP];
+  // interior of the window: elements m with 0 <= m - i < n_i for EVERY position i <= K -- no range test there
+  int lo = K, hi = win;
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
     acc[i] = 0.0;
     const bool in = i <= K && step + i < len;
     n_i[i] = in ? min(T, len - step - i) : 0;
     tp_i[i] = in ? s_tp[i] : 0;
+    if (i <= K) hi = min(hi, i + n_i[i]);
   }
-  for (int m = lane; m < win; m += 32) {
-    const float r = s_rew[m];
-    const int tp = s_tp[m];
+  // the sign of a reward flips where to_play differs from the position's (replay_buffer.py:187-189); when the
+  // whole window belongs to one player (every single-player game) the interior needs no sign test either
+  if (!one_player || hi <= lo) lo = hi = 0;  // everything through the general loop below
+  for (int m = lo + lane; m < hi; m += 32) {
+    const double r = (double)s_rew[m];
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      const int j = m - i;
-      if (j >= 0 && j < n_i[i]) acc[i] += (double)(tp != tp_i[i] ? -r : r) * (double)s_disc[j];
+    for (int i = 0; i < NP; ++i)
+      if (i <= K) acc[i] = fma(r, s_disc[m - i], acc[i]);  // the product of two float32 values is exact
+  }
+  for (int part = 0; part < 2; ++part) {  // the edges [0, lo) and [hi, win): range and sign tests per element
+    const int m_end = part ? win : min(lo, win);
+    for (int m = (part ? hi : 0) + lane; m < m_end; m += 32) {
+      const float r = s_rew[m];
+      const int tp = s_tp[m];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const int j = m - i;
+        if (j >= 0 && j < n_i[i]) acc[i] += (double)(tp != tp_i[i] ? -r : r) * s_disc[j];
+      }
     }
   }
   double mine_acc = 0.0;
@@ -79,7 +94,6 @@ MZ_DEV double nstep_sums(const float* s_rew, const int8_t* s_tp, const float* s_
   }
   return mine_acc;
 }
-
 
 // One warp per sampled row, kTgtWarps rows per CTA.  Every global load of a row (observation, reward /
 // to_play window, bootstrap root values, child-visit rows) is issued before the first dependent use, so a
@@ -99,8 +113,8 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
   const int b = blockIdx.x * kTgtWarps + warp;
   const int K = c.num_unroll_steps, T = c.td_steps, A = w.num_actions, E = w.obs_elems;
   // the discount table f32(discount ** n) (replay_buffer.py:84) is shared by the CTA's rows
-  float* s_disc = reinterpret_cast<float*>(smem_raw);
-  for (int j = threadIdx.x; j < K + T; j += kTgtThreads) s_disc[j] = c.discounts[j];
+  double* s_disc = reinterpret_cast<double*>(smem_raw);  // widened once per CTA
+  for (int j = threadIdx.x; j < K + T; j += kTgtThreads) s_disc[j] = (double)c.discounts[j];
   const bool row_ok = b < c.batch;
   int64_t pos = 0;
   int step = 0, len = 0;
@@ -112,7 +126,7 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
   __syncthreads();
   if (!row_ok) return;  // warps are independent from here on
 
-  unsigned char* mine = smem_raw + ((size_t)(K + T) * sizeof(float) + 15) / 16 * 16 + (size_t)warp * warp_smem_bytes;
+  unsigned char* mine = smem_raw + ((size_t)(K + T) * sizeof(double) + 15) / 16 * 16 + (size_t)warp * warp_smem_bytes;
   float* s_rew = reinterpret_cast<float*>(mine);                       // [K+T] rewards from `step` on
   float* s_val = s_rew + (K + T);                                      // [K+1] value targets
   float* s_lastr = s_val + (K + 1);                                    // [K+1] reward targets
@@ -123,10 +137,15 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
   // ---- loads -------------------------------------------------------------------------------------
   // reward / to_play window [step, min(step + K + T, len))
   const int win = max(0, min(K + T, len - step));
+  int tp_min = 127, tp_max = -128;  // does the whole window belong to one player?
   for (int j = lane; j < win; j += 32) {
     s_rew[j] = w.rewards[pos + j];
-    s_tp[j] = w.to_play[pos + j];
+    const int tp = w.to_play[pos + j];
+    s_tp[j] = (int8_t)tp;
+    tp_min = min(tp_min, tp);
+    tp_max = max(tp_max, tp);
   }
+  const bool one_player = __reduce_min_sync(MZ_FULL, tp_min) >= __reduce_max_sync(MZ_FULL, tp_max);
   const float prev_reward = (step > 0 && step <= len) ? w.rewards[pos - 1] : 0.0f;
   // bootstrap of position `lane`: root_values[step + lane + T] where it exists (replay_buffer.py:180-183)
   double root = 0.0;
@@ -197,8 +216,8 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
 
   // ---- insert_target (replay_buffer.py:165-198) -----------------------------------------------------
   if (K <= kTgtFastK) {
-    const double mine_acc = K < 6 ? nstep_sums<6>(s_rew, s_tp, s_disc, K, T, step, len, win, lane)
-                                  : nstep_sums<kTgtFastK + 1>(s_rew, s_tp, s_disc, K, T, step, len, win, lane);
+    const double mine_acc = K < 6 ? nstep_sums<6>(s_rew, s_tp, s_disc, K, T, step, len, win, lane, one_player)
+                                  : nstep_sums<kTgtFastK + 1>(s_rew, s_tp, s_disc, K, T, step, len, win, lane, one_player);
     if (lane <= K) {
       const int ci = step + lane;
       float value = 0.0f;
@@ -223,7 +242,7 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
         for (int j = lane; j < n; j += 32) {
           float r = s_rew[i + j];
           if (s_tp[i + j] != tp) r = -r;
-          acc += (double)r * (double)s_disc[j];
+          acc += (double)r * s_disc[j];
         }
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) acc += shfl_xor_f64<32>(acc, m);
@@ -575,7 +594,7 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
   }
   // per warp: rewards [K+T] f32, values / rewards [K+1] f32 each, two-hot bins 2 x [K+1] x 16 B, to_play [K+T]
   const int warp_smem = (int)((sizeof(float) * (KT + 2 * K1) + 2 * sizeof(TgtBins) * K1 + KT + 15) / 16 * 16);
-  const size_t smem = (size_t)warp_smem * kTgtWarps + (sizeof(float) * KT + 15) / 16 * 16;  // + discount table
+  const size_t smem = (size_t)warp_smem * kTgtWarps + (sizeof(double) * KT + 15) / 16 * 16;  // + discount table
   if (smem > 200 * 1024) return MZ_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {

@@ -354,15 +354,8 @@ struct ImgLoad {
 // (mcts.py:106-112): returns the winning lane or -1 when no lane is a candidate.
 MZ_DEV int warp_argmax(double score, bool cand) {
   const unsigned long long key = cand ? sortable_key(score) : 0ull;
-  const unsigned hi = (unsigned)(key >> 32);
-  const unsigned hi_max = __reduce_max_sync(MZ_FULL, hi);
-  unsigned winners = __ballot_sync(MZ_FULL, cand && hi == hi_max);
-  if (__popc(winners) > 1) {  // warp-uniform and rare: the scores agree in sign, exponent and 20 mantissa bits
-    const unsigned lo = (unsigned)key;
-    const bool top = cand && hi == hi_max;
-    const unsigned lo_max = __reduce_max_sync(MZ_FULL, top ? lo : 0u);
-    winners = __ballot_sync(MZ_FULL, top && lo == lo_max);
-  }
+  const unsigned long long best_key = warp_max_key(key);
+  const unsigned winners = __ballot_sync(MZ_FULL, cand && key == best_key);
   return winners ? 31 - __clz(winners) : -1;
 }
 
@@ -484,36 +477,20 @@ MZ_DEV void expand_backup_w32(const mz_tree& t, uint8_t* img, uint8_t* gbl, int 
 
   // priors: p_a = exp(logit_a) / sum(p), the sum evaluated like CPython's builtin sum()
   // (every action is legal below the root, mcts.py:72, 97)
-  // Lanes >= A hold p = 0: adding 0.0 changes neither the running sum (f > 0) nor the compensation, so the
-  // loop runs in groups of four with the four shuffles issued ahead of the dependent additions.
   const double p = lane_ok ? mz_exp((double)logit) : 0.0;
   double f = shfl_f64<32>(p, 0), c = 0.0;
   if (t.prior_sum_mode == 0) {
 #pragma unroll 1
-    for (int a0 = 1; a0 < A; a0 += 4) {
-      double x[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) x[u] = shfl_f64<32>(p, (a0 + u) & 31);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) f = __dadd_rn(f, a0 + u < 32 ? x[u] : 0.0);
-    }
+    for (int a = 1; a < A; ++a) f = __dadd_rn(f, shfl_f64<32>(p, a));
   } else {  // Neumaier step, CPython >= 3.12 Python/bltinmodule.c
 #pragma unroll 1
-    for (int a0 = 1; a0 < A; a0 += 4) {
-      double x[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        x[u] = shfl_f64<32>(p, (a0 + u) & 31);
-        if (a0 + u >= 32) x[u] = 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const double s = __dadd_rn(f, x[u]);
-        const bool big = fabs(f) >= fabs(x[u]);
-        const double hi = big ? f : x[u], lo = big ? x[u] : f;
-        c = __dadd_rn(c, __dadd_rn(__dsub_rn(hi, s), lo));
-        f = s;
-      }
+    for (int a = 1; a < A; ++a) {
+      const double x = shfl_f64<32>(p, a);
+      const double s = __dadd_rn(f, x);
+      const bool big = fabs(f) >= fabs(x);
+      const double hi = big ? f : x, lo = big ? x : f;
+      c = __dadd_rn(c, __dadd_rn(__dsub_rn(hi, s), lo));
+      f = s;
     }
     if (c != 0.0 && isfinite(c)) f = __dadd_rn(f, c);
   }
@@ -556,25 +533,16 @@ MZ_DEV void expand_backup_w32(const mz_tree& t, uint8_t* img, uint8_t* gbl, int 
     }
     double myval = 0.0;
     unsigned mysign = 0u;
-    // groups of four path positions: the four reward shuffles are issued ahead of the dependent
-    // multiply-add chain (two float64 operations per position)
 #pragma unroll 1
-    for (int j = min(31, depth - base); j >= 0; j -= 4) {
-      unsigned rj[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) rj[u] = __shfl_sync(MZ_FULL, __float_as_uint(rw), max(j - u, 0));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (j - u >= 0) {  // warp-uniform
-          if (lane == j - u) {
-            myval = value;
-            mysign = signmask;
-          }
-          // value = (-reward if two_players and node.to_play == to_play else reward) + discount * value
-          value = __dadd_rn((double)__uint_as_float(rj[u] ^ signmask), __dmul_rn(disc, value));
-          signmask ^= twomask;
-        }
+    for (int j = min(31, depth - base); j >= 0; --j) {
+      const unsigned rj = __shfl_sync(MZ_FULL, __float_as_uint(rw), j);
+      if (lane == j) {
+        myval = value;
+        mysign = signmask;
       }
+      // value = (-reward if two_players and node.to_play == to_play else reward) + discount * value
+      value = __dadd_rn((double)__uint_as_float(rj ^ signmask), __dmul_rn(disc, value));
+      signmask ^= twomask;
     }
     if (has) {
       // value_sum += value if node.to_play == to_play else -value   (mysign set <=> same player
