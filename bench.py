@@ -669,9 +669,9 @@ def bench_targets(torch, _lib, dev):
                   "algorithmic_bytes_per_sample": bps,
                   "roofline": {"kernel": "build_targets_rows_kernel" if rows_kernel else "build_targets_kernel",
                                "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                               # ncu dram read + write of one launch, profiles/r01s_summary.md (part of the
+                               # ncu dram read + write of one launch, profiles/r01t_summary.md (part of the
                                # written lines is still dirty in L2 when the launch ends)
-                               "traffic": 103.4e6 if name == "C3_breakout_ram" else None,
+                               "traffic": 102.9e6 if name == "C3_breakout_ram" else None,
                                "peak_source": peaks["source"]}}
   res["bulk"] = bulk
   return res

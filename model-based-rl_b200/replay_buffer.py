@@ -111,12 +111,11 @@ class ReplayIndex(object):
     n = len(u01)
     dev = self.device
     d_u = torch.from_numpy(np.ascontiguousarray(u01, np.float64)).to(dev)
-    idx = torch.empty(n, dtype=torch.int64, device=dev)
-    pri = torch.empty(n, dtype=torch.float64, device=dev)
-    pos = torch.empty(n, dtype=torch.int64, device=dev)
-    cstart = torch.empty(n, dtype=torch.int64, device=dev)
-    clen = torch.empty(n, dtype=torch.int32, device=dev)
-    isw = torch.empty(n, dtype=torch.float64, device=dev) if with_weights else None
+    blob = torch.empty(6 * n, dtype=torch.int64, device=dev)  # one allocation for the six outputs
+    idx, pos, cstart = blob[0:n], blob[n:2 * n], blob[2 * n:3 * n]
+    pri = blob[3 * n:4 * n].view(torch.float64)
+    isw = blob[4 * n:5 * n].view(torch.float64) if with_weights else None
+    clen = blob[5 * n:6 * n].view(torch.int32)[:n]
     _lib.check(self.lib.mz_sumtree_sample(_lib.ptr(self.tree), self.max_capacity, n, _lib.ptr(d_u),
                                           _lib.ptr(self.slot_pos), _lib.ptr(self.slot_start),
                                           _lib.ptr(self.slot_len), self.ring.num_memories,
@@ -273,22 +272,28 @@ class PrioritizedReplay(object):
     dev = self.device
     vb = self.value_support[1] - self.value_support[0] + 1
     rb = self.reward_support[1] - self.reward_support[0] + 1
-    out = [torch.empty((B, self.obs_elems), dtype=torch.float32, device=dev),
-           torch.empty((B, K), dtype=torch.int32, device=dev),
-           torch.empty((B, K + 1), dtype=torch.float32, device=dev),
-           torch.empty((B, K + 1), dtype=torch.float32, device=dev),
-           torch.empty((B, K + 1, A), dtype=torch.float32, device=dev)]
+    # one allocation per batch, carved into the output tensors (all float32 / int32: 4-byte elements)
+    shapes = [(B, self.obs_elems), (B, K), (B, K + 1), (B, K + 1), (B, K + 1, A)]
     if fuse_supports:
-      out += [torch.empty((B, K + 1, vb), dtype=torch.float32, device=dev),
-              torch.empty((B, K + 1, rb), dtype=torch.float32, device=dev)]
-    win = _lib.Window(A, self.obs_elems, int(self._obs_dtype == torch.uint8), 0,
-                      self.w_obs.data_ptr(), self.w_actions.data_ptr(), self.w_rewards.data_ptr(),
-                      self.w_to_play.data_ptr(), self.w_root_values.data_ptr(),
-                      self.w_child_visits.data_ptr())
-    cfg = _lib.TargetCfg(B, K, self.td_steps, int(fuse_supports), self.value_support[0],
-                         self.value_support[1], self.reward_support[0], self.reward_support[1],
-                         int(self.no_target_transform), 0, float(self.discount**self.td_steps),
-                         self.d_discounts.data_ptr(), None, None)
+      shapes += [(B, K + 1, vb), (B, K + 1, rb)]
+    sizes = [(int(np.prod(sh)) + 3) // 4 * 4 for sh in shapes]  # every view starts 16-byte aligned
+    blob = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+    out, off = [], 0
+    for i, (sh, n) in enumerate(zip(shapes, sizes)):
+      v = blob[off:off + int(np.prod(sh))]
+      out.append((v.view(torch.int32) if i == 1 else v).view(sh))
+      off += n
+    if getattr(self, '_tgt_structs', None) is None or self._tgt_structs[0] != (self.w_obs.data_ptr(), fuse_supports):
+      win = _lib.Window(A, self.obs_elems, int(self._obs_dtype == torch.uint8), 0,
+                        self.w_obs.data_ptr(), self.w_actions.data_ptr(), self.w_rewards.data_ptr(),
+                        self.w_to_play.data_ptr(), self.w_root_values.data_ptr(),
+                        self.w_child_visits.data_ptr())
+      cfg = _lib.TargetCfg(B, K, self.td_steps, int(fuse_supports), self.value_support[0],
+                           self.value_support[1], self.reward_support[0], self.reward_support[1],
+                           int(self.no_target_transform), 0, float(self.discount**self.td_steps),
+                           self.d_discounts.data_ptr(), None, None)
+      self._tgt_structs = ((self.w_obs.data_ptr(), fuse_supports), win, cfg)
+    _, win, cfg = self._tgt_structs
     ptrs = [_lib.ptr(t) for t in out] + ([None, None] if not fuse_supports else [])
     _lib.check(self.lib.mz_build_targets(win, cfg, _lib.ptr(d_pos), _lib.ptr(d_cs), _lib.ptr(d_cl),
                                          _lib.ptr(d_pads), *ptrs, _lib.current_stream()),
