@@ -356,11 +356,11 @@ def run_b200(args):
     torch.cuda.synchronize()
     return sum(s.elapsed_time(e) for s, e in pairs)
 
-  for _ in range(args.warmup):
-    fs.run()
   clocks = ClockSampler(local)
   if rank == 0:
-    clocks.start()
+    clocks.start()  # sampled from the warm-up on: the GPU is under the same load there
+  for _ in range(args.warmup):
+    fs.run()
   barrier()
   ms_total = timed(fs.run, args.steps)
   barrier()

@@ -116,6 +116,7 @@ class ReplayIndex(object):
     pri = blob[3 * n:4 * n].view(torch.float64)
     isw = blob[4 * n:5 * n].view(torch.float64) if with_weights else None
     clen = blob[5 * n:6 * n].view(torch.int32)[:n]
+    self.last_blob = blob  # sample_batch() brings all six outputs to the host with one copy
     _lib.check(self.lib.mz_sumtree_sample(_lib.ptr(self.tree), self.max_capacity, n, _lib.ptr(d_u),
                                           _lib.ptr(self.slot_pos), _lib.ptr(self.slot_start),
                                           _lib.ptr(self.slot_len), self.ring.num_memories,
@@ -213,7 +214,9 @@ class PrioritizedReplay(object):
     self._step_beta()
     u01 = [random.random() for _ in range(B)]  # random.uniform(s1, s2) draws exactly one random()
     idx, pri, pos, cstart, clen, _ = self.index.sample(u01, self.beta, with_weights=False)
-    h_pos, h_cs, h_cl = pos.cpu().numpy(), cstart.cpu().numpy(), clen.cpu().numpy()
+    h = self.index.last_blob.cpu().numpy()  # one device-to-host copy: idx | pos | chunk start | priority | - | len
+    h_idx, h_pos, h_cs = h[0:B], h[B:2 * B], h[2 * B:3 * B]
+    priorities, h_cl = h[3 * B:4 * B].view(np.float64), h[5 * B:6 * B].view(np.int32)[:B]
     # padding actions are drawn only where the slice is short (replay_buffer.py:149-152)
     n_real = np.clip(h_cl - (h_pos - h_cs), 0, K)
     pads = np.zeros((B, K), np.int32)
@@ -221,14 +224,19 @@ class PrioritizedReplay(object):
       for j in range(K - int(n_real[b])):
         pads[b, j] = np.random.randint(A)
     out = self._targets(pos, cstart, clen, torch.from_numpy(pads).to(self.device), False)
-    obs, actions, t_rewards, t_values, t_policies = [t.cpu().numpy() for t in out]
+    hb = self._tgt_blob.cpu().numpy()  # one copy for the five outputs
+    host, off = [], 0
+    for i, (sh, n) in enumerate(self._tgt_layout):
+      v = hb[off:off + int(np.prod(sh))]
+      host.append((v.view(np.int32) if i == 1 else v).reshape(sh))
+      off += n
+    obs, actions, t_rewards, t_values, t_policies = host
     obs = obs.reshape((B,) + self.obs_space)
-    priorities = pri.cpu().numpy()
     sampling_probabilities = priorities / self.index.total_priority
     is_weights = np.power(self.index.num_memories * sampling_probabilities, -self.beta)
     is_weights /= is_weights.max()
     batch = (obs, actions.tolist(), (t_rewards, t_values, t_policies))
-    return batch, idx.cpu().numpy().tolist(), is_weights
+    return batch, h_idx.tolist(), is_weights
 
   def sample_batch_device(self, fuse_supports=True):
     """Same sampling with nothing leaving the GPU and no host synchronisation: returns
@@ -294,6 +302,7 @@ class PrioritizedReplay(object):
                            self.d_discounts.data_ptr(), None, None)
       self._tgt_structs = ((self.w_obs.data_ptr(), fuse_supports), win, cfg)
     _, win, cfg = self._tgt_structs
+    self._tgt_blob, self._tgt_layout = blob, list(zip(shapes, sizes))
     ptrs = [_lib.ptr(t) for t in out] + ([None, None] if not fuse_supports else [])
     _lib.check(self.lib.mz_build_targets(win, cfg, _lib.ptr(d_pos), _lib.ptr(d_cs), _lib.ptr(d_cl),
                                          _lib.ptr(d_pads), *ptrs, _lib.current_stream()),
