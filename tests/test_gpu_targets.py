@@ -244,3 +244,67 @@ def test_build_targets_ragged_shapes_match_oracle(shape, targets_kernel):
   cfgobj = Config(dict(value_support=[-15, 15], reward_support=[-15, 15], no_target_transform=False))
   assert torch.equal(out[5], cfgobj.value_phi(Config.scalar_transform(out[3])))
   assert torch.equal(out[6], cfgobj.reward_phi(Config.scalar_transform(out[2])))
+
+
+def test_bulk_launch_kernels_agree_and_match_oracle():
+  """65 536 rows in one launch (128 learner batches, the shape bench.py's `targets.bulk` times) over a 200 000
+  position window: the lane-per-position kernel and the warp-per-row kernel are independent implementations and
+  must agree everywhere (gathers, reward / policy targets and supports bit for bit, n-step values to 1e-6
+  relative -- they sum in different orders in float64); 300 random rows are checked against the oracle."""
+  import oracle
+  from model_based_rl_b200 import _lib
+  lib = _lib.load()
+  rng = np.random.default_rng(11)
+  P, A, K, T, B, E = 200_000, 4, 5, 10, 65_536, 128
+  lens = rng.integers(200, 800, size=P // 200)
+  lens = lens[np.cumsum(lens) <= P].astype(np.int32)
+  starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+  obs_np = rng.integers(0, 256, size=(P, E), dtype=np.uint8)
+  rewards = np.sign(rng.normal(size=P) * (rng.random(P) < 0.3)).astype(np.float32)
+  to_play = rng.choice([-1, 1], size=P).astype(np.int8)
+  root_values = rng.normal(0, 2, size=P)
+  cv = rng.random((P, A)).astype(np.float32)
+  cv /= cv.sum(1, keepdims=True)
+  actions = rng.integers(0, A, size=P, dtype=np.int32)
+  d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+  t_obs, t_act, t_rew, t_tp, t_rv, t_cv = d(obs_np), d(actions), d(rewards), d(to_play), d(root_values), d(cv)
+  disc = 0.997
+  discounts = d(np.array([disc**n for n in range(K + T)], np.float32))
+  win = _lib.Window(A, E, 1, 0, t_obs.data_ptr(), t_act.data_ptr(), t_rew.data_ptr(), t_tp.data_ptr(),
+                    t_rv.data_ptr(), t_cv.data_ptr())
+  tc = _lib.TargetCfg(B, K, T, 1, -15, 15, -15, 15, 0, 0, disc**T, discounts.data_ptr(), None, None)
+  ci = rng.integers(0, len(lens), size=B)
+  step = (rng.random(B) * lens[ci]).astype(np.int64)
+  step[:64] = lens[ci[:64]] - 1 - (np.arange(64) % 8)          # rows that run past the end of their chunk
+  pos, cs, cl = d(starts[ci] + step), d(starts[ci]), d(lens[ci])
+  pads = d(rng.integers(0, A, size=(B, K), dtype=np.int32))
+
+  def run(which):
+    lib.mz_debug_set_targets_kernel(which)
+    out = [torch.full((B, E), -7.0, device="cuda"), torch.full((B, K), -7, dtype=torch.int32, device="cuda"),
+           torch.full((B, K + 1), -7.0, device="cuda"), torch.full((B, K + 1), -7.0, device="cuda"),
+           torch.full((B, K + 1, A), -7.0, device="cuda"), torch.full((B, K + 1, 31), -7.0, device="cuda"),
+           torch.full((B, K + 1, 31), -7.0, device="cuda")]
+    try:
+      _lib.check(lib.mz_build_targets(win, tc, _lib.ptr(pos), _lib.ptr(cs), _lib.ptr(cl), _lib.ptr(pads),
+                                      *[_lib.ptr(o) for o in out], _lib.current_stream()), "mz_build_targets")
+      torch.cuda.synchronize()
+    finally:
+      lib.mz_debug_set_targets_kernel(0)
+    return out
+  rows, wide = run(0), run(1)
+  for i in (0, 1, 2, 4):
+    assert torch.equal(rows[i], wide[i]), i
+  rel = ((rows[3] - wide[3]).abs() / wide[3].abs().clamp(min=1.0)).max().item()
+  assert rel <= 1e-6, rel
+  same = rows[3] == wide[3]
+  assert torch.equal(rows[5][same], wide[5][same]) and torch.equal(rows[6], wide[6])
+  assert torch.allclose(rows[5].sum(-1), torch.ones(B, K + 1, device="cuda"), atol=1e-6)
+  assert torch.equal(rows[0], t_obs[pos].float())
+  tr, tv, tp = rows[2].cpu().numpy(), rows[3].cpu().numpy(), rows[4].cpu().numpy()
+  for b in list(range(64)) + rng.integers(0, B, size=236).tolist():
+    lo, n, s = int(starts[ci[b]]), int(lens[ci[b]]), int(step[b])
+    sl = slice(lo, lo + n)
+    wr, wv, wp = oracle.insert_target(rewards[sl], to_play[sl], root_values[sl], cv[sl], K, T, disc, s)
+    assert np.array_equal(tr[b], wr) and np.array_equal(tp[b], wp)
+    assert np.max(np.abs(tv[b] - wv) / np.maximum(np.abs(wv), 1.0)) <= 1e-5
