@@ -23,6 +23,7 @@
 // Reference semantics: networks.py:31-34, 122-174 (FCNetwork), config.py:27-33.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "mz_common.cuh"
 #include "mz_transforms.cuh"
@@ -784,6 +785,18 @@ long long* g_tc_trace = nullptr;
 int g_tc_trace_block = 0;
 int g_tc_split = 1;  // recurrent kernel: two-CTA clusters, heads split between the CTAs
 
+// weight-ring depth of the recurrent kernel; MZ_TC_STAGES=2|3|4 overrides it (diagnostics: a shallower ring leaves
+// shared memory for tree-step CTAs on the same SM)
+int recurrent_stages() {
+  static int st = 0;
+  if (st == 0) {
+    const char* e = getenv("MZ_TC_STAGES");
+    const int v = e ? atoi(e) : 0;
+    st = (v >= 2 && v <= MAX_STAGES) ? v : MAX_STAGES;
+  }
+  return st;
+}
+
 int k1_obs(int obs_dim) { return (obs_dim + 1 + 15) / 16 * 16; }  // observation + bias column
 
 size_t tc_smem_bytes(int k1, int stages) {
@@ -900,7 +913,7 @@ int mz_fc_recurrent_tc(const mz_fc_weights* w, const void* packed, const float* 
   p.logits = logits;
   p.trace = g_tc_trace;
   p.chunk0 = 0;
-  p.stages = MAX_STAGES;
+  p.stages = recurrent_stages();
   p.obs = nullptr;
   p.obs_dim = 0;
   p.split = g_tc_split;

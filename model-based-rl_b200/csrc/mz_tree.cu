@@ -7,6 +7,7 @@
 //
 // Reference: mcts.py:6-145, config.py:70-81, game.py:106-111 (JimOhman/model-based-rl).
 #include <math.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -974,6 +975,24 @@ int check_tree(const mz_tree* t) {
 
 int g_w32_max_games = 0x7fffffff;  // mz_tree_set_wide_step_max_games
 
+// Games (= warps) per CTA of the warp-per-game step kernel.  One game per CTA from 512 games per launch on: a CTA
+// gives its shared memory back as soon as ITS game's descent ends (a four-game CTA holds 4 images until the
+// deepest of them is done), 21 instead of 20 images fit an SM at the last simulation, and a one-game CTA fits
+// beside a network-kernel CTA (16 KB of shared memory left there).  Measured on one box, 30 timed moves, 4 / 2 / 1
+// games per CTA: C4 136.9-137.3 / 135.9 / 139.1-139.3 M expansions/s, 16 384 games 191.6-194.8 / 196.5 / 209.6 M,
+// C3 shape 188.5-189.6 / 186.5 / 205.9-208.7 M; 256-game launches (C2 shape) prefer four: 60.1-60.3 vs 57.6-59.0 M.
+// MZ_W32_GPB=1|2|4 overrides the choice (diagnostics).
+int w32_games_per_block(int num_games) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("MZ_W32_GPB");
+    const int v = e ? atoi(e) : 0;
+    forced = (v == 1 || v == 2 || v == 4) ? v : 0;
+  }
+  if (forced) return forced;
+  return num_games >= 512 ? 1 : kThreads / 32;
+}
+
 template <typename F>
 int dispatch_lpg(int A, F&& f) {
   if (A <= 4) return f(std::integral_constant<int, 4>());
@@ -1019,6 +1038,7 @@ int launch_step(const mz_tree* t, int sim, int live_nodes, int do_backup, int do
     const int nodes = live_nodes + (do_backup ? 1 : 0);
     const int stage_bytes = MZ_GAME_HEADER_BYTES + nodes * t->node_bytes;
     int gpb = kThreads / LPG;
+    if (LPG == 32) gpb = w32_games_per_block(t->num_games);
     while (gpb > 1 && (size_t)gpb * stage_bytes > 96 * 1024) gpb >>= 1;
     const bool staged = (size_t)gpb * stage_bytes <= kMaxStageSmem;
     if (LPG == 32) {  // one game per warp: the converged-warp kernel
