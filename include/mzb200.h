@@ -439,6 +439,11 @@ int mz_debug_div_check(uint64_t seed, int32_t blocks, int32_t per_thread, uint64
  * warp-per-game kernel measured faster at every batch size; 0 = always sub-warps.  Results are identical. */
 int mz_tree_set_wide_step_max_games(int32_t max_games);
 
+/* Games (= warps) per CTA of the warp-per-game step kernel: 1, 2 or 4; 0 (default) = by launch size (one game per
+ * CTA from 512 games per launch on: a CTA frees its staged image as soon as its own descent ends and fits beside a
+ * network-kernel CTA; four below that).  Results are identical; the parity tests run both. */
+int mz_tree_set_games_per_block(int32_t games);
+
 /* The per-simulation kernels (tree step, recurrent network) are launched as programmatic dependents
  * (their prologues overlap the predecessor's tail; griddepcontrol.wait before the first dependent
  * read).  enable = 0 switches back to plain stream-ordered launches.  Default: enabled. */

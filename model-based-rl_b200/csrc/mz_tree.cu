@@ -981,15 +981,15 @@ int g_w32_max_games = 0x7fffffff;  // mz_tree_set_wide_step_max_games
 // beside a network-kernel CTA (16 KB of shared memory left there).  Measured on one box, 30 timed moves, 4 / 2 / 1
 // games per CTA: C4 136.9-137.3 / 135.9 / 139.1-139.3 M expansions/s, 16 384 games 191.6-194.8 / 196.5 / 209.6 M,
 // C3 shape 188.5-189.6 / 186.5 / 205.9-208.7 M; 256-game launches (C2 shape) prefer four: 60.1-60.3 vs 57.6-59.0 M.
-// MZ_W32_GPB=1|2|4 overrides the choice (diagnostics).
+// mz_tree_set_games_per_block(1|2|4) (or MZ_W32_GPB in the environment) forces one value, 0 = by launch size.
+int g_w32_gpb = -1;
 int w32_games_per_block(int num_games) {
-  static int forced = -1;
-  if (forced < 0) {
+  if (g_w32_gpb < 0) {
     const char* e = getenv("MZ_W32_GPB");
     const int v = e ? atoi(e) : 0;
-    forced = (v == 1 || v == 2 || v == 4) ? v : 0;
+    g_w32_gpb = (v == 1 || v == 2 || v == 4) ? v : 0;
   }
-  if (forced) return forced;
+  if (g_w32_gpb) return g_w32_gpb;
   return num_games >= 512 ? 1 : kThreads / 32;
 }
 
@@ -1224,6 +1224,12 @@ int mz_debug_div_check(uint64_t seed, int32_t blocks, int32_t per_thread, uint64
 
 int mz_tree_set_wide_step_max_games(int32_t max_games) {
   g_w32_max_games = max_games;
+  return MZ_OK;
+}
+
+int mz_tree_set_games_per_block(int32_t games) {
+  if (games != 0 && games != 1 && games != 2 && games != 4) return MZ_ERR_BAD_ARG;
+  g_w32_gpb = games;
   return MZ_OK;
 }
 
