@@ -284,7 +284,7 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
 // with no idle lanes, and the outputs of the warp's rows -- contiguous in every output array -- leave as
 // warp-wide runs.  The two-hot supports are zero-filled with 8-byte stores and the two non-zero bins of every
 // position scattered afterwards (high bin first: the low bin wins on integers, config.py:64-67).
-// ~120 instructions per row against ~1000 for the warp-per-row kernel above.
+// 284 warp instructions per row (ncu, C3 shape, both warp roles) against ~1000 for the warp-per-row kernel above.
 constexpr int kRowsMaxPos = 16;
 constexpr int kRowsMaxTd = 64;
 constexpr int kRowsGroup = 4;  // rows whose loads are in flight together
