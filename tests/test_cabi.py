@@ -76,3 +76,11 @@ def test_bad_arguments_are_rejected_without_a_gpu():
   assert lib.mz_tree_select(C.byref(t), 0, None, None, None, None, None) == -1
   assert lib.mz_scalar_transform(-1, None, None, None) == -1
   assert lib.mz_select_action(0, 4, None, None, None, None, None, None) == -1
+  # host-side switches: accepted values only, and back to their defaults
+  assert lib.mz_tree_set_games_per_block(3) == -1 and lib.mz_tree_set_games_per_block(8) == -1
+  for games in (1, 2, 4, 0):
+    assert lib.mz_tree_set_games_per_block(games) == 0
+  assert lib.mz_debug_set_targets_kernel(1) == 0 and lib.mz_debug_set_targets_kernel(0) == 0
+  w, c = _lib.Window(), _lib.TargetCfg()
+  assert lib.mz_build_targets(C.byref(w), C.byref(c), None, None, None, None, None, None, None, None, None,
+                              None, None, None) == -1
