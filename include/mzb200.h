@@ -255,6 +255,65 @@ int mz_fc_initial_tc(const mz_fc_weights* w, const void* packed, const float* ta
                      float* logits, void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
+/* Whole move in one persistent kernel: MCTS.run (mcts.py:78-102) with FCNetwork (networks.py:31-34,  */
+/* 122-174) in the loop.  A thread-block cluster owns 128 games for all S simulations: root set-up */
+/* (Node.expand over the legal actions + add_exploration_noise, mcts.py:47-61), then per simulation  */
+/* descent (mcts.py:87-92, 104-124) -> recurrent_inference on tcgen05 tensor cores -> expand +     */
+/* backpropagate (mcts.py:47-55, 126-143), handed from phase to phase through mbarriers in          */
+/* (distributed) shared memory, and the root statistics of game.py:106-111 at the end.  Same       */
+/* arithmetic as mz_tree_step + mz_fc_recurrent_tc (bit-identical results); the tree uses its own    */
+/* layout (node record = node statistics + per-action {child id, child visits, prior, child q}, so  */
+/* a level of the descent is one memory round trip) and the hidden pool is bf16 [G][S+1][64].       */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct mz_fc_search_args {
+  const mz_fc_weights* weights;  /* dims, supports (the float32 pointers are not read) */
+  const void* packed;            /* mz_fc_tc_pack image */
+  const float* tail;
+  int32_t num_games;             /* G */
+  int32_t num_simulations;       /* S <= 253   config.num_simulations mcts.py:66 */
+  int32_t two_players;           /*            config.two_players     mcts.py:73 */
+  int32_t prior_sum_mode;        /* as in mz_tree */
+  int32_t node_bytes;            /* mz_fc_search_node_bytes(A) */
+  int32_t reserved;
+  int64_t game_bytes;            /* >= mz_fc_search_game_bytes(S, A) */
+  double discount, init_value_score, min_bound, max_bound;  /* as in mz_tree */
+  double noise_frac;             /* config.root_exploration_fraction (used when noise != NULL) */
+  uint8_t* games;                /* [G] game blocks (this kernel's layout) */
+  const double* pb_c_table;      /* [(S+1)*(S+1)] as in mz_tree */
+  void* pool;                    /* [G][S+1][64] bf16 hidden states (Node.hidden_state) */
+  const float* root_logits;      /* [G][A]   initial_inference().policy_logits */
+  const uint32_t* legal_mask;    /* [G] or NULL */
+  const double* noise;           /* [G][A] or NULL */
+  const int8_t* root_to_play;    /* [G] or NULL (kept for the caller; the arithmetic is relative) */
+  const float* root_hidden;      /* [G][50] initial_inference().hidden_state */
+  int32_t* visits;               /* [G][A] */
+  double* child_visits;          /* [G][A]   game.py:107-110 */
+  double* root_value;            /* [G]      root.value() */
+  double* minmax;                /* [G][2] */
+  int32_t* trace_parent;         /* [S][G] or NULL: leaf parent / action / depth of every simulation */
+  int32_t* trace_action;
+  int32_t* trace_depth;
+  float* rec_value;              /* [S][G] or NULL: what the network returned (parity replays) */
+  float* rec_reward;             /* [S][G] */
+  float* rec_logits;             /* [S][G][A] */
+  int64_t* timeline;             /* [S][16] clock64 stamps of tile 0 or NULL (diagnostics) */
+  int32_t* error_flag;           /* set before the kernel traps on a protocol time-out, or NULL */
+} mz_fc_search_args;
+
+int32_t mz_fc_search_node_bytes(int32_t num_actions);
+int64_t mz_fc_search_game_bytes(int32_t num_simulations, int32_t num_actions);
+int32_t mz_fc_search_pool_row(void);                         /* bf16 elements per pool row (64) */
+int mz_fc_search_supported(int32_t num_simulations, int32_t num_actions); /* 1: shapes fit the kernel */
+int mz_fc_search(const mz_fc_search_args* a, void* stream);
+/* one game's tree as the arrays of mz_tree_export (+ the cached child q [S+1][A]) */
+int mz_fc_search_export(const mz_fc_search_args* a, int32_t game, double* prior, int32_t* child,
+                        double* vsum, int32_t* visit, float* reward, double* q, void* stream);
+/* cluster size of mz_fc_search: 2 (rank 0 = reward + value heads, rank 1 = transition + policy, weights
+ * streamed per simulation), 4 (one head per CTA, weights resident in shared memory), 0 = default
+ * (MZ_FS_CLUSTER in the environment, else 2). */
+int mz_fc_search_set_cluster(int32_t cluster);
+
+/* ------------------------------------------------------------------------------------------- */
 /* Scalar transforms and supports (config.py:27-68), float32 in torch's op order.                */
 /* ------------------------------------------------------------------------------------------- */
 /* Config.scalar_transform config.py:51-54, elementwise h(x). */
@@ -277,7 +336,9 @@ typedef struct mz_window {
   int32_t num_actions;      /* A */
   int32_t obs_elems;        /* elements per observation */
   int32_t obs_is_u8;        /* 1: obs stored as uint8, 0: float32 */
-  int32_t reserved;
+  int32_t clip_rewards;     /* 1: every reward is read as np.sign(reward) -- ClipRewardEnv.reward,
+                               wrappers.py:236-238 (the Breakout configuration, README.md:56): the window keeps
+                               the raw environment rewards and the target kernel clips them on the fly */
   const void* obs;          /* [P][obs_elems] u8 or f32   history.observations */
   const int32_t* actions;   /* [P]                        history.actions */
   const float* rewards;     /* [P] f32(history.rewards): both uses (np.array(.., float32) at

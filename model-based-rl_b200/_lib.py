@@ -45,10 +45,26 @@ class FcWeights(C.Structure):
              [(n, C.c_void_p) for n in _names]
 
 
+class FcSearchArgs(C.Structure):
+  """struct mz_fc_search_args"""
+  _fields_ = [("weights", C.POINTER(FcWeights)), ("packed", C.c_void_p), ("tail", C.c_void_p),
+              ("num_games", C.c_int32), ("num_simulations", C.c_int32), ("two_players", C.c_int32),
+              ("prior_sum_mode", C.c_int32), ("node_bytes", C.c_int32), ("reserved", C.c_int32),
+              ("game_bytes", C.c_int64), ("discount", C.c_double), ("init_value_score", C.c_double),
+              ("min_bound", C.c_double), ("max_bound", C.c_double), ("noise_frac", C.c_double),
+              ("games", C.c_void_p), ("pb_c_table", C.c_void_p), ("pool", C.c_void_p),
+              ("root_logits", C.c_void_p), ("legal_mask", C.c_void_p), ("noise", C.c_void_p),
+              ("root_to_play", C.c_void_p), ("root_hidden", C.c_void_p), ("visits", C.c_void_p),
+              ("child_visits", C.c_void_p), ("root_value", C.c_void_p), ("minmax", C.c_void_p),
+              ("trace_parent", C.c_void_p), ("trace_action", C.c_void_p), ("trace_depth", C.c_void_p),
+              ("rec_value", C.c_void_p), ("rec_reward", C.c_void_p), ("rec_logits", C.c_void_p),
+              ("timeline", C.c_void_p), ("error_flag", C.c_void_p)]
+
+
 class Window(C.Structure):
   """struct mz_window"""
   _fields_ = [("num_actions", C.c_int32), ("obs_elems", C.c_int32), ("obs_is_u8", C.c_int32),
-              ("reserved", C.c_int32), ("obs", C.c_void_p), ("actions", C.c_void_p),
+              ("clip_rewards", C.c_int32), ("obs", C.c_void_p), ("actions", C.c_void_p),
               ("rewards", C.c_void_p), ("to_play", C.c_void_p), ("root_values", C.c_void_p),
               ("child_visits", C.c_void_p)]
 
@@ -101,6 +117,13 @@ _SIGNATURES = {
     "mz_fc_tc_initial_packed_bytes": (C.c_int64, [C.c_int32]),
     "mz_fc_tc_pack_initial": (C.c_int, [C.POINTER(FcWeights), _V, _V, _V]),
     "mz_fc_initial_tc": (C.c_int, [C.POINTER(FcWeights), _V, _V, C.c_int32, _V, _V, C.c_int64, _V, _V, _V]),
+    "mz_fc_search_node_bytes": (C.c_int32, [C.c_int32]),
+    "mz_fc_search_game_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "mz_fc_search_pool_row": (C.c_int32, []),
+    "mz_fc_search_supported": (C.c_int, [C.c_int32, C.c_int32]),
+    "mz_fc_search": (C.c_int, [C.POINTER(FcSearchArgs), _V]),
+    "mz_fc_search_export": (C.c_int, [C.POINTER(FcSearchArgs), C.c_int32, _V, _V, _V, _V, _V, _V, _V]),
+    "mz_fc_search_set_cluster": (C.c_int, [C.c_int32]),
     "mz_scalar_transform": (C.c_int, [C.c_int64, _V, _V, _V]),
     "mz_scalar_to_support": (C.c_int, [C.c_int64, _V, C.c_int32, C.c_int32, C.c_int32, _V, _V]),
     "mz_support_to_scalar": (C.c_int, [C.c_int64, _V, C.c_int32, C.c_int32, C.c_int32, _V, _V]),

@@ -42,6 +42,13 @@ MZ_DEV void write_supports(float* __restrict__ dst, const TgtBins* __restrict__ 
   }
 }
 
+// ClipRewardEnv.reward (wrappers.py:236-238): np.sign at the point the replay reads a stored reward
+// (mz_window.clip_rewards); zeros of either sign give +0.0 like numpy, NaN stays NaN
+MZ_DEV float tgt_reward(float r, int clip) {
+  if (!clip) return r;
+  return r > 0.0f ? 1.0f : (r < 0.0f ? -1.0f : (r == 0.0f ? 0.0f : r));
+}
+
 constexpr int kTgtFastK = 7;  // up to 8 unroll positions keep their sums in registers
 
 // n-step sums of NP unroll positions in one pass over the staged window: acc[i] = sum_j (+-)rewards[step+i+j]
@@ -139,14 +146,14 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
   const int win = max(0, min(K + T, len - step));
   int tp_min = 127, tp_max = -128;  // does the whole window belong to one player?
   for (int j = lane; j < win; j += 32) {
-    s_rew[j] = w.rewards[pos + j];
+    s_rew[j] = tgt_reward(w.rewards[pos + j], w.clip_rewards);
     const int tp = w.to_play[pos + j];
     s_tp[j] = (int8_t)tp;
     tp_min = min(tp_min, tp);
     tp_max = max(tp_max, tp);
   }
   const bool one_player = __reduce_min_sync(MZ_FULL, tp_min) >= __reduce_max_sync(MZ_FULL, tp_max);
-  const float prev_reward = (step > 0 && step <= len) ? w.rewards[pos - 1] : 0.0f;
+  const float prev_reward = (step > 0 && step <= len) ? tgt_reward(w.rewards[pos - 1], w.clip_rewards) : 0.0f;
   // bootstrap of position `lane`: root_values[step + lane + T] where it exists (replay_buffer.py:180-183)
   double root = 0.0;
   if (lane <= K && step + lane + T < len) root = w.root_values[pos + lane + T];
@@ -438,7 +445,7 @@ build_targets_rows_kernel(mz_window w, mz_target_cfg c, const int64_t* __restric
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int j = min(j0 + u, n - 1);
-          x[u] = __ldg(rw + j);
+          x[u] = tgt_reward(__ldg(rw + j), w.clip_rewards);
           t[u] = __ldg(tp + j);
         }
 #pragma unroll
@@ -450,7 +457,7 @@ build_targets_rows_kernel(mz_window w, mz_target_cfg c, const int64_t* __restric
       const double boot = (ci + T < len) ? __dmul_rn(root, c.disc_pow_td) : 0.0;
       value = __fadd_rn((float)boot, (float)acc);  // numpy 2: python float + np.float32 -> float32
     }
-    if (ci > 0 && ci <= len) last_reward = w.rewards[pos + i - 1];
+    if (ci > 0 && ci <= len) last_reward = tgt_reward(w.rewards[pos + i - 1], w.clip_rewards);
     t_values[(size_t)b * NP + i] = value;
     t_rewards[(size_t)b * NP + i] = last_reward;
   }

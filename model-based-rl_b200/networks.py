@@ -8,6 +8,7 @@ Training (backward, train-mode support logits) stays with the reference's torch 
 move between the two through the state dict.
 """
 import ctypes as C
+import os
 from collections import OrderedDict, namedtuple
 
 import numpy as np
@@ -66,13 +67,16 @@ class FCNetwork(object):
 
   # -- weights -----------------------------------------------------------------------------------
   def load_weights(self, weights):
-    """Accepts the reference's state dict (networks.py:176-177)."""
+    """Accepts the reference's state dict (networks.py:176-177).
+
+    The network holds a SNAPSHOT (the reference copies through `.cpu()` state dicts, networks.py:36-40):
+    every tensor is copied into storage allocated on the first call, so the device pointers inside
+    `self.weights`, the packed tensor-core images and anything that captured them (the search engines'
+    launch plans and CUDA graphs) stay valid across weight hand-offs (Learner.send_weights)."""
     missing = [k for k in _KEYS if k not in weights]
     if missing:
       raise KeyError("state dict is missing %s" % missing)
-    self._state = {k: torch.as_tensor(weights[k]).detach().to(self.device, torch.float32).contiguous()
-                   for k in _KEYS}
-    s = self._state
+    new = {k: torch.as_tensor(weights[k]).detach().to(self.device, torch.float32) for k in _KEYS}
     shapes = {
         'representation_head.fc1.weight': (512, self.input_dim),
         'transition_head.fc1.weight': (512, HIDDEN + self.action_space),
@@ -83,40 +87,51 @@ class FCNetwork(object):
         'value_head.value.weight': (self.value_bins, 512),
         'policy_head.policy.weight': (self.action_space, 512), 'LN.weight': (HIDDEN,)}
     for k, shp in shapes.items():
-      if tuple(s[k].shape) != shp:
-        raise ValueError("%s has shape %s, expected %s" % (k, tuple(s[k].shape), shp))
-    self._packed = {}
-    fields = {}
-    for k, (name, transposed) in _KEYS.items():
-      t = s[k].t().contiguous() if transposed else s[k]
-      self._packed[name] = t
-      fields[name] = t.data_ptr()
-    self.weights = _lib.FcWeights(self.input_dim, self.action_space, self.value_bins,
-                                  self.reward_bins, self.value_min, self.reward_min,
-                                  int(self.no_target_transform), 0,
-                                  *[fields[n] for n in _lib.FcWeights._names])
-    self._tc_packed = self._tc_tail = None
-    if self.precision == 'bf16':
-      if self.action_space > 32 or self.value_bins > 32 or self.reward_bins > 32:
-        raise NotImplementedError("the tensor-core kernel supports A <= 32 and supports <= 32 bins; "
-                                  "use precision='f32'")
-      nbytes = int(self.lib.mz_fc_tc_packed_bytes(self.action_space))
-      self._tc_packed = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-      self._tc_tail = torch.zeros(int(self.lib.mz_fc_tc_tail_floats()), dtype=torch.float32,
-                                  device=self.device)
-      _lib.check(self.lib.mz_fc_tc_pack(self.weights, _lib.ptr(self._tc_packed),
-                                        _lib.ptr(self._tc_tail), _lib.current_stream()),
-                 "mz_fc_tc_pack")
-      # initial_inference image (representation + prediction heads); observations too wide for
-      # the kernel's shared-memory budget stay on the float32 kernel
+      if tuple(new[k].shape) != shp:
+        raise ValueError("%s has shape %s, expected %s" % (k, tuple(new[k].shape), shp))
+    if self._state is None:
+      self._state = {k: v.clone().contiguous() for k, v in new.items()}
+      self._packed = {}
+      fields = {}
+      for k, (name, transposed) in _KEYS.items():
+        t = self._state[k].t().contiguous() if transposed else self._state[k]
+        self._packed[name] = t
+        fields[name] = t.data_ptr()
+      self.weights = _lib.FcWeights(self.input_dim, self.action_space, self.value_bins,
+                                    self.reward_bins, self.value_min, self.reward_min,
+                                    int(self.no_target_transform), 0,
+                                    *[fields[n] for n in _lib.FcWeights._names])
+      self._tc_packed = self._tc_tail = None
       self._tc_init_packed = self._tc_init_tail = None
-      nbytes = int(self.lib.mz_fc_tc_initial_packed_bytes(self.input_dim))
-      if nbytes > 0:
-        self._tc_init_packed = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-        self._tc_init_tail = torch.zeros_like(self._tc_tail)
-        _lib.check(self.lib.mz_fc_tc_pack_initial(self.weights, _lib.ptr(self._tc_init_packed),
-                                                  _lib.ptr(self._tc_init_tail), _lib.current_stream()),
-                   "mz_fc_tc_pack_initial")
+      if self.precision == 'bf16':
+        if self.action_space > 32 or self.value_bins > 32 or self.reward_bins > 32:
+          raise NotImplementedError("the tensor-core kernel supports A <= 32 and supports <= 32 bins; "
+                                    "use precision='f32'")
+        nbytes = int(self.lib.mz_fc_tc_packed_bytes(self.action_space))
+        self._tc_packed = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self._tc_tail = torch.zeros(int(self.lib.mz_fc_tc_tail_floats()), dtype=torch.float32,
+                                    device=self.device)
+        # initial_inference image (representation + prediction heads); observations too wide for
+        # the kernel's shared-memory budget stay on the float32 kernel
+        nbytes = int(self.lib.mz_fc_tc_initial_packed_bytes(self.input_dim))
+        if nbytes > 0:
+          self._tc_init_packed = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+          self._tc_init_tail = torch.zeros_like(self._tc_tail)
+    else:
+      for k, (name, transposed) in _KEYS.items():
+        self._state[k].copy_(new[k])
+        if transposed:
+          self._packed[name].copy_(self._state[k].t())
+    self.weights_version = getattr(self, 'weights_version', 0) + 1
+    if self.precision == 'bf16':
+      with torch.cuda.device(self.device):
+        _lib.check(self.lib.mz_fc_tc_pack(self.weights, _lib.ptr(self._tc_packed),
+                                          _lib.ptr(self._tc_tail), _lib.current_stream()),
+                   "mz_fc_tc_pack")
+        if self._tc_init_packed is not None:
+          _lib.check(self.lib.mz_fc_tc_pack_initial(self.weights, _lib.ptr(self._tc_init_packed),
+                                                    _lib.ptr(self._tc_init_tail), _lib.current_stream()),
+                     "mz_fc_tc_pack_initial")
 
   load_state_dict = load_weights
 
@@ -263,6 +278,94 @@ class _Lane(object):
     return len(plan)
 
 
+class _FusedEngine(object):
+  """The whole move in one persistent kernel (`mz_fc_search`): root set-up, S x {descent, network,
+  expand + backup} and the root statistics for all games, one launch.  Owns the tree blocks (the fused
+  kernel's layout), the bf16 hidden pool and the argument struct; inputs / outputs are the parent's
+  whole-batch staging tensors."""
+
+  def __init__(self, config, fcnet, parent):
+    from .mcts import pb_c_table, default_prior_sum_mode
+    import math
+    self.net, self.lib = fcnet, fcnet.lib
+    G, S, A, dev = parent.G, parent.S, parent.A, fcnet.device
+    self.G, self.S, self.A = G, S, A
+    self.node_bytes = int(self.lib.mz_fc_search_node_bytes(A))
+    self.game_bytes = int(self.lib.mz_fc_search_game_bytes(S, A))
+    self.games = torch.zeros(G * self.game_bytes, dtype=torch.uint8, device=dev)
+    self.pool = torch.zeros((G, S + 1, int(self.lib.mz_fc_search_pool_row())), dtype=torch.bfloat16, device=dev)
+    self.pb_c = torch.from_numpy(pb_c_table(S, config.pb_c_base, config.pb_c_init)).to(dev)
+    self.root_hidden = torch.zeros((G, HIDDEN), dtype=torch.float32, device=dev)
+    self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    self.trace = None
+    self.record = None
+    self.timeline = None
+    kb = list(config.known_bounds)
+    self.args = _lib.FcSearchArgs()
+    a = self.args
+    a.num_games, a.num_simulations, a.two_players = G, S, int(bool(config.two_players))
+    a.prior_sum_mode = default_prior_sum_mode()
+    a.node_bytes, a.game_bytes = self.node_bytes, self.game_bytes
+    a.discount, a.init_value_score = float(config.discount), float(config.init_value_score)
+    a.min_bound = math.inf if kb[0] is None else float(kb[0])
+    a.max_bound = -math.inf if kb[1] is None else float(kb[1])
+    a.games, a.pb_c_table, a.pool = self.games.data_ptr(), self.pb_c.data_ptr(), self.pool.data_ptr()
+    a.root_logits, a.root_hidden = parent.root_logits.data_ptr(), self.root_hidden.data_ptr()
+    a.legal_mask, a.root_to_play = parent.legal.data_ptr(), parent.to_play.data_ptr()
+    a.visits, a.child_visits = parent.visits.data_ptr(), parent.child_visits.data_ptr()
+    a.root_value, a.minmax = parent.root_value.data_ptr(), parent.minmax.data_ptr()
+    a.error_flag = self.error_flag.data_ptr()
+    self._bind_weights()
+
+  def _bind_weights(self):
+    net, a = self.net, self.args
+    a.weights = C.pointer(net.weights)
+    a.packed, a.tail = net._tc_packed.data_ptr(), net._tc_tail.data_ptr()
+
+  def enable_trace(self):
+    self.trace = tuple(torch.zeros((self.S, self.G), dtype=torch.int32, device=self.net.device) for _ in range(3))
+    a = self.args
+    a.trace_parent, a.trace_action, a.trace_depth = (t.data_ptr() for t in self.trace)
+
+  def enable_record(self):
+    dev = self.net.device
+    self.record = (torch.zeros((self.S, self.G), dtype=torch.float32, device=dev),
+                   torch.zeros((self.S, self.G), dtype=torch.float32, device=dev),
+                   torch.zeros((self.S, self.G, self.A), dtype=torch.float32, device=dev))
+    a = self.args
+    a.rec_value, a.rec_reward, a.rec_logits = (t.data_ptr() for t in self.record)
+
+  def enable_timeline(self):
+    """clock64 stamps of tile 0's phases, [S, 16] int64 (diagnostics; see csrc/mz_fcsearch.cu FS_STAMP)."""
+    self.timeline = torch.zeros((self.S, 16), dtype=torch.int64, device=self.net.device)
+    self.args.timeline = self.timeline.data_ptr()
+
+  def export_game(self, game):
+    """Dense copy of one game's tree in the layout of BatchedMCTS.export_game (+ the cached child q)."""
+    S, A, dev = self.S, self.A, self.net.device
+    prior = torch.zeros((S + 1, A), dtype=torch.float64, device=dev)
+    q = torch.zeros((S + 1, A), dtype=torch.float64, device=dev)
+    child = torch.zeros((S + 1, A), dtype=torch.int32, device=dev)
+    vsum = torch.zeros(S + 1, dtype=torch.float64, device=dev)
+    visit = torch.zeros(S + 1, dtype=torch.int32, device=dev)
+    reward = torch.zeros(S + 1, dtype=torch.float32, device=dev)
+    _lib.check(self.lib.mz_fc_search_export(self.args, int(game), _lib.ptr(prior), _lib.ptr(child), _lib.ptr(vsum),
+                                            _lib.ptr(visit), _lib.ptr(reward), _lib.ptr(q), _lib.current_stream()),
+               "mz_fc_search_export")
+    return dict(prior=prior.cpu().numpy(), child=child.cpu().numpy(), vsum=vsum.cpu().numpy(),
+                visit=visit.cpu().numpy(), reward=reward.cpu().numpy(), q=q.cpu().numpy())
+
+  def plan(self, parent, use_noise, noise_frac, st):
+    net, lib, P = self.net, self.lib, _lib.ptr
+    a = self.args
+    a.noise = parent.noise.data_ptr() if use_noise else None
+    a.noise_frac = float(noise_frac)
+    return [net.initial_call(self.G, parent.obs, self.root_hidden, HIDDEN, parent.init_value, parent.root_logits, st),
+            (lib.mz_fc_search, (C.byref(a), st)),
+            (lib.mz_select_action, (self.G, self.A, P(parent.visits), P(parent.legal), P(parent.temperature),
+                                    P(parent.uniforms), P(parent.actions), st))]
+
+
 class FCSearch(object):
   """The per-move body of Actor.play_game (actors.py:131-153) for G games with FCNetwork.
 
@@ -273,7 +376,11 @@ class FCSearch(object):
   CUDA graph, and inputs / outputs are staged through pinned host buffers for the end-to-end
   (host buffers in, host buffers out) call."""
 
-  def __init__(self, config, fcnet, num_games, noise_frac=None, use_graph=True, num_streams=1):
+  def __init__(self, config, fcnet, num_games, noise_frac=None, use_graph=True, num_streams=1, fused=None):
+    """fused: True = the whole move in one persistent kernel (`mz_fc_search`, csrc/mz_fcsearch.cu), False =
+    one tree launch + one network launch per simulation on `num_streams` slices, None = fused whenever the
+    network runs in bf16 and the shape fits the kernel AND MZ_FUSED=1 is set in the environment.
+    Both give bit-identical searches (tests/test_gpu_fcnet.py)."""
     self.net = fcnet
     G, A, dev = int(num_games), int(config.action_space), fcnet.device
     self.G, self.A, self.S = G, A, int(config.num_simulations)
@@ -300,6 +407,18 @@ class FCSearch(object):
     self.root_logits = torch.zeros((G, A), dtype=torch.float32, device=dev)
     self.visits = torch.zeros((G, A), dtype=torch.int32, device=dev)
     self.minmax = torch.zeros((G, 2), dtype=torch.float64, device=dev)
+    can_fuse = (fcnet.precision == 'bf16' and fcnet.weights is not None and
+                int(fcnet.lib.mz_fc_search_supported(self.S, A)) == 1)
+    if fused is None:
+      fused = can_fuse and os.environ.get("MZ_FUSED", "0") == "1"
+    elif fused and not can_fuse:
+      raise ValueError("the fused search kernel needs a bf16 FCNetwork with loaded weights, A <= 32 and a "
+                       "tree that fits its shared-memory plan")
+    self.fused = _FusedEngine(config, fcnet, self) if fused else None
+    self.lanes = []
+    self.eng = None
+    if self.fused is not None:
+      return
     ns = max(1, min(int(num_streams), G))
     bounds = [(G * i) // ns for i in range(ns + 1)]
     self.lanes = []
@@ -313,6 +432,12 @@ class FCSearch(object):
     """Keep every simulation's network outputs (and the engines' parent/action/depth traces) so
     that a checker can replay the search with identical network outputs."""
     dev = self.net.device
+    if self.fused is not None:
+      self.fused.enable_record()
+      self.fused.enable_trace()
+      self.graph = None
+      self._fused_plan_key = None
+      return
     for lane in self.lanes:
       g = lane.hi - lane.lo
       lane.record = (torch.zeros((self.S, g), dtype=torch.float32, device=dev),
@@ -323,17 +448,33 @@ class FCSearch(object):
 
   @property
   def record(self):
+    if self.fused is not None:
+      return self.fused.record
     if self.lanes[0].record is None:
       return None
     return tuple(torch.cat([lane.record[i] for lane in self.lanes], dim=1) for i in range(3))
 
   @property
   def trace(self):
+    if self.fused is not None:
+      return self.fused.trace
     return tuple(torch.cat([lane.eng.trace[i] for lane in self.lanes], dim=1) for i in range(3))
 
   # -- launch sequence -----------------------------------------------------------------------------
   def _enqueue(self):
     """All launches of one move; lanes fork from / join back into the current stream."""
+    if self.fused is not None:
+      stream_ptr = torch.cuda.current_stream().cuda_stream
+      key = (bool(self.use_noise), float(self.noise_frac), stream_ptr)
+      if getattr(self, '_fused_plan_key', None) != key:
+        self._fused_plan = self.fused.plan(self, self.use_noise, self.noise_frac, C.c_void_p(stream_ptr))
+        self._fused_plan_key = key
+      for fn, args in self._fused_plan:
+        rc = fn(*args)
+        if rc:
+          _lib.check(rc, fn.__name__)
+      self.launches_per_move = len(self._fused_plan)
+      return
     if len(self.lanes) == 1:
       self.launches_per_move = self.lanes[0].enqueue(self.use_noise, self.noise_frac)
       return

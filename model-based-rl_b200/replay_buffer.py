@@ -149,6 +149,10 @@ class PrioritizedReplay(object):
     self.value_support = tuple(getattr(config, 'value_support', (-15, 15)))
     self.reward_support = tuple(getattr(config, 'reward_support', (-15, 15)))
     self.no_target_transform = bool(getattr(config, 'no_target_transform', False))
+    # config.clip_rewards (config.py:111): the reference clips in an env wrapper (ClipRewardEnv.reward =
+    # np.sign, wrappers.py:236-238); here the window keeps what the environment returned and the target
+    # kernel reads every reward through sign() -- same targets, and the raw rewards stay available
+    self.clip_rewards = bool(getattr(config, 'clip_rewards', False))
 
     capacity = int(config.window_size)
     step = capacity if getattr(config, 'window_step', None) is None else int(config.window_step)
@@ -292,7 +296,7 @@ class PrioritizedReplay(object):
       out.append((v.view(torch.int32) if i == 1 else v).view(sh))
       off += n
     if getattr(self, '_tgt_structs', None) is None or self._tgt_structs[0] != (self.w_obs.data_ptr(), fuse_supports):
-      win = _lib.Window(A, self.obs_elems, int(self._obs_dtype == torch.uint8), 0,
+      win = _lib.Window(A, self.obs_elems, int(self._obs_dtype == torch.uint8), int(self.clip_rewards),
                         self.w_obs.data_ptr(), self.w_actions.data_ptr(), self.w_rewards.data_ptr(),
                         self.w_to_play.data_ptr(), self.w_root_values.data_ptr(),
                         self.w_child_visits.data_ptr())

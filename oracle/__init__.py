@@ -151,6 +151,12 @@ def child_visits(visits, child=None):
   return out
 
 
+def clip_reward(reward):
+  """ClipRewardEnv.reward (wrappers.py:236-238): np.sign of what the environment returned, applied per
+  step before the reward enters the history (Breakout configuration, README.md:56)."""
+  return np.sign(reward)
+
+
 def insert_target(rewards, to_play, root_values, child_visits_, K, T, discount, step):
   """One sampled position -> (t_rewards[K+1], t_values[K+1], t_policies[K+1, A])."""
   rewards = np.ascontiguousarray(rewards, dtype=np.float64)

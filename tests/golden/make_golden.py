@@ -304,22 +304,68 @@ REPLAY_CASES = {
 }
 
 
+def import_reference_wrappers():
+  """wrappers.py needs gym and cv2 at import time only (base classes and one cv2 switch); stub modules
+  let the UNMODIFIED file import so that ClipRewardEnv.reward (wrappers.py:236-238) itself is what
+  clips the rewards of the `clip` fixture."""
+  gym = types.ModuleType("gym")
+  for cls in ("Wrapper", "RewardWrapper", "ObservationWrapper", "ActionWrapper", "Env"):
+    setattr(gym, cls, type(cls, (object,), {}))
+  gym.spaces = types.ModuleType("gym.spaces")
+  cv2 = types.ModuleType("cv2")
+  cv2.ocl = types.SimpleNamespace(setUseOpenCL=lambda flag: None)
+  sys.modules.setdefault("gym", gym)
+  sys.modules.setdefault("gym.spaces", gym.spaces)
+  sys.modules.setdefault("cv2", cv2)
+  import wrappers as ref_wrappers
+  return ref_wrappers
+
+
 def gen_replay(rng):
   for name, case in REPLAY_CASES.items():
+    gen_replay_case(rng, name, case)
+
+
+def gen_replay_clip():
+  """Breakout-shaped replay whose histories carry RAW environment rewards (floats of any size, python
+  ints, +0.0 / -0.0); the reference sees them through its own ClipRewardEnv.reward, the product gets the
+  raw rewards plus clip_rewards=True.  Own seed: the fixtures above stay bit-identical."""
+  ref_wrappers = import_reference_wrappers()
+  clip_env = types.SimpleNamespace()
+  clip = lambda r: ref_wrappers.ClipRewardEnv.reward(clip_env, r)
+  case = dict(cfg=dict(action_space=4, td_steps=10, num_unroll_steps=5, discount=0.997, batch_size=64,
+                       obs_space=(128,), window_size=2048, beta=0.4),
+              lens=[80, 33, 4, 150, 61], obs_uint8=True, two_players=False)
+  gen_replay_case(np.random.default_rng(20261018), "breakout_clip", case, clip=clip)
+
+
+def gen_replay_case(rng, name, case, clip=None):
+  if True:
     cfg = make_config(**case["cfg"])
     A, K, B = cfg.action_space, cfg.num_unroll_steps, cfg.batch_size
     obs_dim = cfg.obs_space[0]
     rb = ref_replay.PrioritizedReplay(cfg)
-    hists, ignores = [], []
+    hists, ignores, aliases = [], [], []
     overlap = cfg.num_unroll_steps + cfg.td_steps
     for i, n in enumerate(case["lens"]):
       running = (i % 3 == 1) and n > overlap
       h = synth_history(rng, n, A, obs_dim, case["two_players"], case["obs_uint8"], running)
       ignore = overlap if running else None
-      rb.save_history(h, ignore=ignore, terminal=not running)
+      if clip is not None:
+        raw = [float(x) * 3 for x in rng.normal(size=n)]
+        for j in range(0, n, 7):
+          raw[j] = [0.0, -0.0, 2, -3, 0, 1e-30, -1e-30][(j // 7) % 7]  # zeros of both signs, python ints, tiny
+        seen = h._replace(rewards=[clip(r) for r in raw])                # what the env wrapper hands on
+        rb.save_history(seen, ignore=ignore, terminal=not running)
+        hist_alias = seen
+        h = h._replace(rewards=raw)
+      else:
+        rb.save_history(h, ignore=ignore, terminal=not running)
+        hist_alias = h
+      aliases.append(hist_alias)
       hists.append(h)
       ignores.append(-1 if ignore is None else ignore)
-    hist_index = {id(h): i for i, h in enumerate(hists)}
+    hist_index = {id(h): i for i, h in enumerate(aliases)}
 
     batches = []
     real_uniform, real_randint = ref_replay.random.uniform, np.random.randint
@@ -380,6 +426,8 @@ def gen_replay(rng):
                 epsilon=np.float64(cfg.epsilon), obs_uint8=np.int32(case["obs_uint8"]),
                 n_hist=np.int32(len(hists)), ignores=np.array(ignores, np.int32),
                 n_batches=np.int32(len(batches)))
+    if clip is not None:
+      save["clip_rewards"] = np.int32(1)
     for i, h in enumerate(hists):
       save["h%d_obs" % i] = np.stack(h.observations)
       save["h%d_child_visits" % i] = np.array(h.child_visits, np.float64).reshape(-1, A)
@@ -690,6 +738,9 @@ if __name__ == "__main__":
   if len(sys.argv) > 1 and sys.argv[1] == "selfplay":
     gen_selfplay()
     sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == "clip":
+    gen_replay_clip()
+    sys.exit(0)
   if len(sys.argv) > 1 and sys.argv[1] == "learner":
     gen_learner()
     sys.exit(0)
@@ -702,4 +753,5 @@ if __name__ == "__main__":
   gen_muzero()
   gen_selfplay()
   gen_learner()
+  gen_replay_clip()
   print("python", sys.version.split()[0], "numpy", np.__version__, "torch", torch.__version__)

@@ -9,7 +9,12 @@ import oracle
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 SEARCH_CASES = ["ttt", "lunar", "breakout", "atari18", "atari18_nonoise_bounds", "flat_ties"]
-REPLAY_CASES = ["breakout", "lunar_td1000", "ttt"]
+REPLAY_CASES = ["breakout", "lunar_td1000", "ttt", "breakout_clip"]
+
+
+def is_clip_case(g):
+  """The `breakout_clip` fixture stores RAW rewards; the reference saw them through ClipRewardEnv.reward."""
+  return int(g.get("clip_rewards", 0)) == 1
 
 
 def load(name):

@@ -120,8 +120,9 @@ def test_fc_search_replays_bit_exact_in_oracle():
   noise = rng.dirichlet([0.25] * A, size=G)
   u = rng.random(G)
   temp = rng.choice([0.0, 0.25, 1.0], size=G)
-  for use_graph, streams in ((False, 1), (True, 1), (True, 3)):
-    fs = FCSearch(cfg, net, G, use_graph=use_graph, num_streams=streams)
+  for use_graph, streams, fused in ((False, 1, False), (True, 1, False), (True, 3, False), (False, 1, True),
+                                    (True, 1, True)):
+    fs = FCSearch(cfg, net, G, use_graph=use_graph, num_streams=streams, fused=fused)
     fs.enable_record()
     actions, root_value, child_visits, init_value = fs.search_host(obs, noise, u, temp)
     if use_graph:  # replay the captured graph once more: results must be identical
@@ -140,7 +141,108 @@ def test_fc_search_replays_bit_exact_in_oracle():
     assert np.array_equal(child_visits.numpy(), cv)
     for i in range(G):
       assert int(actions[i]) == oracle.select_action(want["visits"][i], temp[i], u[i])
-    assert fs.launches_per_move == streams * (2 * S + 5)
+    assert fs.launches_per_move == (3 if fused else streams * (2 * S + 5))
+
+
+def _search_cfg(S, A, two_players=False, discount=0.997, known_bounds=(None, None)):
+  return types.SimpleNamespace(
+      num_simulations=S, action_space=A, two_players=two_players, discount=discount, pb_c_base=19652,
+      pb_c_init=1.25, init_value_score=0.0, known_bounds=list(known_bounds), root_exploration_fraction=0.25,
+      value_support=[-15, 15], reward_support=[-15, 15], no_support=False, no_target_transform=False)
+
+
+@pytest.mark.parametrize("cluster", [2, 4])
+@pytest.mark.parametrize("shape", ["atari18", "ttt9", "lunar4", "wide32"])
+def test_fused_search_equals_per_launch_search(cluster, shape):
+  """mz_fc_search (the whole move in one persistent kernel, clusters of 2 or 4 CTAs) against the
+  per-simulation launches of mz_tree_step + mz_fc_recurrent_tc on the same inputs: identical network
+  outputs at every simulation (same MMA sequence on the same bf16 operands), identical (parent, action,
+  depth) traces, visit counts, root values, MinMax bounds, child-visit distributions and selected
+  actions -- bit for bit -- and the same trees (priors, children, value sums, visit counts, rewards).
+  Game counts are not multiples of the 128-game tile (absent rows), TTT has legal masks, two players
+  and known bounds."""
+  from model_based_rl_b200 import _lib
+  from model_based_rl_b200.networks import FCNetwork, FCSearch, random_state_dict
+  G, A, S, D, two, disc, kb = {"atari18": (300, 18, 50, 128, False, 0.997, (None, None)),
+                               "ttt9": (130, 9, 30, 9, True, 1.0, (-1, 1)),
+                               "lunar4": (257, 4, 30, 8, False, 0.997, (None, None)),
+                               "wide32": (100, 32, 20, 16, False, 0.99, (None, None))}[shape]
+  cfg = _search_cfg(S, A, two, disc, kb)
+  net = FCNetwork(D, A, "cuda", cfg)
+  net.load_weights(random_state_dict(D, A, seed=11))
+  rng = np.random.default_rng(5)
+  obs = rng.normal(size=(G, D)).astype(np.float32)
+  legal = to_play = None
+  noise = rng.dirichlet([0.25] * A, size=G)
+  if shape == "ttt9":
+    legal = rng.integers(1, 1 << A, size=G).astype(np.int32)
+    to_play = rng.choice([-1, 1], size=G).astype(np.int8)
+    noise = np.zeros((G, A))
+    for i in range(G):
+      n = bin(int(legal[i])).count("1")
+      noise[i, :n] = rng.dirichlet([0.25] * n)
+  u, temp = rng.random(G), rng.choice([0.0, 0.5, 1.0], size=G)
+  lib = _lib.load()
+  outs = []
+  try:
+    for fused in (False, True):
+      if fused:
+        _lib.check(lib.mz_fc_search_set_cluster(cluster), "mz_fc_search_set_cluster")
+      fs = FCSearch(cfg, net, G, use_graph=False, num_streams=1, fused=fused)
+      fs.enable_record()
+      r = fs.search_host(obs, noise, u, temp, legal=legal, to_play=to_play)
+      torch.cuda.synchronize()
+      if fused:
+        assert int(fs.fused.error_flag.item()) == 0
+      eng = fs.fused if fused else fs.eng
+      trees = [eng.export_game(g) for g in (0, G // 2, G - 1)]
+      outs.append(dict(actions=r[0].clone(), root_value=r[1].clone(), child_visits=r[2].clone(),
+                       init_value=r[3].clone(), visits=fs.visits.cpu(), minmax=fs.minmax.cpu(),
+                       record=[t.cpu() for t in fs.record], trace=[t.cpu() for t in fs.trace], trees=trees))
+  finally:
+    lib.mz_fc_search_set_cluster(0)
+  a, b = outs
+  for i, name in enumerate(("value", "reward", "logits")):
+    assert torch.equal(a["record"][i], b["record"][i]), "network %s differs" % name
+  for i, name in enumerate(("parent", "action", "depth")):
+    assert torch.equal(a["trace"][i], b["trace"][i]), "trace %s differs" % name
+  for k in ("visits", "root_value", "child_visits", "minmax", "actions", "init_value"):
+    assert torch.equal(a[k], b[k]), k
+  for ta, tb in zip(a["trees"], b["trees"]):
+    for k in ("prior", "child", "vsum", "visit", "reward"):
+      assert np.array_equal(ta[k], tb[k]), "tree %s differs" % k
+
+
+def test_search_after_load_weights_uses_new_weights():
+  """Weight hand-off (Learner.send_weights -> network.load_weights): launch plans and CUDA graphs captured
+  before the hand-off hold device pointers; load_weights refills the same storage, so the next search runs
+  on the new weights -- same result as an engine built after the load -- and the network holds a snapshot
+  (later in-place changes of the source tensors do not leak in)."""
+  from model_based_rl_b200.networks import FCNetwork, FCSearch, random_state_dict
+  G, A, S, D = 192, 6, 16, 32
+  cfg = _search_cfg(S, A)
+  rng = np.random.default_rng(21)
+  obs = rng.normal(size=(G, D)).astype(np.float32)
+  noise, u, temp = rng.dirichlet([0.25] * A, size=G), rng.random(G), np.ones(G)
+  sd1 = random_state_dict(D, A, seed=1)
+  sd2 = random_state_dict(D, A, seed=2)
+  for fused in (False, True):
+    net = FCNetwork(D, A, "cuda", cfg)
+    net.load_weights(sd1)
+    fs = FCSearch(cfg, net, G, use_graph=True, num_streams=2, fused=fused)
+    first = [t.clone() for t in fs.search_host(obs, noise, u, temp)]
+    live = {k: v.clone().cuda() for k, v in sd2.items()}
+    net.load_weights(live)
+    for v in live.values():
+      v.add_(1.0)  # the caller's tensors change after the hand-off (an optimiser step): no effect
+    second = [t.clone() for t in fs.search_host(obs, noise, u, temp)]
+    fresh_net = FCNetwork(D, A, "cuda", cfg)
+    fresh_net.load_weights(sd2)
+    fresh = FCSearch(cfg, fresh_net, G, use_graph=False, num_streams=1, fused=fused)
+    want = [t.clone() for t in fresh.search_host(obs, noise, u, temp)]
+    assert not torch.equal(first[2], second[2])
+    for x, y in zip(second, want):
+      assert torch.equal(x, y)
 
 
 @pytest.mark.gpu

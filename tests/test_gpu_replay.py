@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import REPLAY_CASES, load
+from helpers import REPLAY_CASES, is_clip_case, load
 
 pytestmark = pytest.mark.gpu
 
@@ -25,16 +25,20 @@ def _config(g, **kw):
            td_steps=int(g["td_steps"]), discount=float(g["discount"]),
            action_space=int(g["action_space"]), obs_space=(int(g["obs_dim"]),),
            window_size=int(g["window_size"]), window_step=int(g["window_step"]), seed=None,
-           value_support=(-15, 15), reward_support=(-15, 15), no_target_transform=False)
+           value_support=(-15, 15), reward_support=(-15, 15), no_target_transform=False,
+           clip_rewards=is_clip_case(g))
   d.update(kw)
   return types.SimpleNamespace(**d)
 
 
 def _history(g, h):
   n = len(g["h%d_root_values" % h])
+  rewards = g["h%d_rewards" % h].tolist()
+  if is_clip_case(g):  # raw environment rewards; integral ones as python ints, like gym returns them
+    rewards = [int(r) if r == int(r) and abs(r) >= 1 else r for r in rewards]
   return HistorySlice([o for o in g["h%d_obs" % h]], g["h%d_child_visits" % h].tolist(),
                       g["h%d_root_values" % h].tolist(), g["h%d_actions" % h].tolist(),
-                      g["h%d_rewards" % h].tolist(), g["h%d_errors" % h].tolist(), [False] * n,
+                      rewards, g["h%d_errors" % h].tolist(), [False] * n,
                       list(range(n)), [None] * n, g["h%d_to_play" % h].tolist())
 
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import REPLAY_CASES, load
+from helpers import REPLAY_CASES, is_clip_case, load
 
 pytestmark = pytest.mark.gpu
 
@@ -53,7 +53,8 @@ def test_build_targets_matches_reference(case, fuse, targets_kernel):
   A, K, T, B = int(g["action_space"]), int(g["num_unroll_steps"]), int(g["td_steps"]), int(g["batch_size"])
   E, disc = int(g["obs_dim"]), float(g["discount"])
   dev, starts, lens = _window_from_golden(g)
-  win = _lib.Window(A, E, int(g["obs_uint8"]), 0, dev["obs"].data_ptr(), dev["actions"].data_ptr(),
+  # the clip fixture holds raw rewards: the kernel clips on the fly (mz_window.clip_rewards, wrappers.py:236-238)
+  win = _lib.Window(A, E, int(g["obs_uint8"]), int(is_clip_case(g)), dev["obs"].data_ptr(), dev["actions"].data_ptr(),
                     dev["rewards"].data_ptr(), dev["to_play"].data_ptr(),
                     dev["root_values"].data_ptr(), dev["child_visits"].data_ptr())
   discounts = torch.from_numpy(np.array([disc**n for n in range(K + T)], np.float32)).cuda()

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import (REPLAY_CASES, SEARCH_CASES, SEARCH_EXACT_KEYS, load,
+from helpers import (REPLAY_CASES, SEARCH_CASES, SEARCH_EXACT_KEYS, is_clip_case, load,
                      oracle_search_from_golden)
 
 
@@ -59,7 +59,10 @@ def test_insert_target(case):
     steps, hist = g["b%d_steps" % b], g["b%d_hist" % b]
     for row in range(len(steps)):
       h = int(hist[row])
-      tr, tv, tp = oracle.insert_target(g["h%d_rewards" % h], g["h%d_to_play" % h],
+      rewards = g["h%d_rewards" % h]
+      if is_clip_case(g):  # the wrapper clips at env-step time: restated as oracle.clip_reward per step
+        rewards = np.array([oracle.clip_reward(r) for r in rewards.tolist()], np.float64)
+      tr, tv, tp = oracle.insert_target(rewards, g["h%d_to_play" % h],
                                         g["h%d_root_values" % h], g["h%d_child_visits" % h], K, T,
                                         disc, int(steps[row]))
       assert np.array_equal(tr, g["b%d_t_rewards" % b][row])
