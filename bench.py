@@ -58,6 +58,10 @@ def parse():
   p.add_argument("--no-conv", action="store_true", help="skip the C5 MuZeroNetwork section")
   p.add_argument("--no-sweep", action="store_true", help="skip the larger-batch throughput probe")
   p.add_argument("--conv-games", type=int, default=4096, help="C5: concurrent games per GPU")
+  p.add_argument("--fused", choices=["auto", "0", "1"], default="auto",
+                 help="1: the whole move in one persistent kernel (mz_fc_search); 0: one tree + one network launch per "
+                      "simulation; auto: FCSearch's default (MZ_FUSED in the environment)")
+  p.add_argument("--no-f32", action="store_true", help="skip the float32-network throughput line")
   p.add_argument("--ref-moves-per-step", type=int, default=2,
                  help="reference arm: moves each worker plays per step")
   return p.parse_args()
@@ -88,19 +92,29 @@ def synthetic_inputs(args, rank, games, as_bytes=False):
 # ------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the pure-Python port of the reference path (oracle/search_ref.py)
 # ------------------------------------------------------------------------------------------------
+_WORKER_STATE = {}
+
+
 def _cpu_worker(job):
-  """Plays moves of independent games with the python port until the deadline / move budget."""
+  """Plays moves of independent games with the python port until the deadline / move budget.  The network,
+  its weights and the search object live as long as the worker process (an Actor builds them once,
+  actors.py:29-47), so a timed step measures moves only."""
   (wid, args_d, seconds, max_moves) = job
-  os.environ["OMP_NUM_THREADS"] = "1"  # train.py:63
+  key = (args_d["actions"], args_d["sims"], args_d["obs_dim"])
+  if key not in _WORKER_STATE:
+    os.environ["OMP_NUM_THREADS"] = "1"  # train.py:63
+    import torch
+    torch.set_num_threads(1)
+    from oracle.fcnet_ref import FCNetworkRef, random_state_dict
+    from oracle.search_ref import FlatSearch
+    A, S, D = key
+    net = FCNetworkRef(D, A)
+    net.load_state_dict(random_state_dict(D, A))
+    _WORKER_STATE[key] = (net, FlatSearch(S, A), np.random.default_rng(99 + wid + 1000 * os.getpid()))
   import torch
-  torch.set_num_threads(1)
-  from oracle.fcnet_ref import FCNetworkRef, random_state_dict
-  from oracle.search_ref import FlatSearch, play_move
-  A, S, D = args_d["actions"], args_d["sims"], args_d["obs_dim"]
-  net = FCNetworkRef(D, A)
-  net.load_state_dict(random_state_dict(D, A))
-  rng = np.random.default_rng(99 + wid)
-  search = FlatSearch(S, A)
+  from oracle.search_ref import play_move
+  A, S, D = key
+  net, search, rng = _WORKER_STATE[key]
   moves, t0 = 0, time.perf_counter()
   with torch.inference_mode():
     while True:
@@ -167,18 +181,21 @@ def run_reference(args):
       "config": workload_config(args, 1, cpu=True),
       "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "l2": "n/a (CPU)",
   }
   emit(line)
 
 
 def workload_config(args, n_gpus, cpu=False):
+  """Identical in both arms (the driver compares them key by key)."""
   return {"workload": "C4 synthetic Atari-scale search sweep: A=%d, %d games x %d sims per GPU, "
                       "FCNetwork(%d->50), Dirichlet root noise, temperature 1" %
                       (args.actions, args.games, args.sims, args.obs_dim),
           "games_per_gpu": args.games, "num_simulations": args.sims, "action_space": args.actions,
-          "obs_dim": args.obs_dim, "parallelism": "games sharded x%d, no search collective" % n_gpus,
-          "l2": ("n/a (CPU)" if cpu else
-                 "L2 flushed (512 MiB memset) between timed steps, outside the per-step event pairs")}
+          "obs_dim": args.obs_dim, "parallelism": "independent games, sharded across GPUs, no search collective"}
+
+
+L2_POLICY = "L2 flushed (512 MiB memset) between timed steps, outside the per-step event pairs"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -317,7 +334,8 @@ def run_b200(args):
     from model_based_rl_b200 import parallel
     parallel.broadcast_weights(sd, src=0)
   net.load_weights(sd)
-  fs = FCSearch(cfg, net, G, use_graph=not args.no_graph, num_streams=args.streams)
+  fused = {"auto": None, "0": False, "1": True}[args.fused]
+  fs = FCSearch(cfg, net, G, use_graph=not args.no_graph, num_streams=args.streams, fused=fused)
   obs, noise, uniforms, temperature = synthetic_inputs(args, rank, G)
   pin = lambda a: torch.from_numpy(a).pin_memory()
   h_obs, h_noise, h_u, h_t = pin(obs), pin(noise), pin(uniforms), pin(temperature)
@@ -372,12 +390,45 @@ def run_b200(args):
   barrier()
   clock_info = clocks.stop() if rank == 0 else None
 
-  # per-kernel durations (CUDA events around each launch of one un-graphed move)
-  fs1 = FCSearch(cfg, net, G, use_graph=False, num_streams=1)  # un-graphed, one stream
-  for name in ("obs", "noise", "uniforms", "temperature"):
-    getattr(fs1, name).copy_(getattr(fs, name))
-  kern = kernel_breakdown(fs1, torch)
-  del fs1
+  # per-kernel durations (CUDA events around each launch of one un-graphed move), at the launch shape the
+  # timed graph uses: the games of ONE slice (G / streams) per launch, and for reference all G games in one
+  n_slices = 1 if fs.fused is not None else len(fs.lanes)
+  g_slice = (G + n_slices - 1) // n_slices
+  kern, kern_full = None, None
+  for gk in sorted({g_slice, G}):
+    fs1 = FCSearch(cfg, net, gk, use_graph=False, num_streams=1, fused=False)  # un-graphed, one stream
+    for name in ("obs", "noise", "uniforms", "temperature"):
+      getattr(fs1, name).copy_(getattr(fs, name)[:gk])
+    k = kernel_breakdown(fs1, torch)
+    k["games_per_launch"] = gk
+    if gk == g_slice:
+      kern = k
+    if gk == G:
+      kern_full = k
+    del fs1
+  fused_us = None
+  if fs.fused is not None:  # the persistent kernel alone: CUDA events around its launch in an un-graphed move
+    fsu = FCSearch(cfg, net, G, use_graph=False, num_streams=1, fused=True)
+    for name in ("obs", "noise", "uniforms", "temperature"):
+      getattr(fsu, name).copy_(getattr(fs, name))
+    fused_us = fused_kernel_us(fsu, torch)
+    del fsu
+  f32_line = None
+  if rank == 0 and world == 1 and args.precision == "bf16" and not args.no_f32:
+    # the same move with the reference-precision (float32, CUDA-core) network kernel
+    net32 = FCNetwork(args.obs_dim, A, dev, cfg, precision="f32")
+    net32.load_weights(sd)
+    fs32 = FCSearch(cfg, net32, G, use_graph=not args.no_graph, num_streams=args.streams)
+    fs32.search_host(h_obs, h_noise, h_u, h_t)
+    for _ in range(args.warmup):
+      fs32.run()
+    torch.cuda.synchronize()
+    n32 = max(3, min(args.steps, 10))
+    ms32 = timed(fs32.run, n32)
+    f32_line = {"value": G * S * n32 / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32 / n32, "steps": n32,
+                "network": "fc_recurrent_f32_kernel (float32 CUDA cores; parity bar vs the reference's torch module: "
+                           "1e-4, tests/test_gpu_fcnet.py)", "same_workload": True}
+    del fs32, net32
 
   t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
   if world > 1:
@@ -424,25 +475,43 @@ def run_b200(args):
     e2e = expansions / (ms_e2e * 1e-3)
     # algorithmic bytes / flops per launch (DESIGN.md "Kernels")
     d = kern["mean_depth"]
-    tree_bytes = G * (d * (28 * A + 33) + 16 * A + 86)
-    fc_flops = G * FC_FLOPS_PER_EXPANSION(A)
+    gl = kern["games_per_launch"]  # the launch shape of the timed region
+    per_game_bytes = d * (28 * A + 33) + 16 * A + 86
+    tree_bytes = gl * per_game_bytes
+    fc_flops = gl * FC_FLOPS_PER_EXPANSION(A)
     tree_t, fc_t = kern["tree_step_us"] * 1e-6, kern["fc_recurrent_us"] * 1e-6
-    # dram__bytes_read + write per launch from the ncu --set full captures of the default workload
-    # (profiles/r01h_ncu_summary.md, r01m_ncu_summary.md); null for any other configuration
-    default_cfg = (G, S, A, args.obs_dim) == (4096, 50, 18, 128)
-    roof_tree = {"kernel": "tree_step_w32_kernel" if A > 16 else "tree_step_kernel", "bound": "hbm",
-                 "achieved": tree_bytes / tree_t / 1e9,
-                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": 43.2e6 if default_cfg else None,
-                 "algorithmic_bytes_per_launch": tree_bytes, "avg_launch_us": kern["tree_step_us"]}
-    roof_fc = {"kernel": "fc_recurrent_tc_kernel" if args.precision == "bf16" else "fc_recurrent_f32_kernel",
-               "bound": "tensor", "achieved": fc_flops / fc_t / 1e12,
+    tree_name = "tree_step_w32_kernel"
+    fc_name = "fc_recurrent_tc_kernel" if args.precision == "bf16" else "fc_recurrent_f32_kernel"
+    roof_tree = {"kernel": tree_name, "bound": "hbm", "achieved": tree_bytes / tree_t / 1e9,
+                 "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "traffic": ncu_traffic(tree_name, gl, A, S),
+                 "games_per_launch": gl, "algorithmic_bytes_per_launch": tree_bytes,
+                 "avg_launch_us": kern["tree_step_us"]}
+    roof_fc = {"kernel": fc_name, "bound": "tensor", "achieved": fc_flops / fc_t / 1e12,
                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-               "traffic": 1.9e6 if default_cfg else None,
-               "algorithmic_flops_per_launch": fc_flops, "avg_launch_us": kern["fc_recurrent_us"]}
-    for r in (roof_tree, roof_fc):
+               "traffic": ncu_traffic(fc_name, gl, A, S),
+               "games_per_launch": gl, "algorithmic_flops_per_launch": fc_flops,
+               "avg_launch_us": kern["fc_recurrent_us"]}
+    roofs = [roof_tree, roof_fc]
+    if fused_us is not None:  # one launch = the whole move: both resources against the same duration
+      move_bytes, move_flops = S * G * per_game_bytes, S * G * FC_FLOPS_PER_EXPANSION(A)
+      roof_fused = {"kernel": "fc_search_kernel", "bound": "hbm", "achieved": move_bytes / (fused_us * 1e-6) / 1e9,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": ncu_traffic("fc_search_kernel", G, A, S),
+                    "games_per_launch": G, "algorithmic_bytes_per_launch": move_bytes, "avg_launch_us": fused_us,
+                    "tensor_tflops": move_flops / (fused_us * 1e-6) / 1e12,
+                    "tensor_frac": move_flops / (fused_us * 1e-6) / 1e12 / peaks["bf16_tflops_sustained"]}
+      roofs = [roof_fused] + roofs
+    for r in roofs:
       r["frac"] = r["achieved"] / r["peak"]
       r["peak_source"] = peaks["source"]
-    dominant = roof_fc if fc_t >= tree_t else roof_tree
+    dominant = roofs[0] if fused_us is not None else (roof_fc if fc_t >= tree_t else roof_tree)
+    # the whole timed step against both roofs (algorithmic bytes / FLOPs of all S simulations of all games)
+    step_s = ms_total * 1e-3 / args.steps
+    whole_step = {"hbm_gbs": S * G * per_game_bytes / step_s / 1e9,
+                  "hbm_frac": S * G * per_game_bytes / step_s / 1e9 / peaks["hbm_gbs"],
+                  "tensor_tflops": S * G * FC_FLOPS_PER_EXPANSION(A) / step_s / 1e12,
+                  "tensor_frac": S * G * FC_FLOPS_PER_EXPANSION(A) / step_s / 1e12 / peaks["bf16_tflops_sustained"],
+                  "note": "per GPU; the step is %d dependent simulations, not one roofline-bound kernel" % S}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -454,8 +523,10 @@ def run_b200(args):
                           "float64 noise / uniforms / temperatures, legal masks, to_play",
                 "d2h_bytes_per_step": fs.d2h_bytes(), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": fs.launches_per_move * args.steps,
-        "clocks": clock_info, "roofline": dominant, "roofline_all": [roof_tree, roof_fc],
-        "kernel_share": kern, "cuda_graph": not args.no_graph, "streams": len(fs.lanes),
+        "clocks": clock_info, "roofline": dominant, "roofline_all": roofs, "whole_step": whole_step,
+        "kernel_share": kern, "kernel_share_all_games_one_launch": kern_full,
+        "fused_search_kernel": fs.fused is not None, "l2": L2_POLICY,
+        "cuda_graph": not args.no_graph, "streams": n_slices, "f32_network": f32_line,
         "games_sweep": sweep, "other_configs": others, "targets": targets, "replay": replay, "learner": learner,
         "conv": conv,
     }
@@ -495,6 +566,45 @@ def bench_other_configs(args, torch, dev, timed):
                  "ms_per_move": ms / 5}
     del fs
   return out
+
+
+def _source_sha16(name):
+  import hashlib
+  path = os.path.join(REPO, "model-based-rl_b200", "csrc", name)
+  return hashlib.sha256(open(path, "rb").read()).hexdigest()[:16] if os.path.exists(path) else None
+
+
+def ncu_traffic(kernel, games, A, S):
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch from an `ncu --set full` capture of THIS kernel
+  source at THIS launch shape (profiles/traffic.json, written by tests/ncu_traffic.py from the capture;
+  an entry only counts while the kernel's .cu file is byte-identical to the captured one), else null."""
+  path = os.path.join(REPO, "profiles", "traffic.json")
+  if not os.path.exists(path):
+    return None
+  for e in json.load(open(path)).get("entries", []):
+    if (e.get("kernel") == kernel and e.get("games") == games and e.get("actions") == A and e.get("sims") == S and
+        e.get("source_sha16") == _source_sha16(e.get("source", ""))):
+      return e.get("dram_bytes_per_launch")
+  return None
+
+
+def fused_kernel_us(fs, torch):
+  """Device time of the persistent search kernel alone (CUDA events around the launch, un-graphed move)."""
+  fs.run()
+  torch.cuda.synchronize()
+  plan = fs._fused_plan
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  total = 0.0
+  for _ in range(3):
+    plan[0][0](*plan[0][1])
+    a.record()
+    rc = plan[1][0](*plan[1][1])
+    b.record()
+    assert rc == 0, rc
+    plan[2][0](*plan[2][1])
+    torch.cuda.synchronize()
+    total += a.elapsed_time(b) * 1e3
+  return total / 3
 
 
 def kernel_breakdown(fs, torch):
@@ -572,7 +682,7 @@ def bench_conv(args, torch, _lib, dev):
   flops = 2.0 * G * 36 * 128 * 1152  # algorithmic: interior pixels only (the padded rows are overhead)
   roof = {"kernel": "conv_pair_tc_kernel", "bound": "tensor", "achieved": flops / us_conv / 1e6,
           "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-          "traffic": 56.5e6 if (G, C_in) == (4096, 32) else None,  # ncu, profiles/r01o_ncu_summary.md
+          "traffic": ncu_traffic("conv_pair_tc_kernel", G, A, S),
           "algorithmic_flops_per_launch": flops, "avg_launch_us": us_conv,
           "issued_tflops": 2.0 * G * ROWS * 128 * 1152 / us_conv / 1e6, "peak_source": peaks["source"]}
   roof["frac"] = roof["achieved"] / roof["peak"]
@@ -669,9 +779,8 @@ def bench_targets(torch, _lib, dev):
                   "algorithmic_bytes_per_sample": bps,
                   "roofline": {"kernel": "build_targets_rows_kernel" if rows_kernel else "build_targets_kernel",
                                "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                               # ncu dram read + write of one launch, profiles/r01t_summary.md (part of the
-                               # written lines is still dirty in L2 when the launch ends)
-                               "traffic": 102.9e6 if name == "C3_breakout_ram" else None,
+                               "traffic": ncu_traffic("build_targets_rows_kernel" if rows_kernel else
+                                                      "build_targets_kernel", Bb, A2, T2),
                                "peak_source": peaks["source"]}}
   res["bulk"] = bulk
   return res

@@ -296,7 +296,7 @@ typedef struct mz_fc_search_args {
   float* rec_value;              /* [S][G] or NULL: what the network returned (parity replays) */
   float* rec_reward;             /* [S][G] */
   float* rec_logits;             /* [S][G][A] */
-  int64_t* timeline;             /* [S][16] clock64 stamps of tile 0 or NULL (diagnostics) */
+  int64_t* timeline;             /* [S][32] clock64 stamps of tile 0 or NULL (diagnostics) */
   int32_t* error_flag;           /* set before the kernel traps on a protocol time-out, or NULL */
 } mz_fc_search_args;
 
@@ -312,6 +312,11 @@ int mz_fc_search_export(const mz_fc_search_args* a, int32_t game, double* prior,
  * streamed per simulation), 4 (one head per CTA, weights resident in shared memory), 0 = default
  * (MZ_FS_CLUSTER in the environment, else 2). */
 int mz_fc_search_set_cluster(int32_t cluster);
+/* tree engine of mz_fc_search: 0 = dense (four lanes per game walk the tree level by level, every action of a
+ * node scored), 1 = sparse (clusters of four, S <= 63: every expanded node ranks only its expanded children and
+ * its best unexpanded child, all nodes in parallel, then the descent is a pointer chase), -1 = default
+ * (MZ_FS_ENGINE in the environment, else sparse whenever the shape allows).  Same results bit for bit. */
+int mz_fc_search_set_engine(int32_t engine);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Scalar transforms and supports (config.py:27-68), float32 in torch's op order.                */
@@ -397,6 +402,12 @@ int mz_sumtree_update(double* tree, int64_t max_capacity, int64_t n, const int64
 int mz_sumtree_add(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
                    const double* priority, int64_t chunk_start, int32_t chunk_len, int64_t* slot_pos,
                    int64_t* slot_start, int32_t* slot_len, double* scratch, void* stream);
+/* Same for memories first_step .. first_step + n - 1 of the chunk (slot -> chunk_start + first_step + i).  The
+ * tree indices of ONE call must be distinct: a history that laps the ring is added in pieces, so that the last
+ * write to a slot wins like in the reference's one-memory-at-a-time loop (replay_buffer.py:19-33). */
+int mz_sumtree_add_from(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
+                        const double* priority, int64_t chunk_start, int32_t chunk_len, int32_t first_step,
+                        int64_t* slot_pos, int64_t* slot_start, int32_t* slot_len, double* scratch, void* stream);
 /* The sampling half of sample_batch (replay_buffer.py:134-145, 160-162) for n rows:
  *   value_b = random.uniform(seg*b, seg*(b+1)) with seg = total/n, computed on the device from the
  *   host-drawn u01[b] = random.random() (same binary64 operations as CPython's uniform());

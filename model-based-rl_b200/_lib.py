@@ -124,6 +124,7 @@ _SIGNATURES = {
     "mz_fc_search": (C.c_int, [C.POINTER(FcSearchArgs), _V]),
     "mz_fc_search_export": (C.c_int, [C.POINTER(FcSearchArgs), C.c_int32, _V, _V, _V, _V, _V, _V, _V]),
     "mz_fc_search_set_cluster": (C.c_int, [C.c_int32]),
+    "mz_fc_search_set_engine": (C.c_int, [C.c_int32]),
     "mz_scalar_transform": (C.c_int, [C.c_int64, _V, _V, _V]),
     "mz_scalar_to_support": (C.c_int, [C.c_int64, _V, C.c_int32, C.c_int32, C.c_int32, _V, _V]),
     "mz_support_to_scalar": (C.c_int, [C.c_int64, _V, C.c_int32, C.c_int32, C.c_int32, _V, _V]),
@@ -132,6 +133,8 @@ _SIGNATURES = {
     "mz_sumtree_update": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, _V, _V]),
     "mz_sumtree_add": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_int64, C.c_int32, _V, _V, _V,
                                  _V, _V]),
+    "mz_sumtree_add_from": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_int64, C.c_int32, C.c_int32, _V, _V, _V,
+                                      _V, _V]),
     "mz_sumtree_sample": (C.c_int, [_V, C.c_int64, C.c_int32, _V, _V, _V, _V, C.c_int64, C.c_double,
                                     _V, _V, _V, _V, _V, _V, _V]),
     "mz_conv3x3_tc": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _V, _V, _V, C.c_int32, _V, _V, C.c_int32, _V,
@@ -222,3 +225,22 @@ def normalize_device(device=None):
   if dev.index is None:
     dev = torch.device('cuda', torch.cuda.current_device())
   return dev
+
+
+def on_device(method):
+  """Decorator for methods of objects with a `.device` (or `.net.device`): the body runs with that CUDA device
+  current, so `current_stream()` and every launch made through the C ABI land on the object's own GPU even when
+  the caller's current device is another one."""
+  import functools
+
+  @functools.wraps(method)
+  def wrapped(self, *args, **kwargs):
+    import torch
+    dev = getattr(self, "device", None)
+    if dev is None:
+      dev = self.net.device
+    if torch.cuda.current_device() == dev.index:
+      return method(self, *args, **kwargs)
+    with torch.cuda.device(dev):
+      return method(self, *args, **kwargs)
+  return wrapped

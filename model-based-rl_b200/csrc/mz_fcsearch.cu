@@ -48,7 +48,7 @@ constexpr int FS_HDR = 64;              // game header bytes
 constexpr int FS_META = 16, FS_PQ = 80; // offsets inside a node record
 constexpr int CH_UNEXP = 255, CH_ILLEGAL = 254;
 constexpr int POOL_ROW = 64;            // bf16 elements per hidden-pool row (128 bytes, one line)
-constexpr int SP_STRIDE = 25;           // doubles per game of the expansion scratch (bank-conflict free)
+constexpr int SP_STRIDE = 33;           // doubles per game of the expansion scratch (>= 32 actions; odd: conflict free)
 
 struct FsParams {
   // network (same packed image as mz_fc_recurrent_tc)
@@ -77,7 +77,7 @@ struct FsParams {
   // optional
   int32_t *trace_parent, *trace_action, *trace_depth;  // [S][G]
   float *rec_value, *rec_reward, *rec_logits;          // [S][G], [S][G], [S][G][A]
-  long long* timeline;                                 // [S][16] clock64 stamps of tile 0 (diagnostics)
+  long long* timeline;                                 // [S][32] clock64 stamps of tile 0 (diagnostics)
   int* error_flag;
 };
 
@@ -160,6 +160,31 @@ MZ_DEV uint32_t meta_at(const uint4& mw, int t) {  // u16 number t of a lane's m
   return (w >> (16 * (t & 1))) & 0xffffu;
 }
 
+// exp() of mz_exp.cuh with the 2 KB table in shared memory: this kernel's shared-memory footprint leaves almost no
+// L1, so the table lookups of the global-memory version are L2 round trips on the expansion's critical path.
+// Same algorithm and constants (csrc/mz_exp_algo.h), bit-identical results.
+MZ_DEV double fs_exp(double x, const unsigned long long* tab) {
+  const double ax = fabs(x);
+  if (!(ax >= 0x1p-54 && ax < 512.0)) return mz_exp(x);
+  const double InvLn2N = 0x1.71547652b82fep7, Shift = 0x1.8p52;
+  const double NegLn2hiN = -0x1.62e42fefa0000p-8, NegLn2loN = -0x1.cf79abc9e3b3ap-47;
+  const double C2 = 0x1.ffffffffffdbdp-2, C3 = 0x1.555555555543cp-3;
+  const double C4 = 0x1.55555cf172b91p-5, C5 = 0x1.1111167a4d017p-7;
+  const double z = __dmul_rn(InvLn2N, x);
+  double kd = __dadd_rn(z, Shift);
+  const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+  kd = __dsub_rn(kd, Shift);
+  const double r = __fma_rn(kd, NegLn2loN, __fma_rn(kd, NegLn2hiN, x));
+  const unsigned long long idx = 2 * (ki % 128), top = ki << 45;
+  const double tail = __longlong_as_double((long long)tab[idx]);
+  const unsigned long long sbits = tab[idx + 1] + top;
+  const double r2 = __dmul_rn(r, r);
+  const double a = __fma_rn(r, C3, C2), b = __fma_rn(r, C5, C4);
+  const double tmp = __fma_rn(__dmul_rn(r2, r2), b, __fma_rn(r2, a, __dadd_rn(tail, r)));
+  const double scale = __longlong_as_double((long long)sbits);
+  return __fma_rn(scale, tmp, scale);
+}
+
 // ---- shared-memory map of the tree engine (per CTA: GP = 128 / CL games) --------------------------------
 struct FsTreeSmem {
   float* logit;     // [GP][A4]   policy logits of the last network evaluation (st.async from the policy head)
@@ -168,6 +193,7 @@ struct FsTreeSmem {
   double* sp;       // [GP][25]   exp(logit) / reward scratch of the expansion
   double* mm;       // [GP][2]    MinMaxStats (mcts.py:6-25)
   const double* pbc;  // lower-triangular pb_c table: entry N (N + 1) / 2 + n
+  const unsigned long long* exp_tab;  // mz_exp_tab in shared memory
   uint8_t* path_n;  // [GP][PS]  node ids of the current search path
   uint8_t* path_a;  // [GP][PS]  action taken at each level
   uint8_t* depth;   // [GP]
@@ -198,7 +224,7 @@ MZ_DEV double fs_prior_sum(const FsParams& p, const FsTreeSmem& sm, const FsGame
   for (int t = 0; t < T; ++t) {
     const int a = 4 * t + gm.sub;
     double e = 0.0;
-    if (a < A && ((legal_bits >> a) & 1u)) e = mz_exp((double)logits[a]);
+    if (a < A && ((legal_bits >> a) & 1u)) e = fs_exp((double)logits[a], sm.exp_tab);
     pexp[t] = e;
     if (a < A) sp[a] = e;
   }
@@ -565,40 +591,71 @@ MZ_DEV void fs_root_stats(const FsParams& p, const FsTreeSmem& sm, const FsGame&
   }
 }
 
-// shared-memory budget (bytes); must match the carve in the kernel
+}  // namespace
+
+#include "mz_fcs_sparse.cuh"
+
+namespace {
+
+// shared-memory plan (bytes).  Everything a peer CTA addresses (barriers, output slots, A1 / A3 images) sits at
+// the same offset in every CTA of the cluster.  In clusters of four no CTA owns both a dynamics and a prediction
+// head, so the A3 image shares the A1 region.
 __host__ __device__ inline size_t fs_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 struct FsLayout {
   size_t a1, w, a3, bars, tail, sh, logit, val, rew, sp, mm, pbc, path_n, path_a, depth, total;
-  int ps, a4, gp;
+  size_t best_ca, node, xmask, par;  // sparse engine
+  size_t exp_tab;
+  int ps, a4, gp, s1;
 };
-__host__ __device__ inline FsLayout fs_layout(int k1, int stages, int cl, int A, int S) {
+__host__ __device__ inline FsLayout fs_layout(int k1, int stages, int cl, int A, int S, bool sparse) {
   FsLayout L;
   L.gp = ROWS / cl;
   L.a4 = (A + 3) / 4 * 4;
   L.ps = (S + 2 + 15) / 16 * 16;
+  L.s1 = (S + 2) & ~1;
   size_t off = 0;
   L.a1 = off; off += (size_t)ROWS * k1 * 2;
   L.w = off; off += (size_t)stages * stage_bytes_for(k1);
-  L.a3 = off; off += (size_t)ROWS * K3 * 2;
+  if (cl == 4) {
+    L.a3 = L.a1;
+  } else {
+    L.a3 = off; off += (size_t)ROWS * K3 * 2;
+  }
   L.bars = off; off += 32 * sizeof(uint64_t);
   L.tail = off; off += TAIL_FLOATS * sizeof(float);
   L.sh = off; off += (size_t)ROWS * 128;
   L.logit = off; off += fs_align16((size_t)L.gp * L.a4 * 4);
   L.val = off; off += fs_align16((size_t)L.gp * 4);
   L.rew = off; off += fs_align16((size_t)L.gp * 4);
-  L.sp = off; off += fs_align16((size_t)L.gp * SP_STRIDE * 8);
   L.mm = off; off += (size_t)L.gp * 16;
-  L.pbc = off; off += fs_align16((size_t)(S + 1) * (S + 2) / 2 * 8);
   L.path_n = off; off += (size_t)L.gp * L.ps;
   L.path_a = off; off += (size_t)L.gp * L.ps;
   L.depth = off; off += fs_align16((size_t)L.gp);
+  L.exp_tab = off; off += 256 * 8;
+  L.pbc = L.best_ca = L.node = L.xmask = L.par = 0;
+  if (sparse) {
+    // exp / reward scratch and the per-node maxima are used in different phases: one region
+    const size_t sp_bytes = (size_t)L.gp * SP_STRIDE * 8, key_bytes = (size_t)L.gp * L.s1 * 8;
+    L.sp = off; off += fs_align16(sp_bytes > key_bytes ? sp_bytes : key_bytes);
+    L.best_ca = off; off += (size_t)L.gp * L.s1 * 4;
+    L.node = off; off += (size_t)L.gp * L.s1 * 4;
+    L.xmask = off; off += (size_t)L.gp * L.s1 * 4;
+    L.par = off; off += fs_align16((size_t)L.gp * L.s1);
+  } else {
+    L.sp = off; off += fs_align16((size_t)L.gp * SP_STRIDE * 8);
+    L.pbc = off; off += fs_align16((size_t)(S + 1) * (S + 2) / 2 * 8);
+  }
   L.total = off;
   return L;
 }
 
 // ======================================================================================================
-template <int T>
+// T: actions per lane of the dense engine (four lanes per game); AL > 0 selects the sparse engine (eight lanes
+// per game, AL actions per lane at expansion; clusters of four only)
+template <int T, int AL>
 __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
+  constexpr bool SPARSE = AL > 0;
+  constexpr int LANES = SPARSE ? fs2::L : 4;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k1 = p.k1, cl = p.cl, S = p.S, A = p.A;
@@ -617,7 +674,7 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
   auto canon = [&](int c) { return cl == 2 ? (c < 4 ? 4 * rank + c : 8 + 4 * rank + (c - 4)) : 4 * rank + c; };
   int* const err = p.error_flag;
 
-  const FsLayout L = fs_layout(k1, STAGES, cl, A, S);
+  const FsLayout L = fs_layout(k1, STAGES, cl, A, S, SPARSE);
   uint8_t* sA1 = smem + L.a1;
   uint8_t* sW = smem + L.w;
   uint8_t* sA3 = smem + L.a3;
@@ -651,14 +708,30 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
   sm.depth = smem + L.depth;
   sm.ps = L.ps;
   sm.a4 = L.a4;
+  unsigned long long* exp_tab_w = reinterpret_cast<unsigned long long*>(smem + L.exp_tab);
+  sm.exp_tab = exp_tab_w;
+  for (int i = threadIdx.x; i < 256; i += FS_THREADS) exp_tab_w[i] = mz_exp_tab[i];
+  fs2::Smem sm2;
+  sm2.logit = sm.logit; sm2.val = sm.val; sm2.rew = sm.rew; sm2.mm = sm.mm; sm2.sp = sm.sp;
+  sm2.best_key = reinterpret_cast<unsigned long long*>(smem + L.sp);
+  sm2.best_ca = reinterpret_cast<uint32_t*>(smem + L.best_ca);
+  sm2.node = reinterpret_cast<uint32_t*>(smem + L.node);
+  sm2.xmask = reinterpret_cast<uint32_t*>(smem + L.xmask);
+  sm2.par = smem + L.par;
+  sm2.path_n = sm.path_n; sm2.path_a = sm.path_a; sm2.depth = sm.depth;
+  sm2.ps = L.ps; sm2.a4 = L.a4; sm2.s1 = L.s1;
+  sm2.exp_tab = exp_tab_w;
+  const fs2::Geo geo2 = fs2::geo(S, A);
 
   const uint32_t a1_bytes = (uint32_t)(ROWS * k1 * 2), a3_bytes = (uint32_t)(ROWS * K3 * 2);
   const uint32_t out_bytes = (uint32_t)(GP * (8 + 4 * L.a4));
 
   for (int i = threadIdx.x; i < TAIL_FLOATS; i += FS_THREADS) sTail[i] = p.tail[i];
-  for (int i = threadIdx.x; i < (S + 1) * (S + 1); i += FS_THREADS) {
-    const int N = i / (S + 1), n = i % (S + 1);
-    if (n <= N) pbc_w[(N * (N + 1)) / 2 + n] = p.pb_c[i];
+  if (!SPARSE) {
+    for (int i = threadIdx.x; i < (S + 1) * (S + 1); i += FS_THREADS) {
+      const int N = i / (S + 1), n = i % (S + 1);
+      if (n <= N) pbc_w[(N * (N + 1)) / 2 + n] = p.pb_c[i];
+    }
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
@@ -792,18 +865,20 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
     const int row = quarter * 32 + lane;          // the tile row this thread serves in the epilogues
     const int e = (warp - 2) * 32 + lane;         // 0..255
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    const bool tree_role = e < 4 * GP;
+    const bool tree_role = e < LANES * GP;
     FsGame gm;
-    gm.gl = tree_role ? (e >> 2) : 0;
-    gm.sub = e & 3;
+    gm.gl = tree_role ? (e / LANES) : 0;
+    gm.sub = e % LANES;
     gm.g = tile * ROWS + rank * GP + gm.gl;
     gm.valid = tree_role && gm.g < p.G;
     gm.base = p.games + (size_t)(gm.valid ? gm.g : 0) * p.game_bytes;
+    fs2::Game gm2;
+    gm2.valid = gm.valid; gm2.g = gm.g; gm2.gl = gm.gl; gm2.sub = gm.sub; gm2.base = gm.base;
     const int my_row = rank * GP + gm.gl;         // tile row of the game this lane works on
     const bool stamp = p.timeline && blockIdx.x == 0 && e == 0;
 #define FS_STAMP(sim_, slot_)                                           \
   do {                                                                  \
-    if (stamp) p.timeline[(size_t)(sim_) * 16 + (slot_)] = clock64();   \
+    if (stamp) p.timeline[(size_t)(sim_) * 32 + (slot_)] = clock64();   \
   } while (0)
     // output slots of the game a ROW belongs to (the epilogues send there)
     const uint32_t owner = (uint32_t)(row / GP);
@@ -818,7 +893,10 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
       }
     };
     arm();
-    if (tree_role) fs_set_root<T>(p, sm, gm);
+    if (tree_role) {
+      if constexpr (SPARSE) fs2::set_root<(AL > 0 ? AL : 1)>(p, sm2, gm2, geo2);
+      else fs_set_root<T>(p, sm, gm);
+    }
     __syncwarp();
 
     uint32_t v[32], v2[32];
@@ -859,7 +937,10 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
           fs_wait_cluster(out_full, (sim - 1) & 1, err, 10);
           if (sim < S) arm();
           FS_STAMP(sim - 1, 10);
-          fs_expand_backup<T>(p, sm, gm, sim - 1);
+          if constexpr (SPARSE)
+            fs2::expand_backup<(AL > 0 ? AL : 1)>(p, sm2, gm2, geo2, sim - 1,
+                                                  stamp ? p.timeline + (size_t)(sim - 1) * 32 : nullptr);
+          else fs_expand_backup<T>(p, sm, gm, sim - 1);
           FS_STAMP(sim - 1, 11);
         } else if (sim < S) {
           // (CL = 4: the second epilogue group has no games; thread 0, which arms, is always a tree lane)
@@ -868,7 +949,9 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
       if (sim == S) break;
       if (tree_role) {
         int parent, action;
-        fs_descend<T>(p, sm, gm, sim, parent, action);
+        if constexpr (SPARSE)
+          fs2::descend(p, sm2, gm2, geo2, sim, parent, action, stamp ? p.timeline + (size_t)sim * 32 : nullptr);
+        else fs_descend<T>(p, sm, gm, sim, parent, action);
         FS_STAMP(sim, 1);
         // A1 row of the game: bf16([h (50) | onehot(action) (A) | 1 | 0]) as 16-byte blocks of the canonical
         // K-major image, sent to every CTA that owns a dynamics head (ranks 0 and 1)
@@ -876,16 +959,17 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
         const int kbias = H + A;
         const uint32_t a1_r0 = map_to_cta(smem_u32(sA1), 0), a1_r1 = map_to_cta(smem_u32(sA1), 1);
         const uint32_t bar_r0 = map_to_cta(smem_u32(a1_full), 0), bar_r1 = map_to_cta(smem_u32(a1_full), 1);
-        uint4 blk[3];
+        constexpr int NB = (12 + LANES - 1) / LANES;  // 16-byte blocks of the row per lane (k1 / 8 <= 12)
+        uint4 blk[NB];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int kb = gm.sub + 4 * i;
+        for (int i = 0; i < NB; ++i) {
+          const int kb = gm.sub + LANES * i;
           blk[i] = make_uint4(0u, 0u, 0u, 0u);
           if (kb < k1 / 8 && gm.valid && kb <= 6) blk[i] = ldg16_cg(hrow + 8 * kb);
         }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int kb = gm.sub + 4 * i;
+        for (int i = 0; i < NB; ++i) {
+          const int kb = gm.sub + LANES * i;
           if (kb >= k1 / 8) continue;
           uint4 q = blk[i];
           if (kb >= 6) {
@@ -1037,7 +1121,10 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
         FS_STAMP(sim, 8);
       }
     }
-    if (tree_role) fs_root_stats(p, sm, gm);
+    if (tree_role) {
+      if constexpr (SPARSE) fs2::root_stats(p, sm2, gm2, geo2);
+      else fs_root_stats(p, sm, gm);
+    }
 #undef FS_STAMP
   }
 
@@ -1070,6 +1157,32 @@ __global__ void fs_export_kernel(const uint8_t* games, long long game_bytes, int
   }
 }
 
+__global__ void fs2_export_kernel(const uint8_t* games, long long game_bytes, int S, int A, int game, double* prior,
+                                  int32_t* child, double* vsum, int32_t* visit, float* reward, double* q_out) {
+  const fs2::Geo G = fs2::geo(S, A);
+  const uint8_t* base = games + (size_t)game * game_bytes;
+  const uint32_t legal = *reinterpret_cast<const uint32_t*>(base + 16);
+  for (int i = threadIdx.x; i < (S + 1) * A; i += blockDim.x) {
+    const int n = i / A, a = i % A;
+    if (prior) prior[i] = *reinterpret_cast<const double*>(base + G.pri + ((size_t)n * G.a2 + a) * 8);
+    if (child) child[i] = (n == 0 && !((legal >> a) & 1u)) ? MZ_CHILD_ILLEGAL : MZ_CHILD_UNEXPANDED;
+    if (q_out) q_out[i] = 0.0;
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n <= S; n += blockDim.x) {
+    const uint2 m = *reinterpret_cast<const uint2*>(base + G.meta + 8 * n);
+    const uint4 o = *reinterpret_cast<const uint4*>(base + G.own + 16 * n);
+    if (vsum) vsum[n] = u2d(o.x, o.y);
+    if (reward) reward[n] = __uint_as_float(o.z);
+    if (visit) visit[n] = (int)(m.x & 0xffu);
+    if (n > 0 && (m.x & 0xffu) > 0) {
+      const int par = (int)(m.x >> 24), act = (int)((m.x >> 8) & 0xffu);
+      if (child) child[par * A + act] = n;
+      if (q_out) q_out[par * A + act] = *reinterpret_cast<const double*>(base + G.edge + 16 * n + 8);
+    }
+  }
+}
+
 int fs_k1_for(int A) { return (H + A + 1 + 15) / 16 * 16; }
 constexpr size_t kFsMaxSmem = 232448;
 
@@ -1082,6 +1195,21 @@ int fs_cluster() {
   }
   return g_fs_cluster;
 }
+int g_fs_engine = -1;  // -1: from MZ_FS_ENGINE (default 1 = sparse when the shape allows), 0 dense, 1 sparse
+int fs_engine_pref() {
+  if (g_fs_engine < 0) {
+    const char* e = getenv("MZ_FS_ENGINE");
+    g_fs_engine = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  return g_fs_engine;
+}
+int fs_stages(int cl);
+bool fs_sparse_ok(int cl, int S, int A) {
+  if (cl != 4 || S > fs2::MAX_S) return false;
+  return fs_layout(fs_k1_for(A), fs_stages(cl), cl, A, S, true).total <= kFsMaxSmem;
+}
+bool fs_use_sparse(int cl, int S, int A) { return fs_engine_pref() == 1 && fs_sparse_ok(cl, S, A); }
+
 int fs_stages(int cl) {
   const char* e = getenv("MZ_FS_STAGES");
   const int v = e ? atoi(e) : 0;
@@ -1089,11 +1217,11 @@ int fs_stages(int cl) {
   return cl == 4 ? 4 : 3;
 }
 
-template <int T>
+template <int T, int AL>
 int fs_launch(const FsParams& p, size_t smem, void* stream) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(fc_search_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFsMaxSmem);
+    cudaError_t e = cudaFuncSetAttribute(fc_search_kernel<T, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFsMaxSmem);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
@@ -1110,7 +1238,7 @@ int fs_launch(const FsParams& p, size_t smem, void* stream) {
   lattr[0].val.clusterDim.z = 1;
   cfg.attrs = lattr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, fc_search_kernel<T>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fc_search_kernel<T, AL>, p);
   if (e != cudaSuccess) return (int)e;
   MZ_LAUNCH_CHECK();
   return MZ_OK;
@@ -1131,10 +1259,18 @@ int32_t mz_fc_search_node_bytes(int32_t A) {
   return (FS_PQ + 16 * A + 63) / 64 * 64;
 }
 
-int64_t mz_fc_search_game_bytes(int32_t S, int32_t A) {
+int64_t mz_fc_search_game_bytes(int32_t S, int32_t A) {  // large enough for either engine's layout
   if (A < 1 || A > 32 || S < 1 || S > 253) return MZ_ERR_UNSUPPORTED;
-  const int64_t b = FS_HDR + (int64_t)(S + 1) * mz_fc_search_node_bytes(A);
-  return (b + 127) / 128 * 128;
+  int64_t b = FS_HDR + (int64_t)(S + 1) * mz_fc_search_node_bytes(A);
+  b = (b + 127) / 128 * 128;
+  const int64_t b2 = fs2::geo(S, A).bytes;
+  return b > b2 ? b : b2;
+}
+
+int mz_fc_search_set_engine(int32_t engine) {
+  if (engine < -1 || engine > 1) return MZ_ERR_BAD_ARG;
+  g_fs_engine = engine;
+  return MZ_OK;
 }
 
 int32_t mz_fc_search_pool_row(void) { return POOL_ROW; }
@@ -1142,7 +1278,8 @@ int32_t mz_fc_search_pool_row(void) { return POOL_ROW; }
 int mz_fc_search_supported(int32_t S, int32_t A) {
   if (A < 1 || A > 32 || S < 1 || S > 253) return 0;
   const int cl = fs_cluster();
-  const FsLayout L = fs_layout(fs_k1_for(A), fs_stages(cl), cl, A, S);
+  if (fs_use_sparse(cl, S, A)) return 1;
+  const FsLayout L = fs_layout(fs_k1_for(A), fs_stages(cl), cl, A, S, false);
   return L.total <= kFsMaxSmem ? 1 : 0;
 }
 
@@ -1199,22 +1336,35 @@ int mz_fc_search(const mz_fc_search_args* a, void* stream) {
   p.rec_logits = a->rec_logits;
   p.timeline = (long long*)a->timeline;
   p.error_flag = a->error_flag;
-  const FsLayout L = fs_layout(p.k1, p.stages, p.cl, p.A, p.S);
+  const bool sparse = fs_use_sparse(p.cl, p.S, p.A);
+  const FsLayout L = fs_layout(p.k1, p.stages, p.cl, p.A, p.S, sparse);
   if (L.total > kFsMaxSmem) return MZ_ERR_UNSUPPORTED;
+  if (sparse) {
+    const int AL = (p.A + fs2::L - 1) / fs2::L;
+    if (AL <= 1) return fs_launch<1, 1>(p, L.total, stream);
+    if (AL <= 2) return fs_launch<1, 2>(p, L.total, stream);
+    if (AL <= 3) return fs_launch<1, 3>(p, L.total, stream);
+    return fs_launch<1, 4>(p, L.total, stream);
+  }
   const int T = (p.A + 3) / 4;
-  if (T <= 1) return fs_launch<1>(p, L.total, stream);
-  if (T <= 2) return fs_launch<2>(p, L.total, stream);
-  if (T <= 3) return fs_launch<3>(p, L.total, stream);
-  if (T <= 5) return fs_launch<5>(p, L.total, stream);
-  return fs_launch<8>(p, L.total, stream);
+  if (T <= 1) return fs_launch<1, 0>(p, L.total, stream);
+  if (T <= 2) return fs_launch<2, 0>(p, L.total, stream);
+  if (T <= 3) return fs_launch<3, 0>(p, L.total, stream);
+  if (T <= 5) return fs_launch<5, 0>(p, L.total, stream);
+  return fs_launch<8, 0>(p, L.total, stream);
 }
 
 int mz_fc_search_export(const mz_fc_search_args* a, int32_t game, double* prior, int32_t* child, double* vsum,
                         int32_t* visit, float* reward, double* q, void* stream) {
   if (!a || !a->games || !a->weights || game < 0 || game >= a->num_games) return MZ_ERR_BAD_ARG;
-  fs_export_kernel<<<4, 128, 0, (cudaStream_t)stream>>>(a->games, a->game_bytes, a->node_bytes, a->num_simulations,
-                                                        a->weights->num_actions, game, prior, child, vsum, visit,
-                                                        reward, q);
+  if (fs_use_sparse(fs_cluster(), a->num_simulations, a->weights->num_actions))
+    fs2_export_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a->games, a->game_bytes, a->num_simulations,
+                                                           a->weights->num_actions, game, prior, child, vsum, visit,
+                                                           reward, q);
+  else
+    fs_export_kernel<<<4, 128, 0, (cudaStream_t)stream>>>(a->games, a->game_bytes, a->node_bytes, a->num_simulations,
+                                                          a->weights->num_actions, game, prior, child, vsum, visit,
+                                                          reward, q);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }

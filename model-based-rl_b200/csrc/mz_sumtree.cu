@@ -165,17 +165,24 @@ int mz_sumtree_update(double* tree, int64_t max_capacity, int64_t n, const int64
   return MZ_OK;
 }
 
-int mz_sumtree_add(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
-                   const double* priority, int64_t chunk_start, int32_t chunk_len, int64_t* slot_pos,
-                   int64_t* slot_start, int32_t* slot_len, double* scratch, void* stream) {
+int mz_sumtree_add_from(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
+                        const double* priority, int64_t chunk_start, int32_t chunk_len, int32_t first_step,
+                        int64_t* slot_pos, int64_t* slot_start, int32_t* slot_len, double* scratch, void* stream) {
   if (n > 0 && (!slot_pos || !slot_start || !slot_len)) return MZ_ERR_BAD_ARG;
-  if (n > chunk_len) return MZ_ERR_BAD_ARG;
+  if (first_step < 0 || n + first_step > chunk_len) return MZ_ERR_BAD_ARG;
   const int rc = mz_sumtree_update(tree, max_capacity, n, tree_idx, priority, scratch, stream);
   if (rc != MZ_OK || n == 0) return rc;
   sumtree_slots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (int)n, tree_idx, max_capacity - 1, chunk_start, chunk_len, slot_pos, slot_start, slot_len, 0);
+      (int)n, tree_idx, max_capacity - 1, chunk_start, chunk_len, slot_pos, slot_start, slot_len, first_step);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
+}
+
+int mz_sumtree_add(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
+                   const double* priority, int64_t chunk_start, int32_t chunk_len, int64_t* slot_pos,
+                   int64_t* slot_start, int32_t* slot_len, double* scratch, void* stream) {
+  return mz_sumtree_add_from(tree, max_capacity, n, tree_idx, priority, chunk_start, chunk_len, 0, slot_pos,
+                             slot_start, slot_len, scratch, stream);
 }
 
 int mz_sumtree_sample(const double* tree, int64_t max_capacity, int32_t n, const double* u01,

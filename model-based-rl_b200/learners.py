@@ -17,6 +17,8 @@ What runs where:
 
 There is no CPU fallback: the loss needs the CUDA library.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -143,11 +145,12 @@ class UnrollLoss(torch.autograd.Function):
     rows = torch.empty((3, B), dtype=torch.float64, device=dev)
     losses = torch.empty(3, dtype=torch.float64, device=dev)
     new_errors = torch.empty(B, dtype=torch.float32, device=dev)
-    _lib.check(_lib.load().mz_unroll_loss(
-        c, _lib.ptr(value_logits), _lib.ptr(reward_logits), _lib.ptr(policy_logits), _lib.ptr(t_values),
-        _lib.ptr(t_rewards), _lib.ptr(t_policies), _lib.ptr(is_weights), _lib.ptr(d_v), _lib.ptr(d_r),
-        _lib.ptr(d_p), _lib.ptr(rows), _lib.ptr(losses), _lib.ptr(new_errors), _lib.current_stream()),
-               "mz_unroll_loss")
+    with torch.cuda.device(dev):  # the launch goes to the logits' GPU, whatever the caller's current device is
+      _lib.check(_lib.load().mz_unroll_loss(
+          c, _lib.ptr(value_logits), _lib.ptr(reward_logits), _lib.ptr(policy_logits), _lib.ptr(t_values),
+          _lib.ptr(t_rewards), _lib.ptr(t_policies), _lib.ptr(is_weights), _lib.ptr(d_v), _lib.ptr(d_r),
+          _lib.ptr(d_p), _lib.ptr(rows), _lib.ptr(losses), _lib.ptr(new_errors), _lib.current_stream()),
+                 "mz_unroll_loss")
     ctx.save_for_backward(d_v, d_r, d_p)
     ctx.mark_non_differentiable(new_errors)
     return losses, new_errors
@@ -310,12 +313,22 @@ class Learner(object):
     if self.replay_buffer is not None and 'total_frames' in state:
       self.replay_buffer.add_initial_throughput(state['total_frames'], state['total_games'])
 
-  def save_state(self):
-    state = {'weights': self.network.get_weights(), 'optimizer': self.optimizer.state_dict(),
-             'training_step': self.training_step}
-    if self.replay_buffer is not None:
-      tp = self.replay_buffer.get_throughput()
-      state.update(total_frames=tp['frames'], total_games=tp['games'])
+  def save_state(self, path=None, actor_games=None, dirs=None):
+    """The checkpoint dictionary of learners.py:72-83 with every key the reference's tooling reads
+    (evaluate.py: `config`, `weights`; actors.py:75-79: `actor_games[actor_key]`; learners.py:62-70:
+    `optimizer`, `training_step`, `total_frames`, `total_games`).  `actor_games` is the per-actor game counter
+    SharedStorage keeps in the reference (default: the attribute set by the self-play driver, else empty);
+    `dirs` the logger's directory table.  Written with torch.save when `path` is given (the reference saves to
+    dirs['saves']/<training_step>)."""
+    tp = self.replay_buffer.get_throughput() if self.replay_buffer is not None else {'frames': 0, 'games': 0}
+    state = {'dirs': dict(dirs if dirs is not None else getattr(self, 'dirs', {}) or {}),
+             'config': self.config,
+             'weights': self.network.get_weights(), 'optimizer': self.optimizer.state_dict(),
+             'training_step': self.training_step, 'total_games': tp['games'], 'total_frames': tp['frames'],
+             'actor_games': dict(actor_games if actor_games is not None else getattr(self, 'actor_games', {}) or {})}
+    if path is not None:
+      torch.save(state, path)
+    self.last_saved_state = state
     return state
 
   def send_weights(self):
@@ -436,10 +449,21 @@ class Learner(object):
     """The loop of learners.py:116-148 for `training_steps` steps (default config.training_steps)."""
     steps = self.config.training_steps if training_steps is None else training_steps
     self.send_weights()
+    # learners.py:119-120: training starts once the replay buffer holds `stored_before_train` memories.  The
+    # reference polls a buffer that actor processes fill concurrently; here the caller fills it (or runs the
+    # self-play driver between calls), so an under-filled buffer is an error, not a wait that cannot end
+    need = int(getattr(self.config, 'stored_before_train', 0) or 0)
+    if self.replay_buffer.size() < need:
+      raise RuntimeError("replay buffer holds %d memories, config.stored_before_train is %d" %
+                         (self.replay_buffer.size(), need))
+    save_every = int(getattr(self.config, 'save_state_frequency', 0) or 0)
     end = self.training_step + steps
     while self.training_step < end:
       self.update_weights(self.replay_buffer.sample_batch())
       self.training_step += 1
       if self.training_step % self.config.send_weights_frequency == 0:
         self.send_weights()
+      if save_every and self.training_step % save_every == 0:  # learners.py:135-136
+        saves = (getattr(self, 'dirs', None) or {}).get('saves')
+        self.save_state(os.path.join(saves, str(self.training_step)) if saves else None)
     return self.training_step

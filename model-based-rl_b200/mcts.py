@@ -184,6 +184,7 @@ class BatchedMCTS(object):
       return None, None, None
     return tuple(_lib.ptr(t[sim]) for t in self.trace)
 
+  @_lib.on_device
   def set_root(self, root_logits, legal_mask=None, noise=None, noise_frac=0.25, to_play=None,
                root_hidden=None):
     """Node.expand over legal actions + add_exploration_noise + MinMaxStats.reset for all games."""
@@ -197,6 +198,7 @@ class BatchedMCTS(object):
                                          _lib.ptr(noise), float(noise_frac), _lib.ptr(to_play),
                                          _lib.ptr(root_hidden), self._stream()), "mz_tree_set_root")
 
+  @_lib.on_device
   def set_root_priors(self, root_priors, legal_mask=None, to_play=None, root_hidden=None):
     root_priors = self._dev(root_priors, torch.float64, (self.G, self.A))
     legal_mask = self._mask(legal_mask)
@@ -208,17 +210,20 @@ class BatchedMCTS(object):
                                                 _lib.ptr(root_hidden), self._stream()),
                "mz_tree_set_root_priors")
 
+  @_lib.on_device
   def select(self, sim, gather=True):
     tp, ta, td = self._trace_ptrs(sim)
     g = self.gathered if gather else None
     _lib.check(self.lib.mz_tree_select(self.tree, int(sim), _lib.ptr(g), tp, ta, td, self._stream()),
                "mz_tree_select")
 
+  @_lib.on_device
   def expand_backup(self, sim, value, reward, logits, new_hidden=None):
     _lib.check(self.lib.mz_tree_expand_backup(self.tree, int(sim), _lib.ptr(value), _lib.ptr(reward),
                                               _lib.ptr(logits), _lib.ptr(new_hidden), self._stream()),
                "mz_tree_expand_backup")
 
+  @_lib.on_device
   def step(self, sim, value=None, reward=None, logits=None, new_hidden=None, gather=False):
     """expand+backup of `sim` fused with the descent of sim + 1 (sim = -1: first descent only)."""
     tp, ta, td = self._trace_ptrs(sim + 1)
@@ -227,6 +232,7 @@ class BatchedMCTS(object):
                                      _lib.ptr(logits), _lib.ptr(new_hidden), _lib.ptr(g), tp, ta, td,
                                      self._stream()), "mz_tree_step")
 
+  @_lib.on_device
   def root_stats(self):
     """visits [G,A] i32, child_visits [G,A] f64 (game.py:107-110), root_value [G] f64, minmax."""
     _lib.check(self.lib.mz_tree_root_stats(self.tree, _lib.ptr(self.visits),
@@ -235,6 +241,7 @@ class BatchedMCTS(object):
                "mz_tree_root_stats")
     return self.visits, self.child_visits, self.root_value, self.minmax
 
+  @_lib.on_device
   def select_action(self, temperature, uniforms, legal_mask=None, visits=None):
     """Config.select_action (config.py:70-81) for every game; randomness is host supplied."""
     visits = self.visits if visits is None else visits
@@ -247,6 +254,7 @@ class BatchedMCTS(object):
                                          _lib.ptr(self.actions), self._stream()), "mz_select_action")
     return self.actions
 
+  @_lib.on_device
   def export_game(self, game):
     """Dense copy of one game's tree (debug / Node façade)."""
     S, A, dev = self.S, self.A, self.device
@@ -262,6 +270,7 @@ class BatchedMCTS(object):
                 visit=visit.cpu().numpy(), reward=reward.cpu().numpy())
 
   # -- generic search loop: any network with the reference interface -----------------------------
+  @_lib.on_device
   def search(self, network, root_logits, root_hidden, legal_mask=None, noise=None, noise_frac=0.25,
              to_play=None, root_priors=None):
     """MCTS.run (mcts.py:78-102) for all games, driving `network.recurrent_inference` with batch G.

@@ -128,12 +128,18 @@ class MuZeroNetwork(object):
     self.launches = 0  # kernels of csrc/mz_conv_tc.cu launched so far
 
   # -- weights -----------------------------------------------------------------------------------
+  @_lib.on_device
   def load_weights(self, weights):
     """Accepts the reference's state dict (networks.py:549-550); folds BatchNorm (eval statistics)
     into the convolutions and packs everything for the tensor-core kernels."""
     dev = self.device
     sd = {k: torch.as_tensor(v).detach() for k, v in weights.items()}
-    self._state = {k: v.to(dev) for k, v in sd.items()}
+    # a snapshot (the reference hands weights over as `.cpu()` copies, networks.py:36-40): later in-place
+    # changes of the caller's tensors must not reach the search network
+    self._state = {k: v.to(dev, copy=True) for k, v in sd.items()}
+    # the packed tensors below are rebuilt: anything that captured their addresses (ConvSearch's CUDA graph)
+    # must be re-captured -- engines compare this counter before every move
+    self.weights_version = getattr(self, 'weights_version', 0) + 1
 
     def bn(p):
       return (sd[p + '.weight'], sd[p + '.bias'], sd[p + '.running_mean'], sd[p + '.running_var'])
@@ -467,6 +473,9 @@ class ConvSearch(object):
     if not self.use_graph:
       self._enqueue()
       return
+    if getattr(self, '_graph_weights', None) != getattr(self.net, 'weights_version', 0):
+      self.graph = None  # load_weights rebuilt the packed weights: the captured addresses are stale
+      self._graph_weights = getattr(self.net, 'weights_version', 0)
     if self.graph is None:
       self._enqueue()  # warm-up outside capture (cudaFuncSetAttribute, lazy module loading)
       torch.cuda.synchronize()
@@ -475,6 +484,7 @@ class ConvSearch(object):
         self._enqueue()
     self.graph.replay()
 
+  @_lib.on_device
   def search(self, observation, noise=None, uniforms=None, temperature=None):
     """observation [G, C, 96, 96] (device or host); returns device tensors (actions [G] i32,
     root_value [G] f64, child_visits [G, A] f64, initial value [G] f32)."""
@@ -491,6 +501,7 @@ class ConvSearch(object):
     return eng.actions, eng.root_value, eng.child_visits, self.init_value
 
 
+  @_lib.on_device
   def search_host(self, obs, noise=None, uniforms=None, temperature=None, legal=None, to_play=None):
     """Same call as `FCSearch.search_host` (networks.py), so `selfplay.BatchedActor(search=...)` drives either
     engine: HOST arrays in -- frames [G, C, 96, 96] float32, Dirichlet noise [G, A] float64 (row g: one value

@@ -66,6 +66,7 @@ class FCNetwork(object):
     self.weights = None   # _lib.FcWeights
 
   # -- weights -----------------------------------------------------------------------------------
+  @_lib.on_device
   def load_weights(self, weights):
     """Accepts the reference's state dict (networks.py:176-177).
 
@@ -150,6 +151,7 @@ class FCNetwork(object):
     return self
 
   # -- inference ---------------------------------------------------------------------------------
+  @_lib.on_device
   def initial_inference(self, observation, hidden_out=None, hidden_stride=None):
     """BaseNetwork.initial_inference (networks.py:26-29).  observation [B, input_dim] float32."""
     obs = observation.to(self.device, torch.float32).reshape(observation.shape[0], -1).contiguous()
@@ -174,6 +176,7 @@ class FCNetwork(object):
     return self.lib.mz_fc_initial_f32, (self.weights, B, P(obs), P(hidden_out), int(hidden_stride),
                                         P(value), P(logits), stream)
 
+  @_lib.on_device
   def recurrent_inference(self, hidden_state, action):
     """BaseNetwork.recurrent_inference (networks.py:31-34).  `action`: B ints (list or tensor)."""
     h = hidden_state.to(self.device, torch.float32).contiguous()
@@ -336,8 +339,8 @@ class _FusedEngine(object):
     a.rec_value, a.rec_reward, a.rec_logits = (t.data_ptr() for t in self.record)
 
   def enable_timeline(self):
-    """clock64 stamps of tile 0's phases, [S, 16] int64 (diagnostics; see csrc/mz_fcsearch.cu FS_STAMP)."""
-    self.timeline = torch.zeros((self.S, 16), dtype=torch.int64, device=self.net.device)
+    """clock64 stamps of tile 0's phases, [S, 32] int64 (diagnostics; see csrc/mz_fcsearch.cu FS_STAMP)."""
+    self.timeline = torch.zeros((self.S, 32), dtype=torch.int64, device=self.net.device)
     self.args.timeline = self.timeline.data_ptr()
 
   def export_game(self, game):
@@ -401,7 +404,7 @@ class FCSearch(object):
     self.__dict__.update(views)
     self._out_dev, views = _carve(self._out_specs, device=dev)
     self.__dict__.update(views)
-    self.legal.fill_((1 << A) - 1)
+    self.legal.fill_(_all_legal(A))
     self.to_play.fill_(1)
     self.temperature.fill_(1.0)
     self.root_logits = torch.zeros((G, A), dtype=torch.float32, device=dev)
@@ -491,6 +494,7 @@ class FCSearch(object):
       main.wait_event(done)
     self.launches_per_move = n
 
+  @_lib.on_device
   def run(self):
     """One move for all games with inputs already in the device staging buffers."""
     if not self.use_graph:
@@ -512,7 +516,7 @@ class FCSearch(object):
       self._out_host, out = _carve(self._out_specs, pin_memory=True)
       h.update(out)
       h['obs'] = torch.zeros((self.G, self.net.input_dim), dtype=torch.float32, pin_memory=True)
-      h['legal'].fill_((1 << self.A) - 1)
+      h['legal'].fill_(_all_legal(self.A))
       h['to_play'].fill_(1)
       h['temperature'].fill_(1.0)
       self._h = h
@@ -525,6 +529,7 @@ class FCSearch(object):
     h = self._pinned()
     return {name: h[name] for name, _, _ in self._in_specs}
 
+  @_lib.on_device
   def search_pinned(self):
     """search_host for inputs already written into `pinned_inputs()` (byte observations): ONE
     host->device copy of the input blob, normalisation + the move's graph, ONE device->host copy of the
@@ -540,6 +545,7 @@ class FCSearch(object):
     torch.cuda.current_stream().synchronize()
     return h['actions'], h['root_value'], h['child_visits'], h['init_value']
 
+  @_lib.on_device
   def search_host(self, obs, noise=None, uniforms=None, temperature=None, legal=None, to_play=None):
     """The per-move body of Actor.play_game (actors.py:131-153) for G games.
 
@@ -600,6 +606,11 @@ class FCSearch(object):
 
   def h2d_blob_bytes(self):
     return self._in_dev.numel()
+
+
+def _all_legal(A):
+  """int32 bit mask with the low A bits set (A = 32: all ones = -1 as a signed word)."""
+  return -1 if A >= 32 else (1 << A) - 1
 
 
 def _carve(specs, **alloc):

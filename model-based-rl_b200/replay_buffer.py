@@ -38,15 +38,18 @@ class RingCursor(object):
     self.position = 0
 
   def take(self, n):
-    """Slots of the next n memories, in order."""
+    """Slots of the next n memories, in order (one arange per stretch up to the next wrap of the ring)."""
     slots = np.empty(n, np.int64)
-    for i in range(n):
-      pos = self.position
-      slots[i] = pos
-      if pos >= self.prev_capacity:
-        self.num_memories += 1
-      self.position = (pos + 1) % self.capacity
-      if self.position == 0:
+    done = 0
+    while done < n:
+      run = min(n - done, self.capacity - self.position)
+      slots[done:done + run] = np.arange(self.position, self.position + run)
+      # slots at or beyond the previous capacity are new memories (replay_buffer.py:27-28)
+      self.num_memories += max(0, self.position + run - max(self.position, self.prev_capacity))
+      self.position += run
+      done += run
+      if self.position == self.capacity:  # wrapped: the ring grows by one step (replay_buffer.py:30-33)
+        self.position = 0
         self.prev_capacity = self.capacity
         self.capacity = min(self.max_capacity, self.capacity + self.capacity_step)
     return slots
@@ -81,21 +84,41 @@ class ReplayIndex(object):
     return idx, pri, torch.empty_like(pri)
 
   def add(self, priorities, chunk_id, chunk_start, chunk_len):
-    """SumTree.add (replay_buffer.py:19-33); returns the chunk ids whose slots were overwritten."""
+    """SumTree.add (replay_buffer.py:19-33); returns the chunk id every overwritten slot used to refer to
+    (with multiplicity, this chunk's own id included when one add laps the ring).
+
+    A history with more memories than the ring currently holds wraps it, so the same slot appears more
+    than once in the add.  The reference writes one memory at a time -- the last write to a slot wins and
+    every earlier one is an ordinary overwrite -- so the add is applied in pieces without repeated slots."""
     n = len(priorities)
     if n == 0:
       return []
     slots = self.ring.take(n)
-    old = self.slot_chunk[slots]
-    self.slot_chunk[slots] = chunk_id
-    idx, pri, scratch = self._stage(slots + self.max_capacity - 1, priorities)
-    _lib.check(self.lib.mz_sumtree_add(_lib.ptr(self.tree), self.max_capacity, n, _lib.ptr(idx),
-                                       _lib.ptr(pri), int(chunk_start), int(chunk_len),
-                                       _lib.ptr(self.slot_pos), _lib.ptr(self.slot_start),
-                                       _lib.ptr(self.slot_len), _lib.ptr(scratch),
-                                       _lib.current_stream()), "mz_sumtree_add")
-    return [int(c) for c in old if c >= 0]
+    pri_all = np.ascontiguousarray(priorities, np.float64)
+    overwritten = []
+    lo = 0
+    while lo < n:
+      # longest run from `lo` without a repeated slot
+      seg = slots[lo:]
+      _, first = np.unique(seg, return_index=True)
+      repeat = np.ones(seg.size, bool)
+      repeat[first] = False
+      rep = np.nonzero(repeat)[0]
+      hi = lo + (int(rep[0]) if rep.size else seg.size)
+      piece = slots[lo:hi]
+      old = self.slot_chunk[piece]
+      overwritten.extend(int(c) for c in old if c >= 0)
+      self.slot_chunk[piece] = chunk_id
+      idx, pri, scratch = self._stage(piece + self.max_capacity - 1, pri_all[lo:hi])
+      _lib.check(self.lib.mz_sumtree_add_from(_lib.ptr(self.tree), self.max_capacity, hi - lo, _lib.ptr(idx),
+                                              _lib.ptr(pri), int(chunk_start), int(chunk_len), lo,
+                                              _lib.ptr(self.slot_pos), _lib.ptr(self.slot_start),
+                                              _lib.ptr(self.slot_len), _lib.ptr(scratch),
+                                              _lib.current_stream()), "mz_sumtree_add_from")
+      lo = hi
+    return overwritten
 
+  @_lib.on_device
   def update(self, tree_idx, priorities):
     """SumTree.update for a batch, in order (replay_buffer.py:200-203)."""
     if len(tree_idx) == 0:
@@ -190,6 +213,7 @@ class PrioritizedReplay(object):
   def get_priorities(self, errors):
     return np.power((np.abs(errors) + self.epsilon), self.alpha)
 
+  @_lib.on_device
   def save_history(self, history, ignore=None, terminal=False):
     """replay_buffer.py:113-122.  `history` has the HistorySlice fields (game.py:5-16)."""
     if ignore is not None:
@@ -203,6 +227,8 @@ class PrioritizedReplay(object):
       cid = self._next_chunk
       self._next_chunk += 1
       self._chunks.append((cid, start, n))
+      # liveness = sum-tree slots that refer to the chunk: every memory of this history takes one, every
+      # overwritten slot gives one back (to an older chunk, or to this one when the add laps the ring)
       self._live[cid] = len(priorities)
       for old in self.index.add(priorities, cid, start, n):
         if old in self._live:
@@ -211,6 +237,7 @@ class PrioritizedReplay(object):
     if terminal:
       self.throughput['games'] += 1
 
+  @_lib.on_device
   def sample_batch(self):
     """replay_buffer.py:124-163 with numpy outputs like the reference: same draws from `random` and
     `np.random` in the same order (one random() per row, one randint per padded action)."""
@@ -242,6 +269,7 @@ class PrioritizedReplay(object):
     batch = (obs, actions.tolist(), (t_rewards, t_values, t_policies))
     return batch, h_idx.tolist(), is_weights
 
+  @_lib.on_device
   def sample_batch_device(self, fuse_supports=True):
     """Same sampling with nothing leaving the GPU and no host synchronisation: returns
     ((obs, actions [B,K] i32, t_rewards, t_values, t_policies[, value_support, reward_support]),
@@ -256,6 +284,7 @@ class PrioritizedReplay(object):
     out = self._targets(pos, cstart, clen, pads, fuse_supports)
     return tuple(out), idx, isw
 
+  @_lib.on_device
   def update(self, idxs, errors):
     """replay_buffer.py:200-203.  `idxs` may be the list `sample_batch` returned or the CUDA tensor
     of `sample_batch_device`; `errors` a numpy array (learners.py:183) or a CUDA tensor."""

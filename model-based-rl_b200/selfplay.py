@@ -116,13 +116,13 @@ class BatchedActor(object):
       g.errors.append(float(errors[i]))
       # Game.apply (game.py:75-104)
       g.steps.append(g.step)
-      g.sum_rewards += int(reward[i])
+      g.sum_rewards += reward[i].item() if hasattr(reward[i], 'item') else reward[i]  # game.py:85
       g.step = int(env.elapsed[i])
       g.history_idx += 1
       g.observations.append(next_obs[i])
       g.actions.append(int(actions[i]))
       g.dones.append(bool(done[i]))
-      g.rewards.append(int(reward[i]))
+      g.rewards.append(reward[i].item() if hasattr(reward[i], 'item') else reward[i])  # the raw env reward, game.py:97
       g.to_play_hist.append(g.to_play)
       if cfg.two_players:
         g.to_play *= -1

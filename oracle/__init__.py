@@ -208,3 +208,18 @@ def inverse_transform(logits, mn, mx, no_target_transform=False):
   for b in range(B):
     out[b, 0] = lib().orc_inverse_transform(_p(logits[b]), mn, mx, int(no_target_transform))
   return out
+
+
+def inverse_transform_f64(logits, mn, mx, no_target_transform=False):
+  """Config.inverse_transform (config.py:27-33) evaluated in binary64 from the float32 logits: the value the
+  float32 pipelines (torch's and the CUDA kernel's) approximate.  h^-1 cancels catastrophically in float32
+  (sqrt(1 + 4 eps (|x| + 1 + eps)) - 1 with eps = 0.001), so two correct float32 implementations differ by up to
+  ~5e-4; this restatement says which side is closer to the exact result."""
+  z = np.asarray(logits, np.float64)
+  e = np.exp(z - z.max(axis=1, keepdims=True))
+  p = e / e.sum(axis=1, keepdims=True)
+  x = (p * np.arange(mn, mx + 1, dtype=np.float64)).sum(axis=1)
+  if no_target_transform:
+    return x
+  eps = 0.001
+  return np.sign(x) * (((np.sqrt(1 + 4 * eps * (np.abs(x) + 1 + eps)) - 1) / (2 * eps))**2 - 1)

@@ -532,6 +532,36 @@ def gen_muzero():
         rec.reward.flatten().tolist(), "hidden mean", float(rec.hidden_state.mean()))
 
 
+def gen_muzero_wide():
+  """The benchmarked towers: C_in = 32 (stack_obs = 32) and C_in = 64 (with stack_actions, utils.py:28-32),
+  batch 8.  The observations are not stored (9-19 MB): the test redraws them from the same seeded CPU generator."""
+  from oracle import muzero_ref
+  A, B = 18, 8
+  for C_in in (32, 64):
+    seed = 20261017 + C_in
+    cfg = make_config(action_space=A)
+    net = ref_networks.MuZeroNetwork(C_in, A, "cpu", cfg)
+    net.load_state_dict(muzero_ref.seeded_state_dict(C_in, A, seed))
+    net.eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    obs = torch.rand((B, C_in, 96, 96), generator=g)
+    actions, actions2 = [3, 17, 0, 9, 11, 5, 2, 8], [0, 9, 4, 4, 16, 1, 13, 7]
+    with torch.inference_mode():
+      init = net.initial_inference(obs)
+      rec = net.recurrent_inference(init.hidden_state, actions)
+      rec2 = net.recurrent_inference(rec.hidden_state, actions2)
+    np.savez_compressed(
+        os.path.join(HERE, "muzero_net_c%d.npz" % C_in), input_channels=np.int32(C_in), action_space=np.int32(A),
+        seed=np.int64(seed), batch=np.int32(B), obs_checksum=np.float64(obs.double().sum().item()),
+        actions=np.array(actions, np.int32), actions2=np.array(actions2, np.int32),
+        init_hidden=init.hidden_state.numpy(), init_logits=init.policy_logits.numpy(), init_value=init.value.numpy(),
+        rec_hidden=rec.hidden_state.numpy(), rec_logits=rec.policy_logits.numpy(),
+        rec_value=rec.value.numpy(), rec_reward=rec.reward.numpy(),
+        rec2_hidden=rec2.hidden_state.numpy(), rec2_logits=rec2.policy_logits.numpy(),
+        rec2_value=rec2.value.numpy(), rec2_reward=rec2.reward.numpy())
+    print("muzero wide", C_in, "value range", float(rec.value.abs().max()), float(rec2.value.abs().max()))
+
+
 def gen_selfplay():
   """Self-play of Tic-Tac-Toe: the move body and the history hand-off of Actor.play_game
   (actors.py:125-176) restated around the reference's Game, TicTacToe, Node, MCTS and
@@ -738,6 +768,9 @@ if __name__ == "__main__":
   if len(sys.argv) > 1 and sys.argv[1] == "selfplay":
     gen_selfplay()
     sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == "muzero_wide":
+    gen_muzero_wide()
+    sys.exit(0)
   if len(sys.argv) > 1 and sys.argv[1] == "clip":
     gen_replay_clip()
     sys.exit(0)
@@ -754,4 +787,5 @@ if __name__ == "__main__":
   gen_selfplay()
   gen_learner()
   gen_replay_clip()
+  gen_muzero_wide()
   print("python", sys.version.split()[0], "numpy", np.__version__, "torch", torch.__version__)

@@ -219,15 +219,25 @@ def test_pool_gather_scatter_and_fc_heads():
   assert torch.allclose(sc, want_sc, rtol=1e-4, atol=1e-4)
 
 
-def test_network_matches_reference_golden():
-  """Whole network: initial_inference + two recurrent_inference steps on the golden weights."""
+@pytest.mark.parametrize("fixture", ["muzero_net", "muzero_net_c32", "muzero_net_c64"])
+def test_network_matches_reference_golden(fixture):
+  """Whole network against outputs of the reference's own MuZeroNetwork class (eval mode): initial_inference +
+  two recurrent_inference steps.  muzero_net: C_in = 4, B = 2; muzero_net_c32 / _c64: the benchmarked towers
+  (stack_obs = 32, and 64 planes with stack_actions, utils.py:28-32) at B = 8, observations redrawn from the
+  fixture's seeded generator."""
   from model_based_rl_b200.muzero import MuZeroNetwork
   from oracle import muzero_ref
-  g = load("muzero_net")
+  g = load(fixture)
   C_in, A = int(g["input_channels"]), int(g["action_space"])
   net = MuZeroNetwork(C_in, A, "cuda", CFG)
   net.load_weights(muzero_ref.seeded_state_dict(C_in, A, int(g["seed"])))
-  init = net.initial_inference(torch.from_numpy(g["obs"]))
+  if "obs" in g:
+    obs = torch.from_numpy(g["obs"])
+  else:
+    gen = torch.Generator().manual_seed(int(g["seed"]) + 1)
+    obs = torch.rand((int(g["batch"]), C_in, 96, 96), generator=gen)
+    assert float(obs.double().sum().item()) == float(g["obs_checksum"])
+  init = net.initial_inference(obs)
   # representation: float32 stem, then 22 residual blocks in bf16 on the tensor cores
   err = np.abs(init.hidden_state.cpu().numpy() - g["init_hidden"])
   print("init_hidden", float(err.max()), float(err.mean()))
@@ -254,8 +264,16 @@ def test_network_matches_reference_golden():
   assert report["rec2_hidden"][0] < 0.06 and report["rec2_hidden"][1] < 0.01
   for k in ("init_logits", "rec_logits", "rec2_logits"):
     assert report[k][0] < 0.15, (k, report[k])
-  for k in ("init_value", "rec_value", "rec2_value", "rec_reward", "rec2_reward"):
-    assert report[k][0] < 0.3, (k, report[k])
+  # scalars: the network's error lives in support space (softmax expectation over the 31 bins: logit errors of
+  # ~0.03 move it by up to ~0.05) and h^-1 stretches it by dh^-1/dx ~ 2 sqrt(|v| + 1) (7.7 at |v| = 14), so the bar
+  # is stated where it is uniform: |h(got) - h(want)| < 0.06 with h = Config.scalar_transform (config.py:51-54)
+  h = lambda v: np.sign(v) * (np.sqrt(np.abs(v) + 1) - 1) + 0.001 * v
+  for name, got, want in (("init_value", init.value, g["init_value"]), ("rec_value", rec.value, g["rec_value"]),
+                          ("rec_reward", rec.reward, g["rec_reward"]), ("rec2_value", rec2.value, g["rec2_value"]),
+                          ("rec2_reward", rec2.reward, g["rec2_reward"])):
+    dh = np.abs(h(got.cpu().numpy().astype(np.float64)) - h(want.astype(np.float64)))
+    assert dh.max() < 0.06, (name, float(dh.max()), report[name])
+    assert report[name][0] < 0.45, (name, report[name])  # and never more than 0.45 in value space (|v| <= 15)
 
 
 def test_conv_search_replays_bit_exact_in_oracle():
@@ -354,3 +372,32 @@ def test_selfplay_driver_through_conv_search():
   assert kinds.count((4, False)) == G and kinds.count((None, True)) == G
   first = [h for (i, h, ign, term) in fast.saved if i == 0][0]
   assert len(first.actions) == 3 and len(first.observations) == 4 and first.observations[0].shape == (C_in, 96, 96)
+
+
+def test_conv_search_after_load_weights_uses_new_weights():
+  """MuZeroNetwork.load_weights rebuilds the packed tensors; a ConvSearch whose CUDA graph was captured before
+  the hand-off must re-capture, not replay launches that read the freed allocations: the search after the
+  load equals the search of an engine built afterwards."""
+  from model_based_rl_b200.muzero import ConvSearch, MuZeroNetwork, random_state_dict
+  G, A, S, C_in = 8, 6, 4, 4
+  cfg = types.SimpleNamespace(num_simulations=S, action_space=A, two_players=False, discount=0.997, pb_c_base=19652,
+                              pb_c_init=1.25, init_value_score=0.0, known_bounds=[None, None],
+                              root_exploration_fraction=0.25, value_support=[-15, 15], reward_support=[-15, 15],
+                              no_support=False, no_target_transform=False)
+  rng = np.random.default_rng(4)
+  obs = torch.from_numpy(rng.random((G, C_in, 96, 96), dtype=np.float32))
+  noise, u, temp = rng.dirichlet([0.25] * A, size=G), rng.random(G), np.ones(G)
+  net = MuZeroNetwork(C_in, A, "cuda", cfg)
+  net.load_weights(random_state_dict(C_in, A, seed=1))
+  cs = ConvSearch(cfg, net, G, use_graph=True)
+  first = [t.clone() for t in cs.search(obs, noise, u, temp)]
+  sd2 = random_state_dict(C_in, A, seed=2)
+  net.load_weights(sd2)
+  second = [t.clone() for t in cs.search(obs, noise, u, temp)]
+  fresh_net = MuZeroNetwork(C_in, A, "cuda", cfg)
+  fresh_net.load_weights(sd2)
+  want = [t.clone() for t in ConvSearch(cfg, fresh_net, G, use_graph=False).search(obs, noise, u, temp)]
+  torch.cuda.synchronize()
+  assert not torch.equal(first[3], second[3])
+  for x, y in zip(second, want):
+    assert torch.equal(x, y)

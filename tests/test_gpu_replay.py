@@ -207,3 +207,48 @@ def test_window_arena_recycles_dead_chunks():
                                      step)
       assert np.array_equal(t_r[b], r) and np.array_equal(t_p[b], p)
       assert np.allclose(t_v[b], v, rtol=1e-5, atol=1e-6)
+
+
+def test_history_longer_than_the_ring_laps_it_like_the_reference():
+  """A growing ring (window_step) shorter than one history: a single save_history wraps it, the same slot
+  is written more than once inside one add.  The reference writes one memory at a time (replay_buffer.py:
+  19-33): the last write to a slot wins, every earlier one is an ordinary overwrite.  Sums, slot -> (history,
+  step) mapping, num_memories and the liveness of the window chunks must all follow that."""
+  from oracle import replay_ref
+  from model_based_rl_b200.replay_buffer import PrioritizedReplay
+  rng = np.random.default_rng(3)
+  A, K, T, E = 3, 2, 3, 4
+  cfg = types.SimpleNamespace(
+      batch_size=32, beta_increment_per_sampling=0.0, epsilon=0.01, alpha=0.7, beta=0.5,
+      num_unroll_steps=K, td_steps=T, discount=0.99, action_space=A, obs_space=(E,), window_size=40,
+      window_step=8, seed=7, max_history_length=64)
+  rb = PrioritizedReplay(cfg, window_positions=400)
+  ref = replay_ref.SumTreeRef(40, 8)
+  hist = {}
+  for c, n in enumerate([5, 30, 9, 70, 3, 41, 12, 100, 7]):
+    cv = rng.random((n, A))
+    cv /= cv.sum(1, keepdims=True)
+    h = HistorySlice([rng.normal(size=E).astype(np.float32) for _ in range(n)], cv.tolist(),
+                     rng.normal(0, 2, size=n).tolist(), rng.integers(0, A, size=n).tolist(),
+                     rng.normal(size=n).tolist(), rng.normal(size=n).tolist(), [False] * n,
+                     list(range(n)), [None] * n, [1] * n)
+    rb.save_history(h, terminal=True)
+    ref.add(replay_ref.get_priorities(np.array(h.errors), 0.01, 0.7), c)
+    hist[c] = h
+    torch.cuda.synchronize()
+    assert np.array_equal(rb.index.tree.cpu().numpy(), ref.tree)
+    assert rb.size() == ref.num_memories
+    live_slots = ref.slot_hist >= 0
+    assert np.array_equal(rb.index.slot_chunk[live_slots], ref.slot_hist[live_slots])
+    pos = rb.index.slot_pos.cpu().numpy()
+    start = rb.index.slot_start.cpu().numpy()
+    assert np.array_equal((pos - start)[live_slots], ref.slot_step[live_slots])
+    # liveness: a chunk is referenced by exactly the slots that still point at it
+    for cid, n_live in rb._live.items():
+      assert n_live == int((ref.slot_hist == cid).sum()), (cid, n_live)
+    # every sampled row reads the observation of the (history, step) the reference's slot holds
+    (obs, actions, targets), idxs, is_w = rb.sample_batch()
+    for b, ti in enumerate(idxs):
+      slot = ti - (40 - 1)
+      hh = hist[int(ref.slot_hist[slot])]
+      assert np.array_equal(obs[b], hh.observations[int(ref.slot_step[slot])])

@@ -96,7 +96,9 @@ def test_search_matches_reference_golden(case, step_kernel):
           assert g["edge_visit"][gi, n, a] == 0
     legal = g["edge_child"][gi] != -2
     p, q = t["prior"][legal], g["edge_prior"][gi][legal]
-    assert np.allclose(p, q, rtol=1e-14, atol=0)  # device exp() vs libm: <= a few ulp
+    # device exp() (csrc/mz_exp_algo.h, the restatement of glibc's algorithm) + Neumaier sum + IEEE division:
+    # every prior of every node is bit-identical to what the reference computed with math.exp / sum() / '/'
+    assert np.array_equal(p, q), "priors differ in %d of %d entries" % (int((p != q).sum()), p.size)
     exact += int((p == q).sum())
     total += p.size
   print("priors bit-exact: %d / %d" % (exact, total))

@@ -100,6 +100,13 @@ def test_transforms():
   rel = np.abs(inv - g["inverse"]) / np.maximum(np.abs(g["inverse"]), 1.0)
   assert np.mean(rel <= 1e-5) > 0.97
   assert rel.max() < 5e-4
+  # the binary64 restatement bounds the error of BOTH float32 pipelines (torch's golden, the float32 oracle)
+  truth = oracle.inverse_transform_f64(g["logits"], -15, 15)
+  scale = np.maximum(np.abs(truth), 1.0)
+  assert np.max(np.abs(g["inverse"].reshape(-1) - truth) / scale) < 5e-4
+  assert np.max(np.abs(inv.reshape(-1) - truth) / scale) < 5e-4
+  assert np.allclose(oracle.inverse_transform_f64(g["logits"], -15, 15, True), g["inverse_no_transform"].reshape(-1),
+                     rtol=1e-5, atol=1e-6)
 
 
 # ---- the pure-Python port (oracle/search_ref.py, oracle/fcnet_ref.py) used as the CPU baseline ----
