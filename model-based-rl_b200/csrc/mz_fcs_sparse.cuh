@@ -42,8 +42,10 @@ struct Smem {
   float* val;          // [GP]
   float* rew;          // [GP]
   double* mm;          // [GP][2]
-  double* sp;          // [GP][25]  exp(logit) / reward scratch (aliases best_key: used in different phases)
-  unsigned long long* best_key;  // [GP][S1]
+  double* sp;          // [GP][row] exp(logit) / signed-reward scratch.  It shares each game's row with best_key
+                       //           (the two are used in different phases of the SAME game; rows of different games
+                       //           never overlap, so warps in different phases cannot disturb each other)
+  unsigned long long* best_key;  // [GP][row]: per-node maxima, as two u32 arrays [S1] (high / low key words)
   uint32_t* best_ca;   // [GP][S1]  (action << 8) | child id (0xff: the child is unexpanded)
   uint32_t* node;      // [GP][S1]  N | action << 8 | uact << 16
   uint32_t* xmask;     // [GP][S1]
@@ -52,7 +54,8 @@ struct Smem {
   uint8_t* path_a;     // [GP][PS]
   uint8_t* depth;      // [GP]
   const unsigned long long* exp_tab;
-  int ps, a4, s1;
+  const double* rcp;   // [64] correctly rounded reciprocals of the visit counts 1..63
+  int ps, a4, s1, row;  // row = doubles per game of the shared scratch row = max(S1, SP_STRIDE)
 };
 
 struct Game {
@@ -93,42 +96,56 @@ MZ_DEV unsigned long long sortable(double x) {  // monotone map double -> u64 (n
 // bit is clear in `xmask`): returns across the eight lanes the maximal prior, the largest action that has it,
 // and whether another available child with a LARGER action lies within 2^-50 relative below the maximum (then
 // a rounded product could tie and the reference's tie-break would prefer it: the node is ranked densely).
-template <int AL>
-MZ_DEV void top_unexpanded(const double (&pv)[AL], uint32_t xmask, int A, int sub, bool force_dense, double& ptop,
-                           int& uact) {
-  double bp = -1.0;
-  int ba = -1;
+// NS independent sets are reduced side by side (the shuffles of one overlap the compares of the other).
+template <int AL, int NS>
+MZ_DEV void top_unexpanded(const double (&pv)[NS][AL], const uint32_t (&xmask)[NS], int A, int sub, bool force_dense,
+                           double (&ptop)[NS], int (&uact)[NS]) {
+  double bp[NS];
+  int ba[NS];
 #pragma unroll
-  for (int t = 0; t < AL; ++t) {
-    const int a = L * t + sub;
-    if (a < A && !((xmask >> a) & 1u) && pv[t] >= bp) {  // ascending actions: >= keeps the larger one
-      bp = pv[t];
-      ba = a;
+  for (int s = 0; s < NS; ++s) {
+    bp[s] = -1.0;
+    ba[s] = -1;
+#pragma unroll
+    for (int t = 0; t < AL; ++t) {
+      const int a = L * t + sub;
+      if (a < A && !((xmask[s] >> a) & 1u) && pv[s][t] >= bp[s]) {  // ascending actions: >= keeps the larger one
+        bp[s] = pv[s][t];
+        ba[s] = a;
+      }
     }
   }
 #pragma unroll
   for (int m = 1; m < L; m <<= 1) {
-    const double op = shfl8_xor_f64(bp, m);
-    const int oa = __shfl_xor_sync(MZ_FULL, ba, m, L);
-    if (oa >= 0 && (ba < 0 || op > bp || (op == bp && oa > ba))) {
-      bp = op;
-      ba = oa;
-    }
-  }
-  bool close = false;
-  if (ba >= 0) {
-    const double thr = __dmul_rn(bp, 1.0 - 0x1p-50);
+    double op[NS];
+    int oa[NS];
 #pragma unroll
-    for (int t = 0; t < AL; ++t) {
-      const int a = L * t + sub;
-      if (a < A && !((xmask >> a) & 1u) && a > ba && pv[t] < bp && pv[t] >= thr) close = true;
+    for (int s = 0; s < NS; ++s) {
+      op[s] = shfl8_xor_f64(bp[s], m);
+      oa[s] = __shfl_xor_sync(MZ_FULL, ba[s], m, L);
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const bool take = oa[s] >= 0 && (ba[s] < 0 || op[s] > bp[s] || (op[s] == bp[s] && oa[s] > ba[s]));
+      bp[s] = take ? op[s] : bp[s];
+      ba[s] = take ? oa[s] : ba[s];
     }
   }
   const unsigned lane = threadIdx.x & 31u;
   const unsigned gmask = 0xffu << (lane & ~7u);
-  const bool any_close = (__ballot_sync(MZ_FULL, close) & gmask) != 0u;
-  ptop = bp;
-  uact = ba < 0 ? UACT_NONE : (ba | ((any_close || force_dense || bp < 0x1p-900) ? UACT_DENSE : 0));
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    bool close = false;
+    const double thr = __dmul_rn(bp[s], 1.0 - 0x1p-50);
+#pragma unroll
+    for (int t = 0; t < AL; ++t) {
+      const int a = L * t + sub;
+      close = close || (ba[s] >= 0 && a < A && !((xmask[s] >> a) & 1u) && a > ba[s] && pv[s][t] < bp[s] && pv[s][t] >= thr);
+    }
+    const bool any_close = (__ballot_sync(MZ_FULL, close) & gmask) != 0u;
+    ptop[s] = bp[s];
+    uact[s] = ba[s] < 0 ? UACT_NONE : (ba[s] | ((any_close || force_dense || bp[s] < 0x1p-900) ? UACT_DENSE : 0));
+  }
 }
 
 // Node.expand priors for the eight lanes of a game (see fs_prior_sum in mz_fcsearch.cu: same sum order)
@@ -136,7 +153,7 @@ template <int AL>
 MZ_DEV double prior_sum(const FsParams& p, const Smem& sm, const Game& gm, const float* logits, uint32_t legal_bits,
                         double (&pexp)[AL]) {
   const int A = p.A;
-  double* sp = sm.sp + gm.gl * SP_STRIDE;
+  double* sp = sm.sp + gm.gl * sm.row;
 #pragma unroll
   for (int t = 0; t < AL; ++t) {
     const int a = L * t + gm.sub;
@@ -194,9 +211,14 @@ MZ_DEV void set_root(const FsParams& p, const Smem& sm, const Game& gm, const Ge
     pv[t] = prior;
     if (gm.valid && a < A) *reinterpret_cast<double*>(gm.base + G.pri + 8 * a) = prior;
   }
-  double ptop;
-  int uact;
-  top_unexpanded<AL>(pv, ~lm, A, gm.sub, p.init_score != 0.0, ptop, uact);
+  double pvs[1][AL], ptops[1];
+  int uacts[1];
+#pragma unroll
+  for (int t = 0; t < AL; ++t) pvs[0][t] = pv[t];
+  const uint32_t xms[1] = {~lm};
+  top_unexpanded<AL, 1>(pvs, xms, A, gm.sub, p.init_score != 0.0, ptops, uacts);
+  const double ptop = ptops[0];
+  const int uact = uacts[0];
   if (gm.valid && gm.sub == 0) {
     sm.node[gm.gl * sm.s1] = 0u | (0xffu << 8) | ((uint32_t)uact << 16);
     sm.xmask[gm.gl * sm.s1] = ~lm;
@@ -219,136 +241,180 @@ MZ_DEV void set_root(const FsParams& p, const Smem& sm, const Game& gm, const Ge
   *reinterpret_cast<uint4*>(row + 8 * gm.sub) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// ------------------------------------------------------------------------------------------------------
-// descent = [rank every expanded node's candidates in parallel] + [pointer chase from the root]
-// ------------------------------------------------------------------------------------------------------
 #define FS2_STAMP(slot_)                    \
   do {                                      \
     if (tl) tl[(slot_)] = clock64();        \
   } while (0)
 
+// ------------------------------------------------------------------------------------------------------
+// descent = [rank every expanded node's candidates in parallel] + [pointer chase from the root]
+//
+// Items of simulation `sim` (nodes 0..sim exist): i <= sim -> "U": the best unexpanded child of node i;
+// i > sim -> "E": the edge into node j = i - sim.  Lane `sub` of a game owns items sub, sub + 8, ...  The item
+// arithmetic is straight-line (no per-item branches), four items per basic block, so that the independent
+// dependency chains of a lane's items overlap; the rare cases (a node flagged for dense ranking, a MinMax
+// range outside the fast-division guard) are redone exactly in a second pass under a warp vote.
+// The per-parent maximum over (score, action) runs on native 32-bit shared-memory atomics: high words of the
+// order-preserving keys, then low words among the items that reached the high maximum, then actions.
+// ------------------------------------------------------------------------------------------------------
+struct Norm {  // MinMaxStats.normalize (mcts.py:16-21) hoisted per game
+  int mode;    // 2: (v - min) / (max - min) through the reciprocal, 3: IEEE division, 1: constant 1.0, 0: raw
+  double mn, d, r;
+};
+MZ_DEV Norm make_norm(double mn, double mx) {
+  Norm n;
+  n.mn = mn;
+  n.d = __dsub_rn(mx, mn);
+  n.r = 0.0;
+  n.mode = 0;
+  if (mx > mn) {
+    if (fs_divisor_ok(n.d)) {
+      n.mode = 2;
+      n.r = __drcp_rn(n.d);
+    } else {
+      n.mode = 3;
+    }
+  } else if (mx == mn) {
+    n.mode = 1;
+  }
+  return n;
+}
+
 MZ_DEV void descend(const FsParams& p, const Smem& sm, const Game& gm, const Geo& G, int sim, int& out_parent,
                     int& out_action, long long* tl) {
   const int A = p.A, SP1 = p.S + 1;
   const double init_score = p.init_score;
-  const double mn = sm.mm[2 * gm.gl], mx = sm.mm[2 * gm.gl + 1];
-  const double d = __dsub_rn(mx, mn);
-  int mode = 0;
-  double r = 0.0;
-  if (mx > mn) {
-    if (fs_divisor_ok(d)) {
-      mode = 2;
-      r = __drcp_rn(d);
-    } else {
-      mode = 3;
-    }
-  } else if (mx == mn) {
-    mode = 1;
-  }
+  const Norm nm = make_norm(sm.mm[2 * gm.gl], sm.mm[2 * gm.gl + 1]);
   uint32_t* node = sm.node + gm.gl * sm.s1;
   const uint32_t* xmask = sm.xmask + gm.gl * sm.s1;
   const uint8_t* par = sm.par + gm.gl * sm.s1;
-  unsigned long long* best_key = sm.best_key + gm.gl * sm.s1;
+  uint32_t* best_hi = reinterpret_cast<uint32_t*>(sm.best_key + gm.gl * sm.row);
+  uint32_t* best_lo = best_hi + sm.s1;
   uint32_t* best_ca = sm.best_ca + gm.gl * sm.s1;
-  // nodes 0..sim exist; items: i <= sim -> the best unexpanded child of node i; i > sim -> the edge into node i - sim
   const int n_items = gm.valid ? 2 * sim + 1 : 0;
+  const int n_items_max = 2 * sim + 1;  // warp uniform
   for (int n = gm.sub; n <= sim; n += L) {
-    best_key[n] = 0ull;
+    best_hi[n] = 0u;
+    best_lo[n] = 0u;
     best_ca[n] = 0u;
   }
   __syncwarp();
   FS2_STAMP(16);
-  unsigned long long key[MAX_ITEMS];
-  uint32_t pack[MAX_ITEMS];  // parent << 16 | action << 8 | child id (0xff = unexpanded)
-  // ---- issue every global load of this lane's items first (one memory round trip) ----
-  double ld_a[MAX_ITEMS], ld_b[MAX_ITEMS], ld_c[MAX_ITEMS];
+  uint32_t key_hi[MAX_ITEMS], key_lo[MAX_ITEMS], pack[MAX_ITEMS];  // pack: valid << 31 | parent << 16 | action << 8 | child
+  bool any_slow = false;
+  constexpr int BT = 8;  // items per batch: all global loads of a batch are in flight together
 #pragma unroll
-  for (int it = 0; it < MAX_ITEMS; ++it) {
-    const int i = L * it + gm.sub;
-    ld_a[it] = ld_b[it] = ld_c[it] = 0.0;
-    if (L * it < 2 * p.S + 1 && i < n_items) {
-      if (i <= sim) {
-        const uint32_t w = node[i];
-        ld_a[it] = *reinterpret_cast<const double*>(gm.base + G.utop + 8 * i);
-        ld_c[it] = __ldg(p.pb_c + (size_t)(w & 0xffu) * SP1);  // pb_c[N][0]
+  for (int b0 = 0; b0 < MAX_ITEMS; b0 += BT) {
+    if (L * b0 >= n_items_max) {  // warp uniform: nothing left
+#pragma unroll
+      for (int u = 0; u < BT; ++u) key_hi[b0 + u] = key_lo[b0 + u] = pack[b0 + u] = 0u;
+      continue;
+    }
+    // ---- loads ----
+    double prior[BT], q[BT], pbc[BT];
+    uint32_t wj[BT];
+    int pj[BT];
+#pragma unroll
+    for (int u = 0; u < BT; ++u) {
+      const int i = L * (b0 + u) + gm.sub;
+      const bool act = i < n_items, isu = i <= sim;
+      const int j = act ? (isu ? i : i - sim) : 0;
+      wj[u] = node[j];
+      pj[u] = isu ? j : (int)par[j];
+      const int np_ = (int)(node[pj[u]] & 0xffu), nj = isu ? 0 : (int)(wj[u] & 0xffu);
+      pbc[u] = __ldg(p.pb_c + (size_t)np_ * SP1 + nj);
+      if (isu) {
+        prior[u] = *reinterpret_cast<const double*>(gm.base + G.utop + 8 * j);
+        q[u] = 0.0;
       } else {
-        const int j = i - sim;
         const double2 e = *reinterpret_cast<const double2*>(gm.base + G.edge + 16 * j);
-        ld_a[it] = e.x;
-        ld_b[it] = e.y;
-        const int np_ = (int)(node[par[j]] & 0xffu), nj = (int)(node[j] & 0xffu);
-        ld_c[it] = __ldg(p.pb_c + (size_t)np_ * SP1 + nj);
+        prior[u] = e.x;
+        q[u] = e.y;
       }
+    }
+    // ---- scores ----
+#pragma unroll
+    for (int u = 0; u < BT; ++u) {
+      const int it = b0 + u;
+      const int i = L * it + gm.sub;
+      const bool act = i < n_items, isu = i <= sim;
+      const int ua = (int)((wj[u] >> 16) & 0xffu);
+      const bool live = act && !(isu && ua == UACT_NONE);
+      // value term: init_value_score for an unvisited child, the normalised q of a visited one
+      const double x = __dsub_rn(q[u], nm.mn);
+      double vs = fs_div_by_const(x, nm.d, nm.r);  // mode 2 (exact for x == 0 too); other modes selected / redone below
+      const unsigned hx = (unsigned)__double2hiint(x);
+      bool slow = !isu && (nm.mode == 3 || (nm.mode == 2 && x != 0.0 && hx - 0x33700000u > 0x19000000u));
+      vs = nm.mode == 1 ? 1.0 : (nm.mode == 0 ? q[u] : vs);
+      vs = isu ? init_score : vs;
+      double score = __dadd_rn(__dmul_rn(pbc[u], prior[u]), vs);
+      if (sim == 0) score = prior[u];  // mcts.py:105-108: the unvisited root ranks its children by prior
+      slow = slow || (isu && (ua & UACT_DENSE) && ua != UACT_NONE);
+      any_slow = any_slow || (live && slow);
+      const unsigned long long k = sortable(score);
+      key_hi[it] = (uint32_t)(k >> 32);
+      key_lo[it] = (uint32_t)k;
+      const uint32_t action = isu ? (uint32_t)(ua & 0x3f) : ((wj[u] >> 8) & 0xffu);
+      const uint32_t child = isu ? 0xffu : (uint32_t)(i - sim);
+      pack[it] = live ? (0x80000000u | (slow ? 0x40000000u : 0u) | ((uint32_t)pj[u] << 16) | (action << 8) | child) : 0u;
     }
   }
   FS2_STAMP(17);
+  if (__any_sync(MZ_FULL, any_slow)) {
+    // exact redo of the flagged items: IEEE division for the value term, dense ranking of a flagged node
 #pragma unroll
-  for (int it = 0; it < MAX_ITEMS; ++it) {
-    const int i = L * it + gm.sub;
-    key[it] = 0ull;
-    pack[it] = 0u;
-    if (L * it < 2 * p.S + 1 && i < n_items) {
-      if (i <= sim) {  // best unexpanded child of node i
-        const uint32_t w = node[i];
-        const int N = (int)(w & 0xffu), ua = (int)((w >> 16) & 0xffu);
-        if (ua != UACT_NONE) {
-          double score;
-          int action = ua & 0x3f;
-          if (ua & UACT_DENSE) {  // near-tie among the priors (or init_value_score != 0): rank all of them
-            const double pb_c = ld_c[it];
-            const uint32_t xm = xmask[i];
-            bool have = false;
-            score = 0.0;
-            for (int a = 0; a < A; ++a) {
-              if ((xm >> a) & 1u) continue;
-              const double pr = *reinterpret_cast<const double*>(gm.base + G.pri + ((size_t)i * G.a2 + a) * 8);
-              const double s = N == 0 ? pr : __dadd_rn(__dmul_rn(pb_c, pr), init_score);
-              if (!have || s >= score) {
-                score = s;
-                action = a;
-                have = true;
-              }
-            }
-          } else {
-            // mcts.py:105-108 (N == 0: the root before its first visit ranks by prior) / ucb_score mcts.py:115-124
-            score = N == 0 ? ld_a[it] : __dadd_rn(__dmul_rn(ld_c[it], ld_a[it]), init_score);
+    for (int it = 0; it < MAX_ITEMS; ++it) {  // unrolled: the item arrays must stay in registers
+      if (!(pack[it] & 0x40000000u)) continue;
+      const int i = L * it + gm.sub;
+      const int pn = (int)((pack[it] >> 16) & 0xffu);
+      double score;
+      uint32_t action = (pack[it] >> 8) & 0xffu;
+      if (i <= sim) {
+        const int N = (int)(node[i] & 0xffu);
+        const double pb_c = __ldg(p.pb_c + (size_t)N * SP1);
+        const uint32_t xm = xmask[i];
+        bool have = false;
+        score = 0.0;
+        for (int a = 0; a < A; ++a) {
+          if ((xm >> a) & 1u) continue;
+          const double pr = *reinterpret_cast<const double*>(gm.base + G.pri + ((size_t)i * G.a2 + a) * 8);
+          const double sc = sim == 0 ? pr : __dadd_rn(__dmul_rn(pb_c, pr), init_score);
+          if (!have || sc >= score) {
+            score = sc;
+            action = (uint32_t)a;
+            have = true;
           }
-          key[it] = sortable(score);
-          pack[it] = ((uint32_t)i << 16) | ((uint32_t)action << 8) | 0xffu;
-          atomicMax(&best_key[i], key[it]);
         }
-      } else {  // the edge into node j (visited at least once)
+      } else {
         const int j = i - sim;
-        const int pn = (int)par[j];
-        const double q = ld_b[it];
-        double value_score;
-        if (mode == 2) {
-          const double x = __dsub_rn(q, mn);
-          value_score = fs_div_by_const(x, d, r);
-          const unsigned hx = (unsigned)__double2hiint(x);  // x >= 0 because min <= q
-          if (__builtin_expect(hx - 0x33700000u > 0x19000000u, 0)) value_score = (x == 0.0) ? 0.0 : __ddiv_rn(x, d);
-        } else if (mode == 3) {
-          value_score = __ddiv_rn(__dsub_rn(q, mn), d);
-        } else if (mode == 1) {
-          value_score = 1.0;
-        } else {
-          value_score = q;
-        }
-        const double score = __dadd_rn(__dmul_rn(ld_c[it], ld_a[it]), value_score);
-        key[it] = sortable(score);
-        pack[it] = ((uint32_t)pn << 16) | (((node[j] >> 8) & 0xffu) << 8) | (uint32_t)j;
-        atomicMax(&best_key[pn], key[it]);
+        const double2 e = *reinterpret_cast<const double2*>(gm.base + G.edge + 16 * j);
+        const double pb_c = __ldg(p.pb_c + (size_t)(node[pn] & 0xffu) * SP1 + (node[j] & 0xffu));
+        const double x = __dsub_rn(e.y, nm.mn);
+        const double vs = (nm.mode == 2 && x == 0.0) ? 0.0 : __ddiv_rn(x, nm.d);
+        score = __dadd_rn(__dmul_rn(pb_c, e.x), vs);
       }
+      const unsigned long long k = sortable(score);
+      key_hi[it] = (uint32_t)(k >> 32);
+      key_lo[it] = (uint32_t)k;
+      pack[it] = (pack[it] & 0xffff00ffu) | (action << 8);
     }
   }
+  // ---- per-parent maximum over (score, action): three rounds of 32-bit atomics ----
+#pragma unroll
+  for (int it = 0; it < MAX_ITEMS; ++it)
+    if (pack[it]) atomicMax(&best_hi[(pack[it] >> 16) & 0xffu], key_hi[it]);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < MAX_ITEMS; ++it)
+    if (pack[it] && key_hi[it] == best_hi[(pack[it] >> 16) & 0xffu]) atomicMax(&best_lo[(pack[it] >> 16) & 0xffu], key_lo[it]);
   __syncwarp();
   FS2_STAMP(18);
   // ties -> larger action (mcts.py:106-112): among the items that reach a node's maximum the largest action wins
 #pragma unroll
   for (int it = 0; it < MAX_ITEMS; ++it) {
-    if (L * it < 2 * p.S + 1 && key[it] != 0ull) {
-      const int pn = (int)(pack[it] >> 16);
-      if (key[it] == best_key[pn]) atomicMax(&best_ca[pn], pack[it] & 0xffffu);
+    if (pack[it]) {
+      const int pn = (int)((pack[it] >> 16) & 0xffu);
+      if (key_hi[it] == best_hi[pn] && key_lo[it] == best_lo[pn]) atomicMax(&best_ca[pn], pack[it] & 0xffffu);
     }
   }
   __syncwarp();
@@ -359,21 +425,23 @@ MZ_DEV void descend(const FsParams& p, const Smem& sm, const Game& gm, const Geo
   int cur = 0, depth = 0, parent = 0, action = 0;
   bool done = !gm.valid;
   if (gm.valid && gm.sub == 0) pn_[0] = 0;
-  while (__any_sync(MZ_FULL, !done)) {
-    if (!done) {
+  for (;;) {
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {  // finished games idle through the extra level
       const uint32_t ca = best_ca[cur];
       const int a = (int)(ca >> 8), c = (int)(ca & 0xffu);
-      if (gm.sub == 0) pa_[depth] = (uint8_t)a;
-      ++depth;
-      if (c == 0xff) {
-        parent = cur;
-        action = a;
-        done = true;
-      } else {
-        cur = c;
-        if (gm.sub == 0) pn_[depth] = (uint8_t)c;
+      if (!done && gm.sub == 0) {
+        pa_[depth] = (uint8_t)a;
+        pn_[depth + 1] = (uint8_t)c;  // 0xff after the leaf: never read (positions <= depth only)
       }
+      const bool leaf = c == 0xff;
+      parent = done ? parent : cur;
+      action = done ? action : a;
+      depth += done ? 0 : 1;
+      cur = (done || leaf) ? cur : c;
+      done = done || leaf;
     }
+    if (!__any_sync(MZ_FULL, !done)) break;
   }
   FS2_STAMP(20);
   if (gm.valid && gm.sub == 0) {
@@ -384,6 +452,30 @@ MZ_DEV void descend(const FsParams& p, const Smem& sm, const Game& gm, const Geo
   }
   out_parent = parent;
   out_action = action;
+}
+
+// exp for arguments inside the table algorithm's range (every finite logit of a network); `bad` reports the rest
+MZ_DEV double exp_fast(double x, const unsigned long long* tab, bool& bad) {
+  const double ax = fabs(x);
+  bad = !(ax >= 0x1p-54 && ax < 512.0);
+  const double InvLn2N = 0x1.71547652b82fep7, Shift = 0x1.8p52;
+  const double NegLn2hiN = -0x1.62e42fefa0000p-8, NegLn2loN = -0x1.cf79abc9e3b3ap-47;
+  const double C2 = 0x1.ffffffffffdbdp-2, C3 = 0x1.555555555543cp-3;
+  const double C4 = 0x1.55555cf172b91p-5, C5 = 0x1.1111167a4d017p-7;
+  const double z = __dmul_rn(InvLn2N, x);
+  double kd = __dadd_rn(z, Shift);
+  const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+  kd = __dsub_rn(kd, Shift);
+  const double r = __fma_rn(kd, NegLn2loN, __fma_rn(kd, NegLn2hiN, x));
+  const unsigned idx = 2u * ((unsigned)ki & 127u);
+  const unsigned long long top = ki << 45;
+  const double tail = __longlong_as_double((long long)tab[idx]);
+  const unsigned long long sbits = tab[idx + 1] + top;
+  const double r2 = __dmul_rn(r, r);
+  const double a = __fma_rn(r, C3, C2), b = __fma_rn(r, C5, C4);
+  const double tmp = __fma_rn(__dmul_rn(r2, r2), b, __fma_rn(r2, a, __dadd_rn(tail, r)));
+  const double scale = __longlong_as_double((long long)sbits);
+  return __fma_rn(scale, tmp, scale);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -404,19 +496,6 @@ MZ_DEV void expand_backup(const FsParams& p, const Smem& sm, const Game& gm, con
   uint32_t* xmask = sm.xmask + gm.gl * sm.s1;
   const int depth = gm.valid ? (int)sm.depth[gm.gl] : 0;
   const int parent = gm.valid ? (int)pn_[depth - 1] : 0, action = gm.valid ? (int)pa_[depth - 1] : 0;
-  if (gm.valid) {
-    if (gm.sub == 0) {
-      if (p.rec_value) p.rec_value[(size_t)sim * p.G + gm.g] = value_f;
-      if (p.rec_reward) p.rec_reward[(size_t)sim * p.G + gm.g] = reward_in;
-    }
-    if (p.rec_logits) {
-#pragma unroll
-      for (int t = 0; t < AL; ++t) {
-        const int a = L * t + gm.sub;
-        if (a < A) p.rec_logits[((size_t)sim * p.G + gm.g) * A + a] = logits[a];
-      }
-    }
-  }
   int dmax = depth;
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) dmax = max(dmax, __shfl_xor_sync(MZ_FULL, dmax, m));
@@ -438,27 +517,86 @@ MZ_DEV void expand_backup(const FsParams& p, const Smem& sm, const Game& gm, con
     own[m] = make_uint4(0u, 0u, 0u, 0u);
     if (L * m <= dmax && gm.valid && kk < depth) own[m] = ldg16(gm.base + G.own + 16 * (int)pn_[kk]);
   }
-
+  if (gm.valid) {
+    if (gm.sub == 0) {
+      if (p.rec_value) p.rec_value[(size_t)sim * p.G + gm.g] = value_f;
+      if (p.rec_reward) p.rec_reward[(size_t)sim * p.G + gm.g] = reward_in;
+    }
+    if (p.rec_logits) {
+#pragma unroll
+      for (int t = 0; t < AL; ++t) {
+        const int a = L * t + gm.sub;
+        if (a < A) p.rec_logits[((size_t)sim * p.G + gm.g) * A + a] = logits[a];
+      }
+    }
+  }
   FS2_STAMP(22);
-  // ---- expand: priors of the new node (every action is legal below the root, mcts.py:72, 97) ----
+
+  // ---- expand: priors of the new node (every action is legal below the root, mcts.py:72, 97):
+  // p_a = exp(logit_a) / sum, the sum evaluated like CPython's builtin sum() over the actions in order ----
+  double* sp = sm.sp + gm.gl * sm.row;
   double pexp[AL];
-  const uint32_t all = A < 32 ? (1u << A) - 1u : 0xffffffffu;
-  const double f = prior_sum<AL>(p, sm, gm, logits, gm.valid ? all : 0u, pexp);
+  bool bad = false;
+#pragma unroll
+  for (int t = 0; t < AL; ++t) {
+    const int a = L * t + gm.sub;
+    bool b1;
+    pexp[t] = exp_fast((double)logits[a < A ? a : 0], sm.exp_tab, b1);
+    bad = bad || (a < A && b1);
+  }
+  if (__any_sync(MZ_FULL, bad)) {  // a logit outside the table algorithm's range: the general routine
+#pragma unroll
+    for (int t = 0; t < AL; ++t) {
+      const int a = L * t + gm.sub;
+      if (a < A) pexp[t] = fs_exp((double)logits[a], sm.exp_tab);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < AL; ++t) {
+    const int a = L * t + gm.sub;
+    if (a < A) sp[a] = pexp[t];
+  }
+  __syncwarp();
+  double f = sp[0], c = 0.0;  // int 0 + x
+  if (p.prior_sum_mode == 0) {
+#pragma unroll 8
+    for (int a = 1; a < A; ++a) f = __dadd_rn(f, sp[a]);
+  } else {  // Neumaier steps, CPython >= 3.12 Python/bltinmodule.c
+#pragma unroll 8
+    for (int a = 1; a < A; ++a) {
+      const double x = sp[a];
+      const double s = __dadd_rn(f, x);
+      const bool big = fabs(f) >= fabs(x);
+      const double hi = big ? f : x, lo = big ? x : f;
+      c = __dadd_rn(c, __dadd_rn(__dsub_rn(hi, s), lo));
+      f = s;
+    }
+    if (c != 0.0 && isfinite(c)) f = __dadd_rn(f, c);
+  }
+  __syncwarp();
   FS2_STAMP(23);
   double pv[AL];
 #pragma unroll
   for (int t = 0; t < AL; ++t) {
     const int a = L * t + gm.sub;
-    pv[t] = (gm.valid && a < A) ? __ddiv_rn(pexp[t], f) : 0.0;
+    pv[t] = __ddiv_rn(pexp[t], f);
     if (gm.valid && a < A) *reinterpret_cast<double*>(gm.base + G.pri + ((size_t)newn * G.a2 + a) * 8) = pv[t];
   }
   FS2_STAMP(24);
-  double ptop_new, ptop_par;
-  int uact_new, uact_par;
   const bool force_dense = p.init_score != 0.0;
-  top_unexpanded<AL>(pv, ~all, A, gm.sub, force_dense, ptop_new, uact_new);
+  const uint32_t all = A < 32 ? (1u << A) - 1u : 0xffffffffu;
   const uint32_t xm_par = gm.valid ? (xmask[parent] | (1u << action)) : 0xffffffffu;
-  top_unexpanded<AL>(ppv, xm_par, A, gm.sub, force_dense, ptop_par, uact_par);
+  double pvs[2][AL], ptops[2];
+  int uacts[2];
+#pragma unroll
+  for (int t = 0; t < AL; ++t) {
+    pvs[0][t] = pv[t];
+    pvs[1][t] = ppv[t];
+  }
+  const uint32_t xms[2] = {~all, xm_par};
+  top_unexpanded<AL, 2>(pvs, xms, A, gm.sub, force_dense, ptops, uacts);
+  const double ptop_new = ptops[0], ptop_par = ptops[1];
+  const int uact_new = uacts[0], uact_par = uacts[1];
   // the prior of the new edge: the lane that holds the parent's prior of `action` hands it round
   double edge_prior = 0.0;
 #pragma unroll
@@ -467,7 +605,6 @@ MZ_DEV void expand_backup(const FsParams& p, const Smem& sm, const Game& gm, con
                                       __shfl_sync(MZ_FULL, __double2loint(ppv[t]), action & (L - 1), L));
     if (t == action / L) edge_prior = v;
   }
-  __syncwarp();
   if (gm.valid && gm.sub == 0) {
     node[newn] = 0u | ((uint32_t)action << 8) | ((uint32_t)uact_new << 16);
     xmask[newn] = ~all;
@@ -480,65 +617,99 @@ MZ_DEV void expand_backup(const FsParams& p, const Smem& sm, const Game& gm, con
   __syncwarp();
   FS2_STAMP(25);
 
-  // ---- backup.  Position k on the path is node path_n[k] (k < depth) or the new node (k == depth) ----
-  float* scratch = reinterpret_cast<float*>(sm.sp + gm.gl * SP_STRIDE);  // [<= 50] rewards by position
-  // (SP_STRIDE doubles = 50 floats: positions beyond 49 only exist for S > 49 -> chunked below)
+  // ---- backup.  Position k on the path is node path_n[k] (k < depth) or the new node (k == depth); lane `sub`
+  // owns positions 8 m + sub.  The value recurrence (mcts.py:142: value = (+/-)reward + discount * value) is
+  // serial in binary64; it runs in all lanes from the positions' signed rewards in the scratch row ----
   double value = (double)value_f;
   double lmin = INFINITY, lmax = -INFINITY;
-  constexpr int CH = 48;  // positions per chunk (multiple of L, <= 50 scratch floats)
-  for (int base = (dmax / CH) * CH; base >= 0; base -= CH) {
-    const int m0 = base / L;
-    // rewards of the chunk's positions -> scratch
+  constexpr int CHP = 32;       // positions per chunk (the scratch row holds >= 33 doubles)
+  constexpr int CM = CHP / L;   // position slots of a lane per chunk
+  auto chunk = [&](auto m0_tag) {
+    constexpr int M0 = decltype(m0_tag)::value;
+    constexpr int base = M0 * L;
 #pragma unroll
-    for (int m = 0; m < MAXP; ++m) {
+    for (int mm = 0; mm < CM; ++mm) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int m = M0 + mm;
+      if (m >= MAXP) continue;
       const int kk = L * m + gm.sub;
-      if (m >= m0 && m < m0 + CH / L && L * m <= dmax && gm.valid && kk <= depth)
-        scratch[kk - base] = kk < depth ? __uint_as_float(own[m].z) : node_reward_new;
+      const bool on = gm.valid && kk <= depth;
+      const float rw = kk < depth ? __uint_as_float(own[m < MAXP ? m : 0].z) : node_reward_new;
+      // (-reward if two_players and node.to_play == to_play else reward)
+      const bool same = two && (((depth - kk) & 1) == 0);
+      if (on) sp[kk - base] = (double)(same ? -rw : rw);
     }
     __syncwarp();
-    double myval[MAXP];
+    double myval[CM];
 #pragma unroll
-    for (int m = MAXP - 1; m >= 0; --m) {
-      myval[m] = 0.0;
-      if (m < m0 || m >= m0 + CH / L || L * m > dmax) continue;  // warp uniform
+    for (int mm = CM - 1; mm >= 0; --mm) {
+      myval[mm] = 0.0;
+      if (M0 + mm >= MAXP || L * (M0 + mm) > dmax) continue;  // warp uniform
 #pragma unroll
       for (int jj = L - 1; jj >= 0; --jj) {
-        const int kk = L * m + jj;
-        if (gm.valid && kk <= depth) {
-          const float rj = scratch[kk - base];
-          if (jj == gm.sub) myval[m] = value;
-          // value = (-reward if two_players and node.to_play == to_play else reward) + discount * value
-          const bool same = two ? (((depth - kk) & 1) == 0) : false;
-          value = __dadd_rn((double)(same ? -rj : rj), __dmul_rn(disc, value));
-        }
+        const int kk = L * (M0 + mm) + jj;
+        const bool on = gm.valid && kk <= depth;
+        const double rs = sp[on ? kk - base : 0];
+        myval[mm] = jj == gm.sub ? value : myval[mm];
+        const double nv = __dadd_rn(rs, __dmul_rn(disc, value));
+        value = on ? nv : value;
       }
     }
     __syncwarp();
+    // per-position updates, straight-line over the lane's slots (their chains overlap); value_sum / visit_count
+    // through the reciprocal table: bit-identical to IEEE division inside the guarded range, else redone exactly
+    bool on[CM], redo = false;
+    double nvs[CM], nq[CM];
+    int nid[CM], nvc[CM];
+    float rwv[CM];
 #pragma unroll
-    for (int m = 0; m < MAXP; ++m) {
+    for (int mm = 0; mm < CM; ++mm) {
+      const int m = M0 + mm;
       const int kk = L * m + gm.sub;
-      if (m >= m0 && m < m0 + CH / L && L * m <= dmax && gm.valid && kk <= depth) {
-        const bool same = two ? (((depth - kk) & 1) == 0) : true;
-        const double vs0 = kk < depth ? u2d(own[m].x, own[m].y) : 0.0;
-        const float rw = kk < depth ? __uint_as_float(own[m].z) : node_reward_new;
-        const double nvs = __dadd_rn(vs0, same ? myval[m] : -myval[m]);
-        const int nid = kk < depth ? (int)pn_[kk] : newn;
-        const int nvc = (int)(node[nid] & 0xffu) + 1;
-        node[nid] = (node[nid] & 0xffffff00u) | (uint32_t)nvc;
-        *reinterpret_cast<uint4*>(gm.base + G.own + 16 * nid) =
-            make_uint4((uint32_t)__double2loint(nvs), (uint32_t)__double2hiint(nvs), __float_as_uint(rw), 0u);
-        if (kk > 0) {  // mcts.py:136-141
-          const double dq = __dmul_rn(disc, __ddiv_rn(nvs, (double)nvc));
-          const double new_q = two ? __dsub_rn((double)rw, dq) : __dadd_rn((double)rw, dq);
-          lmin = fmin(lmin, new_q);
-          lmax = fmax(lmax, new_q);
-          if (kk == depth) *reinterpret_cast<double2*>(gm.base + G.edge + 16 * nid) = make_double2(edge_prior, new_q);
-          else *reinterpret_cast<double*>(gm.base + G.edge + 16 * nid + 8) = new_q;
+      on[mm] = m < MAXP && gm.valid && kk <= depth;
+      const uint4 o = own[m < MAXP ? m : 0];
+      // value_sum += value if node.to_play == to_play else -value
+      const bool same = two ? (((depth - kk) & 1) == 0) : true;
+      const double vs0 = kk < depth ? u2d(o.x, o.y) : 0.0;
+      rwv[mm] = kk < depth ? __uint_as_float(o.z) : node_reward_new;
+      nvs[mm] = __dadd_rn(vs0, same ? myval[mm] : -myval[mm]);
+      nid[mm] = on[mm] ? (kk < depth ? (int)pn_[kk] : newn) : 0;
+      nvc[mm] = (int)(node[nid[mm]] & 0xffu) + 1;
+      const double dn = (double)nvc[mm];
+      const double mean = fs_div_by_const(nvs[mm], dn, sm.rcp[nvc[mm] & 63]);
+      const unsigned hv = (unsigned)__double2hiint(nvs[mm]) & 0x7fffffffu;
+      redo = redo || (on[mm] && nvs[mm] != 0.0 && hv - 0x33700000u > 0x19000000u);
+      const double dq = __dmul_rn(disc, mean);  // mcts.py:136-141
+      nq[mm] = two ? __dsub_rn((double)rwv[mm], dq) : __dadd_rn((double)rwv[mm], dq);
+    }
+    if (__any_sync(MZ_FULL, redo)) {
+#pragma unroll
+      for (int mm = 0; mm < CM; ++mm) {
+        const double dq = __dmul_rn(disc, __ddiv_rn(nvs[mm], (double)nvc[mm]));
+        nq[mm] = two ? __dsub_rn((double)rwv[mm], dq) : __dadd_rn((double)rwv[mm], dq);
+      }
+    }
+#pragma unroll
+    for (int mm = 0; mm < CM; ++mm) {
+      const int kk = L * (M0 + mm) + gm.sub;
+      if (on[mm]) {
+        node[nid[mm]] = (node[nid[mm]] & 0xffffff00u) | (uint32_t)nvc[mm];
+        *reinterpret_cast<uint4*>(gm.base + G.own + 16 * nid[mm]) = make_uint4(
+            (uint32_t)__double2loint(nvs[mm]), (uint32_t)__double2hiint(nvs[mm]), __float_as_uint(rwv[mm]), 0u);
+        if (kk > 0) {
+          lmin = fmin(lmin, nq[mm]);
+          lmax = fmax(lmax, nq[mm]);
+          if (kk == depth) *reinterpret_cast<double2*>(gm.base + G.edge + 16 * nid[mm]) = make_double2(edge_prior, nq[mm]);
+          else *reinterpret_cast<double*>(gm.base + G.edge + 16 * nid[mm] + 8) = nq[mm];
         }
       }
     }
     __syncwarp();
-  }
+  };
+  if (dmax >= 2 * CHP) chunk(std::integral_constant<int, 2 * CM>());
+  if (dmax >= CHP) chunk(std::integral_constant<int, CM>());
+  chunk(std::integral_constant<int, 0>());
   FS2_STAMP(26);
 #pragma unroll
   for (int m = 1; m < L; m <<= 1) {

@@ -34,6 +34,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "mz_common.cuh"
 #include "mz_exp.cuh"
 #include "mz_fc_tc.cuh"
@@ -604,7 +606,7 @@ __host__ __device__ inline size_t fs_align16(size_t x) { return (x + 15) & ~(siz
 struct FsLayout {
   size_t a1, w, a3, bars, tail, sh, logit, val, rew, sp, mm, pbc, path_n, path_a, depth, total;
   size_t best_ca, node, xmask, par;  // sparse engine
-  size_t exp_tab;
+  size_t exp_tab, rcp;
   int ps, a4, gp, s1;
 };
 __host__ __device__ inline FsLayout fs_layout(int k1, int stages, int cl, int A, int S, bool sparse) {
@@ -632,11 +634,12 @@ __host__ __device__ inline FsLayout fs_layout(int k1, int stages, int cl, int A,
   L.path_a = off; off += (size_t)L.gp * L.ps;
   L.depth = off; off += fs_align16((size_t)L.gp);
   L.exp_tab = off; off += 256 * 8;
+  L.rcp = off; off += 64 * 8;
   L.pbc = L.best_ca = L.node = L.xmask = L.par = 0;
   if (sparse) {
     // exp / reward scratch and the per-node maxima are used in different phases: one region
-    const size_t sp_bytes = (size_t)L.gp * SP_STRIDE * 8, key_bytes = (size_t)L.gp * L.s1 * 8;
-    L.sp = off; off += fs_align16(sp_bytes > key_bytes ? sp_bytes : key_bytes);
+    const int row = L.s1 > SP_STRIDE ? L.s1 : SP_STRIDE;  // doubles per game (fs2::Smem::row)
+    L.sp = off; off += fs_align16((size_t)L.gp * row * 8);
     L.best_ca = off; off += (size_t)L.gp * L.s1 * 4;
     L.node = off; off += (size_t)L.gp * L.s1 * 4;
     L.xmask = off; off += (size_t)L.gp * L.s1 * 4;
@@ -720,7 +723,11 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
   sm2.par = smem + L.par;
   sm2.path_n = sm.path_n; sm2.path_a = sm.path_a; sm2.depth = sm.depth;
   sm2.ps = L.ps; sm2.a4 = L.a4; sm2.s1 = L.s1;
+  sm2.row = L.s1 > SP_STRIDE ? L.s1 : SP_STRIDE;
   sm2.exp_tab = exp_tab_w;
+  double* rcp_w = reinterpret_cast<double*>(smem + L.rcp);
+  sm2.rcp = rcp_w;
+  for (int i = threadIdx.x; i < 64; i += FS_THREADS) rcp_w[i] = i > 0 ? __drcp_rn((double)i) : 0.0;
   const fs2::Geo geo2 = fs2::geo(S, A);
 
   const uint32_t a1_bytes = (uint32_t)(ROWS * k1 * 2), a3_bytes = (uint32_t)(ROWS * K3 * 2);
