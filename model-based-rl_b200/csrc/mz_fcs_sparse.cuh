@@ -21,13 +21,14 @@
 // Per-game block in global memory (L2):   S1 = round_up(S + 1, 2) node slots, A2 = round_up(A, 2)
 //   header 64 B : f64 min | f64 max
 //   own[n]  16 B: f64 value_sum | f32 reward | u32 -
-//   edge[n] 16 B: f64 prior of the edge parent(n) -> n | f64 q(n) = reward -/+ discount * value()
-//   utop[n]  8 B: prior of the best unexpanded child of n
+//   edge[n] 32 B: f64 prior of the edge parent(n) -> n | f64 q(n) = reward -/+ discount * value()
+//                 | f64 utop(n) = prior of the best unexpanded child of n | -    (one record: an item of the
+//                 ranking pass reads 16 bytes at offset 0 (edge) or 16 (best unexpanded child), branch free)
 //   meta[n]  8 B: copy of the shared-memory node words at the end of the move (export / tests)
 //   pri[n][A2]  : all priors of node n (Node.expand, mcts.py:52-55; the root's include the Dirichlet noise)
-// Per-game shared memory: node word  N | action << 8 | uact << 16 (visit count, action from the parent, best
-// unexpanded action with bit 6 = rank densely, 0xff = none), mask of actions that are not unexpanded children
-// (expanded or illegal), parent id, and the per-node winners of the current simulation.
+// Per-game shared memory: node word  N | action << 8 | uact << 16 | parent << 24 (visit count, action from the
+// parent, best unexpanded action with bit 6 = rank densely, 0xff = none, parent id), mask of actions that are not
+// unexpanded children (expanded or illegal), and the per-node winners of the current simulation.
 #pragma once
 
 namespace fs2 {
@@ -49,12 +50,12 @@ struct Smem {
   uint32_t* best_ca;   // [GP][S1]  (action << 8) | child id (0xff: the child is unexpanded)
   uint32_t* node;      // [GP][S1]  N | action << 8 | uact << 16
   uint32_t* xmask;     // [GP][S1]
-  uint8_t* par;        // [GP][S1]
   uint8_t* path_n;     // [GP][PS]
   uint8_t* path_a;     // [GP][PS]
   uint8_t* depth;      // [GP]
   const unsigned long long* exp_tab;
   const double* rcp;   // [64] correctly rounded reciprocals of the visit counts 1..63
+  const double* pbc0;  // [64] pb_c[N][0]: the exploration factor of an unvisited child of a node with N visits
   int ps, a4, s1, row;  // row = doubles per game of the shared scratch row = max(S1, SP_STRIDE)
 };
 
@@ -73,9 +74,9 @@ __host__ __device__ inline Geo geo(int S, int A) {
   g.s1 = (S + 2) & ~1;
   g.a2 = (A + 1) & ~1;
   g.own = 64;
-  g.edge = g.own + 16 * g.s1;
-  g.utop = g.edge + 16 * g.s1;
-  g.meta = g.utop + 8 * g.s1;
+  g.edge = g.own + 16 * g.s1;   // 32-byte records: {prior of the edge into n, q(n), best unexpanded prior of n, -}
+  g.utop = g.edge + 16;         // (same records, third double)
+  g.meta = g.edge + 32 * g.s1;
   g.pri = g.meta + 8 * g.s1;
   g.bytes = ((long long)g.pri + (long long)g.s1 * 8 * g.a2 + 127) / 128 * 128;
   return g;
@@ -222,7 +223,6 @@ MZ_DEV void set_root(const FsParams& p, const Smem& sm, const Game& gm, const Ge
   if (gm.valid && gm.sub == 0) {
     sm.node[gm.gl * sm.s1] = 0u | (0xffu << 8) | ((uint32_t)uact << 16);
     sm.xmask[gm.gl * sm.s1] = ~lm;
-    sm.par[gm.gl * sm.s1] = 0;
     sm.mm[2 * gm.gl] = p.min_bound;
     sm.mm[2 * gm.gl + 1] = p.max_bound;
     *reinterpret_cast<uint4*>(gm.base + G.own) = make_uint4(0u, 0u, 0u, 0u);
@@ -287,12 +287,9 @@ MZ_DEV void descend(const FsParams& p, const Smem& sm, const Game& gm, const Geo
   const Norm nm = make_norm(sm.mm[2 * gm.gl], sm.mm[2 * gm.gl + 1]);
   uint32_t* node = sm.node + gm.gl * sm.s1;
   const uint32_t* xmask = sm.xmask + gm.gl * sm.s1;
-  const uint8_t* par = sm.par + gm.gl * sm.s1;
   uint32_t* best_hi = reinterpret_cast<uint32_t*>(sm.best_key + gm.gl * sm.row);
   uint32_t* best_lo = best_hi + sm.s1;
   uint32_t* best_ca = sm.best_ca + gm.gl * sm.s1;
-  const int n_items = gm.valid ? 2 * sim + 1 : 0;
-  const int n_items_max = 2 * sim + 1;  // warp uniform
   for (int n = gm.sub; n <= sim; n += L) {
     best_hi[n] = 0u;
     best_lo[n] = 0u;
@@ -300,64 +297,79 @@ MZ_DEV void descend(const FsParams& p, const Smem& sm, const Game& gm, const Geo
   }
   __syncwarp();
   FS2_STAMP(16);
-  uint32_t key_hi[MAX_ITEMS], key_lo[MAX_ITEMS], pack[MAX_ITEMS];  // pack: valid << 31 | parent << 16 | action << 8 | child
+  // Items: slot t of a lane is node n = 8 t + sub.  [0, NT): "U" = the best unexpanded child of node n (n <= sim);
+  // [NT, 2 NT): "E" = the edge into node n (1 <= n <= sim), ranked under its parent.
+  constexpr int NT = MAX_ITEMS / 2;
+  uint32_t key_hi[MAX_ITEMS], key_lo[MAX_ITEMS], pack[MAX_ITEMS];  // pack: valid << 31 | slow << 30 | parent << 16 | action << 8 | child
   bool any_slow = false;
-  constexpr int BT = 8;  // items per batch: all global loads of a batch are in flight together
+  const bool fast_norm = __all_sync(MZ_FULL, nm.mode == 2 || !gm.valid);  // the usual case: every game normalises
+  // ---- loads: edges first (two dependent shared-memory reads ahead of them), then the unexpanded-child priors ----
+  double2 ed[NT];
+  double pbc[NT], ut[NT];
+  uint32_t we[NT], wu[NT];
 #pragma unroll
-  for (int b0 = 0; b0 < MAX_ITEMS; b0 += BT) {
-    if (L * b0 >= n_items_max) {  // warp uniform: nothing left
+  for (int t = 0; t < NT; ++t) {
+    const int n = L * t + gm.sub;
+    ed[t] = make_double2(0.0, 0.0);
+    pbc[t] = 0.0;
+    we[t] = 0u;
+    if (L * t > sim) continue;  // warp uniform
+    const bool act = gm.valid && n >= 1 && n <= sim;
+    we[t] = node[act ? n : 0];
+    const int np_ = (int)(node[we[t] >> 24] & 0xffu), nj = (int)(we[t] & 0xffu);
+    pbc[t] = __ldg(p.pb_c + (size_t)np_ * SP1 + nj);
+    ed[t] = *reinterpret_cast<const double2*>(gm.base + G.edge + 32 * (act ? n : 0));
+  }
 #pragma unroll
-      for (int u = 0; u < BT; ++u) key_hi[b0 + u] = key_lo[b0 + u] = pack[b0 + u] = 0u;
-      continue;
+  for (int t = 0; t < NT; ++t) {
+    const int n = L * t + gm.sub;
+    ut[t] = 0.0;
+    wu[t] = 0u;
+    if (L * t > sim) continue;
+    const bool act = gm.valid && n <= sim;
+    wu[t] = node[act ? n : 0];
+    ut[t] = *reinterpret_cast<const double*>(gm.base + G.utop + 32 * (act ? n : 0));
+  }
+  // ---- scores of the unexpanded-child items: pb_c(N, 0) * prior + init_value_score (mcts.py:115-124) ----
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int n = L * t + gm.sub;
+    key_hi[t] = key_lo[t] = pack[t] = 0u;
+    if (L * t > sim) continue;
+    const int ua = (int)((wu[t] >> 16) & 0xffu);
+    const bool live = gm.valid && n <= sim && ua != UACT_NONE;
+    double score = __dadd_rn(__dmul_rn(sm.pbc0[wu[t] & 0x3fu], ut[t]), init_score);
+    if (sim == 0) score = ut[t];  // mcts.py:105-108: the unvisited root ranks its children by prior
+    const bool slow = (ua & UACT_DENSE) != 0;
+    any_slow = any_slow || (live && slow);
+    const unsigned long long k = sortable(score);
+    key_hi[t] = (uint32_t)(k >> 32);
+    key_lo[t] = (uint32_t)k;
+    pack[t] = live ? (0x80000000u | (slow ? 0x40000000u : 0u) | ((uint32_t)n << 16) | ((uint32_t)(ua & 0x3f) << 8) | 0xffu) : 0u;
+  }
+  // ---- scores of the edges: pb_c(N_parent, n) * prior + normalize(q) ----
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int n = L * t + gm.sub;
+    const int it = NT + t;
+    key_hi[it] = key_lo[it] = pack[it] = 0u;
+    if (L * t > sim) continue;
+    const bool live = gm.valid && n >= 1 && n <= sim;
+    const double q = ed[t].y;
+    const double x = __dsub_rn(q, nm.mn);
+    double vs = fs_div_by_const(x, nm.d, nm.r);  // exact for x == 0 too
+    const unsigned hx = (unsigned)__double2hiint(x);
+    bool slow = x != 0.0 && hx - 0x33700000u > 0x19000000u;
+    if (!fast_norm) {  // warp uniform
+      slow = nm.mode == 3 || (nm.mode == 2 && slow);
+      vs = nm.mode == 1 ? 1.0 : (nm.mode == 0 ? q : vs);
     }
-    // ---- loads ----
-    double prior[BT], q[BT], pbc[BT];
-    uint32_t wj[BT];
-    int pj[BT];
-#pragma unroll
-    for (int u = 0; u < BT; ++u) {
-      const int i = L * (b0 + u) + gm.sub;
-      const bool act = i < n_items, isu = i <= sim;
-      const int j = act ? (isu ? i : i - sim) : 0;
-      wj[u] = node[j];
-      pj[u] = isu ? j : (int)par[j];
-      const int np_ = (int)(node[pj[u]] & 0xffu), nj = isu ? 0 : (int)(wj[u] & 0xffu);
-      pbc[u] = __ldg(p.pb_c + (size_t)np_ * SP1 + nj);
-      if (isu) {
-        prior[u] = *reinterpret_cast<const double*>(gm.base + G.utop + 8 * j);
-        q[u] = 0.0;
-      } else {
-        const double2 e = *reinterpret_cast<const double2*>(gm.base + G.edge + 16 * j);
-        prior[u] = e.x;
-        q[u] = e.y;
-      }
-    }
-    // ---- scores ----
-#pragma unroll
-    for (int u = 0; u < BT; ++u) {
-      const int it = b0 + u;
-      const int i = L * it + gm.sub;
-      const bool act = i < n_items, isu = i <= sim;
-      const int ua = (int)((wj[u] >> 16) & 0xffu);
-      const bool live = act && !(isu && ua == UACT_NONE);
-      // value term: init_value_score for an unvisited child, the normalised q of a visited one
-      const double x = __dsub_rn(q[u], nm.mn);
-      double vs = fs_div_by_const(x, nm.d, nm.r);  // mode 2 (exact for x == 0 too); other modes selected / redone below
-      const unsigned hx = (unsigned)__double2hiint(x);
-      bool slow = !isu && (nm.mode == 3 || (nm.mode == 2 && x != 0.0 && hx - 0x33700000u > 0x19000000u));
-      vs = nm.mode == 1 ? 1.0 : (nm.mode == 0 ? q[u] : vs);
-      vs = isu ? init_score : vs;
-      double score = __dadd_rn(__dmul_rn(pbc[u], prior[u]), vs);
-      if (sim == 0) score = prior[u];  // mcts.py:105-108: the unvisited root ranks its children by prior
-      slow = slow || (isu && (ua & UACT_DENSE) && ua != UACT_NONE);
-      any_slow = any_slow || (live && slow);
-      const unsigned long long k = sortable(score);
-      key_hi[it] = (uint32_t)(k >> 32);
-      key_lo[it] = (uint32_t)k;
-      const uint32_t action = isu ? (uint32_t)(ua & 0x3f) : ((wj[u] >> 8) & 0xffu);
-      const uint32_t child = isu ? 0xffu : (uint32_t)(i - sim);
-      pack[it] = live ? (0x80000000u | (slow ? 0x40000000u : 0u) | ((uint32_t)pj[u] << 16) | (action << 8) | child) : 0u;
-    }
+    const double score = __dadd_rn(__dmul_rn(pbc[t], ed[t].x), vs);
+    any_slow = any_slow || (live && slow);
+    const unsigned long long k = sortable(score);
+    key_hi[it] = (uint32_t)(k >> 32);
+    key_lo[it] = (uint32_t)k;
+    pack[it] = live ? (0x80000000u | (slow ? 0x40000000u : 0u) | ((we[t] >> 24) << 16) | (((we[t] >> 8) & 0xffu) << 8) | (uint32_t)n) : 0u;
   }
   FS2_STAMP(17);
   if (__any_sync(MZ_FULL, any_slow)) {
@@ -365,19 +377,19 @@ MZ_DEV void descend(const FsParams& p, const Smem& sm, const Game& gm, const Geo
 #pragma unroll
     for (int it = 0; it < MAX_ITEMS; ++it) {  // unrolled: the item arrays must stay in registers
       if (!(pack[it] & 0x40000000u)) continue;
-      const int i = L * it + gm.sub;
+      const int n = L * (it < NT ? it : it - NT) + gm.sub;
       const int pn = (int)((pack[it] >> 16) & 0xffu);
       double score;
       uint32_t action = (pack[it] >> 8) & 0xffu;
-      if (i <= sim) {
-        const int N = (int)(node[i] & 0xffu);
-        const double pb_c = __ldg(p.pb_c + (size_t)N * SP1);
-        const uint32_t xm = xmask[i];
+      if (it < NT) {
+        const int N = (int)(node[n] & 0xffu);
+        const double pb_c = sm.pbc0[N & 0x3f];
+        const uint32_t xm = xmask[n];
         bool have = false;
         score = 0.0;
         for (int a = 0; a < A; ++a) {
           if ((xm >> a) & 1u) continue;
-          const double pr = *reinterpret_cast<const double*>(gm.base + G.pri + ((size_t)i * G.a2 + a) * 8);
+          const double pr = *reinterpret_cast<const double*>(gm.base + G.pri + ((size_t)n * G.a2 + a) * 8);
           const double sc = sim == 0 ? pr : __dadd_rn(__dmul_rn(pb_c, pr), init_score);
           if (!have || sc >= score) {
             score = sc;
@@ -386,9 +398,8 @@ MZ_DEV void descend(const FsParams& p, const Smem& sm, const Game& gm, const Geo
           }
         }
       } else {
-        const int j = i - sim;
-        const double2 e = *reinterpret_cast<const double2*>(gm.base + G.edge + 16 * j);
-        const double pb_c = __ldg(p.pb_c + (size_t)(node[pn] & 0xffu) * SP1 + (node[j] & 0xffu));
+        const double2 e = *reinterpret_cast<const double2*>(gm.base + G.edge + 32 * n);
+        const double pb_c = __ldg(p.pb_c + (size_t)(node[pn] & 0xffu) * SP1 + (node[n] & 0xffu));
         const double x = __dsub_rn(e.y, nm.mn);
         const double vs = (nm.mode == 2 && x == 0.0) ? 0.0 : __ddiv_rn(x, nm.d);
         score = __dadd_rn(__dmul_rn(pb_c, e.x), vs);
@@ -481,8 +492,68 @@ MZ_DEV double exp_fast(double x, const unsigned long long* tab, bool& bad) {
 // ------------------------------------------------------------------------------------------------------
 // expand (mcts.py:47-55) + backpropagate (mcts.py:126-143) of simulation `sim`
 // ------------------------------------------------------------------------------------------------------
+constexpr int MAXP = (MAX_S + 1 + L) / L;  // path positions per lane (depth <= S)
+
+// What the expansion of a simulation can prepare BEFORE the network outputs arrive (the leaf is known since the
+// descent): the path nodes' own records, the parent's next best unexpanded child and the prior of the new edge.
+// Runs while the lane would otherwise wait for the prediction heads of the other CTAs.
+struct Pre {
+  uint4 own[MAXP];
+  double ptop_par, edge_prior;
+  int uact_par, depth, parent, action, dmax;
+  uint32_t xm_par;
+};
+
 template <int AL>
-MZ_DEV void expand_backup(const FsParams& p, const Smem& sm, const Game& gm, const Geo& G, int sim, long long* tl) {
+MZ_DEV void pre_expand(const FsParams& p, const Smem& sm, const Game& gm, const Geo& G, Pre& pre) {
+  const int A = p.A;
+  const uint8_t* pn_ = sm.path_n + gm.gl * sm.ps;
+  const uint8_t* pa_ = sm.path_a + gm.gl * sm.ps;
+  const uint32_t* xmask = sm.xmask + gm.gl * sm.s1;
+  const int depth = gm.valid ? (int)sm.depth[gm.gl] : 0;
+  const int parent = gm.valid ? (int)pn_[depth - 1] : 0, action = gm.valid ? (int)pa_[depth - 1] : 0;
+  int dmax = depth;
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) dmax = max(dmax, __shfl_xor_sync(MZ_FULL, dmax, m));
+  double ppv[1][AL];
+#pragma unroll
+  for (int t = 0; t < AL; ++t) {
+    const int a = L * t + gm.sub;
+    ppv[0][t] = 0.0;
+    if (gm.valid && a < A) ppv[0][t] = *reinterpret_cast<const double*>(gm.base + G.pri + ((size_t)parent * G.a2 + a) * 8);
+  }
+#pragma unroll
+  for (int m = 0; m < MAXP; ++m) {
+    const int kk = L * m + gm.sub;
+    pre.own[m] = make_uint4(0u, 0u, 0u, 0u);
+    if (L * m <= dmax && gm.valid && kk < depth) pre.own[m] = ldg16(gm.base + G.own + 16 * (int)pn_[kk]);
+  }
+  const uint32_t xm_par = gm.valid ? (xmask[parent] | (1u << action)) : 0xffffffffu;
+  const uint32_t xms[1] = {xm_par};
+  double ptops[1];
+  int uacts[1];
+  top_unexpanded<AL, 1>(ppv, xms, A, gm.sub, p.init_score != 0.0, ptops, uacts);
+  // the prior of the new edge: the lane that holds the parent's prior of `action` hands it round
+  double edge_prior = 0.0;
+#pragma unroll
+  for (int t = 0; t < AL; ++t) {
+    const double v = __hiloint2double(__shfl_sync(MZ_FULL, __double2hiint(ppv[0][t]), action & (L - 1), L),
+                                      __shfl_sync(MZ_FULL, __double2loint(ppv[0][t]), action & (L - 1), L));
+    if (t == action / L) edge_prior = v;
+  }
+  pre.ptop_par = ptops[0];
+  pre.uact_par = uacts[0];
+  pre.edge_prior = edge_prior;
+  pre.depth = depth;
+  pre.parent = parent;
+  pre.action = action;
+  pre.dmax = dmax;
+  pre.xm_par = xm_par;
+}
+
+template <int AL>
+MZ_DEV void expand_backup(const FsParams& p, const Smem& sm, const Game& gm, const Geo& G, int sim, const Pre& pre,
+                          long long* tl) {
   const int A = p.A;
   const bool two = p.two_players != 0;
   const double disc = p.discount;
@@ -491,32 +562,10 @@ MZ_DEV void expand_backup(const FsParams& p, const Smem& sm, const Game& gm, con
   const float value_f = sm.val[gm.gl], reward_in = sm.rew[gm.gl];
   const float node_reward_new = (reward_in != 0.0f) ? reward_in : 0.0f;  // `if network_output.reward:`
   const uint8_t* pn_ = sm.path_n + gm.gl * sm.ps;
-  const uint8_t* pa_ = sm.path_a + gm.gl * sm.ps;
   uint32_t* node = sm.node + gm.gl * sm.s1;
   uint32_t* xmask = sm.xmask + gm.gl * sm.s1;
-  const int depth = gm.valid ? (int)sm.depth[gm.gl] : 0;
-  const int parent = gm.valid ? (int)pn_[depth - 1] : 0, action = gm.valid ? (int)pa_[depth - 1] : 0;
-  int dmax = depth;
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) dmax = max(dmax, __shfl_xor_sync(MZ_FULL, dmax, m));
-
-  // loads that do not depend on the expansion arithmetic: the parent's priors (its next best unexpanded child and
-  // the prior of the new edge) and the path nodes' own records (value sums, rewards)
-  double ppv[AL];
-#pragma unroll
-  for (int t = 0; t < AL; ++t) {
-    const int a = L * t + gm.sub;
-    ppv[t] = 0.0;
-    if (gm.valid && a < A) ppv[t] = *reinterpret_cast<const double*>(gm.base + G.pri + ((size_t)parent * G.a2 + a) * 8);
-  }
-  constexpr int MAXP = (MAX_S + 1 + L) / L;  // path positions per lane (depth <= S)
-  uint4 own[MAXP];
-#pragma unroll
-  for (int m = 0; m < MAXP; ++m) {
-    const int kk = L * m + gm.sub;
-    own[m] = make_uint4(0u, 0u, 0u, 0u);
-    if (L * m <= dmax && gm.valid && kk < depth) own[m] = ldg16(gm.base + G.own + 16 * (int)pn_[kk]);
-  }
+  const int depth = pre.depth, parent = pre.parent, action = pre.action, dmax = pre.dmax;
+  const uint4 (&own)[MAXP] = pre.own;
   if (gm.valid) {
     if (gm.sub == 0) {
       if (p.rec_value) p.rec_value[(size_t)sim * p.G + gm.g] = value_f;
@@ -585,34 +634,22 @@ MZ_DEV void expand_backup(const FsParams& p, const Smem& sm, const Game& gm, con
   FS2_STAMP(24);
   const bool force_dense = p.init_score != 0.0;
   const uint32_t all = A < 32 ? (1u << A) - 1u : 0xffffffffu;
-  const uint32_t xm_par = gm.valid ? (xmask[parent] | (1u << action)) : 0xffffffffu;
-  double pvs[2][AL], ptops[2];
-  int uacts[2];
+  double pvs[1][AL], ptops[1];
+  int uacts[1];
 #pragma unroll
-  for (int t = 0; t < AL; ++t) {
-    pvs[0][t] = pv[t];
-    pvs[1][t] = ppv[t];
-  }
-  const uint32_t xms[2] = {~all, xm_par};
-  top_unexpanded<AL, 2>(pvs, xms, A, gm.sub, force_dense, ptops, uacts);
-  const double ptop_new = ptops[0], ptop_par = ptops[1];
-  const int uact_new = uacts[0], uact_par = uacts[1];
-  // the prior of the new edge: the lane that holds the parent's prior of `action` hands it round
-  double edge_prior = 0.0;
-#pragma unroll
-  for (int t = 0; t < AL; ++t) {
-    const double v = __hiloint2double(__shfl_sync(MZ_FULL, __double2hiint(ppv[t]), action & (L - 1), L),
-                                      __shfl_sync(MZ_FULL, __double2loint(ppv[t]), action & (L - 1), L));
-    if (t == action / L) edge_prior = v;
-  }
+  for (int t = 0; t < AL; ++t) pvs[0][t] = pv[t];
+  const uint32_t xms[1] = {~all};
+  top_unexpanded<AL, 1>(pvs, xms, A, gm.sub, force_dense, ptops, uacts);
+  const double ptop_new = ptops[0], ptop_par = pre.ptop_par, edge_prior = pre.edge_prior;
+  const int uact_new = uacts[0], uact_par = pre.uact_par;
+  const uint32_t xm_par = pre.xm_par;
   if (gm.valid && gm.sub == 0) {
-    node[newn] = 0u | ((uint32_t)action << 8) | ((uint32_t)uact_new << 16);
+    node[newn] = 0u | ((uint32_t)action << 8) | ((uint32_t)uact_new << 16) | ((uint32_t)parent << 24);
     xmask[newn] = ~all;
-    sm.par[gm.gl * sm.s1 + newn] = (uint8_t)parent;
-    *reinterpret_cast<double*>(gm.base + G.utop + 8 * newn) = ptop_new;
+    *reinterpret_cast<double*>(gm.base + G.utop + 32 * newn) = ptop_new;
     node[parent] = (node[parent] & 0xff00ffffu) | ((uint32_t)uact_par << 16);
     xmask[parent] = xm_par;
-    if (uact_par != UACT_NONE) *reinterpret_cast<double*>(gm.base + G.utop + 8 * parent) = ptop_par;
+    if (uact_par != UACT_NONE) *reinterpret_cast<double*>(gm.base + G.utop + 32 * parent) = ptop_par;
   }
   __syncwarp();
   FS2_STAMP(25);
@@ -700,8 +737,8 @@ MZ_DEV void expand_backup(const FsParams& p, const Smem& sm, const Game& gm, con
         if (kk > 0) {
           lmin = fmin(lmin, nq[mm]);
           lmax = fmax(lmax, nq[mm]);
-          if (kk == depth) *reinterpret_cast<double2*>(gm.base + G.edge + 16 * nid[mm]) = make_double2(edge_prior, nq[mm]);
-          else *reinterpret_cast<double*>(gm.base + G.edge + 16 * nid[mm] + 8) = nq[mm];
+          if (kk == depth) *reinterpret_cast<double2*>(gm.base + G.edge + 32 * nid[mm]) = make_double2(edge_prior, nq[mm]);
+          else *reinterpret_cast<double*>(gm.base + G.edge + 32 * nid[mm] + 8) = nq[mm];
         }
       }
     }
@@ -728,7 +765,6 @@ MZ_DEV void root_stats(const FsParams& p, const Smem& sm, const Game& gm, const 
   if (!gm.valid) return;
   const int A = p.A, S = p.S;
   const uint32_t* node = sm.node + gm.gl * sm.s1;
-  const uint8_t* par = sm.par + gm.gl * sm.s1;
   const uint32_t lm = ~sm.xmask[gm.gl * sm.s1] | 0u;  // after the search the root's mask also has its expanded children
   (void)lm;
   uint32_t legal = p.legal ? p.legal[gm.g] : 0xffffffffu;
@@ -740,16 +776,16 @@ MZ_DEV void root_stats(const FsParams& p, const Smem& sm, const Game& gm, const 
   __syncwarp(0xffu << ((threadIdx.x & 31u) & ~7u));
   int sum = 0;
   for (int j = 1; j <= S; ++j)
-    if (par[j] == 0) sum += (int)(node[j] & 0xffu);
+    if ((node[j] >> 24) == 0u) sum += (int)(node[j] & 0xffu);
   for (int j = 1 + gm.sub; j <= S; j += L) {
-    if (par[j] == 0) {
+    if ((node[j] >> 24) == 0u) {
       const int a = (int)((node[j] >> 8) & 0xffu), v = (int)(node[j] & 0xffu);
       if (p.visits) p.visits[(size_t)gm.g * A + a] = v;
       if (p.child_visits) p.child_visits[(size_t)gm.g * A + a] = __ddiv_rn((double)v, (double)sum);
     }
   }
   for (int n = gm.sub; n <= S; n += L)
-    *reinterpret_cast<uint2*>(gm.base + G.meta + 8 * n) = make_uint2(node[n] | ((uint32_t)par[n] << 24), sm.xmask[gm.gl * sm.s1 + n]);
+    *reinterpret_cast<uint2*>(gm.base + G.meta + 8 * n) = make_uint2(node[n], sm.xmask[gm.gl * sm.s1 + n]);
   if (gm.sub == 0) {
     const uint4 o = ldg16(gm.base + G.own);
     const int n = (int)(node[0] & 0xffu);

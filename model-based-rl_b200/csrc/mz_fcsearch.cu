@@ -606,7 +606,7 @@ __host__ __device__ inline size_t fs_align16(size_t x) { return (x + 15) & ~(siz
 struct FsLayout {
   size_t a1, w, a3, bars, tail, sh, logit, val, rew, sp, mm, pbc, path_n, path_a, depth, total;
   size_t best_ca, node, xmask, par;  // sparse engine
-  size_t exp_tab, rcp;
+  size_t exp_tab, rcp, pbf;
   int ps, a4, gp, s1;
 };
 __host__ __device__ inline FsLayout fs_layout(int k1, int stages, int cl, int A, int S, bool sparse) {
@@ -635,6 +635,7 @@ __host__ __device__ inline FsLayout fs_layout(int k1, int stages, int cl, int A,
   L.depth = off; off += fs_align16((size_t)L.gp);
   L.exp_tab = off; off += 256 * 8;
   L.rcp = off; off += 64 * 8;
+  L.pbf = off; off += 64 * 8;
   L.pbc = L.best_ca = L.node = L.xmask = L.par = 0;
   if (sparse) {
     // exp / reward scratch and the per-node maxima are used in different phases: one region
@@ -643,7 +644,6 @@ __host__ __device__ inline FsLayout fs_layout(int k1, int stages, int cl, int A,
     L.best_ca = off; off += (size_t)L.gp * L.s1 * 4;
     L.node = off; off += (size_t)L.gp * L.s1 * 4;
     L.xmask = off; off += (size_t)L.gp * L.s1 * 4;
-    L.par = off; off += fs_align16((size_t)L.gp * L.s1);
   } else {
     L.sp = off; off += fs_align16((size_t)L.gp * SP_STRIDE * 8);
     L.pbc = off; off += fs_align16((size_t)(S + 1) * (S + 2) / 2 * 8);
@@ -720,7 +720,6 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
   sm2.best_ca = reinterpret_cast<uint32_t*>(smem + L.best_ca);
   sm2.node = reinterpret_cast<uint32_t*>(smem + L.node);
   sm2.xmask = reinterpret_cast<uint32_t*>(smem + L.xmask);
-  sm2.par = smem + L.par;
   sm2.path_n = sm.path_n; sm2.path_a = sm.path_a; sm2.depth = sm.depth;
   sm2.ps = L.ps; sm2.a4 = L.a4; sm2.s1 = L.s1;
   sm2.row = L.s1 > SP_STRIDE ? L.s1 : SP_STRIDE;
@@ -728,6 +727,9 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
   double* rcp_w = reinterpret_cast<double*>(smem + L.rcp);
   sm2.rcp = rcp_w;
   for (int i = threadIdx.x; i < 64; i += FS_THREADS) rcp_w[i] = i > 0 ? __drcp_rn((double)i) : 0.0;
+  double* pbc0_w = reinterpret_cast<double*>(smem + L.pbf);
+  sm2.pbc0 = pbc0_w;
+  for (int i = threadIdx.x; i < 64; i += FS_THREADS) pbc0_w[i] = i <= S ? p.pb_c[(size_t)i * (S + 1)] : 0.0;
   const fs2::Geo geo2 = fs2::geo(S, A);
 
   const uint32_t a1_bytes = (uint32_t)(ROWS * k1 * 2), a3_bytes = (uint32_t)(ROWS * K3 * 2);
@@ -900,11 +902,13 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
       }
     };
     arm();
+    FS_STAMP(0, 13);
     if (tree_role) {
       if constexpr (SPARSE) fs2::set_root<(AL > 0 ? AL : 1)>(p, sm2, gm2, geo2);
       else fs_set_root<T>(p, sm, gm);
     }
     __syncwarp();
+    FS_STAMP(0, 14);
 
     uint32_t v[32], v2[32];
     int gc = 0, d2ph = 0;
@@ -941,16 +945,21 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
       FS_STAMP(sim < S ? sim : S - 1, sim < S ? 0 : 12);
       if (sim > 0) {
         if (tree_role) {
-          fs_wait_cluster(out_full, (sim - 1) & 1, err, 10);
-          if (sim < S) arm();
-          FS_STAMP(sim - 1, 10);
-          if constexpr (SPARSE)
-            fs2::expand_backup<(AL > 0 ? AL : 1)>(p, sm2, gm2, geo2, sim - 1,
+          if constexpr (SPARSE) {
+            fs2::Pre pre;
+            fs2::pre_expand<(AL > 0 ? AL : 1)>(p, sm2, gm2, geo2, pre);  // overlaps the wait for the outputs
+            fs_wait_cluster(out_full, (sim - 1) & 1, err, 10);
+            if (sim < S) arm();
+            FS_STAMP(sim - 1, 10);
+            fs2::expand_backup<(AL > 0 ? AL : 1)>(p, sm2, gm2, geo2, sim - 1, pre,
                                                   stamp ? p.timeline + (size_t)(sim - 1) * 32 : nullptr);
-          else fs_expand_backup<T>(p, sm, gm, sim - 1);
+          } else {
+            fs_wait_cluster(out_full, (sim - 1) & 1, err, 10);
+            if (sim < S) arm();
+            FS_STAMP(sim - 1, 10);
+            fs_expand_backup<T>(p, sm, gm, sim - 1);
+          }
           FS_STAMP(sim - 1, 11);
-        } else if (sim < S) {
-          // (CL = 4: the second epilogue group has no games; thread 0, which arms, is always a tree lane)
         }
       }
       if (sim == S) break;
@@ -1132,6 +1141,7 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
       if constexpr (SPARSE) fs2::root_stats(p, sm2, gm2, geo2);
       else fs_root_stats(p, sm, gm);
     }
+    FS_STAMP(S - 1, 15);
 #undef FS_STAMP
   }
 
@@ -1185,7 +1195,7 @@ __global__ void fs2_export_kernel(const uint8_t* games, long long game_bytes, in
     if (n > 0 && (m.x & 0xffu) > 0) {
       const int par = (int)(m.x >> 24), act = (int)((m.x >> 8) & 0xffu);
       if (child) child[par * A + act] = n;
-      if (q_out) q_out[par * A + act] = *reinterpret_cast<const double*>(base + G.edge + 16 * n + 8);
+      if (q_out) q_out[par * A + act] = *reinterpret_cast<const double*>(base + G.edge + 32 * n + 8);
     }
   }
 }

@@ -101,6 +101,9 @@ def timing(G, S=50, A=18, D=128, moves=20):
       med = np.median(rel[5:], axis=0)
       print("  timeline (cycles after the start of a simulation's descent, median over sims 5..):")
       print("   ", ", ".join("%s %d" % (names[k], med[k]) for k in sorted(names)))
+      print("   kernel body (after set-up) %d cycles = %.1f x the median sim period; root set-up %d; last backup + root stats %d" % (
+          tl[-1, 15] - tl[0, 13], (tl[-1, 15] - tl[0, 13]) / np.median(tl[1:, 0] - tl[:-1, 0]), tl[0, 14] - tl[0, 13],
+          tl[-1, 15] - tl[-1, 12]))
       nxt = tl[1:, 0] - tl[:-1, 0]
       print("   sim period median %d cycles" % np.median(nxt))
       if engine == 1:
