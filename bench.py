@@ -39,8 +39,8 @@ def FC_FLOPS_PER_EXPANSION(A):
 def parse():
   p = argparse.ArgumentParser()
   p.add_argument("--gpus", type=int, default=1)
-  p.add_argument("--steps", type=int, default=20)
-  p.add_argument("--warmup", type=int, default=3)
+  p.add_argument("--steps", type=int, default=200)  # ~0.2 s of timed moves: enough NVML clock samples under load
+  p.add_argument("--warmup", type=int, default=5)
   p.add_argument("--impl", choices=["b200", "reference"], default="b200")
   p.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
   p.add_argument("--sims", type=int, default=50)
@@ -568,10 +568,16 @@ def bench_other_configs(args, torch, dev, timed):
   return out
 
 
-def _source_sha16(name):
+def _source_sha16(names):
+  """sha256 over the kernel's source files ('a.cu+b.cuh': concatenated in that order), first 16 hex digits."""
   import hashlib
-  path = os.path.join(REPO, "model-based-rl_b200", "csrc", name)
-  return hashlib.sha256(open(path, "rb").read()).hexdigest()[:16] if os.path.exists(path) else None
+  h = hashlib.sha256()
+  for name in names.split("+"):
+    path = os.path.join(REPO, "model-based-rl_b200", "csrc", name)
+    if not os.path.exists(path):
+      return None
+    h.update(open(path, "rb").read())
+  return h.hexdigest()[:16]
 
 
 def ncu_traffic(kernel, games, A, S):

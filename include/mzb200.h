@@ -310,7 +310,7 @@ int mz_fc_search_export(const mz_fc_search_args* a, int32_t game, double* prior,
                         double* vsum, int32_t* visit, float* reward, double* q, void* stream);
 /* cluster size of mz_fc_search: 2 (rank 0 = reward + value heads, rank 1 = transition + policy, weights
  * streamed per simulation), 4 (one head per CTA, weights resident in shared memory), 0 = default
- * (MZ_FS_CLUSTER in the environment, else 2). */
+ * (MZ_FS_CLUSTER in the environment, else 4). */
 int mz_fc_search_set_cluster(int32_t cluster);
 /* tree engine of mz_fc_search: 0 = dense (four lanes per game walk the tree level by level, every action of a
  * node scored), 1 = sparse (clusters of four, S <= 63: every expanded node ranks only its expanded children and

@@ -46,8 +46,10 @@ struct Smem {
   double* sp;          // [GP][row] exp(logit) / signed-reward scratch.  It shares each game's row with best_key
                        //           (the two are used in different phases of the SAME game; rows of different games
                        //           never overlap, so warps in different phases cannot disturb each other)
-  unsigned long long* best_key;  // [GP][row]: per-node maxima, as two u32 arrays [S1] (high / low key words)
-  uint32_t* best_ca;   // [GP][S1]  (action << 8) | child id (0xff: the child is unexpanded)
+  unsigned long long* best_key;  // [GP][row]: the order-preserving score key of the edge into every node
+  uint16_t* best_ca;   // [GP][S1]  winner of select_child per node: (action << 8) | child id (0xff: unexpanded)
+  uint8_t* first;      // [GP][S1]  first expanded child of a node (0 = none: the root is nobody's child)
+  uint8_t* next;       // [GP][S1]  next expanded child of the same parent
   uint32_t* node;      // [GP][S1]  N | action << 8 | uact << 16
   uint32_t* xmask;     // [GP][S1]
   uint8_t* path_n;     // [GP][PS]
@@ -222,6 +224,7 @@ MZ_DEV void set_root(const FsParams& p, const Smem& sm, const Game& gm, const Ge
   const int uact = uacts[0];
   if (gm.valid && gm.sub == 0) {
     sm.node[gm.gl * sm.s1] = 0u | (0xffu << 8) | ((uint32_t)uact << 16);
+    sm.first[gm.gl * sm.s1] = 0;
     sm.xmask[gm.gl * sm.s1] = ~lm;
     sm.mm[2 * gm.gl] = p.min_bound;
     sm.mm[2 * gm.gl + 1] = p.max_bound;
@@ -287,15 +290,10 @@ MZ_DEV void descend(const FsParams& p, const Smem& sm, const Game& gm, const Geo
   const Norm nm = make_norm(sm.mm[2 * gm.gl], sm.mm[2 * gm.gl + 1]);
   uint32_t* node = sm.node + gm.gl * sm.s1;
   const uint32_t* xmask = sm.xmask + gm.gl * sm.s1;
-  uint32_t* best_hi = reinterpret_cast<uint32_t*>(sm.best_key + gm.gl * sm.row);
-  uint32_t* best_lo = best_hi + sm.s1;
-  uint32_t* best_ca = sm.best_ca + gm.gl * sm.s1;
-  for (int n = gm.sub; n <= sim; n += L) {
-    best_hi[n] = 0u;
-    best_lo[n] = 0u;
-    best_ca[n] = 0u;
-  }
-  __syncwarp();
+  unsigned long long* ekey = sm.best_key + gm.gl * sm.row;
+  uint16_t* best_ca = sm.best_ca + gm.gl * sm.s1;
+  const uint8_t* first = sm.first + gm.gl * sm.s1;
+  const uint8_t* next = sm.next + gm.gl * sm.s1;
   FS2_STAMP(16);
   // Items: slot t of a lane is node n = 8 t + sub.  [0, NT): "U" = the best unexpanded child of node n (n <= sim);
   // [NT, 2 NT): "E" = the edge into node n (1 <= n <= sim), ranked under its parent.
@@ -410,23 +408,77 @@ MZ_DEV void descend(const FsParams& p, const Smem& sm, const Game& gm, const Geo
       pack[it] = (pack[it] & 0xffff00ffu) | (action << 8);
     }
   }
-  // ---- per-parent maximum over (score, action): three rounds of 32-bit atomics ----
+  // ---- select_child per node: max over (score, action), ties -> larger action (mcts.py:106-112) ----
+  // edge keys go to shared memory, indexed by the child node
 #pragma unroll
-  for (int it = 0; it < MAX_ITEMS; ++it)
-    if (pack[it]) atomicMax(&best_hi[(pack[it] >> 16) & 0xffu], key_hi[it]);
-  __syncwarp();
-#pragma unroll
-  for (int it = 0; it < MAX_ITEMS; ++it)
-    if (pack[it] && key_hi[it] == best_hi[(pack[it] >> 16) & 0xffu]) atomicMax(&best_lo[(pack[it] >> 16) & 0xffu], key_lo[it]);
+  for (int t = 0; t < NT; ++t) {
+    const int n = L * t + gm.sub;
+    if (L * t > sim) continue;
+    if (pack[NT + t]) ekey[n] = ((unsigned long long)key_hi[NT + t] << 32) | key_lo[NT + t];
+  }
   __syncwarp();
   FS2_STAMP(18);
-  // ties -> larger action (mcts.py:106-112): among the items that reach a node's maximum the largest action wins
+  // the root (many children): every lane ranks the root's edges it owns, lane 0 adds the root's best unexpanded
+  // child, then a butterfly over the eight lanes
+  {
+    unsigned long long bk = 0ull;
+    int bac = -1;  // (action << 8) | child
 #pragma unroll
-  for (int it = 0; it < MAX_ITEMS; ++it) {
-    if (pack[it]) {
-      const int pn = (int)((pack[it] >> 16) & 0xffu);
-      if (key_hi[it] == best_hi[pn] && key_lo[it] == best_lo[pn]) atomicMax(&best_ca[pn], pack[it] & 0xffffu);
+    for (int t = 0; t < NT; ++t) {
+      if (L * t > sim) continue;
+      const uint32_t pk = pack[NT + t];
+      if (pk && ((pk >> 16) & 0xffu) == 0u) {
+        const unsigned long long k = ((unsigned long long)key_hi[NT + t] << 32) | key_lo[NT + t];
+        const int ac = (int)(pk & 0xffffu);
+        if (k > bk || (k == bk && ac > bac)) {
+          bk = k;
+          bac = ac;
+        }
+      }
     }
+    if (gm.sub == 0 && pack[0]) {
+      const unsigned long long k = ((unsigned long long)key_hi[0] << 32) | key_lo[0];
+      const int ac = (int)(pack[0] & 0xffffu);
+      if (k > bk || (k == bk && ac > bac)) {
+        bk = k;
+        bac = ac;
+      }
+    }
+#pragma unroll
+    for (int m = 1; m < L; m <<= 1) {
+      const uint32_t ohi = __shfl_xor_sync(MZ_FULL, (uint32_t)(bk >> 32), m, L);
+      const uint32_t olo = __shfl_xor_sync(MZ_FULL, (uint32_t)bk, m, L);
+      const int oac = __shfl_xor_sync(MZ_FULL, bac, m, L);
+      const unsigned long long ok = ((unsigned long long)ohi << 32) | olo;
+      if (ok > bk || (ok == bk && oac > bac)) {
+        bk = ok;
+        bac = oac;
+      }
+    }
+    if (gm.valid && gm.sub == 0) best_ca[0] = (uint16_t)bac;
+  }
+  // every other node: its owner lane walks the list of its expanded children
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int n = L * t + gm.sub;
+    if (L * t > sim) continue;
+    const bool act = gm.valid && n >= 1 && n <= sim;
+    unsigned long long bk = pack[t] ? (((unsigned long long)key_hi[t] << 32) | key_lo[t]) : 0ull;
+    int bac = pack[t] ? (int)(pack[t] & 0xffffu) : -1;
+    int c = act ? (int)first[n] : 0;
+    while (__any_sync(MZ_FULL, c != 0)) {
+      if (c != 0) {
+        const unsigned long long k = ekey[c];
+        const int ac = (int)(((node[c] >> 8) & 0xffu) << 8) | c;
+        const int nx = (int)next[c];
+        if (k > bk || (k == bk && ac > bac)) {
+          bk = k;
+          bac = ac;
+        }
+        c = nx;
+      }
+    }
+    if (act) best_ca[n] = (uint16_t)bac;
   }
   __syncwarp();
   FS2_STAMP(19);
@@ -439,7 +491,7 @@ MZ_DEV void descend(const FsParams& p, const Smem& sm, const Game& gm, const Geo
   for (;;) {
 #pragma unroll
     for (int rep = 0; rep < 2; ++rep) {  // finished games idle through the extra level
-      const uint32_t ca = best_ca[cur];
+      const uint32_t ca = (uint32_t)best_ca[cur];
       const int a = (int)(ca >> 8), c = (int)(ca & 0xffu);
       if (!done && gm.sub == 0) {
         pa_[depth] = (uint8_t)a;
@@ -645,6 +697,9 @@ MZ_DEV void expand_backup(const FsParams& p, const Smem& sm, const Game& gm, con
   const uint32_t xm_par = pre.xm_par;
   if (gm.valid && gm.sub == 0) {
     node[newn] = 0u | ((uint32_t)action << 8) | ((uint32_t)uact_new << 16) | ((uint32_t)parent << 24);
+    sm.next[gm.gl * sm.s1 + newn] = sm.first[gm.gl * sm.s1 + parent];
+    sm.first[gm.gl * sm.s1 + parent] = (uint8_t)newn;
+    sm.first[gm.gl * sm.s1 + newn] = 0;
     xmask[newn] = ~all;
     *reinterpret_cast<double*>(gm.base + G.utop + 32 * newn) = ptop_new;
     node[parent] = (node[parent] & 0xff00ffffu) | ((uint32_t)uact_par << 16);

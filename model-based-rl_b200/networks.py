@@ -382,7 +382,7 @@ class FCSearch(object):
   def __init__(self, config, fcnet, num_games, noise_frac=None, use_graph=True, num_streams=1, fused=None):
     """fused: True = the whole move in one persistent kernel (`mz_fc_search`, csrc/mz_fcsearch.cu), False =
     one tree launch + one network launch per simulation on `num_streams` slices, None = fused whenever the
-    network runs in bf16 and the shape fits the kernel AND MZ_FUSED=1 is set in the environment.
+    network runs in bf16, the shape fits the kernel and at most 8192 games play (MZ_FUSED=0 in the environment turns the default off).
     Both give bit-identical searches (tests/test_gpu_fcnet.py)."""
     self.net = fcnet
     G, A, dev = int(num_games), int(config.action_space), fcnet.device
@@ -413,7 +413,10 @@ class FCSearch(object):
     can_fuse = (fcnet.precision == 'bf16' and fcnet.weights is not None and
                 int(fcnet.lib.mz_fc_search_supported(self.S, A)) == 1)
     if fused is None:
-      fused = can_fuse and os.environ.get("MZ_FUSED", "0") == "1"
+      # measured (profiles/r02l_fused_sweep.log): the persistent kernel wins wherever one wave of clusters holds
+      # the games (C4 204 vs 140, C1 254 vs 199, C3 253 vs 196 M expansions/s), ties at 1024 games and loses a
+      # few per cent from 16 384 games on, where the per-launch path has more games in flight per SM
+      fused = can_fuse and os.environ.get("MZ_FUSED", "1") != "0" and G <= 8192
     elif fused and not can_fuse:
       raise ValueError("the fused search kernel needs a bf16 FCNetwork with loaded weights, A <= 32 and a "
                        "tree that fits its shared-memory plan")

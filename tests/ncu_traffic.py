@@ -1,6 +1,6 @@
 """Writes profiles/traffic.json entries from an `ncu --set full` capture (run here, no GPU needed):
 
-  python tests/ncu_traffic.py gpurun_out/x.ncu-rep KERNEL_REGEX SOURCE.cu GAMES ACTIONS SIMS [launch_index]
+  python tests/ncu_traffic.py gpurun_out/x.ncu-rep KERNEL_REGEX SOURCE.cu[+MORE.cuh] GAMES ACTIONS SIMS [launch_index]
 
 dram_bytes_per_launch = dram__bytes_read.sum + dram__bytes_write.sum of the selected launch.  bench.py's
 `roofline.traffic` reads the entry back only while csrc/SOURCE.cu is byte-identical to the captured one
@@ -36,11 +36,13 @@ def main():
   dur = float(r[col["gpu__time_duration.sum"]].replace(",", "")) if "gpu__time_duration.sum" in col else None
   path = os.path.join(REPO, "profiles", "traffic.json")
   doc = json.load(open(path)) if os.path.exists(path) else {"entries": []}
-  src = os.path.join(REPO, "model-based-rl_b200", "csrc", source)
+  h = hashlib.sha256()
+  for name in source.split("+"):
+    h.update(open(os.path.join(REPO, "model-based-rl_b200", "csrc", name), "rb").read())
   kname = re.search(r"(\w+)\s*(<[^>]*>)?\(", r[col["Kernel Name"]]).group(1)
   entry = {"kernel": kname, "games": int(games), "actions": int(actions),
            "sims": int(sims), "dram_bytes_per_launch": total, "capture": os.path.basename(rep), "source": source,
-           "source_sha16": hashlib.sha256(open(src, "rb").read()).hexdigest()[:16],
+           "source_sha16": h.hexdigest()[:16],
            "duration_under_ncu": dur, "duration_unit": units[col["gpu__time_duration.sum"]] if dur is not None else None}
   doc["entries"] = [e for e in doc["entries"] if (e["kernel"], e["games"], e["actions"], e["sims"]) !=
                     (entry["kernel"], entry["games"], entry["actions"], entry["sims"])] + [entry]
