@@ -62,6 +62,7 @@ def parse():
                  help="1: the whole move in one persistent kernel (mz_fc_search); 0: one tree + one network launch per "
                       "simulation; auto: FCSearch's default (MZ_FUSED in the environment)")
   p.add_argument("--no-f32", action="store_true", help="skip the float32-network throughput line")
+  p.add_argument("--no-selfplay", action="store_true", help="skip the self-play driver section")
   p.add_argument("--ref-moves-per-step", type=int, default=2,
                  help="reference arm: moves each worker plays per step")
   return p.parse_args()
@@ -465,6 +466,8 @@ def run_b200(args):
   others = bench_other_configs(args, torch, dev, timed) if rank == 0 and world == 1 and not args.no_sweep else None
   targets = bench_targets(torch, _lib, dev) if rank == 0 else None
   replay = bench_replay(torch, _lib, dev, cpu_baseline=not args.no_cpu_baseline) if rank == 0 else None
+  selfplay = (bench_selfplay(args, torch, dev, cpu_baseline["value"] if cpu_baseline else None)
+              if rank == 0 and world == 1 and not args.no_selfplay else None)
   learner = bench_learner(torch, _lib, dev, world, barrier)  # every rank: the step all-reduces at N > 1
   conv = bench_conv(args, torch, _lib, dev) if rank == 0 and not args.no_conv else None
 
@@ -527,7 +530,7 @@ def run_b200(args):
         "kernel_share": kern, "kernel_share_all_games_one_launch": kern_full,
         "fused_search_kernel": fs.fused is not None, "l2": L2_POLICY,
         "cuda_graph": not args.no_graph, "streams": n_slices, "f32_network": f32_line,
-        "games_sweep": sweep, "other_configs": others, "targets": targets, "replay": replay, "learner": learner,
+        "games_sweep": sweep, "other_configs": others, "targets": targets, "replay": replay, "selfplay": selfplay, "learner": learner,
         "conv": conv,
     }
     if cpu_baseline is not None:
@@ -860,6 +863,60 @@ def bench_replay(torch, _lib, dev, cpu_baseline=True):
     out["cpu_baseline"] = {"value": rows / dt, "unit": "samples/s", "cores": 1, "kind": "port",
                            "sample": "%d rows in %.1f s: python SumTree descent + C insert_target per row "
                                      "(the reference's sample_batch is a per-row Python loop in one Ray actor)" % (rows, dt)}
+  return out
+
+
+def bench_selfplay(args, torch, dev, cpu_expansions_per_s=None):
+  """The actor replacement end to end: `DeviceActor.play_move` at the C4 shape --
+  4096 games, A = 18, 50 simulations, 128-byte observations from a synthetic vector environment -- with the
+  trajectories written on the device into a Breakout-sized replay window (200 000 memories, 500-step chunks with
+  the K + td overlap) and priorities added per finished chunk.  Wall clock per move, everything included: host
+  environment step, noise / uniform draws, the search call with its copies, the append launch, chunk commits.
+  `list_path` is the same move through BatchedActor (per-game Python lists, HistorySlice upload)."""
+  import types
+  from model_based_rl_b200.environments import SyntheticRam
+  from model_based_rl_b200.networks import FCNetwork, FCSearch, random_state_dict
+  from model_based_rl_b200.replay_buffer import PrioritizedReplay
+  from model_based_rl_b200.selfplay import BatchedActor, DeviceActor
+  G, A, S, D = args.games, args.actions, args.sims, args.obs_dim
+  cfg = search_config(args)
+  for k, v in dict(num_unroll_steps=5, td_steps=10, max_history_length=500, max_steps=27000, batch_size=512,
+                   beta_increment_per_sampling=0.001, epsilon=0.01, alpha=1.0, beta=0.4, obs_space=(D,),
+                   window_size=200_000, window_step=None, seed=None, clip_rewards=True).items():
+    setattr(cfg, k, v)
+  net = FCNetwork(D, A, dev, cfg, precision=args.precision)
+  net.load_weights({k: v.to(dev) for k, v in random_state_dict(D, A, seed=5).items()})
+  out = {"workload": "self-play move: %d games, A=%d, %d sims, obs %d u8, episodes of 600 steps, replay window 200000 "
+                     "(chunks of 500 + 15 overlap), clip_rewards" % (G, A, S, D)}
+  np.random.seed(0)
+  for name in ("device", "list_path"):
+    env = SyntheticRam(G, A, D, episode_length=600, seed=1)
+    rb = PrioritizedReplay(cfg, device=dev, window_positions=int(200_000 * 1.3) + 3 * G * 515)
+    fs = FCSearch(cfg, net, G)
+    if name == "device":
+      actor = DeviceActor(cfg, env, rb, fs)
+    else:
+      actor = BatchedActor(cfg, net, env, replay_buffer=rb, device=dev, search=fs)
+    # stagger the games so that chunk commits are spread over the moves like in steady state
+    env.elapsed[:] = np.arange(G) % 600
+    moves = 30 if name == "device" else 6
+    for _ in range(3):
+      actor.play_move()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(moves):
+      actor.play_move()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / moves
+    out[name] = {"ms_per_move": dt * 1e3, "moves_per_s": 1.0 / dt, "expansions_per_s": G * S / dt,
+                 "experiences_per_s": G / dt, "games_finished": actor.games_played, "replay_size": rb.size()}
+    del actor, rb, fs
+  out["speedup_vs_list_path"] = out["list_path"]["ms_per_move"] / out["device"]["ms_per_move"]
+  if cpu_expansions_per_s:
+    out["cpu_baseline"] = {"value": cpu_expansions_per_s / S, "unit": "game-moves/s", "kind": "port",
+                           "sample": "the cpu_baseline leg of this run (the reference's actor spends its time in the "
+                                     "search: moves/s = expansions/s / num_simulations)"}
+    out["device"]["game_moves_per_s"] = G / (out["device"]["ms_per_move"] * 1e-3)
   return out
 
 

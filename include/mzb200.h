@@ -379,6 +379,20 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
                      const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* pad_actions,
                      float* obs_out, int32_t* actions_out, float* t_rewards, float* t_values,
                      float* t_policies, float* value_support, float* reward_support, void* stream);
+/*
+ * Self-play -> replay hand-off on the device (Game.apply + Game.store_search_statistics, game.py:79-115; the
+ * HistorySlice an actor sends, actors.py:160-169): one trajectory step of num_games games written straight into
+ * the window arrays.  Game g's record goes to position dst_pos[g] (< 0: skip the game):
+ *   obs [G][obs_elems] u8 / f32 (the search input of the move), actions [G] i32, rewards [G] f32, to_play [G] i8,
+ *   root_values [G] f64, child_visits [G][A] f64 (stored as float32, like replay_buffer.py:192).
+ * mz_window_copy copies `count` runs of positions (src[r] .. src[r] + n[r] - 1 -> dst[r] ..): the
+ * num_unroll_steps + td_steps positions a running game's next chunk repeats (actors.py:160-166).
+ */
+int mz_window_append(const mz_window* w, int32_t num_games, const int64_t* dst_pos, const void* obs,
+                     const int32_t* actions, const float* rewards, const int8_t* to_play, const double* root_values,
+                     const double* child_visits, void* stream);
+int mz_window_copy(const mz_window* w, int32_t count, const int64_t* src, const int64_t* dst, const int32_t* n,
+                   void* stream);
 /* Two kernels serve mz_build_targets: lane-per-unroll-position (K + 1 <= 16 and td_steps <= 64: a warp owns
  * 32 / (K + 1) consecutive rows) and warp-per-row (everything else, e.g. td_steps = 1000).  which = 1 forces
  * the warp-per-row kernel (parity tests run both on the same inputs), 0 restores the choice by shape. */

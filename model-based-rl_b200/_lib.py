@@ -130,6 +130,8 @@ _SIGNATURES = {
     "mz_support_to_scalar": (C.c_int, [C.c_int64, _V, C.c_int32, C.c_int32, C.c_int32, _V, _V]),
     "mz_build_targets": (C.c_int, [C.POINTER(Window), C.POINTER(TargetCfg), _V, _V, _V, _V, _V, _V,
                                    _V, _V, _V, _V, _V, _V]),
+    "mz_window_append": (C.c_int, [C.POINTER(Window), C.c_int32, _V, _V, _V, _V, _V, _V, _V, _V]),
+    "mz_window_copy": (C.c_int, [C.POINTER(Window), C.c_int32, _V, _V, _V, _V]),
     "mz_sumtree_update": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, _V, _V]),
     "mz_sumtree_add": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_int64, C.c_int32, _V, _V, _V,
                                  _V, _V]),

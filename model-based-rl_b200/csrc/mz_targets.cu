@@ -525,6 +525,63 @@ __global__ void support_to_scalar_kernel(long long n, const float* __restrict__ 
   }
 }
 
+// ---- self-play -> replay hand-off on the device ------------------------------------------------------
+// One trajectory step of every game written straight into the replay window (Game.apply +
+// store_search_statistics, game.py:79-115): a warp per game, coalesced row copies.
+__global__ void window_append_kernel(mz_window w, int G, const int64_t* __restrict__ dst_pos, const void* __restrict__ obs,
+                                     const int32_t* __restrict__ actions, const float* __restrict__ rewards,
+                                     const int8_t* __restrict__ to_play, const double* __restrict__ root_values,
+                                     const double* __restrict__ child_visits) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= G) return;
+  const int64_t pos = dst_pos[g];
+  if (pos < 0) return;
+  const int E = w.obs_elems, A = w.num_actions;
+  if (w.obs_is_u8) {
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(obs) + (size_t)g * E;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(const_cast<void*>(w.obs)) + (size_t)pos * E;
+    if ((E & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0) {
+      for (int e = lane; e < (E >> 2); e += 32) reinterpret_cast<uint32_t*>(dst)[e] = reinterpret_cast<const uint32_t*>(src)[e];
+    } else {
+      for (int e = lane; e < E; e += 32) dst[e] = src[e];
+    }
+  } else {
+    const float* src = reinterpret_cast<const float*>(obs) + (size_t)g * E;
+    float* dst = reinterpret_cast<float*>(const_cast<void*>(w.obs)) + (size_t)pos * E;
+    for (int e = lane; e < E; e += 32) dst[e] = src[e];
+  }
+  float* cv = const_cast<float*>(w.child_visits) + (size_t)pos * A;
+  for (int a = lane; a < A; a += 32) cv[a] = (float)child_visits[(size_t)g * A + a];  // float32(history.child_visits)
+  if (lane == 0) {
+    const_cast<int32_t*>(w.actions)[pos] = actions[g];
+    const_cast<float*>(w.rewards)[pos] = rewards[g];
+    const_cast<int8_t*>(w.to_play)[pos] = to_play[g];
+    const_cast<double*>(w.root_values)[pos] = root_values[g];
+  }
+}
+
+// (src, dst, n) runs of window positions: the overlap a running game's next chunk starts with (actors.py:160-166)
+__global__ void window_copy_kernel(mz_window w, int count, const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                   const int32_t* __restrict__ n) {
+  const int r = blockIdx.x;
+  if (r >= count) return;
+  const int E = w.obs_elems, A = w.num_actions;
+  const int64_t s0 = src[r], d0 = dst[r];
+  const int len = n[r];
+  const size_t obs_bytes = (size_t)E * (w.obs_is_u8 ? 1 : 4);
+  const uint8_t* os = reinterpret_cast<const uint8_t*>(w.obs) + (size_t)s0 * obs_bytes;
+  uint8_t* od = reinterpret_cast<uint8_t*>(const_cast<void*>(w.obs)) + (size_t)d0 * obs_bytes;
+  for (size_t i = threadIdx.x; i < (size_t)len * obs_bytes; i += blockDim.x) od[i] = os[i];
+  float* cvd = const_cast<float*>(w.child_visits) + (size_t)d0 * A;
+  for (int i = threadIdx.x; i < len * A; i += blockDim.x) cvd[i] = w.child_visits[(size_t)s0 * A + i];
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const_cast<int32_t*>(w.actions)[d0 + i] = w.actions[s0 + i];
+    const_cast<float*>(w.rewards)[d0 + i] = w.rewards[s0 + i];
+    const_cast<int8_t*>(w.to_play)[d0 + i] = w.to_play[s0 + i];
+    const_cast<double*>(w.root_values)[d0 + i] = w.root_values[s0 + i];
+  }
+}
+
 int grid_for(long long n, int threads) {
   long long g = (n + threads - 1) / threads;
   const long long cap = 148LL * 16;
@@ -571,6 +628,27 @@ int mz_support_to_scalar(int64_t n, const float* logits, int32_t mn, int32_t mx,
   if (n == 0) return MZ_OK;
   support_to_scalar_kernel<<<grid_for(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(n, logits, mn, mx,
                                                                                     no_tt, out);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+int mz_window_append(const mz_window* w, int32_t num_games, const int64_t* dst_pos, const void* obs,
+                     const int32_t* actions, const float* rewards, const int8_t* to_play, const double* root_values,
+                     const double* child_visits, void* stream) {
+  if (!w || num_games < 1 || !dst_pos || !obs || !actions || !rewards || !to_play || !root_values || !child_visits)
+    return MZ_ERR_BAD_ARG;
+  if (!w->obs || !w->actions || !w->rewards || !w->to_play || !w->root_values || !w->child_visits) return MZ_ERR_BAD_ARG;
+  window_append_kernel<<<(num_games + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*w, num_games, dst_pos, obs, actions, rewards,
+                                                                            to_play, root_values, child_visits);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+int mz_window_copy(const mz_window* w, int32_t count, const int64_t* src, const int64_t* dst, const int32_t* n,
+                   void* stream) {
+  if (!w || count < 0 || (count > 0 && (!src || !dst || !n))) return MZ_ERR_BAD_ARG;
+  if (count == 0) return MZ_OK;
+  window_copy_kernel<<<count, 128, 0, (cudaStream_t)stream>>>(*w, count, src, dst, n);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }

@@ -97,3 +97,37 @@ class SyntheticFrames(object):
     reward = self.rng.integers(-1, 2, size=self.num_games).astype(np.int32)
     done = self.elapsed >= self.episode_length
     return self._frames(self.num_games), reward, done, np.full(self.num_games, -1)
+
+
+class SyntheticRam(object):
+  """G independent synthetic single-player episodes with byte observations [obs_dim] (the Breakout-ram /
+  Atari-sweep shape of BASELINE.json: 128 bytes, README.md:56): every action is legal, rewards are seeded draws
+  from {-1, 0, 1} (P(nonzero) = 0.1), an episode ends after `episode_length` steps.  Stands in for the ALE
+  wrappers (wrappers.py), which are environment code and not on the GPU hot path."""
+
+  two_players = False
+
+  def __init__(self, num_games, num_actions, obs_dim=128, episode_length=600, seed=0):
+    self.num_games, self.num_actions, self.obs_shape = int(num_games), int(num_actions), (int(obs_dim),)
+    self.episode_length = int(episode_length)
+    self.rng = np.random.default_rng(seed)
+    self.elapsed = np.zeros(self.num_games, dtype=np.int32)
+    self._all = np.full(self.num_games, (1 << self.num_actions) - 1 if self.num_actions < 32 else 0xffffffff,
+                        dtype=np.uint32)
+
+  def _frames(self, n):
+    return self.rng.integers(0, 256, size=(n,) + self.obs_shape, dtype=np.uint8)
+
+  def reset(self, which=None):
+    idx = np.arange(self.num_games) if which is None else np.asarray(which)
+    self.elapsed[idx] = 0
+    return self._frames(len(idx))
+
+  def legal_mask(self):
+    return self._all
+
+  def step(self, actions):
+    self.elapsed += 1
+    reward = (self.rng.integers(-1, 2, size=self.num_games) * (self.rng.random(self.num_games) < 0.1)).astype(np.int32)
+    done = self.elapsed >= self.episode_length
+    return self._frames(self.num_games), reward, done, np.full(self.num_games, -1)

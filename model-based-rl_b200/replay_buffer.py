@@ -16,6 +16,7 @@ to the reference's one-leaf-at-a-time loop.
 `sample_batch_device()` returns CUDA tensors (optionally with h(x) + two-hot supports fused,
 learners.py:186-192) for a learner that consumes them in place.
 """
+import bisect
 import random
 from collections import deque
 
@@ -201,7 +202,9 @@ class PrioritizedReplay(object):
     self.w_child_visits = torch.zeros((self.P, self.action_space), dtype=torch.float32, device=dev)
     self.d_discounts = torch.from_numpy(self.discounts).to(dev)
     self._head = 0
-    self._chunks = deque()      # (chunk id, start, length) in arena order
+    self.max_chunk = 1          # longest reservation so far (bounds the backwards scan of _overlapping)
+    self._chunk_at = {}         # chunk id -> [start, length]
+    self._starts = []           # sorted (start, chunk id): which chunks a new allocation would overwrite
     self._live = {}             # chunk id -> referencing slots
     self._next_chunk = 0
 
@@ -226,10 +229,76 @@ class PrioritizedReplay(object):
       start = self._upload(history, n)
       cid = self._next_chunk
       self._next_chunk += 1
-      self._chunks.append((cid, start, n))
+      self._register(cid, start, n)
       # liveness = sum-tree slots that refer to the chunk: every memory of this history takes one, every
       # overwritten slot gives one back (to an older chunk, or to this one when the add laps the ring)
       self._live[cid] = len(priorities)
+      for old in self.index.add(priorities, cid, start, n):
+        if old in self._live:
+          self._live[old] -= 1
+    self.throughput['frames'] += len(priorities)
+    if terminal:
+      self.throughput['games'] += 1
+
+  # -- device-resident ingest: the self-play driver writes trajectories straight into the window ------
+  def _window_struct(self):
+    return _lib.Window(self.action_space, self.obs_elems, int(self._obs_dtype == torch.uint8), int(self.clip_rewards),
+                       self.w_obs.data_ptr(), self.w_actions.data_ptr(), self.w_rewards.data_ptr(),
+                       self.w_to_play.data_ptr(), self.w_root_values.data_ptr(), self.w_child_visits.data_ptr())
+
+  @_lib.on_device
+  def open_chunk(self, capacity, obs_dtype=torch.float32):
+    """Reserves `capacity` consecutive window positions for a history the self-play driver is still writing
+    (`append_steps`); they stay reserved until `commit_chunk`.  Returns (chunk id, first position)."""
+    if self.w_obs is None:
+      self._obs_dtype = obs_dtype
+      self.w_obs = torch.zeros((self.P, self.obs_elems), dtype=obs_dtype, device=self.device)
+    elif obs_dtype != self._obs_dtype:
+      raise TypeError("observations changed dtype between histories")
+    start = self._alloc(int(capacity))
+    cid = self._next_chunk
+    self._next_chunk += 1
+    self._register(cid, start, int(capacity))
+    self._live[cid] = 1 << 30  # open: never recycled
+    return cid, start
+
+  @_lib.on_device
+  def append_steps(self, dst_pos, obs, actions, rewards, to_play, root_values, child_visits):
+    """One step of G games (device tensors, see mz_window_append): game g's record -> window position dst_pos[g]."""
+    G = int(dst_pos.shape[0])
+    if getattr(self, '_win_append', None) is None or self._win_append[0] != self.w_obs.data_ptr():
+      self._win_append = (self.w_obs.data_ptr(), self._window_struct())
+    _lib.check(self.lib.mz_window_append(self._win_append[1], G, _lib.ptr(dst_pos), _lib.ptr(obs), _lib.ptr(actions),
+                                         _lib.ptr(rewards), _lib.ptr(to_play), _lib.ptr(root_values),
+                                         _lib.ptr(child_visits), _lib.current_stream()), "mz_window_append")
+
+  @_lib.on_device
+  def copy_positions(self, src, dst, n):
+    """Runs of window positions src[r].. -> dst[r].. (n[r] each): the overlap a running game's next chunk repeats."""
+    if len(src) == 0:
+      return
+    dev = self.device
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
+    d_src, d_dst, d_n = t(src, np.int64), t(dst, np.int64), t(n, np.int32)
+    if getattr(self, '_win_append', None) is None or self._win_append[0] != self.w_obs.data_ptr():
+      self._win_append = (self.w_obs.data_ptr(), self._window_struct())
+    _lib.check(self.lib.mz_window_copy(self._win_append[1], len(src), _lib.ptr(d_src), _lib.ptr(d_dst), _lib.ptr(d_n),
+                                       _lib.current_stream()), "mz_window_copy")
+
+  @_lib.on_device
+  def commit_chunk(self, cid, start, n, errors, ignore=None, terminal=False):
+    """save_history (replay_buffer.py:113-122) for a history that already sits in the window at [start, start + n):
+    priorities from its `errors` (the last `ignore` steps of a running game get none), sum-tree slots, throughput."""
+    errors = np.asarray(errors, np.float64)[:n]
+    if ignore is not None:
+      errors = errors[:-ignore] if ignore else errors
+      priorities = self.get_priorities(errors) if len(errors) else []
+    else:
+      priorities = self.get_priorities(errors)
+    # shrink the reservation to the history's real length
+    self._chunk_at[cid][1] = n
+    self._live[cid] = len(priorities)
+    if n:
       for old in self.index.add(priorities, cid, start, n):
         if old in self._live:
           self._live[old] -= 1
@@ -348,21 +417,45 @@ class PrioritizedReplay(object):
     SumTree.buffer); chunks without slots are recycled when the ring comes round."""
     if n > self.P:
       raise _lib.MzError("history of %d steps does not fit the replay window arena (%d)" % (n, self.P))
-    if self._head + n > self.P:
-      self._head = 0
-    lo, hi = self._head, self._head + n
-    keep = deque()
-    for cid, s, ln in self._chunks:
-      if s < hi and s + ln > lo:
-        if self._live.get(cid, 0) > 0:
+    wraps = 0
+    while True:
+      if self._head + n > self.P:
+        self._head = 0
+        wraps += 1
+        if wraps > 2:
           raise _lib.MzError("replay window arena is full of live histories; construct "
                              "PrioritizedReplay with a larger window_positions")
-        self._live.pop(cid, None)
-      else:
-        keep.append((cid, s, ln))
-    self._chunks = keep
+      lo, hi = self._head, self._head + n
+      hit = self._overlapping(lo, hi)
+      blocker = [self._chunk_at[c][0] + self._chunk_at[c][1] for c in hit if self._live.get(c, 0) > 0]
+      if not blocker:
+        break
+      self._head = max(blocker)  # a history that is still sampled (or still being written): allocate behind it
+    for cid in hit:
+      self._live.pop(cid, None)
+      start = self._chunk_at.pop(cid)[0]
+      del self._starts[bisect.bisect_left(self._starts, (start, cid))]
     self._head = hi
     return lo
+
+  def _register(self, cid, start, n):
+    self.max_chunk = max(self.max_chunk, n)
+    self._chunk_at[cid] = [start, n]
+    bisect.insort(self._starts, (start, cid))
+
+  def _overlapping(self, lo, hi):
+    """Chunk ids whose reservation [start, start + length) meets [lo, hi) (chunks never overlap one another)."""
+    out = []
+    i = bisect.bisect_left(self._starts, (hi, -1)) - 1
+    while i >= 0:
+      start, cid = self._starts[i]
+      ln = self._chunk_at[cid][1]
+      if start + self.max_chunk <= lo:  # no earlier reservation is long enough to reach `lo`
+        break
+      if start < hi and start + ln > lo:
+        out.append(cid)
+      i -= 1
+    return out
 
   def _upload(self, history, n):
     obs = np.stack([np.asarray(o) for o in history.observations[:n]]).reshape(n, -1)

@@ -154,3 +154,127 @@ class BatchedActor(object):
       for i, o in zip(finished, env.reset(finished)):
         self.games[i] = _Game(o)
     return actions, root_value, child_visits, errors, done
+
+
+class DeviceActor(object):
+  """`BatchedActor` with the trajectories resident on the GPU: the body of Actor.play_game (actors.py:125-176) for
+  G games in lock step, where a move's record (observation, action, reward, to_play, root value, child-visit
+  distribution) goes from the search engine's output buffers straight into the replay window
+  (`PrioritizedReplay.append_steps`, one launch per move) instead of per-game Python lists that are re-uploaded as
+  HistorySlices.  The host keeps what the reference keeps per game -- counters and the priority seeds
+  `error = root.value() - initial value` (actors.py:147) -- as arrays over the games; per-game Python runs only for
+  the few games that finish a chunk in a move (max_history_length steps or a terminal, actors.py:160-169).
+
+  Chunking, the num_unroll_steps + td_steps overlap of a running game's chunks, `ignore` and the priorities are the
+  reference's; tests/test_selfplay.py checks the resulting replay buffer against the list path's, bit for bit.
+  Observations are stored as the environment returns them: uint8 (normalised on the device for the search,
+  `FCSearch.set_obs_normalization`) or float32 without `norm_obs`."""
+
+  def __init__(self, config, env, replay_buffer, search, temperature=1.0):
+    self.config, self.env, self.replay, self.search = config, env, replay_buffer, search
+    if search.G != env.num_games:
+      raise ValueError("the search engine was built for %d games, the environment has %d" % (search.G, env.num_games))
+    if getattr(config, "norm_obs", False):
+      raise ValueError("DeviceActor stores raw observations: use uint8 observations with FCSearch.set_obs_normalization")
+    G = self.G = env.num_games
+    self.A = int(config.action_space)
+    self.L = int(config.max_history_length)
+    self.overlap = int(config.num_unroll_steps + config.td_steps)
+    self.cap = self.L + self.overlap
+    self.temperature = np.broadcast_to(np.asarray(temperature, np.float64), (G,)).copy()
+    self.obs = np.ascontiguousarray(env.reset())
+    self.obs_u8 = self.obs.dtype == np.uint8
+    dev = replay_buffer.device
+    self.history_idx = np.zeros(G, np.int64)      # Game.history_idx
+    self.prev_collect = np.zeros(G, np.int64)     # Game.previous_collect_to
+    self.first = np.zeros(G, np.int64)            # history index of the open chunk's first position
+    self.to_play = np.ones(G, np.int8)
+    self.sum_rewards = np.zeros(G, np.float64)
+    self.errors = np.zeros((G, self.cap), np.float64)
+    self.chunk_id = np.zeros(G, np.int64)
+    self.chunk_start = np.zeros(G, np.int64)
+    odt = torch.uint8 if self.obs_u8 else torch.float32
+    for g in range(G):
+      self.chunk_id[g], self.chunk_start[g] = replay_buffer.open_chunk(self.cap, odt)
+    self._odt = odt
+    self.h_pos = torch.zeros(G, dtype=torch.int64).pin_memory()
+    self.h_rew = torch.zeros(G, dtype=torch.float32).pin_memory()
+    self.d_pos = torch.zeros(G, dtype=torch.int64, device=dev)
+    self.d_rew = torch.zeros(G, dtype=torch.float32, device=dev)
+    self.experiences_collected = 0
+    self.games_played = 0
+    self.results = collections.Counter()
+
+  def play_move(self, noise=None, uniforms=None):
+    cfg, env, G, A, fs = self.config, self.env, self.G, self.A, self.search
+    legal = env.legal_mask()
+    if noise is None:  # Node.add_exploration_noise (mcts.py:57-61): one draw per root over its children
+      if (legal == legal[0]).all():
+        n = bin(int(legal[0])).count("1")
+        noise = np.zeros((G, A))
+        noise[:, :n] = np.random.dirichlet([cfg.root_dirichlet_alpha] * n, size=G)
+      else:
+        noise = np.zeros((G, A))
+        for i in range(G):
+          n = bin(int(legal[i])).count("1")
+          noise[i, :n] = np.random.dirichlet([cfg.root_dirichlet_alpha] * n)
+    if uniforms is None:
+      uniforms = np.random.random(G)
+    obs_in = self.obs if self.obs_u8 else np.ascontiguousarray(self.obs, dtype=np.float32)
+    actions, root_value, child_visits, init_value = fs.search_host(obs_in, noise, uniforms, self.temperature, legal=legal,
+                                                                   to_play=self.to_play)
+    actions = actions.numpy().copy()
+    errors = root_value.numpy() - init_value.numpy().astype(np.float64)  # actors.py:147
+    next_obs, reward, done, result = env.step(actions)
+    # Game.apply + store_search_statistics for every game: one launch, straight from the engine's device buffers
+    idx = self.history_idx - self.first
+    self.h_pos.copy_(torch.from_numpy(self.chunk_start + idx))
+    self.h_rew.copy_(torch.from_numpy(np.asarray(reward, np.float64).astype(np.float32)))
+    self.d_pos.copy_(self.h_pos, non_blocking=True)
+    self.d_rew.copy_(self.h_rew, non_blocking=True)
+    self.replay.append_steps(self.d_pos, fs.obs_u8 if self.obs_u8 else fs.obs, fs.actions, self.d_rew, fs.to_play,
+                             fs.root_value, fs.child_visits)
+    self.errors[np.arange(G), idx] = errors
+    self.sum_rewards += reward
+    self.history_idx += 1
+    if cfg.two_players:
+      self.to_play = (-self.to_play).astype(np.int8)
+    self.experiences_collected += G
+    self.obs = np.ascontiguousarray(next_obs)
+    # actors.py:160-169: a chunk is complete after max_history_length new steps or at a terminal
+    full = ((self.history_idx - self.prev_collect) == self.L) | done
+    over = done | (env.elapsed >= cfg.max_steps)
+    src, dst, cnt = [], [], []
+    for g in np.nonzero(full | over)[0]:
+      g = int(g)
+      if full[g]:
+        n = int(self.history_idx[g] - self.first[g])
+        self.replay.commit_chunk(int(self.chunk_id[g]), int(self.chunk_start[g]), n, self.errors[g],
+                                 ignore=None if done[g] else self.overlap, terminal=bool(done[g]))
+        self.prev_collect[g] = self.history_idx[g]
+      elif over[g]:
+        # cut by max_steps without a terminal: the reference drops the unsent tail with the Game object
+        self.replay.commit_chunk(int(self.chunk_id[g]), int(self.chunk_start[g]), 0, self.errors[g][:0], terminal=False)
+      old_start, old_first = int(self.chunk_start[g]), int(self.first[g])
+      self.chunk_id[g], self.chunk_start[g] = self.replay.open_chunk(self.cap, self._odt)
+      if over[g]:  # run_selfplay: a new game replaces the finished one (actors.py:94-97)
+        if result[g] >= 0:
+          self.results[int(result[g])] += 1
+        self.games_played += 1
+        self.history_idx[g] = self.prev_collect[g] = self.first[g] = 0
+        self.to_play[g] = 1
+        self.sum_rewards[g] = 0.0
+      else:  # the next chunk of a running game starts with the last `overlap` steps of this one
+        first = max(0, int(self.history_idx[g]) - self.overlap)
+        keep = int(self.history_idx[g]) - first
+        src.append(old_start + (first - old_first))
+        dst.append(int(self.chunk_start[g]))
+        cnt.append(keep)
+        self.errors[g, :keep] = self.errors[g, first - old_first:first - old_first + keep].copy()
+        self.first[g] = first
+    if src:
+      self.replay.copy_positions(src, dst, cnt)
+    fin = np.nonzero(over)[0]
+    if len(fin):
+      self.obs[fin] = env.reset(fin)
+    return actions, root_value, child_visits, errors, done

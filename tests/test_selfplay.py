@@ -206,3 +206,78 @@ def test_synthetic_frames_environment_contract():
   assert a.reset([1]).shape == (1, 2, 8, 8) and a.elapsed.tolist() == [2, 0, 2]
   with pytest.raises(ValueError):
     a.step(np.array([0, 6, 0]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_name", ["tictactoe", "ram"])
+def test_device_actor_fills_the_replay_like_the_list_path(env_name):
+  """DeviceActor (trajectories written on the device, straight from the search engine's output buffers into the
+  replay window) against BatchedActor + save_history (per-game Python lists -> HistorySlice -> upload): same
+  moves, and afterwards the same replay buffer -- sum-tree contents, num_memories, and for every slot the same
+  (step, chunk length) and the same chunk contents (observations, actions, rewards, to_play, root values,
+  child visits), bit for bit.  Short max_history_length so that chunks of running games overlap
+  (actors.py:160-169), byte observations with device-side normalisation in the `ram` case."""
+  from model_based_rl_b200.environments import SyntheticRam, VectorTicTacToe
+  from model_based_rl_b200.networks import FCNetwork, FCSearch, random_state_dict
+  from model_based_rl_b200.replay_buffer import PrioritizedReplay
+  from model_based_rl_b200.selfplay import BatchedActor, DeviceActor
+  import torch
+  if env_name == "tictactoe":
+    A, G, S, D, two, L, moves = 9, 64, 12, 9, True, 4, 30
+    make_env = lambda: VectorTicTacToe(G)
+  else:
+    A, G, S, D, two, L, moves = 6, 96, 10, 128, False, 5, 40
+    make_env = lambda: SyntheticRam(G, A, D, episode_length=17, seed=5)
+  cfg = types.SimpleNamespace(
+      num_simulations=S, action_space=A, two_players=two, discount=1.0 if two else 0.997, pb_c_base=19652, pb_c_init=1.25,
+      init_value_score=0.0, known_bounds=[-1, 1] if two else [None, None], root_dirichlet_alpha=0.25,
+      root_exploration_fraction=0.25, num_unroll_steps=3, td_steps=4, max_history_length=L, max_steps=10 ** 9,
+      value_support=[-15, 15], reward_support=[-15, 15], no_support=False, no_target_transform=False,
+      batch_size=32, beta_increment_per_sampling=0.001, epsilon=0.01, alpha=0.8, beta=0.5, obs_space=(D,),
+      window_size=600, window_step=None, seed=None, clip_rewards=False)
+  net = FCNetwork(D, A, "cuda", cfg)
+  net.load_weights(random_state_dict(D, A, seed=3))
+  temps = np.array([[1.0, 0.5, 0.0, 0.25][i % 4] for i in range(G)])
+  rb_a = PrioritizedReplay(cfg, window_positions=40000)
+  rb_b = PrioritizedReplay(cfg, window_positions=40000)
+  fs_a, fs_b = FCSearch(cfg, net, G), FCSearch(cfg, net, G)
+  # the list path feeds float32(bytes) to the network; the same values on the device: (x - 0) / 1
+  fs_b.set_obs_normalization(np.zeros(D, np.float32), np.ones(D, np.float32))
+  list_actor = BatchedActor(cfg, net, make_env(), replay_buffer=rb_a, device="cuda", temperature=temps, search=fs_a)
+  dev_actor = DeviceActor(cfg, make_env(), rb_b, fs_b, temperature=temps)
+  rng = np.random.default_rng(17)
+  for move in range(moves):
+    legal = list_actor.env.legal_mask()
+    assert np.array_equal(legal, dev_actor.env.legal_mask())
+    noise = np.zeros((G, A))
+    for i in range(G):
+      n = bin(int(legal[i])).count("1")
+      noise[i, :n] = rng.dirichlet([0.25] * n)
+    u = rng.random(G)
+    a = list_actor.play_move(noise.copy(), u.copy())
+    b = dev_actor.play_move(noise.copy(), u.copy())
+    for x, y, name in zip(a, b, ("actions", "root_value", "child_visits", "errors", "done")):
+      assert np.array_equal(np.asarray(x), np.asarray(y)), (move, name)
+  torch.cuda.synchronize()
+  assert dev_actor.games_played == list_actor.games_played > 0
+  assert rb_a.size() == rb_b.size() > 0
+  assert rb_a.get_throughput() == rb_b.get_throughput()
+  assert np.array_equal(rb_a.index.tree.cpu().numpy(), rb_b.index.tree.cpu().numpy())
+  ia, ib = rb_a.index, rb_b.index
+  pa, sa, la = ia.slot_pos.cpu().numpy(), ia.slot_start.cpu().numpy(), ia.slot_len.cpu().numpy()
+  pb, sb, lb = ib.slot_pos.cpu().numpy(), ib.slot_start.cpu().numpy(), ib.slot_len.cpu().numpy()
+  live = ia.slot_chunk >= 0
+  assert np.array_equal(live, ib.slot_chunk >= 0) and live.sum() == min(600, rb_a.size())
+  assert np.array_equal((pa - sa)[live], (pb - sb)[live]) and np.array_equal(la[live], lb[live])
+  wa = {k: getattr(rb_a, k).cpu().numpy() for k in ("w_obs", "w_actions", "w_rewards", "w_to_play", "w_root_values", "w_child_visits")}
+  wb = {k: getattr(rb_b, k).cpu().numpy() for k in wa}
+  checked = set()
+  for slot in np.nonzero(live)[0]:
+    key = (int(sa[slot]), int(sb[slot]))
+    if key in checked:
+      continue
+    checked.add(key)
+    n = int(la[slot])
+    for k in wa:
+      assert np.array_equal(wa[k][sa[slot]:sa[slot] + n], wb[k][sb[slot]:sb[slot] + n]), (k, slot)
+  assert len(checked) > 10
