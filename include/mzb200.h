@@ -103,6 +103,16 @@ int mz_tree_set_root(const mz_tree* t, const float* root_logits, const uint32_t*
                      const uint32_t* root_hidden, void* stream);
 
 /*
+ * Node.add_exploration_noise's draw (mcts.py:59: np.random.dirichlet([root_dirichlet_alpha] * len(actions))) for
+ * every game of a move, made on the device into the `noise` layout of mz_tree_set_root / mz_fc_search: row g holds
+ * one value per legal action of game g (legal_mask[g] bit a = action a is legal; NULL = all), dense from column 0,
+ * zeros behind.  Same distribution, another stream than numpy's: Philox4x32-10 keyed by (seed, game, action) and
+ * advanced by `move`; the host-supplied buffer stays the bit-exact path.
+ */
+int mz_dirichlet_noise(int32_t num_games, int32_t num_actions, double alpha, const int32_t* legal_mask,
+                       uint64_t seed, uint64_t move, double* noise, void* stream);
+
+/*
  * Same, for a root the caller has already expanded on the host (the B=1 drop-in path:
  * root.expand + root.add_exploration_noise were run by the caller, actors.py:142-143):
  *   root_priors [G][A] f64 = root.children[a].prior (ignored where the action is illegal).
@@ -422,6 +432,15 @@ int mz_sumtree_add(double* tree, int64_t max_capacity, int64_t n, const int64_t*
 int mz_sumtree_add_from(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
                         const double* priority, int64_t chunk_start, int32_t chunk_len, int32_t first_step,
                         int64_t* slot_pos, int64_t* slot_start, int32_t* slot_len, double* scratch, void* stream);
+/* SumTree.add for the memories of several chunks in one call (the histories every game of a self-play move
+ * finished, actors.py:160-169 -> replay_buffer.py:113-122): memory i belongs to segment s with
+ * seg_begin[s] <= i < seg_begin[s + 1] and is step i - seg_begin[s] of the chunk at window position seg_start[s]
+ * (length seg_len[s]).  seg_begin [num_segments + 1] i32, seg_start [num_segments] i64, seg_len [num_segments] i32.
+ * The tree indices of one call must be distinct, like mz_sumtree_add_from's. */
+int mz_sumtree_add_chunks(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
+                          const double* priority, int32_t num_segments, const int32_t* seg_begin,
+                          const int64_t* seg_start, const int32_t* seg_len, int64_t* slot_pos, int64_t* slot_start,
+                          int32_t* slot_len, double* scratch, void* stream);
 /* The sampling half of sample_batch (replay_buffer.py:134-145, 160-162) for n rows:
  *   value_b = random.uniform(seg*b, seg*(b+1)) with seg = total/n, computed on the device from the
  *   host-drawn u01[b] = random.random() (same binary64 operations as CPython's uniform());

@@ -135,6 +135,8 @@ _SIGNATURES = {
     "mz_sumtree_update": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, _V, _V]),
     "mz_sumtree_add": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_int64, C.c_int32, _V, _V, _V,
                                  _V, _V]),
+    "mz_dirichlet_noise": (C.c_int, [C.c_int32, C.c_int32, C.c_double, _V, C.c_uint64, C.c_uint64, _V, _V]),
+    "mz_sumtree_add_chunks": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_int32, _V, _V, _V, _V, _V, _V, _V, _V]),
     "mz_sumtree_add_from": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_int64, C.c_int32, C.c_int32, _V, _V, _V,
                                       _V, _V]),
     "mz_sumtree_sample": (C.c_int, [_V, C.c_int64, C.c_int32, _V, _V, _V, _V, C.c_int64, C.c_double,

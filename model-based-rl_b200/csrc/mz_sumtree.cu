@@ -84,6 +84,24 @@ __global__ void sumtree_slots_kernel(int n, const int64_t* __restrict__ idx, int
   slot_len[slot] = chunk_len;
 }
 
+// the same for the memories of several chunks: memory i is step i - seg_begin[s] of segment s
+__global__ void sumtree_slots_seg_kernel(int n, const int64_t* __restrict__ idx, int64_t leaf0, int nseg,
+                                         const int32_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_start,
+                                         const int32_t* __restrict__ seg_len, int64_t* __restrict__ slot_pos,
+                                         int64_t* __restrict__ slot_start, int32_t* __restrict__ slot_len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = nseg - 1;  // last segment with seg_begin <= i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (seg_begin[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  const int64_t slot = idx[i] - leaf0;
+  slot_pos[slot] = seg_start[lo] + (i - seg_begin[lo]);
+  slot_start[slot] = seg_start[lo];
+  slot_len[slot] = seg_len[lo];
+}
+
 // SumTree.get_leaf (replay_buffer.py:43-62) for the stratified values of sample_batch
 // (replay_buffer.py:137-141) + the importance weights (replay_buffer.py:160-162).  One CTA.
 __global__ void sumtree_sample_kernel(const double* __restrict__ tree, int64_t size, int64_t leaf0,
@@ -174,6 +192,20 @@ int mz_sumtree_add_from(double* tree, int64_t max_capacity, int64_t n, const int
   if (rc != MZ_OK || n == 0) return rc;
   sumtree_slots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (int)n, tree_idx, max_capacity - 1, chunk_start, chunk_len, slot_pos, slot_start, slot_len, first_step);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+int mz_sumtree_add_chunks(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
+                          const double* priority, int32_t num_segments, const int32_t* seg_begin,
+                          const int64_t* seg_start, const int32_t* seg_len, int64_t* slot_pos, int64_t* slot_start,
+                          int32_t* slot_len, double* scratch, void* stream) {
+  if (n > 0 && (!slot_pos || !slot_start || !slot_len || num_segments < 1 || !seg_begin || !seg_start || !seg_len))
+    return MZ_ERR_BAD_ARG;
+  const int rc = mz_sumtree_update(tree, max_capacity, n, tree_idx, priority, scratch, stream);
+  if (rc != MZ_OK || n == 0) return rc;
+  sumtree_slots_seg_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (int)n, tree_idx, max_capacity - 1, num_segments, seg_begin, seg_start, seg_len, slot_pos, slot_start, slot_len);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }

@@ -548,8 +548,21 @@ class FCSearch(object):
     torch.cuda.current_stream().synchronize()
     return h['actions'], h['root_value'], h['child_visits'], h['init_value']
 
+  def draw_noise(self, alpha):
+    """Node.add_exploration_noise's Dirichlet draw (mcts.py:59) for every root, made on the device from the legal
+    masks already staged there (`mz_dirichlet_noise`): same distribution as np.random.dirichlet, another stream.
+    The seed comes from np.random at first use, so `np.random.seed` still fixes a run."""
+    if getattr(self, '_noise_seed', None) is None:
+      self._noise_seed, self._noise_move = int(np.random.randint(1 << 62)), 0
+    _lib.check(self.net.lib.mz_dirichlet_noise(self.G, self.A, float(alpha), _lib.ptr(self.legal), self._noise_seed,
+                                               self._noise_move, _lib.ptr(self.noise), _lib.current_stream()),
+               "mz_dirichlet_noise")
+    self._noise_move += 1
+    self.use_noise = True
+
   @_lib.on_device
-  def search_host(self, obs, noise=None, uniforms=None, temperature=None, legal=None, to_play=None):
+  def search_host(self, obs, noise=None, uniforms=None, temperature=None, legal=None, to_play=None,
+                  dirichlet_alpha=None):
     """The per-move body of Actor.play_game (actors.py:131-153) for G games.
 
     Inputs are HOST arrays (numpy or CPU tensors): obs [G, input_dim] float32 -- or uint8, in which
@@ -560,7 +573,8 @@ class FCSearch(object):
     masks [G] (bit a = action a is legal, actors.py:141-142) and to_play [G] (+1 / -1).  Returns
     pinned host tensors: actions [G] i32, root_value [G] f64, child_visits [G, A] f64, and the
     initial-inference value [G] f32 (the priority seed `error = root.value() - value`,
-    actors.py:147).  Host->device and device->host copies are part of the call.
+    actors.py:147).  Host->device and device->host copies are part of the call.  With `dirichlet_alpha` set and no
+    `noise` buffer the root noise is drawn on the device instead (`draw_noise`).
     """
     h = self._pinned()
     def stage(name, src, dst):
@@ -588,6 +602,8 @@ class FCSearch(object):
     if to_play is not None:
       stage('to_play', np.ascontiguousarray(np.asarray(to_play, dtype=np.int8)), self.to_play)
     self.use_noise = noise is not None or self.use_noise
+    if noise is None and dirichlet_alpha is not None:
+      self.draw_noise(dirichlet_alpha)
     self.run()
     self._out_host.copy_(self._out_dev, non_blocking=True)  # the four outputs share one blob
     torch.cuda.current_stream().synchronize()

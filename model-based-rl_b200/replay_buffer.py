@@ -17,6 +17,7 @@ to the reference's one-leaf-at-a-time loop.
 learners.py:186-192) for a learner that consumes them in place.
 """
 import bisect
+import ctypes as C
 import random
 from collections import deque
 
@@ -85,18 +86,18 @@ class ReplayIndex(object):
     return idx, pri, torch.empty_like(pri)
 
   def add(self, priorities, chunk_id, chunk_start, chunk_len):
-    """SumTree.add (replay_buffer.py:19-33); returns the chunk id every overwritten slot used to refer to
-    (with multiplicity, this chunk's own id included when one add laps the ring).
+    """SumTree.add (replay_buffer.py:19-33); returns {chunk id: how many of its slots were overwritten} (this
+    chunk's own id included when one add laps the ring).
 
     A history with more memories than the ring currently holds wraps it, so the same slot appears more
     than once in the add.  The reference writes one memory at a time -- the last write to a slot wins and
     every earlier one is an ordinary overwrite -- so the add is applied in pieces without repeated slots."""
     n = len(priorities)
     if n == 0:
-      return []
+      return {}
     slots = self.ring.take(n)
     pri_all = np.ascontiguousarray(priorities, np.float64)
-    overwritten = []
+    overwritten = {}
     lo = 0
     while lo < n:
       # longest run from `lo` without a repeated slot
@@ -108,7 +109,9 @@ class ReplayIndex(object):
       hi = lo + (int(rep[0]) if rep.size else seg.size)
       piece = slots[lo:hi]
       old = self.slot_chunk[piece]
-      overwritten.extend(int(c) for c in old if c >= 0)
+      ids, counts = np.unique(old[old >= 0], return_counts=True)
+      for c, k in zip(ids.tolist(), counts.tolist()):
+        overwritten[c] = overwritten.get(c, 0) + k
       self.slot_chunk[piece] = chunk_id
       idx, pri, scratch = self._stage(piece + self.max_capacity - 1, pri_all[lo:hi])
       _lib.check(self.lib.mz_sumtree_add_from(_lib.ptr(self.tree), self.max_capacity, hi - lo, _lib.ptr(idx),
@@ -117,6 +120,51 @@ class ReplayIndex(object):
                                               _lib.ptr(self.slot_len), _lib.ptr(scratch),
                                               _lib.current_stream()), "mz_sumtree_add_from")
       lo = hi
+    return overwritten
+
+  def add_chunks(self, items):
+    """SumTree.add for the memories of several chunks, in order, with one upload and one call: items =
+    [(priorities, chunk id, chunk start, chunk length)].  Returns {chunk id: overwritten slots} like `add`."""
+    items = [it for it in items if len(it[0])]
+    total = sum(len(it[0]) for it in items)
+    overwritten = {}
+    if total == 0:
+      return overwritten
+    if len(items) == 1 or total > self.ring.capacity:  # an add that laps the ring goes in pieces (see add)
+      for pri, cid, start, n in items:
+        for c, k in self.add(pri, cid, start, n).items():
+          overwritten[c] = overwritten.get(c, 0) + k
+      return overwritten
+    slots = self.ring.take(total)
+    old = self.slot_chunk[slots]
+    ids, counts = np.unique(old[old >= 0], return_counts=True)
+    overwritten = dict(zip(ids.tolist(), counts.tolist()))
+    ns = len(items)
+    # one blob: tree idx [total] i64 | priority [total] f64 | chunk start [ns] i64 | begin [ns + 1] i32 | length [ns] i32
+    blob = np.empty(16 * total + 8 * ns + 4 * (2 * ns + 2), np.uint8)
+    h_idx = blob[:8 * total].view(np.int64)
+    h_pri = blob[8 * total:16 * total].view(np.float64)
+    h_start = blob[16 * total:16 * total + 8 * ns].view(np.int64)
+    h_begin = blob[16 * total + 8 * ns:16 * total + 8 * ns + 4 * (ns + 1)].view(np.int32)
+    h_len = blob[16 * total + 8 * ns + 4 * (ns + 1):16 * total + 8 * ns + 4 * (2 * ns + 1)].view(np.int32)
+    np.add(slots, self.max_capacity - 1, out=h_idx)
+    off = 0
+    for s, (pri, cid, start, n) in enumerate(items):
+      k = len(pri)
+      h_pri[off:off + k] = pri
+      self.slot_chunk[slots[off:off + k]] = cid
+      h_start[s], h_begin[s], h_len[s] = start, off, n
+      off += k
+    h_begin[ns] = total
+    d = torch.from_numpy(blob).to(self.device)
+    base = d.data_ptr()
+    scratch = torch.empty(total, dtype=torch.float64, device=self.device)
+    P = C.c_void_p
+    _lib.check(self.lib.mz_sumtree_add_chunks(_lib.ptr(self.tree), self.max_capacity, total, P(base), P(base + 8 * total),
+                                              ns, P(base + 16 * total + 8 * ns), P(base + 16 * total),
+                                              P(base + 16 * total + 8 * ns + 4 * (ns + 1)), _lib.ptr(self.slot_pos),
+                                              _lib.ptr(self.slot_start), _lib.ptr(self.slot_len), _lib.ptr(scratch),
+                                              _lib.current_stream()), "mz_sumtree_add_chunks")
     return overwritten
 
   @_lib.on_device
@@ -233,9 +281,9 @@ class PrioritizedReplay(object):
       # liveness = sum-tree slots that refer to the chunk: every memory of this history takes one, every
       # overwritten slot gives one back (to an older chunk, or to this one when the add laps the ring)
       self._live[cid] = len(priorities)
-      for old in self.index.add(priorities, cid, start, n):
+      for old, k in self.index.add(priorities, cid, start, n).items():
         if old in self._live:
-          self._live[old] -= 1
+          self._live[old] -= k
     self.throughput['frames'] += len(priorities)
     if terminal:
       self.throughput['games'] += 1
@@ -299,12 +347,33 @@ class PrioritizedReplay(object):
     self._chunk_at[cid][1] = n
     self._live[cid] = len(priorities)
     if n:
-      for old in self.index.add(priorities, cid, start, n):
+      for old, k in self.index.add(priorities, cid, start, n).items():
         if old in self._live:
-          self._live[old] -= 1
+          self._live[old] -= k
     self.throughput['frames'] += len(priorities)
     if terminal:
       self.throughput['games'] += 1
+
+  @_lib.on_device
+  def commit_chunks(self, chunks):
+    """`commit_chunk` for every history the games of one self-play move finished, in order, with one sum-tree call:
+    chunks = [(chunk id, start, n, errors, ignore, terminal)]."""
+    items = []
+    for cid, start, n, errors, ignore, terminal in chunks:
+      errors = np.asarray(errors, np.float64)[:n]
+      if ignore:
+        errors = errors[:-ignore]
+      priorities = self.get_priorities(errors) if len(errors) else np.zeros(0)
+      self._chunk_at[cid][1] = n
+      self._live[cid] = len(priorities)
+      self.throughput['frames'] += len(priorities)
+      if terminal:
+        self.throughput['games'] += 1
+      if n and len(priorities):
+        items.append((priorities, cid, start, n))
+    for old, k in self.index.add_chunks(items).items():
+      if old in self._live:
+        self._live[old] -= k
 
   @_lib.on_device
   def sample_batch(self):

@@ -208,11 +208,12 @@ class DeviceActor(object):
   def play_move(self, noise=None, uniforms=None):
     cfg, env, G, A, fs = self.config, self.env, self.G, self.A, self.search
     legal = env.legal_mask()
-    if noise is None:  # Node.add_exploration_noise (mcts.py:57-61): one draw per root over its children
-      if (legal == legal[0]).all():
-        n = bin(int(legal[0])).count("1")
-        noise = np.zeros((G, A))
-        noise[:, :n] = np.random.dirichlet([cfg.root_dirichlet_alpha] * n, size=G)
+    # Node.add_exploration_noise (mcts.py:57-61): one Dirichlet draw per root over its children -- on the device
+    # (FCSearch.draw_noise) unless the caller brings the draws (the bit-exact path the tests replay)
+    alpha = None
+    if noise is None:
+      if hasattr(fs, "draw_noise"):
+        alpha = cfg.root_dirichlet_alpha
       else:
         noise = np.zeros((G, A))
         for i in range(G):
@@ -221,8 +222,9 @@ class DeviceActor(object):
     if uniforms is None:
       uniforms = np.random.random(G)
     obs_in = self.obs if self.obs_u8 else np.ascontiguousarray(self.obs, dtype=np.float32)
+    kw = {} if alpha is None else {"dirichlet_alpha": alpha}
     actions, root_value, child_visits, init_value = fs.search_host(obs_in, noise, uniforms, self.temperature, legal=legal,
-                                                                   to_play=self.to_play)
+                                                                   to_play=self.to_play, **kw)
     actions = actions.numpy().copy()
     errors = root_value.numpy() - init_value.numpy().astype(np.float64)  # actors.py:147
     next_obs, reward, done, result = env.step(actions)
@@ -244,18 +246,20 @@ class DeviceActor(object):
     # actors.py:160-169: a chunk is complete after max_history_length new steps or at a terminal
     full = ((self.history_idx - self.prev_collect) == self.L) | done
     over = done | (env.elapsed >= cfg.max_steps)
-    src, dst, cnt = [], [], []
+    src, dst, cnt, commits = [], [], [], []
     for g in np.nonzero(full | over)[0]:
       g = int(g)
       if full[g]:
         n = int(self.history_idx[g] - self.first[g])
-        self.replay.commit_chunk(int(self.chunk_id[g]), int(self.chunk_start[g]), n, self.errors[g],
-                                 ignore=None if done[g] else self.overlap, terminal=bool(done[g]))
+        commits.append((int(self.chunk_id[g]), int(self.chunk_start[g]), n, self.errors[g, :n].copy(),
+                        None if done[g] else self.overlap, bool(done[g])))
         self.prev_collect[g] = self.history_idx[g]
       elif over[g]:
         # cut by max_steps without a terminal: the reference drops the unsent tail with the Game object
-        self.replay.commit_chunk(int(self.chunk_id[g]), int(self.chunk_start[g]), 0, self.errors[g][:0], terminal=False)
+        commits.append((int(self.chunk_id[g]), int(self.chunk_start[g]), 0, self.errors[g, :0], None, False))
       old_start, old_first = int(self.chunk_start[g]), int(self.first[g])
+      # the finished chunk stays reserved (open) until every new chunk of this move has its place, so a chunk without
+      # priorities cannot be recycled under the overlap copy below
       self.chunk_id[g], self.chunk_start[g] = self.replay.open_chunk(self.cap, self._odt)
       if over[g]:  # run_selfplay: a new game replaces the finished one (actors.py:94-97)
         if result[g] >= 0:
@@ -274,6 +278,8 @@ class DeviceActor(object):
         self.first[g] = first
     if src:
       self.replay.copy_positions(src, dst, cnt)
+    if commits:  # save_history for every finished chunk of the move: one sum-tree call
+      self.replay.commit_chunks(commits)
     fin = np.nonzero(over)[0]
     if len(fin):
       self.obs[fin] = env.reset(fin)

@@ -252,3 +252,32 @@ def test_history_longer_than_the_ring_laps_it_like_the_reference():
       slot = ti - (40 - 1)
       hh = hist[int(ref.slot_hist[slot])]
       assert np.array_equal(obs[b], hh.observations[int(ref.slot_step[slot])])
+
+
+@pytest.mark.parametrize("capacity,step", [(700, 200), (5000, 5000)])
+def test_add_chunks_equals_one_add_per_chunk(capacity, step):
+  """ReplayIndex.add_chunks (every chunk a self-play move finished: one upload, one mz_sumtree_add_chunks call)
+  against one ReplayIndex.add per chunk: identical float64 tree, identical slot -> (position, chunk start, chunk
+  length) tables, identical ring cursor and overwritten-slot counts -- also across ring wraps and capacity growth."""
+  from model_based_rl_b200.replay_buffer import ReplayIndex
+  rng = np.random.default_rng(capacity)
+  a, b = ReplayIndex(capacity, step, "cuda"), ReplayIndex(capacity, step, "cuda")
+  cid, start = 0, 0
+  for move in range(40):
+    items = []
+    for _ in range(int(rng.integers(1, 7))):
+      n = int(rng.integers(1, 90))
+      k = int(rng.integers(0, n + 1))  # a running game's chunk has fewer priorities than steps
+      items.append((rng.random(k) + 0.01, cid, start, n))
+      cid, start = cid + 1, start + n
+    want = {}
+    for pri, c, s, n in items:
+      for old, cnt in a.add(pri, c, s, n).items():
+        want[old] = want.get(old, 0) + cnt
+    got = b.add_chunks(items)
+    assert got == want, move
+  torch.cuda.synchronize()
+  assert a.ring.__dict__ == b.ring.__dict__
+  assert np.array_equal(a.slot_chunk, b.slot_chunk)
+  for name in ("tree", "slot_pos", "slot_start", "slot_len"):
+    assert np.array_equal(getattr(a, name).cpu().numpy(), getattr(b, name).cpu().numpy()), name

@@ -281,3 +281,86 @@ def test_device_actor_fills_the_replay_like_the_list_path(env_name):
     for k in wa:
       assert np.array_equal(wa[k][sa[slot]:sa[slot] + n], wb[k][sb[slot]:sb[slot] + n]), (k, slot)
   assert len(checked) > 10
+
+
+@pytest.mark.gpu
+def test_device_dirichlet_noise_has_the_reference_distribution():
+  """mz_dirichlet_noise against np.random.dirichlet([alpha] * n) (mcts.py:59): rows are dense over the legal actions
+  and sum to one, every component follows Beta(alpha, (n - 1) * alpha) (Kolmogorov-Smirnov against scipy's CDF and
+  against numpy's own draws), components of a row are negatively correlated by -1 / (n - 1), draws repeat for equal
+  (seed, move) and differ otherwise."""
+  import ctypes as C
+  import torch
+  from scipy import stats
+  from model_based_rl_b200 import _lib
+  lib = _lib.load()
+  G, A, alpha = 20000, 18, 0.25
+  rng = np.random.default_rng(0)
+  legal = np.full(G, (1 << A) - 1, np.int64)
+  legal[G // 2:] = rng.integers(1, 1 << A, size=G - G // 2)
+  d_legal = torch.from_numpy(legal.astype(np.int32)).cuda()
+  out = torch.full((G, A), -1.0, dtype=torch.float64, device="cuda")
+  def draw(seed, move):
+    _lib.check(lib.mz_dirichlet_noise(G, A, alpha, _lib.ptr(d_legal), seed, move, _lib.ptr(out), None), "noise")
+    torch.cuda.synchronize()
+    return out.cpu().numpy().copy()
+  x = draw(7, 0)
+  n = np.array([bin(int(m)).count("1") for m in legal])
+  assert np.allclose(x.sum(1), 1.0, atol=1e-12) and (x >= 0).all()
+  assert all((x[g, n[g]:] == 0).all() for g in range(G // 2, G, 97))
+  full = x[:G // 2]
+  for col in (0, 7, 17):
+    assert stats.kstest(full[:, col], stats.beta(alpha, (A - 1) * alpha).cdf).pvalue > 1e-3
+    assert stats.ks_2samp(full[:, col], rng.dirichlet([alpha] * A, size=G // 2)[:, col]).pvalue > 1e-3
+  corr = np.corrcoef(full[:, 0], full[:, 1])[0, 1]
+  assert abs(corr - (-1.0 / (A - 1))) < 0.03
+  # a subset of legal actions: components over n_g children follow Beta(alpha, (n_g - 1) * alpha)
+  for k in (2, 5, 9):
+    rows = np.nonzero((n == k) & (np.arange(G) >= G // 2))[0]
+    if len(rows) > 300:
+      assert stats.kstest(x[rows, 0], stats.beta(alpha, (k - 1) * alpha).cdf).pvalue > 1e-3
+  assert (x[n == 1, 0] == 1.0).all()
+  assert np.array_equal(draw(7, 0), x)
+  assert not np.array_equal(draw(7, 1), x) and not np.array_equal(draw(8, 0), x)
+  # alpha >= 1 takes the Marsaglia-Tsang branch without the power correction
+  alpha = 1.5
+  y = draw(3, 0)[:G // 2]
+  assert stats.kstest(y[:, 4], stats.beta(alpha, (A - 1) * alpha).cdf).pvalue > 1e-3
+
+
+@pytest.mark.gpu
+def test_device_actor_with_device_noise_runs_the_whole_loop():
+  """DeviceActor.play_move with nothing brought by the caller: Dirichlet noise drawn on the device, uniforms on the
+  host; moves are legal, chunk commits go through commit_chunks, sampling from the filled replay buffer works."""
+  from model_based_rl_b200.environments import SyntheticRam
+  from model_based_rl_b200.networks import FCNetwork, FCSearch, random_state_dict
+  from model_based_rl_b200.replay_buffer import PrioritizedReplay
+  from model_based_rl_b200.selfplay import DeviceActor
+  import torch
+  A, G, S, D = 6, 256, 8, 128
+  cfg = types.SimpleNamespace(
+      num_simulations=S, action_space=A, two_players=False, discount=0.997, pb_c_base=19652, pb_c_init=1.25,
+      init_value_score=0.0, known_bounds=[None, None], root_dirichlet_alpha=0.25, root_exploration_fraction=0.25,
+      num_unroll_steps=3, td_steps=4, max_history_length=20, max_steps=10 ** 9, value_support=[-15, 15],
+      reward_support=[-15, 15], no_support=False, no_target_transform=False, batch_size=64,
+      beta_increment_per_sampling=0.001, epsilon=0.01, alpha=1.0, beta=0.5, obs_space=(D,), window_size=3000,
+      window_step=None, seed=None, clip_rewards=True)
+  np.random.seed(4)
+  net = FCNetwork(D, A, "cuda", cfg)
+  net.load_weights(random_state_dict(D, A, seed=3))
+  rb = PrioritizedReplay(cfg, window_positions=60000)
+  env = SyntheticRam(G, A, D, episode_length=33, seed=2)
+  actor = DeviceActor(cfg, env, rb, FCSearch(cfg, net, G))
+  env.elapsed[:] = np.arange(G) % 33  # games end on different moves
+  seen = []
+  for _ in range(60):
+    actions, root_value, child_visits, errors, done = actor.play_move()
+    assert ((actions >= 0) & (actions < A)).all()
+    assert np.allclose(np.asarray(child_visits).sum(1), 1.0)
+    seen.append(actor.search.noise.cpu().numpy().copy())
+  assert not np.array_equal(seen[0], seen[1])
+  assert np.allclose(seen[-1].sum(1), 1.0)
+  assert actor.games_played > G and rb.size() > 2000
+  (obs, acts, t_r, t_v, t_p, vs, rs), idx, isw = rb.sample_batch_device(True)
+  torch.cuda.synchronize()
+  assert obs.shape == (64, D) and torch.isfinite(t_v).all() and float(isw.max()) == 1.0
