@@ -403,10 +403,16 @@ int mz_window_append(const mz_window* w, int32_t num_games, const int64_t* dst_p
                      const double* child_visits, void* stream);
 int mz_window_copy(const mz_window* w, int32_t count, const int64_t* src, const int64_t* dst, const int32_t* n,
                    void* stream);
-/* Two kernels serve mz_build_targets: lane-per-unroll-position (K + 1 <= 16 and td_steps <= 64: a warp owns
- * 32 / (K + 1) consecutive rows) and warp-per-row (everything else, e.g. td_steps = 1000).  which = 1 forces
- * the warp-per-row kernel (parity tests run both on the same inputs), 0 restores the choice by shape. */
+/* Three kernels serve mz_build_targets.  For K + 1 <= 16 and td_steps <= 64: the TMA-staged kernel (a CTA stages
+ * the observation / child-visit windows of its rows with cp.async.bulk, builds shared-memory images of all seven
+ * outputs and hands them to the bulk-copy engine) and, where its images do not fit shared memory, the
+ * lane-per-unroll-position kernel (a warp owns 32 / (K + 1) consecutive rows).  Everything else (e.g.
+ * td_steps = 1000): warp per row.  which = 1 forces the warp-per-row kernel, 2 the lane-per-position kernel,
+ * 3 the TMA-staged kernel (parity tests run all of them on the same inputs), 0 restores the choice by shape. */
 int mz_debug_set_targets_kernel(int32_t which);
+/* launch shape of the TMA-staged kernel: sampled rows per CTA (4, 8, 16 or 32) and threads per CTA (a power of
+ * two, 32 .. 256, at least one per row) */
+int mz_debug_set_targets_tma(int32_t rows_per_cta, int32_t threads);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Prioritized-replay sum-tree in HBM (SumTree, replay_buffer.py:6-66): float64 array-embedded    */

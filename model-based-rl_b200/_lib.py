@@ -108,6 +108,7 @@ _SIGNATURES = {
     "mz_fc_tc_packed_bytes": (C.c_int64, [C.c_int32]),
     "mz_debug_set_tc_trace": (C.c_int, [_V]),
     "mz_debug_set_targets_kernel": (C.c_int, [C.c_int32]),
+    "mz_debug_set_targets_tma": (C.c_int, [C.c_int32, C.c_int32]),
     "mz_debug_set_tc_trace_block": (C.c_int, [C.c_int32]),
     "mz_fc_tc_tail_floats": (C.c_int32, []),
     "mz_fc_tc_pack": (C.c_int, [C.POINTER(FcWeights), _V, _V, _V]),

@@ -488,6 +488,262 @@ build_targets_rows_kernel(mz_window w, mz_target_cfg c, const int64_t* __restric
   }
 }
 
+// ---- TMA-staged variant ------------------------------------------------------------------------------
+// The learner's shapes again (K + 1 <= 16, td_steps <= 64), with the window staged through shared memory by the
+// bulk-copy engine.  A CTA owns kTmaRows consecutive sampled rows and keeps a shared-memory image of EVERY output
+// run of those rows (observations, actions, reward / value / policy targets, both supports: contiguous in each
+// output array, a multiple of 16 bytes because kTmaRows is a multiple of four):
+//   1. one lane per row issues cp.async.bulk (global -> shared, mbarrier complete_tx) for the row's observation and
+//      its run of child-visit rows -- the latter straight into the policy image, float32 observations straight into
+//      the observation image -- so the bulky reads of all rows are in flight at once without holding registers;
+//   2. meanwhile all threads fetch the small windows (rewards from pos - 1, to_play, bootstrap root values, actions)
+//      with one independent load per element, zero the supports and the policy tails behind the chunk's end;
+//   3. one thread per (row, unroll position) does insert_target's arithmetic out of shared memory (same operation
+//      order as the lane-per-position kernel: bit-identical outputs) and scatters the two-hot bins;
+//   4. bytes -> float32 (+ normalisation) after the mbarrier flips, fence.proxy.async, and ONE thread hands the seven
+//      images to the bulk-copy engine (shared -> global) and waits until they have been read.
+// ~45 warp instructions per row against 284, no store instruction on the output path.  A last, partial CTA (or
+// unaligned output pointers) writes its images with ordinary stores.
+constexpr int kTmaMaxThreads = 256;
+constexpr int kTmaTpRegs = 5;  // to_play bytes a lane holds: (kRowsMaxPos - 1 + kRowsMaxTd) / kTmaTpRegs lanes per row at least
+
+struct TmaPlan {  // byte offsets into dynamic shared memory, every one a multiple of 16
+  int obs_out, pol, act, val, rew, vs, rs, obs_in, rw, tp, root, pos, bar;
+  int obs_bulk, cv_bulk, out_bulk;
+  int rows;       // rows per CTA: 4, 8, 16 or 32 (every output run of a CTA is then a multiple of 16 bytes)
+  int lpr_shift;  // log2(threads / rows): the lanes that serve one row
+};
+
+MZ_DEV void bulk_copy_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+// 4- / 8-byte asynchronous copies global -> shared (LDGSTS): nothing waits on the loaded value, so a thread's
+// copies of several windows overlap; !valid writes zeros without reading
+MZ_DEV void cp_async4(void* dst_smem, const void* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+MZ_DEV void cp_async8(void* dst_smem, const void* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(valid ? 8 : 0) : "memory");
+}
+MZ_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+MZ_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+MZ_DEV void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+MZ_DEV void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kTmaMaxThreads)
+build_targets_tma_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ pos_arr,
+                         const int64_t* __restrict__ chunk_start, const int32_t* __restrict__ chunk_len,
+                         const int32_t* __restrict__ pad_actions, float* __restrict__ obs_out,
+                         int32_t* __restrict__ actions_out, float* __restrict__ t_rewards,
+                         float* __restrict__ t_values, float* __restrict__ t_policies,
+                         float* __restrict__ value_support, float* __restrict__ reward_support, TmaPlan pl) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int tid = threadIdx.x, nthr = blockDim.x, RB = pl.rows;
+  const int K = c.num_unroll_steps, T = c.td_steps, A = w.num_actions, E = w.obs_elems;
+  const int NP = K + 1, KT = K + T, RW = KT + 1;  // RW: rewards from pos - 1 on
+  const int row0 = blockIdx.x * RB;
+  const int nrows = min(RB, c.batch - row0);
+  const int vb = c.value_max - c.value_min + 1, rb = c.reward_max - c.reward_min + 1;
+  float* s_obs = reinterpret_cast<float*>(sm + pl.obs_out);
+  float* s_pol = reinterpret_cast<float*>(sm + pl.pol);
+  int32_t* s_act = reinterpret_cast<int32_t*>(sm + pl.act);
+  float* s_val = reinterpret_cast<float*>(sm + pl.val);
+  float* s_rew = reinterpret_cast<float*>(sm + pl.rew);
+  float* s_vs = reinterpret_cast<float*>(sm + pl.vs);
+  float* s_rs = reinterpret_cast<float*>(sm + pl.rs);
+  uint8_t* s_obs_in = sm + pl.obs_in;
+  float* s_rw = reinterpret_cast<float*>(sm + pl.rw);
+  int8_t* s_tp = reinterpret_cast<int8_t*>(sm + pl.tp);
+  double* s_root = reinterpret_cast<double*>(sm + pl.root);
+  int32_t* s_step = reinterpret_cast<int32_t*>(sm + pl.pos);
+  int32_t* s_len = s_step + RB;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + pl.bar);
+
+  // thread (r, q0): lane q0 of the LPR = blockDim / rows lanes that serve row r (both powers of two)
+  const int LPR = 1 << pl.lpr_shift;
+  const int r = tid >> pl.lpr_shift, q0 = tid & (LPR - 1);
+  if (tid == 0) {
+    mbar_init(bar, nrows);  // one arrive.expect_tx per row
+    mbar_fence_init();
+  }
+  int64_t pos = 0;
+  int step = 0, len = 0;
+  if (r < nrows) {
+    pos = pos_arr[row0 + r];
+    step = (int)(pos - chunk_start[row0 + r]);
+    len = chunk_len[row0 + r];  // len(root_values) == len(rewards) == len(to_play)
+    if (q0 == 0) {
+      s_step[r] = step;
+      s_len[r] = len;
+    }
+  }
+  __syncthreads();  // the mbarrier is initialised
+
+  // ---- 1. bulk loads: the first lane of a row sends for its observation and its run of child-visit rows
+  const int rem = len - step;  // positions from `step` to the chunk's end
+  const int n_pol = max(0, min(NP, rem)) * A;
+  if (r < nrows && q0 == 0) {
+    const uint32_t obs_row_bytes = (uint32_t)E * (w.obs_is_u8 ? 1u : 4u);
+    const uint32_t cv_bytes = (uint32_t)n_pol * 4u;
+    mbar_arrive_expect_tx(bar, (pl.obs_bulk ? obs_row_bytes : 0u) + (pl.cv_bulk ? cv_bytes : 0u));
+    if (pl.obs_bulk) {
+      void* dst = w.obs_is_u8 ? static_cast<void*>(s_obs_in + (size_t)r * E) : static_cast<void*>(s_obs + (size_t)r * E);
+      bulk_copy_g2s(dst, reinterpret_cast<const uint8_t*>(w.obs) + (size_t)pos * obs_row_bytes, obs_row_bytes, bar);
+    }
+    if (pl.cv_bulk && cv_bytes) bulk_copy_g2s(s_pol + (size_t)r * NP * A, w.child_visits + (size_t)pos * A, cv_bytes, bar);
+  }
+
+  // ---- 2. small windows: asynchronous 4- / 8-byte copies (no thread waits on a loaded value, so the windows of a
+  // row are one round trip), to_play bytes through registers; zero fills
+  if (r < nrows) {
+    int8_t tpv[kTmaTpRegs];
+#pragma unroll
+    for (int u = 0; u < kTmaTpRegs; ++u) {
+      const int j = q0 + u * LPR;
+      tpv[u] = (j < KT && j < rem) ? __ldg(w.to_play + pos + j) : (int8_t)0;
+    }
+    for (int q = q0; q < RW; q += LPR) {  // raw rewards pos - 1 .. pos + K + T - 1 (clipped where they are read)
+      const int ci = step + q - 1;
+      const bool ok = ci >= 0 && ci < len;
+      cp_async4(s_rw + r * RW + q, ok ? w.rewards + pos + q - 1 : w.rewards, ok);
+    }
+    const int n_act = max(0, min(K, rem));
+    for (int i = q0; i < NP; i += LPR) {
+      const bool ok = i + T < rem;  // replay_buffer.py:180-183
+      cp_async8(s_root + r * NP + i, ok ? w.root_values + pos + i + T : w.root_values, ok);
+      if (i < K)  // replay_buffer.py:149-152
+        cp_async4(s_act + r * K + i, i < n_act ? w.actions + pos + i : pad_actions + (size_t)(row0 + r) * K + (i - n_act), true);
+    }
+    if (pl.cv_bulk) {  // absorbing policy behind the chunk's end
+      for (int q = n_pol + q0; q < NP * A; q += LPR) s_pol[r * NP * A + q] = 0.0f;
+    } else {
+      for (int q = q0; q < NP * A; q += LPR) 
+        cp_async4(s_pol + r * NP * A + q, q < n_pol ? w.child_visits + (size_t)pos * A + q : w.child_visits, q < n_pol);
+    }
+#pragma unroll
+    for (int u = 0; u < kTmaTpRegs; ++u) {
+      const int j = q0 + u * LPR;
+      if (j < KT) s_tp[r * KT + j] = tpv[u];
+    }
+  }
+  if (c.fuse_supports) {  // both images are multiples of 16 bytes (rows % 4 == 0)
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* z = reinterpret_cast<float4*>(s_vs);
+    const int nv = (RB * NP * vb) >> 2, nr = (RB * NP * rb) >> 2;
+#pragma unroll 4
+    for (int e = tid; e < nv; e += nthr) z[e] = z4;
+    z = reinterpret_cast<float4*>(s_rs);
+#pragma unroll 4
+    for (int e = tid; e < nr; e += nthr) z[e] = z4;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- 3. insert_target (replay_buffer.py:165-198) for position i of row ri, then learners.py:186-192
+  for (int it = tid; it < nrows * NP; it += nthr) {
+    const int ri = it / NP, i = it - ri * NP;
+    const int len_i = s_len[ri], ci = s_step[ri] + i;
+    float value = 0.0f, last_reward = 0.0f;
+    if (ci < len_i) {
+      const int n = min(T, len_i - ci);
+      const float* rw = s_rw + ri * RW + 1 + i;
+      const int8_t* tp = s_tp + ri * KT + i;
+      const int tp0 = tp[0];
+      double acc = 0.0;  // exact products of float32 pairs, accumulated in binary64, j ascending
+      for (int j = 0; j < n; ++j) {  // replay_buffer.py:187-189
+        const float x = tgt_reward(rw[j], w.clip_rewards);
+        acc += (double)(tp[j] != tp0 ? -x : x) * (double)__ldg(c.discounts + j);
+      }
+      const double boot = (ci + T < len_i) ? __dmul_rn(s_root[it], c.disc_pow_td) : 0.0;
+      value = __fadd_rn((float)boot, (float)acc);  // numpy 2: python float + np.float32 -> float32
+    }
+    if (ci > 0 && ci <= len_i) last_reward = tgt_reward(s_rw[ri * RW + i], w.clip_rewards);
+    s_val[it] = value;
+    s_rew[it] = last_reward;
+    if (c.fuse_supports) {
+      const MzTwoHot tv = mz_two_hot(c.no_target_transform ? value : mz_scalar_transform_f(value), c.value_min, c.value_max);
+      const MzTwoHot tr = mz_two_hot(c.no_target_transform ? last_reward : mz_scalar_transform_f(last_reward), c.reward_min,
+                                     c.reward_max);
+      float* pv = s_vs + (size_t)it * vb;
+      pv[tv.hi] = tv.p_hi;
+      pv[tv.lo] = tv.p_lo;  // the low bin wins on integers (config.py:64-67)
+      float* pr = s_rs + (size_t)it * rb;
+      pr[tr.hi] = tr.p_hi;
+      pr[tr.lo] = tr.p_lo;
+    }
+  }
+
+  // ---- 4. observations: np.float32(history.observations[step]) (replay_buffer.py:147)
+  mbar_wait(bar, 0);
+  if (r < nrows) {
+    float* so = s_obs + (size_t)r * E;
+    if (w.obs_is_u8 && pl.obs_bulk) {  // E % 16 == 0
+      const uint32_t* in = reinterpret_cast<const uint32_t*>(s_obs_in + (size_t)r * E);
+      for (int e = q0; e < (E >> 2); e += LPR) {
+        const uint32_t q = in[e];
+        float4 v = make_float4((float)(q & 255u), (float)((q >> 8) & 255u), (float)((q >> 16) & 255u), (float)(q >> 24));
+        if (c.normalize_obs) {
+          const int k = e * 4;
+          v.x = __fdiv_rn(__fsub_rn(v.x, c.obs_min[k]), c.obs_range[k]);
+          v.y = __fdiv_rn(__fsub_rn(v.y, c.obs_min[k + 1]), c.obs_range[k + 1]);
+          v.z = __fdiv_rn(__fsub_rn(v.z, c.obs_min[k + 2]), c.obs_range[k + 2]);
+          v.w = __fdiv_rn(__fsub_rn(v.w, c.obs_min[k + 3]), c.obs_range[k + 3]);
+        }
+        reinterpret_cast<float4*>(so)[e] = v;
+      }
+    } else if (w.obs_is_u8) {
+      const uint8_t* in = reinterpret_cast<const uint8_t*>(w.obs) + (size_t)pos * E;
+      for (int k = q0; k < E; k += LPR) {
+        float v = (float)__ldg(in + k);
+        if (c.normalize_obs) v = __fdiv_rn(__fsub_rn(v, c.obs_min[k]), c.obs_range[k]);
+        so[k] = v;
+      }
+    } else if (!pl.obs_bulk || c.normalize_obs) {
+      const float* in = reinterpret_cast<const float*>(w.obs) + (size_t)pos * E;
+      for (int k = q0; k < E; k += LPR) {
+        float v = pl.obs_bulk ? so[k] : __ldg(in + k);
+        if (c.normalize_obs) v = __fdiv_rn(__fsub_rn(v, c.obs_min[k]), c.obs_range[k]);
+        so[k] = v;
+      }
+    }
+  }
+
+  // ---- 5. the images leave
+  if (pl.out_bulk && nrows == RB) {
+    fence_proxy_async_smem();  // generic-proxy writes of this thread -> visible to the bulk-copy engine
+    __syncthreads();
+    if (tid == 0) {
+      bulk_copy_s2g(obs_out + (size_t)row0 * E, s_obs, (uint32_t)(RB * E) * 4u);
+      bulk_copy_s2g(t_policies + (size_t)row0 * NP * A, s_pol, (uint32_t)(RB * NP * A) * 4u);
+      if (K > 0) bulk_copy_s2g(actions_out + (size_t)row0 * K, s_act, (uint32_t)(RB * K) * 4u);
+      bulk_copy_s2g(t_values + (size_t)row0 * NP, s_val, (uint32_t)(RB * NP) * 4u);
+      bulk_copy_s2g(t_rewards + (size_t)row0 * NP, s_rew, (uint32_t)(RB * NP) * 4u);
+      if (c.fuse_supports) {
+        bulk_copy_s2g(value_support + (size_t)row0 * NP * vb, s_vs, (uint32_t)(RB * NP * vb) * 4u);
+        bulk_copy_s2g(reward_support + (size_t)row0 * NP * rb, s_rs, (uint32_t)(RB * NP * rb) * 4u);
+      }
+      bulk_commit();
+      bulk_wait_read_all();  // shared memory must stay until the engine has read it
+    }
+    return;
+  }
+  __syncthreads();
+  auto flush = [&](float* dst, const float* src, int n) {
+    for (int e = tid; e < n; e += nthr) dst[e] = src[e];
+  };
+  flush(obs_out + (size_t)row0 * E, s_obs, nrows * E);
+  flush(t_policies + (size_t)row0 * NP * A, s_pol, nrows * NP * A);
+  flush(reinterpret_cast<float*>(actions_out) + (size_t)row0 * K, reinterpret_cast<const float*>(s_act), nrows * K);
+  flush(t_values + (size_t)row0 * NP, s_val, nrows * NP);
+  flush(t_rewards + (size_t)row0 * NP, s_rew, nrows * NP);
+  if (c.fuse_supports) {
+    flush(value_support + (size_t)row0 * NP * vb, s_vs, nrows * NP * vb);
+    flush(reward_support + (size_t)row0 * NP * rb, s_rs, nrows * NP * rb);
+  }
+}
+
 __global__ void scalar_transform_kernel(long long n, const float* __restrict__ x,
                                         float* __restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -590,12 +846,24 @@ int grid_for(long long n, int threads) {
 
 }  // namespace
 
-int g_targets_kernel = 0;  // 0: by shape, 1: always the warp-per-row kernel (tests)
+int g_tma_rows = 8, g_tma_threads = 128;
+// 0: by shape, 1: always the warp-per-row kernel, 2: lane-per-position kernel where the shape allows it (never the
+// TMA-staged one), 3: TMA-staged kernel where the shape allows it (tests run all on the same inputs)
+int g_targets_kernel = 0;
 
 extern "C" {
 
 int mz_debug_set_targets_kernel(int32_t which) {
   g_targets_kernel = which;
+  return MZ_OK;
+}
+
+int mz_debug_set_targets_tma(int32_t rows_per_cta, int32_t threads) {
+  if (rows_per_cta < 4 || rows_per_cta > 32 || (rows_per_cta & (rows_per_cta - 1)) || threads < 32 ||
+      threads > kTmaMaxThreads || (threads & (threads - 1)) || threads < rows_per_cta)
+    return MZ_ERR_BAD_ARG;
+  g_tma_rows = rows_per_cta;
+  g_tma_threads = threads;
   return MZ_OK;
 }
 
@@ -669,7 +937,56 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
   if (!w->obs || !w->actions || !w->rewards || !w->to_play || !w->root_values || !w->child_visits)
     return MZ_ERR_BAD_ARG;
   const int K1 = c->num_unroll_steps + 1, KT = c->num_unroll_steps + c->td_steps;
-  if (K1 <= kRowsMaxPos && c->td_steps <= kRowsMaxTd && g_targets_kernel != 1) {
+  if (K1 <= kRowsMaxPos && c->td_steps <= kRowsMaxTd && g_targets_kernel != 1 && g_targets_kernel != 2) {
+    // TMA-staged kernel: shared-memory images of `rows` rows of every output
+    const int A = w->num_actions, E = w->obs_elems;
+    const int vb = c->fuse_supports ? c->value_max - c->value_min + 1 : 0;
+    const int rb = c->fuse_supports ? c->reward_max - c->reward_min + 1 : 0;
+    TmaPlan pl;
+    const int kTmaRows = g_tma_rows, kTmaThreads = g_tma_threads;
+    pl.rows = kTmaRows;
+    pl.lpr_shift = 0;
+    while ((kTmaRows << (pl.lpr_shift + 1)) <= kTmaThreads) ++pl.lpr_shift;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+      const size_t o = off;
+      off += (bytes + 15) / 16 * 16;
+      return (int)o;
+    };
+    pl.obs_out = take((size_t)kTmaRows * E * 4);
+    pl.pol = take((size_t)kTmaRows * K1 * A * 4);
+    pl.act = take((size_t)kTmaRows * c->num_unroll_steps * 4);
+    pl.val = take((size_t)kTmaRows * K1 * 4);
+    pl.rew = take((size_t)kTmaRows * K1 * 4);
+    pl.vs = take((size_t)kTmaRows * K1 * vb * 4);
+    pl.rs = take((size_t)kTmaRows * K1 * rb * 4);
+    pl.obs_in = take(w->obs_is_u8 ? (size_t)kTmaRows * E : 0);
+    pl.rw = take((size_t)kTmaRows * (KT + 1) * 4);
+    pl.tp = take((size_t)kTmaRows * KT);
+    pl.root = take((size_t)kTmaRows * K1 * 8);
+    pl.pos = take((size_t)kTmaRows * 16);
+    pl.bar = take(8);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const size_t obs_row_bytes = (size_t)E * (w->obs_is_u8 ? 1 : 4);
+    pl.obs_bulk = (obs_row_bytes % 16 == 0) && al16(w->obs);
+    pl.cv_bulk = (A % 4 == 0) && al16(w->child_visits);
+    pl.out_bulk = al16(obs_out) && al16(actions_out) && al16(t_rewards) && al16(t_values) && al16(t_policies) &&
+                  al16(value_support) && al16(reward_support);
+    if (off <= 96 * 1024 && KT <= (kTmaTpRegs << pl.lpr_shift)) {  // several CTAs per SM, so that loads, arithmetic and stores of different CTAs overlap
+      static bool tma_attr_set = false;
+      if (!tma_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(build_targets_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        tma_attr_set = true;
+      }
+      build_targets_tma_kernel<<<(c->batch + kTmaRows - 1) / kTmaRows, kTmaThreads, off, (cudaStream_t)stream>>>(
+          *w, *c, pos, chunk_start, chunk_len, pad_actions, obs_out, actions_out, t_rewards, t_values, t_policies,
+          value_support, reward_support, pl);
+      MZ_LAUNCH_CHECK();
+      return MZ_OK;
+    }
+  }
+  if (K1 <= kRowsMaxPos && c->td_steps <= kRowsMaxTd && g_targets_kernel != 1 && g_targets_kernel != 3) {
     const int rows_per_cta = (kTgtWarps / 2) * (32 / K1);
     build_targets_rows_kernel<<<(c->batch + rows_per_cta - 1) / rows_per_cta, kTgtThreads, 0, (cudaStream_t)stream>>>(
         *w, *c, pos, chunk_start, chunk_len, pad_actions, obs_out, actions_out, t_rewards, t_values, t_policies,

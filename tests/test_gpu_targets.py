@@ -34,9 +34,10 @@ def _window_from_golden(g):
   return dev, np.array(starts, np.int64), np.array(lens, np.int32)
 
 
-@pytest.fixture(params=[0, 1], ids=["kernel_by_shape", "warp_per_row_kernel"])
+@pytest.fixture(params=[0, 1, 2], ids=["kernel_by_shape", "warp_per_row_kernel", "lane_per_position_kernel"])
 def targets_kernel(request):
-  """Both kernels behind mz_build_targets (include/mzb200.h) run every case they are able to."""
+  """The three kernels behind mz_build_targets (include/mzb200.h: TMA-staged by shape, warp per row, lane per
+  position) run every case they are able to."""
   from model_based_rl_b200 import _lib
   lib = _lib.load()
   lib.mz_debug_set_targets_kernel(request.param)
@@ -190,6 +191,9 @@ def test_full_size_target_properties():
     (18, 5, 1, 33, 12, True, False, False),    # td_steps = 1
     (4, 15, 64, 7, 128, True, False, True),    # the lane-per-position kernel's limits: 16 positions, td_steps 64
     (6, 9, 7, 31, 16, False, True, True),      # three rows per warp, two idle lanes
+    (4, 5, 10, 48, 16, True, True, True),      # TMA-staged kernel, every bulk path on: full CTAs, byte observations
+    (8, 3, 6, 35, 8, False, False, False),     # same with float32 observations landing in the output image directly
+    (4, 2, 5, 32, 64, False, True, False),     # float32 observations normalised in place in shared memory
 ])
 def test_build_targets_ragged_shapes_match_oracle(shape, targets_kernel):
   """Every row of a batch against oracle.insert_target (replay_buffer.py:165-198) on short ragged chunks:
@@ -303,7 +307,10 @@ def test_bulk_launch_kernels_agree_and_match_oracle():
     finally:
       lib.mz_debug_set_targets_kernel(0)
     return out
-  rows, wide = run(0), run(1)
+  rows, wide, lanes = run(0), run(1), run(2)
+  # the TMA-staged kernel (by shape) and the lane-per-position kernel do the same arithmetic in the same order
+  for i in range(7):
+    assert torch.equal(rows[i], lanes[i]), i
   for i in (0, 1, 2, 4):
     assert torch.equal(rows[i], wide[i]), i
   rel = ((rows[3] - wide[3]).abs() / wide[3].abs().clamp(min=1.0)).max().item()
