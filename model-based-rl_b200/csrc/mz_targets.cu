@@ -505,7 +505,6 @@ build_targets_rows_kernel(mz_window w, mz_target_cfg c, const int64_t* __restric
 // ~45 warp instructions per row against 284, no store instruction on the output path.  A last, partial CTA (or
 // unaligned output pointers) writes its images with ordinary stores.
 constexpr int kTmaMaxThreads = 256;
-constexpr int kTmaTpRegs = 5;  // to_play bytes a lane holds: (kRowsMaxPos - 1 + kRowsMaxTd) / kTmaTpRegs lanes per row at least
 
 struct TmaPlan {  // byte offsets into dynamic shared memory, every one a multiple of 16
   int obs_out, pol, act, val, rew, vs, rs, obs_in, rw, tp, root, pos, bar;
@@ -559,6 +558,8 @@ build_targets_tma_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict
   double* s_root = reinterpret_cast<double*>(sm + pl.root);
   int32_t* s_step = reinterpret_cast<int32_t*>(sm + pl.pos);
   int32_t* s_len = s_step + RB;
+  int32_t* s_tpoff = s_len + RB;
+  const int TPS = (KT + 6) & ~3;  // to_play bytes per row: the window plus its 4-byte alignment slack
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + pl.bar);
 
   // thread (r, q0): lane q0 of the LPR = blockDim / rows lanes that serve row r (both powers of two)
@@ -577,6 +578,7 @@ build_targets_tma_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict
     if (q0 == 0) {
       s_step[r] = step;
       s_len[r] = len;
+      s_tpoff[r] = (int)(pos & 3);
     }
   }
   __syncthreads();  // the mbarrier is initialised
@@ -598,11 +600,16 @@ build_targets_tma_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict
   // ---- 2. small windows: asynchronous 4- / 8-byte copies (no thread waits on a loaded value, so the windows of a
   // row are one round trip), to_play bytes through registers; zero fills
   if (r < nrows) {
-    int8_t tpv[kTmaTpRegs];
-#pragma unroll
-    for (int u = 0; u < kTmaTpRegs; ++u) {
-      const int j = q0 + u * LPR;
-      tpv[u] = (j < KT && j < rem) ? __ldg(w.to_play + pos + j) : (int8_t)0;
+    {  // to_play: the 4-byte words that cover bytes [pos, pos + min(K + T, rem)); byte j of the window then sits at
+       // s_tp[r * TPS + (pos & 3) + j].  The last word is read only as far as the window reaches.
+      const int off = (int)(pos & 3), nbytes = off + max(0, min(KT, rem));
+      const int8_t* base = w.to_play + (pos - off);
+      for (int q = q0; q * 4 < off + KT; q += LPR) {
+        const int have = min(4, nbytes - q * 4);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(s_tp + r * TPS + q * 4)),
+                     "l"(have > 0 ? base + q * 4 : w.to_play), "r"(max(have, 0))
+                     : "memory");
+      }
     }
     for (int q = q0; q < RW; q += LPR) {  // raw rewards pos - 1 .. pos + K + T - 1 (clipped where they are read)
       const int ci = step + q - 1;
@@ -622,21 +629,13 @@ build_targets_tma_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict
       for (int q = q0; q < NP * A; q += LPR) 
         cp_async4(s_pol + r * NP * A + q, q < n_pol ? w.child_visits + (size_t)pos * A + q : w.child_visits, q < n_pol);
     }
-#pragma unroll
-    for (int u = 0; u < kTmaTpRegs; ++u) {
-      const int j = q0 + u * LPR;
-      if (j < KT) s_tp[r * KT + j] = tpv[u];
-    }
   }
-  if (c.fuse_supports) {  // both images are multiples of 16 bytes (rows % 4 == 0)
+  if (c.fuse_supports) {  // both images are multiples of 16 bytes (rows % 4 == 0) and adjacent: one fill
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4* z = reinterpret_cast<float4*>(s_vs);
-    const int nv = (RB * NP * vb) >> 2, nr = (RB * NP * rb) >> 2;
+    const int nz = (RB * NP * (vb + rb)) >> 2;
 #pragma unroll 4
-    for (int e = tid; e < nv; e += nthr) z[e] = z4;
-    z = reinterpret_cast<float4*>(s_rs);
-#pragma unroll 4
-    for (int e = tid; e < nr; e += nthr) z[e] = z4;
+    for (int e = tid; e < nz; e += nthr) z[e] = z4;
   }
   cp_async_wait_all();
   __syncthreads();
@@ -649,7 +648,7 @@ build_targets_tma_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict
     if (ci < len_i) {
       const int n = min(T, len_i - ci);
       const float* rw = s_rw + ri * RW + 1 + i;
-      const int8_t* tp = s_tp + ri * KT + i;
+      const int8_t* tp = s_tp + ri * TPS + s_tpoff[ri] + i;
       const int tp0 = tp[0];
       double acc = 0.0;  // exact products of float32 pairs, accumulated in binary64, j ascending
       for (int j = 0; j < n; ++j) {  // replay_buffer.py:187-189
@@ -962,7 +961,7 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
     pl.rs = take((size_t)kTmaRows * K1 * rb * 4);
     pl.obs_in = take(w->obs_is_u8 ? (size_t)kTmaRows * E : 0);
     pl.rw = take((size_t)kTmaRows * (KT + 1) * 4);
-    pl.tp = take((size_t)kTmaRows * KT);
+    pl.tp = take((size_t)kTmaRows * ((KT + 6) & ~3));
     pl.root = take((size_t)kTmaRows * K1 * 8);
     pl.pos = take((size_t)kTmaRows * 16);
     pl.bar = take(8);
@@ -972,7 +971,7 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
     pl.cv_bulk = (A % 4 == 0) && al16(w->child_visits);
     pl.out_bulk = al16(obs_out) && al16(actions_out) && al16(t_rewards) && al16(t_values) && al16(t_policies) &&
                   al16(value_support) && al16(reward_support);
-    if (off <= 96 * 1024 && KT <= (kTmaTpRegs << pl.lpr_shift)) {  // several CTAs per SM, so that loads, arithmetic and stores of different CTAs overlap
+    if (off <= 96 * 1024 && (reinterpret_cast<uintptr_t>(w->to_play) & 3) == 0) {  // several CTAs per SM, so that loads, arithmetic and stores of different CTAs overlap
       static bool tma_attr_set = false;
       if (!tma_attr_set) {
         cudaError_t e = cudaFuncSetAttribute(build_targets_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
