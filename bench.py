@@ -834,15 +834,22 @@ def bench_replay(torch, _lib, dev, cpu_baseline=True):
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n
   t_host = wall(rb.sample_batch, 20)
-  t_dev = wall(lambda: rb.sample_batch_device(True), 50)
+  t_dev0 = wall(lambda: rb.sample_batch_device(True), 50)
+  t_dev = wall(lambda: rb.sample_batch_device(True, ring=4), 200)
   _, idxs, _ = rb.sample_batch()
   errs = np.abs(rng.normal(size=B)).astype(np.float32)
-  t_upd = wall(lambda: rb.update(idxs, errs), 20)
+  t_upd0 = wall(lambda: rb.update(idxs, errs), 20)
+  d_idx, d_err = torch.tensor(idxs, dtype=torch.int64, device=dev), torch.from_numpy(errs).to(dev)
+  t_upd = wall(lambda: rb.update(d_idx, d_err), 200)
   out = {"workload": "C3 Breakout-ram replay: window %d filled by save_history, B=%d, K=%d, td=%d, A=%d, obs %d u8" % (W, B, K, T, A, E),
          "size": rb.size(),
          "sample_batch_samples_per_s": B / t_host, "sample_batch_ms": t_host * 1e3,
          "sample_batch_device_samples_per_s": B / t_dev, "sample_batch_device_ms": t_dev * 1e3,
-         "update_ms": t_upd * 1e3}
+         "sample_batch_device_fresh_outputs_ms": t_dev0 * 1e3,
+         "update_ms": t_upd * 1e3, "update_host_arrays_ms": t_upd0 * 1e3,
+         "note": "sample_batch_device: ring of 4 preallocated output sets, pinned staging, one library call "
+                 "(mz_replay_sample_targets); update: CUDA idxs + float32 errors (mz_sumtree_update_errors); the "
+                 "*_fresh_outputs / *_host_arrays figures are the same calls with per-call allocations / numpy inputs"}
   if cpu_baseline:
     import oracle
     from oracle import replay_ref

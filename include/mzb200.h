@@ -458,6 +458,35 @@ int mz_sumtree_sample(const double* tree, int64_t max_capacity, int32_t n, const
                       int64_t num_memories, double beta, int64_t* tree_idx, double* priority,
                       int64_t* pos, int64_t* chunk_start, int32_t* chunk_len, double* is_weights,
                       void* stream);
+/* sample_batch in one call (replay_buffer.py:124-163): mz_sumtree_sample followed by mz_build_targets on the rows
+ * it drew -- the sampling outputs (pos / chunk_start / chunk_len) stay on the device as the target kernel's inputs.
+ * Arguments as in the two functions, plus:
+ *   u01_is_mt_words != 0: u01[b] holds the two raw MT19937 outputs CPython's random.random() would consume for
+ *     row b (little endian, as random.getrandbits(64 * n).to_bytes(8 * n, "little") lays them out); the kernel forms
+ *     ((w0 >> 5) * 2**26 + (w1 >> 6)) / 2**53 itself -- the same float64, without 512 interpreter calls;
+ *   pad_seed != 0: the padding actions (np.random.randint(action_space), replay_buffer.py:149-152) are drawn on
+ *     the device into pad_actions [B][K] from splitmix64(pad_seed, index) instead of being read from it. */
+int mz_replay_sample_targets(const double* tree, int64_t max_capacity, const double* u01, int32_t u01_is_mt_words,
+                             const int64_t* slot_pos, const int64_t* slot_start, const int32_t* slot_len,
+                             int64_t num_memories, double beta, int64_t* tree_idx, double* priority, int64_t* pos,
+                             int64_t* chunk_start, int32_t* chunk_len, double* is_weights, const mz_window* w,
+                             const mz_target_cfg* c, int32_t* pad_actions, uint64_t pad_seed, float* obs_out,
+                             int32_t* actions_out, float* t_rewards, float* t_values, float* t_policies,
+                             float* value_support, float* reward_support, void* stream);
+/* mz_sumtree_sample with the u01_is_mt_words switch described above */
+int mz_sumtree_sample_mt(const double* tree, int64_t max_capacity, int32_t n, const double* u01, int32_t u01_is_mt_words,
+                         const int64_t* slot_pos, const int64_t* slot_start, const int32_t* slot_len,
+                         int64_t num_memories, double beta, int64_t* tree_idx, double* priority,
+                         int64_t* pos, int64_t* chunk_start, int32_t* chunk_len, double* is_weights,
+                         void* stream);
+/* PrioritizedReplay.update (replay_buffer.py:200-203) from the learner's float32 errors still on the device
+ * (learners.py:183): priority = (|error| + epsilon) ** alpha in numpy's float32 arithmetic (np.abs(float32 array) +
+ * python float stays float32, NEP 50), widened to the tree's float64, then mz_sumtree_update.  alpha == 1 is
+ * bit-exact; any other alpha goes through pow() and may differ from numpy's powf in the last float32 bit (the
+ * Python facade routes those through the host).  priority / scratch: [n] f64 workspaces. */
+int mz_sumtree_update_errors(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
+                             const float* errors, double epsilon, double alpha, double* priority, double* scratch,
+                             void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* MuZeroNetwork (residual conv tower, networks.py:393-554) on tcgen05 tensor cores, bf16/f32 acc. */

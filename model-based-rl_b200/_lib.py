@@ -138,6 +138,12 @@ _SIGNATURES = {
                                  _V, _V]),
     "mz_dirichlet_noise": (C.c_int, [C.c_int32, C.c_int32, C.c_double, _V, C.c_uint64, C.c_uint64, _V, _V]),
     "mz_sumtree_add_chunks": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_int32, _V, _V, _V, _V, _V, _V, _V, _V]),
+    "mz_replay_sample_targets": (C.c_int, [_V, C.c_int64, _V, C.c_int32, _V, _V, _V, C.c_int64, C.c_double, _V, _V, _V, _V,
+                                           _V, _V, C.POINTER(Window), C.POINTER(TargetCfg), _V, C.c_uint64, _V, _V, _V, _V,
+                                           _V, _V, _V, _V]),
+    "mz_sumtree_sample_mt": (C.c_int, [_V, C.c_int64, C.c_int32, _V, C.c_int32, _V, _V, _V, C.c_int64, C.c_double, _V, _V,
+                                       _V, _V, _V, _V, _V]),
+    "mz_sumtree_update_errors": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_double, C.c_double, _V, _V, _V]),
     "mz_sumtree_add_from": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_int64, C.c_int32, C.c_int32, _V, _V, _V,
                                       _V, _V]),
     "mz_sumtree_sample": (C.c_int, [_V, C.c_int64, C.c_int32, _V, _V, _V, _V, C.c_int64, C.c_double,

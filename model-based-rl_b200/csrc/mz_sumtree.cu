@@ -13,7 +13,7 @@
 namespace {
 
 constexpr int kUpdThreads = 256;
-constexpr int kUpdChunk = 2048;  // updates per launch (16 B of shared memory each)
+constexpr int kUpdChunk = 2048;  // updates per launch (a power of two: 16 B of shared memory each, 12 key bits)
 
 // depth of a node in the array-embedded heap (root = 0)
 MZ_DEV int node_depth(int64_t node) { return 63 - __clzll((unsigned long long)(node + 1)); }
@@ -23,50 +23,76 @@ MZ_DEV int64_t ancestor_at(int64_t leaf, int depth) {
   return up < 0 ? -1 : (((leaf + 1) >> up) - 1);
 }
 
-// change[i] = priority[i] - (value of the leaf just before update i)  (replay_buffer.py:36)
-__global__ void sumtree_change_kernel(const double* __restrict__ tree, int n,
+// Both kernels below bring the updates that touch the same node together by sorting 64-bit keys (node << 12 |
+// batch index) in shared memory: a node's updates end up adjacent AND in batch order, so one thread can apply them
+// with the reference's sequence of float64 additions.  O(n log^2 n) compare-exchanges per CTA instead of the
+// O(n^2) scans of the first version (a 500-memory add: 176 -> ~20 us).
+MZ_DEV void bitonic_sort_u64(unsigned long long* keys, int N) {  // N a power of two, all threads of the CTA call
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;  // pair (lo, lo + j)
+        const unsigned long long a = keys[lo], b = keys[hi];
+        const bool up = (lo & k) == 0;
+        if ((a > b) == up) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+constexpr unsigned long long kKeySkip = ~0ull;
+
+// change[i] = priority[i] - (value of the leaf just before update i)  (replay_buffer.py:36): the priority of the
+// previous update of the same leaf in this batch, else the tree's
+__global__ void sumtree_change_kernel(const double* __restrict__ tree, int n, int N,
                                       const int64_t* __restrict__ idx,
                                       const double* __restrict__ pri, double* __restrict__ change) {
-  __shared__ int64_t s_idx[kUpdChunk];
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s_idx[i] = idx[i];
+  __shared__ unsigned long long s_key[kUpdChunk];
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    s_key[i] = i < n ? ((unsigned long long)idx[i] << 12) | (unsigned)i : kKeySkip;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int64_t leaf = s_idx[i];
-    int j = i - 1;
-    while (j >= 0 && s_idx[j] != leaf) --j;
-    const double before = j >= 0 ? pri[j] : tree[leaf];
+  bitonic_sort_u64(s_key, N);
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const unsigned long long key = s_key[p];
+    const int i = (int)(key & 4095);
+    const int64_t leaf = (int64_t)(key >> 12);
+    const bool again = p > 0 && (int64_t)(s_key[p - 1] >> 12) == leaf;
+    const double before = again ? pri[s_key[p - 1] & 4095] : tree[leaf];
     change[i] = __dsub_rn(pri[i], before);
   }
 }
 
 // blockIdx.x = depth of the nodes this CTA owns (with a capacity that is not a power of two the
 // leaves sit on two depths, so ownership goes by absolute depth, not by height above the leaf)
-__global__ void sumtree_apply_kernel(double* __restrict__ tree, int n,
+__global__ void sumtree_apply_kernel(double* __restrict__ tree, int n, int N,
                                      const int64_t* __restrict__ idx, const double* __restrict__ pri,
                                      const double* __restrict__ change) {
-  __shared__ int64_t s_node[kUpdChunk];
+  __shared__ unsigned long long s_key[kUpdChunk];
   __shared__ double s_change[kUpdChunk];
   const int depth = blockIdx.x;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    s_node[i] = ancestor_at(idx[i], depth);
-    s_change[i] = change[i];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int64_t node = i < n ? ancestor_at(idx[i], depth) : -1;  // -1: this leaf sits above `depth`
+    s_key[i] = node >= 0 ? ((unsigned long long)node << 12) | (unsigned)i : kKeySkip;
+    if (i < n) s_change[i] = change[i];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int64_t node = s_node[i];
-    if (node < 0) continue;  // this leaf sits above `depth`
-    if (node == idx[i]) {    // the leaf itself
-      int j = i + 1;
-      while (j < n && s_node[j] != node) ++j;
-      if (j == n) tree[node] = pri[i];  // the last write to a leaf wins
+  bitonic_sort_u64(s_key, N);
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const unsigned long long key = s_key[p];
+    if (key == kKeySkip) continue;
+    const int64_t node = (int64_t)(key >> 12);
+    if (p > 0 && (int64_t)(s_key[p - 1] >> 12) == node) continue;  // an earlier update owns this node
+    int q = p;
+    if (node == idx[key & 4095]) {  // the leaf itself: the last write wins
+      while (q + 1 < n && (int64_t)(s_key[q + 1] >> 12) == node) ++q;
+      tree[node] = pri[s_key[q] & 4095];
       continue;
     }
-    int j = i - 1;
-    while (j >= 0 && s_node[j] != node) --j;
-    if (j >= 0) continue;  // an earlier update owns this node
     double v = tree[node];
-    for (j = i; j < n; ++j)
-      if (s_node[j] == node) v = __dadd_rn(v, s_change[j]);
+    for (; q < n && (int64_t)(s_key[q] >> 12) == node; ++q) v = __dadd_rn(v, s_change[s_key[q] & 4095]);
     tree[node] = v;
   }
 }
@@ -109,7 +135,7 @@ __global__ void sumtree_sample_kernel(const double* __restrict__ tree, int64_t s
                                       const int64_t* __restrict__ slot_pos,
                                       const int64_t* __restrict__ slot_start,
                                       const int32_t* __restrict__ slot_len, double num_memories,
-                                      double beta, int64_t* __restrict__ out_idx,
+                                      double beta, int u01_is_mt_words, int64_t* __restrict__ out_idx,
                                       double* __restrict__ out_pri, int64_t* __restrict__ out_pos,
                                       int64_t* __restrict__ out_start, int32_t* __restrict__ out_len,
                                       double* __restrict__ is_weights) {
@@ -120,7 +146,12 @@ __global__ void sumtree_sample_kernel(const double* __restrict__ tree, int64_t s
   for (int b = threadIdx.x; b < n; b += blockDim.x) {
     // random.uniform(s1, s2) = s1 + (s2 - s1) * random()
     const double s1 = __dmul_rn(segment, (double)b), s2 = __dmul_rn(segment, (double)(b + 1));
-    double value = __dadd_rn(s1, __dmul_rn(__dsub_rn(s2, s1), u01[b]));
+    double u = u01[b];
+    if (u01_is_mt_words) {  // CPython's random(): (a >> 5) * 2**26 + (b >> 6)) / 2**53 from two MT19937 outputs
+      const uint2 w = reinterpret_cast<const uint2*>(u01)[b];
+      u = __dmul_rn(__dadd_rn(__dmul_rn((double)(w.x >> 5), 67108864.0), (double)(w.y >> 6)), 1.0 / 9007199254740992.0);
+    }
+    double value = __dadd_rn(s1, __dmul_rn(__dsub_rn(s2, s1), u));
     int64_t parent = 0;
     for (;;) {
       const int64_t left = 2 * parent + 1;
@@ -157,6 +188,16 @@ __global__ void sumtree_sample_kernel(const double* __restrict__ tree, int64_t s
   for (int b = threadIdx.x; b < n; b += blockDim.x) is_weights[b] = __ddiv_rn(is_weights[b], wmax);
 }
 
+// (|error| + epsilon) ** alpha like numpy on a float32 array with python-float epsilon / alpha
+__global__ void priorities_kernel(int n, const float* __restrict__ errors, float epsilon, float alpha,
+                                  double* __restrict__ priority) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float p = __fadd_rn(fabsf(errors[i]), epsilon);
+  if (alpha != 1.0f) p = (float)pow((double)p, (double)alpha);
+  priority[i] = (double)p;
+}
+
 int tree_levels(int64_t max_capacity) {
   int levels = 1;  // leaves
   for (int64_t deepest = 2 * max_capacity - 1; deepest > 1; deepest >>= 1) ++levels;
@@ -175,8 +216,10 @@ int mz_sumtree_update(double* tree, int64_t max_capacity, int64_t n, const int64
   const int levels = tree_levels(max_capacity);
   for (int64_t o = 0; o < n; o += kUpdChunk) {
     const int m = (int)((n - o) < kUpdChunk ? (n - o) : kUpdChunk);
-    sumtree_change_kernel<<<1, kUpdThreads, 0, st>>>(tree, m, tree_idx + o, priority + o, scratch + o);
-    sumtree_apply_kernel<<<levels, kUpdThreads, 0, st>>>(tree, m, tree_idx + o, priority + o,
+    int N = 2;
+    while (N < m) N <<= 1;  // the sort runs over the next power of two
+    sumtree_change_kernel<<<1, kUpdThreads, 0, st>>>(tree, m, N, tree_idx + o, priority + o, scratch + o);
+    sumtree_apply_kernel<<<levels, kUpdThreads, 0, st>>>(tree, m, N, tree_idx + o, priority + o,
                                                           scratch + o);
   }
   MZ_LAUNCH_CHECK();
@@ -194,6 +237,17 @@ int mz_sumtree_add_from(double* tree, int64_t max_capacity, int64_t n, const int
       (int)n, tree_idx, max_capacity - 1, chunk_start, chunk_len, slot_pos, slot_start, slot_len, first_step);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
+}
+
+int mz_sumtree_update_errors(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
+                             const float* errors, double epsilon, double alpha, double* priority, double* scratch,
+                             void* stream) {
+  if (n < 0 || (n > 0 && (!errors || !priority))) return MZ_ERR_BAD_ARG;
+  if (n == 0) return MZ_OK;
+  priorities_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((int)n, errors, (float)epsilon,
+                                                                                   (float)alpha, priority);
+  MZ_LAUNCH_CHECK();
+  return mz_sumtree_update(tree, max_capacity, n, tree_idx, priority, scratch, stream);
 }
 
 int mz_sumtree_add_chunks(double* tree, int64_t max_capacity, int64_t n, const int64_t* tree_idx,
@@ -217,18 +271,33 @@ int mz_sumtree_add(double* tree, int64_t max_capacity, int64_t n, const int64_t*
                              slot_start, slot_len, scratch, stream);
 }
 
+int mz_sumtree_sample_mt(const double* tree, int64_t max_capacity, int32_t n, const double* u01, int32_t u01_is_mt_words,
+                         const int64_t* slot_pos, const int64_t* slot_start, const int32_t* slot_len,
+                         int64_t num_memories, double beta, int64_t* tree_idx, double* priority,
+                         int64_t* pos, int64_t* chunk_start, int32_t* chunk_len, double* is_weights,
+                         void* stream);
+
 int mz_sumtree_sample(const double* tree, int64_t max_capacity, int32_t n, const double* u01,
                       const int64_t* slot_pos, const int64_t* slot_start, const int32_t* slot_len,
                       int64_t num_memories, double beta, int64_t* tree_idx, double* priority,
                       int64_t* pos, int64_t* chunk_start, int32_t* chunk_len, double* is_weights,
                       void* stream) {
+  return mz_sumtree_sample_mt(tree, max_capacity, n, u01, 0, slot_pos, slot_start, slot_len, num_memories, beta, tree_idx,
+                              priority, pos, chunk_start, chunk_len, is_weights, stream);
+}
+
+int mz_sumtree_sample_mt(const double* tree, int64_t max_capacity, int32_t n, const double* u01, int32_t u01_is_mt_words,
+                         const int64_t* slot_pos, const int64_t* slot_start, const int32_t* slot_len,
+                         int64_t num_memories, double beta, int64_t* tree_idx, double* priority,
+                         int64_t* pos, int64_t* chunk_start, int32_t* chunk_len, double* is_weights,
+                         void* stream) {
   if (!tree || max_capacity < 1 || n < 1 || !u01 || !tree_idx || !priority) return MZ_ERR_BAD_ARG;
   if (slot_pos && (!slot_start || !slot_len || !pos || !chunk_start || !chunk_len))
     return MZ_ERR_BAD_ARG;
   const int threads = n >= 1024 ? 1024 : ((n + 31) / 32) * 32;
   sumtree_sample_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(
       tree, 2 * max_capacity - 1, max_capacity - 1, n, u01, slot_pos, slot_start, slot_len,
-      (double)num_memories, beta, tree_idx, priority, pos, chunk_start, chunk_len, is_weights);
+      (double)num_memories, beta, u01_is_mt_words, tree_idx, priority, pos, chunk_start, chunk_len, is_weights);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }

@@ -837,6 +837,18 @@ __global__ void window_copy_kernel(mz_window w, int count, const int64_t* __rest
   }
 }
 
+// padding actions of sample_batch (np.random.randint(action_space), replay_buffer.py:151) drawn on the device:
+// splitmix64 of (seed, index), reduced to [0, A) by multiply-shift
+__global__ void pad_actions_kernel(int n, int A, unsigned long long seed, int32_t* __restrict__ pads) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  pads[i] = (int32_t)(((z >> 32) * (unsigned long long)A) >> 32);
+}
+
 int grid_for(long long n, int threads) {
   long long g = (n + threads - 1) / threads;
   const long long cap = 148LL * 16;
@@ -845,6 +857,11 @@ int grid_for(long long n, int threads) {
 
 }  // namespace
 
+extern "C" int mz_sumtree_sample_mt(const double* tree, int64_t max_capacity, int32_t n, const double* u01,
+                                    int32_t u01_is_mt_words, const int64_t* slot_pos, const int64_t* slot_start,
+                                    const int32_t* slot_len, int64_t num_memories, double beta, int64_t* tree_idx,
+                                    double* priority, int64_t* pos, int64_t* chunk_start, int32_t* chunk_len,
+                                    double* is_weights, void* stream);
 int g_tma_rows = 8, g_tma_threads = 128;
 // 0: by shape, 1: always the warp-per-row kernel, 2: lane-per-position kernel where the shape allows it (never the
 // TMA-staged one), 3: TMA-staged kernel where the shape allows it (tests run all on the same inputs)
@@ -1009,6 +1026,28 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
       t_policies, value_support, reward_support, warp_smem);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
+}
+
+int mz_replay_sample_targets(const double* tree, int64_t max_capacity, const double* u01, int32_t u01_is_mt_words,
+                             const int64_t* slot_pos, const int64_t* slot_start, const int32_t* slot_len,
+                             int64_t num_memories, double beta, int64_t* tree_idx, double* priority, int64_t* pos,
+                             int64_t* chunk_start, int32_t* chunk_len, double* is_weights, const mz_window* w,
+                             const mz_target_cfg* c, int32_t* pad_actions, uint64_t pad_seed, float* obs_out,
+                             int32_t* actions_out, float* t_rewards, float* t_values, float* t_policies,
+                             float* value_support, float* reward_support, void* stream) {
+  if (!c || !w || !slot_pos) return MZ_ERR_BAD_ARG;
+  const int rc = mz_sumtree_sample_mt(tree, max_capacity, c->batch, u01, u01_is_mt_words, slot_pos, slot_start, slot_len,
+                                      num_memories, beta, tree_idx, priority, pos, chunk_start, chunk_len, is_weights,
+                                      stream);
+  if (rc != MZ_OK) return rc;
+  if (pad_seed && c->num_unroll_steps > 0) {
+    if (!pad_actions) return MZ_ERR_BAD_ARG;
+    const int n = c->batch * c->num_unroll_steps;
+    pad_actions_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, w->num_actions, pad_seed, pad_actions);
+    MZ_LAUNCH_CHECK();
+  }
+  return mz_build_targets(w, c, pos, chunk_start, chunk_len, pad_actions, obs_out, actions_out, t_rewards, t_values,
+                          t_policies, value_support, reward_support, stream);
 }
 
 }  // extern "C"

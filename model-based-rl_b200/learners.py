@@ -417,7 +417,10 @@ class Learner(object):
 
   def _feed_back(self, idxs, new_errors):
     if self.replay_buffer is not None:  # learners.py:182-184
-      self.replay_buffer.update(idxs, new_errors.cpu().numpy())
+      if torch.is_tensor(idxs) and idxs.is_cuda:  # a device-resident batch: nothing crosses to the host
+        self.replay_buffer.update(idxs, new_errors)
+      else:
+        self.replay_buffer.update(idxs, new_errors.cpu().numpy())
 
   def _capture(self, inputs):
     """Captures the step for this batch shape.  Gradients are released first so that the captured

@@ -408,24 +408,108 @@ class PrioritizedReplay(object):
     return batch, h_idx.tolist(), is_weights
 
   @_lib.on_device
-  def sample_batch_device(self, fuse_supports=True):
+  def sample_batch_device(self, fuse_supports=True, ring=0):
     """Same sampling with nothing leaving the GPU and no host synchronisation: returns
     ((obs, actions [B,K] i32, t_rewards, t_values, t_policies[, value_support, reward_support]),
     idxs (int64 CUDA tensor, accepted by `update`), is_weights (float64 CUDA tensor)).  The padding
     actions are drawn for every row up front (one `np.random.randint(A, size=(B, K))`), which
-    consumes the numpy stream differently from the reference; the sampled rows are the same."""
+    consumes the numpy stream differently from the reference; the sampled rows are the same.
+
+    ring = R > 0: the outputs live in R preallocated sets used in turn (a batch stays valid until R - 1 further
+    calls); the B draws of `random.random()` cross as the raw generator words they are made of (one
+    `random.getrandbits`, same stream position afterwards, same float64 values formed on the device), the padding
+    actions are drawn on the device from one np.random seed per batch, and sampling + target construction are ONE
+    call into the library (`mz_replay_sample_targets`) with prebuilt arguments."""
     B, K, A = self.batch_size, self.num_unroll_steps, self.action_space
     self._step_beta()
+    if ring:
+      return self._sample_ring(fuse_supports, int(ring))
     u01 = [random.random() for _ in range(B)]
     idx, pri, pos, cstart, clen, isw = self.index.sample(u01, self.beta, with_weights=True)
     pads = torch.from_numpy(np.random.randint(A, size=(B, K)).astype(np.int32)).to(self.device)
     out = self._targets(pos, cstart, clen, pads, fuse_supports)
     return tuple(out), idx, isw
 
+  def _sample_ring(self, fuse_supports, R):
+    B, K, A = self.batch_size, self.num_unroll_steps, self.action_space
+    key = (self.w_obs.data_ptr(), fuse_supports, R)
+    st = getattr(self, '_ring', None)
+    if st is None or st['key'] != key:
+      st = self._ring = {'key': key, 'i': 0, 'sets': [self._ring_set(fuse_supports) for _ in range(R)]}
+    e = st['sets'][st['i']]
+    st['i'] = (st['i'] + 1) % R
+    e['event'].synchronize()  # the copy that last read this set's pinned blob is done (it long is)
+    # B draws of random.random() (random.uniform(s1, s2) consumes exactly one each) as the 2 * B raw generator
+    # outputs they are made of; the sampling kernel forms the float64 values (mz_replay_sample_targets)
+    C.memmove(e['h_ptr'], random.getrandbits(64 * B).to_bytes(8 * B, 'little'), 8 * B)
+    e['d_in'].copy_(e['h_in'], non_blocking=True)
+    e['event'].record()
+    args = e['args']
+    args[7], args[8], args[26] = self.index.ring.num_memories, float(self.beta), torch.cuda.current_stream().cuda_stream
+    args[18] = int(np.random.randint(1, 1 << 62))  # seed of the device-drawn padding actions
+    rc = self.lib.mz_replay_sample_targets(*args)
+    if rc:
+      _lib.check(rc, "mz_replay_sample_targets")
+    return e['ret']
+
+  def _ring_set(self, fuse_supports):
+    """One preallocated set of sampling + target outputs, its pinned input blob and the argument list of
+    mz_replay_sample_targets."""
+    B, K, A = self.batch_size, self.num_unroll_steps, self.action_space
+    dev, idx = self.device, self.index
+    h_in = torch.zeros(8 * B, dtype=torch.uint8).pin_memory()
+    d_in = torch.zeros_like(h_in, device=dev)
+    d_u = d_in.view(torch.float64)
+    d_pads = torch.zeros(B * max(K, 1), dtype=torch.int32, device=dev)
+    blob = torch.zeros(6 * B, dtype=torch.int64, device=dev)
+    t_idx, pos, cstart = blob[0:B], blob[B:2 * B], blob[2 * B:3 * B]
+    pri, isw = blob[3 * B:4 * B].view(torch.float64), blob[4 * B:5 * B].view(torch.float64)
+    clen = blob[5 * B:6 * B].view(torch.int32)[:B]
+    vb = self.value_support[1] - self.value_support[0] + 1
+    rb = self.reward_support[1] - self.reward_support[0] + 1
+    shapes = [(B, self.obs_elems), (B, K), (B, K + 1), (B, K + 1), (B, K + 1, A)]
+    if fuse_supports:
+      shapes += [(B, K + 1, vb), (B, K + 1, rb)]
+    sizes = [(int(np.prod(sh)) + 3) // 4 * 4 for sh in shapes]
+    tb = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+    out, off = [], 0
+    for i, (sh, n) in enumerate(zip(shapes, sizes)):
+      v = tb[off:off + int(np.prod(sh))]
+      out.append((v.view(torch.int32) if i == 1 else v).view(sh))
+      off += n
+    win = self._window_struct()
+    cfg = _lib.TargetCfg(B, K, self.td_steps, int(fuse_supports), self.value_support[0], self.value_support[1],
+                         self.reward_support[0], self.reward_support[1], int(self.no_target_transform), 0,
+                         float(self.discount**self.td_steps), self.d_discounts.data_ptr(), None, None)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    outs = [P(t) for t in out] + ([None, None] if not fuse_supports else [])
+    args = [P(idx.tree), idx.max_capacity, P(d_u), 1, P(idx.slot_pos), P(idx.slot_start), P(idx.slot_len), 0, 0.0,
+            P(t_idx), P(pri), P(pos), P(cstart), P(clen), P(isw), win, cfg, P(d_pads), 1] + outs + [None]
+    return {'h_in': h_in, 'd_in': d_in, 'h_ptr': h_in.data_ptr(), 'event': torch.cuda.Event(), 'args': args,
+            'ret': (tuple(out), t_idx, isw), 'keep': (blob, tb, win, cfg, d_pads)}
+
   @_lib.on_device
   def update(self, idxs, errors):
     """replay_buffer.py:200-203.  `idxs` may be the list `sample_batch` returned or the CUDA tensor
-    of `sample_batch_device`; `errors` a numpy array (learners.py:183) or a CUDA tensor."""
+    of `sample_batch_device`; `errors` a numpy array (learners.py:183) or a CUDA tensor.  With both on the device,
+    float32 errors and alpha == 1 (the reference's default) nothing comes back to the host: the priorities are
+    computed by the library (`mz_sumtree_update_errors`, bit-exact for alpha == 1)."""
+    if (torch.is_tensor(errors) and torch.is_tensor(idxs) and errors.is_cuda and idxs.is_cuda and
+        errors.dtype == torch.float32 and idxs.dtype == torch.int64 and float(self.alpha) == 1.0):
+      n = int(idxs.shape[0])
+      if n == 0:
+        return
+      errors, idxs = errors.detach().contiguous(), idxs.contiguous()
+      ws = getattr(self, '_upd_ws', None)
+      if ws is None or ws.shape[1] < n:
+        ws = self._upd_ws = torch.empty((2, n), dtype=torch.float64, device=self.device)
+      rc = self.lib.mz_sumtree_update_errors(C.c_void_p(self.index.tree.data_ptr()), self.index.max_capacity, n,
+                                             C.c_void_p(idxs.data_ptr()), C.c_void_p(errors.data_ptr()),
+                                             float(self.epsilon), 1.0, C.c_void_p(ws[0].data_ptr()),
+                                             C.c_void_p(ws[1].data_ptr()), torch.cuda.current_stream().cuda_stream)
+      if rc:
+        _lib.check(rc, "mz_sumtree_update_errors")
+      return
     if torch.is_tensor(errors):
       errors = errors.detach().cpu().numpy()
     if torch.is_tensor(idxs):

@@ -100,10 +100,13 @@ def test_facade_matches_reference(case, monkeypatch):
     assert np.array_equal(rb.index.tree.cpu().numpy(), g["b%d_tree_after_update" % b])  # bit-exact sums
 
 
+@pytest.mark.parametrize("ring", [0, 3], ids=["fresh_outputs", "ring_of_3"])
 @pytest.mark.parametrize("case", REPLAY_CASES)
-def test_device_sampling_matches_reference(case, monkeypatch):
+def test_device_sampling_matches_reference(case, ring, monkeypatch):
   """sample_batch_device: same rows, importance weights from the device pow (<= 1e-14 relative),
-  supports fused; idxs/errors may stay CUDA tensors for update()."""
+  supports fused; idxs/errors may stay CUDA tensors for update() (float32 errors and alpha == 1: priorities
+  computed on the device, tree bit-exact against the reference's).  ring = 3: preallocated output sets, pinned
+  staging, one library call per batch (mz_replay_sample_targets)."""
   from model_based_rl_b200 import replay_buffer as rbmod
   from model_based_rl_b200.config import Config
   g = load("replay_" + case)
@@ -114,8 +117,21 @@ def test_device_sampling_matches_reference(case, monkeypatch):
     frac = list(g["b%d_frac" % b])
     pads = g["b%d_pads" % b]
     monkeypatch.setattr(rbmod.random, "random", lambda frac=frac: frac.pop(0))
-    monkeypatch.setattr(np.random, "randint", lambda A, size=None, pads=pads: pads)
-    out, idxs, is_w = rb.sample_batch_device(fuse_supports=True)
+    if ring:
+      # the ring path takes the B draws as raw MT19937 words (random.getrandbits) and forms the float64 values on
+      # the device: feed it the words the golden fractions are made of, random() = ((a >> 5) * 2**26 + (b >> 6)) / 2**53
+      def words(k, frac=list(frac)):
+        assert k == 64 * B
+        x = 0
+        for i, f in enumerate(frac):
+          n = int(f * 2**53)
+          assert n / 2**53 == f
+          x |= (((n >> 26) << 5) | ((n & (2**26 - 1)) << 6 << 32)) << (64 * i)
+        return x
+      monkeypatch.setattr(rbmod.random, "getrandbits", words)
+    else:
+      monkeypatch.setattr(np.random, "randint", lambda A, size=None, pads=pads, **kw: pads)
+    out, idxs, is_w = rb.sample_batch_device(fuse_supports=True, ring=ring)
     monkeypatch.undo()
     assert idxs.is_cuda and idxs.cpu().tolist() == g["b%d_idxs" % b].tolist()
     want_w = g["b%d_is_weights" % b]
@@ -123,13 +139,50 @@ def test_device_sampling_matches_reference(case, monkeypatch):
     assert np.max(np.abs(is_w.cpu().numpy() - want_w) / want_w) <= 1e-14
     obs, actions, t_r, t_v, t_p, vs, rs = out
     assert np.array_equal(obs.cpu().numpy(), g["b%d_obs" % b])
-    assert np.array_equal(actions.cpu().numpy(), g["b%d_actions" % b])
+    if ring:  # padding actions drawn on the device: the real prefix of every action slice is the reference's
+      lens = [len(g["h%d_root_values" % h]) for h in range(int(g["n_hist"]))]
+      n_real = np.clip(np.array([lens[h] for h in g["b%d_hist" % b]]) - g["b%d_steps" % b], 0, K)
+      got, want_a = actions.cpu().numpy(), g["b%d_actions" % b]
+      real = np.arange(K)[None, :] < n_real[:, None]
+      assert np.array_equal(got[real], want_a[real])
+      assert ((got >= 0) & (got < int(g["action_space"]))).all()
+    else:
+      assert np.array_equal(actions.cpu().numpy(), g["b%d_actions" % b])
     assert np.array_equal(t_r.cpu().numpy(), g["b%d_t_rewards" % b])
     assert torch.equal(vs, cfg.value_phi(Config.scalar_transform(t_v)))
     assert torch.equal(rs, cfg.reward_phi(Config.scalar_transform(t_r)))
     rb.update(idxs, torch.from_numpy(g["b%d_update_errors" % b]).cuda())
     torch.cuda.synchronize()
     assert np.array_equal(rb.index.tree.cpu().numpy(), g["b%d_tree_after_update" % b])
+
+
+def test_device_priority_update_equals_host_update():
+  """update() with CUDA idxs + float32 CUDA errors (mz_sumtree_update_errors) against update() with the same values
+  as numpy arrays (numpy's (|e| + eps) ** alpha on the host): identical float64 trees, repeated indices included."""
+  from model_based_rl_b200.replay_buffer import PrioritizedReplay
+  rng = np.random.default_rng(3)
+  cfg = types.SimpleNamespace(batch_size=64, beta_increment_per_sampling=0.001, epsilon=0.01, alpha=1.0, beta=0.5,
+                              num_unroll_steps=3, td_steps=5, discount=0.997, action_space=4, obs_space=(8,),
+                              window_size=3000, window_step=None, seed=None)
+  a, b = PrioritizedReplay(cfg), PrioritizedReplay(cfg)
+  for rb in (a, b):
+    r2 = np.random.default_rng(5)
+    for _ in range(12):
+      n = int(r2.integers(50, 400))
+      h = HistorySlice(list(r2.normal(size=(n, 8)).astype(np.float32)), r2.random((n, 4)).tolist(), r2.normal(size=n).tolist(),
+                       r2.integers(0, 4, size=n).tolist(), r2.normal(size=n).tolist(), np.abs(r2.normal(size=n)).tolist(),
+                       [False] * n, list(range(n)), [None] * n, [1] * n)
+      rb.save_history(h, ignore=None, terminal=True)
+  leaf0 = a.index.max_capacity - 1
+  for _ in range(10):
+    idx = leaf0 + rng.integers(0, a.size(), size=512)
+    idx[100:110] = idx[0]  # the same memory sampled several times in one batch: the last update wins
+    err = rng.normal(size=512).astype(np.float32)
+    a.update(idx.tolist(), err)
+    b.update(torch.from_numpy(idx).cuda(), torch.from_numpy(err).cuda())
+  torch.cuda.synchronize()
+  assert np.array_equal(a.index.tree.cpu().numpy(), b.index.tree.cpu().numpy())
+  assert a.index.total_priority == b.index.total_priority > 0
 
 
 @pytest.mark.parametrize("capacity,step", [(1000, 250), (4096, 4096), (200_000, 200_000)])
@@ -281,3 +334,29 @@ def test_add_chunks_equals_one_add_per_chunk(capacity, step):
   assert np.array_equal(a.slot_chunk, b.slot_chunk)
   for name in ("tree", "slot_pos", "slot_start", "slot_len"):
     assert np.array_equal(getattr(a, name).cpu().numpy(), getattr(b, name).cpu().numpy()), name
+
+
+def test_ring_sampling_consumes_random_like_the_reference_loop():
+  """The ring path's one random.getrandbits(64 * B) leaves the `random` module in the state B calls of
+  random.random() leave it in, and draws the same rows: a run that mixes both paths stays on the reference's stream."""
+  from model_based_rl_b200.replay_buffer import PrioritizedReplay
+  cfg = types.SimpleNamespace(batch_size=96, beta_increment_per_sampling=0.001, epsilon=0.01, alpha=1.0, beta=0.5,
+                              num_unroll_steps=3, td_steps=5, discount=0.997, action_space=4, obs_space=(8,),
+                              window_size=2000, window_step=None, seed=None)
+  rb = PrioritizedReplay(cfg)
+  r2 = np.random.default_rng(5)
+  for _ in range(8):
+    n = int(r2.integers(50, 300))
+    rb.save_history(HistorySlice(list(r2.normal(size=(n, 8)).astype(np.float32)), r2.random((n, 4)).tolist(),
+                                 r2.normal(size=n).tolist(), r2.integers(0, 4, size=n).tolist(), r2.normal(size=n).tolist(),
+                                 np.abs(r2.normal(size=n)).tolist(), [False] * n, list(range(n)), [None] * n, [1] * n),
+                    ignore=None, terminal=True)
+  random.seed(123)
+  _, idx_a, w_a = rb.sample_batch_device(True)
+  state_a = random.getstate()
+  idx_a, w_a = idx_a.cpu().numpy().copy(), w_a.cpu().numpy().copy()
+  rb.beta = 0.5
+  random.seed(123)
+  _, idx_b, w_b = rb.sample_batch_device(True, ring=2)
+  assert random.getstate() == state_a
+  assert np.array_equal(idx_a, idx_b.cpu().numpy()) and np.array_equal(w_a, w_b.cpu().numpy())
