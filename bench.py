@@ -63,6 +63,7 @@ def parse():
                       "simulation; auto: FCSearch's default (MZ_FUSED in the environment)")
   p.add_argument("--no-f32", action="store_true", help="skip the float32-network throughput line")
   p.add_argument("--no-selfplay", action="store_true", help="skip the self-play driver section")
+  p.add_argument("--no-concurrent", action="store_true", help="skip the search + concurrent learner section")
   p.add_argument("--ref-moves-per-step", type=int, default=2,
                  help="reference arm: moves each worker plays per step")
   return p.parse_args()
@@ -469,6 +470,8 @@ def run_b200(args):
   selfplay = (bench_selfplay(args, torch, dev, cpu_baseline["value"] if cpu_baseline else None)
               if rank == 0 and world == 1 and not args.no_selfplay else None)
   learner = bench_learner(torch, _lib, dev, world, barrier)  # every rank: the step all-reduces at N > 1
+  concurrent = (bench_concurrent(args, torch, dev, world, fs, net, barrier, flush)
+                if not args.no_concurrent else None)  # every rank: gradient all-reduce + weight broadcast
   conv = bench_conv(args, torch, _lib, dev) if rank == 0 and not args.no_conv else None
 
   if rank == 0:
@@ -531,6 +534,7 @@ def run_b200(args):
         "fused_search_kernel": fs.fused is not None, "l2": L2_POLICY,
         "cuda_graph": not args.no_graph, "streams": n_slices, "f32_network": f32_line,
         "games_sweep": sweep, "other_configs": others, "targets": targets, "replay": replay, "selfplay": selfplay, "learner": learner,
+        "concurrent_learner": concurrent,
         "conv": conv,
     }
     if cpu_baseline is not None:
@@ -925,6 +929,111 @@ def bench_selfplay(args, torch, dev, cpu_expansions_per_s=None):
                                      "search: moves/s = expansions/s / num_simulations)"}
     out["device"]["game_moves_per_s"] = G / (out["device"]["ms_per_move"] * 1e-3)
   return out
+
+
+def bench_concurrent(args, torch, dev, world, fs, net, barrier, flush):
+  """BASELINE config C4 "with learner allreduce" as it runs in training: while the search plays its moves on the
+  main stream, a real learner (`Learner.update_weights` on batches from `PrioritizedReplay.sample_batch_device`,
+  priorities fed back on the device) trains on a side stream of the same GPU -- at N > 1 with the NCCL gradient
+  all-reduce of the data-parallel step every step -- and hands its weights to the search network every
+  `send_weights_frequency` steps (learners.py:115-148, actors.py:81-85; rank 0's weights are broadcast).  One
+  learner step is enqueued per move.  Reported: both rates alone and together, max over ranks."""
+  import types
+  import torch.distributed as dist
+  from model_based_rl_b200 import learners
+  from model_based_rl_b200.replay_buffer import PrioritizedReplay
+  from model_based_rl_b200.selfplay import HistorySlice
+  G, S, A, D = args.games, args.sims, args.actions, args.obs_dim
+  B, K, T, L, W = 512, 5, 10, 500, 30_000
+  cfg = types.SimpleNamespace(value_support=[-15, 15], reward_support=[-15, 15], no_support=False, no_target_transform=False,
+                              num_unroll_steps=K, td_steps=T, optimizer="AdamW", lr_init=0.0008, momentum=0.9,
+                              weight_decay=1e-4, clip_grad=0, lr_scheduler=None, norm_obs=False, batch_size=B,
+                              beta_increment_per_sampling=0.001, epsilon=0.01, alpha=1.0, beta=0.4, discount=0.997,
+                              action_space=A, obs_space=(D,), window_size=W, window_step=None, max_history_length=L,
+                              seed=None, clip_rewards=True)
+  rng = np.random.default_rng(21)
+  rb = PrioritizedReplay(cfg, device=dev)
+  for _ in range(W // L):
+    cv = rng.random((L, A))
+    rb.save_history(HistorySlice(list(rng.integers(0, 256, size=(L + 1, D), dtype=np.uint8)),
+                                 (cv / cv.sum(1, keepdims=True)).tolist(), rng.normal(0, 2, size=L).tolist(),
+                                 rng.integers(0, A, size=L).tolist(),
+                                 np.sign(rng.normal(size=L) * (rng.random(L) < 0.1)).astype(np.int64).tolist(),
+                                 np.abs(rng.normal(size=L)).tolist(), [False] * L, list(range(L)), [None] * L, [1] * L),
+                    ignore=None, terminal=True)
+  torch.manual_seed(3)
+  learner = learners.Learner(cfg, learners.FCNetworkTrain(D, A, dev, cfg), replay_buffer=rb, search_network=net,
+                             use_graph=True)
+  main, side = torch.cuda.current_stream(), torch.cuda.Stream(device=dev)
+  send_every = 25
+
+  def learner_step():
+    (obs, act, t_r, t_v, t_p), idx, isw = rb.sample_batch_device(False, ring=4)
+    learner.update_weights(((obs, act, (t_r, t_v, t_p)), idx, isw))
+
+  def hand_off():  # between two moves: the search never sees half-written weights
+    main.wait_stream(side)
+    learner.send_weights()
+    side.wait_stream(main)
+
+  with torch.cuda.stream(side):
+    for _ in range(6):
+      learner_step()
+  torch.cuda.synchronize()
+  hand_off()
+  for _ in range(3):
+    fs.run()
+  barrier()
+  n = max(20, min(args.steps, 100))
+  ev = lambda: torch.cuda.Event(enable_timing=True)
+
+  def run(with_search, with_learner):
+    pairs, a, b = [], ev(), ev()
+    a.record(side)
+    for i in range(n):
+      flush.zero_()
+      if with_learner:
+        with torch.cuda.stream(side):
+          learner_step()
+        if (i + 1) % send_every == 0:
+          hand_off()
+      if with_search:
+        s, e = ev(), ev()
+        s.record()
+        fs.run()
+        e.record()
+        pairs.append((s, e))
+    b.record(side)
+    torch.cuda.synchronize()
+    t = torch.tensor([sum(s.elapsed_time(e) for s, e in pairs), a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    barrier()
+    return t.tolist()
+
+  ms_search_alone, _ = run(True, False)
+  _, ms_learner_alone = run(False, True)
+  ms_search, ms_learner = run(True, True)
+  n_params = sum(p.numel() for p in learner.network.parameters())
+  rate = lambda ms: world * G * S * n / (ms * 1e-3)
+  return {
+      "workload": "C4 search (%d games x %d sims, A=%d per GPU) + C3-shaped learner (B=%d, K=%d, td=%d, AdamW, FCNetwork) "
+                  "on a side stream of the same GPU, one learner step enqueued per move, %d moves" % (G, S, A, B, K, T, n),
+      "ranks": world,
+      "collectives": ("gradient all-reduce of %d float32 per learner step + weight broadcast every %d steps (NCCL)"
+                      % (n_params, send_every)) if world > 1 else "none at one rank (weights handed to the search network "
+                                                                   "on the device every %d steps)" % send_every,
+      "search_alone_expansions_per_s": rate(ms_search_alone),
+      "learner_alone_steps_per_s": world * n / (ms_learner_alone * 1e-3),
+      "search_expansions_per_s": rate(ms_search),
+      "learner_steps_per_s": world * n / (ms_learner * 1e-3),
+      "search_kept": ms_search_alone / ms_search,
+      "learner_kept": ms_learner_alone / ms_learner,
+      "weight_handoffs": n // send_every,
+      "note": "search time = sum of per-move CUDA-event pairs (L2 flushed between moves, like the headline); learner "
+              "time = first enqueue to last completion on the side stream (it includes the waits at the hand-offs); "
+              "learner steps/s is the aggregate over ranks of data-parallel steps x ranks",
+  }
 
 
 def bench_learner(torch, _lib, dev, world, barrier):
