@@ -652,45 +652,65 @@ def kernel_breakdown(fs, torch):
 
 
 def bench_conv(args, torch, _lib, dev):
-  """C5 (BASELINE.json configs[4]): MuZeroNetwork residual conv tower, synthetic 96x96x32 frames,
-  A=18, 50 simulations, bf16 tensor-core recurrent_inference.  Reports whole-move expansions/s
-  through ConvSearch (representation included) and the tensor roofline of the conv kernel."""
+  """C5 (BASELINE.json configs[4]): MuZeroNetwork residual conv tower, synthetic 96x96 frames with 32 stacked
+  channels (and 64: `stack_actions`, utils.py:28-32), A=18, 50 simulations, bf16 tensor-core recurrent_inference.
+  Reports whole-move expansions/s through ConvSearch.search (initial_inference -- representation tower included --
+  and the search in one CUDA graph), the same with the two parts timed separately, and the tensor roofline of the
+  conv kernel."""
   from model_based_rl_b200.muzero import CH, ROWS, ConvSearch, MuZeroNetwork, random_state_dict
   cfg = search_config(args)
-  G, S, A, C_in = args.conv_games, args.sims, args.actions, 32
-  net = MuZeroNetwork(C_in, A, dev, cfg)
-  net.load_weights(random_state_dict(C_in, A))
-  cs = ConvSearch(cfg, net, G)
+  G, S, A = args.conv_games, args.sims, args.actions
   rng = np.random.default_rng(77)
-  obs = torch.from_numpy(rng.random((G, C_in, 96, 96), dtype=np.float32)).to(dev)
   noise, u = rng.dirichlet([0.25] * A, size=G), rng.random(G)
-  for _ in range(2):
-    cs.search(obs, noise, u)
-  torch.cuda.synchronize()
-  steps = 3
   a, b, c = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-  ms_move = ms_search = 0.0
-  for _ in range(steps):
-    a.record()
-    cs.set_roots(obs)
-    b.record()
-    cs.run()
-    c.record()
+  res = {}
+  for C_in in (32, 64):
+    net = MuZeroNetwork(C_in, A, dev, cfg)
+    net.load_weights(random_state_dict(C_in, A))
+    cs = ConvSearch(cfg, net, G)
+    obs = torch.from_numpy(rng.random((G, C_in, 96, 96), dtype=np.float32)).to(dev)
+    for _ in range(2):
+      cs.search(obs, noise, u)
     torch.cuda.synchronize()
-    ms_move += a.elapsed_time(c)
-    ms_search += b.elapsed_time(c)
-  # one convolution launch alone (the dominant kernel: 65 of the 70 launches per simulation)
-  x = torch.rand((G * ROWS, CH), device=dev).to(torch.bfloat16)
-  out = net.buffers(G)["x"][0]
-  n = 20
-  for _ in range(3):
-    net._conv(G, net.dyn_tower[0], x, 3, out, residual=x)
-  a.record()
-  for _ in range(n):
-    net._conv(G, net.dyn_tower[0], x, 3, out, residual=x)
-  b.record()
-  torch.cuda.synchronize()
-  us_conv = a.elapsed_time(b) * 1e3 / n
+    steps = 3
+    ms_graph = 0.0
+    for _ in range(steps):  # the public call: one graph per move
+      a.record()
+      cs.search(obs)
+      b.record()
+      torch.cuda.synchronize()
+      ms_graph += a.elapsed_time(b)
+    cs.set_roots(obs)
+    cs.run()
+    torch.cuda.synchronize()
+    ms_move = ms_search = 0.0
+    for _ in range(steps):  # the two halves apart: eager initial_inference, then the search graph
+      a.record()
+      cs.set_roots(obs)
+      b.record()
+      cs.run()
+      c.record()
+      torch.cuda.synchronize()
+      ms_move += a.elapsed_time(c)
+      ms_search += b.elapsed_time(c)
+    res[C_in] = {"expansions_per_s": G * S * steps / (ms_graph * 1e-3), "ms_per_move": ms_graph / steps,
+                 "expansions_per_s_search_only": G * S * steps / (ms_search * 1e-3),
+                 "ms_per_move_two_parts": ms_move / steps, "ms_representation_eager": (ms_move - ms_search) / steps,
+                 "recurrent_tflops_useful": G * S * steps * 0.705e9 / (ms_search * 1e-3) / 1e12}
+    if C_in == 32:
+      # one convolution launch alone (the dominant kernel: 65 of the 70 launches per simulation)
+      x = torch.rand((G * ROWS, CH), device=dev).to(torch.bfloat16)
+      out = net.buffers(G)["x"][0]
+      n = 20
+      for _ in range(3):
+        net._conv(G, net.dyn_tower[0], x, 3, out, residual=x)
+      a.record()
+      for _ in range(n):
+        net._conv(G, net.dyn_tower[0], x, 3, out, residual=x)
+      b.record()
+      torch.cuda.synchronize()
+      us_conv = a.elapsed_time(b) * 1e3 / n
+    del cs, net, obs
   peaks = measured_peaks()
   flops = 2.0 * G * 36 * 128 * 1152  # algorithmic: interior pixels only (the padded rows are overhead)
   roof = {"kernel": "conv_pair_tc_kernel", "bound": "tensor", "achieved": flops / us_conv / 1e6,
@@ -699,15 +719,13 @@ def bench_conv(args, torch, _lib, dev):
           "algorithmic_flops_per_launch": flops, "avg_launch_us": us_conv,
           "issued_tflops": 2.0 * G * ROWS * 128 * 1152 / us_conv / 1e6, "peak_source": peaks["source"]}
   roof["frac"] = roof["achieved"] / roof["peak"]
-  del cs
-  return {"workload": "C5 MuZeroNetwork residual conv (16+16 blocks, 128 ch, 6x6 state), %d games x %d "
-                      "sims, A=%d, synthetic 96x96x%d frames, bf16 tcgen05 initial_inference (representation "
-                      "tower included) and recurrent_inference" % (G, S, A, C_in),
-          "expansions_per_s": G * S * steps / (ms_move * 1e-3),
-          "expansions_per_s_search_only": G * S * steps / (ms_search * 1e-3),
-          "ms_per_move": ms_move / steps, "ms_representation": (ms_move - ms_search) / steps,
-          "gpu_launches_per_move": cs_launches(G, S), "recurrent_tflops_useful":
-              G * S * steps * 0.705e9 / (ms_search * 1e-3) / 1e12, "roofline": roof}
+  out = {"workload": "C5 MuZeroNetwork residual conv (16+16 blocks, 128 ch, 6x6 state), %d games x %d "
+                     "sims, A=%d, synthetic 96x96x32 frames, bf16 tcgen05 initial_inference (representation "
+                     "tower included) and recurrent_inference; one CUDA graph per move" % (G, S, A),
+         "gpu_launches_per_move": cs_launches(G, S), "roofline": roof}
+  out.update(res[32])
+  out["stack_actions_64_channels"] = res[64]
+  return out
 
 
 def cs_launches(G, S):

@@ -422,7 +422,7 @@ class ConvSearch(object):
                    torch.zeros((S, G), dtype=torch.float32, device=dev),
                    torch.zeros((S, G, A), dtype=torch.float32, device=dev))
     self.eng.enable_trace()
-    self.graph = None
+    self.graph = self.graph_move = None
 
   @property
   def trace(self):
@@ -484,19 +484,44 @@ class ConvSearch(object):
         self._enqueue()
     self.graph.replay()
 
+  def run_move(self, observation):
+    """initial_inference (representation tower + prediction) AND the search of one move as ONE CUDA graph over a
+    static observation buffer: the ~190 launches of the representation join the 3 604 of the search, no eager
+    launch is left in a move."""
+    obs = torch.as_tensor(observation)
+    if not self.use_graph:
+      self.set_roots(obs.to(self.net.device, non_blocking=True))
+      self._enqueue()
+      return
+    st = getattr(self, '_obs_static', None)
+    if st is None or st.shape != obs.shape:
+      st = self._obs_static = torch.empty(obs.shape, dtype=torch.float32, device=self.net.device)
+      self.graph_move = None
+    st.copy_(obs, non_blocking=True)
+    if getattr(self, '_graph_move_weights', None) != getattr(self.net, 'weights_version', 0):
+      self.graph_move = None  # load_weights rebuilt the packed weights: the captured addresses are stale
+      self._graph_move_weights = getattr(self.net, 'weights_version', 0)
+    if getattr(self, 'graph_move', None) is None:
+      self.set_roots(st)  # warm-up outside capture (scratch buffers, cudaFuncSetAttribute, lazy module loading)
+      self._enqueue()
+      torch.cuda.synchronize()
+      self.graph_move = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self.graph_move):
+        self.set_roots(st)
+        self._enqueue()
+    self.graph_move.replay()
+
   @_lib.on_device
   def search(self, observation, noise=None, uniforms=None, temperature=None):
     """observation [G, C, 96, 96] (device or host); returns device tensors (actions [G] i32,
     root_value [G] f64, child_visits [G, A] f64, initial value [G] f32)."""
-    dev = self.net.device
     if noise is not None:
       self.noise.copy_(torch.as_tensor(noise), non_blocking=True)
     if uniforms is not None:
       self.uniforms.copy_(torch.as_tensor(uniforms), non_blocking=True)
     if temperature is not None:
       self.temperature.copy_(torch.as_tensor(temperature), non_blocking=True)
-    self.set_roots(torch.as_tensor(observation).to(dev, non_blocking=True))
-    self.run()
+    self.run_move(observation)
     eng = self.eng
     return eng.actions, eng.root_value, eng.child_visits, self.init_value
 
