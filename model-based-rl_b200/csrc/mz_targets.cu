@@ -15,33 +15,6 @@ namespace {
 constexpr int kTgtWarps = 8;  // sampled rows per CTA
 constexpr int kTgtThreads = kTgtWarps * 32;
 
-struct TgtBins {  // two-hot bins of one scalar target
-  int lo, hi;
-  float p_lo, p_hi;
-};
-
-// One row of [n_pos][bins] two-hot supports, written by a whole warp as 8-byte stores when the row
-// base allows it (a row is (K+1) * bins floats; 256 contiguous bytes per warp instruction).
-// idx / bins through a multiply-shift (exact while idx * bins < 2^20; plain division otherwise).
-MZ_DEV void write_supports(float* __restrict__ dst, const TgtBins* __restrict__ th, int n_pos, int bins,
-                           int lane) {
-  const int total = n_pos * bins;
-  const bool fast = (long long)total * bins < (1 << 20);
-  const unsigned magic = (1u << 20) / (unsigned)bins + 1u;
-  auto elem = [&](int idx) {
-    const int i = fast ? (int)(((unsigned)idx * magic) >> 20) : idx / bins;
-    const int j = idx - i * bins;
-    const TgtBins t = th[i];
-    return j == t.lo ? t.p_lo : (j == t.hi ? t.p_hi : 0.0f);  // low bin wins (config.py:64-67)
-  };
-  if (((total & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
-    float2* d2 = reinterpret_cast<float2*>(dst);
-    for (int e = lane; e < (total >> 1); e += 32) d2[e] = make_float2(elem(2 * e), elem(2 * e + 1));
-  } else {
-    for (int e = lane; e < total; e += 32) dst[e] = elem(e);
-  }
-}
-
 // ClipRewardEnv.reward (wrappers.py:236-238): np.sign at the point the replay reads a stored reward
 // (mz_window.clip_rewards); zeros of either sign give +0.0 like numpy, NaN stays NaN
 MZ_DEV float tgt_reward(float r, int clip) {
@@ -50,43 +23,34 @@ MZ_DEV float tgt_reward(float r, int clip) {
 }
 
 constexpr int kTgtFastK = 7;  // up to 8 unroll positions keep their sums in registers
+constexpr int kDiscPad = 8;   // zeros in front of the widened discount table: reads at small negative indices are safe
 
-// n-step sums of NP unroll positions in one pass over the staged window: acc[i] = sum_j (+-)rewards[step+i+j]
-// * discounts[j], j < min(T, len - (step+i)); the sign flips where to_play differs from the position's
-// (replay_buffer.py:187-189).  Exact float32 products accumulated in binary64; returns position `lane`'s sum.
+// The interior of a row's window -- the elements m with 0 <= m - i < n_i for EVERY position i <= K, all of one
+// player: no range or sign test there -- is summed on the FP64 tensor cores (see the kernel); this function adds the
+// edges [0, lo) and [hi, win) with per-element tests: acc[i] = sum_j (+-)rewards[step+i+j] * discounts[j],
+// j < min(T, len - (step+i)); the sign flips where to_play differs from the position's (replay_buffer.py:187-189).
+// Exact float32 products accumulated in binary64; returns position `lane`'s edge sum.
 template <int NP>
-MZ_DEV double nstep_sums(const float* s_rew, const int8_t* s_tp, const double* s_disc, int K, int T, int step,
-                         int len, int win, int lane, bool one_player) {
+MZ_DEV double nstep_edges(const float* rw, const int8_t* tp, const double* s_disc, int K, int T, int step, int len,
+                          int win, int lo, int hi, int lane, int clip) {
   double acc[NP];
   int tp_i[NP], n_i[NP];
-  // interior of the window: elements m with 0 <= m - i < n_i for EVERY position i <= K -- no range test there
-  int lo = K, hi = win;
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
     acc[i] = 0.0;
     const bool in = i <= K && step + i < len;
     n_i[i] = in ? min(T, len - step - i) : 0;
-    tp_i[i] = in ? s_tp[i] : 0;
-    if (i <= K) hi = min(hi, i + n_i[i]);
+    tp_i[i] = in ? tp[i] : 0;
   }
-  // the sign of a reward flips where to_play differs from the position's (replay_buffer.py:187-189); when the
-  // whole window belongs to one player (every single-player game) the interior needs no sign test either
-  if (!one_player || hi <= lo) lo = hi = 0;  // everything through the general loop below
-  for (int m = lo + lane; m < hi; m += 32) {
-    const double r = (double)s_rew[m];
-#pragma unroll
-    for (int i = 0; i < NP; ++i)
-      if (i <= K) acc[i] = fma(r, s_disc[m - i], acc[i]);  // the product of two float32 values is exact
-  }
-  for (int part = 0; part < 2; ++part) {  // the edges [0, lo) and [hi, win): range and sign tests per element
+  for (int part = 0; part < 2; ++part) {
     const int m_end = part ? win : min(lo, win);
     for (int m = (part ? hi : 0) + lane; m < m_end; m += 32) {
-      const float r = s_rew[m];
-      const int tp = s_tp[m];
+      const float r = tgt_reward(rw[m], clip);
+      const int t = tp[m];
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
         const int j = m - i;
-        if (j >= 0 && j < n_i[i]) acc[i] += (double)(tp != tp_i[i] ? -r : r) * s_disc[j];
+        if (j >= 0 && j < n_i[i]) acc[i] += (double)(t != tp_i[i] ? -r : r) * s_disc[j];
       }
     }
   }
@@ -102,11 +66,27 @@ MZ_DEV double nstep_sums(const float* s_rew, const int8_t* s_tp, const double* s
   return mine_acc;
 }
 
-// One warp per sampled row, kTgtWarps rows per CTA.  Every global load of a row (observation, reward /
-// to_play window, bootstrap root values, child-visit rows) is issued before the first dependent use, so a
-// row costs two DRAM round trips (index arrays, then everything else); all stores are warp-contiguous.
-// The n-step sums of all K+1 positions come out of ONE pass over the staged window (a window element
-// contributes to every position it is in range of); lane i then finishes position i.
+// D (8 x 8, f64) += A (8 x 4, row major) * B (4 x 8, column major) on the FP64 tensor cores (DMMA.8x8x4).  Lane l holds
+// A[l >> 2][l & 3], B[l & 3][l >> 2] and D[l >> 2][2 * (l & 3) + {0, 1}].
+MZ_DEV void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// One warp per sampled row, kTgtWarps rows per CTA.  The row's reward and to_play windows (td_steps = 1000: 4 KB +
+// 1 KB) are staged by the bulk-copy engine: one cp.async.bulk each over the 16-byte-aligned part of the window
+// (start rounded down -- still inside the array --, end rounded down, the ragged tail of <= 3 rewards / <= 15 bytes
+// with ordinary loads), completion on the warp's own mbarrier; the other global loads of the row (observation,
+// bootstrap root values, child-visit rows) are issued before the wait, so a row costs two DRAM round trips
+// (index arrays, then everything else); all stores are warp-contiguous.
+// The n-step sums are a short convolution: value_i = sum_m rewards[m] * discounts[m - i] over the window.  For up
+// to 8 unroll positions the CTA's eight rows go through the FP64 tensor cores together: D[i][row] += A[i][k] *
+// B[k][row] with A[i][k] = discounts[m0 + k - i] (the same for every row: window-relative indices) and B[k][row] =
+// the row's reward at element m0 + k (zero outside the row's interior), four window elements per DMMA.8x8x4, the
+// steps dealt round-robin to the eight warps and the partial tiles added in shared memory.  One shared-memory load
+// per lane and tensor-core step instead of seven per element and lane (the kernel was shared-memory-bandwidth bound:
+// 13 wavefronts per 32 elements); the edges of the window (range / sign tests) stay with the row's own warp.
 __global__ void __launch_bounds__(kTgtThreads)
 build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ pos_arr,
                      const int64_t* __restrict__ chunk_start, const int32_t* __restrict__ chunk_len,
@@ -114,45 +94,55 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
                      int32_t* __restrict__ actions_out, float* __restrict__ t_rewards,
                      float* __restrict__ t_values, float* __restrict__ t_policies,
                      float* __restrict__ value_support, float* __restrict__ reward_support,
-                     int warp_smem_bytes) {
+                     int warp_smem_bytes, int bulk_ok) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kTgtWarps + warp;
+  // a warp without a row of its own (last CTA) repeats the batch's last row: same values to the same addresses, and
+  // every warp stays for the CTA-wide tensor-core pass
+  const int b = min(blockIdx.x * kTgtWarps + warp, c.batch - 1);
   const int K = c.num_unroll_steps, T = c.td_steps, A = w.num_actions, E = w.obs_elems;
+  __shared__ int s_lo[kTgtWarps], s_hi[kTgtWarps], s_rwoff[kTgtWarps];
+  __shared__ double s_part[kTgtWarps][64];
   // the discount table f32(discount ** n) (replay_buffer.py:84) is shared by the CTA's rows
-  double* s_disc = reinterpret_cast<double*>(smem_raw);  // widened once per CTA
-  for (int j = threadIdx.x; j < K + T; j += kTgtThreads) s_disc[j] = (double)c.discounts[j];
-  const bool row_ok = b < c.batch;
-  int64_t pos = 0;
-  int step = 0, len = 0;
-  if (row_ok) {
-    pos = pos_arr[b];
-    step = (int)(pos - chunk_start[b]);
-    len = chunk_len[b];  // len(root_values) == len(rewards) == len(to_play)
-  }
+  double* s_disc = reinterpret_cast<double*>(smem_raw) + kDiscPad;  // widened once per CTA, kDiscPad zeros in front
+  for (int j = threadIdx.x; j < K + T + kDiscPad; j += kTgtThreads)
+    s_disc[j - kDiscPad] = j < kDiscPad ? 0.0 : (double)c.discounts[j - kDiscPad];
+  const int64_t pos = pos_arr[b];
+  const int step = (int)(pos - chunk_start[b]);
+  const int len = chunk_len[b];  // len(root_values) == len(rewards) == len(to_play)
   __syncthreads();
-  if (!row_ok) return;  // warps are independent from here on
 
-  unsigned char* mine = smem_raw + ((size_t)(K + T) * sizeof(double) + 15) / 16 * 16 + (size_t)warp * warp_smem_bytes;
-  float* s_rew = reinterpret_cast<float*>(mine);                       // [K+T] rewards from `step` on
-  float* s_val = s_rew + (K + T);                                      // [K+1] value targets
+  unsigned char* rows_base = smem_raw + ((size_t)(K + T + kDiscPad) * sizeof(double) + 15) / 16 * 16;
+  unsigned char* mine = rows_base + (size_t)warp * warp_smem_bytes;
+  const int KT4 = (K + T + 4 + 3) & ~3, KT16 = (K + T + 16 + 15) & ~15;
+  float* s_rew_buf = reinterpret_cast<float*>(mine);                   // [KT4] rewards from position pos & ~3 on
+  int8_t* s_tp_buf = reinterpret_cast<int8_t*>(s_rew_buf + KT4);       // [KT16] to_play from position pos & ~15 on
+  float* s_val = reinterpret_cast<float*>(s_tp_buf + KT16);            // [K+1] value targets
   float* s_lastr = s_val + (K + 1);                                    // [K+1] reward targets
-  TgtBins* s_vth = reinterpret_cast<TgtBins*>(s_lastr + (K + 1));      // [K+1]
-  TgtBins* s_rth = s_vth + (K + 1);                                    // [K+1]
-  int8_t* s_tp = reinterpret_cast<int8_t*>(s_rth + (K + 1));           // [K+T]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_lastr + (K + 1));      // the warp's mbarrier (8-byte aligned)
 
   // ---- loads -------------------------------------------------------------------------------------
-  // reward / to_play window [step, min(step + K + T, len))
+  // reward / to_play window [step, min(step + K + T, len)): element j of the window = position pos + j
   const int win = max(0, min(K + T, len - step));
-  int tp_min = 127, tp_max = -128;  // does the whole window belong to one player?
-  for (int j = lane; j < win; j += 32) {
-    s_rew[j] = tgt_reward(w.rewards[pos + j], w.clip_rewards);
-    const int tp = w.to_play[pos + j];
-    s_tp[j] = (int8_t)tp;
-    tp_min = min(tp_min, tp);
-    tp_max = max(tp_max, tp);
+  const int rw_off = (int)(pos & 3), tp_off = (int)(pos & 15);
+  float* s_rew = s_rew_buf + rw_off;   // s_rew[j] = rewards[pos + j] (raw: clipped where it is read)
+  int8_t* s_tp = s_tp_buf + tp_off;    // s_tp[j] = to_play[pos + j]
+  {
+    const int64_t r_end = (pos + win) & ~(int64_t)3, t_end = (pos + win) & ~(int64_t)15;  // ends rounded down
+    const uint32_t r_bytes = (bulk_ok && r_end > pos - rw_off) ? (uint32_t)(r_end - (pos - rw_off)) * 4u : 0u;
+    const uint32_t t_bytes = (bulk_ok && t_end > pos - tp_off) ? (uint32_t)(t_end - (pos - tp_off)) : 0u;
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      mbar_fence_init();
+      mbar_arrive_expect_tx(bar, r_bytes + t_bytes);
+      if (r_bytes) bulk_copy_g2s(s_rew_buf, w.rewards + (pos - rw_off), r_bytes, bar);
+      if (t_bytes) bulk_copy_g2s(s_tp_buf, w.to_play + (pos - tp_off), t_bytes, bar);
+    }
+    // ragged tails with ordinary loads (disjoint from what the engine writes)
+    const int r_tail0 = r_bytes ? (int)(r_end - pos) : 0, t_tail0 = t_bytes ? (int)(t_end - pos) : 0;
+    for (int j = r_tail0 + lane; j < win; j += 32) s_rew[j] = w.rewards[pos + j];
+    for (int j = t_tail0 + lane; j < win; j += 32) s_tp[j] = w.to_play[pos + j];
   }
-  const bool one_player = __reduce_min_sync(MZ_FULL, tp_min) >= __reduce_max_sync(MZ_FULL, tp_max);
   const float prev_reward = (step > 0 && step <= len) ? tgt_reward(w.rewards[pos - 1], w.clip_rewards) : 0.0f;
   // bootstrap of position `lane`: root_values[step + lane + T] where it exists (replay_buffer.py:180-183)
   double root = 0.0;
@@ -219,12 +209,91 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
     for (int k = lane; k < K; k += 32)
       actions_out[(size_t)b * K + k] = k < n_real ? w.actions[pos + k] : pad_actions[(size_t)b * K + (k - n_real)];
   }
-  __syncwarp();
+  __syncwarp();       // the tails written by other lanes
+  mbar_wait(bar, 0);  // the bulk copies have landed
+  // does the whole window belong to one player?  The slack bytes around the window (up to 15 in front, up to 15
+  // behind, inside the 16-byte groups the window touches) are overwritten with its first byte, then whole 16-byte
+  // groups are compared against that byte, 16 per lane and step
+  bool one_player = true;
+  if (win > 0) {
+    const int8_t first = s_tp[0];
+    const int end16 = (tp_off + win + 15) & ~15;
+    __syncwarp();
+    if (lane < tp_off) s_tp_buf[lane] = first;
+    if (tp_off + win + lane < end16) s_tp_buf[tp_off + win + lane] = first;
+    __syncwarp();
+    const uint32_t splat = 0x01010101u * (uint32_t)(uint8_t)first;
+    uint32_t diff = 0;
+    for (int q = lane; q < (end16 >> 4); q += 32) {
+      const uint4 x4 = reinterpret_cast<const uint4*>(s_tp_buf)[q];
+      diff |= (x4.x ^ splat) | (x4.y ^ splat) | (x4.z ^ splat) | (x4.w ^ splat);
+    }
+    one_player = diff == 0;
+  }
+  one_player = __all_sync(MZ_FULL, one_player);
+  const int clip = w.clip_rewards;
 
   // ---- insert_target (replay_buffer.py:165-198) -----------------------------------------------------
   if (K <= kTgtFastK) {
-    const double mine_acc = K < 6 ? nstep_sums<6>(s_rew, s_tp, s_disc, K, T, step, len, win, lane, one_player)
-                                  : nstep_sums<kTgtFastK + 1>(s_rew, s_tp, s_disc, K, T, step, len, win, lane, one_player);
+    // the row's interior: window elements every position is in range of (replay_buffer.py:187-189 without tests)
+    int lo_r = K, hi_r = win;
+    for (int i = 0; i <= K; ++i) hi_r = min(hi_r, i + ((step + i < len) ? min(T, len - step - i) : 0));
+    if (!one_player || hi_r <= lo_r) lo_r = hi_r = 0;  // everything through the edge loop
+    if (lane == 0) {
+      s_lo[warp] = lo_r;
+      s_hi[warp] = hi_r;
+      s_rwoff[warp] = rw_off;
+    }
+    __syncthreads();  // every row's window is staged, every interior known
+    double dm = 0.0;
+    {
+      int lo_all = 1 << 30, hi_all = 0, lo_in = 0, hi_in = 1 << 30;  // union and intersection of the rows' interiors
+#pragma unroll
+      for (int r = 0; r < kTgtWarps; ++r) {
+        if (s_hi[r] > s_lo[r]) {
+          lo_all = min(lo_all, s_lo[r]);
+          hi_all = max(hi_all, s_hi[r]);
+        }
+        lo_in = max(lo_in, s_lo[r]);
+        hi_in = min(hi_in, s_hi[r]);
+      }
+      const int n = lane >> 2, k = lane & 3;  // B: element k of row n;  A: element k for position i = lane >> 2
+      const float* rw_n = reinterpret_cast<const float*>(rows_base + (size_t)n * warp_smem_bytes) + s_rwoff[n];
+      const int lo_n = s_lo[n], hi_n = s_hi[n];
+      double c0 = 0.0, c1 = 0.0;
+      const double* dk = s_disc - n;  // discounts[m0 + k - i], i = lane >> 2 (zeros in front of the table)
+      int m = lo_all + 4 * warp + k;
+      if (!clip && lo_in <= lo_all) {
+        // steps that lie inside EVERY row's interior need no range test (lo_in / hi_in: intersection of the interiors)
+        const int m_end = hi_in - 3 + k;  // m0 + 3 < hi_in
+#pragma unroll 4
+        for (; m < m_end; m += 4 * kTgtWarps) dmma_8x8x4(c0, c1, dk[m], (double)rw_n[m]);
+      }
+      for (; m - k < hi_all; m += 4 * kTgtWarps) {
+        const double bv = (m >= lo_n && m < hi_n) ? (double)tgt_reward(rw_n[m], clip) : 0.0;
+        dmma_8x8x4(c0, c1, dk[m], bv);
+      }
+      s_part[warp][2 * lane] = c0;
+      s_part[warp][2 * lane + 1] = c1;
+      __syncthreads();
+      if (lane <= K) {  // position `lane` of this warp's row: D[lane][warp] of every warp's tile
+#pragma unroll
+        for (int r = 0; r < kTgtWarps; ++r) dm += s_part[r][2 * (4 * lane + (warp >> 1)) + (warp & 1)];
+      }
+    }
+    double mine_acc = dm;
+    if (hi_r > lo_r) {
+      // the edges of an interior are a handful of elements: lane i walks those of position i itself, [i, lo) and
+      // [hi, i + n_i), one player (no sign test) -- no warp reduction
+      if (lane <= K && step + lane < len) {
+        const int n_i = min(T, len - step - lane);
+        for (int m = lane; m < lo_r; ++m) mine_acc += (double)tgt_reward(s_rew[m], clip) * s_disc[m - lane];
+        for (int m = hi_r; m < lane + n_i; ++m) mine_acc += (double)tgt_reward(s_rew[m], clip) * s_disc[m - lane];
+      }
+    } else {
+      mine_acc += K < 6 ? nstep_edges<6>(s_rew, s_tp, s_disc, K, T, step, len, win, lo_r, hi_r, lane, clip)
+                        : nstep_edges<kTgtFastK + 1>(s_rew, s_tp, s_disc, K, T, step, len, win, lo_r, hi_r, lane, clip);
+    }
     if (lane <= K) {
       const int ci = step + lane;
       float value = 0.0f;
@@ -233,7 +302,7 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
         value = __fadd_rn((float)boot, (float)mine_acc);  // numpy 2: python float + np.float32 -> float32
       }
       float last_reward = 0.0f;
-      if (ci > 0 && ci <= len) last_reward = (lane > 0) ? s_rew[lane - 1] : prev_reward;
+      if (ci > 0 && ci <= len) last_reward = (lane > 0) ? tgt_reward(s_rew[lane - 1], clip) : prev_reward;
       s_val[lane] = value;
       s_lastr[lane] = last_reward;
     }
@@ -247,7 +316,7 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
         const int n = min(T, len - ci);
         double acc = 0.0;
         for (int j = lane; j < n; j += 32) {
-          float r = s_rew[i + j];
+          float r = tgt_reward(s_rew[i + j], clip);
           if (s_tp[i + j] != tp) r = -r;
           acc += (double)r * s_disc[j];
         }
@@ -258,7 +327,7 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
       }
       if (lane == 0) {
         float last_reward = 0.0f;
-        if (ci > 0 && ci <= len) last_reward = (i > 0) ? s_rew[i - 1] : prev_reward;
+        if (ci > 0 && ci <= len) last_reward = (i > 0) ? tgt_reward(s_rew[i - 1], clip) : prev_reward;
         s_val[i] = value;
         s_lastr[i] = last_reward;
       }
@@ -266,22 +335,34 @@ build_targets_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict__ p
   }
   __syncwarp();
   for (int i = lane; i <= K; i += 32) {
-    const float v = s_val[i], r = s_lastr[i];
-    t_values[(size_t)b * (K + 1) + i] = v;
-    t_rewards[(size_t)b * (K + 1) + i] = r;
-    if (c.fuse_supports) {
-      // learners.py:186-192: h(x) then two-hot projection of values and rewards
-      const MzTwoHot tv = mz_two_hot(c.no_target_transform ? v : mz_scalar_transform_f(v), c.value_min, c.value_max);
-      const MzTwoHot tr = mz_two_hot(c.no_target_transform ? r : mz_scalar_transform_f(r), c.reward_min, c.reward_max);
-      s_vth[i] = TgtBins{tv.lo, tv.hi, tv.p_lo, tv.p_hi};
-      s_rth[i] = TgtBins{tr.lo, tr.hi, tr.p_lo, tr.p_hi};
-    }
+    t_values[(size_t)b * (K + 1) + i] = s_val[i];
+    t_rewards[(size_t)b * (K + 1) + i] = s_lastr[i];
   }
   if (!c.fuse_supports) return;
-  __syncwarp();
+  // learners.py:186-192: h(x) then two-hot projection of values and rewards: the row's supports are zero-filled
+  // with 8-byte stores, then every position scatters its two bins (high first: the low bin wins on integers)
   const int vb = c.value_max - c.value_min + 1, rb = c.reward_max - c.reward_min + 1;
-  write_supports(value_support + (size_t)b * (K + 1) * vb, s_vth, K + 1, vb, lane);
-  write_supports(reward_support + (size_t)b * (K + 1) * rb, s_rth, K + 1, rb, lane);
+  float* vs_row = value_support + (size_t)b * (K + 1) * vb;
+  float* rs_row = reward_support + (size_t)b * (K + 1) * rb;
+  auto zero_fill = [&](float* dst, int n) {
+    if (((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+      for (int e = lane; e < (n >> 1); e += 32) reinterpret_cast<float2*>(dst)[e] = make_float2(0.0f, 0.0f);
+    } else {
+      for (int e = lane; e < n; e += 32) dst[e] = 0.0f;
+    }
+  };
+  zero_fill(vs_row, (K + 1) * vb);
+  zero_fill(rs_row, (K + 1) * rb);
+  __syncwarp();  // orders the fills before the scatters of the other lanes
+  for (int i = lane; i <= K; i += 32) {
+    const float v = s_val[i], r = s_lastr[i];
+    const MzTwoHot tv = mz_two_hot(c.no_target_transform ? v : mz_scalar_transform_f(v), c.value_min, c.value_max);
+    const MzTwoHot tr = mz_two_hot(c.no_target_transform ? r : mz_scalar_transform_f(r), c.reward_min, c.reward_max);
+    vs_row[i * vb + tv.hi] = tv.p_hi;
+    vs_row[i * vb + tv.lo] = tv.p_lo;
+    rs_row[i * rb + tr.hi] = tr.p_hi;
+    rs_row[i * rb + tr.lo] = tr.p_lo;
+  }
 }
 
 // ---- lane-per-position variant ---------------------------------------------------------------------
@@ -1010,9 +1091,11 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
     MZ_LAUNCH_CHECK();
     return MZ_OK;
   }
-  // per warp: rewards [K+T] f32, values / rewards [K+1] f32 each, two-hot bins 2 x [K+1] x 16 B, to_play [K+T]
-  const int warp_smem = (int)((sizeof(float) * (KT + 2 * K1) + 2 * sizeof(TgtBins) * K1 + KT + 15) / 16 * 16);
-  const size_t smem = (size_t)warp_smem * kTgtWarps + (sizeof(double) * KT + 15) / 16 * 16;  // + discount table
+  // per warp: rewards [KT4] f32, to_play [KT16], values / rewards [K+1] f32 each, mbarrier
+  const int KT4 = (KT + 4 + 3) & ~3, KT16 = (KT + 16 + 15) & ~15;
+  const int warp_smem = (int)((sizeof(float) * (KT4 + 2 * K1) + KT16 + 8 + 15) / 16 * 16);
+  const size_t smem = (size_t)warp_smem * kTgtWarps + (sizeof(double) * (KT + kDiscPad) + 15) / 16 * 16;  // + discount table
+  const int bulk_ok = ((reinterpret_cast<uintptr_t>(w->rewards) | reinterpret_cast<uintptr_t>(w->to_play)) & 15) == 0;
   if (smem > 200 * 1024) return MZ_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
@@ -1023,7 +1106,7 @@ int mz_build_targets(const mz_window* w, const mz_target_cfg* c, const int64_t* 
   }
   build_targets_kernel<<<(c->batch + kTgtWarps - 1) / kTgtWarps, kTgtThreads, smem, (cudaStream_t)stream>>>(
       *w, *c, pos, chunk_start, chunk_len, pad_actions, obs_out, actions_out, t_rewards, t_values,
-      t_policies, value_support, reward_support, warp_smem);
+      t_policies, value_support, reward_support, warp_smem, bulk_ok);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }
