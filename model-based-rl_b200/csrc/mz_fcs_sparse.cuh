@@ -315,7 +315,9 @@ MZ_DEV void descend(const FsParams& p, const Smem& sm, const Game& gm, const Geo
     const bool act = gm.valid && n >= 1 && n <= sim;
     we[t] = node[act ? n : 0];
     const int np_ = (int)(node[we[t] >> 24] & 0xffu), nj = (int)(we[t] & 0xffu);
-    pbc[t] = __ldg(p.pb_c + (size_t)np_ * SP1 + nj);
+    // a lane without an edge (a game beyond num_games in the last tile, node 0) reads shared memory nobody
+    // initialised: keep its table index inside pb_c
+    pbc[t] = __ldg(p.pb_c + (act ? (size_t)np_ * SP1 + nj : (size_t)0));
     ed[t] = *reinterpret_cast<const double2*>(gm.base + G.edge + 32 * (act ? n : 0));
   }
 #pragma unroll
