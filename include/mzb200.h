@@ -593,6 +593,39 @@ int mz_set_programmatic_launch(int32_t enable);
 const char* mz_version(void);
 int32_t mz_compiled_arch(void); /* 100 for sm_100a */
 
+/* ------------------------------------------------------------------------------------------- */
+/* Learner network forward / backward for the FCNetwork architecture (learners.py:164-230,      */
+/* networks.py:55-174), float32 like the reference.  Weights: torch layout W1 [512][d_in], W2     */
+/* [d_out][512] in the flat parameter buffer, plus k-major copies W1T [d_in][512], W2T            */
+/* [512][d_out] (mz_learner_transpose) for the forward.  d_in <= 128, d_out <= 64.                */
+/* ------------------------------------------------------------------------------------------- */
+/* Y[r][0:d_out] = W2 relu(W1 X[r][0:d_in] + b1) + b2 -- one head (networks.py:55-119) over `rows` rows. */
+int mz_mlp2_forward(int32_t rows, int32_t d_in, int32_t ldx, const float* X, const float* W1T, const float* b1,
+                    const float* W2T, const float* b2, int32_t d_out, float* Y, int32_t ldy, void* stream);
+/* Backward of the same head: dX[r][0:d_in] += ... (NULL: not needed), gW1 / gb1 / gW2 / gb2 += (atomics, torch
+ * layouts); the 512-wide activation is recomputed from X. */
+int mz_mlp2_backward(int32_t rows, int32_t d_in, int32_t ldx, const float* X, const float* W1T, const float* b1,
+                     const float* W1, const float* W2, int32_t d_out, const float* dY, int32_t ldy, float* dX,
+                     int32_t lddx, float* gW1, float* gb1, float* gW2, float* gb2, void* stream);
+/* X_out[r] = [relu(LayerNorm(Y[r][0:d])) | one_hot(actions[r * action_stride], num_actions)]: the hidden state
+ * (networks.py:144, 160, 171) and the next head's input row (networks.py:165-166); actions NULL: zeros. */
+int mz_ln_relu_forward(int32_t rows, int32_t d, const float* Y, const float* gamma, const float* beta,
+                       const int32_t* actions, int32_t action_stride, int32_t num_actions, float* X_out, int32_t ldx,
+                       float* mean, float* rstd, void* stream);
+/* dY = backward of relu(LayerNorm(Y)) for the incoming gradient scale * dH (scale 0.5: the gradient hook of
+ * learners.py:201); ggamma / gbeta += . */
+int mz_ln_relu_backward(int32_t rows, int32_t d, const float* dH, int32_t lddh, float scale, const float* Y,
+                        const float* H, int32_t ldh, const float* mean, const float* rstd, const float* gamma, float* dY,
+                        float* ggamma, float* gbeta, void* stream);
+/* out [cols][rows] = in [rows][cols]^T */
+int mz_learner_transpose(int32_t rows, int32_t cols, const float* in, float* out, void* stream);
+/* torch.optim.AdamW (decoupled != 0) / Adam step over a flat buffer (utils.py:72-83), gradients first multiplied by
+ * grad_scale (1 / ranks after a summing all-reduce) and, with clip_norm > 0, clipped to that global norm
+ * (learners.py:217-218).  state [3] f32 on the device: step count (incremented here), learning rate, scratch. */
+int mz_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* state,
+                 float beta1, float beta2, float eps, float weight_decay, int32_t decoupled, float grad_scale,
+                 float clip_norm, void* stream);
+
 #if defined(MZ_BUILDING) && defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

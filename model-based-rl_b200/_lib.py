@@ -144,6 +144,15 @@ _SIGNATURES = {
     "mz_sumtree_sample_mt": (C.c_int, [_V, C.c_int64, C.c_int32, _V, C.c_int32, _V, _V, _V, C.c_int64, C.c_double, _V, _V,
                                        _V, _V, _V, _V, _V]),
     "mz_sumtree_update_errors": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_double, C.c_double, _V, _V, _V]),
+    "mz_mlp2_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _V, _V, _V, _V, _V, C.c_int32, _V, C.c_int32, _V]),
+    "mz_mlp2_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _V, _V, _V, _V, _V, C.c_int32, _V, C.c_int32, _V,
+                                   C.c_int32, _V, _V, _V, _V, _V]),
+    "mz_ln_relu_forward": (C.c_int, [C.c_int32, C.c_int32, _V, _V, _V, _V, C.c_int32, C.c_int32, _V, C.c_int32, _V, _V, _V]),
+    "mz_ln_relu_backward": (C.c_int, [C.c_int32, C.c_int32, _V, C.c_int32, C.c_float, _V, _V, C.c_int32, _V, _V, _V, _V, _V,
+                                      _V, _V]),
+    "mz_learner_transpose": (C.c_int, [C.c_int32, C.c_int32, _V, _V, _V]),
+    "mz_adam_step": (C.c_int, [C.c_int64, _V, _V, _V, _V, _V, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
+                               C.c_float, C.c_float, _V]),
     "mz_sumtree_add_from": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_int64, C.c_int32, C.c_int32, _V, _V, _V,
                                       _V, _V]),
     "mz_sumtree_sample": (C.c_int, [_V, C.c_int64, C.c_int32, _V, _V, _V, _V, C.c_int64, C.c_double,

@@ -687,9 +687,13 @@ build_targets_tma_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict
       const int8_t* base = w.to_play + (pos - off);
       for (int q = q0; q * 4 < off + KT; q += LPR) {
         const int have = min(4, nbytes - q * 4);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(s_tp + r * TPS + q * 4)),
-                     "l"(have > 0 ? base + q * 4 : w.to_play), "r"(max(have, 0))
-                     : "memory");
+        if (have == 4 || have <= 0) {  // a whole word of the array, or nothing (zero fill)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(s_tp + r * TPS + q * 4)),
+                       "l"(have > 0 ? base + q * 4 : w.to_play), "r"(max(have, 0))
+                       : "memory");
+        } else {  // the last, partial word: byte loads, so that nothing behind the window is touched
+          for (int bb = 0; bb < have; ++bb) s_tp[r * TPS + q * 4 + bb] = __ldg(base + q * 4 + bb);
+        }
       }
     }
     for (int q = q0; q < RW; q += LPR) {  // raw rewards pos - 1 .. pos + K + T - 1 (clipped where they are read)
