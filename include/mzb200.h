@@ -626,6 +626,74 @@ int mz_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, f
                  float beta1, float beta2, float eps, float weight_decay, int32_t decoupled, float grad_scale,
                  float clip_norm, void* stream);
 
+/* ------------------------------------------------------------------------------------------- */
+/* The same forward / backward on the tensor cores (csrc/mz_learner_tc.cu): bf16 operands, f32   */
+/* accumulation, f32 master weights and gradients.  A training step is FOUR launches: the chain    */
+/* representation -> LN -> K x (dynamics -> LN) (learners.py:175-206), the three output heads      */
+/* over the stacked hidden states, their backward, and the chain's backward with the 0.5 gradient  */
+/* hook of learners.py:201.                                                                        */
+/* ------------------------------------------------------------------------------------------- */
+/* One matrix to pack as an mma B operand: B[k][n] = src[n * stride_n + k * stride_k] (n < N, k < K), as bf16
+ * fragments of 8 (n) x 32 (k) blocks, mz_learner_packed_words(N, K) 32-bit words (zero padded). */
+typedef struct mz_pack_job {
+  const float* src;
+  uint32_t* dst; /* 16-byte aligned */
+  int32_t n, k, stride_n, stride_k;
+} mz_pack_job;
+int64_t mz_learner_packed_words(int32_t n, int32_t k);
+/* Up to 24 matrices per launch (a step packs four images per head from the float32 master weights). */
+int mz_learner_pack(int32_t njobs, const mz_pack_job* jobs, void* stream);
+
+/* One head Linear(d_in, 512) -> ReLU -> Linear(512, d_out) (networks.py:55-119); d_in <= 128, d_out <= 64.
+ * Packed images of W1 [512][d_in] and W2 [d_out][512] (torch layouts):
+ *   w1p  (N = 512, K = d_in;  src W1, stride_n d_in, stride_k 1)    layer 1
+ *   w2p  (N = d_out, K = 512; src W2, stride_n 512, stride_k 1)     layer 2
+ *   w2tp (N = 512, K = d_out; src W2, stride_n 1, stride_k 512)     dH = dY W2        (backward)
+ *   w1tp (N = d_in, K = 512;  src W1, stride_n 1, stride_k d_in)    dX = dH W1        (backward)
+ * gw1 / gb1 / gw2 / gb2: float32 gradients in torch layouts, accumulated with atomics (backward). */
+typedef struct mz_tc_head {
+  const uint32_t *w1p, *w2p, *w2tp, *w1tp;
+  const float *b1, *b2;
+  float *gw1, *gb1, *gw2, *gb2;
+  int32_t d_in, d_out;
+} mz_tc_head;
+/* One head over `rows` rows.  Forward: y[r][0:d_out] = head(x[r][0:d_in]).  Backward: dy in, parameter gradients
+ * accumulated, dx[r][0:d_in] += (atomics: several heads may share the rows; NULL = not needed). */
+typedef struct mz_tc_job {
+  mz_tc_head head;
+  int32_t rows, ldx, ldy, lddx;
+  const float* x;
+  float* y;
+  const float* dy;
+  float* dx;
+} mz_tc_job;
+/* Up to three heads in one launch (the value / policy / reward heads of FCNetwork over all unroll steps). */
+int mz_heads_forward_tc(int32_t njobs, const mz_tc_job* jobs, void* stream);
+int mz_heads_backward_tc(int32_t njobs, const mz_tc_job* jobs, void* stream);
+
+/* The recurrent part: step 0 = `first` (representation) on x0, steps 1..steps-1 = `next` (dynamics) on the row
+ * [hidden | one_hot(action)] the step before produced.  Per step s: yall[s] = head output (pre-LayerNorm),
+ * mean / rstd[s], xs[s][r] = [relu(LN(yall[s][r])) (d values) | one_hot(actions[r * action_stride + s]) for
+ * s < action_steps, zeros after].  Backward: dxs[s][r][0:d] = gradient of xs[s] from the output heads; the states
+ * the dynamics produced get hook_scale (learners.py:201); ggamma / gbeta and the heads' gradients are accumulated. */
+typedef struct mz_tc_chain {
+  mz_tc_head first, next;
+  int32_t rows, steps, d, num_actions;
+  const float* x0;
+  int32_t ldx0;
+  const int32_t* actions;
+  int32_t action_stride, action_steps;
+  const float *gamma, *beta; /* LayerNorm affine (networks.py:144) */
+  float* xs;
+  int32_t ldxs; /* >= d + num_actions */
+  float *yall, *mean, *rstd;
+  const float* dxs; /* backward */
+  float hook_scale;
+  float *ggamma, *gbeta;
+} mz_tc_chain;
+int mz_chain_forward_tc(const mz_tc_chain* chain, void* stream);
+int mz_chain_backward_tc(const mz_tc_chain* chain, void* stream);
+
 #if defined(MZ_BUILDING) && defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

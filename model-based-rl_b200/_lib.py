@@ -86,6 +86,34 @@ class LossCfg(C.Structure):
               ("reward_max", C.c_int32), ("no_target_transform", C.c_int32)]
 
 
+class PackJob(C.Structure):
+  """struct mz_pack_job"""
+  _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n", C.c_int32), ("k", C.c_int32), ("stride_n", C.c_int32),
+              ("stride_k", C.c_int32)]
+
+
+class TcHead(C.Structure):
+  """struct mz_tc_head"""
+  _fields_ = [("w1p", C.c_void_p), ("w2p", C.c_void_p), ("w2tp", C.c_void_p), ("w1tp", C.c_void_p), ("b1", C.c_void_p),
+              ("b2", C.c_void_p), ("gw1", C.c_void_p), ("gb1", C.c_void_p), ("gw2", C.c_void_p), ("gb2", C.c_void_p),
+              ("d_in", C.c_int32), ("d_out", C.c_int32)]
+
+
+class TcJob(C.Structure):
+  """struct mz_tc_job"""
+  _fields_ = [("head", TcHead), ("rows", C.c_int32), ("ldx", C.c_int32), ("ldy", C.c_int32), ("lddx", C.c_int32),
+              ("x", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p), ("dx", C.c_void_p)]
+
+
+class TcChain(C.Structure):
+  """struct mz_tc_chain"""
+  _fields_ = [("first", TcHead), ("next", TcHead), ("rows", C.c_int32), ("steps", C.c_int32), ("d", C.c_int32),
+              ("num_actions", C.c_int32), ("x0", C.c_void_p), ("ldx0", C.c_int32), ("actions", C.c_void_p),
+              ("action_stride", C.c_int32), ("action_steps", C.c_int32), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+              ("xs", C.c_void_p), ("ldxs", C.c_int32), ("yall", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
+              ("dxs", C.c_void_p), ("hook_scale", C.c_float), ("ggamma", C.c_void_p), ("gbeta", C.c_void_p)]
+
+
 _V = C.c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)
@@ -153,6 +181,12 @@ _SIGNATURES = {
     "mz_learner_transpose": (C.c_int, [C.c_int32, C.c_int32, _V, _V, _V]),
     "mz_adam_step": (C.c_int, [C.c_int64, _V, _V, _V, _V, _V, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                C.c_float, C.c_float, _V]),
+    "mz_learner_packed_words": (C.c_int64, [C.c_int32, C.c_int32]),
+    "mz_learner_pack": (C.c_int, [C.c_int32, C.POINTER(PackJob), _V]),
+    "mz_heads_forward_tc": (C.c_int, [C.c_int32, C.POINTER(TcJob), _V]),
+    "mz_heads_backward_tc": (C.c_int, [C.c_int32, C.POINTER(TcJob), _V]),
+    "mz_chain_forward_tc": (C.c_int, [C.POINTER(TcChain), _V]),
+    "mz_chain_backward_tc": (C.c_int, [C.POINTER(TcChain), _V]),
     "mz_sumtree_add_from": (C.c_int, [_V, C.c_int64, C.c_int64, _V, _V, C.c_int64, C.c_int32, C.c_int32, _V, _V, _V,
                                       _V, _V]),
     "mz_sumtree_sample": (C.c_int, [_V, C.c_int64, C.c_int32, _V, _V, _V, _V, C.c_int64, C.c_double,

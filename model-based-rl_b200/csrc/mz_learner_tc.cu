@@ -1,0 +1,657 @@
+// The learner's network forward and backward (Learner.update_weights, learners.py:164-230) on the tensor cores:
+// bf16 operands, float32 accumulation, float32 master weights and gradients.
+//
+// The step of the FCNetwork architecture (networks.py:55-174) is 4 GFLOP behind a chain of 2 (K + 1) + 3 dependent
+// two-layer heads, 32..3072 rows each: what bounds it is the length of that chain, not tensor throughput.  So the
+// kernels here are built to make the chain short rather than the tiles big:
+//
+//   chain_fwd   ONE launch for representation -> LN -> K x (dynamics -> LN): the rows of a batch are independent in
+//               the forward, so a CTA keeps its 32 rows for all K + 1 steps; the hidden state of a step goes from the
+//               LayerNorm epilogue straight into the next step's A tile in shared memory
+//   heads_fwd   ONE launch for the value / policy / reward heads over the stacked hidden states (blockIdx.y = head)
+//   heads_bwd   ONE launch for their backward (dX accumulated into the hidden states' gradient rows)
+//   chain_bwd   ONE launch back through K x (LN -> dynamics), LN, representation: the gradient of a row's hidden state
+//               only depends on the same row's later steps, so again a CTA keeps its rows; the dynamics head's dX tile
+//               feeds the next LayerNorm backward through shared memory; the 0.5 gradient hook (learners.py:201) is a
+//               scale there
+//
+// -- 4 launches where the float32 CUDA-core path (mz_learner.cu) needs 30.  Inside a tile every contraction is
+// mma.sync.m16n8k16 (bf16 x bf16 -> f32): the tiles are 32 rows x 64 columns per warp and change role five times per
+// head (activation, dH, dX, two weight gradients with the batch rows as the K dimension, fed by ldmatrix.trans from the
+// same row-major tiles), which warp-level fragments do without a TMEM / descriptor round trip per role.  Weights are
+// read as pre-packed B fragments (mz_learner_pack: one 16-byte load per lane covers two k-steps), refreshed once per
+// step from the float32 master copy.  Weight gradients leave as float32 atomics (one per weight and CTA).
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "mz_common.cuh"
+
+namespace {
+
+constexpr int LW = 512;    // hidden width of every head (networks.py:55-119)
+constexpr int RT = 32;     // rows per CTA
+constexpr int NTH = 256;   // threads per CTA: warp w owns hidden units [64 w, 64 w + 64)
+constexpr int XLD = 136;   // bf16 per row of the input tile (<= 128 features; 272 B: ldmatrix rows 16 B apart mod 128)
+constexpr int HLD = 520;   // bf16 per row of the activation tiles
+constexpr int DYLD = 72;   // bf16 per row of the output-gradient tile (<= 64 outputs)
+constexpr int FLD = 68;    // floats per row of the float32 tile (layer-2 output / dX of the dynamics head)
+constexpr int MAXJOBS = 3, MAXPACK = 24;
+
+struct PlainParams {
+  mz_tc_job jobs[MAXJOBS];
+};
+struct PackParams {
+  mz_pack_job jobs[MAXPACK];
+};
+
+MZ_DEV void ldsm4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+MZ_DEV void ldsm4t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+// D (16 x 8, f32) += A (16 x 16, row) * B (16 x 8, col), bf16 operands
+MZ_DEV void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+MZ_DEV uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+MZ_DEV int round_up32(int v) { return (v + 31) & ~31; }
+
+// Packed B operand of a matrix Bm [N][K] (B[k][n] = Bm[n][k]): 32-bit word ((nt KQ + kq) 32 + lane) 4 + i holds
+// (Bm[8 nt + g][kk], Bm[8 nt + g][kk + 1]) with g = lane >> 2, kk = 32 kq + 16 (i >> 1) + 8 (i & 1) + 2 (lane & 3):
+// the b0 / b1 registers of k-steps 2 kq and 2 kq + 1 of n-tile nt, one 16-byte load per lane.  Zeros outside N x K.
+__global__ void pack_kernel(PackParams p) {
+  const mz_pack_job job = p.jobs[blockIdx.y];
+  const int KQ = (job.k + 31) >> 5, NTl = (job.n + 7) >> 3;
+  const int words = NTl * KQ * 128;
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+    const int i = w & 3, lane = (w >> 2) & 31, rest = w >> 7;
+    const int kq = rest % KQ, nt = rest / KQ;
+    const int nn = 8 * nt + (lane >> 2), kk = 32 * kq + 16 * (i >> 1) + 8 * (i & 1) + 2 * (lane & 3);
+    float lo = 0.0f, hi = 0.0f;
+    if (nn < job.n) {
+      if (kk < job.k) lo = job.src[(size_t)nn * job.stride_n + (size_t)kk * job.stride_k];
+      if (kk + 1 < job.k) hi = job.src[(size_t)nn * job.stride_n + (size_t)(kk + 1) * job.stride_k];
+    }
+    job.dst[w] = pack2(lo, hi);
+  }
+}
+
+// acc[2][8][4] += A (32 rows x 32 KQ, row-major bf16 in shared memory) * B (packed; n-tiles nt0 .. nt0 + 7)
+MZ_DEV void gemm_wide(float (&acc)[2][8][4], const __nv_bfloat16* As, int lda, const uint32_t* __restrict__ Bp, int KQ,
+                      int nt0, int lane) {
+  const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
+  const uint4* bp = reinterpret_cast<const uint4*>(Bp) + (size_t)nt0 * KQ * 32 + lane;
+  uint4 b[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) b[n] = __ldg(bp + (size_t)n * KQ * 32);
+  for (int kq = 0; kq < KQ; ++kq) {
+    uint4 bn[8];
+    if (kq + 1 < KQ) {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) bn[n] = __ldg(bp + ((size_t)n * KQ + kq + 1) * 32);
+    }
+    uint32_t a[2][2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) ldsm4(a[ks][mt], As + (16 * mt + arow) * lda + 32 * kq + 16 * ks + acol);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      mma16816(acc[0][n], a[0][0], b[n].x, b[n].y);
+      mma16816(acc[1][n], a[0][1], b[n].x, b[n].y);
+      mma16816(acc[0][n], a[1][0], b[n].z, b[n].w);
+      mma16816(acc[1][n], a[1][1], b[n].z, b[n].w);
+    }
+    if (kq + 1 < KQ) {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) b[n] = bn[n];
+    }
+  }
+}
+
+// acc[2][4] = A (32 rows x 512, row-major bf16 in shared memory) * B (packed, KQ = 16; n-tile nt)
+MZ_DEV void gemm_tall(float (&acc)[2][4], const __nv_bfloat16* As, int lda, const uint32_t* __restrict__ Bp, int nt,
+                      int lane) {
+  const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
+  const uint4* bp = reinterpret_cast<const uint4*>(Bp) + (size_t)nt * 16 * 32 + lane;
+  uint4 b[16];
+#pragma unroll
+  for (int kq = 0; kq < 16; ++kq) b[kq] = __ldg(bp + kq * 32);
+  float acc2[2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[mt][c] = acc2[mt][c] = 0.0f;
+#pragma unroll
+  for (int kq = 0; kq < 16; ++kq) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      uint32_t a0[4], a1[4];
+      ldsm4(a0, As + (16 * mt + arow) * lda + 32 * kq + acol);
+      ldsm4(a1, As + (16 * mt + arow) * lda + 32 * kq + 16 + acol);
+      mma16816(acc[mt], a0, b[kq].x, b[kq].y);
+      mma16816(acc2[mt], a1, b[kq].z, b[kq].w);
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[mt][c] += acc2[mt][c];
+}
+
+// rows [row0, row0 + 32) x columns [0, d) of a float32 matrix -> bf16 tile, zeros up to column dpad and behind `rows`
+MZ_DEV void load_rows(__nv_bfloat16* Ts, int ld, const float* __restrict__ X, int ldx, int row0, int rows, int d, int dpad) {
+  for (int idx = threadIdx.x; idx < RT * dpad; idx += NTH) {
+    const int r = idx / dpad, c = idx - r * dpad;
+    const float v = (row0 + r < rows && c < d) ? X[(size_t)(row0 + r) * ldx + c] : 0.0f;
+    Ts[r * ld + c] = __float2bfloat16_rn(v);
+  }
+}
+
+// H = relu(W1 X + b1) for the warp's 64 hidden units -> Hs (bf16); returns the sign bits (bit 4 n + c of mask[mt])
+MZ_DEV void hidden_phase(const mz_tc_head& h, const __nv_bfloat16* Xs, __nv_bfloat16* Hs, uint32_t (&mask)[2], int warp,
+                         int lane) {
+  float acc[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[mt][n][c] = 0.0f;
+  gemm_wide(acc, Xs, XLD, h.w1p, round_up32(h.d_in) >> 5, 8 * warp, lane);
+  const int g = lane >> 2, t = lane & 3;
+  mask[0] = mask[1] = 0u;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int j = 64 * warp + 8 * n + 2 * t;
+    const float2 bb = make_float2(__ldg(h.b1 + j), __ldg(h.b1 + j + 1));  // views of a flat buffer: 4-byte aligned
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const float v0 = fmaxf(acc[mt][n][0] + bb.x, 0.0f), v1 = fmaxf(acc[mt][n][1] + bb.y, 0.0f);
+      const float v2 = fmaxf(acc[mt][n][2] + bb.x, 0.0f), v3 = fmaxf(acc[mt][n][3] + bb.y, 0.0f);
+      mask[mt] |= (v0 > 0.0f ? 1u : 0u) << (4 * n) | (v1 > 0.0f ? 2u : 0u) << (4 * n) | (v2 > 0.0f ? 4u : 0u) << (4 * n) |
+                  (v3 > 0.0f ? 8u : 0u) << (4 * n);
+      *reinterpret_cast<uint32_t*>(Hs + (16 * mt + g) * HLD + j) = pack2(v0, v1);
+      *reinterpret_cast<uint32_t*>(Hs + (16 * mt + g + 8) * HLD + j) = pack2(v2, v3);
+    }
+  }
+}
+
+// Y = H W2^T + b2: warp w < ceil(d_out / 8) owns outputs [8 w, 8 w + 8).  To global memory (Y != nullptr) or to the
+// float32 tile Fs.
+MZ_DEV void output_phase(const mz_tc_head& h, const __nv_bfloat16* Hs, float* __restrict__ Y, int ldy, int row0, int rows,
+                         float* Fs, int warp, int lane) {
+  if (8 * warp >= h.d_out) return;
+  float acc[2][4];
+  gemm_tall(acc, Hs, HLD, h.w2p, warp, lane);
+  const int g = lane >> 2, o = 8 * warp + 2 * (lane & 3);
+  const float b0 = o < h.d_out ? __ldg(h.b2 + o) : 0.0f, b1 = o + 1 < h.d_out ? __ldg(h.b2 + o + 1) : 0.0f;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = 16 * mt + g + 8 * half;
+      const float y0 = acc[mt][2 * half] + b0, y1 = acc[mt][2 * half + 1] + b1;
+      if (Y != nullptr) {
+        if (row0 + r < rows) {
+          if (o < h.d_out) Y[(size_t)(row0 + r) * ldy + o] = y0;
+          if (o + 1 < h.d_out) Y[(size_t)(row0 + r) * ldy + o + 1] = y1;
+        }
+      } else {
+        Fs[r * FLD + o] = y0;
+        Fs[r * FLD + o + 1] = y1;
+      }
+    }
+  }
+}
+
+// Backward of one head over the CTA's tile.  In: Xs (input rows, bf16), dYs (output gradient, bf16, zero padded to a
+// multiple of 32 columns).  Out: the four parameter gradients (atomics), and dX (columns [0, dx_cols)) accumulated into
+// global memory (dX != nullptr) or left in Fs (dx_cols > 0, dX == nullptr).
+MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __nv_bfloat16* dYs, __nv_bfloat16* Hs,
+                          __nv_bfloat16* dHs, float* __restrict__ dX, int lddx, int dx_cols, int row0, int rows, float* Fs,
+                          int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t mask[2];
+  hidden_phase(h, Xs, Hs, mask, warp, lane);
+  {  // dH = dY W2 for the warp's hidden units, masked by the ReLU; gb1; -> dHs
+    float acc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[mt][n][c] = 0.0f;
+    gemm_wide(acc, dYs, DYLD, h.w2tp, round_up32(h.d_out) >> 5, 8 * warp, lane);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int j = 64 * warp + 8 * n + 2 * t;
+      float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t m = mask[mt] >> (4 * n);
+        const float v0 = (m & 1u) ? acc[mt][n][0] : 0.0f, v1 = (m & 2u) ? acc[mt][n][1] : 0.0f;
+        const float v2 = (m & 4u) ? acc[mt][n][2] : 0.0f, v3 = (m & 8u) ? acc[mt][n][3] : 0.0f;
+        s0 += v0 + v2;
+        s1 += v1 + v3;
+        *reinterpret_cast<uint32_t*>(dHs + (16 * mt + g) * HLD + j) = pack2(v0, v1);
+        *reinterpret_cast<uint32_t*>(dHs + (16 * mt + g + 8) * HLD + j) = pack2(v2, v3);
+      }
+#pragma unroll
+      for (int m = 4; m < 32; m <<= 1) {
+        s0 += __shfl_xor_sync(MZ_FULL, s0, m);
+        s1 += __shfl_xor_sync(MZ_FULL, s1, m);
+      }
+      if (g == 0) {
+        atomicAdd(h.gb1 + j, s0);
+        atomicAdd(h.gb1 + j + 1, s1);
+      }
+    }
+  }
+  __syncthreads();
+  // dX = dH W1: n-tiles w and w + 8 of the input features
+  if (dx_cols > 0) {
+    for (int nt = warp; 8 * nt < dx_cols; nt += 8) {
+      float acc[2][4];
+      gemm_tall(acc, dHs, HLD, h.w1tp, nt, lane);
+      const int k = 8 * nt + 2 * t;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int r = 16 * mt + g + 8 * half;
+          if (dX != nullptr) {
+            if (row0 + r < rows) {
+              if (k < dx_cols) atomicAdd(dX + (size_t)(row0 + r) * lddx + k, acc[mt][2 * half]);
+              if (k + 1 < dx_cols) atomicAdd(dX + (size_t)(row0 + r) * lddx + k + 1, acc[mt][2 * half + 1]);
+            }
+          } else {
+            Fs[r * FLD + k] = acc[mt][2 * half];
+            Fs[r * FLD + k + 1] = acc[mt][2 * half + 1];
+          }
+        }
+      }
+    }
+  }
+  const int lrow = lane & 7, lsel = lane >> 3;  // ldmatrix.trans: lanes 8 i .. 8 i + 7 address matrix i
+  // gW2[o][j] = sum_r dY[r][o] H[r][j]: M = outputs (16 per m-tile), N = the warp's hidden units, K = the tile's rows
+  for (int mt = 0; 16 * mt < h.d_out; ++mt) {
+    float acc[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[n][c] = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t a[4];
+      ldsm4t(a, dYs + (16 * ks + lrow + (lsel >> 1) * 8) * DYLD + 16 * mt + (lsel & 1) * 8);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b[4];
+        ldsm4t(b, Hs + (16 * ks + lrow + (lsel & 1) * 8) * HLD + 64 * warp + 16 * np + (lsel >> 1) * 8);
+        mma16816(acc[2 * np], a, b[0], b[1]);
+        mma16816(acc[2 * np + 1], a, b[2], b[3]);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int j = 64 * warp + 8 * n + 2 * t;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int o = 16 * mt + g + 8 * half;
+        if (o < h.d_out) {
+          atomicAdd(h.gw2 + (size_t)o * LW + j, acc[n][2 * half]);
+          atomicAdd(h.gw2 + (size_t)o * LW + j + 1, acc[n][2 * half + 1]);
+        }
+      }
+    }
+  }
+  // gW1[j][k] = sum_r dH[r][j] X[r][k]: M = the warp's hidden units, N = input features in chunks of 64, K = rows
+  for (int mt = 0; mt < 4; ++mt) {
+    for (int chunk = 0; 64 * chunk < h.d_in; ++chunk) {
+      float acc[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[n][c] = 0.0f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t a[4];
+        ldsm4t(a, dHs + (16 * ks + lrow + (lsel >> 1) * 8) * HLD + 64 * warp + 16 * mt + (lsel & 1) * 8);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          if (64 * chunk + 16 * np < h.d_in) {  // warp-uniform; the tile is zero padded to a multiple of 32 columns
+            uint32_t b[4];
+            ldsm4t(b, Xs + (16 * ks + lrow + (lsel & 1) * 8) * XLD + 64 * chunk + 16 * np + (lsel >> 1) * 8);
+            mma16816(acc[2 * np], a, b[0], b[1]);
+            mma16816(acc[2 * np + 1], a, b[2], b[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int k = 64 * chunk + 8 * n + 2 * t;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int j = 64 * warp + 16 * mt + g + 8 * half;
+          if (k < h.d_in) atomicAdd(h.gw1 + (size_t)j * h.d_in + k, acc[n][2 * half]);
+          if (k + 1 < h.d_in) atomicAdd(h.gw1 + (size_t)j * h.d_in + k + 1, acc[n][2 * half + 1]);
+        }
+      }
+    }
+  }
+}
+
+struct Tiles {
+  __nv_bfloat16 *Xs, *Hs, *dHs, *dYs;
+  float* Fs;
+  float* red;  // [3][64]
+};
+constexpr size_t FWD_SMEM = (size_t)RT * XLD * 2 + (size_t)RT * HLD * 2 + (size_t)RT * FLD * 4;
+constexpr size_t BWD_SMEM = (size_t)RT * XLD * 2 + 2 * (size_t)RT * HLD * 2 + (size_t)RT * DYLD * 2 + (size_t)RT * FLD * 4 +
+                            3 * 64 * 4;
+MZ_DEV Tiles carve(unsigned char* base, bool backward) {
+  Tiles t;
+  t.Xs = reinterpret_cast<__nv_bfloat16*>(base);
+  t.Hs = t.Xs + RT * XLD;
+  unsigned char* p = reinterpret_cast<unsigned char*>(t.Hs + RT * HLD);
+  t.dHs = nullptr;
+  t.dYs = nullptr;
+  if (backward) {
+    t.dHs = reinterpret_cast<__nv_bfloat16*>(p);
+    t.dYs = t.dHs + RT * HLD;
+    p = reinterpret_cast<unsigned char*>(t.dYs + RT * DYLD);
+  }
+  t.Fs = reinterpret_cast<float*>(p);
+  t.red = t.Fs + RT * FLD;
+  return t;
+}
+
+// ---- the output heads: one job per blockIdx.y --------------------------------------------------------------------
+__global__ void __launch_bounds__(NTH) heads_fwd_kernel(PlainParams p) {
+  extern __shared__ __align__(16) unsigned char tc_smem[];
+  const mz_tc_job& job = p.jobs[blockIdx.y];
+  const int row0 = blockIdx.x * RT;
+  if (row0 >= job.rows) return;
+  const Tiles s = carve(tc_smem, false);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  load_rows(s.Xs, XLD, job.x, job.ldx, row0, job.rows, job.head.d_in, round_up32(job.head.d_in));
+  __syncthreads();
+  uint32_t mask[2];
+  hidden_phase(job.head, s.Xs, s.Hs, mask, warp, lane);
+  __syncthreads();
+  output_phase(job.head, s.Hs, job.y, job.ldy, row0, job.rows, nullptr, warp, lane);
+}
+
+__global__ void __launch_bounds__(NTH) heads_bwd_kernel(PlainParams p) {
+  extern __shared__ __align__(16) unsigned char tc_smem[];
+  const mz_tc_job& job = p.jobs[blockIdx.y];
+  const int row0 = blockIdx.x * RT;
+  if (row0 >= job.rows) return;
+  const Tiles s = carve(tc_smem, true);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const mz_tc_head& h = job.head;
+  load_rows(s.Xs, XLD, job.x, job.ldx, row0, job.rows, h.d_in, round_up32(h.d_in));
+  load_rows(s.dYs, DYLD, job.dy, job.ldy, row0, job.rows, h.d_out, round_up32(h.d_out));
+  if ((int)threadIdx.x < h.d_out) {  // gb2[o] = sum_r dY[r][o]
+    float sum = 0.0f;
+    for (int r = 0; r < RT && row0 + r < job.rows; ++r) sum += job.dy[(size_t)(row0 + r) * job.ldy + threadIdx.x];
+    atomicAdd(h.gb2 + threadIdx.x, sum);
+  }
+  __syncthreads();
+  backward_tile(h, s.Xs, s.dYs, s.Hs, s.dHs, job.dx, job.lddx, job.dx != nullptr ? h.d_in : 0, row0, job.rows, s.Fs, warp,
+                lane);
+}
+
+// ---- the recurrent chain ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTH) chain_fwd_kernel(mz_tc_chain c) {
+  extern __shared__ __align__(16) unsigned char tc_smem[];
+  const int row0 = blockIdx.x * RT;
+  const Tiles s = carve(tc_smem, false);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = c.d, A = c.num_actions, next_pad = round_up32(d + A);
+  load_rows(s.Xs, XLD, c.x0, c.ldx0, row0, c.rows, c.first.d_in, round_up32(c.first.d_in));
+  __syncthreads();
+  for (int step = 0; step < c.steps; ++step) {
+    const mz_tc_head& h = step ? c.next : c.first;
+    uint32_t mask[2];
+    hidden_phase(h, s.Xs, s.Hs, mask, warp, lane);
+    __syncthreads();
+    output_phase(h, s.Hs, nullptr, 0, row0, c.rows, s.Fs, warp, lane);
+    __syncthreads();
+    // LayerNorm (networks.py:144, eps 1e-5, biased variance) + ReLU, one-hot action appended: the next step's input
+    for (int r = 4 * warp; r < 4 * warp + 4; ++r) {
+      const int row = row0 + r;
+      const bool live = row < c.rows;
+      const float v0 = lane < d ? s.Fs[r * FLD + lane] : 0.0f, v1 = lane + 32 < d ? s.Fs[r * FLD + lane + 32] : 0.0f;
+      float sum = v0 + v1;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) sum += __shfl_xor_sync(MZ_FULL, sum, m);
+      const float mean = sum / (float)d;
+      const float c0 = lane < d ? v0 - mean : 0.0f, c1 = lane + 32 < d ? v1 - mean : 0.0f;
+      float q = c0 * c0 + c1 * c1;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) q += __shfl_xor_sync(MZ_FULL, q, m);
+      const float rstd = 1.0f / sqrtf(q / (float)d + 1e-5f);
+      const int act = (live && c.actions != nullptr && step < c.action_steps)
+                          ? c.actions[(size_t)row * c.action_stride + step] : -1;
+      const size_t grow = (size_t)step * c.rows + row;
+      for (int col = lane; col < next_pad; col += 32) {
+        float out = 0.0f;
+        if (col < d) {
+          const float cen = col < 32 ? c0 : c1;
+          out = fmaxf(cen * rstd * __ldg(c.gamma + col) + __ldg(c.beta + col), 0.0f);
+          if (live) c.yall[grow * d + col] = col < 32 ? v0 : v1;
+        } else if (col < d + A) {
+          out = (col - d == act) ? 1.0f : 0.0f;
+        }
+        if (live && col < d + A) c.xs[grow * c.ldxs + col] = out;
+        s.Xs[r * XLD + col] = __float2bfloat16_rn(live ? out : 0.0f);
+      }
+      if (live && lane == 0) {
+        c.mean[grow] = mean;
+        c.rstd[grow] = rstd;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(NTH) chain_bwd_kernel(mz_tc_chain c) {
+  extern __shared__ __align__(16) unsigned char tc_smem[];
+  const int row0 = blockIdx.x * RT;
+  const Tiles s = carve(tc_smem, true);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = c.d, A = c.num_actions;
+  if (threadIdx.x < 3 * 64) s.red[threadIdx.x] = 0.0f;
+  __syncthreads();
+  float gg[2] = {0.0f, 0.0f}, gb[2] = {0.0f, 0.0f};  // LayerNorm weight / bias gradients of columns lane, lane + 32
+  for (int step = c.steps - 1; step >= 0; --step) {
+    const mz_tc_head& h = step ? c.next : c.first;
+    if (step) load_rows(s.Xs, XLD, c.xs + (size_t)(step - 1) * c.rows * c.ldxs, c.ldxs, row0, c.rows, d + A, round_up32(d + A));
+    else load_rows(s.Xs, XLD, c.x0, c.ldx0, row0, c.rows, h.d_in, round_up32(h.d_in));
+    // backward of relu(LayerNorm(y)) for this step's hidden state: gradient = heads' part (+ the dynamics head's dX of
+    // the step after), scaled by the hook (learners.py:201) for the states the dynamics produced
+    const float scale = step ? c.hook_scale : 1.0f;
+    const int out_pad = round_up32(d);
+    float b2sum[2] = {0.0f, 0.0f};
+    for (int r = 4 * warp; r < 4 * warp + 4; ++r) {
+      const int row = row0 + r;
+      const bool live = row < c.rows;
+      const size_t grow = (size_t)step * c.rows + row;
+      float gi[2], xh[2], dxh[2];
+      const float mean = live ? c.mean[grow] : 0.0f, rstd = live ? c.rstd[grow] : 0.0f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = lane + 32 * u;
+        gi[u] = xh[u] = dxh[u] = 0.0f;
+        if (live && i < d) {
+          float up = c.dxs[grow * c.ldxs + i];
+          if (step + 1 < c.steps) up += s.Fs[r * FLD + i];
+          gi[u] = c.xs[grow * c.ldxs + i] > 0.0f ? up * scale : 0.0f;
+          xh[u] = (c.yall[grow * d + i] - mean) * rstd;
+          dxh[u] = gi[u] * __ldg(c.gamma + i);
+        }
+      }
+      float s1 = dxh[0] + dxh[1], s2 = dxh[0] * xh[0] + dxh[1] * xh[1];
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        s1 += __shfl_xor_sync(MZ_FULL, s1, m);
+        s2 += __shfl_xor_sync(MZ_FULL, s2, m);
+      }
+      const float m1 = s1 / (float)d, m2 = s2 / (float)d;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = lane + 32 * u;
+        const float dy = (live && i < d) ? rstd * (dxh[u] - m1 - xh[u] * m2) : 0.0f;
+        if (i < out_pad) s.dYs[r * DYLD + i] = __float2bfloat16_rn(dy);
+        b2sum[u] += dy;
+        gg[u] += gi[u] * xh[u];
+        gb[u] += gi[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (lane + 32 * u < d) atomicAdd(&s.red[lane + 32 * u], b2sum[u]);
+    __syncthreads();
+    if ((int)threadIdx.x < d) {
+      atomicAdd(h.gb2 + threadIdx.x, s.red[threadIdx.x]);
+      s.red[threadIdx.x] = 0.0f;
+    }
+    backward_tile(h, s.Xs, s.dYs, s.Hs, s.dHs, nullptr, 0, step ? d : 0, row0, c.rows, s.Fs, warp, lane);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (lane + 32 * u < d) {
+      atomicAdd(&s.red[64 + lane + 32 * u], gg[u]);
+      atomicAdd(&s.red[128 + lane + 32 * u], gb[u]);
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < d) {
+    atomicAdd(c.ggamma + threadIdx.x, s.red[64 + threadIdx.x]);
+    atomicAdd(c.gbeta + threadIdx.x, s.red[128 + threadIdx.x]);
+  }
+}
+
+bool g_tc_attr = false;
+int tc_attrs() {
+  if (g_tc_attr) return 0;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM)) != cudaSuccess)
+    return (int)e;
+  g_tc_attr = true;
+  return 0;
+}
+
+bool head_ok(const mz_tc_head& h, bool backward) {
+  if (h.d_in < 1 || h.d_in > 128 || h.d_out < 1 || h.d_out > 64 || !h.w1p || !h.w2p || !h.b1 || !h.b2) return false;
+  if (backward && (!h.w2tp || !h.w1tp || !h.gw1 || !h.gb1 || !h.gw2 || !h.gb2)) return false;
+  return true;
+}
+
+bool chain_ok(const mz_tc_chain* c, bool backward) {
+  if (!c || c->rows < 1 || c->steps < 1 || c->d < 1 || c->d > 64 || c->num_actions < 0 || c->d + c->num_actions > 128) return false;
+  if (!head_ok(c->first, backward) || c->first.d_out != c->d) return false;
+  if (c->steps > 1 && (!head_ok(c->next, backward) || c->next.d_out != c->d || c->next.d_in != c->d + c->num_actions)) return false;
+  if (!c->x0 || c->ldx0 < c->first.d_in || !c->gamma || !c->beta || !c->xs || c->ldxs < c->d + c->num_actions || !c->yall ||
+      !c->mean || !c->rstd)
+    return false;
+  if (c->actions && (c->action_stride < c->action_steps || c->action_steps < 0)) return false;
+  if (backward && (!c->dxs || !c->ggamma || !c->gbeta)) return false;
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t mz_learner_packed_words(int32_t n, int32_t k) {
+  if (n < 1 || k < 1) return 0;
+  return (int64_t)((n + 7) / 8) * ((k + 31) / 32) * 128;
+}
+
+int mz_learner_pack(int32_t njobs, const mz_pack_job* jobs, void* stream) {
+  if (njobs < 1 || njobs > MAXPACK || !jobs) return MZ_ERR_BAD_ARG;
+  PackParams p;
+  int64_t most = 0;
+  for (int i = 0; i < njobs; ++i) {
+    if (!jobs[i].src || !jobs[i].dst || jobs[i].n < 1 || jobs[i].k < 1) return MZ_ERR_BAD_ARG;
+    p.jobs[i] = jobs[i];
+    const int64_t w = mz_learner_packed_words(jobs[i].n, jobs[i].k);
+    most = w > most ? w : most;
+  }
+  int blocks = (int)((most + 1023) / 1024);
+  blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
+  pack_kernel<<<dim3(blocks, njobs), 256, 0, (cudaStream_t)stream>>>(p);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+int mz_heads_forward_tc(int32_t njobs, const mz_tc_job* jobs, void* stream) {
+  if (njobs < 1 || njobs > MAXJOBS || !jobs) return MZ_ERR_BAD_ARG;
+  PlainParams p;
+  int most = 0;
+  for (int i = 0; i < njobs; ++i) {
+    const mz_tc_job& j = jobs[i];
+    if (!head_ok(j.head, false) || j.rows < 1 || !j.x || !j.y || j.ldx < j.head.d_in || j.ldy < j.head.d_out) return MZ_ERR_BAD_ARG;
+    p.jobs[i] = j;
+    most = j.rows > most ? j.rows : most;
+  }
+  if (int rc = tc_attrs()) return rc;
+  heads_fwd_kernel<<<dim3((most + RT - 1) / RT, njobs), NTH, FWD_SMEM, (cudaStream_t)stream>>>(p);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+int mz_heads_backward_tc(int32_t njobs, const mz_tc_job* jobs, void* stream) {
+  if (njobs < 1 || njobs > MAXJOBS || !jobs) return MZ_ERR_BAD_ARG;
+  PlainParams p;
+  int most = 0;
+  for (int i = 0; i < njobs; ++i) {
+    const mz_tc_job& j = jobs[i];
+    if (!head_ok(j.head, true) || j.rows < 1 || !j.x || !j.dy || j.ldx < j.head.d_in || j.ldy < j.head.d_out ||
+        (j.dx && j.lddx < j.head.d_in))
+      return MZ_ERR_BAD_ARG;
+    p.jobs[i] = j;
+    most = j.rows > most ? j.rows : most;
+  }
+  if (int rc = tc_attrs()) return rc;
+  heads_bwd_kernel<<<dim3((most + RT - 1) / RT, njobs), NTH, BWD_SMEM, (cudaStream_t)stream>>>(p);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+int mz_chain_forward_tc(const mz_tc_chain* chain, void* stream) {
+  if (!chain_ok(chain, false)) return MZ_ERR_BAD_ARG;
+  if (int rc = tc_attrs()) return rc;
+  chain_fwd_kernel<<<(chain->rows + RT - 1) / RT, NTH, FWD_SMEM, (cudaStream_t)stream>>>(*chain);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+int mz_chain_backward_tc(const mz_tc_chain* chain, void* stream) {
+  if (!chain_ok(chain, true)) return MZ_ERR_BAD_ARG;
+  if (int rc = tc_attrs()) return rc;
+  chain_bwd_kernel<<<(chain->rows + RT - 1) / RT, NTH, BWD_SMEM, (cudaStream_t)stream>>>(*chain);
+  MZ_LAUNCH_CHECK();
+  return MZ_OK;
+}
+
+}  // extern "C"

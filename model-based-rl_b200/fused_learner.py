@@ -88,6 +88,22 @@ class FusedFCNetwork(object):
       off += WIDTH * h.d_out
       h.p = [self.views[k] for k in h.keys]
       h.g = [self.grads[k] for k in h.keys]
+    # bf16 mma B-operand images of the same matrices for the tensor-core kernels (csrc/mz_learner_tc.cu), refreshed
+    # every step from the float32 master weights by ONE launch
+    words = lambda n, k: int(self.lib.mz_learner_packed_words(n, k))
+    shapes = lambda h: [(WIDTH, h.d_in), (h.d_out, WIDTH), (WIDTH, h.d_out), (h.d_in, WIDTH)]  # (N, K) of w1p w2p w2tp w1tp
+    self.packed = torch.zeros(sum(words(n, k) for h in self.heads.values() for n, k in shapes(h)), dtype=torch.int32,
+                              device=self.device)
+    jobs, off = [], 0
+    for h in self.heads.values():
+      w1, w2 = h.p[0], h.p[2]
+      h.images = []
+      for (n, k), (src, sn, sk) in zip(shapes(h), [(w1, h.d_in, 1), (w2, WIDTH, 1), (w2, 1, WIDTH), (w1, 1, h.d_in)]):
+        dst = self.packed[off:off + words(n, k)]
+        off += words(n, k)
+        h.images.append(dst)
+        jobs.append(_lib.PackJob(src.data_ptr(), dst.data_ptr(), n, k, sn, sk))
+    self._pack_jobs = (_lib.PackJob * len(jobs))(*jobs)
     # the reference's initialisation: torch's defaults for nn.Linear / nn.LayerNorm
     ref = learners.FCNetworkTrain(self.input_dim, A, 'cpu', config)
     self.load_weights(ref.state_dict())
@@ -118,6 +134,17 @@ class FusedFCNetwork(object):
   def train(self, mode=True):
     return self
 
+  def tc_head(self, name):
+    """struct mz_tc_head of one head: packed images, float32 biases, gradient views."""
+    h = self.heads[name]
+    return _lib.TcHead(h.images[0].data_ptr(), h.images[1].data_ptr(), h.images[2].data_ptr(), h.images[3].data_ptr(),
+                       h.p[1].data_ptr(), h.p[3].data_ptr(), h.g[0].data_ptr(), h.g[1].data_ptr(), h.g[2].data_ptr(),
+                       h.g[3].data_ptr(), h.d_in, h.d_out)
+
+  @_lib.on_device
+  def refresh_packed(self):
+    _lib.check(self.lib.mz_learner_pack(len(self._pack_jobs), self._pack_jobs, _lib.current_stream()), "mz_learner_pack")
+
   @_lib.on_device
   def refresh_transposes(self):
     st = _lib.current_stream()
@@ -131,10 +158,13 @@ class FusedLearner(object):
   `PrioritizedReplay.sample_batch()` / `sample_batch_device()` returns, priority feedback, weight hand-off,
   schedules and checkpoint keys."""
 
-  def __init__(self, config, network, replay_buffer=None, search_network=None, use_graph=True):
+  def __init__(self, config, network, replay_buffer=None, search_network=None, use_graph=True, precision='bf16'):
     _lib.require_cuda()
     if not isinstance(network, FusedFCNetwork):
       raise TypeError("FusedLearner trains a FusedFCNetwork")
+    if precision not in ('bf16', 'f32'):
+      raise ValueError("precision is 'bf16' (tensor cores, float32 accumulation and master weights) or 'f32'")
+    self.precision = precision
     self.config, self.network, self.lib = config, network, _lib.load()
     self.device = network.device
     self.replay_buffer, self.search_network = replay_buffer, search_network
@@ -196,6 +226,23 @@ class FusedLearner(object):
     self.c_loss = _lib.LossCfg(B, K, A, self.loss_cfg['value_min'], self.loss_cfg['value_max'], self.loss_cfg['reward_min'],
                                self.loss_cfg['reward_max'], int(self.loss_cfg['no_target_transform']))
     self._shape, self._graphs = B, None
+    if self.precision == 'bf16':
+      self._alloc_tc()
+
+  def _alloc_tc(self):
+    """Argument structs of the four tensor-core launches (pointers into the buffers of this batch shape)."""
+    net, K, B, A, ldx = self.network, self.K, self.B, self.A, self.ldx
+    P = lambda t: t.data_ptr()
+    self.tc_chain = _lib.TcChain(net.tc_head('representation_head'), net.tc_head('transition_head'), B, K + 1, HIDDEN, A,
+                                 P(self.s_obs), net.input_dim, P(self.s_actions), max(K, 1), K, P(net.views['LN.weight']),
+                                 P(net.views['LN.bias']), P(self.xs), ldx, P(self.yall), P(self.mean), P(self.rstd),
+                                 P(self.dxs), 0.5, P(net.grads['LN.weight']), P(net.grads['LN.bias']))
+    V, R = self.v.shape[2], self.r.shape[2]
+    jobs = [_lib.TcJob(net.tc_head('value_head'), (K + 1) * B, ldx, V, ldx, P(self.xs), P(self.v), P(self.dv), P(self.dxs)),
+            _lib.TcJob(net.tc_head('policy_head'), (K + 1) * B, ldx, A, ldx, P(self.xs), P(self.p), P(self.dp), P(self.dxs))]
+    if K > 0:
+      jobs.append(_lib.TcJob(net.tc_head('reward_head'), K * B, ldx, R, ldx, P(self.xs), P(self.r), P(self.dr), P(self.dxs)))
+    self.tc_jobs = (_lib.TcJob * len(jobs))(*jobs)
 
   # -- launch sequences --------------------------------------------------------------------------------
   def _fwd(self, head, rows, x, ldx, y, ldy, st):
@@ -214,6 +261,17 @@ class FusedLearner(object):
     output heads (whose parameter gradients are then complete)."""
     net, lib, K, B, A, ldx = self.network, self.lib, self.K, self.B, self.A, self.ldx
     st = _lib.current_stream()
+    if self.precision == 'bf16':
+      net.refresh_packed()
+      net.grad.zero_()
+      self.dxs.zero_()
+      _lib.check(lib.mz_chain_forward_tc(self.tc_chain, st), "mz_chain_forward_tc")
+      _lib.check(lib.mz_heads_forward_tc(len(self.tc_jobs), self.tc_jobs, st), "mz_heads_forward_tc")
+      _lib.check(lib.mz_unroll_loss(self.c_loss, _P(self.v), _P(self.r), _P(self.p), _P(self.s_tv), _P(self.s_tr),
+                                    _P(self.s_tp), _P(self.s_isw), _P(self.dv), _P(self.dr), _P(self.dp), _P(self.rows),
+                                    _P(self.losses), _P(self.new_errors), st), "mz_unroll_loss")
+      _lib.check(lib.mz_heads_backward_tc(len(self.tc_jobs), self.tc_jobs, st), "mz_heads_backward_tc")
+      return
     ln_w, ln_b = net.views['LN.weight'], net.views['LN.bias']
     net.refresh_transposes()
     net.grad.zero_()
@@ -243,6 +301,9 @@ class FusedLearner(object):
     of every hidden state the dynamics produced."""
     net, lib, K, B, ldx = self.network, self.lib, self.K, self.B, self.ldx
     st = _lib.current_stream()
+    if self.precision == 'bf16':
+      _lib.check(lib.mz_chain_backward_tc(self.tc_chain, st), "mz_chain_backward_tc")
+      return
     ln_w = net.views['LN.weight']
     g_w, g_b = net.grads['LN.weight'], net.grads['LN.bias']
     xs, dxs = self.xs.view(K + 1, B, ldx), self.dxs.view(K + 1, B, ldx)

@@ -15,9 +15,10 @@ batch = ((r(B, E), torch.randint(0, A, (B, K), device=dev, generator=g),
           ((r(B, K + 1) < 0.1).float(), 4 * torch.randn(B, K + 1, device=dev, generator=g), pol / pol.sum(-1, keepdim=True))),
          None, r(B).double())
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for name in ("fused_graph", "fused_eager", "torch_graph"):
-  if name.startswith("fused"):
-    lr = fused_learner.FusedLearner(cfg, fused_learner.FusedFCNetwork(E, A, dev, cfg), use_graph=name.endswith("graph"))
+for name in ("bf16_graph", "bf16_eager", "f32_graph", "torch_graph"):
+  if not name.startswith("torch"):
+    lr = fused_learner.FusedLearner(cfg, fused_learner.FusedFCNetwork(E, A, dev, cfg), use_graph=name.endswith("graph"),
+                                    precision=name.split("_")[0])
   else:
     lr = learners.Learner(cfg, learners.FCNetworkTrain(E, A, dev, cfg), use_graph=True)
   for _ in range(5):

@@ -42,6 +42,8 @@ int main(void) {
   printf("%zu %zu %zu %zu\n", sizeof(mz_tree), sizeof(mz_fc_weights), sizeof(mz_window), sizeof(mz_target_cfg));
   printf("%zu %zu %zu %zu\n", offsetof(mz_tree, games), offsetof(mz_tree, leaf_action),
          offsetof(mz_fc_weights, rep_w1), offsetof(mz_target_cfg, discounts));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mz_pack_job), sizeof(mz_tc_head), sizeof(mz_tc_job), sizeof(mz_tc_chain),
+         offsetof(mz_tc_job, dx), offsetof(mz_tc_chain, hook_scale), offsetof(mz_tc_chain, gbeta));
   return 0;
 }'''
   with tempfile.TemporaryDirectory() as d:
@@ -52,8 +54,10 @@ int main(void) {
   sizes = [int(x) for x in out]
   assert sizes[:4] == [C.sizeof(_lib.Tree), C.sizeof(_lib.FcWeights), C.sizeof(_lib.Window),
                        C.sizeof(_lib.TargetCfg)]
-  assert sizes[4:] == [_lib.Tree.games.offset, _lib.Tree.leaf_action.offset,
-                       _lib.FcWeights.rep_w1.offset, _lib.TargetCfg.discounts.offset]
+  assert sizes[4:8] == [_lib.Tree.games.offset, _lib.Tree.leaf_action.offset,
+                        _lib.FcWeights.rep_w1.offset, _lib.TargetCfg.discounts.offset]
+  assert sizes[8:] == [C.sizeof(_lib.PackJob), C.sizeof(_lib.TcHead), C.sizeof(_lib.TcJob), C.sizeof(_lib.TcChain),
+                       _lib.TcJob.dx.offset, _lib.TcChain.hook_scale.offset, _lib.TcChain.gbeta.offset]
 
 
 def test_tree_geometry_and_pb_c_table_host_helpers():
@@ -81,6 +85,10 @@ def test_bad_arguments_are_rejected_without_a_gpu():
   for games in (1, 2, 4, 0):
     assert lib.mz_tree_set_games_per_block(games) == 0
   assert lib.mz_debug_set_targets_kernel(1) == 0 and lib.mz_debug_set_targets_kernel(0) == 0
+  assert lib.mz_learner_packed_words(512, 54) == 64 * 2 * 128 and lib.mz_learner_packed_words(31, 512) == 4 * 16 * 128
+  assert lib.mz_learner_pack(0, None, None) == -1 and lib.mz_heads_forward_tc(4, None, None) == -1
+  assert lib.mz_chain_forward_tc(C.byref(_lib.TcChain()), None) == -1
+  assert lib.mz_chain_backward_tc(C.byref(_lib.TcChain()), None) == -1
   w, c = _lib.Window(), _lib.TargetCfg()
   assert lib.mz_build_targets(C.byref(w), C.byref(c), None, None, None, None, None, None, None, None, None,
                               None, None, None) == -1
