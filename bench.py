@@ -958,7 +958,7 @@ def bench_concurrent(args, torch, dev, world, fs, net, barrier, flush):
   learner step is enqueued per move.  Reported: both rates alone and together, max over ranks."""
   import types
   import torch.distributed as dist
-  from model_based_rl_b200 import learners
+  from model_based_rl_b200 import fused_learner
   from model_based_rl_b200.replay_buffer import PrioritizedReplay
   from model_based_rl_b200.selfplay import HistorySlice
   G, S, A, D = args.games, args.sims, args.actions, args.obs_dim
@@ -980,8 +980,8 @@ def bench_concurrent(args, torch, dev, world, fs, net, barrier, flush):
                                  np.abs(rng.normal(size=L)).tolist(), [False] * L, list(range(L)), [None] * L, [1] * L),
                     ignore=None, terminal=True)
   torch.manual_seed(3)
-  learner = learners.Learner(cfg, learners.FCNetworkTrain(D, A, dev, cfg), replay_buffer=rb, search_network=net,
-                             use_graph=True)
+  learner = fused_learner.FusedLearner(cfg, fused_learner.FusedFCNetwork(D, A, dev, cfg), replay_buffer=rb,
+                                       search_network=net, use_graph=True, precision="bf16")
   main, side = torch.cuda.current_stream(), torch.cuda.Stream(device=dev)
   send_every = 25
 
@@ -1035,8 +1035,9 @@ def bench_concurrent(args, torch, dev, world, fs, net, barrier, flush):
   n_params = sum(p.numel() for p in learner.network.parameters())
   rate = lambda ms: world * G * S * n / (ms * 1e-3)
   return {
-      "workload": "C4 search (%d games x %d sims, A=%d per GPU) + C3-shaped learner (B=%d, K=%d, td=%d, AdamW, FCNetwork) "
-                  "on a side stream of the same GPU, one learner step enqueued per move, %d moves" % (G, S, A, B, K, T, n),
+      "workload": "C4 search (%d games x %d sims, A=%d per GPU) + C3-shaped learner (B=%d, K=%d, td=%d, AdamW, FCNetwork; "
+                  "FusedLearner: bf16 tensor-core forward / backward, bucketed gradient all-reduce overlapped with the "
+                  "recurrent backward) on a side stream of the same GPU, one learner step enqueued per move, %d moves" % (G, S, A, B, K, T, n),
       "ranks": world,
       "collectives": ("gradient all-reduce of %d float32 per learner step + weight broadcast every %d steps (NCCL)"
                       % (n_params, send_every)) if world > 1 else "none at one rank (weights handed to the search network "
@@ -1056,9 +1057,10 @@ def bench_concurrent(args, torch, dev, world, fs, net, barrier, flush):
 
 def bench_learner(torch, _lib, dev, world, barrier):
   """Learner.update_weights on the C3 shape: B=512, K=5, A=4, 128-float
-  observations, AdamW; device-resident synthetic batch.  Reports whole steps/s (network forward +
-  backward on cuBLAS, the fused loss, the optimiser, the gradient all-reduce at N > 1; max over
-  ranks) and the fused loss kernel alone against HBM."""
+  observations, AdamW; device-resident synthetic batch.  Reports whole steps/s of FusedLearner (network forward +
+  backward on the library's tensor-core kernels, the fused loss, the AdamW kernel, the gradient all-reduce at
+  N > 1; max over ranks), the same step on the float32 kernels and on torch modules (cuBLAS) beside it, and the
+  fused loss kernel alone against HBM."""
   import types
   import torch.distributed as dist
   from model_based_rl_b200 import learners
@@ -1072,18 +1074,21 @@ def bench_learner(torch, _lib, dev, world, barrier):
   batch = ((r(B, E), torch.randint(0, A, (B, K), device=dev, generator=g),
             ((r(B, K + 1) < 0.1).float(), 4 * torch.randn(B, K + 1, device=dev, generator=g),
              pol / pol.sum(-1, keepdim=True))), None, r(B).double())
-  torch.manual_seed(11)
-  net = learners.FCNetworkTrain(E, A, dev, cfg)
+  from model_based_rl_b200 import fused_learner
   a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   ms = {}
-  for mode in ("eager", "graph"):
-    net = learners.FCNetworkTrain(E, A, dev, cfg)
-    lr = learners.Learner(cfg, net, use_graph=(mode == "graph"))
+  for mode in ("torch_eager", "torch_graph", "fused_f32_graph", "fused_bf16_graph"):
+    torch.manual_seed(11)
+    if mode.startswith("torch"):
+      lr = learners.Learner(cfg, learners.FCNetworkTrain(E, A, dev, cfg), use_graph=mode.endswith("graph"))
+    else:
+      lr = fused_learner.FusedLearner(cfg, fused_learner.FusedFCNetwork(E, A, dev, cfg), use_graph=True,
+                                      precision=mode.split("_")[1])
     lr.send_weights()
     for _ in range(5):
       lr.update_weights(batch)
     barrier()
-    steps = 30
+    steps = 100 if mode == "fused_bf16_graph" else 30
     a.record()
     for _ in range(steps):
       lr.update_weights(batch)
@@ -1093,7 +1098,8 @@ def bench_learner(torch, _lib, dev, world, barrier):
     if world > 1:
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms[mode] = float(t.item()) / steps
-  ms_step = ms["graph"]
+    del lr
+  ms_step = ms["fused_bf16_graph"]
   # the loss kernel alone
   V = 31
   vl, rl, pl = torch.randn(K + 1, B, V, device=dev), torch.randn(K, B, V, device=dev), torch.randn(K + 1, B, A, device=dev)
@@ -1119,9 +1125,14 @@ def bench_learner(torch, _lib, dev, world, barrier):
   logit_bytes = 4 * (vl.numel() + rl.numel() + pl.numel())
   alg = 2 * logit_bytes + 4 * (2 * B * (K + 1) + t_p.numel()) + 8 * B + 8 * 3 * B + 4 * B
   return {"steps_per_s": 1e3 / ms_step, "samples_per_s": world * B * 1e3 / ms_step, "ms_per_step": ms_step,
-          "ms_per_step_eager": ms["eager"], "cuda_graph": True,
-          "workload": "C3 learner step: B=512 per GPU, K=5, A=4, obs 128 f32, FCNetwork, AdamW, f32 GEMMs (cuBLAS) + "
-                      "fused unroll loss; gradient all-reduce over %d rank(s)" % world,
+          "cuda_graph": True,
+          "workload": "C3 learner step: B=512 per GPU, K=5, A=4, obs 128 f32, FCNetwork, AdamW; FusedLearner: forward / "
+                      "backward on the library's tensor-core kernels (bf16 operands, f32 accumulation and master "
+                      "weights: chain, heads, heads backward, chain backward = 4 launches), fused unroll loss, own AdamW "
+                      "kernel; gradient all-reduce over %d rank(s)" % world,
+          "variants_ms_per_step": {"fused_bf16_cuda_graph": ms["fused_bf16_graph"], "fused_f32_cuda_graph": ms["fused_f32_graph"],
+                                   "torch_modules_cublas_f32_cuda_graph": ms["torch_graph"],
+                                   "torch_modules_cublas_f32_eager": ms["torch_eager"]},
           "loss_kernel": {"us_per_launch": us, "algorithmic_bytes": alg, "achieved_gbs": alg / us / 1e3,
                           "launches": 2}}
 

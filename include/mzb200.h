@@ -674,8 +674,13 @@ int mz_heads_backward_tc(int32_t njobs, const mz_tc_job* jobs, void* stream);
 /* The recurrent part: step 0 = `first` (representation) on x0, steps 1..steps-1 = `next` (dynamics) on the row
  * [hidden | one_hot(action)] the step before produced.  Per step s: yall[s] = head output (pre-LayerNorm),
  * mean / rstd[s], xs[s][r] = [relu(LN(yall[s][r])) (d values) | one_hot(actions[r * action_stride + s]) for
- * s < action_steps, zeros after].  Backward: dxs[s][r][0:d] = gradient of xs[s] from the output heads; the states
- * the dynamics produced get hook_scale (learners.py:201); ggamma / gbeta and the heads' gradients are accumulated. */
+ * s < action_steps, zeros after]; relu_mask (NULL in inference): the sign bits of the dynamics heads' 512-wide
+ * activations in the kernels' fragment order, mz_chain_mask_words(rows, steps) words, for the backward.
+ * Backward (the serial part only): dxs[s][r][0:d] = gradient of xs[s] from the output heads; the states the
+ * dynamics produced get hook_scale (learners.py:201); per step LayerNorm backward -> dyall[s] (gradient of yall[s])
+ * -> dX of the dynamics head -> the step before.  ggamma / gbeta are accumulated here; the parameter gradients of
+ * `first` / `next` follow from mz_heads_backward_tc over (x0, dyall[0]) and (xs[0 .. steps-2], dyall[1 .. steps-1])
+ * -- all rows in parallel instead of on the chain. */
 typedef struct mz_tc_chain {
   mz_tc_head first, next;
   int32_t rows, steps, d, num_actions;
@@ -687,10 +692,13 @@ typedef struct mz_tc_chain {
   float* xs;
   int32_t ldxs; /* >= d + num_actions */
   float *yall, *mean, *rstd;
+  uint32_t* relu_mask;
   const float* dxs; /* backward */
   float hook_scale;
   float *ggamma, *gbeta;
+  float* dyall; /* [steps][rows][d] */
 } mz_tc_chain;
+int64_t mz_chain_mask_words(int32_t rows, int32_t steps);
 int mz_chain_forward_tc(const mz_tc_chain* chain, void* stream);
 int mz_chain_backward_tc(const mz_tc_chain* chain, void* stream);
 

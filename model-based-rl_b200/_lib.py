@@ -111,7 +111,8 @@ class TcChain(C.Structure):
               ("num_actions", C.c_int32), ("x0", C.c_void_p), ("ldx0", C.c_int32), ("actions", C.c_void_p),
               ("action_stride", C.c_int32), ("action_steps", C.c_int32), ("gamma", C.c_void_p), ("beta", C.c_void_p),
               ("xs", C.c_void_p), ("ldxs", C.c_int32), ("yall", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
-              ("dxs", C.c_void_p), ("hook_scale", C.c_float), ("ggamma", C.c_void_p), ("gbeta", C.c_void_p)]
+              ("relu_mask", C.c_void_p), ("dxs", C.c_void_p), ("hook_scale", C.c_float), ("ggamma", C.c_void_p),
+              ("gbeta", C.c_void_p), ("dyall", C.c_void_p)]
 
 
 _V = C.c_void_p
@@ -181,6 +182,7 @@ _SIGNATURES = {
     "mz_learner_transpose": (C.c_int, [C.c_int32, C.c_int32, _V, _V, _V]),
     "mz_adam_step": (C.c_int, [C.c_int64, _V, _V, _V, _V, _V, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                C.c_float, C.c_float, _V]),
+    "mz_chain_mask_words": (C.c_int64, [C.c_int32, C.c_int32]),
     "mz_learner_packed_words": (C.c_int64, [C.c_int32, C.c_int32]),
     "mz_learner_pack": (C.c_int, [C.c_int32, C.POINTER(PackJob), _V]),
     "mz_heads_forward_tc": (C.c_int, [C.c_int32, C.POINTER(TcJob), _V]),

@@ -145,12 +145,6 @@ MZ_DEV bool fs_divisor_ok(double d) {
   const unsigned h = (unsigned)__double2hiint(d), l = (unsigned)__double2loint(d);
   return fs_exp_in_fast_range(d) && !(((h & 0xfffffu) == 0xfffffu) && l == 0xffffffffu);
 }
-MZ_DEV double shfl4_f64(double v, int src) {  // within the four lanes of a game
-  int lo = __double2loint(v), hi = __double2hiint(v);
-  lo = __shfl_sync(MZ_FULL, lo, src, 4);
-  hi = __shfl_sync(MZ_FULL, hi, src, 4);
-  return __hiloint2double(hi, lo);
-}
 MZ_DEV double shfl4_xor_f64(double v, int m) {
   int lo = __double2loint(v), hi = __double2hiint(v);
   lo = __shfl_xor_sync(MZ_FULL, lo, m, 4);

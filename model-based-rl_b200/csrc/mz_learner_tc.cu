@@ -30,12 +30,25 @@ namespace {
 
 constexpr int LW = 512;    // hidden width of every head (networks.py:55-119)
 constexpr int RT = 32;     // rows per CTA
-constexpr int NTH = 256;   // threads per CTA: warp w owns hidden units [64 w, 64 w + 64)
+constexpr int NW = 16;             // warps per CTA: a CTA runs alone on its SM and every phase is a dependent chain
+constexpr int NTH = 32 * NW;       // threads per CTA
+constexpr int CW = LW / NW;        // hidden units per warp: warp w owns [CW w, CW w + CW)
+constexpr int NTW = CW / 8;        // n-tiles per warp
+constexpr int LPR = NW;            // LayerNorm phases: lanes per row (a warp owns 32 / LPR rows at once)
+constexpr int CPL = 64 / LPR;      // ... and columns per lane: lane (rr, cl) holds columns cl + LPR i, i < CPL
 constexpr int XLD = 136;   // bf16 per row of the input tile (<= 128 features; 272 B: ldmatrix rows 16 B apart mod 128)
 constexpr int HLD = 520;   // bf16 per row of the activation tiles
 constexpr int DYLD = 72;   // bf16 per row of the output-gradient tile (<= 64 outputs)
 constexpr int FLD = 68;    // floats per row of the float32 tile (layer-2 output / dX of the dynamics head)
 constexpr int MAXJOBS = 3, MAXPACK = 24;
+#ifndef MZ_TC_SKIP
+#define MZ_TC_SKIP 0  // diagnostics builds: 1 = weight-gradient atomics only for an impossible value, 2 = no weight-gradient phases, 4 = no dX phase
+#endif
+#if MZ_TC_SKIP & 1
+#define MZ_WG_ADD(p, v) do { if ((v) == 12345.678f) atomicAdd((p), (v)); } while (0)
+#else
+#define MZ_WG_ADD(p, v) atomicAdd((p), (v))
+#endif
 
 struct PlainParams {
   mz_tc_job jobs[MAXJOBS];
@@ -88,19 +101,19 @@ __global__ void pack_kernel(PackParams p) {
   }
 }
 
-// acc[2][8][4] += A (32 rows x 32 KQ, row-major bf16 in shared memory) * B (packed; n-tiles nt0 .. nt0 + 7)
-MZ_DEV void gemm_wide(float (&acc)[2][8][4], const __nv_bfloat16* As, int lda, const uint32_t* __restrict__ Bp, int KQ,
+// acc[2][NTW][4] += A (32 rows x 32 KQ, row-major bf16 in shared memory) * B (packed; n-tiles nt0 .. nt0 + NTW - 1)
+MZ_DEV void gemm_wide(float (&acc)[2][NTW][4], const __nv_bfloat16* As, int lda, const uint32_t* __restrict__ Bp, int KQ,
                       int nt0, int lane) {
   const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
   const uint4* bp = reinterpret_cast<const uint4*>(Bp) + (size_t)nt0 * KQ * 32 + lane;
-  uint4 b[8];
+  uint4 b[NTW];
 #pragma unroll
-  for (int n = 0; n < 8; ++n) b[n] = __ldg(bp + (size_t)n * KQ * 32);
+  for (int n = 0; n < NTW; ++n) b[n] = __ldg(bp + (size_t)n * KQ * 32);
   for (int kq = 0; kq < KQ; ++kq) {
-    uint4 bn[8];
+    uint4 bn[NTW];
     if (kq + 1 < KQ) {
 #pragma unroll
-      for (int n = 0; n < 8; ++n) bn[n] = __ldg(bp + ((size_t)n * KQ + kq + 1) * 32);
+      for (int n = 0; n < NTW; ++n) bn[n] = __ldg(bp + ((size_t)n * KQ + kq + 1) * 32);
     }
     uint32_t a[2][2][4];
 #pragma unroll
@@ -108,7 +121,7 @@ MZ_DEV void gemm_wide(float (&acc)[2][8][4], const __nv_bfloat16* As, int lda, c
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) ldsm4(a[ks][mt], As + (16 * mt + arow) * lda + 32 * kq + 16 * ks + acol);
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
+    for (int n = 0; n < NTW; ++n) {
       mma16816(acc[0][n], a[0][0], b[n].x, b[n].y);
       mma16816(acc[1][n], a[0][1], b[n].x, b[n].y);
       mma16816(acc[0][n], a[1][0], b[n].z, b[n].w);
@@ -116,7 +129,7 @@ MZ_DEV void gemm_wide(float (&acc)[2][8][4], const __nv_bfloat16* As, int lda, c
     }
     if (kq + 1 < KQ) {
 #pragma unroll
-      for (int n = 0; n < 8; ++n) b[n] = bn[n];
+      for (int n = 0; n < NTW; ++n) b[n] = bn[n];
     }
   }
 }
@@ -151,31 +164,87 @@ MZ_DEV void gemm_tall(float (&acc)[2][4], const __nv_bfloat16* As, int lda, cons
     for (int c = 0; c < 4; ++c) acc[mt][c] += acc2[mt][c];
 }
 
-// rows [row0, row0 + 32) x columns [0, d) of a float32 matrix -> bf16 tile, zeros up to column dpad and behind `rows`
+// rows [row0, row0 + 32) x columns [0, d) of a float32 matrix -> bf16 tile, zeros up to column dpad (a multiple of 32)
+// and behind `rows`.  A warp moves 32-column segments; all of a thread's loads are in flight before its first store.
 MZ_DEV void load_rows(__nv_bfloat16* Ts, int ld, const float* __restrict__ X, int ldx, int row0, int rows, int d, int dpad) {
-  for (int idx = threadIdx.x; idx < RT * dpad; idx += NTH) {
-    const int r = idx / dpad, c = idx - r * dpad;
-    const float v = (row0 + r < rows && c < d) ? X[(size_t)(row0 + r) * ldx + c] : 0.0f;
-    Ts[r * ld + c] = __float2bfloat16_rn(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int spr = dpad >> 5, segs = RT * spr;  // segments per row (1..4), in all (32..128)
+  constexpr int NI = 128 / NW;
+  float v[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int sg = warp + NW * i, r = sg / spr, c = 32 * (sg - r * spr) + lane;
+    v[i] = (sg < segs && row0 + r < rows && c < d) ? X[(size_t)(row0 + r) * ldx + c] : 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int sg = warp + NW * i, r = sg / spr, c = 32 * (sg - r * spr) + lane;
+    if (sg < segs) Ts[r * ld + c] = __float2bfloat16_rn(v[i]);
   }
 }
 
-// H = relu(W1 X + b1) for the warp's 64 hidden units -> Hs (bf16); returns the sign bits (bit 4 n + c of mask[mt])
+MZ_DEV void red4(float* p, const float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// A warp's 16 x 8 NT accumulator tile (C fragments: rows g, g + 8; columns 8 n + 2 t + {0, 1}) added to global memory:
+// element (r, c) -> dst[r * ld + c] for r < rows_ok, c < cols.  Eight rows at a time cross the warp's staging area and
+// leave as 16-byte vector reductions over whole lines (one red.v4 per lane moves 512 contiguous bytes per warp) where
+// the alignment allows: always when the rows are dense in memory (cols == ld: the eight rows are one span that starts
+// at a multiple of 8 ld floats), per row when ld and cols are multiples of 4; scalar atomics otherwise.
+// dst must be 16-byte aligned.
+template <int NT>
+MZ_DEV void tile_add(float* __restrict__ dst, int ld, int rows_ok, int cols, const float (&acc)[NT][4], float* stage, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const bool dense = cols == ld;
+  const int sld = dense ? cols : 68;  // staging row stride (68: 16-byte aligned rows, banks spread)
+  for (int half = 0; half < 2; ++half) {
+    if (8 * half >= rows_ok) break;  // warp-uniform
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const int c = 8 * n + 2 * t;
+      if (c < cols) stage[g * sld + c] = acc[n][2 * half];
+      if (c + 1 < cols) stage[g * sld + c + 1] = acc[n][2 * half + 1];
+    }
+    __syncwarp();
+    float* out = dst + (size_t)(8 * half) * ld;
+    const int live = min(8, rows_ok - 8 * half);
+    if (dense) {
+      const float4* s4 = reinterpret_cast<const float4*>(stage);
+      for (int i = lane; i < (live * cols) >> 2; i += 32) red4(out + 4 * i, s4[i]);
+      for (int i = ((live * cols) & ~3) + lane; i < live * cols; i += 32) atomicAdd(out + i, stage[i]);
+    } else if (((ld | cols) & 3) == 0) {
+      const int c4n = cols >> 2;
+      for (int i = lane; i < live * c4n; i += 32) {
+        const int r = i / c4n, c4 = i - r * c4n;
+        red4(out + (size_t)r * ld + 4 * c4, *reinterpret_cast<const float4*>(stage + r * sld + 4 * c4));
+      }
+    } else {
+      for (int i = lane; i < live * cols; i += 32) {
+        const int r = i / cols, c = i - r * cols;
+        atomicAdd(out + (size_t)r * ld + c, stage[r * sld + c]);
+      }
+    }
+  }
+}
+
+// H = relu(W1 X + b1) for the warp's CW hidden units -> Hs (bf16); returns the sign bits (bit 4 n + c of mask[mt])
 MZ_DEV void hidden_phase(const mz_tc_head& h, const __nv_bfloat16* Xs, __nv_bfloat16* Hs, uint32_t (&mask)[2], int warp,
                          int lane) {
-  float acc[2][8][4];
+  float acc[2][NTW][4];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int n = 0; n < 8; ++n)
+    for (int n = 0; n < NTW; ++n)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[mt][n][c] = 0.0f;
-  gemm_wide(acc, Xs, XLD, h.w1p, round_up32(h.d_in) >> 5, 8 * warp, lane);
+  gemm_wide(acc, Xs, XLD, h.w1p, round_up32(h.d_in) >> 5, NTW * warp, lane);
   const int g = lane >> 2, t = lane & 3;
   mask[0] = mask[1] = 0u;
 #pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    const int j = 64 * warp + 8 * n + 2 * t;
+  for (int n = 0; n < NTW; ++n) {
+    const int j = CW * warp + 8 * n + 2 * t;
     const float2 bb = make_float2(__ldg(h.b1 + j), __ldg(h.b1 + j + 1));  // views of a flat buffer: 4-byte aligned
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -222,22 +291,22 @@ MZ_DEV void output_phase(const mz_tc_head& h, const __nv_bfloat16* Hs, float* __
 // global memory (dX != nullptr) or left in Fs (dx_cols > 0, dX == nullptr).
 MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __nv_bfloat16* dYs, __nv_bfloat16* Hs,
                           __nv_bfloat16* dHs, float* __restrict__ dX, int lddx, int dx_cols, int row0, int rows, float* Fs,
-                          int warp, int lane) {
+                          float* stage, int warp, int lane) {
   const int g = lane >> 2, t = lane & 3;
   uint32_t mask[2];
   hidden_phase(h, Xs, Hs, mask, warp, lane);
   {  // dH = dY W2 for the warp's hidden units, masked by the ReLU; gb1; -> dHs
-    float acc[2][8][4];
+    float acc[2][NTW][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int n = 0; n < 8; ++n)
+      for (int n = 0; n < NTW; ++n)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[mt][n][c] = 0.0f;
-    gemm_wide(acc, dYs, DYLD, h.w2tp, round_up32(h.d_out) >> 5, 8 * warp, lane);
+    gemm_wide(acc, dYs, DYLD, h.w2tp, round_up32(h.d_out) >> 5, NTW * warp, lane);
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int j = 64 * warp + 8 * n + 2 * t;
+    for (int n = 0; n < NTW; ++n) {
+      const int j = CW * warp + 8 * n + 2 * t;
       float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
@@ -261,9 +330,9 @@ MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __
     }
   }
   __syncthreads();
-  // dX = dH W1: n-tiles w and w + 8 of the input features
-  if (dx_cols > 0) {
-    for (int nt = warp; 8 * nt < dx_cols; nt += 8) {
+  // dX = dH W1: n-tile w of the input features
+  if (dx_cols > 0 && !(MZ_TC_SKIP & 4)) {
+    for (int nt = warp; 8 * nt < dx_cols; nt += NW) {
       float acc[2][4];
       gemm_tall(acc, dHs, HLD, h.w1tp, nt, lane);
       const int k = 8 * nt + 2 * t;
@@ -285,12 +354,13 @@ MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __
       }
     }
   }
+  if (MZ_TC_SKIP & 2) return;
   const int lrow = lane & 7, lsel = lane >> 3;  // ldmatrix.trans: lanes 8 i .. 8 i + 7 address matrix i
   // gW2[o][j] = sum_r dY[r][o] H[r][j]: M = outputs (16 per m-tile), N = the warp's hidden units, K = the tile's rows
   for (int mt = 0; 16 * mt < h.d_out; ++mt) {
-    float acc[8][4];
+    float acc[NTW][4];
 #pragma unroll
-    for (int n = 0; n < 8; ++n)
+    for (int n = 0; n < NTW; ++n)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[n][c] = 0.0f;
 #pragma unroll
@@ -298,28 +368,17 @@ MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __
       uint32_t a[4];
       ldsm4t(a, dYs + (16 * ks + lrow + (lsel >> 1) * 8) * DYLD + 16 * mt + (lsel & 1) * 8);
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {
+      for (int np = 0; np < NTW / 2; ++np) {
         uint32_t b[4];
-        ldsm4t(b, Hs + (16 * ks + lrow + (lsel & 1) * 8) * HLD + 64 * warp + 16 * np + (lsel >> 1) * 8);
+        ldsm4t(b, Hs + (16 * ks + lrow + (lsel & 1) * 8) * HLD + CW * warp + 16 * np + (lsel >> 1) * 8);
         mma16816(acc[2 * np], a, b[0], b[1]);
         mma16816(acc[2 * np + 1], a, b[2], b[3]);
       }
     }
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int j = 64 * warp + 8 * n + 2 * t;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int o = 16 * mt + g + 8 * half;
-        if (o < h.d_out) {
-          atomicAdd(h.gw2 + (size_t)o * LW + j, acc[n][2 * half]);
-          atomicAdd(h.gw2 + (size_t)o * LW + j + 1, acc[n][2 * half + 1]);
-        }
-      }
-    }
+    tile_add<NTW>(h.gw2 + (size_t)(16 * mt) * LW + CW * warp, LW, h.d_out - 16 * mt, CW, acc, stage, lane);
   }
   // gW1[j][k] = sum_r dH[r][j] X[r][k]: M = the warp's hidden units, N = input features in chunks of 64, K = rows
-  for (int mt = 0; mt < 4; ++mt) {
+  for (int mt = 0; mt < CW / 16; ++mt) {
     for (int chunk = 0; 64 * chunk < h.d_in; ++chunk) {
       float acc[8][4];
 #pragma unroll
@@ -329,7 +388,7 @@ MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         uint32_t a[4];
-        ldsm4t(a, dHs + (16 * ks + lrow + (lsel >> 1) * 8) * HLD + 64 * warp + 16 * mt + (lsel & 1) * 8);
+        ldsm4t(a, dHs + (16 * ks + lrow + (lsel >> 1) * 8) * HLD + CW * warp + 16 * mt + (lsel & 1) * 8);
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
           if (64 * chunk + 16 * np < h.d_in) {  // warp-uniform; the tile is zero padded to a multiple of 32 columns
@@ -340,16 +399,8 @@ MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __
           }
         }
       }
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        const int k = 64 * chunk + 8 * n + 2 * t;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int j = 64 * warp + 16 * mt + g + 8 * half;
-          if (k < h.d_in) atomicAdd(h.gw1 + (size_t)j * h.d_in + k, acc[n][2 * half]);
-          if (k + 1 < h.d_in) atomicAdd(h.gw1 + (size_t)j * h.d_in + k + 1, acc[n][2 * half + 1]);
-        }
-      }
+      tile_add<8>(h.gw1 + (size_t)(CW * warp + 16 * mt) * h.d_in + 64 * chunk, h.d_in, 16, min(64, h.d_in - 64 * chunk), acc,
+                  stage, lane);
     }
   }
 }
@@ -357,11 +408,13 @@ MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __
 struct Tiles {
   __nv_bfloat16 *Xs, *Hs, *dHs, *dYs;
   float* Fs;
-  float* red;  // [3][64]
+  float* red;    // [4][64]
+  float* stage;  // [NW][STAGE]
 };
+constexpr int STAGE = 8 * 68;  // floats per warp: eight rows of a weight-gradient tile
 constexpr size_t FWD_SMEM = (size_t)RT * XLD * 2 + (size_t)RT * HLD * 2 + (size_t)RT * FLD * 4;
 constexpr size_t BWD_SMEM = (size_t)RT * XLD * 2 + 2 * (size_t)RT * HLD * 2 + (size_t)RT * DYLD * 2 + (size_t)RT * FLD * 4 +
-                            3 * 64 * 4;
+                            4 * 64 * 4 + NW * STAGE * 4;
 MZ_DEV Tiles carve(unsigned char* base, bool backward) {
   Tiles t;
   t.Xs = reinterpret_cast<__nv_bfloat16*>(base);
@@ -376,6 +429,7 @@ MZ_DEV Tiles carve(unsigned char* base, bool backward) {
   }
   t.Fs = reinterpret_cast<float*>(p);
   t.red = t.Fs + RT * FLD;
+  t.stage = t.red + 4 * 64;
   return t;
 }
 
@@ -406,146 +460,238 @@ __global__ void __launch_bounds__(NTH) heads_bwd_kernel(PlainParams p) {
   load_rows(s.Xs, XLD, job.x, job.ldx, row0, job.rows, h.d_in, round_up32(h.d_in));
   load_rows(s.dYs, DYLD, job.dy, job.ldy, row0, job.rows, h.d_out, round_up32(h.d_out));
   if ((int)threadIdx.x < h.d_out) {  // gb2[o] = sum_r dY[r][o]
-    float sum = 0.0f;
-    for (int r = 0; r < RT && row0 + r < job.rows; ++r) sum += job.dy[(size_t)(row0 + r) * job.ldy + threadIdx.x];
-    atomicAdd(h.gb2 + threadIdx.x, sum);
+    float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+      if (row0 + r < job.rows) part[r & 3] += job.dy[(size_t)(row0 + r) * job.ldy + threadIdx.x];
+    atomicAdd(h.gb2 + threadIdx.x, (part[0] + part[1]) + (part[2] + part[3]));
   }
   __syncthreads();
-  backward_tile(h, s.Xs, s.dYs, s.Hs, s.dHs, job.dx, job.lddx, job.dx != nullptr ? h.d_in : 0, row0, job.rows, s.Fs, warp,
-                lane);
+  backward_tile(h, s.Xs, s.dYs, s.Hs, s.dHs, job.dx, job.lddx, job.dx != nullptr ? h.d_in : 0, row0, job.rows, s.Fs,
+                s.stage + warp * STAGE, warp, lane);
 }
 
 // ---- the recurrent chain ---------------------------------------------------------------------------------------
+// LayerNorm phases: a warp owns 32 / LPR rows at once, LPR lanes per row; lane (rr, c8) holds columns c8 + LPR i
+// (i < CPL) of its row, so the row statistics are log2(LPR) shuffle steps and the rows run side by side.
 __global__ void __launch_bounds__(NTH) chain_fwd_kernel(mz_tc_chain c) {
   extern __shared__ __align__(16) unsigned char tc_smem[];
   const int row0 = blockIdx.x * RT;
   const Tiles s = carve(tc_smem, false);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = c.d, A = c.num_actions, next_pad = round_up32(d + A);
+  const int r = (32 / LPR) * warp + lane / LPR, c8 = lane % LPR, row = row0 + r;
+  const bool live = row < c.rows;
+  const float inv_d = 1.0f / (float)d;
+  float gam[CPL], bet[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int col = c8 + LPR * i;
+    gam[i] = col < d ? __ldg(c.gamma + col) : 0.0f;
+    bet[i] = col < d ? __ldg(c.beta + col) : 0.0f;
+  }
   load_rows(s.Xs, XLD, c.x0, c.ldx0, row0, c.rows, c.first.d_in, round_up32(c.first.d_in));
   __syncthreads();
   for (int step = 0; step < c.steps; ++step) {
     const mz_tc_head& h = step ? c.next : c.first;
+    const int act = (live && c.actions != nullptr && step < c.action_steps)
+                        ? __ldg(c.actions + (size_t)row * c.action_stride + step) : -1;  // in flight during the head
     uint32_t mask[2];
     hidden_phase(h, s.Xs, s.Hs, mask, warp, lane);
+    if (step && c.relu_mask != nullptr)  // the backward chain gates dH with these bits instead of recomputing the layer
+      reinterpret_cast<uint2*>(c.relu_mask)[((size_t)step * gridDim.x + blockIdx.x) * NTH + threadIdx.x] = make_uint2(mask[0], mask[1]);
     __syncthreads();
     output_phase(h, s.Hs, nullptr, 0, row0, c.rows, s.Fs, warp, lane);
     __syncthreads();
     // LayerNorm (networks.py:144, eps 1e-5, biased variance) + ReLU, one-hot action appended: the next step's input
-    for (int r = 4 * warp; r < 4 * warp + 4; ++r) {
-      const int row = row0 + r;
-      const bool live = row < c.rows;
-      const float v0 = lane < d ? s.Fs[r * FLD + lane] : 0.0f, v1 = lane + 32 < d ? s.Fs[r * FLD + lane + 32] : 0.0f;
-      float sum = v0 + v1;
+    float v[CPL], sum = 0.0f;
 #pragma unroll
-      for (int m = 16; m > 0; m >>= 1) sum += __shfl_xor_sync(MZ_FULL, sum, m);
-      const float mean = sum / (float)d;
-      const float c0 = lane < d ? v0 - mean : 0.0f, c1 = lane + 32 < d ? v1 - mean : 0.0f;
-      float q = c0 * c0 + c1 * c1;
+    for (int i = 0; i < CPL; ++i) {
+      v[i] = c8 + LPR * i < d ? s.Fs[r * FLD + c8 + LPR * i] : 0.0f;
+      sum += v[i];
+    }
 #pragma unroll
-      for (int m = 16; m > 0; m >>= 1) q += __shfl_xor_sync(MZ_FULL, q, m);
-      const float rstd = 1.0f / sqrtf(q / (float)d + 1e-5f);
-      const int act = (live && c.actions != nullptr && step < c.action_steps)
-                          ? c.actions[(size_t)row * c.action_stride + step] : -1;
-      const size_t grow = (size_t)step * c.rows + row;
-      for (int col = lane; col < next_pad; col += 32) {
-        float out = 0.0f;
-        if (col < d) {
-          const float cen = col < 32 ? c0 : c1;
-          out = fmaxf(cen * rstd * __ldg(c.gamma + col) + __ldg(c.beta + col), 0.0f);
-          if (live) c.yall[grow * d + col] = col < 32 ? v0 : v1;
-        } else if (col < d + A) {
-          out = (col - d == act) ? 1.0f : 0.0f;
-        }
-        if (live && col < d + A) c.xs[grow * c.ldxs + col] = out;
-        s.Xs[r * XLD + col] = __float2bfloat16_rn(live ? out : 0.0f);
+    for (int m = 1; m < LPR; m <<= 1) sum += __shfl_xor_sync(MZ_FULL, sum, m);
+    const float mean = sum * inv_d;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const float cen = c8 + LPR * i < d ? v[i] - mean : 0.0f;
+      q += cen * cen;
+    }
+#pragma unroll
+    for (int m = 1; m < LPR; m <<= 1) q += __shfl_xor_sync(MZ_FULL, q, m);
+    const float rstd = rsqrtf(q * inv_d + 1e-5f);
+    const size_t grow = (size_t)step * c.rows + row;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int col = c8 + LPR * i;
+      float out = 0.0f;
+      if (col < d) {
+        out = fmaxf((v[i] - mean) * rstd * gam[i] + bet[i], 0.0f);
+        if (live) c.yall[grow * d + col] = v[i];
+      } else if (col < d + A) {
+        out = (col - d == act) ? 1.0f : 0.0f;
       }
-      if (live && lane == 0) {
-        c.mean[grow] = mean;
-        c.rstd[grow] = rstd;
-      }
+      if (live && col < d + A) c.xs[grow * c.ldxs + col] = out;
+      s.Xs[r * XLD + col] = __float2bfloat16_rn(live ? out : 0.0f);
+    }
+    for (int col = 64 + c8; col < next_pad; col += LPR) {  // d + A > 64 (A = 18): the rest of the one-hot
+      const float out = (col < d + A && col - d == act) ? 1.0f : 0.0f;
+      if (live && col < d + A) c.xs[grow * c.ldxs + col] = out;
+      s.Xs[r * XLD + col] = __float2bfloat16_rn(out);
+    }
+    if (live && c8 == 0) {
+      c.mean[grow] = mean;
+      c.rstd[grow] = rstd;
     }
     __syncthreads();
   }
 }
 
+// The serial part of the chain's backward: per step LayerNorm backward -> dY (kept in dyall for the weight gradients)
+// -> dH = dY W2 gated by the forward's ReLU bits -> dX = dH W1 -> next LayerNorm backward.  The parameter gradients of
+// the two heads do not sit on this chain: mz_heads_backward_tc computes them afterwards from (xs, dyall) over all
+// K B + B rows in parallel.
+struct LnIn {
+  float up[CPL], hv[CPL], yv[CPL], mean, rstd;
+};
+MZ_DEV void ln_load(LnIn& v, const mz_tc_chain& c, int step, int row, bool live, int c8) {
+  const size_t grow = (size_t)step * c.rows + row;
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int col = c8 + LPR * i;
+    const bool in = live && col < c.d;
+    v.up[i] = in ? c.dxs[grow * c.ldxs + col] : 0.0f;
+    v.hv[i] = in ? c.xs[grow * c.ldxs + col] : 0.0f;
+    v.yv[i] = in ? c.yall[grow * c.d + col] : 0.0f;
+  }
+  v.mean = live ? c.mean[grow] : 0.0f;
+  v.rstd = live ? c.rstd[grow] : 0.0f;
+}
+
 __global__ void __launch_bounds__(NTH) chain_bwd_kernel(mz_tc_chain c) {
   extern __shared__ __align__(16) unsigned char tc_smem[];
   const int row0 = blockIdx.x * RT;
-  const Tiles s = carve(tc_smem, true);
+  __nv_bfloat16* dYs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
+  __nv_bfloat16* dHs = dYs + RT * DYLD;
+  float* Fs = reinterpret_cast<float*>(dHs + RT * HLD);
+  float* red = Fs + RT * FLD;  // [2][64]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int d = c.d, A = c.num_actions;
-  if (threadIdx.x < 3 * 64) s.red[threadIdx.x] = 0.0f;
+  const int d = c.d, out_pad = round_up32(d);
+  const int r = (32 / LPR) * warp + lane / LPR, c8 = lane % LPR, row = row0 + r;
+  const bool live = row < c.rows;
+  const float inv_d = 1.0f / (float)d;
+  if (threadIdx.x < 2 * 64) red[threadIdx.x] = 0.0f;
   __syncthreads();
-  float gg[2] = {0.0f, 0.0f}, gb[2] = {0.0f, 0.0f};  // LayerNorm weight / bias gradients of columns lane, lane + 32
-  for (int step = c.steps - 1; step >= 0; --step) {
-    const mz_tc_head& h = step ? c.next : c.first;
-    if (step) load_rows(s.Xs, XLD, c.xs + (size_t)(step - 1) * c.rows * c.ldxs, c.ldxs, row0, c.rows, d + A, round_up32(d + A));
-    else load_rows(s.Xs, XLD, c.x0, c.ldx0, row0, c.rows, h.d_in, round_up32(h.d_in));
-    // backward of relu(LayerNorm(y)) for this step's hidden state: gradient = heads' part (+ the dynamics head's dX of
-    // the step after), scaled by the hook (learners.py:201) for the states the dynamics produced
-    const float scale = step ? c.hook_scale : 1.0f;
-    const int out_pad = round_up32(d);
-    float b2sum[2] = {0.0f, 0.0f};
-    for (int r = 4 * warp; r < 4 * warp + 4; ++r) {
-      const int row = row0 + r;
-      const bool live = row < c.rows;
-      const size_t grow = (size_t)step * c.rows + row;
-      float gi[2], xh[2], dxh[2];
-      const float mean = live ? c.mean[grow] : 0.0f, rstd = live ? c.rstd[grow] : 0.0f;
+  float gam[CPL], gg[CPL], gb[CPL];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int i = lane + 32 * u;
-        gi[u] = xh[u] = dxh[u] = 0.0f;
-        if (live && i < d) {
-          float up = c.dxs[grow * c.ldxs + i];
-          if (step + 1 < c.steps) up += s.Fs[r * FLD + i];
-          gi[u] = c.xs[grow * c.ldxs + i] > 0.0f ? up * scale : 0.0f;
-          xh[u] = (c.yall[grow * d + i] - mean) * rstd;
-          dxh[u] = gi[u] * __ldg(c.gamma + i);
+  for (int i = 0; i < CPL; ++i) {
+    gam[i] = c8 + LPR * i < d ? __ldg(c.gamma + c8 + LPR * i) : 0.0f;
+    gg[i] = gb[i] = 0.0f;
+  }
+  LnIn cur, nxt;
+  ln_load(cur, c, c.steps - 1, row, live, c8);
+  for (int step = c.steps - 1; step >= 0; --step) {
+    if (step) ln_load(nxt, c, step - 1, row, live, c8);  // in flight during this step's contractions
+    uint2 mbits = make_uint2(0u, 0u);
+    if (step) mbits = reinterpret_cast<const uint2*>(c.relu_mask)[((size_t)step * gridDim.x + blockIdx.x) * NTH + threadIdx.x];
+    // backward of relu(LayerNorm(y)): gradient = heads' part (+ the dynamics head's dX of the step after), scaled by
+    // the hook (learners.py:201) for the states the dynamics produced
+    const float scale = step ? c.hook_scale : 1.0f;
+    float gi[CPL], xh[CPL], s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int col = c8 + LPR * i;
+      float u = cur.up[i];
+      if (step + 1 < c.steps && col < d) u += Fs[r * FLD + col];
+      gi[i] = cur.hv[i] > 0.0f ? u * scale : 0.0f;
+      xh[i] = (cur.yv[i] - cur.mean) * cur.rstd;
+      const float dxh = gi[i] * gam[i];
+      s1 += dxh;
+      s2 += dxh * xh[i];
+    }
+#pragma unroll
+    for (int m = 1; m < LPR; m <<= 1) {
+      s1 += __shfl_xor_sync(MZ_FULL, s1, m);
+      s2 += __shfl_xor_sync(MZ_FULL, s2, m);
+    }
+    const float m1 = s1 * inv_d, m2 = s2 * inv_d;
+    const size_t grow = (size_t)step * c.rows + row;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int col = c8 + LPR * i;
+      const float dy = (live && col < d) ? cur.rstd * (gi[i] * gam[i] - m1 - xh[i] * m2) : 0.0f;
+      if (col < out_pad) dYs[r * DYLD + col] = __float2bfloat16_rn(dy);
+      if (live && col < d) c.dyall[grow * d + col] = dy;
+      gg[i] += gi[i] * xh[i];
+      gb[i] += gi[i];
+    }
+    if (step == 0) break;  // the representation head's input needs no gradient
+    __syncthreads();
+    {  // dH = dY W2 for the warp's hidden units, gated by the forward's ReLU bits -> dHs
+      const mz_tc_head& h = c.next;
+      const int g = lane >> 2, t = lane & 3;
+      float acc[2][NTW][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < NTW; ++n)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[mt][n][q] = 0.0f;
+      gemm_wide(acc, dYs, DYLD, h.w2tp, round_up32(h.d_out) >> 5, NTW * warp, lane);
+#pragma unroll
+      for (int n = 0; n < NTW; ++n) {
+        const int j = CW * warp + 8 * n + 2 * t;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint32_t m = (mt ? mbits.y : mbits.x) >> (4 * n);
+          *reinterpret_cast<uint32_t*>(dHs + (16 * mt + g) * HLD + j) =
+              pack2((m & 1u) ? acc[mt][n][0] : 0.0f, (m & 2u) ? acc[mt][n][1] : 0.0f);
+          *reinterpret_cast<uint32_t*>(dHs + (16 * mt + g + 8) * HLD + j) =
+              pack2((m & 4u) ? acc[mt][n][2] : 0.0f, (m & 8u) ? acc[mt][n][3] : 0.0f);
         }
       }
-      float s1 = dxh[0] + dxh[1], s2 = dxh[0] * xh[0] + dxh[1] * xh[1];
+      __syncthreads();
+      // dX = dH W1, the hidden-state columns only -> Fs
+      for (int nt = warp; 8 * nt < d; nt += NW) {
+        float a2[2][4];
+        gemm_tall(a2, dHs, HLD, h.w1tp, nt, lane);
+        const int k = 8 * nt + 2 * t;
 #pragma unroll
-      for (int m = 16; m > 0; m >>= 1) {
-        s1 += __shfl_xor_sync(MZ_FULL, s1, m);
-        s2 += __shfl_xor_sync(MZ_FULL, s2, m);
-      }
-      const float m1 = s1 / (float)d, m2 = s2 / (float)d;
+        for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int i = lane + 32 * u;
-        const float dy = (live && i < d) ? rstd * (dxh[u] - m1 - xh[u] * m2) : 0.0f;
-        if (i < out_pad) s.dYs[r * DYLD + i] = __float2bfloat16_rn(dy);
-        b2sum[u] += dy;
-        gg[u] += gi[u] * xh[u];
-        gb[u] += gi[u];
+          for (int half = 0; half < 2; ++half) {
+            Fs[(16 * mt + g + 8 * half) * FLD + k] = a2[mt][2 * half];
+            Fs[(16 * mt + g + 8 * half) * FLD + k + 1] = a2[mt][2 * half + 1];
+          }
+        }
       }
     }
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (lane + 32 * u < d) atomicAdd(&s.red[lane + 32 * u], b2sum[u]);
     __syncthreads();
-    if ((int)threadIdx.x < d) {
-      atomicAdd(h.gb2 + threadIdx.x, s.red[threadIdx.x]);
-      s.red[threadIdx.x] = 0.0f;
-    }
-    backward_tile(h, s.Xs, s.dYs, s.Hs, s.dHs, nullptr, 0, step ? d : 0, row0, c.rows, s.Fs, warp, lane);
-    __syncthreads();
+    cur = nxt;
   }
+  // LayerNorm weight / bias gradients: the four rows of a warp by shuffles, the eight warps through shared memory
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    if (lane + 32 * u < d) {
-      atomicAdd(&s.red[64 + lane + 32 * u], gg[u]);
-      atomicAdd(&s.red[128 + lane + 32 * u], gb[u]);
+  for (int i = 0; i < CPL; ++i) {
+#pragma unroll
+    for (int m = LPR; m < 32; m <<= 1) {
+      gg[i] += __shfl_xor_sync(MZ_FULL, gg[i], m);
+      gb[i] += __shfl_xor_sync(MZ_FULL, gb[i], m);
+    }
+    if (lane < LPR && c8 + LPR * i < d) {
+      atomicAdd(&red[c8 + LPR * i], gg[i]);
+      atomicAdd(&red[64 + c8 + LPR * i], gb[i]);
     }
   }
   __syncthreads();
   if ((int)threadIdx.x < d) {
-    atomicAdd(c.ggamma + threadIdx.x, s.red[64 + threadIdx.x]);
-    atomicAdd(c.gbeta + threadIdx.x, s.red[128 + threadIdx.x]);
+    atomicAdd(c.ggamma + threadIdx.x, red[threadIdx.x]);
+    atomicAdd(c.gbeta + threadIdx.x, red[64 + threadIdx.x]);
   }
 }
+
+constexpr size_t CHAIN_BWD_SMEM = (size_t)RT * DYLD * 2 + (size_t)RT * HLD * 2 + (size_t)RT * FLD * 4 + 2 * 64 * 4;
 
 bool g_tc_attr = false;
 int tc_attrs() {
@@ -554,7 +700,7 @@ int tc_attrs() {
   if ((e = cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM)) != cudaSuccess ||
       (e = cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM)) != cudaSuccess ||
       (e = cudaFuncSetAttribute(heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM)) != cudaSuccess)
+      (e = cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_BWD_SMEM)) != cudaSuccess)
     return (int)e;
   g_tc_attr = true;
   return 0;
@@ -563,24 +709,32 @@ int tc_attrs() {
 bool head_ok(const mz_tc_head& h, bool backward) {
   if (h.d_in < 1 || h.d_in > 128 || h.d_out < 1 || h.d_out > 64 || !h.w1p || !h.w2p || !h.b1 || !h.b2) return false;
   if (backward && (!h.w2tp || !h.w1tp || !h.gw1 || !h.gb1 || !h.gw2 || !h.gb2)) return false;
+  if (backward && (((uintptr_t)h.gw1 | (uintptr_t)h.gw2) & 15)) return false;  // weight gradients leave as red.v4
   return true;
 }
 
 bool chain_ok(const mz_tc_chain* c, bool backward) {
   if (!c || c->rows < 1 || c->steps < 1 || c->d < 1 || c->d > 64 || c->num_actions < 0 || c->d + c->num_actions > 128) return false;
-  if (!head_ok(c->first, backward) || c->first.d_out != c->d) return false;
-  if (c->steps > 1 && (!head_ok(c->next, backward) || c->next.d_out != c->d || c->next.d_in != c->d + c->num_actions)) return false;
+  // (the chain's backward reads the packed images only; the heads' gradients are mz_heads_backward_tc's job)
+  if (!head_ok(c->first, false) || c->first.d_out != c->d) return false;
+  if (c->steps > 1 && (!head_ok(c->next, false) || c->next.d_out != c->d || c->next.d_in != c->d + c->num_actions)) return false;
+  if (backward && c->steps > 1 && (!c->next.w2tp || !c->next.w1tp)) return false;
   if (!c->x0 || c->ldx0 < c->first.d_in || !c->gamma || !c->beta || !c->xs || c->ldxs < c->d + c->num_actions || !c->yall ||
       !c->mean || !c->rstd)
     return false;
   if (c->actions && (c->action_stride < c->action_steps || c->action_steps < 0)) return false;
-  if (backward && (!c->dxs || !c->ggamma || !c->gbeta)) return false;
+  if (backward && (!c->dxs || !c->ggamma || !c->gbeta || !c->dyall || (c->steps > 1 && !c->relu_mask))) return false;
   return true;
 }
 
 }  // namespace
 
 extern "C" {
+
+int64_t mz_chain_mask_words(int32_t rows, int32_t steps) {
+  if (rows < 1 || steps < 1) return 0;
+  return (int64_t)steps * ((rows + RT - 1) / RT) * NTH * 2;
+}
 
 int64_t mz_learner_packed_words(int32_t n, int32_t k) {
   if (n < 1 || k < 1) return 0;
@@ -649,7 +803,7 @@ int mz_chain_forward_tc(const mz_tc_chain* chain, void* stream) {
 int mz_chain_backward_tc(const mz_tc_chain* chain, void* stream) {
   if (!chain_ok(chain, true)) return MZ_ERR_BAD_ARG;
   if (int rc = tc_attrs()) return rc;
-  chain_bwd_kernel<<<(chain->rows + RT - 1) / RT, NTH, BWD_SMEM, (cudaStream_t)stream>>>(*chain);
+  chain_bwd_kernel<<<(chain->rows + RT - 1) / RT, NTH, CHAIN_BWD_SMEM, (cudaStream_t)stream>>>(*chain);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }

@@ -66,9 +66,11 @@ class FusedFCNetwork(object):
     specs = []
     for h in self.heads.values():
       specs += list(zip(h.keys, h.shapes))
-    self.bucket_split = sum(int(np.prod(s)) for k, s in specs if k.split('.')[0] in ('value_head', 'policy_head', 'reward_head'))
     specs += [('LN.weight', (HIDDEN,)), ('LN.bias', (HIDDEN,))]
-    n = sum(int(np.prod(s)) for _, s in specs)
+    # every tensor starts on a 16-byte boundary of the flat buffers (the tensor-core backward adds weight gradients
+    # with 16-byte vector reductions); the padding floats stay zero in parameters, gradients and optimiser state
+    pad4 = lambda m: (m + 3) & ~3
+    n = sum(pad4(int(np.prod(s))) for _, s in specs)
     self.flat = torch.zeros(n, dtype=torch.float32, device=self.device)
     self.grad = torch.zeros(n, dtype=torch.float32, device=self.device)
     self.views, self.grads, off = {}, {}, 0
@@ -76,7 +78,9 @@ class FusedFCNetwork(object):
       m = int(np.prod(s))
       self.views[k] = self.flat[off:off + m].view(s)
       self.grads[k] = self.grad[off:off + m].view(s)
-      off += m
+      off += pad4(m)
+      if k == 'reward_head.reward.bias':
+        self.bucket_split = off  # value, policy and reward heads: the gradient bucket that is complete first
     # k-major copies of the weight matrices (refreshed every step)
     nt = sum(WIDTH * h.d_in + WIDTH * h.d_out for h in self.heads.values())
     self.t_flat = torch.zeros(nt, dtype=torch.float32, device=self.device)
@@ -233,10 +237,19 @@ class FusedLearner(object):
     """Argument structs of the four tensor-core launches (pointers into the buffers of this batch shape)."""
     net, K, B, A, ldx = self.network, self.K, self.B, self.A, self.ldx
     P = lambda t: t.data_ptr()
+    self.relu_mask = torch.zeros(int(self.lib.mz_chain_mask_words(B, K + 1)), dtype=torch.int32, device=self.device)
+    self.dyall = torch.zeros((K + 1, B, HIDDEN), dtype=torch.float32, device=self.device)
     self.tc_chain = _lib.TcChain(net.tc_head('representation_head'), net.tc_head('transition_head'), B, K + 1, HIDDEN, A,
                                  P(self.s_obs), net.input_dim, P(self.s_actions), max(K, 1), K, P(net.views['LN.weight']),
                                  P(net.views['LN.bias']), P(self.xs), ldx, P(self.yall), P(self.mean), P(self.rstd),
-                                 P(self.dxs), 0.5, P(net.grads['LN.weight']), P(net.grads['LN.bias']))
+                                 P(self.relu_mask), P(self.dxs), 0.5, P(net.grads['LN.weight']), P(net.grads['LN.bias']),
+                                 P(self.dyall))
+    # parameter gradients of the recurrent heads, off the chain: all K B + B rows in one launch
+    rec = [_lib.TcJob(net.tc_head('representation_head'), B, net.input_dim, HIDDEN, 0, P(self.s_obs), None, P(self.dyall[0]),
+                      None)]
+    if K > 0:
+      rec.append(_lib.TcJob(net.tc_head('transition_head'), K * B, ldx, HIDDEN, 0, P(self.xs), None, P(self.dyall[1]), None))
+    self.tc_rec_jobs = (_lib.TcJob * len(rec))(*rec)
     V, R = self.v.shape[2], self.r.shape[2]
     jobs = [_lib.TcJob(net.tc_head('value_head'), (K + 1) * B, ldx, V, ldx, P(self.xs), P(self.v), P(self.dv), P(self.dxs)),
             _lib.TcJob(net.tc_head('policy_head'), (K + 1) * B, ldx, A, ldx, P(self.xs), P(self.p), P(self.dp), P(self.dxs))]
@@ -303,6 +316,7 @@ class FusedLearner(object):
     st = _lib.current_stream()
     if self.precision == 'bf16':
       _lib.check(lib.mz_chain_backward_tc(self.tc_chain, st), "mz_chain_backward_tc")
+      _lib.check(lib.mz_heads_backward_tc(len(self.tc_rec_jobs), self.tc_rec_jobs, st), "mz_heads_backward_tc")
       return
     ln_w = net.views['LN.weight']
     g_w, g_b = net.grads['LN.weight'], net.grads['LN.bias']

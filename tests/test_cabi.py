@@ -43,7 +43,7 @@ int main(void) {
   printf("%zu %zu %zu %zu\n", offsetof(mz_tree, games), offsetof(mz_tree, leaf_action),
          offsetof(mz_fc_weights, rep_w1), offsetof(mz_target_cfg, discounts));
   printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mz_pack_job), sizeof(mz_tc_head), sizeof(mz_tc_job), sizeof(mz_tc_chain),
-         offsetof(mz_tc_job, dx), offsetof(mz_tc_chain, hook_scale), offsetof(mz_tc_chain, gbeta));
+         offsetof(mz_tc_job, dx), offsetof(mz_tc_chain, hook_scale), offsetof(mz_tc_chain, dyall));
   return 0;
 }'''
   with tempfile.TemporaryDirectory() as d:
@@ -57,7 +57,7 @@ int main(void) {
   assert sizes[4:8] == [_lib.Tree.games.offset, _lib.Tree.leaf_action.offset,
                         _lib.FcWeights.rep_w1.offset, _lib.TargetCfg.discounts.offset]
   assert sizes[8:] == [C.sizeof(_lib.PackJob), C.sizeof(_lib.TcHead), C.sizeof(_lib.TcJob), C.sizeof(_lib.TcChain),
-                       _lib.TcJob.dx.offset, _lib.TcChain.hook_scale.offset, _lib.TcChain.gbeta.offset]
+                       _lib.TcJob.dx.offset, _lib.TcChain.hook_scale.offset, _lib.TcChain.dyall.offset]
 
 
 def test_tree_geometry_and_pb_c_table_host_helpers():
