@@ -805,12 +805,12 @@ def bench_targets(torch, _lib, dev):
     Bb = 128 * 512
     sec, bps = _targets_case(torch, _lib, dev, rng, P, A2, K, T2, Bb, E2, u8, 4, 5, disc)
     gbs = Bb * bps / sec / 1e9
-    rows_kernel = T2 <= 64  # mz_build_targets picks the lane-per-position kernel for K + 1 <= 16, td_steps <= 64
+    rows_kernel = T2 <= 64  # mz_build_targets picks the TMA-staged lane-per-position kernel for K + 1 <= 16, td_steps <= 64
     bulk[name] = {"rows_per_launch": Bb, "us_per_launch": sec * 1e6, "samples_per_s": Bb / sec,
                   "algorithmic_bytes_per_sample": bps,
-                  "roofline": {"kernel": "build_targets_rows_kernel" if rows_kernel else "build_targets_kernel",
+                  "roofline": {"kernel": "build_targets_tma_kernel" if rows_kernel else "build_targets_kernel",
                                "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                               "traffic": ncu_traffic("build_targets_rows_kernel" if rows_kernel else
+                               "traffic": ncu_traffic("build_targets_tma_kernel" if rows_kernel else
                                                       "build_targets_kernel", Bb, A2, T2),
                                "peak_source": peaks["source"]}}
   res["bulk"] = bulk
@@ -1051,7 +1051,8 @@ def bench_concurrent(args, torch, dev, world, fs, net, barrier, flush):
       "weight_handoffs": n // send_every,
       "note": "search time = sum of per-move CUDA-event pairs (L2 flushed between moves, like the headline); learner "
               "time = first enqueue to last completion on the side stream (it includes the waits at the hand-offs); "
-              "learner steps/s is the aggregate over ranks of data-parallel steps x ranks",
+              "learner steps/s is the aggregate over ranks of data-parallel steps x ranks; together the learner is paced "
+              "at one step per move, so its rate cannot exceed moves/s (alone it runs back to back)",
   }
 
 

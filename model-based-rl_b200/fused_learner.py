@@ -1,23 +1,30 @@
 """Learner.update_weights (learners.py:164-230) for FCNetwork with the network forward and backward on this
-library's own kernels (csrc/mz_learner.cu) instead of torch modules on library GEMMs.
+library's own kernels instead of torch modules on library GEMMs.
 
 `FusedFCNetwork` keeps every parameter of the reference's FCNetwork (networks.py:122-174) in ONE flat float32 buffer;
 its state dict is a set of views with the reference's keys and shapes, so checkpoints, `Learner.send_weights` and the
-search kernels' `FCNetwork.load_weights` see the usual tensors.  `FusedLearner` runs a step as
+search kernels' `FCNetwork.load_weights` see the usual tensors.  `FusedLearner(precision=...)` runs a step as
 
-    transposes (k-major weight copies)            10 launches
-    representation -> LN -> K x (dynamics -> LN)  2 (K + 1) launches     mz_mlp2_forward / mz_ln_relu_forward
-    value / policy / reward heads over all steps  3 launches             (stacked rows, like FCNetworkTrain.unroll)
-    fused unroll loss                             2 launches             mz_unroll_loss (csrc/mz_unroll_loss.cu)
-    heads backward                                3 launches             mz_mlp2_backward
-    K x (LN backward -> dynamics backward), LN, representation backward   2 (K + 1) launches
-    optimiser                                     2-4 launches           mz_adam_step (AdamW / Adam) or the torch
-                                                                         optimiser over the flat buffer (SGD / RMSprop)
+  precision='bf16' (default; csrc/mz_learner_tc.cu: tensor cores, bf16 operands, float32 accumulation, float32 master
+  weights / gradients / optimiser state)
+    mz_learner_pack           the 20 weight images as bf16 mma B fragments              1 launch
+    mz_chain_forward_tc       representation -> LN -> K x (dynamics -> LN)               1 launch
+    mz_heads_forward_tc       value / policy / reward heads over all K + 1 steps         1 launch
+    mz_unroll_loss            fused loss + logit gradients (csrc/mz_unroll_loss.cu)      2 launches
+    mz_heads_backward_tc      the three output heads                                     1 launch
+    mz_chain_backward_tc      the serial part: LN backward -> dH -> dX per step          1 launch
+    mz_heads_backward_tc      parameter gradients of dynamics + representation           1 launch
+    mz_adam_step              AdamW / Adam over the flat buffer                          2 launches
+  -- 10 kernels + 2 memsets per step, 161 us at B = 512, K = 5 (6 200 steps/s on a B200; the torch-module step in a
+  CUDA graph: 1 100 us).
 
--- about 50 launches where the torch module issues ~270 -- captured in CUDA graphs.  Arithmetic is float32 like the
-reference's; gradients differ from autograd's only by summation order (float32 atomics).  With torch.distributed
-initialised the gradients of the three output heads are all-reduced on a side stream while the recurrent part of the
-backward still runs; the rest follows before the optimiser step.
+  precision='f32' (csrc/mz_learner.cu: float32 CUDA-core kernels, one launch per head evaluation; the parity baseline
+  against the reference's goldens at float32 bars)
+    transposes, 2 (K + 1) forward launches, 3 head launches, loss, 3 + 2 (K + 1) backward launches, optimiser.
+
+Both are captured in CUDA graphs.  SGD / RMSprop use the torch optimiser over the flat buffer (elementwise, the
+reference's arithmetic).  With torch.distributed initialised the gradients of the three output heads are all-reduced
+on a side stream while the recurrent part of the backward still runs; the rest follows before the optimiser step.
 """
 import ctypes as C
 

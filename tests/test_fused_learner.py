@@ -286,6 +286,79 @@ def test_tc_chain_kernels_match_the_per_phase_float32_kernels(B, K, A, D):
   _teacher_forced_check(bf, out["bf16"][1], 2e-3, 3e-3)
 
 
+def _dp_fused_worker(rank, world_size, port, optimizer, graph, out):
+  """One of two data-parallel FusedLearner ranks (both on cuda:0; gloo moves the CUDA buffers, NCCL refuses two ranks
+  on one device): rank r trains on the golden batch of step r."""
+  import os
+  import torch.distributed as dist
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world_size)
+  try:
+    from model_based_rl_b200 import fused_learner
+    g = helpers.load("learner_ttt")
+    cfg = _config(g)
+    cfg.optimizer, cfg.clip_grad = optimizer, 0
+    net, _ = _nets(g, cfg)
+    if rank == 1:  # ranks start from different weights: send_weights must align them
+      net.flat.add_(0.01)
+    learner = fused_learner.FusedLearner(cfg, net, use_graph=graph)
+    learner.send_weights()
+    w0 = _weights(g)
+    for k, v in net.state_dict().items():
+      assert torch.equal(v.cpu(), w0[k]), k
+    learner.update_weights(_batch(g, rank))
+    torch.cuda.synchronize()
+    mine = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    # single-process restatement: the gradients of both batches summed, the same optimiser step with scale 1 / 2
+    solo_net, _ = _nets(g, cfg)
+    solo = fused_learner.FusedLearner(cfg, solo_net, use_graph=False)
+    total = torch.zeros_like(solo_net.grad)
+    for r in range(world_size):
+      solo._stage(_batch(g, r))
+      solo._forward_and_heads_backward()
+      solo._recurrent_backward()
+      total += solo_net.grad
+    solo_net.grad.copy_(total)
+    solo._apply(world_size)
+    torch.cuda.synchronize()
+    bar = 1e-6 if optimizer == "SGD" else 2.5 * cfg.lr_init  # atomics order the sums differently; Adam normalises
+    for k, v in solo_net.state_dict().items():
+      assert torch.allclose(v.cpu(), mine[k], rtol=0, atol=bar), (k, float((v.cpu() - mine[k]).abs().max()))
+    gathered = [None] * world_size
+    dist.all_gather_object(gathered, {k: v.numpy() for k, v in mine.items()})
+    for k in mine:
+      assert np.array_equal(gathered[0][k], gathered[1][k]), k  # every rank holds the same weights, bit for bit
+    out.put((rank, "ok"))
+  except Exception:  # pragma: no cover
+    import traceback
+    out.put((rank, traceback.format_exc()))
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("optimizer,graph", [("SGD", False), ("AdamW", True)])
+def test_fused_learner_data_parallel_two_ranks(optimizer, graph):
+  """The bucketed gradient all-reduce of FusedLearner (output heads' bucket on a side stream under the recurrent
+  backward, the rest after it) with two ranks: same weights on both ranks bit for bit, equal to one process applying
+  the summed gradients of both batches."""
+  import socket
+  import torch.multiprocessing as mp
+  ctx = mp.get_context("spawn")
+  out = ctx.Queue()
+  sk = socket.socket()
+  sk.bind(("127.0.0.1", 0))
+  port = sk.getsockname()[1]
+  sk.close()
+  procs = [ctx.Process(target=_dp_fused_worker, args=(r, 2, port, optimizer, graph, out)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = [out.get(timeout=300) for _ in procs]
+  for p in procs:
+    p.join(timeout=60)
+  assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 def test_mlp2_kernels_ragged_rows_match_torch():
   """mz_mlp2_forward / mz_mlp2_backward on row counts that are not multiples of the 32-row tile, wide inputs, strided
   rows: against the same two-layer head in torch (float64 reference)."""
