@@ -641,7 +641,8 @@ typedef struct mz_pack_job {
   int32_t n, k, stride_n, stride_k;
 } mz_pack_job;
 int64_t mz_learner_packed_words(int32_t n, int32_t k);
-/* Up to 24 matrices per launch (a step packs four images per head from the float32 master weights). */
+/* Up to 24 jobs per launch (a step packs four images per head from the float32 master weights).  A job with src == NULL
+ * clears n 32-bit words at dst instead (the gradient buffers a step accumulates into), so one launch prepares the step. */
 int mz_learner_pack(int32_t njobs, const mz_pack_job* jobs, void* stream);
 
 /* One head Linear(d_in, 512) -> ReLU -> Linear(512, d_out) (networks.py:55-119); d_in <= 128, d_out <= 64.

@@ -86,6 +86,10 @@ MZ_DEV int round_up32(int v) { return (v + 31) & ~31; }
 // the b0 / b1 registers of k-steps 2 kq and 2 kq + 1 of n-tile nt, one 16-byte load per lane.  Zeros outside N x K.
 __global__ void pack_kernel(PackParams p) {
   const mz_pack_job job = p.jobs[blockIdx.y];
+  if (job.src == nullptr) {  // a buffer to clear before the step (gradients): n 32-bit words
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < job.n; w += gridDim.x * blockDim.x) job.dst[w] = 0u;
+    return;
+  }
   const int KQ = (job.k + 31) >> 5, NTl = (job.n + 7) >> 3;
   const int words = NTl * KQ * 128;
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
@@ -746,13 +750,13 @@ int mz_learner_pack(int32_t njobs, const mz_pack_job* jobs, void* stream) {
   PackParams p;
   int64_t most = 0;
   for (int i = 0; i < njobs; ++i) {
-    if (!jobs[i].src || !jobs[i].dst || jobs[i].n < 1 || jobs[i].k < 1) return MZ_ERR_BAD_ARG;
+    if (!jobs[i].dst || jobs[i].n < 1 || (jobs[i].src && jobs[i].k < 1)) return MZ_ERR_BAD_ARG;
     p.jobs[i] = jobs[i];
-    const int64_t w = mz_learner_packed_words(jobs[i].n, jobs[i].k);
+    const int64_t w = jobs[i].src ? mz_learner_packed_words(jobs[i].n, jobs[i].k) : (jobs[i].n + 3) / 4;
     most = w > most ? w : most;
   }
   int blocks = (int)((most + 1023) / 1024);
-  blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
+  blocks = blocks < 1 ? 1 : (blocks > 96 ? 96 : blocks);
   pack_kernel<<<dim3(blocks, njobs), 256, 0, (cudaStream_t)stream>>>(p);
   MZ_LAUNCH_CHECK();
   return MZ_OK;

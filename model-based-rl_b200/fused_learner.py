@@ -114,6 +114,7 @@ class FusedFCNetwork(object):
         off += words(n, k)
         h.images.append(dst)
         jobs.append(_lib.PackJob(src.data_ptr(), dst.data_ptr(), n, k, sn, sk))
+    self._pack_list = jobs
     self._pack_jobs = (_lib.PackJob * len(jobs))(*jobs)
     # the reference's initialisation: torch's defaults for nn.Linear / nn.LayerNorm
     ref = learners.FCNetworkTrain(self.input_dim, A, 'cpu', config)
@@ -257,6 +258,10 @@ class FusedLearner(object):
     if K > 0:
       rec.append(_lib.TcJob(net.tc_head('transition_head'), K * B, ldx, HIDDEN, 0, P(self.xs), None, P(self.dyall[1]), None))
     self.tc_rec_jobs = (_lib.TcJob * len(rec))(*rec)
+    # the step's first launch packs the weight images AND clears the two accumulation buffers (src NULL = zero n words)
+    first = list(net._pack_list) + [_lib.PackJob(None, P(net.grad), net.grad.numel(), 0, 0, 0),
+                                    _lib.PackJob(None, P(self.dxs), self.dxs.numel(), 0, 0, 0)]
+    self.tc_first_jobs = (_lib.PackJob * len(first))(*first)
     V, R = self.v.shape[2], self.r.shape[2]
     jobs = [_lib.TcJob(net.tc_head('value_head'), (K + 1) * B, ldx, V, ldx, P(self.xs), P(self.v), P(self.dv), P(self.dxs)),
             _lib.TcJob(net.tc_head('policy_head'), (K + 1) * B, ldx, A, ldx, P(self.xs), P(self.p), P(self.dp), P(self.dxs))]
@@ -282,9 +287,7 @@ class FusedLearner(object):
     net, lib, K, B, A, ldx = self.network, self.lib, self.K, self.B, self.A, self.ldx
     st = _lib.current_stream()
     if self.precision == 'bf16':
-      net.refresh_packed()
-      net.grad.zero_()
-      self.dxs.zero_()
+      _lib.check(lib.mz_learner_pack(len(self.tc_first_jobs), self.tc_first_jobs, st), "mz_learner_pack")
       _lib.check(lib.mz_chain_forward_tc(self.tc_chain, st), "mz_chain_forward_tc")
       _lib.check(lib.mz_heads_forward_tc(len(self.tc_jobs), self.tc_jobs, st), "mz_heads_forward_tc")
       _lib.check(lib.mz_unroll_loss(self.c_loss, _P(self.v), _P(self.r), _P(self.p), _P(self.s_tv), _P(self.s_tr),
