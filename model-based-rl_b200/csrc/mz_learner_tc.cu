@@ -290,16 +290,26 @@ MZ_DEV void output_phase(const mz_tc_head& h, const __nv_bfloat16* Hs, float* __
   }
 }
 
-// Backward of one head over the CTA's tile.  In: Xs (input rows, bf16), dYs (output gradient, bf16, zero padded to a
-// multiple of 32 columns).  Out: the four parameter gradients (atomics), and dX (columns [0, dx_cols)) accumulated into
-// global memory (dX != nullptr) or left in Fs (dx_cols > 0, dX == nullptr).
-MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __nv_bfloat16* dYs, __nv_bfloat16* Hs,
-                          __nv_bfloat16* dHs, float* __restrict__ dX, int lddx, int dx_cols, int row0, int rows, float* Fs,
-                          float* stage, int warp, int lane) {
+// Backward of one head over the CTA's TILES tiles of 32 rows.  In: Xs (input rows, bf16), dYs (output gradient, bf16,
+// zero padded to a multiple of 32 columns).  Out: the four parameter gradients (vector reductions: one per weight and
+// CTA, so two tiles per CTA halve that traffic), and dX (columns [0, dx_cols)) accumulated into global memory.
+template <int TILES>
+MZ_DEV void backward_tiles(const mz_tc_head& h, const __nv_bfloat16* Xs, const __nv_bfloat16* dYs, __nv_bfloat16* Hs,
+                           __nv_bfloat16* dHs, float* __restrict__ dX, int lddx, int dx_cols, int row0, int rows,
+                           float* stage, int warp, int lane) {
   const int g = lane >> 2, t = lane & 3;
-  uint32_t mask[2];
-  hidden_phase(h, Xs, Hs, mask, warp, lane);
-  {  // dH = dY W2 for the warp's hidden units, masked by the ReLU; gb1; -> dHs
+  float s0[NTW], s1[NTW];  // column sums of the gated dH: gb1
+#pragma unroll
+  for (int n = 0; n < NTW; ++n) s0[n] = s1[n] = 0.0f;
+#pragma unroll 1
+  for (int tile = 0; tile < TILES; ++tile) {
+    const __nv_bfloat16* Xt = Xs + tile * RT * XLD;
+    const __nv_bfloat16* dYt = dYs + tile * RT * DYLD;
+    __nv_bfloat16* Ht = Hs + tile * RT * HLD;
+    __nv_bfloat16* dHt = dHs + tile * RT * HLD;
+    uint32_t mask[2];
+    hidden_phase(h, Xt, Ht, mask, warp, lane);
+    // dH = dY W2 for the warp's hidden units, masked by the ReLU -> dHs
     float acc[2][NTW][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -307,52 +317,51 @@ MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __
       for (int n = 0; n < NTW; ++n)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[mt][n][c] = 0.0f;
-    gemm_wide(acc, dYs, DYLD, h.w2tp, round_up32(h.d_out) >> 5, NTW * warp, lane);
+    gemm_wide(acc, dYt, DYLD, h.w2tp, round_up32(h.d_out) >> 5, NTW * warp, lane);
 #pragma unroll
     for (int n = 0; n < NTW; ++n) {
       const int j = CW * warp + 8 * n + 2 * t;
-      float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const uint32_t m = mask[mt] >> (4 * n);
         const float v0 = (m & 1u) ? acc[mt][n][0] : 0.0f, v1 = (m & 2u) ? acc[mt][n][1] : 0.0f;
         const float v2 = (m & 4u) ? acc[mt][n][2] : 0.0f, v3 = (m & 8u) ? acc[mt][n][3] : 0.0f;
-        s0 += v0 + v2;
-        s1 += v1 + v3;
-        *reinterpret_cast<uint32_t*>(dHs + (16 * mt + g) * HLD + j) = pack2(v0, v1);
-        *reinterpret_cast<uint32_t*>(dHs + (16 * mt + g + 8) * HLD + j) = pack2(v2, v3);
-      }
-#pragma unroll
-      for (int m = 4; m < 32; m <<= 1) {
-        s0 += __shfl_xor_sync(MZ_FULL, s0, m);
-        s1 += __shfl_xor_sync(MZ_FULL, s1, m);
-      }
-      if (g == 0) {
-        atomicAdd(h.gb1 + j, s0);
-        atomicAdd(h.gb1 + j + 1, s1);
+        s0[n] += v0 + v2;
+        s1[n] += v1 + v3;
+        *reinterpret_cast<uint32_t*>(dHt + (16 * mt + g) * HLD + j) = pack2(v0, v1);
+        *reinterpret_cast<uint32_t*>(dHt + (16 * mt + g + 8) * HLD + j) = pack2(v2, v3);
       }
     }
   }
+#pragma unroll
+  for (int n = 0; n < NTW; ++n) {
+#pragma unroll
+    for (int m = 4; m < 32; m <<= 1) {
+      s0[n] += __shfl_xor_sync(MZ_FULL, s0[n], m);
+      s1[n] += __shfl_xor_sync(MZ_FULL, s1[n], m);
+    }
+    if (g == 0) {
+      atomicAdd(h.gb1 + CW * warp + 8 * n + 2 * t, s0[n]);
+      atomicAdd(h.gb1 + CW * warp + 8 * n + 2 * t + 1, s1[n]);
+    }
+  }
   __syncthreads();
-  // dX = dH W1: n-tile w of the input features
+  // dX = dH W1: (tile, n-tile) pairs over the warps
   if (dx_cols > 0 && !(MZ_TC_SKIP & 4)) {
-    for (int nt = warp; 8 * nt < dx_cols; nt += NW) {
+    const int ntl = (dx_cols + 7) >> 3;
+    for (int w = warp; w < TILES * ntl; w += NW) {
+      const int tile = w / ntl, nt = w - tile * ntl;
       float acc[2][4];
-      gemm_tall(acc, dHs, HLD, h.w1tp, nt, lane);
+      gemm_tall(acc, dHs + tile * RT * HLD, HLD, h.w1tp, nt, lane);
       const int k = 8 * nt + 2 * t;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          const int r = 16 * mt + g + 8 * half;
-          if (dX != nullptr) {
-            if (row0 + r < rows) {
-              if (k < dx_cols) atomicAdd(dX + (size_t)(row0 + r) * lddx + k, acc[mt][2 * half]);
-              if (k + 1 < dx_cols) atomicAdd(dX + (size_t)(row0 + r) * lddx + k + 1, acc[mt][2 * half + 1]);
-            }
-          } else {
-            Fs[r * FLD + k] = acc[mt][2 * half];
-            Fs[r * FLD + k + 1] = acc[mt][2 * half + 1];
+          const int r = row0 + RT * tile + 16 * mt + g + 8 * half;
+          if (r < rows) {
+            if (k < dx_cols) atomicAdd(dX + (size_t)r * lddx + k, acc[mt][2 * half]);
+            if (k + 1 < dx_cols) atomicAdd(dX + (size_t)r * lddx + k + 1, acc[mt][2 * half + 1]);
           }
         }
       }
@@ -360,7 +369,7 @@ MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __
   }
   if (MZ_TC_SKIP & 2) return;
   const int lrow = lane & 7, lsel = lane >> 3;  // ldmatrix.trans: lanes 8 i .. 8 i + 7 address matrix i
-  // gW2[o][j] = sum_r dY[r][o] H[r][j]: M = outputs (16 per m-tile), N = the warp's hidden units, K = the tile's rows
+  // gW2[o][j] = sum_r dY[r][o] H[r][j]: M = outputs (16 per m-tile), N = the warp's hidden units, K = the CTA's rows
   for (int mt = 0; 16 * mt < h.d_out; ++mt) {
     float acc[NTW][4];
 #pragma unroll
@@ -368,7 +377,7 @@ MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[n][c] = 0.0f;
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
+    for (int ks = 0; ks < 2 * TILES; ++ks) {
       uint32_t a[4];
       ldsm4t(a, dYs + (16 * ks + lrow + (lsel >> 1) * 8) * DYLD + 16 * mt + (lsel & 1) * 8);
 #pragma unroll
@@ -390,7 +399,7 @@ MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[n][c] = 0.0f;
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
+      for (int ks = 0; ks < 2 * TILES; ++ks) {
         uint32_t a[4];
         ldsm4t(a, dHs + (16 * ks + lrow + (lsel >> 1) * 8) * HLD + CW * warp + 16 * mt + (lsel & 1) * 8);
 #pragma unroll
@@ -412,28 +421,16 @@ MZ_DEV void backward_tile(const mz_tc_head& h, const __nv_bfloat16* Xs, const __
 struct Tiles {
   __nv_bfloat16 *Xs, *Hs, *dHs, *dYs;
   float* Fs;
-  float* red;    // [4][64]
-  float* stage;  // [NW][STAGE]
 };
 constexpr int STAGE = 8 * 68;  // floats per warp: eight rows of a weight-gradient tile
 constexpr size_t FWD_SMEM = (size_t)RT * XLD * 2 + (size_t)RT * HLD * 2 + (size_t)RT * FLD * 4;
-constexpr size_t BWD_SMEM = (size_t)RT * XLD * 2 + 2 * (size_t)RT * HLD * 2 + (size_t)RT * DYLD * 2 + (size_t)RT * FLD * 4 +
-                            4 * 64 * 4 + NW * STAGE * 4;
-MZ_DEV Tiles carve(unsigned char* base, bool backward) {
+MZ_DEV Tiles carve(unsigned char* base) {  // the forward kernels' tiles
   Tiles t;
   t.Xs = reinterpret_cast<__nv_bfloat16*>(base);
   t.Hs = t.Xs + RT * XLD;
-  unsigned char* p = reinterpret_cast<unsigned char*>(t.Hs + RT * HLD);
   t.dHs = nullptr;
   t.dYs = nullptr;
-  if (backward) {
-    t.dHs = reinterpret_cast<__nv_bfloat16*>(p);
-    t.dYs = t.dHs + RT * HLD;
-    p = reinterpret_cast<unsigned char*>(t.dYs + RT * DYLD);
-  }
-  t.Fs = reinterpret_cast<float*>(p);
-  t.red = t.Fs + RT * FLD;
-  t.stage = t.red + 4 * 64;
+  t.Fs = reinterpret_cast<float*>(t.Hs + RT * HLD);
   return t;
 }
 
@@ -443,7 +440,7 @@ __global__ void __launch_bounds__(NTH) heads_fwd_kernel(PlainParams p) {
   const mz_tc_job& job = p.jobs[blockIdx.y];
   const int row0 = blockIdx.x * RT;
   if (row0 >= job.rows) return;
-  const Tiles s = carve(tc_smem, false);
+  const Tiles s = carve(tc_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   load_rows(s.Xs, XLD, job.x, job.ldx, row0, job.rows, job.head.d_in, round_up32(job.head.d_in));
   __syncthreads();
@@ -453,26 +450,38 @@ __global__ void __launch_bounds__(NTH) heads_fwd_kernel(PlainParams p) {
   output_phase(job.head, s.Hs, job.y, job.ldy, row0, job.rows, nullptr, warp, lane);
 }
 
+template <int TILES>
 __global__ void __launch_bounds__(NTH) heads_bwd_kernel(PlainParams p) {
   extern __shared__ __align__(16) unsigned char tc_smem[];
   const mz_tc_job& job = p.jobs[blockIdx.y];
-  const int row0 = blockIdx.x * RT;
+  constexpr int RTT = RT * TILES;  // rows per CTA
+  const int row0 = blockIdx.x * RTT;
   if (row0 >= job.rows) return;
-  const Tiles s = carve(tc_smem, true);
+  __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
+  __nv_bfloat16* Hs = Xs + RTT * XLD;
+  __nv_bfloat16* dHs = Hs + RTT * HLD;
+  __nv_bfloat16* dYs = dHs + RTT * HLD;
+  float* stage = reinterpret_cast<float*>(dYs + RTT * DYLD);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const mz_tc_head& h = job.head;
-  load_rows(s.Xs, XLD, job.x, job.ldx, row0, job.rows, h.d_in, round_up32(h.d_in));
-  load_rows(s.dYs, DYLD, job.dy, job.ldy, row0, job.rows, h.d_out, round_up32(h.d_out));
+#pragma unroll
+  for (int tile = 0; tile < TILES; ++tile) {
+    load_rows(Xs + tile * RT * XLD, XLD, job.x, job.ldx, row0 + RT * tile, job.rows, h.d_in, round_up32(h.d_in));
+    load_rows(dYs + tile * RT * DYLD, DYLD, job.dy, job.ldy, row0 + RT * tile, job.rows, h.d_out, round_up32(h.d_out));
+  }
   if ((int)threadIdx.x < h.d_out) {  // gb2[o] = sum_r dY[r][o]
     float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-    for (int r = 0; r < RT; ++r)
+#pragma unroll 8
+    for (int r = 0; r < RTT; ++r)
       if (row0 + r < job.rows) part[r & 3] += job.dy[(size_t)(row0 + r) * job.ldy + threadIdx.x];
     atomicAdd(h.gb2 + threadIdx.x, (part[0] + part[1]) + (part[2] + part[3]));
   }
   __syncthreads();
-  backward_tile(h, s.Xs, s.dYs, s.Hs, s.dHs, job.dx, job.lddx, job.dx != nullptr ? h.d_in : 0, row0, job.rows, s.Fs,
-                s.stage + warp * STAGE, warp, lane);
+  backward_tiles<TILES>(h, Xs, dYs, Hs, dHs, job.dx, job.lddx, job.dx != nullptr ? h.d_in : 0, row0, job.rows,
+                        stage + warp * STAGE, warp, lane);
+}
+constexpr size_t heads_bwd_smem(int tiles) {
+  return (size_t)tiles * RT * (XLD + 2 * HLD + DYLD) * 2 + (size_t)NW * STAGE * 4;
 }
 
 // ---- the recurrent chain ---------------------------------------------------------------------------------------
@@ -481,7 +490,7 @@ __global__ void __launch_bounds__(NTH) heads_bwd_kernel(PlainParams p) {
 __global__ void __launch_bounds__(NTH) chain_fwd_kernel(mz_tc_chain c) {
   extern __shared__ __align__(16) unsigned char tc_smem[];
   const int row0 = blockIdx.x * RT;
-  const Tiles s = carve(tc_smem, false);
+  const Tiles s = carve(tc_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = c.d, A = c.num_actions, next_pad = round_up32(d + A);
   const int r = (32 / LPR) * warp + lane / LPR, c8 = lane % LPR, row = row0 + r;
@@ -703,7 +712,8 @@ int tc_attrs() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM)) != cudaSuccess ||
       (e = cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(heads_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_bwd_smem(1))) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(heads_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_bwd_smem(2))) != cudaSuccess ||
       (e = cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_BWD_SMEM)) != cudaSuccess)
     return (int)e;
   g_tc_attr = true;
@@ -791,7 +801,13 @@ int mz_heads_backward_tc(int32_t njobs, const mz_tc_job* jobs, void* stream) {
     most = j.rows > most ? j.rows : most;
   }
   if (int rc = tc_attrs()) return rc;
-  heads_bwd_kernel<<<dim3((most + RT - 1) / RT, njobs), NTH, BWD_SMEM, (cudaStream_t)stream>>>(p);
+  // more CTAs than one wave of single-tile CTAs: two tiles per CTA (half the weight-gradient reductions, one wave)
+  int ctas = 0;
+  for (int i = 0; i < njobs; ++i) ctas += (jobs[i].rows + RT - 1) / RT;
+  if (ctas > 148)
+    heads_bwd_kernel<2><<<dim3((most + 2 * RT - 1) / (2 * RT), njobs), NTH, heads_bwd_smem(2), (cudaStream_t)stream>>>(p);
+  else
+    heads_bwd_kernel<1><<<dim3((most + RT - 1) / RT, njobs), NTH, heads_bwd_smem(1), (cudaStream_t)stream>>>(p);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }
