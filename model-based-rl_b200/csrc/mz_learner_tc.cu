@@ -34,8 +34,6 @@ constexpr int NW = 16;             // warps per CTA: a CTA runs alone on its SM 
 constexpr int NTH = 32 * NW;       // threads per CTA
 constexpr int CW = LW / NW;        // hidden units per warp: warp w owns [CW w, CW w + CW)
 constexpr int NTW = CW / 8;        // n-tiles per warp
-constexpr int LPR = NW;            // LayerNorm phases: lanes per row (a warp owns 32 / LPR rows at once)
-constexpr int CPL = 64 / LPR;      // ... and columns per lane: lane (rr, cl) holds columns cl + LPR i, i < CPL
 constexpr int XLD = 136;   // bf16 per row of the input tile (<= 128 features; 272 B: ldmatrix rows 16 B apart mod 128)
 constexpr int HLD = 520;   // bf16 per row of the activation tiles
 constexpr int DYLD = 72;   // bf16 per row of the output-gradient tile (<= 64 outputs)
@@ -48,6 +46,16 @@ constexpr int MAXJOBS = 3, MAXPACK = 24;
 #define MZ_WG_ADD(p, v) do { if ((v) == 12345.678f) atomicAdd((p), (v)); } while (0)
 #else
 #define MZ_WG_ADD(p, v) atomicAdd((p), (v))
+#endif
+
+#ifdef MZ_TC_TRACE  // diagnostics build: clock64 stamps of CTA 0 (warps 0 and NW - 1) per phase of chain_fwd
+__device__ long long g_tc_trace[2][2][16][8];  // [kernel][warp 0 / last][step][phase]
+#define TC_T(kern, step, ph)                                                                               \
+  do {                                                                                                     \
+    if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == NTH - 32)) g_tc_trace[kern][threadIdx.x != 0][step][ph] = clock64(); \
+  } while (0)
+#else
+#define TC_T(kern, step, ph)
 #endif
 
 struct PlainParams {
@@ -105,8 +113,9 @@ __global__ void pack_kernel(PackParams p) {
   }
 }
 
-// acc[2][NTW][4] += A (32 rows x 32 KQ, row-major bf16 in shared memory) * B (packed; n-tiles nt0 .. nt0 + NTW - 1)
-MZ_DEV void gemm_wide(float (&acc)[2][NTW][4], const __nv_bfloat16* As, int lda, const uint32_t* __restrict__ Bp, int KQ,
+// acc[MT][NTW][4] += A (16 MT rows x 32 KQ, row-major bf16 in shared memory) * B (packed; n-tiles nt0 .. nt0 + NTW - 1)
+template <int MT>
+MZ_DEV void gemm_wide(float (&acc)[MT][NTW][4], const __nv_bfloat16* As, int lda, const uint32_t* __restrict__ Bp, int KQ,
                       int nt0, int lane) {
   const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
   const uint4* bp = reinterpret_cast<const uint4*>(Bp) + (size_t)nt0 * KQ * 32 + lane;
@@ -119,17 +128,17 @@ MZ_DEV void gemm_wide(float (&acc)[2][NTW][4], const __nv_bfloat16* As, int lda,
 #pragma unroll
       for (int n = 0; n < NTW; ++n) bn[n] = __ldg(bp + ((size_t)n * KQ + kq + 1) * 32);
     }
-    uint32_t a[2][2][4];
+    uint32_t a[2][MT][4];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) ldsm4(a[ks][mt], As + (16 * mt + arow) * lda + 32 * kq + 16 * ks + acol);
+      for (int mt = 0; mt < MT; ++mt) ldsm4(a[ks][mt], As + (16 * mt + arow) * lda + 32 * kq + 16 * ks + acol);
 #pragma unroll
     for (int n = 0; n < NTW; ++n) {
-      mma16816(acc[0][n], a[0][0], b[n].x, b[n].y);
-      mma16816(acc[1][n], a[0][1], b[n].x, b[n].y);
-      mma16816(acc[0][n], a[1][0], b[n].z, b[n].w);
-      mma16816(acc[1][n], a[1][1], b[n].z, b[n].w);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma16816(acc[mt][n], a[0][mt], b[n].x, b[n].y);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma16816(acc[mt][n], a[1][mt], b[n].z, b[n].w);
     }
     if (kq + 1 < KQ) {
 #pragma unroll
@@ -138,23 +147,24 @@ MZ_DEV void gemm_wide(float (&acc)[2][NTW][4], const __nv_bfloat16* As, int lda,
   }
 }
 
-// acc[2][4] = A (32 rows x 512, row-major bf16 in shared memory) * B (packed, KQ = 16; n-tile nt)
-MZ_DEV void gemm_tall(float (&acc)[2][4], const __nv_bfloat16* As, int lda, const uint32_t* __restrict__ Bp, int nt,
+// acc[MT][4] = A (16 MT rows x 512, row-major bf16 in shared memory) * B (packed, KQ = 16; n-tile nt)
+template <int MT>
+MZ_DEV void gemm_tall(float (&acc)[MT][4], const __nv_bfloat16* As, int lda, const uint32_t* __restrict__ Bp, int nt,
                       int lane) {
   const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
   const uint4* bp = reinterpret_cast<const uint4*>(Bp) + (size_t)nt * 16 * 32 + lane;
   uint4 b[16];
 #pragma unroll
   for (int kq = 0; kq < 16; ++kq) b[kq] = __ldg(bp + kq * 32);
-  float acc2[2][4];
+  float acc2[MT][4];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[mt][c] = acc2[mt][c] = 0.0f;
 #pragma unroll
   for (int kq = 0; kq < 16; ++kq) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       uint32_t a0[4], a1[4];
       ldsm4(a0, As + (16 * mt + arow) * lda + 32 * kq + acol);
       ldsm4(a1, As + (16 * mt + arow) * lda + 32 * kq + 16 + acol);
@@ -163,17 +173,18 @@ MZ_DEV void gemm_tall(float (&acc)[2][4], const __nv_bfloat16* As, int lda, cons
     }
   }
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[mt][c] += acc2[mt][c];
 }
 
-// rows [row0, row0 + 32) x columns [0, d) of a float32 matrix -> bf16 tile, zeros up to column dpad (a multiple of 32)
+// rows [row0, row0 + ROWS) x columns [0, d) of a float32 matrix -> bf16 tile, zeros up to column dpad (a multiple of 32)
 // and behind `rows`.  A warp moves 32-column segments; all of a thread's loads are in flight before its first store.
+template <int ROWS = RT>
 MZ_DEV void load_rows(__nv_bfloat16* Ts, int ld, const float* __restrict__ X, int ldx, int row0, int rows, int d, int dpad) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int spr = dpad >> 5, segs = RT * spr;  // segments per row (1..4), in all (32..128)
-  constexpr int NI = 128 / NW;
+  const int spr = dpad >> 5, segs = ROWS * spr;  // segments per row (1..4), in all
+  constexpr int NI = (4 * ROWS + NW - 1) / NW;
   float v[NI];
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
@@ -234,24 +245,26 @@ MZ_DEV void tile_add(float* __restrict__ dst, int ld, int rows_ok, int cols, con
 }
 
 // H = relu(W1 X + b1) for the warp's CW hidden units -> Hs (bf16); returns the sign bits (bit 4 n + c of mask[mt])
-MZ_DEV void hidden_phase(const mz_tc_head& h, const __nv_bfloat16* Xs, __nv_bfloat16* Hs, uint32_t (&mask)[2], int warp,
+template <int MT>
+MZ_DEV void hidden_phase(const mz_tc_head& h, const __nv_bfloat16* Xs, __nv_bfloat16* Hs, uint32_t (&mask)[MT], int warp,
                          int lane) {
-  float acc[2][NTW][4];
+  float acc[MT][NTW][4];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int n = 0; n < NTW; ++n)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[mt][n][c] = 0.0f;
   gemm_wide(acc, Xs, XLD, h.w1p, round_up32(h.d_in) >> 5, NTW * warp, lane);
   const int g = lane >> 2, t = lane & 3;
-  mask[0] = mask[1] = 0u;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) mask[mt] = 0u;
 #pragma unroll
   for (int n = 0; n < NTW; ++n) {
     const int j = CW * warp + 8 * n + 2 * t;
     const float2 bb = make_float2(__ldg(h.b1 + j), __ldg(h.b1 + j + 1));  // views of a flat buffer: 4-byte aligned
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       const float v0 = fmaxf(acc[mt][n][0] + bb.x, 0.0f), v1 = fmaxf(acc[mt][n][1] + bb.y, 0.0f);
       const float v2 = fmaxf(acc[mt][n][2] + bb.x, 0.0f), v3 = fmaxf(acc[mt][n][3] + bb.y, 0.0f);
       mask[mt] |= (v0 > 0.0f ? 1u : 0u) << (4 * n) | (v1 > 0.0f ? 2u : 0u) << (4 * n) | (v2 > 0.0f ? 4u : 0u) << (4 * n) |
@@ -268,7 +281,7 @@ MZ_DEV void output_phase(const mz_tc_head& h, const __nv_bfloat16* Hs, float* __
                          float* Fs, int warp, int lane) {
   if (8 * warp >= h.d_out) return;
   float acc[2][4];
-  gemm_tall(acc, Hs, HLD, h.w2p, warp, lane);
+  gemm_tall<2>(acc, Hs, HLD, h.w2p, warp, lane);
   const int g = lane >> 2, o = 8 * warp + 2 * (lane & 3);
   const float b0 = o < h.d_out ? __ldg(h.b2 + o) : 0.0f, b1 = o + 1 < h.d_out ? __ldg(h.b2 + o + 1) : 0.0f;
 #pragma unroll
@@ -308,7 +321,7 @@ MZ_DEV void backward_tiles(const mz_tc_head& h, const __nv_bfloat16* Xs, const _
     __nv_bfloat16* Ht = Hs + tile * RT * HLD;
     __nv_bfloat16* dHt = dHs + tile * RT * HLD;
     uint32_t mask[2];
-    hidden_phase(h, Xt, Ht, mask, warp, lane);
+    hidden_phase<2>(h, Xt, Ht, mask, warp, lane);
     // dH = dY W2 for the warp's hidden units, masked by the ReLU -> dHs
     float acc[2][NTW][4];
 #pragma unroll
@@ -317,7 +330,7 @@ MZ_DEV void backward_tiles(const mz_tc_head& h, const __nv_bfloat16* Xs, const _
       for (int n = 0; n < NTW; ++n)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[mt][n][c] = 0.0f;
-    gemm_wide(acc, dYt, DYLD, h.w2tp, round_up32(h.d_out) >> 5, NTW * warp, lane);
+    gemm_wide<2>(acc, dYt, DYLD, h.w2tp, round_up32(h.d_out) >> 5, NTW * warp, lane);
 #pragma unroll
     for (int n = 0; n < NTW; ++n) {
       const int j = CW * warp + 8 * n + 2 * t;
@@ -352,7 +365,7 @@ MZ_DEV void backward_tiles(const mz_tc_head& h, const __nv_bfloat16* Xs, const _
     for (int w = warp; w < TILES * ntl; w += NW) {
       const int tile = w / ntl, nt = w - tile * ntl;
       float acc[2][4];
-      gemm_tall(acc, dHs + tile * RT * HLD, HLD, h.w1tp, nt, lane);
+      gemm_tall<2>(acc, dHs + tile * RT * HLD, HLD, h.w1tp, nt, lane);
       const int k = 8 * nt + 2 * t;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
@@ -445,7 +458,7 @@ __global__ void __launch_bounds__(NTH) heads_fwd_kernel(PlainParams p) {
   load_rows(s.Xs, XLD, job.x, job.ldx, row0, job.rows, job.head.d_in, round_up32(job.head.d_in));
   __syncthreads();
   uint32_t mask[2];
-  hidden_phase(job.head, s.Xs, s.Hs, mask, warp, lane);
+  hidden_phase<2>(job.head, s.Xs, s.Hs, mask, warp, lane);
   __syncthreads();
   output_phase(job.head, s.Hs, job.y, job.ldy, row0, job.rows, nullptr, warp, lane);
 }
@@ -485,17 +498,35 @@ constexpr size_t heads_bwd_smem(int tiles) {
 }
 
 // ---- the recurrent chain ---------------------------------------------------------------------------------------
-// LayerNorm phases: a warp owns 32 / LPR rows at once, LPR lanes per row; lane (rr, c8) holds columns c8 + LPR i
+// A CTA owns 16 MT rows for all steps.  MT = 1 (16 rows, twice the CTAs) whenever that still fits one wave: the phases
+// of a step are bound by the issue rate of the warp-level mma on the CTA's SM (~16 cycles per m16n8k16 and scheduler),
+// so half the rows per CTA is half the time per step.
+// LayerNorm phases: a warp owns 16 MT / NW rows at once, LPR lanes per row; lane (rr, c8) holds columns c8 + LPR i
 // (i < CPL) of its row, so the row statistics are log2(LPR) shuffle steps and the rows run side by side.
+template <int MT>
+struct ChainGeo {
+  static constexpr int ROWS = 16 * MT;
+  static constexpr int LPR = 32 * NW / ROWS;  // lanes per row (MT = 1: 32, MT = 2: 16)
+  static constexpr int CPL = 64 / LPR;        // columns per lane
+  static constexpr size_t FWD_SMEM = (size_t)ROWS * XLD * 2 + (size_t)ROWS * HLD * 2 + (size_t)ROWS * FLD * 4;
+  static constexpr size_t BWD_SMEM = (size_t)ROWS * DYLD * 2 + (size_t)ROWS * HLD * 2 + (size_t)ROWS * FLD * 4 + 2 * 64 * 4;
+};
+
+template <int MT>
 __global__ void __launch_bounds__(NTH) chain_fwd_kernel(mz_tc_chain c) {
+  using G = ChainGeo<MT>;
+  constexpr int ROWS = G::ROWS, LPR = G::LPR, CPL = G::CPL;
   extern __shared__ __align__(16) unsigned char tc_smem[];
-  const int row0 = blockIdx.x * RT;
-  const Tiles s = carve(tc_smem);
+  const int row0 = blockIdx.x * ROWS;
+  __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
+  __nv_bfloat16* Hs = Xs + ROWS * XLD;
+  float* Fs = reinterpret_cast<float*>(Hs + ROWS * HLD);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = c.d, A = c.num_actions, next_pad = round_up32(d + A);
   const int r = (32 / LPR) * warp + lane / LPR, c8 = lane % LPR, row = row0 + r;
   const bool live = row < c.rows;
   const float inv_d = 1.0f / (float)d;
+  const int g = lane >> 2, t = lane & 3;
   float gam[CPL], bet[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) {
@@ -503,24 +534,43 @@ __global__ void __launch_bounds__(NTH) chain_fwd_kernel(mz_tc_chain c) {
     gam[i] = col < d ? __ldg(c.gamma + col) : 0.0f;
     bet[i] = col < d ? __ldg(c.beta + col) : 0.0f;
   }
-  load_rows(s.Xs, XLD, c.x0, c.ldx0, row0, c.rows, c.first.d_in, round_up32(c.first.d_in));
+  load_rows<ROWS>(Xs, XLD, c.x0, c.ldx0, row0, c.rows, c.first.d_in, round_up32(c.first.d_in));
   __syncthreads();
   for (int step = 0; step < c.steps; ++step) {
     const mz_tc_head& h = step ? c.next : c.first;
     const int act = (live && c.actions != nullptr && step < c.action_steps)
                         ? __ldg(c.actions + (size_t)row * c.action_stride + step) : -1;  // in flight during the head
-    uint32_t mask[2];
-    hidden_phase(h, s.Xs, s.Hs, mask, warp, lane);
+    TC_T(0, step, 0);
+    uint32_t mask[MT];
+    hidden_phase<MT>(h, Xs, Hs, mask, warp, lane);
+    TC_T(0, step, 1);
     if (step && c.relu_mask != nullptr)  // the backward chain gates dH with these bits instead of recomputing the layer
-      reinterpret_cast<uint2*>(c.relu_mask)[((size_t)step * gridDim.x + blockIdx.x) * NTH + threadIdx.x] = make_uint2(mask[0], mask[1]);
+      reinterpret_cast<uint2*>(c.relu_mask)[((size_t)step * gridDim.x + blockIdx.x) * NTH + threadIdx.x] =
+          make_uint2(mask[0], MT > 1 ? mask[MT - 1] : 0u);
     __syncthreads();
-    output_phase(h, s.Hs, nullptr, 0, row0, c.rows, s.Fs, warp, lane);
+    TC_T(0, step, 2);
+    if (8 * warp < d) {  // Y = H W2^T + b2: warp w owns outputs [8 w, 8 w + 8) -> Fs
+      float acc[MT][4];
+      gemm_tall<MT>(acc, Hs, HLD, h.w2p, warp, lane);
+      const int o = 8 * warp + 2 * t;
+      const float b0 = o < d ? __ldg(h.b2 + o) : 0.0f, b1 = o + 1 < d ? __ldg(h.b2 + o + 1) : 0.0f;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          Fs[(16 * mt + g + 8 * half) * FLD + o] = acc[mt][2 * half] + b0;
+          Fs[(16 * mt + g + 8 * half) * FLD + o + 1] = acc[mt][2 * half + 1] + b1;
+        }
+      }
+    }
+    TC_T(0, step, 3);
     __syncthreads();
+    TC_T(0, step, 4);
     // LayerNorm (networks.py:144, eps 1e-5, biased variance) + ReLU, one-hot action appended: the next step's input
     float v[CPL], sum = 0.0f;
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
-      v[i] = c8 + LPR * i < d ? s.Fs[r * FLD + c8 + LPR * i] : 0.0f;
+      v[i] = c8 + LPR * i < d ? Fs[r * FLD + c8 + LPR * i] : 0.0f;
       sum += v[i];
     }
 #pragma unroll
@@ -547,18 +597,20 @@ __global__ void __launch_bounds__(NTH) chain_fwd_kernel(mz_tc_chain c) {
         out = (col - d == act) ? 1.0f : 0.0f;
       }
       if (live && col < d + A) c.xs[grow * c.ldxs + col] = out;
-      s.Xs[r * XLD + col] = __float2bfloat16_rn(live ? out : 0.0f);
+      Xs[r * XLD + col] = __float2bfloat16_rn(live ? out : 0.0f);
     }
     for (int col = 64 + c8; col < next_pad; col += LPR) {  // d + A > 64 (A = 18): the rest of the one-hot
       const float out = (col < d + A && col - d == act) ? 1.0f : 0.0f;
       if (live && col < d + A) c.xs[grow * c.ldxs + col] = out;
-      s.Xs[r * XLD + col] = __float2bfloat16_rn(out);
+      Xs[r * XLD + col] = __float2bfloat16_rn(out);
     }
     if (live && c8 == 0) {
       c.mean[grow] = mean;
       c.rstd[grow] = rstd;
     }
+    TC_T(0, step, 5);
     __syncthreads();
+    TC_T(0, step, 6);
   }
 }
 
@@ -566,10 +618,12 @@ __global__ void __launch_bounds__(NTH) chain_fwd_kernel(mz_tc_chain c) {
 // -> dH = dY W2 gated by the forward's ReLU bits -> dX = dH W1 -> next LayerNorm backward.  The parameter gradients of
 // the two heads do not sit on this chain: mz_heads_backward_tc computes them afterwards from (xs, dyall) over all
 // K B + B rows in parallel.
+template <int CPL>
 struct LnIn {
   float up[CPL], hv[CPL], yv[CPL], mean, rstd;
 };
-MZ_DEV void ln_load(LnIn& v, const mz_tc_chain& c, int step, int row, bool live, int c8) {
+template <int CPL, int LPR>
+MZ_DEV void ln_load(LnIn<CPL>& v, const mz_tc_chain& c, int step, int row, bool live, int c8) {
   const size_t grow = (size_t)step * c.rows + row;
 #pragma unroll
   for (int i = 0; i < CPL; ++i) {
@@ -583,13 +637,16 @@ MZ_DEV void ln_load(LnIn& v, const mz_tc_chain& c, int step, int row, bool live,
   v.rstd = live ? c.rstd[grow] : 0.0f;
 }
 
+template <int MT>
 __global__ void __launch_bounds__(NTH) chain_bwd_kernel(mz_tc_chain c) {
+  using G = ChainGeo<MT>;
+  constexpr int ROWS = G::ROWS, LPR = G::LPR, CPL = G::CPL;
   extern __shared__ __align__(16) unsigned char tc_smem[];
-  const int row0 = blockIdx.x * RT;
+  const int row0 = blockIdx.x * ROWS;
   __nv_bfloat16* dYs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
-  __nv_bfloat16* dHs = dYs + RT * DYLD;
-  float* Fs = reinterpret_cast<float*>(dHs + RT * HLD);
-  float* red = Fs + RT * FLD;  // [2][64]
+  __nv_bfloat16* dHs = dYs + ROWS * DYLD;
+  float* Fs = reinterpret_cast<float*>(dHs + ROWS * HLD);
+  float* red = Fs + ROWS * FLD;  // [2][64]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = c.d, out_pad = round_up32(d);
   const int r = (32 / LPR) * warp + lane / LPR, c8 = lane % LPR, row = row0 + r;
@@ -603,10 +660,10 @@ __global__ void __launch_bounds__(NTH) chain_bwd_kernel(mz_tc_chain c) {
     gam[i] = c8 + LPR * i < d ? __ldg(c.gamma + c8 + LPR * i) : 0.0f;
     gg[i] = gb[i] = 0.0f;
   }
-  LnIn cur, nxt;
-  ln_load(cur, c, c.steps - 1, row, live, c8);
+  LnIn<CPL> cur, nxt;
+  ln_load<CPL, LPR>(cur, c, c.steps - 1, row, live, c8);
   for (int step = c.steps - 1; step >= 0; --step) {
-    if (step) ln_load(nxt, c, step - 1, row, live, c8);  // in flight during this step's contractions
+    if (step) ln_load<CPL, LPR>(nxt, c, step - 1, row, live, c8);  // in flight during this step's contractions
     uint2 mbits = make_uint2(0u, 0u);
     if (step) mbits = reinterpret_cast<const uint2*>(c.relu_mask)[((size_t)step * gridDim.x + blockIdx.x) * NTH + threadIdx.x];
     // backward of relu(LayerNorm(y)): gradient = heads' part (+ the dynamics head's dX of the step after), scaled by
@@ -645,19 +702,19 @@ __global__ void __launch_bounds__(NTH) chain_bwd_kernel(mz_tc_chain c) {
     {  // dH = dY W2 for the warp's hidden units, gated by the forward's ReLU bits -> dHs
       const mz_tc_head& h = c.next;
       const int g = lane >> 2, t = lane & 3;
-      float acc[2][NTW][4];
+      float acc[MT][NTW][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int n = 0; n < NTW; ++n)
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[mt][n][q] = 0.0f;
-      gemm_wide(acc, dYs, DYLD, h.w2tp, round_up32(h.d_out) >> 5, NTW * warp, lane);
+      gemm_wide<MT>(acc, dYs, DYLD, h.w2tp, round_up32(h.d_out) >> 5, NTW * warp, lane);
 #pragma unroll
       for (int n = 0; n < NTW; ++n) {
         const int j = CW * warp + 8 * n + 2 * t;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
           const uint32_t m = (mt ? mbits.y : mbits.x) >> (4 * n);
           *reinterpret_cast<uint32_t*>(dHs + (16 * mt + g) * HLD + j) =
               pack2((m & 1u) ? acc[mt][n][0] : 0.0f, (m & 2u) ? acc[mt][n][1] : 0.0f);
@@ -668,11 +725,11 @@ __global__ void __launch_bounds__(NTH) chain_bwd_kernel(mz_tc_chain c) {
       __syncthreads();
       // dX = dH W1, the hidden-state columns only -> Fs
       for (int nt = warp; 8 * nt < d; nt += NW) {
-        float a2[2][4];
-        gemm_tall(a2, dHs, HLD, h.w1tp, nt, lane);
+        float a2[MT][4];
+        gemm_tall<MT>(a2, dHs, HLD, h.w1tp, nt, lane);
         const int k = 8 * nt + 2 * t;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             Fs[(16 * mt + g + 8 * half) * FLD + k] = a2[mt][2 * half];
@@ -684,7 +741,7 @@ __global__ void __launch_bounds__(NTH) chain_bwd_kernel(mz_tc_chain c) {
     __syncthreads();
     cur = nxt;
   }
-  // LayerNorm weight / bias gradients: the four rows of a warp by shuffles, the eight warps through shared memory
+  // LayerNorm weight / bias gradients: the rows of a warp by shuffles, the warps through shared memory
 #pragma unroll
   for (int i = 0; i < CPL; ++i) {
 #pragma unroll
@@ -704,21 +761,26 @@ __global__ void __launch_bounds__(NTH) chain_bwd_kernel(mz_tc_chain c) {
   }
 }
 
-constexpr size_t CHAIN_BWD_SMEM = (size_t)RT * DYLD * 2 + (size_t)RT * HLD * 2 + (size_t)RT * FLD * 4 + 2 * 64 * 4;
-
 bool g_tc_attr = false;
 int tc_attrs() {
   if (g_tc_attr) return 0;
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(heads_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_bwd_smem(1))) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(heads_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_bwd_smem(2))) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_BWD_SMEM)) != cudaSuccess)
+  const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+  if ((e = cudaFuncSetAttribute(heads_fwd_kernel, attr, (int)FWD_SMEM)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(chain_fwd_kernel<1>, attr, (int)ChainGeo<1>::FWD_SMEM)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(chain_fwd_kernel<2>, attr, (int)ChainGeo<2>::FWD_SMEM)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(heads_bwd_kernel<1>, attr, (int)heads_bwd_smem(1))) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(heads_bwd_kernel<2>, attr, (int)heads_bwd_smem(2))) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(chain_bwd_kernel<1>, attr, (int)ChainGeo<1>::BWD_SMEM)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(chain_bwd_kernel<2>, attr, (int)ChainGeo<2>::BWD_SMEM)) != cudaSuccess)
     return (int)e;
   g_tc_attr = true;
   return 0;
 }
+
+// rows per CTA of the chain kernels: 16 while that is at most one wave of CTAs, else 32 (forward and backward of a
+// step must agree: the ReLU bits are stored per CTA and thread)
+int chain_mt(int rows) { return (rows + 15) / 16 <= 148 ? 1 : 2; }
 
 bool head_ok(const mz_tc_head& h, bool backward) {
   if (h.d_in < 1 || h.d_in > 128 || h.d_out < 1 || h.d_out > 64 || !h.w1p || !h.w2p || !h.b1 || !h.b2) return false;
@@ -745,9 +807,15 @@ bool chain_ok(const mz_tc_chain* c, bool backward) {
 
 extern "C" {
 
+#ifdef MZ_TC_TRACE
+__attribute__((visibility("default"))) int mz_debug_tc_trace(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, g_tc_trace, sizeof(long long) * 2 * 2 * 16 * 8);
+}
+#endif
+
 int64_t mz_chain_mask_words(int32_t rows, int32_t steps) {
   if (rows < 1 || steps < 1) return 0;
-  return (int64_t)steps * ((rows + RT - 1) / RT) * NTH * 2;
+  return (int64_t)steps * ((rows + 15) / 16) * NTH * 2;
 }
 
 int64_t mz_learner_packed_words(int32_t n, int32_t k) {
@@ -815,7 +883,10 @@ int mz_heads_backward_tc(int32_t njobs, const mz_tc_job* jobs, void* stream) {
 int mz_chain_forward_tc(const mz_tc_chain* chain, void* stream) {
   if (!chain_ok(chain, false)) return MZ_ERR_BAD_ARG;
   if (int rc = tc_attrs()) return rc;
-  chain_fwd_kernel<<<(chain->rows + RT - 1) / RT, NTH, FWD_SMEM, (cudaStream_t)stream>>>(*chain);
+  if (chain_mt(chain->rows) == 1)
+    chain_fwd_kernel<1><<<(chain->rows + 15) / 16, NTH, ChainGeo<1>::FWD_SMEM, (cudaStream_t)stream>>>(*chain);
+  else
+    chain_fwd_kernel<2><<<(chain->rows + 31) / 32, NTH, ChainGeo<2>::FWD_SMEM, (cudaStream_t)stream>>>(*chain);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }
@@ -823,7 +894,10 @@ int mz_chain_forward_tc(const mz_tc_chain* chain, void* stream) {
 int mz_chain_backward_tc(const mz_tc_chain* chain, void* stream) {
   if (!chain_ok(chain, true)) return MZ_ERR_BAD_ARG;
   if (int rc = tc_attrs()) return rc;
-  chain_bwd_kernel<<<(chain->rows + RT - 1) / RT, NTH, CHAIN_BWD_SMEM, (cudaStream_t)stream>>>(*chain);
+  if (chain_mt(chain->rows) == 1)
+    chain_bwd_kernel<1><<<(chain->rows + 15) / 16, NTH, ChainGeo<1>::BWD_SMEM, (cudaStream_t)stream>>>(*chain);
+  else
+    chain_bwd_kernel<2><<<(chain->rows + 31) / 32, NTH, ChainGeo<2>::BWD_SMEM, (cudaStream_t)stream>>>(*chain);
   MZ_LAUNCH_CHECK();
   return MZ_OK;
 }
