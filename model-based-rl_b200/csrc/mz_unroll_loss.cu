@@ -132,21 +132,19 @@ __global__ void unroll_loss_kernel(mz_loss_cfg c, const float* __restrict__ valu
   }
 }
 
-// (is_weights * loss).mean() for the three losses: fixed-order float64 tree, one CTA.
+// (is_weights * loss).mean() for the three losses: fixed-order float64 tree, one CTA per loss.
 __global__ void loss_mean_kernel(int B, const double* __restrict__ row_losses, double* __restrict__ losses) {
   __shared__ double s[256];
-  for (int which = 0; which < 3; ++which) {
-    double acc = 0.0;
-    for (int b = threadIdx.x; b < B; b += 256) acc += row_losses[(size_t)which * B + b];
-    s[threadIdx.x] = acc;
-    __syncthreads();
-    for (int k = 128; k > 0; k >>= 1) {
-      if (threadIdx.x < k) s[threadIdx.x] += s[threadIdx.x + k];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) losses[which] = s[0] / (double)B;
+  const int which = blockIdx.x;
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < B; b += 256) acc += row_losses[(size_t)which * B + b];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) s[threadIdx.x] += s[threadIdx.x + k];
     __syncthreads();
   }
+  if (threadIdx.x == 0) losses[which] = s[0] / (double)B;
 }
 
 }  // namespace
@@ -167,7 +165,7 @@ extern "C" int mz_unroll_loss(const mz_loss_cfg* c, const float* value_logits, c
       *c, value_logits, reward_logits, policy_logits, t_values, t_rewards, t_policies, is_weights, d_value_logits,
       d_reward_logits, d_policy_logits, row_losses, new_errors);
   MZ_LAUNCH_CHECK();
-  loss_mean_kernel<<<1, 256, 0, st>>>(c->batch, row_losses, losses);
+  loss_mean_kernel<<<3, 256, 0, st>>>(c->batch, row_losses, losses);
   MZ_LAUNCH_CHECK();
   return 0;
 }
