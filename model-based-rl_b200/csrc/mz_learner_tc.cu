@@ -311,6 +311,7 @@ MZ_DEV void backward_tiles(const mz_tc_head& h, const __nv_bfloat16* Xs, const _
                            __nv_bfloat16* dHs, float* __restrict__ dX, int lddx, int dx_cols, int row0, int rows,
                            float* stage, int warp, int lane) {
   const int g = lane >> 2, t = lane & 3;
+  TC_T(1, 0, 1);
   float s0[NTW], s1[NTW];  // column sums of the gated dH: gb1
 #pragma unroll
   for (int n = 0; n < NTW; ++n) s0[n] = s1[n] = 0.0f;
@@ -358,7 +359,9 @@ MZ_DEV void backward_tiles(const mz_tc_head& h, const __nv_bfloat16* Xs, const _
       atomicAdd(h.gb1 + CW * warp + 8 * n + 2 * t + 1, s1[n]);
     }
   }
+  TC_T(1, 0, 2);
   __syncthreads();
+  TC_T(1, 0, 3);
   // dX = dH W1: (tile, n-tile) pairs over the warps
   if (dx_cols > 0 && !(MZ_TC_SKIP & 4)) {
     const int ntl = (dx_cols + 7) >> 3;
@@ -380,6 +383,7 @@ MZ_DEV void backward_tiles(const mz_tc_head& h, const __nv_bfloat16* Xs, const _
       }
     }
   }
+  TC_T(1, 0, 4);
   if (MZ_TC_SKIP & 2) return;
   const int lrow = lane & 7, lsel = lane >> 3;  // ldmatrix.trans: lanes 8 i .. 8 i + 7 address matrix i
   // gW2[o][j] = sum_r dY[r][o] H[r][j]: M = outputs (16 per m-tile), N = the warp's hidden units, K = the CTA's rows
@@ -403,6 +407,7 @@ MZ_DEV void backward_tiles(const mz_tc_head& h, const __nv_bfloat16* Xs, const _
     }
     tile_add<NTW>(h.gw2 + (size_t)(16 * mt) * LW + CW * warp, LW, h.d_out - 16 * mt, CW, acc, stage, lane);
   }
+  TC_T(1, 0, 5);
   // gW1[j][k] = sum_r dH[r][j] X[r][k]: M = the warp's hidden units, N = input features in chunks of 64, K = rows
   for (int mt = 0; mt < CW / 16; ++mt) {
     for (int chunk = 0; 64 * chunk < h.d_in; ++chunk) {
@@ -429,6 +434,7 @@ MZ_DEV void backward_tiles(const mz_tc_head& h, const __nv_bfloat16* Xs, const _
                   stage, lane);
     }
   }
+  TC_T(1, 0, 6);
 }
 
 struct Tiles {
@@ -477,6 +483,7 @@ __global__ void __launch_bounds__(NTH) heads_bwd_kernel(PlainParams p) {
   float* stage = reinterpret_cast<float*>(dYs + RTT * DYLD);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const mz_tc_head& h = job.head;
+  TC_T(1, 0, 0);
 #pragma unroll
   for (int tile = 0; tile < TILES; ++tile) {
     load_rows(Xs + tile * RT * XLD, XLD, job.x, job.ldx, row0 + RT * tile, job.rows, h.d_in, round_up32(h.d_in));

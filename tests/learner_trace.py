@@ -23,3 +23,7 @@ for wi, wn in enumerate(("warp 0", "last warp")):
     t = buf[0, wi, step]
     print("  step %d: " % step + ", ".join("%s +%d" % (names[i], t[i] - t[i - 1]) for i in range(1, 7)) + "  | total %d" % (t[6] - t[0]))
 print("whole chain (warp 0): %d cycles" % (buf[0, 0, K, 6] - buf[0, 0, 0, 0]))
+hn = ["loads + gb2 + sync", "hidden + dH", "sync", "dX", "gW2", "gW1"]
+for wi, wn in enumerate(("warp 0", "last warp")):
+  t = buf[1, wi, 0]
+  print("heads_bwd CTA (0, y) last launch, %s: " % wn + ", ".join("%s +%d" % (hn[i - 1], t[i] - t[i - 1]) for i in range(1, 7)) + " | total %d" % (t[6] - t[0]))
