@@ -391,6 +391,7 @@ class FCSearch(object):
                             if noise_frac is None else noise_frac)
     self.use_graph = use_graph
     self.graph = None
+    self._e2e_key = None
     self.use_noise = True
     self.launches_per_move = 0
     self.obs = torch.zeros((G, fcnet.input_dim), dtype=torch.float32, device=dev)
@@ -442,6 +443,7 @@ class FCSearch(object):
       self.fused.enable_record()
       self.fused.enable_trace()
       self.graph = None
+      self._e2e_key = None
       self._fused_plan_key = None
       return
     for lane in self.lanes:
@@ -451,6 +453,7 @@ class FCSearch(object):
                      torch.zeros((self.S, g, self.A), dtype=torch.float32, device=dev))
       lane.eng.enable_trace()
     self.graph = None
+    self._e2e_key = None
 
   @property
   def record(self):
@@ -538,8 +541,91 @@ class FCSearch(object):
     host->device copy of the input blob, normalisation + the move's graph, ONE device->host copy of the
     output blob.  Returns the pinned (actions, root_value, child_visits, init_value)."""
     h = self._pinned()
-    self._in_dev.copy_(self._in_host, non_blocking=True)
     mn, rg = getattr(self, '_obs_norm', (None, None))
+    if self.fused is not None and self.use_graph:
+      # ONE graph launch for the whole call: the input blob's copy, the normalisation, the move, the output blob's
+      # copy (tests/e2e_probe.py: 1081 -> 1048 us per call; copying the noise on a second branch under the initial
+      # inference was measured too and is not faster)
+      key = (bool(self.use_noise), float(self.noise_frac), stream_ptr)
+      if getattr(self, '_fused_plan_key', None) != key:
+        self._fused_plan = self.fused.plan(self, self.use_noise, self.noise_frac, C.c_void_p(stream_ptr))
+        self._fused_plan_key = key
+      for fn, args in self._fused_plan:
+        rc = fn(*args)
+        if rc:
+          _lib.check(rc, fn.__name__)
+      self.launches_per_move = len(self._fused_plan)
+      return
+    if len(self.lanes) == 1:
+      self.launches_per_move = self.lanes[0].enqueue(self.use_noise, self.noise_frac)
+      return
+    main = torch.cuda.current_stream()
+    fork = torch.cuda.Event()
+    fork.record(main)
+    n = 0
+    for lane in self.lanes:
+      lane.stream.wait_event(fork)
+      with torch.cuda.stream(lane.stream):
+        n += lane.enqueue(self.use_noise, self.noise_frac)
+        done = torch.cuda.Event()
+        done.record(lane.stream)
+      main.wait_event(done)
+    self.launches_per_move = n
+
+  @_lib.on_device
+  def run(self):
+    """One move for all games with inputs already in the device staging buffers."""
+    if not self.use_graph:
+      self._enqueue()
+      return
+    if self.graph is None:
+      # warm up once outside capture (lazy module loading, cudaFuncSetAttribute)
+      self._enqueue()
+      torch.cuda.synchronize()
+      self.graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self.graph):
+        self._enqueue()
+    self.graph.replay()
+
+  # -- end-to-end call: host buffers in, host buffers out ----------------------------------------
+  def _pinned(self):
+    if getattr(self, '_h', None) is None:
+      self._in_host, h = _carve(self._in_specs, pin_memory=True)
+      self._out_host, out = _carve(self._out_specs, pin_memory=True)
+      h.update(out)
+      h['obs'] = torch.zeros((self.G, self.net.input_dim), dtype=torch.float32, pin_memory=True)
+      h['legal'].fill_(_all_legal(self.A))
+      h['to_play'].fill_(1)
+      h['temperature'].fill_(1.0)
+      self._h = h
+    return self._h
+
+  def pinned_inputs(self):
+    """Pinned host views of the per-move inputs (one contiguous blob): 'obs_u8' [G, input_dim] uint8,
+    'noise' [G, A] f64, 'uniforms' [G] f64, 'temperature' [G] f64, 'legal' [G] i32 bit masks, 'to_play'
+    [G] i8.  Write the move's inputs here and call `search_pinned()`: no host-side staging copy."""
+    h = self._pinned()
+    return {name: h[name] for name, _, _ in self._in_specs}
+
+  @_lib.on_device
+  def search_pinned(self):
+    """search_host for inputs already written into `pinned_inputs()` (byte observations): ONE
+    host->device copy of the input blob, normalisation + the move's graph, ONE device->host copy of the
+    output blob.  Returns the pinned (actions, root_value, child_visits, init_value)."""
+    h = self._pinned()
+    mn, rg = getattr(self, '_obs_norm', (None, None))
+    if self.fused is not None and self.use_graph:
+      # ONE graph launch for the whole call: the observation bytes cross first and the initial inference starts on
+      # them while the rest of the blob (noise, uniforms, temperatures, masks) crosses on a second branch that joins
+      # in front of the search kernel; the output blob's copy is the graph's last node
+      key = (bool(self.use_noise), float(self.noise_frac), None if mn is None else mn.data_ptr(),
+             None if rg is None else rg.data_ptr())
+      if getattr(self, '_e2e_key', None) != key:
+        self._e2e_graph, self._e2e_key = self._capture_e2e(mn, rg), key
+      self._e2e_graph.replay()
+      torch.cuda.current_stream().synchronize()
+      return h['actions'], h['root_value'], h['child_visits'], h['init_value']
+    self._in_dev.copy_(self._in_host, non_blocking=True)
     _lib.check(self.net.lib.mz_obs_normalize_u8(self.G, self.net.input_dim, _lib.ptr(self.obs_u8), _lib.ptr(mn),
                                                 _lib.ptr(rg), _lib.ptr(self.obs), _lib.current_stream()),
                "mz_obs_normalize_u8")
@@ -547,6 +633,23 @@ class FCSearch(object):
     self._out_host.copy_(self._out_dev, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return h['actions'], h['root_value'], h['child_visits'], h['init_value']
+
+  def _capture_e2e(self, mn, rg):
+    """The CUDA graph behind `search_pinned` (fused path)."""
+    def body():
+      self._in_dev.copy_(self._in_host, non_blocking=True)
+      _lib.check(self.net.lib.mz_obs_normalize_u8(self.G, self.net.input_dim, _lib.ptr(self.obs_u8), _lib.ptr(mn),
+                                                  _lib.ptr(rg), _lib.ptr(self.obs), _lib.current_stream()),
+                 "mz_obs_normalize_u8")
+      self._enqueue()
+      self._out_host.copy_(self._out_dev, non_blocking=True)
+
+    body()  # warm up once outside capture (lazy module loading, cudaFuncSetAttribute)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+      body()
+    return graph
 
   def draw_noise(self, alpha):
     """Node.add_exploration_noise's Dirichlet draw (mcts.py:59) for every root, made on the device from the legal
