@@ -7,7 +7,7 @@ search kernels' `FCNetwork.load_weights` see the usual tensors.  `FusedLearner(p
 
   precision='bf16' (default; csrc/mz_learner_tc.cu: tensor cores, bf16 operands, float32 accumulation, float32 master
   weights / gradients / optimiser state)
-    mz_learner_pack           the 20 weight images as bf16 mma B fragments              1 launch
+    mz_learner_pack           the 20 weight images as bf16 mma B fragments + clears     1 launch
     mz_chain_forward_tc       representation -> LN -> K x (dynamics -> LN)               1 launch
     mz_heads_forward_tc       value / policy / reward heads over all K + 1 steps         1 launch
     mz_unroll_loss            fused loss + logit gradients (csrc/mz_unroll_loss.cu)      2 launches
@@ -15,7 +15,7 @@ search kernels' `FCNetwork.load_weights` see the usual tensors.  `FusedLearner(p
     mz_chain_backward_tc      the serial part: LN backward -> dH -> dX per step          1 launch
     mz_heads_backward_tc      parameter gradients of dynamics + representation           1 launch
     mz_adam_step              AdamW / Adam over the flat buffer                          2 launches
-  -- 10 kernels + 2 memsets per step, 161 us at B = 512, K = 5 (6 200 steps/s on a B200; the torch-module step in a
+  -- 10 kernels per step, 128 us at B = 512, K = 5 (7 800 steps/s on a B200; the torch-module step in a
   CUDA graph: 1 100 us).
 
   precision='f32' (csrc/mz_learner.cu: float32 CUDA-core kernels, one launch per head evaluation; the parity baseline
