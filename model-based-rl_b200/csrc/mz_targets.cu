@@ -686,14 +686,12 @@ build_targets_tma_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict
       const int off = (int)(pos & 3), nbytes = off + max(0, min(KT, rem));
       const int8_t* base = w.to_play + (pos - off);
       for (int q = q0; q * 4 < off + KT; q += LPR) {
-        const int have = min(4, nbytes - q * 4);
-        if (have == 4 || have <= 0) {  // a whole word of the array, or nothing (zero fill)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(s_tp + r * TPS + q * 4)),
-                       "l"(have > 0 ? base + q * 4 : w.to_play), "r"(max(have, 0))
-                       : "memory");
-        } else {  // the last, partial word: byte loads, so that nothing behind the window is touched
-          for (int bb = 0; bb < have; ++bb) s_tp[r * TPS + q * 4 + bb] = __ldg(base + q * 4 + bb);
-        }
+        // a whole word of the array, its first `have` bytes (the last, partial word: the copy's source size keeps
+        // anything behind the window untouched and zero-fills the rest), or nothing (zero fill)
+        const int have = max(0, min(4, nbytes - q * 4));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(s_tp + r * TPS + q * 4)),
+                     "l"(have > 0 ? base + q * 4 : w.to_play), "r"(have)
+                     : "memory");
       }
     }
     for (int q = q0; q < RW; q += LPR) {  // raw rewards pos - 1 .. pos + K + T - 1 (clipped where they are read)
@@ -717,10 +715,15 @@ build_targets_tma_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict
   }
   if (c.fuse_supports) {  // both images are multiples of 16 bytes (rows % 4 == 0) and adjacent: one fill
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4* z = reinterpret_cast<float4*>(s_vs);
-    const int nz = (RB * NP * (vb + rb)) >> 2;
-#pragma unroll 4
-    for (int e = tid; e < nz; e += nthr) z[e] = z4;
+    float4* z = reinterpret_cast<float4*>(s_vs) + tid;
+    float4* const zend = reinterpret_cast<float4*>(s_vs) + ((RB * NP * (vb + rb)) >> 2);
+    for (; z + 3 * nthr < zend; z += 4 * nthr) {  // four stores per trip
+      z[0] = z4;
+      z[nthr] = z4;
+      z[2 * nthr] = z4;
+      z[3 * nthr] = z4;
+    }
+    for (; z < zend; z += nthr) *z = z4;
   }
   cp_async_wait_all();
   __syncthreads();

@@ -446,7 +446,9 @@ class PrioritizedReplay(object):
     e['event'].record()
     args = e['args']
     args[7], args[8], args[26] = self.index.ring.num_memories, float(self.beta), torch.cuda.current_stream().cuda_stream
-    args[18] = int(np.random.randint(1, 1 << 62))  # seed of the device-drawn padding actions
+    if not st.get('seeds'):  # seeds of the device-drawn padding actions: 256 np.random draws at a time
+      st['seeds'] = np.random.randint(1, 1 << 62, size=256).tolist()
+    args[18] = st['seeds'].pop()
     rc = self.lib.mz_replay_sample_targets(*args)
     if rc:
       _lib.check(rc, "mz_replay_sample_targets")
@@ -527,8 +529,8 @@ class PrioritizedReplay(object):
   def _step_beta(self):
     if self.index.num_memories == 0:
       raise _lib.MzError("sample_batch on an empty replay buffer")
-    if self.beta < 1:
-      self.beta = np.min([1., self.beta + self.beta_increment_per_sampling])
+    if self.beta < 1:  # replay_buffer.py:137: np.min([1., beta + increment]) -- same float64 arithmetic, without the array
+      self.beta = min(1., self.beta + self.beta_increment_per_sampling)
 
   def _targets(self, d_pos, d_cs, d_cl, d_pads, fuse_supports):
     B, K, A = self.batch_size, self.num_unroll_steps, self.action_space
