@@ -686,12 +686,16 @@ build_targets_tma_kernel(mz_window w, mz_target_cfg c, const int64_t* __restrict
       const int off = (int)(pos & 3), nbytes = off + max(0, min(KT, rem));
       const int8_t* base = w.to_play + (pos - off);
       for (int q = q0; q * 4 < off + KT; q += LPR) {
-        // a whole word of the array, its first `have` bytes (the last, partial word: the copy's source size keeps
-        // anything behind the window untouched and zero-fills the rest), or nothing (zero fill)
+        // a whole word of the array -- also for the window's last, partial word while that word still lies inside
+        // the chunk (bytes behind the window are read but never used) --, or nothing (zero fill)
         const int have = max(0, min(4, nbytes - q * 4));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(s_tp + r * TPS + q * 4)),
-                     "l"(have > 0 ? base + q * 4 : w.to_play), "r"(have)
-                     : "memory");
+        if (have == 0 || q * 4 + 4 <= off + rem) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(s_tp + r * TPS + q * 4)),
+                       "l"(have > 0 ? base + q * 4 : w.to_play), "r"(have > 0 ? 4 : 0)
+                       : "memory");
+        } else {  // the chunk (and possibly the array) ends inside this word: byte loads
+          for (int bb = 0; bb < 4; ++bb) s_tp[r * TPS + q * 4 + bb] = bb < have ? __ldg(base + q * 4 + bb) : (int8_t)0;
+        }
       }
     }
     for (int q = q0; q < RW; q += LPR) {  // raw rewards pos - 1 .. pos + K + T - 1 (clipped where they are read)
