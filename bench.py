@@ -433,6 +433,20 @@ def run_b200(args):
                 "network": "fc_recurrent_f32_kernel (float32 CUDA cores; parity bar vs the reference's torch module: "
                            "1e-4, tests/test_gpu_fcnet.py)", "same_workload": True}
     del fs32, net32
+    # and with the float32-accurate TENSOR-CORE network kernel (three TF32 products per multiply)
+    net3 = FCNetwork(args.obs_dim, A, dev, cfg, precision="tf32x3")
+    net3.load_weights(sd)
+    fs3 = FCSearch(cfg, net3, G, use_graph=not args.no_graph, num_streams=args.streams)
+    fs3.search_host(h_obs, h_noise, h_u, h_t)
+    for _ in range(args.warmup):
+      fs3.run()
+    torch.cuda.synchronize()
+    ms3 = timed(fs3.run, n32)
+    f32_line["tensor_core"] = {
+        "value": G * S * n32 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / n32, "steps": n32,
+        "network": "fc_recurrent_tf32x3_kernel (mma.sync TF32 x 3 on split operands, float32 accumulate; same parity "
+                   "bars as the CUDA-core kernel + 2e-5 against it, tests/test_gpu_fcnet.py)"}
+    del fs3, net3
 
   t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
   if world > 1:

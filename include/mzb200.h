@@ -229,6 +229,19 @@ int mz_fc_recurrent_f32(const mz_fc_weights* w, int32_t batch, const float* hidd
                         float* reward, float* logits, void* stream);
 
 /*
+ * float32-ACCURATE tensor-core path (csrc/mz_fcnet_tf32.cu): the arguments and the results (within float32
+ * rounding) of mz_fc_initial_f32 / mz_fc_recurrent_f32, every Linear layer (networks.py:55-119) on the tensor
+ * cores as three TF32 instructions per product on split operands (x_lo*w_hi + x_hi*w_lo + x_hi*w_hi, float32
+ * accumulation).  MZ_ERR_UNSUPPORTED when obs_dim is too wide for the shared-memory budget (~450).
+ */
+int mz_fc_initial_tf32x3(const mz_fc_weights* w, int32_t batch, const float* obs, float* hidden,
+                         int64_t hidden_stride, float* value, float* logits, void* stream);
+int mz_fc_recurrent_tf32x3(const mz_fc_weights* w, int32_t batch, const float* hidden_in,
+                           int64_t in_row_stride, const int32_t* in_index, const int32_t* actions,
+                           float* hidden_out, int64_t out_row_stride, int64_t out_offset, float* value,
+                           float* reward, float* logits, void* stream);
+
+/*
  * bf16 tensor-core path (tcgen05.mma, accumulators in TMEM, fp32 accumulation) of
  * recurrent_inference.  The weights are first re-packed once per weight update into the
  * shared-memory image the MMA consumes:

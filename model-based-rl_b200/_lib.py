@@ -134,6 +134,9 @@ _SIGNATURES = {
     "mz_fc_initial_f32": (C.c_int, [C.POINTER(FcWeights), C.c_int32, _V, _V, C.c_int64, _V, _V, _V]),
     "mz_fc_recurrent_f32": (C.c_int, [C.POINTER(FcWeights), C.c_int32, _V, C.c_int64, _V, _V, _V,
                                       C.c_int64, C.c_int64, _V, _V, _V, _V]),
+    "mz_fc_initial_tf32x3": (C.c_int, [C.POINTER(FcWeights), C.c_int32, _V, _V, C.c_int64, _V, _V, _V]),
+    "mz_fc_recurrent_tf32x3": (C.c_int, [C.POINTER(FcWeights), C.c_int32, _V, C.c_int64, _V, _V, _V,
+                                         C.c_int64, C.c_int64, _V, _V, _V, _V]),
     "mz_fc_tc_packed_bytes": (C.c_int64, [C.c_int32]),
     "mz_debug_set_tc_trace": (C.c_int, [_V]),
     "mz_debug_set_targets_kernel": (C.c_int, [C.c_int32]),

@@ -45,10 +45,12 @@ class FCNetwork(object):
 
   def __init__(self, input_dim, action_space, device, config, precision='bf16'):
     """precision: 'bf16' = tcgen05 tensor-core kernel for recurrent_inference (bf16 operands, fp32
-    accumulation); 'f32' = CUDA-core float32 kernel (reference precision, used for parity)."""
+    accumulation); 'f32' = CUDA-core float32 kernel (reference precision, used for parity); 'tf32x3' =
+    reference precision on the tensor cores (three TF32 instructions per product on split operands,
+    float32 accumulation: the results of 'f32' within float32 rounding)."""
     _lib.require_cuda()
-    if precision not in ('bf16', 'f32'):
-      raise ValueError("precision must be 'bf16' or 'f32'")
+    if precision not in ('bf16', 'f32', 'tf32x3'):
+      raise ValueError("precision must be 'bf16', 'f32' or 'tf32x3'")
     self.precision = precision
     if getattr(config, 'no_support', False):
       raise NotImplementedError("no_support networks are not on the B200 path")
@@ -173,8 +175,9 @@ class FCNetwork(object):
       return self.lib.mz_fc_initial_tc, (self.weights, P(self._tc_init_packed), P(self._tc_init_tail), B,
                                          P(obs), P(hidden_out), int(hidden_stride), P(value), P(logits),
                                          stream)
-    return self.lib.mz_fc_initial_f32, (self.weights, B, P(obs), P(hidden_out), int(hidden_stride),
-                                        P(value), P(logits), stream)
+    fn = self.lib.mz_fc_initial_tf32x3 if self.precision == 'tf32x3' and self.input_dim <= 448 \
+        else self.lib.mz_fc_initial_f32
+    return fn, (self.weights, B, P(obs), P(hidden_out), int(hidden_stride), P(value), P(logits), stream)
 
   @_lib.on_device
   def recurrent_inference(self, hidden_state, action):
@@ -197,11 +200,14 @@ class FCNetwork(object):
           int(out_row_stride), int(out_offset), _lib.ptr(value), _lib.ptr(reward), _lib.ptr(logits),
           _lib.current_stream()), "mz_fc_recurrent_tc")
       return
-    _lib.check(self.lib.mz_fc_recurrent_f32(
-        self.weights, B, _lib.ptr(hidden_in), int(in_row_stride), _lib.ptr(in_index),
-        _lib.ptr(actions), _lib.ptr(hidden_out), int(out_row_stride), int(out_offset),
-        _lib.ptr(value), _lib.ptr(reward), _lib.ptr(logits), _lib.current_stream()),
-               "mz_fc_recurrent_f32")
+    fn = self.recurrent_f32_fn()
+    _lib.check(fn(self.weights, B, _lib.ptr(hidden_in), int(in_row_stride), _lib.ptr(in_index),
+                  _lib.ptr(actions), _lib.ptr(hidden_out), int(out_row_stride), int(out_offset),
+                  _lib.ptr(value), _lib.ptr(reward), _lib.ptr(logits), _lib.current_stream()), fn.__name__)
+
+  def recurrent_f32_fn(self):
+    """The float32-accurate recurrent_inference entry point: CUDA cores ('f32') or tensor cores ('tf32x3')."""
+    return self.lib.mz_fc_recurrent_tf32x3 if self.precision == 'tf32x3' else self.lib.mz_fc_recurrent_f32
 
   def _buffers(self, B):
     dev = self.device
@@ -262,7 +268,7 @@ class _Lane(object):
       if bf16:
         plan.append((lib.mz_fc_recurrent_tc, (net.weights, P(net._tc_packed), P(net._tc_tail)) + tail))
       else:
-        plan.append((lib.mz_fc_recurrent_f32, (net.weights,) + tail))
+        plan.append((net.recurrent_f32_fn(), (net.weights,) + tail))
       plan.append((lib.mz_tree_step, (tree, sim, P(v), P(r), P(l), None, None) +
                    eng._trace_ptrs(sim + 1) + (st,)))
     plan.append((lib.mz_tree_root_stats, (tree, P(eng.visits), P(eng.child_visits), P(eng.root_value),

@@ -24,10 +24,13 @@ def _net_from_golden(g, obs_dim, A, precision="f32"):
   return net
 
 
+@pytest.mark.parametrize("precision", ["f32", "tf32x3"])
 @pytest.mark.parametrize("name,obs_dim,A", [("atari18", 128, 18), ("ttt", 9, 9)])
-def test_fc_f32_matches_torch_reference(name, obs_dim, A):
+def test_fc_f32_matches_torch_reference(name, obs_dim, A, precision):
+  """Both float32-accurate paths (CUDA cores; tensor cores with three TF32 products per multiply) against the
+  outputs of the reference's torch module, at the same bars."""
   g = load("fcnet_" + name)
-  net = _net_from_golden(g, obs_dim, A)
+  net = _net_from_golden(g, obs_dim, A, precision)
   obs = torch.from_numpy(g["obs"]).cuda()
   init = net.initial_inference(obs)
   torch.cuda.synchronize()
@@ -46,6 +49,40 @@ def test_fc_f32_matches_torch_reference(name, obs_dim, A):
   sd = net.get_weights()
   assert set(sd) == {k[2:] for k in g if k.startswith("w_")}
   assert np.array_equal(sd["LN.weight"].numpy(), g["w_LN.weight"])
+
+
+@pytest.mark.parametrize("name,obs_dim,A", [("atari18", 128, 18), ("ttt", 9, 9)])
+@pytest.mark.parametrize("batch", [1, 31, 129, 1000])
+def test_fc_tf32x3_matches_f32_kernel(name, obs_dim, A, batch):
+  """mz_fc_*_tf32x3 (split-TF32 tensor-core products) against the CUDA-core float32 kernels on the same weights:
+  float32 rounding level (different summation order only) -- 2e-5 on hidden states and logits; the scalars go
+  through softmax + h^-1, which amplifies last-bit differences (same bar as against torch).  Ragged last CTAs,
+  gather through in_index / scatter at an offset like the search engine's calls."""
+  g = load("fcnet_" + name)
+  tc = _net_from_golden(g, obs_dim, A, "tf32x3")
+  f32 = _net_from_golden(g, obs_dim, A, "f32")
+  gen = torch.Generator(device="cuda").manual_seed(11 + batch)
+  obs = torch.rand((batch, obs_dim), device="cuda", generator=gen)
+  a, b = f32.initial_inference(obs), tc.initial_inference(obs)
+  torch.cuda.synchronize()
+  for x, y, tol in ((a.hidden_state, b.hidden_state, 2e-5), (a.policy_logits, b.policy_logits, 2e-5),
+                    (a.value, b.value, 1e-3)):
+    assert torch.allclose(x, y, rtol=tol, atol=tol), (x - y).abs().max().item()
+  # raw form: three candidate parent rows per game, the kernel picks in_index[b]; output at slot 3
+  pool = torch.rand((batch, 4, 50), device="cuda", generator=gen) * 2.0
+  idx = torch.randint(0, 3, (batch,), device="cuda", generator=gen, dtype=torch.int32)
+  act = torch.randint(0, A, (batch,), device="cuda", generator=gen, dtype=torch.int32)
+  outs = []
+  for net in (f32, tc):
+    p = pool.clone()
+    v, r = torch.empty((batch, 1), device="cuda"), torch.empty((batch, 1), device="cuda")
+    l = torch.empty((batch, A), device="cuda")
+    net.recurrent_into(p, 200, idx, act, p, 200, 150, v, r, l)
+    torch.cuda.synchronize()
+    assert torch.equal(p[:, :3], pool[:, :3])
+    outs.append((p[:, 3].clone(), l, v, r))
+  for x, y, tol in zip(outs[0], outs[1], (2e-5, 2e-5, 1e-3, 1e-3)):
+    assert torch.allclose(x, y, rtol=tol, atol=tol), (x - y).abs().max().item()
 
 
 @pytest.mark.parametrize("name,obs_dim,A", [("atari18", 128, 18), ("ttt", 9, 9)])
