@@ -30,14 +30,12 @@ constexpr int LDA = 520;         // row stride of the first-layer activations: 8
 constexpr int LDO = 72;          // row stride of second-layer outputs (<= 64 columns)
 constexpr int LDR = 64;          // row stride of a partial-sum slot
 
-MZ_DEV uint32_t tf32_of(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// x = hi + lo with hi = x rounded to TF32's 11 significant bits (half up in magnitude, as an integer add on the bit
+// pattern: `cvt.rna.tf32.f32` compiles to five instructions on sm_100a because it also handles Inf / NaN, which the
+// network's activations and weights never are) and lo = the exact float32 remainder cut to its top 11 bits
 MZ_DEV void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = tf32_of(x);
-  lo = tf32_of(x - __uint_as_float(hi));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
 }
 MZ_DEV void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
@@ -46,8 +44,9 @@ MZ_DEV void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-MZ_DEV float4 load4(const float* __restrict__ p, bool ok) {
-  return ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+// weight row k of a first layer, this thread's four columns; rows past K - 1 read row K - 1 (their x column is zero)
+MZ_DEV float4 load4(const float* __restrict__ wcol, int k, int K) {
+  return __ldg(reinterpret_cast<const float4*>(wcol + (size_t)min(k, K - 1) * W));
 }
 
 // out[r][n] = relu(b1[n] + sum_{k < K} x[r][k] * w1t[k][n] (+ w1t[K + act[r]][n])), n < 512, r < 32.
@@ -64,16 +63,16 @@ MZ_DEV void first_layer(const float* __restrict__ w1t, const float* __restrict__
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.0f;
   const int ksteps = (K + 7) >> 3;
-  const float* wcol = w1t + n0 + g * 4 + (size_t)t * W;  // row t (and t + 4) of a k step, this thread's 4 columns
+  const float* wcol = w1t + n0 + g * 4;  // this thread's 4 columns; rows t and t + 4 of a k step
   // weight rows of the next two k steps are in flight while a step computes
-  float4 p0a = load4(wcol, t < K), p0b = load4(wcol + 4 * W, t + 4 < K);
-  float4 p1a = load4(wcol + 8 * W, 8 + t < K), p1b = load4(wcol + 12 * W, 12 + t < K);
+  float4 p0a = load4(wcol, t, K), p0b = load4(wcol, t + 4, K);
+  float4 p1a = load4(wcol, 8 + t, K), p1b = load4(wcol, 12 + t, K);
   for (int ks = 0; ks < ksteps; ++ks) {
     const int k0 = ks * 8;
     const float4 ca = p0a, cb = p0b;
     p0a = p1a, p0b = p1b;
-    p1a = load4(wcol + (size_t)(k0 + 16) * W, k0 + 16 + t < K);
-    p1b = load4(wcol + (size_t)(k0 + 20) * W, k0 + 20 + t < K);
+    p1a = load4(wcol, k0 + 16 + t, K);
+    p1b = load4(wcol, k0 + 20 + t, K);
     uint32_t ah[2][4], al[2][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -141,25 +140,45 @@ MZ_DEV void first_layer(const float* __restrict__ w1t, const float* __restrict__
     }
 }
 
-// partial second layer of one warp: rows of tile (warp & 1), k in [64 (warp >> 1), +64), all N2 <= 64 outputs
-MZ_DEV void second_partial(const float* __restrict__ w2, const float* in, int N2, float (&acc)[8][4]) {
+// Second layers.  Warp (warp & 1, warp >> 1) = (row tile, k slice of 64); NT = compile-time bound of the n tiles.
+// A warp's B fragments of k step s: NT 8-byte loads, issued one step ahead (the first ones before the barrier that
+// ends the first layers) so that the L2 round trip runs under the previous step's instructions.
+template <int NT>
+struct W2Frag {
+  float2 v[NT > 0 ? NT : 1];
+};
+template <int NT>
+MZ_DEV void w2_prefetch(W2Frag<NT>& f, const float* __restrict__ w2, int N2, int s) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const float* wr = w2 + (warp >> 1) * 64 + 2 * t + 8 * s;
+  const int ntiles = (N2 + 7) >> 3;
+  // rows past N2 read the last row instead: their output columns are never reduced (no select behind the load, which
+  // would wait for it right here)
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+    if (nt < ntiles) f.v[nt] = __ldg(reinterpret_cast<const float2*>(wr + (size_t)min(nt * 8 + g, N2 - 1) * W));
+}
+// partial second layer of one warp: rows of tile (warp & 1), k in [64 (warp >> 1), +64), all N2 <= 8 NT outputs
+template <int NT>
+MZ_DEV void second_partial(W2Frag<NT>& f, const float* __restrict__ w2, const float* in, int N2, float (&acc)[NT > 0 ? NT : 1][4]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int mt = warp & 1, kw = (warp >> 1) * 64;
   const int ntiles = (N2 + 7) >> 3;
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
+  for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
   const float* x0 = in + (mt * 16 + g) * LDA + kw + 2 * t;
-  const float* wr = w2 + (size_t)g * W + kw + 2 * t;
 #pragma unroll 2
   for (int s = 0; s < 8; ++s) {
-    float2 wv[8];
+    uint32_t bh[NT > 0 ? NT : 1][2], bl[NT > 0 ? NT : 1][2];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-      if (nt < ntiles)
-        wv[nt] = nt * 8 + g < N2 ? __ldg(reinterpret_cast<const float2*>(wr + (size_t)nt * 8 * W + 8 * s))
-                                 : make_float2(0.0f, 0.0f);
+    for (int nt = 0; nt < NT; ++nt)
+      if (nt < ntiles) {
+        split_tf32(f.v[nt].x, bh[nt][0], bl[nt][0]);
+        split_tf32(f.v[nt].y, bh[nt][1], bl[nt][1]);
+      }
+    if (s + 1 < 8) w2_prefetch<NT>(f, w2, N2, s + 1);
     const float2 xa = *reinterpret_cast<const float2*>(x0 + 8 * s);
     const float2 xb = *reinterpret_cast<const float2*>(x0 + 8 * LDA + 8 * s);
     uint32_t ah[4], al[4];
@@ -167,31 +186,25 @@ MZ_DEV void second_partial(const float* __restrict__ w2, const float* in, int N2
     split_tf32(xb.x, ah[1], al[1]);
     split_tf32(xa.y, ah[2], al[2]);
     split_tf32(xb.y, ah[3], al[3]);
-    uint32_t bh[8][2], bl[8][2];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-      if (nt < ntiles) {
-        split_tf32(wv[nt].x, bh[nt][0], bl[nt][0]);
-        split_tf32(wv[nt].y, bh[nt][1], bl[nt][1]);
-      }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
       if (nt < ntiles) mma_tf32(acc[nt], al, bh[nt]);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
       if (nt < ntiles) mma_tf32(acc[nt], ah, bl[nt]);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
       if (nt < ntiles) mma_tf32(acc[nt], ah, bh[nt]);
   }
 }
 // a warp's partial sums -> slot (warp >> 1) of `red` ([8][R][LDR])
-MZ_DEV void store_partial(const float (&acc)[8][4], int N2, float* red) {
+template <int NT>
+MZ_DEV void store_partial(const float (&acc)[NT > 0 ? NT : 1][4], int N2, float* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int mt = warp & 1, ntiles = (N2 + 7) >> 3;
   float* base = red + ((warp >> 1) * R + mt * 16 + g) * LDR + 2 * t;
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
+  for (int nt = 0; nt < NT; ++nt)
     if (nt < ntiles) {
       *reinterpret_cast<float2*>(base + nt * 8) = make_float2(acc[nt][0], acc[nt][1]);
       *reinterpret_cast<float2*>(base + 8 * LDR + nt * 8) = make_float2(acc[nt][2], acc[nt][3]);
@@ -250,27 +263,49 @@ MZ_DEV Smem carve(float* base) {
 }
 size_t smem_bytes(int ldx) { return sizeof(float) * (size_t)(2 * R * LDA + R * LDH + 2 * R * LDO + R + R * ldx); }
 
-// two heads that read the same input: first layers -> a[0], a[1]; second layers -> o0 [R][ldo0], o1 [R][ldo1]
-MZ_DEV void head_pair(const Smem& s, const float* x, int ldx, int K, const int* act, const float* w1a, const float* b1a,
-                      const float* w2a, const float* b2a, int Na, float* oa, int ldoa, const float* w1b,
-                      const float* b1b, const float* w2b, const float* b2b, int Nb, float* ob, int ldob) {
+// two heads that read the same input: first layers -> a[0], a[1]; second layers -> oa [R][ldoa], ob [R][ldob]
+// (NTA / NTB: bounds of the heads' n tiles; NTB = 0: one head)
+template <int NTA, int NTB>
+MZ_DEV void head_pair_t(const Smem& s, const float* x, int ldx, int K, const int* act, const float* w1a,
+                        const float* b1a, const float* w2a, const float* b2a, int Na, float* oa, int ldoa,
+                        const float* w1b, const float* b1b, const float* w2b, const float* b2b, int Nb, float* ob,
+                        int ldob) {
   float* a0 = s.a;
   float* a1 = s.a + R * LDA;
   first_layer(w1a, b1a, x, ldx, K, act, a0);
-  if (w1b) first_layer(w1b, b1b, x, ldx, K, act, a1);
+  if (NTB > 0) first_layer(w1b, b1b, x, ldx, K, act, a1);
+  W2Frag<NTA> fa;
+  W2Frag<NTB> fb;
+  w2_prefetch<NTA>(fa, w2a, Na, 0);
+  if (NTB > 0) w2_prefetch<NTB>(fb, w2b, Nb, 0);
   __syncthreads();
-  float acc_a[8][4], acc_b[8][4];
-  second_partial(w2a, a0, Na, acc_a);
-  if (w1b) second_partial(w2b, a1, Nb, acc_b);
+  float acc_a[NTA][4], acc_b[NTB > 0 ? NTB : 1][4];
+  second_partial<NTA>(fa, w2a, a0, Na, acc_a);
+  if (NTB > 0) second_partial<NTB>(fb, w2b, a1, Nb, acc_b);
   __syncthreads();  // every warp is done with the activations: their storage takes the partial sums
   float* red_a = s.a;
   float* red_b = s.a + 8 * R * LDR;
-  store_partial(acc_a, Na, red_a);
-  if (w1b) store_partial(acc_b, Nb, red_b);
+  store_partial<NTA>(acc_a, Na, red_a);
+  if (NTB > 0) store_partial<NTB>(acc_b, Nb, red_b);
   __syncthreads();
   reduce_partials(red_a, b2a, Na, oa, ldoa);
-  if (w1b) reduce_partials(red_b, b2b, Nb, ob, ldob);
+  if (NTB > 0) reduce_partials(red_b, b2b, Nb, ob, ldob);
   __syncthreads();
+}
+MZ_DEV void head_pair(const Smem& s, const float* x, int ldx, int K, const int* act, const float* w1a, const float* b1a,
+                      const float* w2a, const float* b2a, int Na, float* oa, int ldoa, const float* w1b,
+                      const float* b1b, const float* w2b, const float* b2b, int Nb, float* ob, int ldob) {
+#define MZ_HP(NTA, NTB) \
+  head_pair_t<NTA, NTB>(s, x, ldx, K, act, w1a, b1a, w2a, b2a, Na, oa, ldoa, w1b, b1b, w2b, b2b, Nb, ob, ldob)
+  if (!w1b)
+    MZ_HP(8, 0);
+  else if (Na <= 32 && Nb <= 32)
+    MZ_HP(4, 4);
+  else if (Na <= 32)
+    MZ_HP(4, 8);
+  else
+    MZ_HP(8, 8);
+#undef MZ_HP
 }
 
 // prediction (networks.py:151-157) from s.h; writes value [B], logits [B][A]
