@@ -62,6 +62,9 @@ MZ_DEV void first_layer(const float* __restrict__ w1t, const float* __restrict__
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.0f;
+  // the epilogue's operands (this warp's 128-byte line of the bias and of each row's one-hot weight row) -> L1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(act ? w1t + (size_t)(K + act[lane]) * W + n0 : b1 + n0));
+  if (act && lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(b1 + n0));
   const int ksteps = (K + 7) >> 3;
   const float* wcol = w1t + n0 + g * 4;  // this thread's 4 columns; rows t and t + 4 of a k step
   // weight rows of the next two k steps are in flight while a step computes
@@ -263,28 +266,25 @@ MZ_DEV Smem carve(float* base) {
 }
 size_t smem_bytes(int ldx) { return sizeof(float) * (size_t)(2 * R * LDA + R * LDH + 2 * R * LDO + R + R * ldx); }
 
-// two heads that read the same input: first layers -> a[0], a[1]; second layers -> oa [R][ldoa], ob [R][ldob]
+// second layers of two heads whose first-layer activations sit in a[0] / a[1] -> oa [R][ldoa], ob [R][ldob]
 // (NTA / NTB: bounds of the heads' n tiles; NTB = 0: one head)
 template <int NTA, int NTB>
-MZ_DEV void head_pair_t(const Smem& s, const float* x, int ldx, int K, const int* act, const float* w1a,
-                        const float* b1a, const float* w2a, const float* b2a, int Na, float* oa, int ldoa,
-                        const float* w1b, const float* b1b, const float* w2b, const float* b2b, int Nb, float* ob,
-                        int ldob) {
-  float* a0 = s.a;
-  float* a1 = s.a + R * LDA;
-  first_layer(w1a, b1a, x, ldx, K, act, a0);
-  if (NTB > 0) first_layer(w1b, b1b, x, ldx, K, act, a1);
+MZ_DEV void second_stage(float* a, const float* __restrict__ w2a, const float* __restrict__ b2a, int Na,
+                                          float* oa, int ldoa, const float* __restrict__ w2b,
+                                          const float* __restrict__ b2b, int Nb, float* ob, int ldob) {
+  float* a0 = a;
+  float* a1 = a + R * LDA;
   W2Frag<NTA> fa;
   W2Frag<NTB> fb;
   w2_prefetch<NTA>(fa, w2a, Na, 0);
   if (NTB > 0) w2_prefetch<NTB>(fb, w2b, Nb, 0);
-  __syncthreads();
+  __syncthreads();  // the first layers are complete
   float acc_a[NTA][4], acc_b[NTB > 0 ? NTB : 1][4];
   second_partial<NTA>(fa, w2a, a0, Na, acc_a);
   if (NTB > 0) second_partial<NTB>(fb, w2b, a1, Nb, acc_b);
   __syncthreads();  // every warp is done with the activations: their storage takes the partial sums
-  float* red_a = s.a;
-  float* red_b = s.a + 8 * R * LDR;
+  float* red_a = a;
+  float* red_b = a + 8 * R * LDR;
   store_partial<NTA>(acc_a, Na, red_a);
   if (NTB > 0) store_partial<NTB>(acc_b, Nb, red_b);
   __syncthreads();
@@ -292,20 +292,20 @@ MZ_DEV void head_pair_t(const Smem& s, const float* x, int ldx, int K, const int
   if (NTB > 0) reduce_partials(red_b, b2b, Nb, ob, ldob);
   __syncthreads();
 }
+// two heads that read the same input x [R][ldx] (w1b = nullptr: one head)
 MZ_DEV void head_pair(const Smem& s, const float* x, int ldx, int K, const int* act, const float* w1a, const float* b1a,
                       const float* w2a, const float* b2a, int Na, float* oa, int ldoa, const float* w1b,
                       const float* b1b, const float* w2b, const float* b2b, int Nb, float* ob, int ldob) {
-#define MZ_HP(NTA, NTB) \
-  head_pair_t<NTA, NTB>(s, x, ldx, K, act, w1a, b1a, w2a, b2a, Na, oa, ldoa, w1b, b1b, w2b, b2b, Nb, ob, ldob)
+  first_layer(w1a, b1a, x, ldx, K, act, s.a);
+  if (w1b) first_layer(w1b, b1b, x, ldx, K, act, s.a + R * LDA);
   if (!w1b)
-    MZ_HP(8, 0);
+    second_stage<8, 0>(s.a, w2a, b2a, Na, oa, ldoa, w2b, b2b, Nb, ob, ldob);
   else if (Na <= 32 && Nb <= 32)
-    MZ_HP(4, 4);
+    second_stage<4, 4>(s.a, w2a, b2a, Na, oa, ldoa, w2b, b2b, Nb, ob, ldob);
   else if (Na <= 32)
-    MZ_HP(4, 8);
+    second_stage<4, 8>(s.a, w2a, b2a, Na, oa, ldoa, w2b, b2b, Nb, ob, ldob);
   else
-    MZ_HP(8, 8);
-#undef MZ_HP
+    second_stage<8, 8>(s.a, w2a, b2a, Na, oa, ldoa, w2b, b2b, Nb, ob, ldob);
 }
 
 // prediction (networks.py:151-157) from s.h; writes value [B], logits [B][A]
