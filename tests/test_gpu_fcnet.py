@@ -191,6 +191,43 @@ def test_fc_search_replays_bit_exact_in_oracle():
     assert fs.launches_per_move == (3 if fused else streams * (2 * S + 5))
 
 
+def test_fc_search_tf32x3_replays_bit_exact_in_oracle():
+  """The same move with the float32-accurate tensor-core network (per-launch path, graph + three slices): the tree
+  the engine builds from the kernel's outputs is the oracle's, bit for bit; and its root values stay within the
+  float32 kernels' distance of the CUDA-core float32 network's (the search amplifies nothing here: same visits
+  for nearly every game)."""
+  from model_based_rl_b200.networks import FCSearch
+  g = load("fcnet_atari18")
+  G, A, S = 200, 18, 50
+  cfg = types.SimpleNamespace(num_simulations=S, action_space=A, two_players=False, discount=0.997,
+                              pb_c_base=19652, pb_c_init=1.25, init_value_score=0.0,
+                              known_bounds=[None, None], root_exploration_fraction=0.25)
+  rng = np.random.default_rng(17)
+  obs = rng.random(size=(G, 128)).astype(np.float32)
+  noise = rng.dirichlet([0.25] * A, size=G)
+  u = rng.random(G)
+  temp = np.ones(G)
+  visits = {}
+  for precision in ("tf32x3", "f32"):
+    net = _net_from_golden(g, 128, 18, precision)
+    fs = FCSearch(cfg, net, G, use_graph=True, num_streams=3)
+    assert fs.fused is None
+    fs.enable_record()
+    actions, root_value, child_visits, init_value = fs.search_host(obs, noise, u, temp)
+    ocfg = oracle.make_cfg(S, A, False, 0.997)
+    want = oracle.search(ocfg, fs.root_logits.cpu().numpy(), noise=noise, noise_frac=0.25,
+                         rec_value=fs.record[0].cpu().numpy().T, rec_reward=fs.record[1].cpu().numpy().T,
+                         rec_logits=fs.record[2].cpu().numpy().transpose(1, 0, 2))
+    assert np.array_equal(fs.trace[0].cpu().numpy().T, want["trace_parent"])
+    assert np.array_equal(fs.visits.cpu().numpy(), want["visits"])
+    assert np.array_equal(root_value.numpy(), want["root_value"])
+    visits[precision] = (fs.visits.cpu().numpy().copy(), root_value.numpy().copy())
+  same = (visits["tf32x3"][0] == visits["f32"][0]).all(axis=1)
+  print("games with identical visit counts under both float32 networks: %d / %d" % (same.sum(), G))
+  assert same.mean() >= 0.9
+  assert np.allclose(visits["tf32x3"][1][same], visits["f32"][1][same], rtol=1e-3, atol=1e-3)
+
+
 def _search_cfg(S, A, two_players=False, discount=0.997, known_bounds=(None, None)):
   return types.SimpleNamespace(
       num_simulations=S, action_space=A, two_players=two_players, discount=discount, pb_c_base=19652,
