@@ -195,7 +195,10 @@ typedef struct mz_fc_weights { /* device pointers, float32.  First layers (*_w1)
   int32_t obs_dim, num_actions, value_bins, reward_bins;
   int32_t value_min, reward_min;    /* support = [min, min + bins - 1]  config.py:12-19 */
   int32_t no_target_transform;      /* config.no_target_transform   config.py:31 */
-  int32_t reserved;
+  int32_t no_support;               /* config.no_support (config.py:95; networks.py:135-136, 153, 161): value_bins =
+                                       reward_bins = 1 and the heads' raw outputs are the scalars.  The float32 /
+                                       tf32x3 kernels take it; the bf16 kernels and mz_fc_search return
+                                       MZ_ERR_UNSUPPORTED. */
   const float *rep_w1, *rep_b1, *rep_w2, *rep_b2;  /* representation_head  networks.py:55-67 */
   const float *dyn_w1, *dyn_b1, *dyn_w2, *dyn_b2;  /* transition_head      networks.py:70-80 */
   const float *rew_w1, *rew_b1, *rew_w2, *rew_b2;  /* reward_head          networks.py:83-93 */

@@ -41,7 +41,7 @@ class FcWeights(C.Structure):
             "pol_w1", "pol_b1", "pol_w2", "pol_b2", "ln_w", "ln_b"]
   _fields_ = [("obs_dim", C.c_int32), ("num_actions", C.c_int32), ("value_bins", C.c_int32),
               ("reward_bins", C.c_int32), ("value_min", C.c_int32), ("reward_min", C.c_int32),
-              ("no_target_transform", C.c_int32), ("reserved", C.c_int32)] + \
+              ("no_target_transform", C.c_int32), ("no_support", C.c_int32)] + \
              [(n, C.c_void_p) for n in _names]
 
 

@@ -652,7 +652,7 @@ int32_t mz_fc_tc_tail_floats(void) { return TAIL_FLOATS; }
 int mz_fc_tc_pack(const mz_fc_weights* w, void* packed, float* tail, void* stream) {
   if (!w || !packed || !tail) return MZ_ERR_BAD_ARG;
   if (w->num_actions < 1 || w->num_actions > 32 || w->value_bins < 1 || w->value_bins > 32 ||
-      w->reward_bins < 1 || w->reward_bins > 32)
+      w->reward_bins < 1 || w->reward_bins > 32 || w->no_support)
     return MZ_ERR_UNSUPPORTED;
   fc_tc_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(*w, k1_for(w->num_actions), 0, (uint8_t*)packed, tail);
   MZ_LAUNCH_CHECK();
@@ -666,7 +666,7 @@ int mz_fc_recurrent_tc(const mz_fc_weights* w, const void* packed, const float* 
   if (!w || !packed || !tail || batch < 1 || !hidden_in || !actions || !hidden_out || !value ||
       !reward || !logits)
     return MZ_ERR_BAD_ARG;
-  if (w->num_actions < 1 || w->num_actions > 32 || w->value_bins > 32 || w->reward_bins > 32)
+  if (w->num_actions < 1 || w->num_actions > 32 || w->value_bins > 32 || w->reward_bins > 32 || w->no_support)
     return MZ_ERR_UNSUPPORTED;
   TcParams p;
   p.chunks = (const uint8_t*)packed;
@@ -709,7 +709,7 @@ int64_t mz_fc_tc_initial_packed_bytes(int32_t obs_dim) {
 
 int mz_fc_tc_pack_initial(const mz_fc_weights* w, void* packed, float* tail, void* stream) {
   if (!w || !packed || !tail) return MZ_ERR_BAD_ARG;
-  if (w->num_actions < 1 || w->num_actions > 32 || w->value_bins < 1 || w->value_bins > 32)
+  if (w->num_actions < 1 || w->num_actions > 32 || w->value_bins < 1 || w->value_bins > 32 || w->no_support)
     return MZ_ERR_UNSUPPORTED;
   if (tc_smem_bytes(k1_obs(w->obs_dim), 2) > kTcMaxSmem) return MZ_ERR_UNSUPPORTED;
   fc_tc_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(*w, k1_obs(w->obs_dim), 4, (uint8_t*)packed, tail);
@@ -721,7 +721,7 @@ int mz_fc_initial_tc(const mz_fc_weights* w, const void* packed, const float* ta
                      const float* obs, float* hidden_out, int64_t out_row_stride, float* value,
                      float* logits, void* stream) {
   if (!w || !packed || !tail || batch < 1 || !obs || !hidden_out || !value || !logits) return MZ_ERR_BAD_ARG;
-  if (w->num_actions < 1 || w->num_actions > 32 || w->value_bins > 32) return MZ_ERR_UNSUPPORTED;
+  if (w->num_actions < 1 || w->num_actions > 32 || w->value_bins > 32 || w->no_support) return MZ_ERR_UNSUPPORTED;
   TcParams p;
   p.chunks = (const uint8_t*)packed;
   p.tail = tail;

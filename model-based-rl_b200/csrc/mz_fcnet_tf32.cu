@@ -319,7 +319,8 @@ MZ_DEV void prediction(const mz_fc_weights& w, const Smem& s, int row0, int batc
   for (int r = warp; r < R; r += kWarps) {
     const int b = row0 + r;
     if (b >= batch) continue;
-    const float v = mz_support_to_scalar_warp(o0 + r * LDO, w.value_bins, w.value_min, w.no_target_transform, lane);
+    const float v = w.no_support ? o0[r * LDO]  // networks.py:153: the raw output of a one-unit head
+                                 : mz_support_to_scalar_warp(o0 + r * LDO, w.value_bins, w.value_min, w.no_target_transform, lane);
     if (lane == 0) value[b] = v;
     for (int a = lane; a < w.num_actions; a += 32) logits[(size_t)b * w.num_actions + a] = o1[r * LDO + a];
   }
@@ -348,7 +349,8 @@ fc_recurrent_tf32x3_kernel(mz_fc_weights w, int batch, const float* __restrict__
   for (int r = warp; r < R; r += kWarps) {
     const int b = row0 + r;
     if (b >= batch) continue;
-    const float rv = mz_support_to_scalar_warp(s.o + r * LDO, w.reward_bins, w.reward_min, w.no_target_transform, lane);
+    const float rv = w.no_support ? s.o[r * LDO]  // networks.py:161
+                                  : mz_support_to_scalar_warp(s.o + r * LDO, w.reward_bins, w.reward_min, w.no_target_transform, lane);
     if (lane == 0) reward[b] = rv;
   }
   __syncthreads();
@@ -388,6 +390,7 @@ int check_weights(const mz_fc_weights* w, bool need_rep) {
   if (w->num_actions < 1 || w->num_actions > 64 || w->value_bins < 1 || w->value_bins > 64 || w->reward_bins < 1 ||
       w->reward_bins > 64)
     return MZ_ERR_UNSUPPORTED;
+  if (w->no_support && (w->value_bins != 1 || w->reward_bins != 1)) return MZ_ERR_BAD_ARG;
   if (!w->dyn_w1 || !w->rew_w1 || !w->val_w1 || !w->pol_w1 || !w->ln_w || !w->ln_b) return MZ_ERR_BAD_ARG;
   if (need_rep && (!w->rep_w1 || !w->rep_w2 || w->obs_dim < 1)) return MZ_ERR_BAD_ARG;
   return MZ_OK;

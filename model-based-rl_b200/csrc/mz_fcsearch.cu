@@ -672,6 +672,12 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
   auto canon = [&](int c) { return cl == 2 ? (c < 4 ? 4 * rank + c : 8 + 4 * rank + (c - 4)) : 4 * rank + c; };
   int* const err = p.error_flag;
 
+  if (p.timeline && blockIdx.x == 0 && threadIdx.x == 64) {  // diagnostics: kernel entry (cycles, ns)
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.timeline[27] = clock64();
+    p.timeline[29] = (long long)ns;
+  }
   const FsLayout L = fs_layout(k1, STAGES, cl, A, S, SPARSE);
   uint8_t* sA1 = smem + L.a1;
   uint8_t* sW = smem + L.w;
@@ -1144,6 +1150,12 @@ __global__ void __maxnreg__(152) fc_search_kernel(FsParams p) {
 
   __syncthreads();
   cluster_sync_all();  // no CTA leaves while a peer may still address its shared memory
+  if (p.timeline && blockIdx.x == 0 && threadIdx.x == 64) {  // diagnostics: kernel exit
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.timeline[28] = clock64();
+    p.timeline[30] = (long long)ns;
+  }
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
@@ -1308,7 +1320,7 @@ int mz_fc_search(const mz_fc_search_args* a, void* stream) {
   const mz_fc_weights* w = a->weights;
   if (a->num_games < 1 || a->num_simulations < 1) return MZ_ERR_BAD_ARG;
   if (w->num_actions < 1 || w->num_actions > 32 || w->value_bins > 32 || w->reward_bins > 32 ||
-      a->num_simulations > 253)
+      a->num_simulations > 253 || w->no_support)
     return MZ_ERR_UNSUPPORTED;
   if (a->node_bytes != mz_fc_search_node_bytes(w->num_actions) ||
       a->game_bytes < mz_fc_search_game_bytes(a->num_simulations, w->num_actions))

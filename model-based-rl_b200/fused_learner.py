@@ -54,7 +54,8 @@ class FusedFCNetwork(object):
 
   def __init__(self, input_dim, action_space, device, config):
     if getattr(config, 'no_support', False):
-      raise NotImplementedError("no_support networks are not on the B200 path")
+      raise NotImplementedError("the fused learner kernels cover the support heads; train --no_support networks with "
+                                "learners.Learner (FCNetworkTrain + scalar_unroll_loss)")
     self.device = _lib.normalize_device(device)
     self.lib = _lib.load()
     self.input_dim, self.action_space = int(input_dim), int(action_space)

@@ -53,15 +53,14 @@ class FCNetworkTrain(nn.Module):
 
   def __init__(self, input_dim, action_space, device, config):
     super().__init__()
-    if getattr(config, 'no_support', False):
-      raise NotImplementedError("no_support networks are not on the B200 path")
     self.action_space = int(action_space)
     vmin, vmax = [int(v) for v in config.value_support]
     rmin, rmax = [int(v) for v in config.reward_support]
+    no_support = bool(getattr(config, 'no_support', False))  # networks.py:135-136: one-unit scalar heads
     self.representation_head = _Head(input_dim, HIDDEN, 'out')
-    self.value_head = _Head(HIDDEN, vmax - vmin + 1, 'value')
+    self.value_head = _Head(HIDDEN, 1 if no_support else vmax - vmin + 1, 'value')
     self.policy_head = _Head(HIDDEN, self.action_space, 'policy')
-    self.reward_head = _Head(HIDDEN + self.action_space, rmax - rmin + 1, 'reward')
+    self.reward_head = _Head(HIDDEN + self.action_space, 1 if no_support else rmax - rmin + 1, 'reward')
     self.transition_head = _Head(HIDDEN + self.action_space, HIDDEN, 'out')
     self.LN = nn.LayerNorm([HIDDEN], elementwise_affine=True)
     self.device = torch.device(device)
@@ -178,6 +177,36 @@ def unroll_loss(config, values, rewards, policies, t_values, t_rewards, t_polici
                           loss_cfg(config))
 
 
+def scalar_unroll_loss(config, values, rewards, policies, t_values, t_rewards, t_policies, is_weights):
+  """The loss half of Learner.update_weights for `--no_support` networks (learners.py:182-213 with utils.py:61-70):
+  the value / reward heads emit one scalar, compared with the (h-transformed unless no_target_transform) targets by
+  `--scalar_loss` MSE or Huber (SmoothL1), the policy by cross entropy; importance weights in float64, the 1/K
+  gradient scale of learners.py:213 inside.  Same signature and results layout as `unroll_loss`; plain torch
+  (this configuration is outside the benchmarked ones -- the fused CUDA loss covers the support heads)."""
+  v, r, p = [t if torch.is_tensor(t) else torch.stack(t, 0) for t in (values, rewards, policies)]
+  K = r.shape[0]
+  with torch.no_grad():
+    new_errors = v[0].squeeze(-1) - t_values[:, 0]  # learners.py:182-183: no inverse transform
+    if not getattr(config, 'no_target_transform', False):  # config.py:51-54
+      h = lambda x: torch.sign(x) * (torch.sqrt(torch.abs(x) + 1) - 1) + 0.001 * x
+      t_values, t_rewards = h(t_values), h(t_rewards)
+  kind = getattr(config, 'scalar_loss', 'MSE')
+  if kind == 'MSE':
+    scalar = torch.nn.MSELoss(reduction='none')
+  elif kind == 'Huber':
+    scalar = torch.nn.SmoothL1Loss(reduction='none')
+  else:
+    raise NotImplementedError(kind)
+  value_loss = sum(scalar(v[i].squeeze(-1), t_values[:, i]) for i in range(K + 1))
+  reward_loss = sum(scalar(r[i - 1].squeeze(-1), t_rewards[:, i]) for i in range(1, K + 1)) if K else torch.zeros_like(value_loss)
+  policy_loss = sum((-t_policies[:, i] * F.log_softmax(p[i], dim=1)).sum(1) for i in range(K + 1))
+  losses = torch.stack([(is_weights * reward_loss).mean(), (is_weights * value_loss).mean(),
+                        (is_weights * policy_loss).mean()])
+  if losses.requires_grad:
+    losses.register_hook(lambda grad: grad * (1.0 / max(K, 1)))
+  return losses, new_errors
+
+
 # ------------------------------------------------------------------------------------------------
 # optimisers / schedules (utils.py:72-128)
 # ------------------------------------------------------------------------------------------------
@@ -280,7 +309,7 @@ class Learner(object):
       _lib.require_cuda()
       if self.device.type != 'cuda':
         raise RuntimeError("the B200 learner only runs on CUDA devices, got %s" % self.device)
-      loss_fn = unroll_loss
+      loss_fn = scalar_unroll_loss if getattr(config, 'no_support', False) else unroll_loss
     self.loss_fn = loss_fn
     self.replay_buffer = replay_buffer
     self.search_network = search_network

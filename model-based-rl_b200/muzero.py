@@ -111,7 +111,8 @@ class MuZeroNetwork(object):
   def __init__(self, input_channels, action_space, device, config):
     _lib.require_cuda()
     if getattr(config, 'no_support', False):
-      raise NotImplementedError("no_support networks are not on the B200 path")
+      raise NotImplementedError("no_support is implemented for the FCNetwork family (networks.FCNetwork, "
+                                "learners.FCNetworkTrain), not for the conv network")
     self.lib = _lib.load()
     self.device = _lib.normalize_device(device)
     self.input_channels = int(input_channels)

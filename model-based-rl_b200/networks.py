@@ -51,17 +51,21 @@ class FCNetwork(object):
     _lib.require_cuda()
     if precision not in ('bf16', 'f32', 'tf32x3'):
       raise ValueError("precision must be 'bf16', 'f32' or 'tf32x3'")
+    # --no_support (config.py:95; networks.py:135-136, 153, 161): one-unit value / reward heads, their raw outputs
+    # are the scalars.  The float32-accurate kernels evaluate it; the bf16 kernels (and with them the persistent
+    # search kernel) are built around the support heads, so the default precision becomes 'tf32x3' here.
+    self.no_support = bool(getattr(config, 'no_support', False))
+    if self.no_support and precision == 'bf16':
+      precision = 'tf32x3'
     self.precision = precision
-    if getattr(config, 'no_support', False):
-      raise NotImplementedError("no_support networks are not on the B200 path")
     self.lib = _lib.load()
     self.device = _lib.normalize_device(device)
     self.input_dim = int(input_dim)
     self.action_space = int(action_space)
     self.value_min, self.value_max = [int(v) for v in config.value_support]
     self.reward_min, self.reward_max = [int(v) for v in config.reward_support]
-    self.value_bins = self.value_max - self.value_min + 1
-    self.reward_bins = self.reward_max - self.reward_min + 1
+    self.value_bins = 1 if self.no_support else self.value_max - self.value_min + 1
+    self.reward_bins = 1 if self.no_support else self.reward_max - self.reward_min + 1
     self.no_target_transform = bool(getattr(config, 'no_target_transform', False))
     self._state = None    # reference-layout float32 tensors (device)
     self._packed = None   # kernel-layout tensors, kept alive for the struct
@@ -102,7 +106,7 @@ class FCNetwork(object):
         fields[name] = t.data_ptr()
       self.weights = _lib.FcWeights(self.input_dim, self.action_space, self.value_bins,
                                     self.reward_bins, self.value_min, self.reward_min,
-                                    int(self.no_target_transform), 0,
+                                    int(self.no_target_transform), int(self.no_support),
                                     *[fields[n] for n in _lib.FcWeights._names])
       self._tc_packed = self._tc_tail = None
       self._tc_init_packed = self._tc_init_tail = None

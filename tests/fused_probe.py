@@ -93,7 +93,25 @@ def timing(G, S=50, A=18, D=128, moves=20):
       fs.use_graph = False
       fs.run()
       torch.cuda.synchronize()
+      k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      import ctypes as C
+      from model_based_rl_b200 import _lib
+      plan = fs.fused.plan(fs, fs.use_noise, fs.noise_frac, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+      names_ = [fn.__name__ for fn, _ in plan]
+      for fn, args in plan:
+        if fn.__name__ == "mz_fc_search":
+          k0.record()
+        fn(*args)
+        if fn.__name__ == "mz_fc_search":
+          k1.record()
+      torch.cuda.synchronize()
       tl = fs.fused.timeline.cpu().numpy().astype(np.int64)
+      t0 = tl[0]
+      print("   launches of a move: %s" % names_)
+      print("   mz_fc_search by CUDA events %.1f us; block 0: entry -> exit %d cycles = %.1f us by globaltimer (%.0f MHz), "
+            "entry -> set-up done %d cycles, last stamp -> exit %d cycles" % (
+                k0.elapsed_time(k1) * 1e3, t0[28] - t0[27], (t0[30] - t0[29]) / 1e3,
+                (t0[28] - t0[27]) / max(1, (t0[30] - t0[29])) * 1e3, t0[13] - t0[27], t0[28] - tl[-1, 15]))
       base = tl[:, 0:1]
       names = {1: "descent", 2: "a1 sent", 3: "a1 ready", 4: "dyn d2", 5: "dyn out", 6: "a3 ready", 7: "pred d2",
                8: "pred out"}

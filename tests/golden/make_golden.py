@@ -503,6 +503,33 @@ def gen_fcnet(rng):
     print("fcnet", name, "params", sum(p.numel() for p in net.parameters()))
 
 
+def gen_fcnet_nosupport():
+  """FCNetwork with `--no_support` (config.py:95; networks.py:135-136, 153, 161): one-unit value / reward heads whose
+  raw outputs are the scalars.  Own generator so that the other fixtures keep their draws."""
+  rng = np.random.default_rng(20261018)
+  torch.manual_seed(4321)
+  obs_dim, A, B = 8, 4, 48
+  cfg = make_config(action_space=A, no_support=True)
+  net = ref_networks.FCNetwork(obs_dim, A, torch.device("cpu"), cfg)
+  with torch.no_grad():
+    net.LN.weight.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, size=50).astype(np.float32)))
+    net.LN.bias.copy_(torch.from_numpy(rng.normal(0, 0.1, size=50).astype(np.float32)))
+  net.eval()
+  obs = torch.from_numpy(rng.normal(size=(B, obs_dim)).astype(np.float32))
+  actions = [int(a) for a in rng.integers(0, A, size=B)]
+  with torch.inference_mode():
+    init = net.initial_inference(obs)
+    rec = net.recurrent_inference(init.hidden_state, actions)
+  assert init.value.shape == (B, 1) and rec.reward.shape == (B, 1)
+  save = {"w_" + k: v.numpy() for k, v in net.state_dict().items()}
+  np.savez_compressed(
+      os.path.join(HERE, "fcnet_nosupport.npz"), obs=obs.numpy(), actions=np.array(actions, np.int32),
+      init_value=init.value.numpy(), init_logits=init.policy_logits.numpy(), init_hidden=init.hidden_state.numpy(),
+      rec_value=rec.value.numpy(), rec_reward=rec.reward.numpy(), rec_logits=rec.policy_logits.numpy(),
+      rec_hidden=rec.hidden_state.numpy(), **save)
+  print("fcnet no_support params", sum(p.numel() for p in net.parameters()))
+
+
 def gen_muzero():
   """MuZeroNetwork (networks.py:393-554) in eval mode on weights drawn by
   oracle.muzero_ref.seeded_state_dict (23 M parameters are not committed, only the seed)."""
@@ -673,22 +700,26 @@ def reference_update_weights(net, cfg, optimizer, batch, clip_grad):
     target_values = torch.from_numpy(target_values)
     target_rewards = torch.from_numpy(target_rewards)
     is_weights = torch.from_numpy(is_weights)
-    init_value = cfg.inverse_value_transform(value)
+    init_value = cfg.inverse_value_transform(value) if not cfg.no_support else value  # learners.py:182
     new_errors = (init_value.squeeze() - target_values[:, 0]).cpu().numpy()
     if not cfg.no_target_transform:
       target_values = cfg.scalar_transform(target_values)
       target_rewards = cfg.scalar_transform(target_rewards)
-    target_values = cfg.value_phi(target_values)
-    target_rewards = cfg.reward_phi(target_rewards)
+    if not cfg.no_support:  # learners.py:190-192
+      target_values = cfg.value_phi(target_values)
+      target_rewards = cfg.reward_phi(target_rewards)
+  policy_ce = ce
+  if cfg.no_support:  # utils.py:61-70: the scalar heads' loss
+    ce = {"MSE": torch.nn.MSELoss(reduction='none'), "Huber": torch.nn.SmoothL1Loss(reduction='none')}[cfg.scalar_loss]
   reward_loss = 0
   value_loss = ce(value.squeeze(), target_values[:, 0])
-  policy_loss = ce(policy_logits.squeeze(), target_policies[:, 0])
+  policy_loss = policy_ce(policy_logits.squeeze(), target_policies[:, 0])
   for i, action in enumerate(zip(*actions), 1):
     value, reward, policy_logits, hidden_state = net.recurrent_inference(hidden_state, action)
     hidden_state.register_hook(lambda grad: grad * 0.5)
     reward_loss += ce(reward.squeeze(), target_rewards[:, i])
     value_loss += ce(value.squeeze(), target_values[:, i])
-    policy_loss += ce(policy_logits.squeeze(), target_policies[:, i])
+    policy_loss += policy_ce(policy_logits.squeeze(), target_policies[:, i])
   reward_loss = (is_weights * reward_loss).mean()
   value_loss = (is_weights * value_loss).mean()
   policy_loss = (is_weights * policy_loss).mean()
@@ -703,13 +734,23 @@ def reference_update_weights(net, cfg, optimizer, batch, clip_grad):
   return (reward_loss.item(), value_loss.item(), policy_loss.item()), new_errors, grads
 
 
-def gen_learner():
+# --no_support learners (config.py:95-96; utils.py:61-70): name: (..., scalar_loss)
+LEARNER_NOSUPPORT_CASES = {
+    "nosupport_mse": (8, 4, 24, 5, "AdamW", 0, False, "MSE"),
+    "nosupport_huber": (9, 9, 16, 3, "RMSprop", 5, True, "Huber"),
+}
+
+
+def gen_learner(cases=None):
   """Two consecutive Learner.update_weights steps per case; optimisers as utils.get_optimizer
   (utils.py:72-83) with the reference's default hyper-parameters (config.py:183-188)."""
-  for name, (obs_dim, A, B, K, opt_name, clip, no_tt) in LEARNER_CASES.items():
-    rng = np.random.default_rng({"breakout": 1, "ttt": 2, "lunar_raw": 3}[name])
+  for name, spec in (LEARNER_CASES if cases is None else cases).items():
+    obs_dim, A, B, K, opt_name, clip, no_tt = spec[:7]
+    scalar_loss = spec[7] if len(spec) > 7 else None
+    rng = np.random.default_rng({"breakout": 1, "ttt": 2, "lunar_raw": 3, "nosupport_mse": 4, "nosupport_huber": 5}[name])
     torch.manual_seed(4321)
-    cfg = make_config(action_space=A, num_unroll_steps=K, batch_size=B, no_target_transform=no_tt)
+    cfg = make_config(action_space=A, num_unroll_steps=K, batch_size=B, no_target_transform=no_tt,
+                      **({} if scalar_loss is None else dict(no_support=True, scalar_loss=scalar_loss)))
     net = ref_networks.FCNetwork(obs_dim, A, torch.device("cpu"), cfg)
     with torch.no_grad():
       net.LN.weight.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, size=50).astype(np.float32)))
@@ -726,6 +767,8 @@ def gen_learner():
     save.update(obs_dim=np.int32(obs_dim), action_space=np.int32(A), batch=np.int32(B), K=np.int32(K),
                 optimizer=np.array(opt_name), clip_grad=np.int32(clip), no_target_transform=np.int32(no_tt),
                 lr=np.float64(lr), momentum=np.float64(mom), weight_decay=np.float64(wd))
+    if scalar_loss is not None:
+      save.update(no_support=np.int32(1), scalar_loss=np.array(scalar_loss))
     for step in range(2):
       obs = rng.normal(size=(B, obs_dim)).astype(np.float32)
       actions = [[int(a) for a in rng.integers(0, A, size=K)] for _ in range(B)]
@@ -774,8 +817,14 @@ if __name__ == "__main__":
   if len(sys.argv) > 1 and sys.argv[1] == "clip":
     gen_replay_clip()
     sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == "fcnet_nosupport":
+    gen_fcnet_nosupport()
+    sys.exit(0)
   if len(sys.argv) > 1 and sys.argv[1] == "learner":
     gen_learner()
+    sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == "learner_nosupport":
+    gen_learner(LEARNER_NOSUPPORT_CASES)
     sys.exit(0)
   rng = np.random.default_rng(20261017)
   gen_search(rng)
@@ -788,4 +837,6 @@ if __name__ == "__main__":
   gen_learner()
   gen_replay_clip()
   gen_muzero_wide()
+  gen_fcnet_nosupport()
+  gen_learner(LEARNER_NOSUPPORT_CASES)
   print("python", sys.version.split()[0], "numpy", np.__version__, "torch", torch.__version__)

@@ -51,6 +51,61 @@ def test_fc_f32_matches_torch_reference(name, obs_dim, A, precision):
   assert np.array_equal(sd["LN.weight"].numpy(), g["w_LN.weight"])
 
 
+@pytest.mark.parametrize("precision", ["f32", "tf32x3", "bf16"])
+def test_fc_no_support_matches_torch_reference(precision):
+  """`--no_support` networks (config.py:95; networks.py:135-136, 153, 161): one-unit value / reward heads whose raw
+  outputs are the scalars, against outputs of the reference's FCNetwork(no_support=True).  Asking for the default
+  bf16 precision gives the float32-accurate tensor-core kernels (the bf16 kernels are built around the support heads
+  and refuse such weights)."""
+  from model_based_rl_b200.networks import FCNetwork, FCSearch
+  g = load("fcnet_nosupport")
+  cfg = types.SimpleNamespace(value_support=[-15, 15], reward_support=[-15, 15], no_support=True,
+                              no_target_transform=False)
+  net = FCNetwork(8, 4, "cuda", cfg, precision=precision)
+  assert net.precision == ("tf32x3" if precision == "bf16" else precision)
+  net.load_weights({k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("w_")})
+  init = net.initial_inference(torch.from_numpy(g["obs"]).cuda())
+  rec = net.recurrent_inference(torch.from_numpy(g["init_hidden"]).cuda(), g["actions"].tolist())
+  torch.cuda.synchronize()
+  for got, want in ((init.hidden_state, "init_hidden"), (init.policy_logits, "init_logits"), (init.value, "init_value"),
+                    (rec.hidden_state, "rec_hidden"), (rec.policy_logits, "rec_logits"), (rec.value, "rec_value"),
+                    (rec.reward, "rec_reward")):
+    assert got.shape == g[want].shape
+    assert np.allclose(got.cpu().numpy(), g[want], rtol=RTOL, atol=ATOL), want
+  # and a search on it: per-launch path, tree bit-exact against the oracle's replay of the recorded outputs
+  G, A, S = 96, 4, 20
+  scfg = types.SimpleNamespace(num_simulations=S, action_space=A, two_players=False, discount=0.997,
+                               pb_c_base=19652, pb_c_init=1.25, init_value_score=0.0, known_bounds=[None, None],
+                               root_exploration_fraction=0.25)
+  rng = np.random.default_rng(3)
+  noise, u = rng.dirichlet([0.25] * A, size=G), rng.random(G)
+  fs = FCSearch(scfg, net, G, use_graph=True, num_streams=2)
+  assert fs.fused is None
+  fs.enable_record()
+  actions, root_value, child_visits, init_value = fs.search_host(rng.normal(size=(G, 8)).astype(np.float32), noise, u,
+                                                                 np.ones(G))
+  want = oracle.search(oracle.make_cfg(S, A, False, 0.997), fs.root_logits.cpu().numpy(), noise=noise, noise_frac=0.25,
+                       rec_value=fs.record[0].cpu().numpy().T, rec_reward=fs.record[1].cpu().numpy().T,
+                       rec_logits=fs.record[2].cpu().numpy().transpose(1, 0, 2))
+  assert np.array_equal(fs.visits.cpu().numpy(), want["visits"])
+  assert np.array_equal(root_value.numpy(), want["root_value"])
+
+
+def test_bf16_kernels_refuse_no_support_weights():
+  """The C ABI of the bf16 kernels answers MZ_ERR_UNSUPPORTED for a weights struct with no_support set."""
+  from model_based_rl_b200 import _lib
+  from model_based_rl_b200.networks import FCNetwork
+  cfg = types.SimpleNamespace(value_support=[-15, 15], reward_support=[-15, 15], no_support=True,
+                              no_target_transform=False)
+  g = load("fcnet_nosupport")
+  net = FCNetwork(8, 4, "cuda", cfg)
+  net.load_weights({k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("w_")})
+  buf = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+  tail = torch.zeros(512, dtype=torch.float32, device="cuda")
+  rc = net.lib.mz_fc_tc_pack(net.weights, _lib.ptr(buf), _lib.ptr(tail), _lib.current_stream())
+  assert rc == -2  # MZ_ERR_UNSUPPORTED
+
+
 @pytest.mark.parametrize("name,obs_dim,A", [("atari18", 128, 18), ("ttt", 9, 9)])
 @pytest.mark.parametrize("batch", [1, 31, 129, 1000])
 def test_fc_tf32x3_matches_f32_kernel(name, obs_dim, A, batch):

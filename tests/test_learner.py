@@ -109,6 +109,23 @@ def test_product_network_unroll_matches_reference_golden(case, batched):
   _check_against_golden(g, learner, net, tol=1e-6)
 
 
+@pytest.mark.parametrize("case", ["nosupport_mse", "nosupport_huber"])
+@pytest.mark.parametrize("batched", [True, False])
+def test_no_support_learner_matches_reference_golden(case, batched):
+  """`--no_support` training (config.py:95-96; utils.py:61-70; learners.py:182, 190): one-unit value / reward heads,
+  MSE or Huber against the scalar targets.  The product's FCNetworkTrain + scalar_unroll_loss through Learner
+  reproduce two steps of the reference's FCNetwork(no_support=True) around the restated update_weights body."""
+  from model_based_rl_b200 import learners
+  g = helpers.load("learner_" + case)
+  cfg = _config(g)
+  cfg.no_support, cfg.scalar_loss = True, str(g["scalar_loss"])
+  net = learners.FCNetworkTrain(int(g["obs_dim"]), int(g["action_space"]), "cpu", cfg)
+  assert net.value_head.value.weight.shape == (1, 512) and net.reward_head.reward.weight.shape == (1, 512)
+  net.load_weights(_weights(g))
+  learner = learners.Learner(cfg, net, loss_fn=learners.scalar_unroll_loss, batched_heads=batched)
+  _check_against_golden(g, learner, net, tol=1e-6)
+
+
 def test_product_train_network_has_reference_keys_and_outputs():
   """FCNetworkTrain (torch module of the product) == the oracle network on the golden weights."""
   from model_based_rl_b200 import learners
@@ -337,6 +354,46 @@ def test_gpu_learner_two_steps_match_reference_golden(case):
       np.testing.assert_allclose(_sub(v.detach().cpu()).numpy(), g["s%d_w_%s" % (step, k)], rtol=0, atol=2e-5,
                                  err_msg="step %d %s" % (step, k))
   assert learner.log_losses()[1] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["nosupport_mse", "nosupport_huber"])
+def test_gpu_no_support_learner_and_weight_handoff(case):
+  """`--no_support` on the device: Learner picks the scalar loss by itself, two steps against the reference's golden,
+  then the weight hand-off into the search kernels' FCNetwork (which takes the float32-accurate tensor-core kernels
+  for such networks): its value / reward are the train network's raw head outputs."""
+  from model_based_rl_b200 import learners, networks
+  torch.backends.cuda.matmul.allow_tf32 = False
+  g = helpers.load("learner_" + case)
+  cfg = _config(g)
+  cfg.no_support, cfg.scalar_loss = True, str(g["scalar_loss"])
+  D, A = int(g["obs_dim"]), int(g["action_space"])
+  net = learners.FCNetworkTrain(D, A, "cuda", cfg)
+  net.load_weights(_weights(g))
+  search_net = networks.FCNetwork(D, A, "cuda", cfg)
+  assert search_net.precision == "tf32x3"
+  learner = learners.Learner(cfg, net, search_network=search_net)
+  assert learner.loss_fn is learners.scalar_unroll_loss
+  for step in range(2):
+    losses = learner.update_weights(_batch(g, step))
+    np.testing.assert_allclose(losses.cpu().numpy(), g["s%d_losses" % step], rtol=1e-4)
+    np.testing.assert_allclose(learner.last_errors.cpu().numpy(), g["s%d_new_errors" % step], rtol=0, atol=1e-4)
+    for k, v in net.state_dict().items():
+      np.testing.assert_allclose(_sub(v.detach().cpu()).numpy(), g["s%d_w_%s" % (step, k)], rtol=0, atol=2e-5,
+                                 err_msg="step %d %s" % (step, k))
+  learner.send_weights()
+  obs = torch.from_numpy(g["s0_obs"]).cuda()
+  acts = torch.from_numpy(g["s0_actions"][:, 0].astype(np.int64)).cuda()
+  with torch.no_grad():
+    t0 = net.initial_inference(obs)
+    t1 = net.recurrent_inference(t0.hidden_state, acts)
+  s0 = search_net.initial_inference(obs)
+  s1 = search_net.recurrent_inference(t0.hidden_state, acts.to(torch.int32))
+  torch.cuda.synchronize()
+  for a, b in ((t0.value, s0.value), (t0.policy_logits, s0.policy_logits), (t1.value, s1.value), (t1.reward, s1.reward),
+               (t1.hidden_state, s1.hidden_state)):
+    assert a.shape == b.shape
+    assert torch.allclose(a, b, rtol=1e-4, atol=2e-5), (a - b).abs().max().item()
 
 
 @pytest.mark.gpu
