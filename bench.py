@@ -51,8 +51,9 @@ def parse():
   p.add_argument("--no-graph", action="store_true")
   p.add_argument("--streams", type=int, default=4,
                  help="game slices run on separate CUDA streams inside the move graph")
-  p.add_argument("--precision", choices=["bf16", "f32"], default="bf16",
-                 help="network kernel: bf16 tcgen05 tensor cores (default) or float32 CUDA cores")
+  p.add_argument("--precision", choices=["bf16", "f32", "tf32x3"], default="bf16",
+                 help="network kernel: bf16 tcgen05 tensor cores (default), float32 CUDA cores, or float32 accuracy on "
+                      "the tensor cores (three TF32 products per multiply)")
   p.add_argument("--wide-step-max-games", type=int, default=None,
                  help="diagnostics: mz_tree_set_wide_step_max_games (trees with <= 16 actions)")
   p.add_argument("--no-conv", action="store_true", help="skip the C5 MuZeroNetwork section")
@@ -503,7 +504,8 @@ def run_b200(args):
     fc_flops = gl * FC_FLOPS_PER_EXPANSION(A)
     tree_t, fc_t = kern["tree_step_us"] * 1e-6, kern["fc_recurrent_us"] * 1e-6
     tree_name = "tree_step_w32_kernel"
-    fc_name = "fc_recurrent_tc_kernel" if args.precision == "bf16" else "fc_recurrent_f32_kernel"
+    fc_name = {"bf16": "fc_recurrent_tc_kernel", "f32": "fc_recurrent_f32_kernel",
+               "tf32x3": "fc_recurrent_tf32x3_kernel"}[args.precision]
     roof_tree = {"kernel": tree_name, "bound": "hbm", "achieved": tree_bytes / tree_t / 1e9,
                  "peak": peaks["hbm_gbs"], "unit": "GB/s",
                  "traffic": ncu_traffic(tree_name, gl, A, S),
@@ -538,7 +540,8 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 (tree) / %s (network)" % ("bf16 tcgen05, f32 accumulate" if args.precision == "bf16" else "f32"),
+        "dtype": "f64 (tree) / %s (network)" % {"bf16": "bf16 tcgen05, f32 accumulate", "f32": "f32",
+                                                 "tf32x3": "tf32 x 3 mma.sync, f32 accumulate"}[args.precision],
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": fs.h2d_blob_bytes(),
                 "inputs": "pinned host blob, one copy per direction: uint8 observations (normalised on the device), "
