@@ -959,6 +959,33 @@ def bench_selfplay(args, torch, dev, cpu_expansions_per_s=None):
     out[name] = {"ms_per_move": dt * 1e3, "moves_per_s": 1.0 / dt, "expansions_per_s": G * S / dt,
                  "experiences_per_s": G / dt, "games_finished": actor.games_played, "replay_size": rb.size()}
     del actor, rb, fs
+  # two actors of G games each taking turns on the GPU (the reference runs several Ray actors beside each other):
+  # one actor's search runs on the device while the host does the other's environment step / append / staging
+  from model_based_rl_b200.selfplay import PipelinedActors
+  rb = PrioritizedReplay(cfg, device=dev, window_positions=int(200_000 * 1.3) + 6 * G * 515)
+  actors = []
+  for k in range(2):
+    env = SyntheticRam(G, A, D, episode_length=600, seed=1 + k)
+    actors.append(DeviceActor(cfg, env, rb, FCSearch(cfg, net, G)))
+    env.elapsed[:] = np.arange(G) % 600  # (after the actor's reset) chunk commits spread over the moves
+  pipe = PipelinedActors(actors)
+  for _ in range(3):
+    pipe.play_round()
+  torch.cuda.synchronize()
+  rounds = 30
+  t0 = time.perf_counter()
+  for _ in range(rounds):
+    pipe.play_round()
+  torch.cuda.synchronize()
+  dt = (time.perf_counter() - t0) / rounds
+  pipe.drain()
+  out["pipelined_two_actors"] = {
+      "actors": 2, "games_per_actor": G, "ms_per_round": dt * 1e3, "ms_per_actor_move": dt * 1e3 / 2,
+      "expansions_per_s": 2 * G * S / dt, "experiences_per_s": 2 * G / dt, "replay_size": rb.size(),
+      "games_finished": sum(a.games_played for a in actors),
+      "note": "PipelinedActors: the same DeviceActor moves, each actor's next search enqueued before the other's host "
+              "work starts"}
+  del pipe, actors, rb
   out["speedup_vs_list_path"] = out["list_path"]["ms_per_move"] / out["device"]["ms_per_move"]
   if cpu_expansions_per_s:
     out["cpu_baseline"] = {"value": cpu_expansions_per_s / S, "unit": "game-moves/s", "kind": "port",

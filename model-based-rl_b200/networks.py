@@ -675,7 +675,7 @@ class FCSearch(object):
 
   @_lib.on_device
   def search_host(self, obs, noise=None, uniforms=None, temperature=None, legal=None, to_play=None,
-                  dirichlet_alpha=None):
+                  dirichlet_alpha=None, wait=True):
     """The per-move body of Actor.play_game (actors.py:131-153) for G games.
 
     Inputs are HOST arrays (numpy or CPU tensors): obs [G, input_dim] float32 -- or uint8, in which
@@ -688,6 +688,8 @@ class FCSearch(object):
     initial-inference value [G] f32 (the priority seed `error = root.value() - value`,
     actors.py:147).  Host->device and device->host copies are part of the call.  With `dirichlet_alpha` set and no
     `noise` buffer the root noise is drawn on the device instead (`draw_noise`).
+    wait=False: the call returns once everything is enqueued; `search_result()` waits for the move and returns the
+    outputs (the host side of another actor's move then runs under this search: selfplay.PipelinedActors).
     """
     h = self._pinned()
     def stage(name, src, dst):
@@ -719,7 +721,18 @@ class FCSearch(object):
       self.draw_noise(dirichlet_alpha)
     self.run()
     self._out_host.copy_(self._out_dev, non_blocking=True)  # the four outputs share one blob
+    if not wait:
+      if getattr(self, '_done', None) is None:
+        self._done = torch.cuda.Event()
+      self._done.record()
+      return None
     torch.cuda.current_stream().synchronize()
+    return h['actions'], h['root_value'], h['child_visits'], h['init_value']
+
+  def search_result(self):
+    """The outputs of the move a `search_host(..., wait=False)` call enqueued (pinned host tensors)."""
+    self._done.synchronize()
+    h = self._pinned()
     return h['actions'], h['root_value'], h['child_visits'], h['init_value']
 
   def set_obs_normalization(self, obs_min, obs_range):

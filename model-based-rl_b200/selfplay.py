@@ -206,6 +206,12 @@ class DeviceActor(object):
     self.results = collections.Counter()
 
   def play_move(self, noise=None, uniforms=None):
+    self.begin_move(noise, uniforms)
+    return self.finish_move()
+
+  def begin_move(self, noise=None, uniforms=None):
+    """First half of a move: the roots' inputs go to the device and the search is enqueued; returns without
+    waiting for it (`finish_move` does).  Between the two, the host is free for another actor's move."""
     cfg, env, G, A, fs = self.config, self.env, self.G, self.A, self.search
     legal = env.legal_mask()
     # Node.add_exploration_noise (mcts.py:57-61): one Dirichlet draw per root over its children -- on the device
@@ -223,8 +229,16 @@ class DeviceActor(object):
       uniforms = np.random.random(G)
     obs_in = self.obs if self.obs_u8 else np.ascontiguousarray(self.obs, dtype=np.float32)
     kw = {} if alpha is None else {"dirichlet_alpha": alpha}
-    actions, root_value, child_visits, init_value = fs.search_host(obs_in, noise, uniforms, self.temperature, legal=legal,
-                                                                   to_play=self.to_play, **kw)
+    if hasattr(fs, "search_result"):  # enqueue only: the host goes on while the device searches
+      kw["wait"] = False
+    self._pending = fs.search_host(obs_in, noise, uniforms, self.temperature, legal=legal, to_play=self.to_play, **kw)
+
+  def finish_move(self):
+    """Second half: waits for the search, steps the environments, appends the move's record to the replay window on
+    the device and commits the chunks that ended (actors.py:147-169)."""
+    cfg, env, G, fs = self.config, self.env, self.G, self.search
+    out, self._pending = self._pending, None
+    actions, root_value, child_visits, init_value = fs.search_result() if out is None else out
     actions = actions.numpy().copy()
     errors = root_value.numpy() - init_value.numpy().astype(np.float64)  # actors.py:147
     next_obs, reward, done, result = env.step(actions)
@@ -284,3 +298,63 @@ class DeviceActor(object):
     if len(fin):
       self.obs[fin] = env.reset(fin)
     return actions, root_value, child_visits, errors, done
+
+
+class PipelinedActors(object):
+  """Several `DeviceActor`s (each with its own environments and search engine, one shared replay buffer) taking turns
+  on one GPU, the way the reference runs several Ray actors beside each other (train.py: `--num_actors`): while one
+  actor's search runs on the device, the host steps the environments, appends the records and stages the next roots
+  of the others.  A move costs max(device search, host work) instead of their sum.  Results -- every record, chunk
+  commit and random draw -- are those of calling the actors' `play_move` in turn (tests/test_selfplay.py)."""
+
+  def __init__(self, actors, copy_outputs=False):
+    """copy_outputs: root values / child-visit distributions of a move are views of the engine's pinned output
+    blob, which the actor's NEXT search (enqueued before `play_round` returns) overwrites when it completes; pass
+    True to get private copies."""
+    self.actors = list(actors)
+    self.copy_outputs = bool(copy_outputs)
+    self._primed = False
+    self._staged, self._events, self._flip = None, None, 0
+
+  def play_round(self):
+    """One move of every actor; returns their `play_move` results in order."""
+    if not self._primed:
+      for a in self.actors:
+        a.begin_move()
+      self._primed = True
+    out = []
+    for a in self.actors:
+      # the replay buffer's pinned staging areas are shared: the previous actor's append / commit copies (enqueued
+      # behind THIS actor's search, so a few microseconds after it) must have read them before they are rewritten
+      if self._staged is not None:
+        self._staged.synchronize()
+      res = a.finish_move()
+      if self._events is None:
+        self._events = [torch.cuda.Event() for _ in range(2)]
+      self._staged = self._events[self._flip]
+      self._flip ^= 1
+      self._staged.record()
+      if self.copy_outputs:
+        res = (res[0], res[1].clone(), res[2].clone(), res[3], res[4])
+      out.append(res)
+      a.begin_move()  # its next search runs under the other actors' host work
+    return out
+
+  def drain(self):
+    """Finishes the moves in flight (call before reading the actors' counters for the last time)."""
+    out = []
+    if self._primed:
+      for a in self.actors:
+        if self._staged is not None:
+          self._staged.synchronize()
+        out.append(a.finish_move())
+        self._staged = self._events[self._flip] if self._events else None
+        if self._staged is not None:
+          self._flip ^= 1
+          self._staged.record()
+      self._primed = False
+    return out
+
+  @property
+  def experiences_collected(self):
+    return sum(a.experiences_collected for a in self.actors)

@@ -364,3 +364,70 @@ def test_device_actor_with_device_noise_runs_the_whole_loop():
   (obs, acts, t_r, t_v, t_p, vs, rs), idx, isw = rb.sample_batch_device(True)
   torch.cuda.synchronize()
   assert obs.shape == (64, D) and torch.isfinite(t_v).all() and float(isw.max()) == 1.0
+
+
+@pytest.mark.gpu
+def test_pipelined_actors_equal_actors_taking_turns():
+  """PipelinedActors (every actor's next search is enqueued before the next actor's host work starts) against the same
+  two DeviceActors called in turn: same actions, root values and errors move by move, same replay buffer at the end
+  (size, sum-tree total, a sampled batch) -- the overlap changes when things run, not what is computed."""
+  import random
+  from model_based_rl_b200.environments import SyntheticRam
+  from model_based_rl_b200.networks import FCNetwork, FCSearch, random_state_dict
+  from model_based_rl_b200.replay_buffer import PrioritizedReplay
+  from model_based_rl_b200.selfplay import DeviceActor, PipelinedActors
+  import torch
+  A, G, S, D = 6, 192, 8, 128
+  cfg = types.SimpleNamespace(
+      num_simulations=S, action_space=A, two_players=False, discount=0.997, pb_c_base=19652, pb_c_init=1.25,
+      init_value_score=0.0, known_bounds=[None, None], root_dirichlet_alpha=0.25, root_exploration_fraction=0.25,
+      num_unroll_steps=3, td_steps=4, max_history_length=20, max_steps=10 ** 9, value_support=[-15, 15],
+      reward_support=[-15, 15], no_support=False, no_target_transform=False, batch_size=64,
+      beta_increment_per_sampling=0.001, epsilon=0.01, alpha=1.0, beta=0.5, obs_space=(D,), window_size=4000,
+      window_step=None, seed=None, clip_rewards=True)
+  net = FCNetwork(D, A, "cuda", cfg)
+  net.load_weights(random_state_dict(D, A, seed=3))
+
+  def build():
+    np.random.seed(11)
+    random.seed(11)
+    rb = PrioritizedReplay(cfg, window_positions=80000)
+    actors = []
+    for k in range(2):
+      env = SyntheticRam(G, A, D, episode_length=29 + 4 * k, seed=5 + k)
+      actors.append(DeviceActor(cfg, env, rb, FCSearch(cfg, net, G)))
+      env.elapsed[:] = np.arange(G) % (29 + 4 * k)  # games end on different moves
+    return rb, actors
+
+  moves = 45
+  rb_a, turn = build()
+  log_a = []
+  for _ in range(moves + 1):  # one more: the pipelined run ends with a move of every actor in flight
+    for a in turn:
+      r = a.play_move()
+      log_a.append((r[0].copy(), r[1].numpy().copy(), r[3].copy(), r[4].copy()))
+  rb_b, piped = build()
+  pipe = PipelinedActors(piped, copy_outputs=True)
+  log_b = []
+  for _ in range(moves):
+    for r in pipe.play_round():
+      log_b.append((r[0].copy(), r[1].numpy().copy(), r[3].copy(), r[4].copy()))
+  for r in pipe.drain():  # the moves in flight
+    log_b.append((r[0].copy(), r[1].numpy().copy(), r[3].copy(), r[4].copy()))
+  assert len(log_a) == len(log_b) == 2 * (moves + 1)
+  for x, y in zip(log_a, log_b):
+    for u, v in zip(x, y):
+      assert np.array_equal(u, v)
+  torch.cuda.synchronize()
+  assert rb_a.size() == rb_b.size() and rb_a.size() > 2000
+  assert rb_a.index.total_priority == rb_b.index.total_priority
+  assert sum(a.games_played for a in turn) == sum(a.games_played for a in piped)
+  random.seed(1), np.random.seed(1)
+  sa = rb_a.sample_batch()
+  random.seed(1), np.random.seed(1)
+  sb = rb_b.sample_batch()
+  assert sa[1] == sb[1] and np.array_equal(sa[2], sb[2])
+  for u, v in zip(sa[0][2], sb[0][2]):
+    assert np.array_equal(u, v)
+  assert sa[0][1] == sb[0][1]
+  assert np.array_equal(sa[0][0], sb[0][0]), "observation rows differ: %s" % np.nonzero((sa[0][0] != sb[0][0]).any(1))[0]
