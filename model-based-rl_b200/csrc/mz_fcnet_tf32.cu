@@ -1,7 +1,7 @@
 // FCNetwork inference at float32 accuracy ON THE TENSOR CORES: every product of the eight Linear layers runs as
-// three TF32 tensor-core instructions on split operands (x = x_hi + x_lo, w = w_hi + w_lo with both halves
-// representable in TF32; x*w ~= x_lo*w_hi + x_hi*w_lo + x_hi*w_hi, float32 accumulation: the dropped x_lo*w_lo
-// term is 2^-22 of the product, i.e. float32 rounding level).  Same interface, same weights struct and the same
+// three TF32 tensor-core instructions on split operands (x = x_hi + x_lo, w = w_hi + w_lo, see split_tf32;
+// x*w ~= x_lo*w_hi + x_hi*w_lo + x_hi*w_hi, float32 accumulation: what is dropped is below 2^-20 of the product,
+// the level of the float32 kernels' own summation-order differences).  Same interface, same weights struct and the same
 // results within float32 rounding as the CUDA-core kernels of mz_fcnet_f32.cu (tests/test_gpu_fcnet.py: 1e-4
 // against the reference's torch module like the float32 kernel, 2e-5 against the float32 kernel itself).
 //
